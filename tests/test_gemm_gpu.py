@@ -1,0 +1,155 @@
+"""GPU parity of the tcgen05 GEMM (vitb_gemm) against a plain torch fp32 matmul on the same
+bf16-rounded operands.  Tolerances: fp32 outputs differ only by accumulation order (rel-L2 1e-5);
+bf16 outputs add one rounding (2^-9 relative per element -> rel-L2 4e-3)."""
+import pytest
+import torch
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(shape, seed, scale=1.0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(shape, generator=g, device="cuda") * scale).to(torch.bfloat16)
+
+
+def _operands(M, N, K, a_mn, b_mn, seed=0):
+    A = _mk((K, M) if a_mn else (M, K), seed)
+    B = _mk((K, N) if b_mn else (N, K), seed + 1)
+    Af = A.float().t() if a_mn else A.float()
+    Bf = B.float().t() if b_mn else B.float()
+    return A, B, Af @ Bf.t()
+
+
+@pytest.mark.parametrize("a_mn", [False, True])
+@pytest.mark.parametrize("b_mn", [False, True])
+@pytest.mark.parametrize("shape", [(128, 256, 64), (256, 512, 256), (384, 128, 192), (592, 104, 72),
+                                   (1000, 776, 328)])
+def test_gemm_majors_fp32_out(shape, a_mn, b_mn):
+    import vitb200
+    M, N, K = shape
+    A, B, ref = _operands(M, N, K, a_mn, b_mn)
+    out = vitb200.ops.gemm(A, B, a_mn=a_mn, b_mn=b_mn, out_dtype=torch.float32)
+    torch.cuda.synchronize()
+    assert rel_l2(out, ref) < 1e-5, (shape, a_mn, b_mn, rel_l2(out, ref))
+
+
+def test_gemm_c2_qkv_bias_bf16():
+    import vitb200
+    M, N, K = 25216, 2304, 768
+    A, B, ref = _operands(M, N, K, False, False, seed=3)
+    bias = torch.randn(N, device="cuda")
+    out = vitb200.ops.gemm(A, B, bias=bias)
+    torch.cuda.synchronize()
+    assert out.dtype == torch.bfloat16
+    assert rel_l2(out, ref + bias) < 4e-3
+
+
+def test_gemm_gelu_epilogue_and_preact():
+    import vitb200
+    M, N, K = 640, 3072, 768
+    A, B, ref = _operands(M, N, K, False, False, seed=5)
+    A = (A.float() * 0.05).to(torch.bfloat16)
+    ref = A.float() @ B.float().t()
+    bias = torch.randn(N, device="cuda") * 0.1
+    z = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    out = vitb200.ops.gemm(A, B, bias=bias, epilogue=vitb200.ops.EPI_GELU, d2=z)
+    torch.cuda.synchronize()
+    zr = ref + bias
+    assert rel_l2(z, zr) < 4e-3
+    assert rel_l2(out, torch.nn.functional.gelu(zr)) < 4e-3
+
+
+def test_gemm_gelu_bwd_epilogue():
+    import vitb200
+    M, N, K = 512, 1024, 256
+    A, B, ref = _operands(M, N, K, False, True, seed=7)
+    z = _mk((M, N), 11)
+    out = vitb200.ops.gemm(A, B, b_mn=True, epilogue=vitb200.ops.EPI_GELU_BWD, aux=z)
+    torch.cuda.synchronize()
+    zf = z.float().requires_grad_(True)
+    torch.nn.functional.gelu(zf).backward(ref)
+    assert rel_l2(out, zf.grad) < 4e-3
+
+
+@pytest.mark.parametrize("r_dtype", [torch.float32, torch.bfloat16])
+def test_gemm_bias_residual_fp32_out(r_dtype):
+    import vitb200
+    M, N, K = 788, 768, 3072
+    A, B, ref = _operands(M, N, K, False, False, seed=9)
+    bias = torch.randn(N, device="cuda")
+    res = torch.randn(M, N, device="cuda").to(r_dtype)
+    out = vitb200.ops.gemm(A, B, bias=bias, residual=res, out_dtype=torch.float32)
+    torch.cuda.synchronize()
+    assert rel_l2(out, ref + bias + res.float()) < 1e-5
+
+
+def test_gemm_patch_embed_row_remap():
+    import vitb200
+    Bsz, npatch, D, K = 4, 196, 768, 768
+    A, B, ref = _operands(Bsz * npatch, D, K, False, False, seed=13)
+    bias = torch.randn(D, device="cuda")
+    pos = torch.randn(npatch + 1, D, device="cuda")
+    out = torch.zeros(Bsz * (npatch + 1), D, device="cuda")
+    vitb200.ops.gemm(A, B, bias=bias, residual=pos, row_remap_group=npatch, out=out)
+    torch.cuda.synchronize()
+    exp = torch.zeros(Bsz, npatch + 1, D, device="cuda")
+    exp[:, 1:] = (ref + bias).view(Bsz, npatch, D) + pos[1:]
+    assert rel_l2(out, exp.view(-1, D)) < 1e-5
+    assert out.view(Bsz, npatch + 1, D)[:, 0].abs().max() == 0  # class-token rows untouched
+
+
+@pytest.mark.parametrize("split_k", [0, 1, 3, 8])
+def test_gemm_wgrad_accumulate_split_k(split_k):
+    import vitb200
+    T, Nout, Kin = 5000, 768, 384
+    dY = _mk((T, Nout), 21, 0.1)
+    X = _mk((T, Kin), 22)
+    ref = dY.float().t() @ X.float()
+    acc = torch.ones(Nout, Kin, device="cuda")
+    vitb200.ops.gemm(dY, X, a_mn=True, b_mn=True, out=acc, accumulate=True, split_k=split_k)
+    torch.cuda.synchronize()
+    assert rel_l2(acc, ref + 1.0) < 2e-5
+
+
+def test_gemm_three_segments_bf16x3():
+    """fp32 parity mode: A = Ah + Al, B = Bh + Bl (bf16 pieces); AhBh + AhBl + AlBh ~ fp32 product."""
+    import vitb200
+    M, N, K = 300, 520, 200
+    g = torch.Generator(device="cuda").manual_seed(31)
+    A = torch.randn(M, K, generator=g, device="cuda")
+    B = torch.randn(N, K, generator=g, device="cuda")
+    Ah = A.to(torch.bfloat16); Al = (A - Ah.float()).to(torch.bfloat16)
+    Bh = B.to(torch.bfloat16); Bl = (B - Bh.float()).to(torch.bfloat16)
+    out = vitb200.ops.gemm([Ah, Ah, Al], [Bh, Bl, Bh], out_dtype=torch.float32)
+    torch.cuda.synchronize()
+    ref = A.double() @ B.double().t()
+    assert rel_l2(out, ref) < 2e-5
+
+
+def test_gemm_lora_segment_small_k():
+    import vitb200
+    M, N, K, r = 394, 768, 768, 8
+    A, B, ref = _operands(M, N, K, False, False, seed=41)
+    t = _mk((M, r), 42)
+    Bl = _mk((N, r), 43)
+    out = vitb200.ops.gemm([A, t], [B, Bl], out_dtype=torch.float32)
+    torch.cuda.synchronize()
+    assert rel_l2(out, ref + t.float() @ Bl.float().t()) < 1e-5
+
+
+def test_gemm_row_bias():
+    import vitb200
+    Bsz, Ntok, N, K = 6, 50, 512, 512
+    A, B, ref = _operands(Bsz * Ntok, N, K, False, False, seed=51)
+    rb = torch.randn(Bsz, N, device="cuda")
+    out = vitb200.ops.gemm(A, B, row_bias=rb, row_bias_group=Ntok, out_dtype=torch.float32)
+    torch.cuda.synchronize()
+    assert rel_l2(out, ref + rb.repeat_interleave(Ntok, 0)) < 1e-5
+
+
+def test_gemm_rejects_cpu_tensors():
+    import vitb200
+    with pytest.raises(RuntimeError):
+        vitb200.ops.gemm(torch.zeros(8, 8, dtype=torch.bfloat16), torch.zeros(8, 8, dtype=torch.bfloat16))

@@ -1,0 +1,89 @@
+"""In-tree build of libvitb200.so (sm_100a only) with nvcc.
+
+The shared library lands next to this file so that it travels with the repo snapshot to the GPU
+box; it is git-ignored.  `python vit-of-pytorch_b200/build.py` or `__graft_entry__.build()`.
+"""
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")
+LIB = os.path.join(HERE, "libvitb200.so")
+INCLUDE = os.path.join(os.path.dirname(HERE), "include")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-std=c++17", "-lineinfo",
+    "-Xcompiler", "-fPIC",
+    "--expt-relaxed-constexpr",
+    "-Xptxas", "-v",
+]
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found (set NVCC)")
+
+
+def sources():
+    return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def _digest(path, flags):
+    h = hashlib.sha256()
+    h.update(" ".join(flags).encode())
+    for dep in [path] + [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cuh", ".h"))] + [
+        os.path.join(INCLUDE, "vitb200.h")
+    ]:
+        with open(dep, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
+def _compile_one(nvcc, src, verbose):
+    path = os.path.join(CSRC, src)
+    obj = os.path.join(OBJ, src[:-3] + ".o")
+    stamp = obj + ".sha"
+    dig = _digest(path, NVCC_FLAGS)
+    if os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == dig:
+        return obj, ""
+    cmd = [nvcc] + NVCC_FLAGS + ["-I", INCLUDE, "-c", path, "-o", obj]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, res.stdout, res.stderr))
+    with open(stamp, "w") as fh:
+        fh.write(dig)
+    return obj, res.stderr if verbose else ""
+
+
+def build(verbose=False, force=False):
+    nvcc = _nvcc()
+    os.makedirs(OBJ, exist_ok=True)
+    if force:
+        for f in os.listdir(OBJ):
+            os.remove(os.path.join(OBJ, f))
+    srcs = sources()
+    with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
+        results = list(ex.map(lambda s: _compile_one(nvcc, s, verbose), srcs))
+    objs = [r[0] for r in results]
+    for _, log in results:
+        if log:
+            sys.stderr.write(log)
+    newest = max(os.path.getmtime(o) for o in objs)
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < newest:
+        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("link failed:\n%s\n%s" % (res.stdout, res.stderr))
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(verbose="-v" in sys.argv, force="-f" in sys.argv))

@@ -1,0 +1,137 @@
+// vitb_api.cu — library-level entry points of the C ABI: version, error text, device gate,
+// TMA descriptor encoding.  See include/vitb200.h.
+#include <mutex>
+#include <stdarg.h>
+#include <string.h>
+
+#include "../../include/vitb200.h"
+#include "vitb_common.cuh"
+
+namespace {
+std::mutex g_err_mu;
+char g_err[1024] = "";
+std::mutex g_dev_mu;
+int g_dev_ok[64];      // 0 unknown, 1 ok, -1 unsupported
+int g_dev_sms[64];
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled g_encode = nullptr;
+
+int load_encode() {
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  if (g_encode) return VITB_OK;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || fn == nullptr) {
+    vitb_set_error("cuTensorMapEncodeTiled entry point unavailable: %s", cudaGetErrorString(e));
+    return VITB_ERR_CUDA;
+  }
+  g_encode = reinterpret_cast<PFN_encodeTiled>(fn);
+  return VITB_OK;
+}
+}  // namespace
+
+void vitb_set_error(const char* fmt, ...) {
+  std::lock_guard<std::mutex> lk(g_err_mu);
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int vitb_check_device() {
+  int dev = 0;
+  VITB_CUDA_CHECK(cudaGetDevice(&dev));
+  VITB_REQUIRE(dev >= 0 && dev < 64, VITB_ERR_BAD_ARG, "device index %d out of range", dev);
+  {
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    if (g_dev_ok[dev] == 1) return VITB_OK;
+  }
+  int major = 0, minor = 0, sms = 0;
+  VITB_CUDA_CHECK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  VITB_CUDA_CHECK(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  VITB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if (major != 10) {
+    vitb_set_error("libvitb200 needs an sm_100a GPU (B200); device %d is sm_%d%d — no fallback path",
+                   dev, major, minor);
+    return VITB_ERR_UNSUPPORTED_ARCH;
+  }
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  g_dev_ok[dev] = 1;
+  g_dev_sms[dev] = sms;
+  return VITB_OK;
+}
+
+int vitb_num_sms() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  return g_dev_sms[dev] > 0 ? g_dev_sms[dev] : 148;
+}
+
+int vitb_make_tmap_nd_bf16(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims,
+                           const uint64_t* strides_bytes, const uint32_t* box) {
+  int st = load_encode();
+  if (st != VITB_OK) return st;
+  VITB_REQUIRE(rank >= 1 && rank <= 5, VITB_ERR_BAD_ARG, "tensor map rank %d", rank);
+  VITB_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15u) == 0, VITB_ERR_BAD_ARG,
+               "TMA base pointer %p not 16-byte aligned", ptr);
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bx[5];
+  cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    VITB_REQUIRE(box[i] >= 1 && box[i] <= 256, VITB_ERR_BAD_ARG, "TMA box[%d]=%u", i, box[i]);
+  }
+  for (int i = 0; i + 1 < rank; ++i) {
+    gstr[i] = strides_bytes[i];
+    VITB_REQUIRE((strides_bytes[i] & 15u) == 0, VITB_ERR_UNSUPPORTED_SHAPE,
+                 "TMA stride[%d]=%llu bytes is not a multiple of 16", i,
+                 (unsigned long long)strides_bytes[i]);
+  }
+  VITB_REQUIRE(box[0] * 2u <= 128u, VITB_ERR_BAD_ARG, "TMA inner box %u exceeds the 128B swizzle span",
+               box[0]);
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank,
+                        const_cast<void*>(ptr), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    vitb_set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu,%llu box %u,%u)",
+                   (int)r, rank, (unsigned long long)dims[0],
+                   (unsigned long long)(rank > 1 ? dims[1] : 0), box[0], rank > 1 ? box[1] : 0);
+    return VITB_ERR_CUDA;
+  }
+  return VITB_OK;
+}
+
+int vitb_make_tmap_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer,
+                           uint64_t outer_stride_bytes, uint32_t box_inner, uint32_t box_outer) {
+  uint64_t dims[2] = {inner, outer};
+  uint64_t str[1] = {outer_stride_bytes};
+  uint32_t box[2] = {box_inner, box_outer};
+  return vitb_make_tmap_nd_bf16(out, ptr, 2, dims, str, box);
+}
+
+extern "C" {
+
+int vitb_version(void) { return VITB200_VERSION; }
+
+int vitb_last_error(char* buf, size_t n) {
+  std::lock_guard<std::mutex> lk(g_err_mu);
+  if (buf && n) {
+    strncpy(buf, g_err, n - 1);
+    buf[n - 1] = 0;
+  }
+  return (int)strlen(g_err);
+}
+
+int vitb_device_check(void) { return vitb_check_device(); }
+
+}  // extern "C"

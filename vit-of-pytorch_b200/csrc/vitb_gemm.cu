@@ -1,0 +1,469 @@
+// vitb_gemm.cu — the dense contraction of the ViT encoder path on sm_100a.
+//
+//   D[M,N] = epilogue( sum_seg A_seg[M,K_seg] * B_seg[N,K_seg]^T )        (contract: vitb200.h)
+//
+// Design (B200-first, not a port of anything in the reference — the reference only calls ATen):
+//   * persistent CTAs (one per SM), static tile scheduler, 256 threads, warp-specialised:
+//       warp 0   : TMA producer (cp.async.bulk.tensor, SWIZZLE_128B) into a 4/6-stage smem ring
+//       warp 1   : one elected thread issues tcgen05.mma (128 x BN x 16, bf16 -> fp32 in TMEM)
+//       warp 2   : TMEM allocator (2 accumulator stages so the epilogue overlaps the next tile)
+//       warps 4-7: epilogue — tcgen05.ld TMEM->registers, transpose through padded smem so that
+//                  every global access of the fused epilogue is row-coalesced
+//   * K-major and MN-major operands are both fed straight from their HBM layout through the UMMA
+//     shared-memory descriptors (no transposition pass for dgrad / wgrad / LinearGeneral weights)
+//   * up to 3 (A,B,K) segments accumulate in the same TMEM tile: LoRA rank-r update, bf16x3 split
+//   * split-K with fp32 red.global accumulation for the weight-gradient shapes (few output tiles)
+//
+// Algorithmic work per launch: 2*M*N*sum(K_seg) FLOP; bytes >= 2*(M*K + N*K) + out.
+#include "../../include/vitb200.h"
+#include "vitb_common.cuh"
+
+namespace {
+
+using namespace vitb;
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kThreads = 256;
+constexpr int kEpiWarp0 = 4;
+constexpr int A_BYTES = BM * BK * 2;                 // 16 KiB
+constexpr int kStagingFloats = 32 * 33;              // per epilogue warp, padded transpose tile
+constexpr int kStagingBytes = 4 * kStagingFloats * 4;
+
+template <int BN>
+struct Cfg {
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + kStagingBytes + 256 /*barriers*/ + 1024 /*align*/;
+};
+
+struct GemmDev {
+  int M, N;
+  int nseg;
+  int kblocks[3];
+  int total_kblocks;
+  int split_k;
+  int m_tiles, n_tiles;
+  int epilogue;
+  void* D;
+  long long ldd;
+  int d_bf16;
+  int accumulate;
+  void* D2;
+  long long ldd2;
+  const float* bias;
+  const float* row_bias;
+  int row_bias_group;
+  int row_remap_group;
+  const void* residual;
+  long long ldr;
+  int r_bf16;
+  const void* aux;
+  long long ldaux;
+};
+
+struct TileCoord {
+  int m_blk, n_blk, g0, g1;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const GemmDev& p, int tile) {
+  TileCoord t;
+  const int split = tile % p.split_k;
+  const int t2 = tile / p.split_k;
+  t.n_blk = t2 % p.n_tiles;
+  t.m_blk = t2 / p.n_tiles;
+  t.g0 = static_cast<int>((static_cast<long long>(split) * p.total_kblocks) / p.split_k);
+  t.g1 = static_cast<int>((static_cast<long long>(split + 1) * p.total_kblocks) / p.split_k);
+  return t;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kThreads, 1)
+vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
+                 const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
+                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+                 const GemmDev p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  float* staging = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES + kStagingBytes);
+  // bars: [0,STAGES) full, [STAGES,2*STAGES) empty, then tmem_full[2], tmem_empty[2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t full0 = smem_u32(bars);
+  const uint32_t empty0 = smem_u32(bars + C::STAGES);
+  const uint32_t tfull0 = smem_u32(bars + 2 * C::STAGES);
+  const uint32_t tempty0 = smem_u32(bars + 2 * C::STAGES + 2);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmB0);
+    if (p.nseg > 1) { tma_prefetch_desc(&tmA1); tma_prefetch_desc(&tmB1); }
+    if (p.nseg > 2) { tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmB2); }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull0 + 8 * s, 1);
+      mbar_init(tempty0 + 8 * s, 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32(tmem_slot), C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = p.m_tiles * p.n_tiles * p.split_k;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile);
+        const int m0 = t.m_blk * BM;
+        const int n0 = t.n_blk * BN;
+        for (int g = t.g0; g < t.g1; ++g) {
+          int seg = 0, kb = g;
+          if (kb >= p.kblocks[0]) { kb -= p.kblocks[0]; seg = 1; }
+          if (seg == 1 && kb >= p.kblocks[1]) { kb -= p.kblocks[1]; seg = 2; }
+          const CUtensorMap* ma = seg == 0 ? &tmA0 : (seg == 1 ? &tmA1 : &tmA2);
+          const CUtensorMap* mb = seg == 0 ? &tmB0 : (seg == 1 ? &tmB1 : &tmB2);
+          mbar_wait(empty0 + 8 * stage, phase ^ 1u);
+          const uint32_t fb = full0 + 8 * stage;
+          mbar_arrive_expect_tx(fb, C::STAGE_BYTES);
+          const uint32_t sA = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t sB = sA + A_BYTES;
+          if constexpr (!A_MN) {
+            tma_load_2d(ma, fb, sA, kb * BK, m0);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BM / 64; ++i) tma_load_2d(ma, fb, sA + i * 8192, m0 + 64 * i, kb * BK);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d(mb, fb, sB, kb * BK, n0);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i) tma_load_2d(mb, fb, sB + i * 8192, n0 + 64 * i, kb * BK);
+          }
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile);
+        mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int g = t.g0; g < t.g1; ++g) {
+          mbar_wait(full0 + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sA = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t sB = sA + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = A_MN ? umma_smem_desc_sw128(sA + k * 2048, BK * 128, 1024)
+                                     : umma_smem_desc_sw128(sA + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? umma_smem_desc_sw128(sB + k * 2048, BK * 128, 1024)
+                                     : umma_smem_desc_sw128(sB + k * 32, 16, 1024);
+            umma_bf16_ss(d_tmem, da, db, idesc, (g > t.g0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty0 + 8 * stage);                    // smem slot free once MMAs retire
+          if (g == t.g1 - 1) umma_commit(tfull0 + 8 * acc);   // accumulator ready for the epilogue
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // =============================== epilogue ===============================
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    float* stg = staging + (warp - kEpiWarp0) * kStagingFloats;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const bool has_gelu = p.epilogue == VITB_EPI_GELU;
+    const bool has_gelu_bwd = p.epilogue == VITB_EPI_GELU_BWD;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      const int n0 = t.n_blk * BN;
+      const int row_base = t.m_blk * BM + q * 32;
+      mbar_wait(tfull0 + 8 * acc, acc_phase);
+      tc_fence_after();
+      // bias-type terms are added exactly once: by the split that owns the first k-block
+      const bool lead_split = (t.g0 == 0);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= p.N) break;
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                               static_cast<uint32_t>(acc * BN + c * 32), r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(r[j]);
+        __syncwarp();
+        if (!p.d_bf16) {
+          // lane == column; each warp instruction touches 128 contiguous bytes of one row
+          const int col = col0 + lane;
+          const bool col_ok = col < p.N;
+          const float bv = (p.bias != nullptr && col_ok && lead_split) ? p.bias[col] : 0.f;
+#pragma unroll 4
+          for (int rr = 0; rr < 32; ++rr) {
+            const int m = row_base + rr;
+            if (m >= p.M) break;
+            if (!col_ok) continue;
+            float v = stg[rr * 33 + lane] + bv;
+            if (p.row_bias != nullptr && lead_split)
+              v += p.row_bias[static_cast<long long>(m / p.row_bias_group) * p.N + col];
+            if (has_gelu) {
+              if (p.D2 != nullptr)
+                reinterpret_cast<__nv_bfloat16*>(p.D2)[static_cast<long long>(m) * p.ldd2 + col] =
+                    __float2bfloat16(v);
+              v = gelu_erf(v);
+            } else if (has_gelu_bwd) {
+              const float z = __bfloat162float(
+                  reinterpret_cast<const __nv_bfloat16*>(p.aux)[static_cast<long long>(m) * p.ldaux + col]);
+              v *= gelu_erf_grad(z);
+            }
+            int om = m, rm = m;
+            if (p.row_remap_group > 0) {
+              om = m + m / p.row_remap_group + 1;
+              rm = m % p.row_remap_group + 1;
+            }
+            if (p.residual != nullptr && lead_split) {
+              const long long ri = static_cast<long long>(rm) * p.ldr + col;
+              v += p.r_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.residual)[ri])
+                            : reinterpret_cast<const float*>(p.residual)[ri];
+            }
+            float* dst = reinterpret_cast<float*>(p.D) + static_cast<long long>(om) * p.ldd + col;
+            if (p.accumulate) atomicAdd(dst, v);
+            else *dst = v;
+          }
+        } else {
+          // bf16 output: lane -> (row parity, column pair); 2 rows x 64 contiguous bytes per instruction
+          const int half = lane >> 4;
+          const int cl = (lane & 15) * 2;
+          const int col = col0 + cl;
+          const bool c0_ok = col < p.N, c1_ok = (col + 1) < p.N;
+          float b0 = 0.f, b1 = 0.f;
+          if (p.bias != nullptr) {
+            if (c0_ok) b0 = p.bias[col];
+            if (c1_ok) b1 = p.bias[col + 1];
+          }
+#pragma unroll 4
+          for (int rr = 0; rr < 32; rr += 2) {
+            const int rl = rr + half;
+            const int m = row_base + rl;
+            if (m >= p.M || !c0_ok) continue;
+            float v0 = stg[rl * 33 + cl] + b0;
+            float v1 = stg[rl * 33 + cl + 1] + b1;
+            if (p.row_bias != nullptr) {
+              const float* rb = p.row_bias + static_cast<long long>(m / p.row_bias_group) * p.N + col;
+              v0 += rb[0];
+              if (c1_ok) v1 += rb[1];
+            }
+            if (has_gelu) {
+              if (p.D2 != nullptr) {
+                __nv_bfloat16* z = reinterpret_cast<__nv_bfloat16*>(p.D2) + static_cast<long long>(m) * p.ldd2 + col;
+                if (c1_ok) *reinterpret_cast<uint32_t*>(z) = pack_bf16x2(v0, v1);
+                else z[0] = __float2bfloat16(v0);
+              }
+              v0 = gelu_erf(v0);
+              v1 = gelu_erf(v1);
+            } else if (has_gelu_bwd) {
+              const __nv_bfloat16* z = reinterpret_cast<const __nv_bfloat16*>(p.aux) + static_cast<long long>(m) * p.ldaux + col;
+              if (c1_ok) {
+                const uint32_t zz = *reinterpret_cast<const uint32_t*>(z);
+                v0 *= gelu_erf_grad(bf16_lo(zz));
+                v1 *= gelu_erf_grad(bf16_hi(zz));
+              } else {
+                v0 *= gelu_erf_grad(__bfloat162float(z[0]));
+              }
+            }
+            int om = m, rm = m;
+            if (p.row_remap_group > 0) {
+              om = m + m / p.row_remap_group + 1;
+              rm = m % p.row_remap_group + 1;
+            }
+            if (p.residual != nullptr) {
+              const long long ri = static_cast<long long>(rm) * p.ldr + col;
+              if (p.r_bf16) {
+                const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + ri;
+                v0 += __bfloat162float(rp[0]);
+                if (c1_ok) v1 += __bfloat162float(rp[1]);
+              } else {
+                const float* rp = reinterpret_cast<const float*>(p.residual) + ri;
+                v0 += rp[0];
+                if (c1_ok) v1 += rp[1];
+              }
+            }
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.D) + static_cast<long long>(om) * p.ldd + col;
+            if (c1_ok) *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(v0, v1);
+            else dst[0] = __float2bfloat16(v0);
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+template <int BN, bool A_MN, bool B_MN>
+int launch(const CUtensorMap* tm, const GemmDev& d, int grid, cudaStream_t stream) {
+  auto kern = vitb_gemm_kernel<BN, A_MN, B_MN>;
+  VITB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg<BN>::SMEM_BYTES));
+  kern<<<grid, kThreads, Cfg<BN>::SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], d);
+  VITB_LAUNCH_CHECK("vitb_gemm_kernel");
+  return VITB_OK;
+}
+
+}  // namespace
+
+extern "C" int vitb_gemm(const vitb_gemm_params* p, void* stream_) {
+  VITB_REQUIRE(p != nullptr, VITB_ERR_BAD_ARG, "vitb_gemm: null params");
+  VITB_REQUIRE(p->struct_bytes == (int)sizeof(vitb_gemm_params), VITB_ERR_BAD_ARG,
+               "vitb_gemm: struct_bytes %d != %d (ABI mismatch)", p->struct_bytes,
+               (int)sizeof(vitb_gemm_params));
+  int st = vitb_check_device();
+  if (st != VITB_OK) return st;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VITB_REQUIRE(p->M >= 0 && p->N >= 0, VITB_ERR_BAD_ARG, "vitb_gemm: negative M/N");
+  if (p->M == 0 || p->N == 0) return VITB_OK;  // empty problem: nothing to launch
+  VITB_REQUIRE(p->num_segments >= 1 && p->num_segments <= 3, VITB_ERR_BAD_ARG,
+               "vitb_gemm: num_segments %d", p->num_segments);
+  VITB_REQUIRE(p->D != nullptr, VITB_ERR_BAD_ARG, "vitb_gemm: D is null");
+  VITB_REQUIRE(p->d_dtype == VITB_F32 || p->d_dtype == VITB_BF16, VITB_ERR_BAD_ARG, "vitb_gemm: d_dtype");
+  VITB_REQUIRE(!(p->accumulate && p->d_dtype != VITB_F32), VITB_ERR_BAD_ARG,
+               "vitb_gemm: accumulate needs an fp32 D");
+  VITB_REQUIRE(!(p->split_k > 1 && !p->accumulate), VITB_ERR_BAD_ARG,
+               "vitb_gemm: split_k > 1 needs accumulate = 1");
+  VITB_REQUIRE(p->epilogue >= 0 && p->epilogue <= 2, VITB_ERR_BAD_ARG, "vitb_gemm: epilogue %d", p->epilogue);
+  VITB_REQUIRE(!(p->epilogue == VITB_EPI_GELU_BWD && p->aux == nullptr), VITB_ERR_BAD_ARG,
+               "vitb_gemm: GELU_BWD needs aux");
+  VITB_REQUIRE(!(p->accumulate && p->epilogue != VITB_EPI_NONE && p->split_k != 1), VITB_ERR_BAD_ARG,
+               "vitb_gemm: a non-linear epilogue cannot be split along K");
+  if (p->d_dtype == VITB_BF16) {
+    VITB_REQUIRE(p->ldd % 2 == 0, VITB_ERR_UNSUPPORTED_SHAPE, "vitb_gemm: bf16 D needs even ldd");
+    VITB_REQUIRE(p->D2 == nullptr || p->ldd2 % 2 == 0, VITB_ERR_UNSUPPORTED_SHAPE, "vitb_gemm: even ldd2");
+    VITB_REQUIRE(p->aux == nullptr || p->ldaux % 2 == 0, VITB_ERR_UNSUPPORTED_SHAPE, "vitb_gemm: even ldaux");
+  }
+  VITB_REQUIRE(p->row_bias == nullptr || p->row_bias_group > 0, VITB_ERR_BAD_ARG,
+               "vitb_gemm: row_bias_group must be > 0");
+
+  GemmDev d{};
+  d.M = p->M;
+  d.N = p->N;
+  d.nseg = p->num_segments;
+  d.total_kblocks = 0;
+  for (int s = 0; s < 3; ++s) d.kblocks[s] = 0;
+  for (int s = 0; s < p->num_segments; ++s) {
+    VITB_REQUIRE(p->K[s] > 0, VITB_ERR_BAD_ARG, "vitb_gemm: K[%d] = %d", s, p->K[s]);
+    VITB_REQUIRE(p->A[s] != nullptr && p->B[s] != nullptr, VITB_ERR_BAD_ARG, "vitb_gemm: null operand %d", s);
+    d.kblocks[s] = (p->K[s] + BK - 1) / BK;
+    d.total_kblocks += d.kblocks[s];
+  }
+  // tile width: 256 unless that pads N more than 128 would
+  const int pad256 = ((p->N + 255) / 256) * 256 - p->N;
+  const int pad128 = ((p->N + 127) / 128) * 128 - p->N;
+  const int BN = (pad256 <= pad128) ? 256 : 128;
+  d.m_tiles = (p->M + BM - 1) / BM;
+  d.n_tiles = (p->N + BN - 1) / BN;
+  const int sms = vitb_num_sms();
+  int split = p->split_k;
+  if (split <= 0) {
+    split = 1;
+    if (p->accumulate && p->epilogue == VITB_EPI_NONE) {
+      const int tiles = d.m_tiles * d.n_tiles;
+      split = sms / (tiles > 0 ? tiles : 1);
+      if (split < 1) split = 1;
+      // keep at least 4 k-blocks per split so the pipeline fill is amortised
+      if (split > d.total_kblocks / 4) split = d.total_kblocks / 4;
+      if (split < 1) split = 1;
+    }
+  }
+  VITB_REQUIRE(split <= d.total_kblocks, VITB_ERR_BAD_ARG, "vitb_gemm: split_k %d > k-blocks %d", split,
+               d.total_kblocks);
+  d.split_k = split;
+  d.epilogue = p->epilogue;
+  d.D = p->D;
+  d.ldd = p->ldd;
+  d.d_bf16 = p->d_dtype == VITB_BF16;
+  d.accumulate = p->accumulate;
+  d.D2 = p->D2;
+  d.ldd2 = p->ldd2;
+  d.bias = p->bias;
+  d.row_bias = p->row_bias;
+  d.row_bias_group = p->row_bias_group;
+  d.row_remap_group = p->row_remap_group;
+  d.residual = p->residual;
+  d.ldr = p->ldr;
+  d.r_bf16 = p->r_dtype == VITB_BF16;
+  d.aux = p->aux;
+  d.ldaux = p->ldaux;
+
+  CUtensorMap tm[6];
+  for (int s = 0; s < 3; ++s) {
+    const int src = s < p->num_segments ? s : 0;
+    const uint64_t K = (uint64_t)p->K[src];
+    if (!p->a_mn_major)
+      st = vitb_make_tmap_2d_bf16(&tm[2 * s], p->A[src], K, (uint64_t)p->M, (uint64_t)p->lda[src] * 2, BK, BM);
+    else
+      st = vitb_make_tmap_2d_bf16(&tm[2 * s], p->A[src], (uint64_t)p->M, K, (uint64_t)p->lda[src] * 2, 64, BK);
+    if (st != VITB_OK) return st;
+    if (!p->b_mn_major)
+      st = vitb_make_tmap_2d_bf16(&tm[2 * s + 1], p->B[src], K, (uint64_t)p->N, (uint64_t)p->ldb[src] * 2, BK, BN);
+    else
+      st = vitb_make_tmap_2d_bf16(&tm[2 * s + 1], p->B[src], (uint64_t)p->N, K, (uint64_t)p->ldb[src] * 2, 64, BK);
+    if (st != VITB_OK) return st;
+  }
+  const long long total_tiles = (long long)d.m_tiles * d.n_tiles * d.split_k;
+  const int grid = (int)(total_tiles < sms ? total_tiles : sms);
+
+#define VITB_DISPATCH(BN_)                                                              \
+  do {                                                                                  \
+    if (!p->a_mn_major && !p->b_mn_major) return launch<BN_, false, false>(tm, d, grid, stream); \
+    if (!p->a_mn_major && p->b_mn_major) return launch<BN_, false, true>(tm, d, grid, stream);   \
+    if (p->a_mn_major && !p->b_mn_major) return launch<BN_, true, false>(tm, d, grid, stream);   \
+    return launch<BN_, true, true>(tm, d, grid, stream);                                \
+  } while (0)
+  if (BN == 256) VITB_DISPATCH(256);
+  VITB_DISPATCH(128);
+#undef VITB_DISPATCH
+}
