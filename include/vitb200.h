@@ -96,6 +96,98 @@ typedef struct vitb_gemm_params {
 
 int vitb_gemm(const vitb_gemm_params* p, void* stream);
 
+/* ---- LayerNorm ----------------------------------------------------------------------------------
+ * nn.LayerNorm(D, eps) — src/model.py:108,114,146 (calls :119,:127,:155); res-vit/model.py:119-130.
+ * x is [rows, D] with row stride x_row_stride (elements); D must be a multiple of 128.
+ * Outputs (each optional, contiguous [rows, D]): y_f32, y_bf16 (GEMM operand), y_bf16_lo (the
+ * x - bf16(x) half for the bf16x3 fp32-parity GEMMs); mean/rstd [rows] are saved for the backward.
+ */
+int vitb_layernorm_fwd(const void* x, int x_dtype, int64_t x_row_stride, int rows, int D,
+                       const float* gamma, const float* beta, float eps, float* y_f32, void* y_bf16,
+                       void* y_bf16_lo, float* mean, float* rstd, void* stream);
+
+/* Backward of the above.  dx = LN'(dy) + dres (dres = gradient arriving on the residual branch,
+ * optional).  dgamma/dbeta/dcolsum [D] are ACCUMULATED (+=); dcolsum = column sums of dx, i.e. the
+ * bias gradient of the Linear whose output (plus residual) fed this LayerNorm. */
+int vitb_layernorm_bwd(const void* dy, int dy_dtype, const float* x, int64_t x_row_stride,
+                       const float* mean, const float* rstd, const float* gamma, int rows, int D,
+                       const float* dres, int64_t dres_row_stride, float* dx_f32,
+                       int64_t dx_row_stride, void* dx_bf16, void* dx_bf16_lo, float* dgamma,
+                       float* dbeta, float* dcolsum, void* stream);
+
+/* ---- attention ----------------------------------------------------------------------------------
+ * softmax(q k^T / sqrt(dh)) v with no mask and no dropout — SelfAttention.forward
+ * src/model.py:90-97, Attention.forward res-vit/model.py:273-293 — and its backward.
+ * Element (b, n, h, d) of a tensor lives at base + b*batch_stride + n*row_stride + h*head_dim + d
+ * (strides in elements), so q/k/v can alias one packed [T, 3D] projection output.
+ *   *_tc  : tcgen05/TMEM kernels, bf16, head_dim 64, Nq == Nk <= 256; gradients dq/dk/dv are bf16.
+ *   *_simt: CUDA-core fp32 math, dtype f32 or bf16, any head_dim, Nk <= 320, Nq != Nk allowed;
+ *           gradients dq/dk/dv are FP32 and dq must be zeroed by the caller (atomic accumulation).
+ * lse is [B, H, Nq] fp32 (log-sum-exp of the scaled scores), written by fwd and read by bwd.
+ */
+typedef struct vitb_attn_params {
+  int32_t struct_bytes;
+  int32_t dtype;
+  int32_t B, H, Nq, Nk, head_dim;
+  int32_t _pad0;
+  const void* q;
+  const void* k;
+  const void* v;
+  void* o;
+  float* lse;
+  int64_t q_batch_stride, q_row_stride;
+  int64_t k_batch_stride, k_row_stride;
+  int64_t v_batch_stride, v_row_stride;
+  int64_t o_batch_stride, o_row_stride;
+  const void* dout;
+  int64_t do_batch_stride, do_row_stride;
+  void* dq;
+  void* dk;
+  void* dv;
+  int64_t dq_batch_stride, dq_row_stride;
+  int64_t dk_batch_stride, dk_row_stride;
+  int64_t dv_batch_stride, dv_row_stride;
+} vitb_attn_params;
+
+int vitb_attn_supported_tc(int head_dim, int Nq, int Nk);
+int vitb_attn_fwd_tc(const vitb_attn_params* p, void* stream);
+int vitb_attn_bwd_tc(const vitb_attn_params* p, void* stream);
+int vitb_attn_fwd_simt(const vitb_attn_params* p, void* stream);
+int vitb_attn_bwd_simt(const vitb_attn_params* p, void* stream);
+
+/* ---- operand preparation / embedding stage ---------------------------------------------------- */
+/* hi = bf16(x); lo = bf16(x - hi) (optional).  Weight shadows and fp32-parity operands. */
+int vitb_cast_split(const float* x, int64_t n, void* hi, void* lo, void* stream);
+/* Patch extraction for the Conv2d(3,D,P,P) patch embedding (src/model.py:179,197;
+ * res-vit/model.py:543,602): img [B,C,H,W] fp32 -> rows (b,py,px) x k (c,ph,pw), K padded to ldk. */
+int vitb_im2col(const float* img, int B, int C, int H, int W, int P, int ldk, void* hi, void* lo,
+                void* stream);
+/* x[b,0,:] = cls + pos[0]  (cls_token.repeat + cat + pos add, src/model.py:203-204,17). */
+int vitb_cls_rows(float* x, int B, int N, int D, const float* cls, const float* pos, void* stream);
+/* Backward of the embedding stage from dx [B,N,D]: dpos [N,D] += sum_b dx; dcls [D] += sum_b dx[:,0];
+ * dbias [D] += sum over patch rows; dpatch [B*(N-1), D] = bf16 patch rows (wgrad operand). */
+int vitb_embed_bwd(const float* dx, int B, int N, int D, float* dpos, float* dcls, float* dbias,
+                   void* dpatch_hi, void* dpatch_lo, void* stream);
+/* out[c] += sum_r x[r,c]  (bias gradients). */
+int vitb_colsum(const void* x, int x_dtype, int rows, int cols, int64_t ld, float* out, void* stream);
+
+/* ---- loss and optimizer ------------------------------------------------------------------------- */
+/* nn.CrossEntropyLoss (mean) — src/train.py:151,22; res-vit/model.py:550,681.
+ * loss[0] = mean_b(lse_b - logits[b,label_b]); dlogits = (softmax - onehot)/B (optional). */
+int vitb_cross_entropy(const float* logits, const int64_t* labels, int B, int C, float* loss,
+                       float* dlogits, void* stream);
+/* torch.optim.SGD(momentum) over a flat buffer (src/train.py:154-158), refreshing the bf16 shadow. */
+int vitb_sgd_momentum(float* p, const float* g, float* m, int64_t n, float lr, float momentum,
+                      float dampening, float weight_decay, int nesterov, int first_step,
+                      void* shadow_hi, void* shadow_lo, void* stream);
+/* torch.optim.AdamW over a flat buffer (res-vit/train.py:272-277); grad_scale_dev (optional device
+ * scalar) carries the clip_grad_norm_ coefficient (res-vit/train.py:65). */
+int vitb_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+               float beta2, float eps, float weight_decay, int step, const float* grad_scale_dev,
+               void* shadow_hi, void* shadow_lo, void* stream);
+int vitb_sumsq(const float* x, int64_t n, float* out, void* stream);
+int vitb_clip_coef(const float* sumsq, float max_norm, float* coef, float* norm_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

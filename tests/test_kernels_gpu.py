@@ -1,0 +1,244 @@
+"""GPU parity of the non-GEMM kernels against plain torch fp32 references of the same op.
+Tolerances are stated per test: fp32 paths 1e-5 rel-L2 (accumulation order only); bf16 outputs 4e-3
+(one bf16 rounding); bf16 attention 1e-2 (P and dS are rounded to bf16 before the second MMA)."""
+import math
+
+import pytest
+import torch
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _randn(shape, seed, scale=1.0, dtype=torch.float32):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(shape, generator=g, device="cuda") * scale).to(dtype)
+
+
+# ---------------------------------------------------------------------------------------------- LN
+@pytest.mark.parametrize("D", [128, 384, 768, 1024, 1280])
+def test_layernorm_fwd(D):
+    import vitb200
+    rows = 1000
+    x = _randn((rows, D), 1, 3.0) + 0.5
+    g, b = _randn((D,), 2), _randn((D,), 3)
+    yf, yh, yl, mean, rstd = vitb200.ops.layernorm_fwd(x, g, b, 1e-5, want_f32=True, want_bf16=True, want_lo=True)
+    ref = torch.nn.functional.layer_norm(x, (D,), g, b, 1e-5)
+    assert rel_l2(yf, ref) < 1e-6
+    assert rel_l2(yh, ref) < 4e-3
+    assert rel_l2(yh.float() + yl.float(), ref) < 2e-5
+    assert rel_l2(mean, x.mean(1)) < 1e-5
+    assert rel_l2(rstd, (x.var(1, unbiased=False) + 1e-5).rsqrt()) < 1e-5
+
+
+def test_layernorm_fwd_strided_rows():
+    import vitb200
+    B, N, D = 16, 197, 768
+    x = _randn((B, N, D), 4)
+    g, b = _randn((D,), 5), _randn((D,), 6)
+    cls = x.view(B, N * D)[:, :D]  # row 0 of every image, stride N*D
+    yf, _, _, _, _ = vitb200.ops.layernorm_fwd(cls, g, b, 1e-5, want_f32=True, want_bf16=False)
+    assert rel_l2(yf, torch.nn.functional.layer_norm(x[:, 0], (D,), g, b, 1e-5)) < 1e-6
+
+
+@pytest.mark.parametrize("D,dy_dtype", [(256, torch.float32), (768, torch.bfloat16), (768, torch.float32),
+                                        (1024, torch.bfloat16), (1280, torch.float32)])
+def test_layernorm_bwd(D, dy_dtype):
+    import vitb200
+    rows = 2500
+    x = (_randn((rows, D), 7, 2.0) + 0.3).requires_grad_(True)
+    g = _randn((D,), 8).requires_grad_(True)
+    b = _randn((D,), 9).requires_grad_(True)
+    dy = _randn((rows, D), 10, 1.0, dy_dtype)
+    dres = _randn((rows, D), 11)
+    y = torch.nn.functional.layer_norm(x, (D,), g, b, 1e-5)
+    y.backward(dy.float())
+    _, _, _, mean, rstd = vitb200.ops.layernorm_fwd(x.detach(), g.detach(), b.detach(), 1e-5, want_bf16=False)
+    dgamma = torch.zeros(D, device="cuda"); dbeta = torch.zeros(D, device="cuda"); dcol = torch.zeros(D, device="cuda")
+    dxf, dxh, dxl = vitb200.ops.layernorm_bwd(dy, x.detach(), mean, rstd, g.detach(), dres=dres, want_f32=True,
+                                              want_bf16=True, want_lo=True, dgamma=dgamma, dbeta=dbeta, dcolsum=dcol)
+    ref_dx = x.grad + dres
+    assert rel_l2(dxf, ref_dx) < 1e-5
+    assert rel_l2(dxh, ref_dx) < 4e-3
+    assert rel_l2(dxh.float() + dxl.float(), ref_dx) < 3e-5
+    assert rel_l2(dgamma, g.grad) < 1e-4
+    assert rel_l2(dbeta, b.grad) < 1e-4
+    assert rel_l2(dcol, ref_dx.sum(0)) < 1e-4
+
+
+# ---------------------------------------------------------------------------------------- attention
+def _attn_ref(q, k, v, H):
+    B, Nq, HD = q.shape
+    dh = HD // H
+    qh = q.float().view(B, Nq, H, dh).permute(0, 2, 1, 3)
+    kh = k.float().view(B, -1, H, dh).permute(0, 2, 1, 3)
+    vh = v.float().view(B, -1, H, dh).permute(0, 2, 1, 3)
+    s = qh @ kh.transpose(-1, -2) / math.sqrt(dh)
+    p = torch.softmax(s, -1)
+    o = (p @ vh).permute(0, 2, 1, 3).reshape(B, Nq, HD)
+    return o, torch.logsumexp(s, -1)
+
+
+@pytest.mark.parametrize("N", [197, 50, 256, 16, 130])
+def test_attn_tc_fwd_bwd_packed_qkv(N):
+    import vitb200
+    B, H, dh = 3, 12, 64
+    D = H * dh
+    qkv = _randn((B, N, 3 * D), 20 + N, 1.0, torch.bfloat16)
+    q, k, v = qkv[:, :, :D], qkv[:, :, D:2 * D], qkv[:, :, 2 * D:]
+    assert vitb200.ops.attn_supported_tc(dh, N, N, torch.bfloat16)
+    o, lse = vitb200.ops.attn_fwd(q, k, v, H)
+    qf, kf, vf = (t.float().detach().requires_grad_(True) for t in (q, k, v))
+    ro, rlse = _attn_ref(qf, kf, vf, H)
+    assert rel_l2(o, ro) < 1e-2
+    assert rel_l2(lse, rlse) < 1e-4
+    do = _randn((B, N, D), 99, 1.0, torch.bfloat16)
+    ro.backward(do.float())
+    dqkv = torch.empty_like(qkv)
+    dq, dk, dv = vitb200.ops.attn_bwd(do, q, k, v, o, lse, H, dq=dqkv[:, :, :D], dk=dqkv[:, :, D:2 * D],
+                                      dv=dqkv[:, :, 2 * D:])
+    torch.cuda.synchronize()
+    assert rel_l2(dv, vf.grad) < 1.5e-2
+    assert rel_l2(dq, qf.grad) < 1.5e-2
+    assert rel_l2(dk, kf.grad) < 1.5e-2
+
+
+def test_attn_tc_c2_size_runs_and_matches_on_a_slice():
+    import vitb200
+    B, N, H, dh = 128, 197, 12, 64
+    D = H * dh
+    qkv = _randn((B, N, 3 * D), 5, 0.5, torch.bfloat16)
+    q, k, v = qkv[:, :, :D], qkv[:, :, D:2 * D], qkv[:, :, 2 * D:]
+    o, lse = vitb200.ops.attn_fwd(q, k, v, H)
+    ro, _ = _attn_ref(q[-2:], k[-2:], v[-2:], H)
+    assert rel_l2(o[-2:], ro) < 1e-2
+
+
+@pytest.mark.parametrize("dtype,dh,N,tol", [(torch.float32, 64, 197, 2e-5), (torch.float32, 80, 257, 2e-5),
+                                            (torch.bfloat16, 80, 257, 1e-2), (torch.float32, 32, 50, 2e-5)])
+def test_attn_simt_fwd_bwd(dtype, dh, N, tol):
+    import vitb200
+    B, H = 2, 4
+    D = H * dh
+    q, k, v = (_randn((B, N, D), s, 1.0, dtype) for s in (1, 2, 3))
+    o, lse = vitb200.ops.attn_fwd(q, k, v, H, use_tc=False)
+    qf, kf, vf = (t.float().detach().requires_grad_(True) for t in (q, k, v))
+    ro, rlse = _attn_ref(qf, kf, vf, H)
+    assert rel_l2(o, ro) < tol
+    assert rel_l2(lse, rlse) < 1e-5
+    do = _randn((B, N, D), 4, 1.0, dtype)
+    ro.backward(do.float())
+    dq, dk, dv = vitb200.ops.attn_bwd(do, q, k, v, o, lse, H, use_tc=False)
+    btol = tol * (4 if dtype == torch.bfloat16 else 2)
+    assert rel_l2(dq, qf.grad) < btol and rel_l2(dk, kf.grad) < btol and rel_l2(dv, vf.grad) < btol
+
+
+def test_attn_simt_asymmetric_queries():
+    import vitb200
+    B, H, dh, Nq, Nk = 2, 4, 64, 77, 197
+    D = H * dh
+    q = _randn((B, Nq, D), 1); k = _randn((B, Nk, D), 2); v = _randn((B, Nk, D), 3)
+    o, _ = vitb200.ops.attn_fwd(q, k, v, H, use_tc=False)
+    ro, _ = _attn_ref(q, k, v, H)
+    assert rel_l2(o, ro) < 2e-5
+
+
+# ---------------------------------------------------------------------------------- elementwise etc.
+def test_cast_split():
+    import vitb200
+    x = _randn((1000, 771), 1)
+    hi, lo = vitb200.ops.cast_split(x, want_lo=True)
+    assert torch.equal(hi, x.to(torch.bfloat16))
+    assert rel_l2(hi.float() + lo.float(), x) < 1e-5
+
+
+@pytest.mark.parametrize("P", [16, 32, 14])
+def test_im2col_matches_conv2d(P):
+    import vitb200
+    B, D = 3, 64
+    img = _randn((B, 3, 224, 224), 2)
+    w = _randn((D, 3, P, P), 3, 0.05)
+    hi, lo = vitb200.ops.im2col(img, P, want_lo=True)
+    K = 3 * P * P
+    cols = hi.float() + lo.float()
+    assert cols.shape[1] % 8 == 0 and cols.shape[1] >= K
+    assert (cols[:, K:] == 0).all()
+    ref = torch.nn.functional.conv2d(img, w, stride=P).permute(0, 2, 3, 1).reshape(-1, D)
+    out = cols[:, :K] @ w.reshape(D, K).t()
+    assert rel_l2(out, ref) < 2e-5
+
+
+def test_cls_rows_and_embed_bwd():
+    import vitb200
+    B, N, D = 5, 50, 256
+    x = torch.zeros(B, N, D, device="cuda")
+    cls, pos = _randn((D,), 1), _randn((N, D), 2)
+    vitb200.ops.cls_rows(x, cls, pos)
+    assert torch.allclose(x[:, 0], (cls + pos[0]).expand(B, D)) and x[:, 1:].abs().max() == 0
+    dx = _randn((B, N, D), 3)
+    dpos = torch.zeros(N, D, device="cuda"); dcls = torch.zeros(D, device="cuda"); dbias = torch.zeros(D, device="cuda")
+    hi, lo = vitb200.ops.embed_bwd(dx, dpos=dpos, dcls=dcls, dbias=dbias, want_lo=True)
+    assert rel_l2(dpos, dx.sum(0)) < 1e-6
+    assert rel_l2(dcls, dx[:, 0].sum(0)) < 1e-6
+    assert rel_l2(dbias, dx[:, 1:].sum((0, 1))) < 1e-5
+    assert rel_l2(hi.float() + lo.float(), dx[:, 1:].reshape(-1, D)) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_colsum(dtype):
+    import vitb200
+    x = _randn((5000, 2304), 1, 1.0, dtype)
+    out = torch.ones(2304, device="cuda")
+    vitb200.ops.colsum(x, out)
+    assert rel_l2(out, x.float().sum(0) + 1) < 1e-4
+
+
+def test_cross_entropy():
+    import vitb200
+    B, Ccls = 128, 100
+    logits = _randn((B, Ccls), 1, 3.0).requires_grad_(True)
+    labels = torch.randint(0, Ccls, (B,), device="cuda")
+    ref = torch.nn.functional.cross_entropy(logits, labels)
+    ref.backward()
+    loss, dl = vitb200.ops.cross_entropy(logits.detach(), labels)
+    assert abs(float(loss) - float(ref)) < 1e-5 * abs(float(ref))
+    assert rel_l2(dl, logits.grad) < 1e-5
+
+
+def test_sgd_momentum_matches_torch():
+    import vitb200
+    n = 4 * 1000 + 4
+    p0 = _randn((n,), 1)
+    p_ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.SGD([p_ref], lr=0.03, momentum=0.9, weight_decay=1e-4)
+    p = p0.clone(); m = torch.zeros_like(p)
+    hi = torch.empty(n, dtype=torch.bfloat16, device="cuda")
+    for step in range(3):
+        g = _randn((n,), 10 + step)
+        p_ref.grad = g.clone()
+        opt.step()
+        vitb200.ops.sgd_momentum(p, g, m, 0.03, 0.9, weight_decay=1e-4, first_step=(step == 0), shadow_hi=hi)
+    assert rel_l2(p, p_ref.detach()) < 1e-6
+    assert torch.equal(hi, p.to(torch.bfloat16))
+
+
+def test_adamw_and_clip_match_torch():
+    import vitb200
+    n = 5003
+    p0 = _randn((n,), 1)
+    p_ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([p_ref], lr=1e-3, weight_decay=0.05)
+    p = p0.clone(); m = torch.zeros_like(p); v = torch.zeros_like(p)
+    ss = torch.zeros((), device="cuda"); coef = torch.zeros((), device="cuda"); nrm = torch.zeros((), device="cuda")
+    for step in range(1, 4):
+        g = _randn((n,), 10 + step, 2.0)
+        p_ref.grad = g.clone()
+        ref_norm = torch.nn.utils.clip_grad_norm_([p_ref], 1.0)
+        opt.step()
+        ss.zero_()
+        vitb200.ops.sumsq(g, ss)
+        vitb200.ops.clip_coef(ss, 1.0, coef, nrm)
+        assert abs(float(nrm) - float(ref_norm)) < 1e-4 * float(ref_norm)
+        vitb200.ops.adamw(p, g, m, v, 1e-3, 0.9, 0.999, 1e-8, 0.05, step, grad_scale=coef)
+    assert rel_l2(p, p_ref.detach()) < 1e-6

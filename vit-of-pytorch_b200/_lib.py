@@ -113,3 +113,62 @@ def require_cuda(*tensors):
 
 def ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class AttnParams(C.Structure):
+    _fields_ = [
+        ("struct_bytes", C.c_int32),
+        ("dtype", C.c_int32),
+        ("B", C.c_int32),
+        ("H", C.c_int32),
+        ("Nq", C.c_int32),
+        ("Nk", C.c_int32),
+        ("head_dim", C.c_int32),
+        ("_pad0", C.c_int32),
+        ("q", C.c_void_p),
+        ("k", C.c_void_p),
+        ("v", C.c_void_p),
+        ("o", C.c_void_p),
+        ("lse", C.c_void_p),
+        ("q_batch_stride", C.c_int64), ("q_row_stride", C.c_int64),
+        ("k_batch_stride", C.c_int64), ("k_row_stride", C.c_int64),
+        ("v_batch_stride", C.c_int64), ("v_row_stride", C.c_int64),
+        ("o_batch_stride", C.c_int64), ("o_row_stride", C.c_int64),
+        ("dout", C.c_void_p),
+        ("do_batch_stride", C.c_int64), ("do_row_stride", C.c_int64),
+        ("dq", C.c_void_p),
+        ("dk", C.c_void_p),
+        ("dv", C.c_void_p),
+        ("dq_batch_stride", C.c_int64), ("dq_row_stride", C.c_int64),
+        ("dk_batch_stride", C.c_int64), ("dk_row_stride", C.c_int64),
+        ("dv_batch_stride", C.c_int64), ("dv_row_stride", C.c_int64),
+    ]
+
+
+_vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
+_vitb_layernorm_fwd = _sig("vitb_layernorm_fwd", [_vp, _i, _i64, _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp])
+_vitb_layernorm_bwd = _sig("vitb_layernorm_bwd", [_vp, _i, _vp, _i64, _vp, _vp, _vp, _i, _i, _vp, _i64, _vp, _i64,
+                                                   _vp, _vp, _vp, _vp, _vp, _vp])
+vitb_attn_supported_tc = _sig("vitb_attn_supported_tc", [_i, _i, _i])
+_vitb_attn_fwd_tc = _sig("vitb_attn_fwd_tc", [C.POINTER(AttnParams), _vp])
+_vitb_attn_bwd_tc = _sig("vitb_attn_bwd_tc", [C.POINTER(AttnParams), _vp])
+_vitb_attn_fwd_simt = _sig("vitb_attn_fwd_simt", [C.POINTER(AttnParams), _vp])
+_vitb_attn_bwd_simt = _sig("vitb_attn_bwd_simt", [C.POINTER(AttnParams), _vp])
+_vitb_cast_split = _sig("vitb_cast_split", [_vp, _i64, _vp, _vp, _vp])
+_vitb_im2col = _sig("vitb_im2col", [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp])
+_vitb_cls_rows = _sig("vitb_cls_rows", [_vp, _i, _i, _i, _vp, _vp, _vp])
+_vitb_embed_bwd = _sig("vitb_embed_bwd", [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp])
+_vitb_colsum = _sig("vitb_colsum", [_vp, _i, _i, _i, _i64, _vp, _vp])
+_vitb_cross_entropy = _sig("vitb_cross_entropy", [_vp, _vp, _i, _i, _vp, _vp, _vp])
+_vitb_sgd_momentum = _sig("vitb_sgd_momentum", [_vp, _vp, _vp, _i64, _f, _f, _f, _f, _i, _i, _vp, _vp, _vp])
+_vitb_adamw = _sig("vitb_adamw", [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _i, _vp, _vp, _vp, _vp])
+_vitb_sumsq = _sig("vitb_sumsq", [_vp, _i64, _vp, _vp])
+_vitb_clip_coef = _sig("vitb_clip_coef", [_vp, _f, _vp, _vp, _vp])
+
+EXPORTED_SYMBOLS = [
+    "vitb_version", "vitb_last_error", "vitb_device_check", "vitb_gemm", "vitb_layernorm_fwd",
+    "vitb_layernorm_bwd", "vitb_attn_supported_tc", "vitb_attn_fwd_tc", "vitb_attn_bwd_tc",
+    "vitb_attn_fwd_simt", "vitb_attn_bwd_simt", "vitb_cast_split", "vitb_im2col", "vitb_cls_rows",
+    "vitb_embed_bwd", "vitb_colsum", "vitb_cross_entropy", "vitb_sgd_momentum", "vitb_adamw",
+    "vitb_sumsq", "vitb_clip_coef",
+]

@@ -1,0 +1,578 @@
+// vitb_attention_tc.cu — flash-style SelfAttention on tcgen05 tensor cores (bf16 in, fp32 in TMEM).
+//
+// Replaces the q k^T / softmax / v chain of SelfAttention.forward (src/model.py:90-97) and
+// Attention.forward (res-vit/model.py:273-293) plus its autograd backward, for head_dim 64 and up
+// to 256 keys (ViT-B/L at 224 px: N = 197 or 50).  The [B,H,N,N] score tensor the reference
+// materialises in HBM never leaves the SM: S lives in TMEM, P goes through shared memory straight
+// into the second MMA.  The non-power-of-two tail (197 = 128 + 69 query rows, 208 = 13 x 16 key
+// columns) is handled by TMA zero fill plus explicit masking of key columns >= N.
+//
+// Forward, one CTA per (image, head, 128-query tile), 2 CTAs resident per SM:
+//   TMA   : Q[128x64], K[NKx64], V[NKx64] straight from the packed [T, 3D] projection output
+//   MMA 1 : S = Q K^T        (128 x NK x 64, one accumulator of NK <= 256 TMEM columns)
+//   warps : row max / exp2 / row sum in fp32 (one thread per query row), P -> bf16 -> swizzled smem
+//   MMA 2 : O = P V          (128 x 64 x NK, V consumed MN-major from the same TMA image)
+//   warps : O / rowsum -> bf16 -> HBM, LSE -> HBM
+// Because all keys fit one accumulator there is no online-softmax rescale pass at these sizes.
+//
+// Backward, one CTA per (image, head); loops over the query tiles, dK/dV accumulate in TMEM:
+//   S = Q K^T ; P = exp(S*c - LSE) ; dP = dO V^T ; dS = P * (dP - D) * c
+//   dV += P^T dO ; dK += dS^T Q ; dQ = dS K            (5 tcgen05 GEMMs per query tile)
+#include "../../include/vitb200.h"
+#include "vitb_common.cuh"
+
+namespace {
+using namespace vitb;
+
+constexpr int DH = 64;
+constexpr int kChunkBytes = 128 * 128;  // one 64-key chunk of a [128 x keys] bf16 operand
+
+struct AttnTc {
+  int N;    // tokens (queries == keys)
+  int NK;   // keys padded to a multiple of 16
+  int H;
+  float scale;       // 1/sqrt(dh)
+  float scale_log2;  // scale * log2(e)
+  __nv_bfloat16* o;
+  long long o_bs, o_rs;
+  float* lse;  // [B,H,N]
+  // backward
+  const __nv_bfloat16* o_in;
+  const __nv_bfloat16* dout;
+  long long do_bs, do_rs;
+  __nv_bfloat16 *dq, *dk, *dv;
+  long long dq_bs, dq_rs, dk_bs, dk_rs, dv_bs, dv_rs;
+};
+
+// byte offset of the 16-byte unit holding keys [8u, 8u+8) of row r inside one 128B-swizzled chunk
+__device__ __forceinline__ uint32_t swz_unit(int r, int u) {
+  return static_cast<uint32_t>(r * 128 + ((u ^ (r & 7)) << 4));
+}
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+// ================================================================================================
+// forward
+// ================================================================================================
+__global__ void __launch_bounds__(128)
+attn_fwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+            const __grid_constant__ CUtensorMap tmV, const AttnTc a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const int NK = a.NK;
+  const int kv_bytes = NK * 128;
+  const int nchunks = (NK + 63) >> 6;
+  const int u_bytes = max(kChunkBytes + kv_bytes, nchunks * kChunkBytes);
+  uint8_t* sV = smem;
+  uint8_t* sU = smem + kv_bytes;       // Q | K, later overwritten by P
+  uint8_t* sQ = sU;
+  uint8_t* sK = sU + kChunkBytes;
+  uint8_t* sP = sU;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sU + u_bytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  const uint32_t bar_qk = smem_u32(bars), bar_v = bar_qk + 8, bar_s = bar_qk + 16, bar_o = bar_qk + 24;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+    mbar_init(bar_qk, 1); mbar_init(bar_v, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) { tmem_alloc(smem_u32(tmem_slot), 256); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (tid == 0) {
+    mbar_arrive_expect_tx(bar_qk, kChunkBytes + kv_bytes);
+    tma_load_3d(&tmQ, bar_qk, smem_u32(sQ), h * DH, row0, b);
+    tma_load_3d(&tmK, bar_qk, smem_u32(sK), h * DH, 0, b);
+    mbar_arrive_expect_tx(bar_v, kv_bytes);
+    tma_load_3d(&tmV, bar_v, smem_u32(sV), h * DH, 0, b);
+    mbar_wait(bar_qk, 0);
+    tc_fence_after();
+    const uint32_t idesc = umma_idesc_bf16(128, NK, false, false);
+#pragma unroll
+    for (int k = 0; k < DH / 16; ++k)
+      umma_bf16_ss(tmem_base, umma_smem_desc_sw128(smem_u32(sQ) + k * 32, 16, 1024),
+                   umma_smem_desc_sw128(smem_u32(sK) + k * 32, 16, 1024), idesc, k > 0 ? 1u : 0u);
+    umma_commit(bar_s);
+  }
+  __syncwarp();
+  mbar_wait(bar_s, 0);
+  tc_fence_after();
+
+  const int r = warp * 32 + lane;  // query row within the tile == TMEM lane
+  const uint32_t trow = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+  // pass 1: row max over the valid keys
+  float mx = -INFINITY;
+  for (int c0 = 0; c0 < NK; c0 += 32) {
+    uint32_t v[32];
+    if (c0 + 32 <= NK) {
+      tmem_ld_32x32b_x32(trow + c0, v);
+    } else {
+      uint32_t w[16];
+      tmem_ld_32x32b_x16(trow + c0, w);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { v[j] = w[j]; v[16 + j] = 0xff800000u; }
+    }
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (c0 + j < a.N) mx = fmaxf(mx, __uint_as_float(v[j]));
+  }
+  // pass 2: p = exp2((s - max) * c), row sum, bf16 P into the swizzled A-operand image
+  float sum = 0.f;
+  const float mxs = mx * a.scale_log2;
+  const uint32_t sP_u = smem_u32(sP);
+  for (int c0 = 0; c0 < NK; c0 += 32) {
+    uint32_t v[32];
+    const bool full = (c0 + 32 <= NK);
+    if (full) {
+      tmem_ld_32x32b_x32(trow + c0, v);
+    } else {
+      uint32_t w[16];
+      tmem_ld_32x32b_x16(trow + c0, w);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { v[j] = w[j]; v[16 + j] = 0u; }
+    }
+    tmem_ld_wait();
+    float pv[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float e = exp2f(fmaf(__uint_as_float(v[j]), a.scale_log2, -mxs));
+      pv[j] = (c0 + j < a.N) ? e : 0.f;
+      sum += pv[j];
+    }
+    const int kc = c0 >> 6;
+    const int u0 = (c0 & 63) >> 3;
+    const int nunits = full ? 4 : 2;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (u < nunits)
+        st_shared_v4(sP_u + kc * kChunkBytes + swz_unit(r, u0 + u), pack_bf16x2(pv[8 * u + 0], pv[8 * u + 1]),
+                     pack_bf16x2(pv[8 * u + 2], pv[8 * u + 3]), pack_bf16x2(pv[8 * u + 4], pv[8 * u + 5]),
+                     pack_bf16x2(pv[8 * u + 6], pv[8 * u + 7]));
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    tc_fence_after();
+    mbar_wait(bar_v, 0);
+    const uint32_t idesc = umma_idesc_bf16(128, DH, false, true);
+    const int nks = NK >> 4;
+    for (int t = 0; t < nks; ++t)
+      umma_bf16_ss(tmem_base, umma_smem_desc_sw128(sP_u + (t >> 2) * kChunkBytes + (t & 3) * 32, 16, 1024),
+                   umma_smem_desc_sw128(smem_u32(sV) + t * 2048, 8192, 1024), idesc, t > 0 ? 1u : 0u);
+    umma_commit(bar_o);
+  }
+  __syncwarp();
+  mbar_wait(bar_o, 0);
+  tc_fence_after();
+  const int row = row0 + r;
+  const float inv = 1.0f / sum;
+  {
+    uint32_t v0[32], v1[32];
+    tmem_ld_32x32b_x32(trow, v0);
+    tmem_ld_32x32b_x32(trow + 32, v1);
+    tmem_ld_wait();
+    if (row < a.N) {
+      uint4* dst = reinterpret_cast<uint4*>(a.o + b * a.o_bs + static_cast<long long>(row) * a.o_rs + h * DH);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        uint4 w;
+        w.x = pack_bf16x2(__uint_as_float(v0[8 * u + 0]) * inv, __uint_as_float(v0[8 * u + 1]) * inv);
+        w.y = pack_bf16x2(__uint_as_float(v0[8 * u + 2]) * inv, __uint_as_float(v0[8 * u + 3]) * inv);
+        w.z = pack_bf16x2(__uint_as_float(v0[8 * u + 4]) * inv, __uint_as_float(v0[8 * u + 5]) * inv);
+        w.w = pack_bf16x2(__uint_as_float(v0[8 * u + 6]) * inv, __uint_as_float(v0[8 * u + 7]) * inv);
+        dst[u] = w;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        uint4 w;
+        w.x = pack_bf16x2(__uint_as_float(v1[8 * u + 0]) * inv, __uint_as_float(v1[8 * u + 1]) * inv);
+        w.y = pack_bf16x2(__uint_as_float(v1[8 * u + 2]) * inv, __uint_as_float(v1[8 * u + 3]) * inv);
+        w.z = pack_bf16x2(__uint_as_float(v1[8 * u + 4]) * inv, __uint_as_float(v1[8 * u + 5]) * inv);
+        w.w = pack_bf16x2(__uint_as_float(v1[8 * u + 6]) * inv, __uint_as_float(v1[8 * u + 7]) * inv);
+        dst[4 + u] = w;
+      }
+      if (a.lse) a.lse[(static_cast<long long>(b) * a.H + h) * a.N + row] = mx * a.scale + logf(sum);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
+}
+
+// ================================================================================================
+// backward
+// ================================================================================================
+// TMEM columns: [0,256) S then dP then dQ ; [256,384) dK (two 128-key M tiles x 64) ; [384,512) dV
+__global__ void __launch_bounds__(128, 1)
+attn_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+            const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
+            const AttnTc a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const int NK = a.NK;
+  const int kv_bytes = NK * 128;
+  const int mtiles = (NK + 127) >> 7;        // 128-key M tiles of dK / dV
+  const int nchunks = mtiles * 2;            // P / dS images always hold whole M tiles
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + kv_bytes;
+  uint8_t* sQ = sV + kv_bytes;
+  uint8_t* sDO = sQ + kChunkBytes;
+  uint8_t* sP = sDO + kChunkBytes;
+  uint8_t* sDS = sP + nchunks * kChunkBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDS + nchunks * kChunkBytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  const uint32_t bar_kv = smem_u32(bars), bar_q = bar_kv + 8, bar_s = bar_kv + 16, bar_dp = bar_kv + 24,
+                 bar_dq = bar_kv + 32, bar_fin = bar_kv + 40;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int r = warp * 32 + lane;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
+    for (int i = 0; i < 6; ++i) mbar_init(bar_kv + 8 * i, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) { tmem_alloc(smem_u32(tmem_slot), 512); tmem_relinquish(); }
+  // zero the P / dS images once: key columns >= NK of the last M tile are never written again
+  {
+    const uint32_t base = smem_u32(sP);
+    const int total16 = 2 * nchunks * kChunkBytes / 16;
+    for (int i = tid; i < total16; i += 128) st_shared_v4(base + i * 16, 0u, 0u, 0u, 0u);
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t trow = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+  const uint32_t sP_u = smem_u32(sP), sDS_u = smem_u32(sDS);
+  const uint32_t sQ_u = smem_u32(sQ), sDO_u = smem_u32(sDO), sK_u = smem_u32(sK), sV_u = smem_u32(sV);
+
+  if (tid == 0) {
+    mbar_arrive_expect_tx(bar_kv, 2 * kv_bytes);
+    tma_load_3d(&tmK, bar_kv, sK_u, h * DH, 0, b);
+    tma_load_3d(&tmV, bar_kv, sV_u, h * DH, 0, b);
+  }
+  const int qtiles = (a.N + 127) >> 7;
+  for (int qt = 0; qt < qtiles; ++qt) {
+    const uint32_t ph = qt & 1;
+    const int row0 = qt * 128;
+    const int row = row0 + r;
+    if (tid == 0) {
+      mbar_arrive_expect_tx(bar_q, 2 * kChunkBytes);
+      tma_load_3d(&tmQ, bar_q, sQ_u, h * DH, row0, b);
+      tma_load_3d(&tmDO, bar_q, sDO_u, h * DH, row0, b);
+      if (qt == 0) mbar_wait(bar_kv, 0);
+      mbar_wait(bar_q, ph);
+      tc_fence_after();
+      const uint32_t idesc = umma_idesc_bf16(128, NK, false, false);
+#pragma unroll
+      for (int k = 0; k < DH / 16; ++k)  // S = Q K^T
+        umma_bf16_ss(tmem_base, umma_smem_desc_sw128(sQ_u + k * 32, 16, 1024),
+                     umma_smem_desc_sw128(sK_u + k * 32, 16, 1024), idesc, k > 0 ? 1u : 0u);
+      umma_commit(bar_s);
+    }
+    // D_i = rowsum(dO * O) and LSE straight from HBM while the MMA runs
+    float Di = 0.f, lse = INFINITY;
+    if (row < a.N) {
+      const uint4* po = reinterpret_cast<const uint4*>(a.o_in + b * a.o_bs + static_cast<long long>(row) * a.o_rs + h * DH);
+      const uint4* pg = reinterpret_cast<const uint4*>(a.dout + b * a.do_bs + static_cast<long long>(row) * a.do_rs + h * DH);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const uint4 x = po[u], y = pg[u];
+        Di += bf16_lo(x.x) * bf16_lo(y.x) + bf16_hi(x.x) * bf16_hi(y.x) + bf16_lo(x.y) * bf16_lo(y.y) +
+              bf16_hi(x.y) * bf16_hi(y.y) + bf16_lo(x.z) * bf16_lo(y.z) + bf16_hi(x.z) * bf16_hi(y.z) +
+              bf16_lo(x.w) * bf16_lo(y.w) + bf16_hi(x.w) * bf16_hi(y.w);
+      }
+      lse = a.lse[(static_cast<long long>(b) * a.H + h) * a.N + row];
+    }
+    const float lse2 = lse * 1.4426950408889634f;
+    __syncwarp();
+    mbar_wait(bar_s, ph);
+    tc_fence_after();
+    // P = exp2(S*c - LSE*log2e) -> bf16 -> sP   (rows >= N and keys >= N give exactly 0)
+    for (int c0 = 0; c0 < NK; c0 += 32) {
+      uint32_t v[32];
+      const bool full = (c0 + 32 <= NK);
+      if (full) {
+        tmem_ld_32x32b_x32(trow + c0, v);
+      } else {
+        uint32_t w[16];
+        tmem_ld_32x32b_x16(trow + c0, w);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { v[j] = w[j]; v[16 + j] = 0u; }
+      }
+      tmem_ld_wait();
+      float pv[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float e = exp2f(fmaf(__uint_as_float(v[j]), a.scale_log2, -lse2));
+        pv[j] = (c0 + j < a.N && row < a.N) ? e : 0.f;
+      }
+      const int kc = c0 >> 6, u0 = (c0 & 63) >> 3, nunits = full ? 4 : 2;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (u < nunits)
+          st_shared_v4(sP_u + kc * kChunkBytes + swz_unit(r, u0 + u), pack_bf16x2(pv[8 * u + 0], pv[8 * u + 1]),
+                       pack_bf16x2(pv[8 * u + 2], pv[8 * u + 3]), pack_bf16x2(pv[8 * u + 4], pv[8 * u + 5]),
+                       pack_bf16x2(pv[8 * u + 6], pv[8 * u + 7]));
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t idesc_dp = umma_idesc_bf16(128, NK, false, false);
+#pragma unroll
+      for (int k = 0; k < DH / 16; ++k)  // dP = dO V^T  (overwrites S)
+        umma_bf16_ss(tmem_base, umma_smem_desc_sw128(sDO_u + k * 32, 16, 1024),
+                     umma_smem_desc_sw128(sV_u + k * 32, 16, 1024), idesc_dp, k > 0 ? 1u : 0u);
+      umma_commit(bar_dp);
+      // dV[m-tile] += P^T dO : A = P^T (MN-major image of sP), B = dO (MN-major), K = 128 query rows
+      const uint32_t idesc_t = umma_idesc_bf16(128, DH, true, true);
+      for (int mt = 0; mt < mtiles; ++mt)
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_bf16_ss(tmem_base + 384 + mt * 64,
+                       umma_smem_desc_sw128(sP_u + mt * 2 * kChunkBytes + k * 2048, kChunkBytes, 1024),
+                       umma_smem_desc_sw128(sDO_u + k * 2048, 8192, 1024), idesc_t, (qt > 0 || k > 0) ? 1u : 0u);
+    }
+    __syncwarp();
+    mbar_wait(bar_dp, ph);
+    tc_fence_after();
+    // dS = P * (dP - D) * c  -> bf16 -> sDS
+    for (int c0 = 0; c0 < NK; c0 += 32) {
+      uint32_t v[32];
+      const bool full = (c0 + 32 <= NK);
+      if (full) {
+        tmem_ld_32x32b_x32(trow + c0, v);
+      } else {
+        uint32_t w[16];
+        tmem_ld_32x32b_x16(trow + c0, w);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { v[j] = w[j]; v[16 + j] = 0u; }
+      }
+      tmem_ld_wait();
+      const int kc = c0 >> 6, u0 = (c0 & 63) >> 3, nunits = full ? 4 : 2;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (u < nunits) {
+          const uint32_t off = kc * kChunkBytes + swz_unit(r, u0 + u);
+          const uint4 pp = ld_shared_v4(sP_u + off);
+          const float d0 = bf16_lo(pp.x) * (__uint_as_float(v[8 * u + 0]) - Di) * a.scale;
+          const float d1 = bf16_hi(pp.x) * (__uint_as_float(v[8 * u + 1]) - Di) * a.scale;
+          const float d2 = bf16_lo(pp.y) * (__uint_as_float(v[8 * u + 2]) - Di) * a.scale;
+          const float d3 = bf16_hi(pp.y) * (__uint_as_float(v[8 * u + 3]) - Di) * a.scale;
+          const float d4 = bf16_lo(pp.z) * (__uint_as_float(v[8 * u + 4]) - Di) * a.scale;
+          const float d5 = bf16_hi(pp.z) * (__uint_as_float(v[8 * u + 5]) - Di) * a.scale;
+          const float d6 = bf16_lo(pp.w) * (__uint_as_float(v[8 * u + 6]) - Di) * a.scale;
+          const float d7 = bf16_hi(pp.w) * (__uint_as_float(v[8 * u + 7]) - Di) * a.scale;
+          st_shared_v4(sDS_u + off, pack_bf16x2(d0, d1), pack_bf16x2(d2, d3), pack_bf16x2(d4, d5),
+                       pack_bf16x2(d6, d7));
+        }
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      // dQ = dS K : A = dS (K-major over keys), B = K (MN-major: keys x dh)
+      const uint32_t idesc_dq = umma_idesc_bf16(128, DH, false, true);
+      const int nks = NK >> 4;
+      for (int t = 0; t < nks; ++t)
+        umma_bf16_ss(tmem_base, umma_smem_desc_sw128(sDS_u + (t >> 2) * kChunkBytes + (t & 3) * 32, 16, 1024),
+                     umma_smem_desc_sw128(sK_u + t * 2048, 8192, 1024), idesc_dq, t > 0 ? 1u : 0u);
+      umma_commit(bar_dq);
+      // dK[m-tile] += dS^T Q
+      const uint32_t idesc_t = umma_idesc_bf16(128, DH, true, true);
+      for (int mt = 0; mt < mtiles; ++mt)
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_bf16_ss(tmem_base + 256 + mt * 64,
+                       umma_smem_desc_sw128(sDS_u + mt * 2 * kChunkBytes + k * 2048, kChunkBytes, 1024),
+                       umma_smem_desc_sw128(sQ_u + k * 2048, 8192, 1024), idesc_t, (qt > 0 || k > 0) ? 1u : 0u);
+      umma_commit(bar_fin);
+    }
+    __syncwarp();
+    mbar_wait(bar_dq, ph);
+    tc_fence_after();
+    {
+      uint32_t v0[32], v1[32];
+      tmem_ld_32x32b_x32(trow, v0);
+      tmem_ld_32x32b_x32(trow + 32, v1);
+      tmem_ld_wait();
+      if (row < a.N) {
+        uint4* dst = reinterpret_cast<uint4*>(a.dq + b * a.dq_bs + static_cast<long long>(row) * a.dq_rs + h * DH);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(v0[8 * u + 0]), __uint_as_float(v0[8 * u + 1]));
+          w.y = pack_bf16x2(__uint_as_float(v0[8 * u + 2]), __uint_as_float(v0[8 * u + 3]));
+          w.z = pack_bf16x2(__uint_as_float(v0[8 * u + 4]), __uint_as_float(v0[8 * u + 5]));
+          w.w = pack_bf16x2(__uint_as_float(v0[8 * u + 6]), __uint_as_float(v0[8 * u + 7]));
+          dst[u] = w;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(v1[8 * u + 0]), __uint_as_float(v1[8 * u + 1]));
+          w.y = pack_bf16x2(__uint_as_float(v1[8 * u + 2]), __uint_as_float(v1[8 * u + 3]));
+          w.z = pack_bf16x2(__uint_as_float(v1[8 * u + 4]), __uint_as_float(v1[8 * u + 5]));
+          w.w = pack_bf16x2(__uint_as_float(v1[8 * u + 6]), __uint_as_float(v1[8 * u + 7]));
+          dst[4 + u] = w;
+        }
+      }
+    }
+    // the next query tile overwrites sQ/sDO/sP/sDS and TMEM[0,256): wait until every MMA of this
+    // tile (dK included) has retired, and until all warps have drained dQ from TMEM
+    mbar_wait(bar_fin, ph);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
+  // dK, dV: TMEM lane = key within the M tile
+  for (int mt = 0; mt < mtiles; ++mt) {
+    const int key = mt * 128 + r;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      uint32_t v0[32], v1[32];
+      const uint32_t col = (which == 0 ? 256u : 384u) + static_cast<uint32_t>(mt * 64);
+      tmem_ld_32x32b_x32(trow + col, v0);
+      tmem_ld_32x32b_x32(trow + col + 32, v1);
+      tmem_ld_wait();
+      if (key < a.N) {
+        __nv_bfloat16* base = which == 0 ? a.dk + b * a.dk_bs + static_cast<long long>(key) * a.dk_rs
+                                         : a.dv + b * a.dv_bs + static_cast<long long>(key) * a.dv_rs;
+        uint4* dst = reinterpret_cast<uint4*>(base + h * DH);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(v0[8 * u + 0]), __uint_as_float(v0[8 * u + 1]));
+          w.y = pack_bf16x2(__uint_as_float(v0[8 * u + 2]), __uint_as_float(v0[8 * u + 3]));
+          w.z = pack_bf16x2(__uint_as_float(v0[8 * u + 4]), __uint_as_float(v0[8 * u + 5]));
+          w.w = pack_bf16x2(__uint_as_float(v0[8 * u + 6]), __uint_as_float(v0[8 * u + 7]));
+          dst[u] = w;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(v1[8 * u + 0]), __uint_as_float(v1[8 * u + 1]));
+          w.y = pack_bf16x2(__uint_as_float(v1[8 * u + 2]), __uint_as_float(v1[8 * u + 3]));
+          w.z = pack_bf16x2(__uint_as_float(v1[8 * u + 4]), __uint_as_float(v1[8 * u + 5]));
+          w.w = pack_bf16x2(__uint_as_float(v1[8 * u + 6]), __uint_as_float(v1[8 * u + 7]));
+          dst[4 + u] = w;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+int make_head_map(CUtensorMap* m, const void* base, int H, int N, int B, long long row_stride, long long batch_stride,
+                  int box_rows) {
+  uint64_t dims[3] = {(uint64_t)H * DH, (uint64_t)N, (uint64_t)B};
+  uint64_t str[2] = {(uint64_t)row_stride * 2, (uint64_t)batch_stride * 2};
+  uint32_t box[3] = {DH, (uint32_t)box_rows, 1};
+  return vitb_make_tmap_nd_bf16(m, base, 3, dims, str, box);
+}
+
+int check_common(const vitb_attn_params* p, const char* who) {
+  VITB_REQUIRE(p && p->struct_bytes == (int)sizeof(vitb_attn_params), VITB_ERR_BAD_ARG, "%s: ABI mismatch", who);
+  VITB_REQUIRE(p->dtype == VITB_BF16, VITB_ERR_UNSUPPORTED_SHAPE, "%s: bf16 only", who);
+  VITB_REQUIRE(p->head_dim == DH, VITB_ERR_UNSUPPORTED_SHAPE, "%s: head_dim %d (only 64)", who, p->head_dim);
+  VITB_REQUIRE(p->Nq == p->Nk && p->Nk >= 1 && p->Nk <= 256, VITB_ERR_UNSUPPORTED_SHAPE,
+               "%s: Nq=%d Nk=%d (need Nq == Nk <= 256)", who, p->Nq, p->Nk);
+  VITB_REQUIRE(p->q && p->k && p->v && p->o, VITB_ERR_BAD_ARG, "%s: null tensor", who);
+  VITB_REQUIRE(p->o_row_stride % 8 == 0 && p->o_batch_stride % 8 == 0, VITB_ERR_UNSUPPORTED_SHAPE, "%s: o strides %% 8", who);
+  return VITB_OK;
+}
+
+}  // namespace
+
+extern "C" int vitb_attn_supported_tc(int head_dim, int Nq, int Nk) {
+  return head_dim == DH && Nq == Nk && Nk >= 1 && Nk <= 256;
+}
+
+extern "C" int vitb_attn_fwd_tc(const vitb_attn_params* p, void* stream_) {
+  int st = vitb_check_device();
+  if (st != VITB_OK) return st;
+  st = check_common(p, "attn_fwd_tc");
+  if (st != VITB_OK) return st;
+  if (p->B == 0) return VITB_OK;
+  const int N = p->Nk, NK = (N + 15) & ~15;
+  CUtensorMap tq, tk, tv;
+  if ((st = make_head_map(&tq, p->q, p->H, N, p->B, p->q_row_stride, p->q_batch_stride, 128)) != VITB_OK) return st;
+  if ((st = make_head_map(&tk, p->k, p->H, N, p->B, p->k_row_stride, p->k_batch_stride, NK)) != VITB_OK) return st;
+  if ((st = make_head_map(&tv, p->v, p->H, N, p->B, p->v_row_stride, p->v_batch_stride, NK)) != VITB_OK) return st;
+  AttnTc a{};
+  a.N = N; a.NK = NK; a.H = p->H;
+  a.scale = 1.0f / sqrtf((float)DH);
+  a.scale_log2 = a.scale * 1.4426950408889634f;
+  a.o = reinterpret_cast<__nv_bfloat16*>(p->o); a.o_bs = p->o_batch_stride; a.o_rs = p->o_row_stride;
+  a.lse = p->lse;
+  const int kv_bytes = NK * 128, nchunks = (NK + 63) / 64;
+  const int u_bytes = (kChunkBytes + kv_bytes) > nchunks * kChunkBytes ? (kChunkBytes + kv_bytes) : nchunks * kChunkBytes;
+  const int smem = kv_bytes + u_bytes + 64 + 1024;
+  VITB_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  dim3 grid((N + 127) / 128, p->H, p->B);
+  attn_fwd_tc<<<grid, 128, smem, reinterpret_cast<cudaStream_t>(stream_)>>>(tq, tk, tv, a);
+  VITB_LAUNCH_CHECK("attn_fwd_tc");
+  return VITB_OK;
+}
+
+extern "C" int vitb_attn_bwd_tc(const vitb_attn_params* p, void* stream_) {
+  int st = vitb_check_device();
+  if (st != VITB_OK) return st;
+  st = check_common(p, "attn_bwd_tc");
+  if (st != VITB_OK) return st;
+  if (p->B == 0) return VITB_OK;
+  VITB_REQUIRE(p->lse && p->dout && p->dq && p->dk && p->dv, VITB_ERR_BAD_ARG, "attn_bwd_tc: null tensor");
+  VITB_REQUIRE(p->dq_row_stride % 8 == 0 && p->dk_row_stride % 8 == 0 && p->dv_row_stride % 8 == 0 &&
+                   p->do_row_stride % 8 == 0,
+               VITB_ERR_UNSUPPORTED_SHAPE, "attn_bwd_tc: gradient row strides %% 8");
+  const int N = p->Nk, NK = (N + 15) & ~15;
+  CUtensorMap tq, tk, tv, tdo;
+  if ((st = make_head_map(&tq, p->q, p->H, N, p->B, p->q_row_stride, p->q_batch_stride, 128)) != VITB_OK) return st;
+  if ((st = make_head_map(&tk, p->k, p->H, N, p->B, p->k_row_stride, p->k_batch_stride, NK)) != VITB_OK) return st;
+  if ((st = make_head_map(&tv, p->v, p->H, N, p->B, p->v_row_stride, p->v_batch_stride, NK)) != VITB_OK) return st;
+  if ((st = make_head_map(&tdo, p->dout, p->H, N, p->B, p->do_row_stride, p->do_batch_stride, 128)) != VITB_OK) return st;
+  AttnTc a{};
+  a.N = N; a.NK = NK; a.H = p->H;
+  a.scale = 1.0f / sqrtf((float)DH);
+  a.scale_log2 = a.scale * 1.4426950408889634f;
+  a.o_in = reinterpret_cast<const __nv_bfloat16*>(p->o); a.o_bs = p->o_batch_stride; a.o_rs = p->o_row_stride;
+  a.lse = p->lse;
+  a.dout = reinterpret_cast<const __nv_bfloat16*>(p->dout); a.do_bs = p->do_batch_stride; a.do_rs = p->do_row_stride;
+  a.dq = reinterpret_cast<__nv_bfloat16*>(p->dq); a.dq_bs = p->dq_batch_stride; a.dq_rs = p->dq_row_stride;
+  a.dk = reinterpret_cast<__nv_bfloat16*>(p->dk); a.dk_bs = p->dk_batch_stride; a.dk_rs = p->dk_row_stride;
+  a.dv = reinterpret_cast<__nv_bfloat16*>(p->dv); a.dv_bs = p->dv_batch_stride; a.dv_rs = p->dv_row_stride;
+  const int kv_bytes = NK * 128, mtiles = (NK + 127) / 128, nchunks = 2 * mtiles;
+  const int smem = 2 * kv_bytes + 2 * kChunkBytes + 2 * nchunks * kChunkBytes + 128 + 1024;
+  VITB_REQUIRE(smem <= 227 * 1024, VITB_ERR_UNSUPPORTED_SHAPE, "attn_bwd_tc: %d B of shared memory", smem);
+  VITB_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  dim3 grid(p->H, p->B);
+  attn_bwd_tc<<<grid, 128, smem, reinterpret_cast<cudaStream_t>(stream_)>>>(tq, tk, tv, tdo, a);
+  VITB_LAUNCH_CHECK("attn_bwd_tc");
+  return VITB_OK;
+}

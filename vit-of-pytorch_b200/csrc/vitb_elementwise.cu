@@ -1,0 +1,445 @@
+// vitb_elementwise.cu — the HBM-bound, non-contraction kernels of the ViT encoder path:
+// operand casts / bf16 hi-lo split, patch extraction, class-token + position rows, the embedding
+// backward reduction, column sums (bias gradients), cross-entropy, fused SGD / AdamW.
+// All use 128-bit coalesced access and grid sizes in multiples of the SM count.
+#include "../../include/vitb200.h"
+#include "vitb_common.cuh"
+
+namespace {
+using namespace vitb;
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16(v)); }
+
+inline int grid_for(long long work_items, int per_sm = 8) {
+  long long blocks = (work_items + kThreads - 1) / kThreads;
+  long long cap = static_cast<long long>(vitb_num_sms()) * per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp32 -> bf16 cast, optionally with the residual "lo" half (x - bf16(x)) for the bf16x3 GEMMs
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+cast_split_kernel(const float* __restrict__ x, long long n, __nv_bfloat16* __restrict__ hi,
+                  __nv_bfloat16* __restrict__ lo) {
+  const long long n4 = n >> 2;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    uint2 h;
+    h.x = pack_bf16x2(v.x, v.y);
+    h.y = pack_bf16x2(v.z, v.w);
+    reinterpret_cast<uint2*>(hi)[i] = h;
+    if (lo) {
+      uint2 l;
+      l.x = pack_bf16x2(v.x - bf16_round(v.x), v.y - bf16_round(v.y));
+      l.y = pack_bf16x2(v.z - bf16_round(v.z), v.w - bf16_round(v.w));
+      reinterpret_cast<uint2*>(lo)[i] = l;
+    }
+  }
+  // tail
+  const long long t0 = n4 << 2;
+  for (long long i = t0 + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float v = x[i];
+    hi[i] = __float2bfloat16(v);
+    if (lo) lo[i] = __float2bfloat16(v - bf16_round(v));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Patch extraction (the Conv2d(3,D,P,P) of src/model.py:179,197 as a GEMM operand):
+// rows = (b, py, px), k = (c, ph, pw) — the flattening of conv weight [D,3,P,P]; K padded to ldk.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+im2col_kernel(const float* __restrict__ img, int Bsz, int Cin, int H, int W, int P, int gh, int gw,
+              int ldk, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  const int kgroups = ldk >> 3;
+  const long long total = static_cast<long long>(Bsz) * gh * gw * kgroups;
+  const int Kreal = Cin * P * P;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int kg = static_cast<int>(i % kgroups);
+    const long long r = i / kgroups;
+    const int px = static_cast<int>(r % gw);
+    const int py = static_cast<int>((r / gw) % gh);
+    const int b = static_cast<int>(r / (static_cast<long long>(gw) * gh));
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = kg * 8 + j;
+      float val = 0.f;
+      if (k < Kreal) {
+        const int c = k / (P * P);
+        const int rem = k - c * P * P;
+        const int ph = rem / P, pw = rem - ph * P;
+        val = img[((static_cast<long long>(b) * Cin + c) * H + (py * P + ph)) * W + (px * P + pw)];
+      }
+      v[j] = val;
+    }
+    uint4 h;
+    h.x = pack_bf16x2(v[0], v[1]); h.y = pack_bf16x2(v[2], v[3]);
+    h.z = pack_bf16x2(v[4], v[5]); h.w = pack_bf16x2(v[6], v[7]);
+    reinterpret_cast<uint4*>(hi + r * ldk)[kg] = h;
+    if (lo) {
+      uint4 l;
+      l.x = pack_bf16x2(v[0] - bf16_round(v[0]), v[1] - bf16_round(v[1]));
+      l.y = pack_bf16x2(v[2] - bf16_round(v[2]), v[3] - bf16_round(v[3]));
+      l.z = pack_bf16x2(v[4] - bf16_round(v[4]), v[5] - bf16_round(v[5]));
+      l.w = pack_bf16x2(v[6] - bf16_round(v[6]), v[7] - bf16_round(v[7]));
+      reinterpret_cast<uint4*>(lo + r * ldk)[kg] = l;
+    }
+  }
+}
+
+// x[b, 0, :] = cls + pos[0]   (torch.cat([cls_token.repeat], ...) + pos_embedding, src/model.py:203-204,17)
+__global__ void __launch_bounds__(kThreads)
+cls_rows_kernel(float* __restrict__ x, int Bsz, int N, int D, const float* __restrict__ cls,
+                const float* __restrict__ pos) {
+  const int total = Bsz * D;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int b = i / D, d = i - b * D;
+    x[static_cast<long long>(b) * N * D + d] = cls[d] + (pos ? pos[d] : 0.f);
+  }
+}
+
+// Backward of the embedding stage: dx is the gradient of (cat(cls, patches) + pos) [B,N,D].
+//   dpos[n,d]  += sum_b dx[b,n,d]                   (pos_embedding grad)
+//   dcls[d]    += sum_b dx[b,0,d]                   (cls_token grad)
+//   dbias[d]   += sum_{b,n>=1} dx[b,n,d]            (conv bias grad)
+//   dpatch[b*np + n-1, d] = bf16(dx[b,n,d]) (+ lo)  (A^T operand of the conv-weight wgrad GEMM)
+__global__ void __launch_bounds__(kThreads)
+embed_bwd_kernel(const float* __restrict__ dx, int Bsz, int N, int D, float* __restrict__ dpos,
+                 float* __restrict__ dcls, float* __restrict__ dbias, __nv_bfloat16* __restrict__ dp_hi,
+                 __nv_bfloat16* __restrict__ dp_lo) {
+  const int d4 = D >> 2;
+  const int total = N * d4;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int n = i / d4, c = (i - n * d4) * 4;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int b = 0; b < Bsz; ++b) {
+      const float4 v = *reinterpret_cast<const float4*>(dx + (static_cast<long long>(b) * N + n) * D + c);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      if (n >= 1 && dp_hi) {
+        const long long off = (static_cast<long long>(b) * (N - 1) + (n - 1)) * D + c;
+        uint2 h;
+        h.x = pack_bf16x2(v.x, v.y); h.y = pack_bf16x2(v.z, v.w);
+        *reinterpret_cast<uint2*>(dp_hi + off) = h;
+        if (dp_lo) {
+          uint2 l;
+          l.x = pack_bf16x2(v.x - bf16_round(v.x), v.y - bf16_round(v.y));
+          l.y = pack_bf16x2(v.z - bf16_round(v.z), v.w - bf16_round(v.w));
+          *reinterpret_cast<uint2*>(dp_lo + off) = l;
+        }
+      }
+    }
+    if (dpos) {
+      float* p = dpos + static_cast<long long>(n) * D + c;
+      atomicAdd(p + 0, s.x); atomicAdd(p + 1, s.y); atomicAdd(p + 2, s.z); atomicAdd(p + 3, s.w);
+    }
+    if (n == 0 && dcls) {
+      atomicAdd(dcls + c + 0, s.x); atomicAdd(dcls + c + 1, s.y);
+      atomicAdd(dcls + c + 2, s.z); atomicAdd(dcls + c + 3, s.w);
+    }
+    if (n >= 1 && dbias) {
+      atomicAdd(dbias + c + 0, s.x); atomicAdd(dbias + c + 1, s.y);
+      atomicAdd(dbias + c + 2, s.z); atomicAdd(dbias + c + 3, s.w);
+    }
+  }
+}
+
+// out[c] += sum_r x[r, c]; thread owns 4 columns (bf16) / 4 columns (fp32), rows split across blocks.y
+template <bool BF16>
+__global__ void __launch_bounds__(kThreads)
+colsum_kernel(const void* __restrict__ x_, int rows, int cols, long long ld, float* __restrict__ out) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (c >= cols) return;
+  const int rows_per = (rows + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * rows_per;
+  const int r1 = min(rows, r0 + rows_per);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int r = r0; r < r1; ++r) {
+    float4 v;
+    if constexpr (BF16) {
+      const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(x_) + static_cast<long long>(r) * ld + c);
+      v = make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
+    } else {
+      v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x_) + static_cast<long long>(r) * ld + c);
+    }
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  }
+  atomicAdd(out + c + 0, s.x); atomicAdd(out + c + 1, s.y);
+  atomicAdd(out + c + 2, s.z); atomicAdd(out + c + 3, s.w);
+}
+
+// Cross entropy (mean) forward + gradient in one block: nn.CrossEntropyLoss, src/train.py:151,22;
+// res-vit/model.py:550,681.  loss = mean_b(lse_b - logit[b,label_b]); dlogits = (softmax - onehot)/B.
+__global__ void __launch_bounds__(1024)
+ce_kernel(const float* __restrict__ logits, const long long* __restrict__ labels, int Bsz, int Ccls,
+          float* __restrict__ loss, float* __restrict__ dlogits) {
+  __shared__ float s_part[32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float acc = 0.f;
+  for (int b = warp; b < Bsz; b += 32) {
+    const float* row = logits + static_cast<long long>(b) * Ccls;
+    float mx = -INFINITY;
+    for (int c = lane; c < Ccls; c += 32) mx = fmaxf(mx, row[c]);
+    mx = warp_max(mx);
+    float se = 0.f;
+    for (int c = lane; c < Ccls; c += 32) se += expf(row[c] - mx);
+    se = warp_sum(se);
+    const int lab = static_cast<int>(labels[b]);
+    const float lse = mx + logf(se);
+    if (lane == 0) acc += lse - row[lab];
+    if (dlogits) {
+      const float inv = 1.0f / se, sc = 1.0f / Bsz;
+      for (int c = lane; c < Ccls; c += 32) {
+        const float pr = expf(row[c] - mx) * inv;
+        dlogits[static_cast<long long>(b) * Ccls + c] = (pr - (c == lab ? 1.f : 0.f)) * sc;
+      }
+    }
+  }
+  if (lane == 0) s_part[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 32; ++w) t += s_part[w];
+    *loss = t / Bsz;
+  }
+}
+
+// SGD with momentum (torch.optim.SGD semantics, src/train.py:154-158) over a flat parameter buffer,
+// refreshing the bf16 GEMM shadow (and its lo half in fp32 parity mode) in the same pass.
+__global__ void __launch_bounds__(kThreads)
+sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, long long n,
+           float lr, float momentum, float dampening, float wd, int nesterov, int first_step,
+           __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  const long long n4 = n >> 2;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 pv = reinterpret_cast<float4*>(p)[i];
+    const float4 gv0 = reinterpret_cast<const float4*>(g)[i];
+    float pa[4] = {pv.x, pv.y, pv.z, pv.w};
+    float ga[4] = {gv0.x, gv0.y, gv0.z, gv0.w};
+    float ma[4] = {0.f, 0.f, 0.f, 0.f};
+    if (m && !first_step) {
+      const float4 mv = reinterpret_cast<float4*>(m)[i];
+      ma[0] = mv.x; ma[1] = mv.y; ma[2] = mv.z; ma[3] = mv.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float gg = ga[j] + wd * pa[j];
+      if (m) {
+        ma[j] = first_step ? gg : momentum * ma[j] + (1.f - dampening) * gg;
+        gg = nesterov ? gg + momentum * ma[j] : ma[j];
+      }
+      pa[j] -= lr * gg;
+    }
+    reinterpret_cast<float4*>(p)[i] = make_float4(pa[0], pa[1], pa[2], pa[3]);
+    if (m) reinterpret_cast<float4*>(m)[i] = make_float4(ma[0], ma[1], ma[2], ma[3]);
+    if (hi) {
+      uint2 h;
+      h.x = pack_bf16x2(pa[0], pa[1]); h.y = pack_bf16x2(pa[2], pa[3]);
+      reinterpret_cast<uint2*>(hi)[i] = h;
+    }
+    if (lo) {
+      uint2 l;
+      l.x = pack_bf16x2(pa[0] - bf16_round(pa[0]), pa[1] - bf16_round(pa[1]));
+      l.y = pack_bf16x2(pa[2] - bf16_round(pa[2]), pa[3] - bf16_round(pa[3]));
+      reinterpret_cast<uint2*>(lo)[i] = l;
+    }
+  }
+}
+
+// AdamW (torch.optim.AdamW semantics, res-vit/train.py:272-277); grad_scale_dev (optional, device)
+// carries the clip_grad_norm_ coefficient (res-vit/train.py:65) so no host sync is needed.
+__global__ void __launch_bounds__(kThreads)
+adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+             float* __restrict__ v, long long n, float lr, float b1, float b2, float eps, float wd,
+             float bc1, float bc2, const float* __restrict__ grad_scale_dev,
+             __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  const float gs = grad_scale_dev ? *grad_scale_dev : 1.f;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float pv = p[i];
+    const float gv = g[i] * gs;
+    pv *= (1.f - lr * wd);
+    const float mv = b1 * m[i] + (1.f - b1) * gv;
+    const float vv = b2 * v[i] + (1.f - b2) * gv * gv;
+    m[i] = mv;
+    v[i] = vv;
+    const float denom = sqrtf(vv) / sqrtf(bc2) + eps;
+    pv -= (lr / bc1) * (mv / denom);
+    p[i] = pv;
+    if (hi) hi[i] = __float2bfloat16(pv);
+    if (lo) lo[i] = __float2bfloat16(pv - bf16_round(pv));
+  }
+}
+
+// out[0] += sum x^2   (for clip_grad_norm_)
+__global__ void __launch_bounds__(kThreads)
+sumsq_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
+  __shared__ float s_part[kThreads / 32];
+  float acc = 0.f;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float v = x[i];
+    acc += v * v;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < kThreads / 32; ++w) t += s_part[w];
+    atomicAdd(out, t);
+  }
+}
+
+// coef = min(1, max_norm / (sqrt(sumsq) + 1e-6))     (torch clip_grad_norm_)
+__global__ void clip_coef_kernel(const float* __restrict__ sumsq, float max_norm, float* __restrict__ coef,
+                                 float* __restrict__ norm_out) {
+  const float nrm = sqrtf(*sumsq);
+  if (norm_out) *norm_out = nrm;
+  const float c = max_norm / (nrm + 1e-6f);
+  *coef = c < 1.f ? c : 1.f;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vitb_cast_split(const float* x, int64_t n, void* hi, void* lo, void* stream_) {
+  int st = vitb_check_device();
+  if (st != VITB_OK) return st;
+  if (n == 0) return VITB_OK;
+  VITB_REQUIRE(x && hi && n > 0, VITB_ERR_BAD_ARG, "cast_split: bad args");
+  cast_split_kernel<<<grid_for((n + 3) / 4), kThreads, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      x, n, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo));
+  VITB_LAUNCH_CHECK("cast_split_kernel");
+  return VITB_OK;
+}
+
+int vitb_im2col(const float* img, int B, int C, int H, int W, int P, int ldk, void* hi, void* lo,
+                void* stream_) {
+  int st = vitb_check_device();
+  if (st != VITB_OK) return st;
+  if (B == 0) return VITB_OK;
+  VITB_REQUIRE(img && hi && B > 0 && C > 0 && P > 0 && H >= P && W >= P, VITB_ERR_BAD_ARG, "im2col: bad args");
+  VITB_REQUIRE(ldk % 8 == 0 && ldk >= C * P * P, VITB_ERR_UNSUPPORTED_SHAPE,
+               "im2col: ldk=%d must be a multiple of 8 and >= %d", ldk, C * P * P);
+  const int gh = H / P, gw = W / P;
+  const long long total = static_cast<long long>(B) * gh * gw * (ldk / 8);
+  im2col_kernel<<<grid_for(total, 16), kThreads, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      img, B, C, H, W, P, gh, gw, ldk, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo));
+  VITB_LAUNCH_CHECK("im2col_kernel");
+  return VITB_OK;
+}
+
+int vitb_cls_rows(float* x, int B, int N, int D, const float* cls, const float* pos, void* stream_) {
+  int st = vitb_check_device();
+  if (st != VITB_OK) return st;
+  if (B == 0) return VITB_OK;
+  VITB_REQUIRE(x && cls && B > 0 && N > 0 && D > 0, VITB_ERR_BAD_ARG, "cls_rows: bad args");
+  cls_rows_kernel<<<grid_for(static_cast<long long>(B) * D), kThreads, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      x, B, N, D, cls, pos);
+  VITB_LAUNCH_CHECK("cls_rows_kernel");
+  return VITB_OK;
+}
+
+int vitb_embed_bwd(const float* dx, int B, int N, int D, float* dpos, float* dcls, float* dbias,
+                   void* dpatch_hi, void* dpatch_lo, void* stream_) {
+  int st = vitb_check_device();
+  if (st != VITB_OK) return st;
+  if (B == 0) return VITB_OK;
+  VITB_REQUIRE(dx && B > 0 && N > 0 && D > 0 && D % 4 == 0, VITB_ERR_BAD_ARG, "embed_bwd: bad args");
+  embed_bwd_kernel<<<grid_for(static_cast<long long>(N) * (D / 4)), kThreads, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      dx, B, N, D, dpos, dcls, dbias, reinterpret_cast<__nv_bfloat16*>(dpatch_hi),
+      reinterpret_cast<__nv_bfloat16*>(dpatch_lo));
+  VITB_LAUNCH_CHECK("embed_bwd_kernel");
+  return VITB_OK;
+}
+
+int vitb_colsum(const void* x, int x_dtype, int rows, int cols, int64_t ld, float* out, void* stream_) {
+  int st = vitb_check_device();
+  if (st != VITB_OK) return st;
+  if (rows == 0 || cols == 0) return VITB_OK;
+  VITB_REQUIRE(x && out && rows > 0 && cols > 0 && cols % 4 == 0 && ld % 4 == 0, VITB_ERR_UNSUPPORTED_SHAPE,
+               "colsum: rows=%d cols=%d ld=%lld (cols, ld must be multiples of 4)", rows, cols, (long long)ld);
+  const int bx = (cols / 4 + 127) / 128;
+  int by = (vitb_num_sms() * 4 + bx - 1) / bx;
+  if (by > (rows + 63) / 64) by = (rows + 63) / 64;
+  if (by < 1) by = 1;
+  dim3 grid(bx, by);
+  if (x_dtype == VITB_BF16)
+    colsum_kernel<true><<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(x, rows, cols, ld, out);
+  else
+    colsum_kernel<false><<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(x, rows, cols, ld, out);
+  VITB_LAUNCH_CHECK("colsum_kernel");
+  return VITB_OK;
+}
+
+int vitb_cross_entropy(const float* logits, const int64_t* labels, int B, int C, float* loss,
+                       float* dlogits, void* stream_) {
+  int st = vitb_check_device();
+  if (st != VITB_OK) return st;
+  VITB_REQUIRE(logits && labels && loss && B > 0 && C > 0, VITB_ERR_BAD_ARG, "cross_entropy: bad args");
+  ce_kernel<<<1, 1024, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      logits, reinterpret_cast<const long long*>(labels), B, C, loss, dlogits);
+  VITB_LAUNCH_CHECK("ce_kernel");
+  return VITB_OK;
+}
+
+int vitb_sgd_momentum(float* p, const float* g, float* m, int64_t n, float lr, float momentum,
+                      float dampening, float weight_decay, int nesterov, int first_step, void* shadow_hi,
+                      void* shadow_lo, void* stream_) {
+  int st = vitb_check_device();
+  if (st != VITB_OK) return st;
+  if (n == 0) return VITB_OK;
+  VITB_REQUIRE(p && g && n > 0 && n % 4 == 0, VITB_ERR_UNSUPPORTED_SHAPE, "sgd: n=%lld must be a multiple of 4",
+               (long long)n);
+  sgd_kernel<<<grid_for(n / 4), kThreads, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      p, g, m, n, lr, momentum, dampening, weight_decay, nesterov, first_step,
+      reinterpret_cast<__nv_bfloat16*>(shadow_hi), reinterpret_cast<__nv_bfloat16*>(shadow_lo));
+  VITB_LAUNCH_CHECK("sgd_kernel");
+  return VITB_OK;
+}
+
+int vitb_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+               float eps, float weight_decay, int step, const float* grad_scale_dev, void* shadow_hi,
+               void* shadow_lo, void* stream_) {
+  int st = vitb_check_device();
+  if (st != VITB_OK) return st;
+  if (n == 0) return VITB_OK;
+  VITB_REQUIRE(p && g && m && v && n > 0 && step >= 1, VITB_ERR_BAD_ARG, "adamw: bad args");
+  const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+  adamw_kernel<<<grid_for(n), kThreads, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2, grad_scale_dev,
+      reinterpret_cast<__nv_bfloat16*>(shadow_hi), reinterpret_cast<__nv_bfloat16*>(shadow_lo));
+  VITB_LAUNCH_CHECK("adamw_kernel");
+  return VITB_OK;
+}
+
+int vitb_sumsq(const float* x, int64_t n, float* out, void* stream_) {
+  int st = vitb_check_device();
+  if (st != VITB_OK) return st;
+  if (n == 0) return VITB_OK;
+  VITB_REQUIRE(x && out && n > 0, VITB_ERR_BAD_ARG, "sumsq: bad args");
+  sumsq_kernel<<<grid_for(n, 4), kThreads, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(x, n, out);
+  VITB_LAUNCH_CHECK("sumsq_kernel");
+  return VITB_OK;
+}
+
+int vitb_clip_coef(const float* sumsq, float max_norm, float* coef, float* norm_out, void* stream_) {
+  int st = vitb_check_device();
+  if (st != VITB_OK) return st;
+  VITB_REQUIRE(sumsq && coef, VITB_ERR_BAD_ARG, "clip_coef: bad args");
+  clip_coef_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(sumsq, max_norm, coef, norm_out);
+  VITB_LAUNCH_CHECK("clip_coef_kernel");
+  return VITB_OK;
+}
+
+}  // extern "C"

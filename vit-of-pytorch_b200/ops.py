@@ -87,3 +87,218 @@ def gemm(A, B, *, a_mn=False, b_mn=False, out=None, out_dtype=torch.bfloat16, bi
         p.aux, p.ldaux = aux.data_ptr(), aux.stride(0)
     L.check(L._vitb_gemm(C.byref(p), L.stream_ptr(out.device)), "vitb_gemm")
     return out
+
+
+# --------------------------------------------------------------------------------------------------
+# LayerNorm
+# --------------------------------------------------------------------------------------------------
+def layernorm_fwd(x, gamma, beta, eps, *, want_f32=False, want_bf16=True, want_lo=False):
+    """x: [rows, D] (row stride free, fp32 or bf16).  Returns (y_f32|None, y_bf16|None, y_lo|None, mean, rstd)."""
+    L.require_cuda(x, gamma, beta)
+    _check_2d_rowmajor(x, "x")
+    rows, D = x.shape
+    dev = x.device
+    yf = torch.empty((rows, D), dtype=torch.float32, device=dev) if want_f32 else None
+    yh = torch.empty((rows, D), dtype=torch.bfloat16, device=dev) if want_bf16 else None
+    yl = torch.empty((rows, D), dtype=torch.bfloat16, device=dev) if want_lo else None
+    mean = torch.empty(rows, dtype=torch.float32, device=dev)
+    rstd = torch.empty(rows, dtype=torch.float32, device=dev)
+    L.check(L._vitb_layernorm_fwd(L.ptr(x), L.dtype_code(x), x.stride(0), rows, D, L.ptr(gamma), L.ptr(beta),
+                                  float(eps), L.ptr(yf), L.ptr(yh), L.ptr(yl), L.ptr(mean), L.ptr(rstd),
+                                  L.stream_ptr(dev)), "vitb_layernorm_fwd")
+    return yf, yh, yl, mean, rstd
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, *, dres=None, want_f32=True, want_bf16=False, want_lo=False,
+                  dgamma=None, dbeta=None, dcolsum=None, dx_out=None):
+    """dx = LN'(dy) + dres.  dgamma/dbeta/dcolsum ([D] fp32) are accumulated in place when given."""
+    L.require_cuda(dy, x, mean, rstd, gamma, dres)
+    _check_2d_rowmajor(x, "x")
+    rows, D = x.shape
+    if not dy.is_contiguous() or tuple(dy.shape) != (rows, D):
+        raise L.VitbError("layernorm_bwd: dy must be contiguous [rows, D]")
+    if x.dtype != torch.float32:
+        raise L.VitbError("layernorm_bwd: x must be fp32")
+    dev = x.device
+    dxf = dx_out if dx_out is not None else (torch.empty((rows, D), dtype=torch.float32, device=dev) if want_f32 else None)
+    dxh = torch.empty((rows, D), dtype=torch.bfloat16, device=dev) if want_bf16 else None
+    dxl = torch.empty((rows, D), dtype=torch.bfloat16, device=dev) if want_lo else None
+    if dres is not None:
+        _check_2d_rowmajor(dres, "dres")
+    L.check(L._vitb_layernorm_bwd(L.ptr(dy), L.dtype_code(dy), L.ptr(x), x.stride(0), L.ptr(mean), L.ptr(rstd),
+                                  L.ptr(gamma), rows, D, L.ptr(dres), dres.stride(0) if dres is not None else 0,
+                                  L.ptr(dxf), dxf.stride(0) if dxf is not None else 0, L.ptr(dxh), L.ptr(dxl),
+                                  L.ptr(dgamma), L.ptr(dbeta), L.ptr(dcolsum), L.stream_ptr(dev)),
+            "vitb_layernorm_bwd")
+    return dxf, dxh, dxl
+
+
+# --------------------------------------------------------------------------------------------------
+# attention
+# --------------------------------------------------------------------------------------------------
+def _head_strides(t, H, dh, what):
+    """t: [B, N, H*dh]-shaped view (last dim contiguous, any row/batch stride)."""
+    if t.dim() != 3 or t.stride(2) != 1 or t.shape[2] != H * dh:
+        raise L.VitbError("%s must be a [B, N, H*dh] view with unit inner stride" % what)
+    return t.stride(0), t.stride(1)
+
+
+def attn_supported_tc(dh, Nq, Nk, dtype):
+    return dtype == torch.bfloat16 and bool(L.vitb_attn_supported_tc(dh, Nq, Nk))
+
+
+def _attn_params(q, k, v, o, lse, H):
+    B, Nq, HD = q.shape
+    Nk = k.shape[1]
+    dh = HD // H
+    p = L.AttnParams()
+    p.struct_bytes = C.sizeof(L.AttnParams)
+    p.dtype = L.dtype_code(q)
+    p.B, p.H, p.Nq, p.Nk, p.head_dim = B, H, Nq, Nk, dh
+    p.q, p.k, p.v, p.o, p.lse = q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr()
+    p.q_batch_stride, p.q_row_stride = _head_strides(q, H, dh, "q")
+    p.k_batch_stride, p.k_row_stride = _head_strides(k, H, dh, "k")
+    p.v_batch_stride, p.v_row_stride = _head_strides(v, H, dh, "v")
+    p.o_batch_stride, p.o_row_stride = _head_strides(o, H, dh, "o")
+    return p
+
+
+def attn_fwd(q, k, v, H, *, use_tc=None):
+    """q: [B,Nq,H*dh], k/v: [B,Nk,H*dh] views (same dtype).  Returns (o [B,Nq,H*dh], lse [B,H,Nq])."""
+    L.require_cuda(q, k, v)
+    B, Nq, HD = q.shape
+    dh = HD // H
+    if use_tc is None:
+        use_tc = attn_supported_tc(dh, Nq, k.shape[1], q.dtype)
+    o = torch.empty((B, Nq, HD), dtype=q.dtype, device=q.device)
+    lse = torch.empty((B, H, Nq), dtype=torch.float32, device=q.device)
+    p = _attn_params(q, k, v, o, lse, H)
+    fn = L._vitb_attn_fwd_tc if use_tc else L._vitb_attn_fwd_simt
+    L.check(fn(C.byref(p), L.stream_ptr(q.device)), "vitb_attn_fwd")
+    return o, lse
+
+
+def attn_bwd(dout, q, k, v, o, lse, H, *, use_tc=None, dq=None, dk=None, dv=None):
+    """Returns (dq, dk, dv).  tc: bf16 gradients; simt: fp32 gradients.  dq/dk/dv may be strided views."""
+    L.require_cuda(dout, q, k, v, o, lse)
+    B, Nq, HD = q.shape
+    Nk = k.shape[1]
+    dh = HD // H
+    if use_tc is None:
+        use_tc = attn_supported_tc(dh, Nq, Nk, q.dtype)
+    gdt = torch.bfloat16 if use_tc else torch.float32
+    if dq is None:
+        dq = torch.zeros((B, Nq, HD), dtype=gdt, device=q.device) if not use_tc else torch.empty((B, Nq, HD), dtype=gdt, device=q.device)
+    elif not use_tc:
+        dq.zero_()
+    if dk is None:
+        dk = torch.empty((B, Nk, HD), dtype=gdt, device=q.device)
+    if dv is None:
+        dv = torch.empty((B, Nk, HD), dtype=gdt, device=q.device)
+    for t in (dq, dk, dv):
+        if t.dtype != gdt:
+            raise L.VitbError("attn_bwd: gradient buffers must be %s" % gdt)
+    p = _attn_params(q, k, v, o, lse, H)
+    p.dout = dout.data_ptr()
+    p.do_batch_stride, p.do_row_stride = _head_strides(dout, H, dh, "dout")
+    p.dq, p.dk, p.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
+    p.dq_batch_stride, p.dq_row_stride = _head_strides(dq, H, dh, "dq")
+    p.dk_batch_stride, p.dk_row_stride = _head_strides(dk, H, dh, "dk")
+    p.dv_batch_stride, p.dv_row_stride = _head_strides(dv, H, dh, "dv")
+    fn = L._vitb_attn_bwd_tc if use_tc else L._vitb_attn_bwd_simt
+    L.check(fn(C.byref(p), L.stream_ptr(q.device)), "vitb_attn_bwd")
+    return dq, dk, dv
+
+
+# --------------------------------------------------------------------------------------------------
+# operand preparation / embedding stage
+# --------------------------------------------------------------------------------------------------
+def cast_split(x, *, want_lo=False, hi=None, lo=None):
+    L.require_cuda(x)
+    if x.dtype != torch.float32 or not x.is_contiguous():
+        raise L.VitbError("cast_split: x must be contiguous fp32")
+    if hi is None:
+        hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    if want_lo and lo is None:
+        lo = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    L.check(L._vitb_cast_split(L.ptr(x), x.numel(), L.ptr(hi), L.ptr(lo), L.stream_ptr(x.device)), "vitb_cast_split")
+    return hi, lo
+
+
+def im2col(img, P, *, want_lo=False):
+    L.require_cuda(img)
+    if img.dtype != torch.float32 or not img.is_contiguous() or img.dim() != 4:
+        raise L.VitbError("im2col: img must be contiguous fp32 [B,C,H,W]")
+    B, Cin, H, W = img.shape
+    K = Cin * P * P
+    ldk = (K + 7) // 8 * 8
+    rows = B * (H // P) * (W // P)
+    hi = torch.empty((rows, ldk), dtype=torch.bfloat16, device=img.device)
+    lo = torch.empty((rows, ldk), dtype=torch.bfloat16, device=img.device) if want_lo else None
+    L.check(L._vitb_im2col(L.ptr(img), B, Cin, H, W, P, ldk, L.ptr(hi), L.ptr(lo), L.stream_ptr(img.device)), "vitb_im2col")
+    return hi, lo
+
+
+def cls_rows(x, cls, pos):
+    """x: [B,N,D] fp32 contiguous; writes x[:,0,:] = cls + pos[0]."""
+    L.require_cuda(x, cls, pos)
+    B, N, D = x.shape
+    L.check(L._vitb_cls_rows(L.ptr(x), B, N, D, L.ptr(cls), L.ptr(pos), L.stream_ptr(x.device)), "vitb_cls_rows")
+
+
+def embed_bwd(dx, *, dpos=None, dcls=None, dbias=None, want_patch=True, want_lo=False):
+    L.require_cuda(dx)
+    if dx.dtype != torch.float32 or not dx.is_contiguous() or dx.dim() != 3:
+        raise L.VitbError("embed_bwd: dx must be contiguous fp32 [B,N,D]")
+    B, N, D = dx.shape
+    hi = torch.empty((B * (N - 1), D), dtype=torch.bfloat16, device=dx.device) if want_patch else None
+    lo = torch.empty((B * (N - 1), D), dtype=torch.bfloat16, device=dx.device) if (want_patch and want_lo) else None
+    L.check(L._vitb_embed_bwd(L.ptr(dx), B, N, D, L.ptr(dpos), L.ptr(dcls), L.ptr(dbias), L.ptr(hi), L.ptr(lo),
+                              L.stream_ptr(dx.device)), "vitb_embed_bwd")
+    return hi, lo
+
+
+def colsum(x, out):
+    """out[c] += sum_r x[r,c]."""
+    L.require_cuda(x, out)
+    _check_2d_rowmajor(x, "x")
+    L.check(L._vitb_colsum(L.ptr(x), L.dtype_code(x), x.shape[0], x.shape[1], x.stride(0), L.ptr(out),
+                           L.stream_ptr(x.device)), "vitb_colsum")
+    return out
+
+
+def cross_entropy(logits, labels, *, want_grad=True):
+    L.require_cuda(logits, labels)
+    if logits.dtype != torch.float32 or not logits.is_contiguous() or labels.dtype != torch.int64:
+        raise L.VitbError("cross_entropy: logits fp32 contiguous [B,C], labels int64 [B]")
+    B, Ccls = logits.shape
+    loss = torch.empty((), dtype=torch.float32, device=logits.device)
+    dl = torch.empty_like(logits) if want_grad else None
+    L.check(L._vitb_cross_entropy(L.ptr(logits), L.ptr(labels), B, Ccls, L.ptr(loss), L.ptr(dl),
+                                  L.stream_ptr(logits.device)), "vitb_cross_entropy")
+    return loss, dl
+
+
+def sgd_momentum(p, g, m, lr, momentum, *, dampening=0.0, weight_decay=0.0, nesterov=False, first_step=False,
+                 shadow_hi=None, shadow_lo=None):
+    L.require_cuda(p, g, m)
+    L.check(L._vitb_sgd_momentum(L.ptr(p), L.ptr(g), L.ptr(m), p.numel(), float(lr), float(momentum),
+                                 float(dampening), float(weight_decay), int(nesterov), int(first_step),
+                                 L.ptr(shadow_hi), L.ptr(shadow_lo), L.stream_ptr(p.device)), "vitb_sgd_momentum")
+
+
+def adamw(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, *, grad_scale=None, shadow_hi=None, shadow_lo=None):
+    L.require_cuda(p, g, m, v)
+    L.check(L._vitb_adamw(L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), p.numel(), float(lr), float(beta1), float(beta2),
+                          float(eps), float(weight_decay), int(step), L.ptr(grad_scale), L.ptr(shadow_hi),
+                          L.ptr(shadow_lo), L.stream_ptr(p.device)), "vitb_adamw")
+
+
+def sumsq(x, out):
+    L.require_cuda(x, out)
+    L.check(L._vitb_sumsq(L.ptr(x), x.numel(), L.ptr(out), L.stream_ptr(x.device)), "vitb_sumsq")
+
+
+def clip_coef(sumsq_t, max_norm, coef, norm_out=None):
+    L.check(L._vitb_clip_coef(L.ptr(sumsq_t), float(max_norm), L.ptr(coef), L.ptr(norm_out),
+                              L.stream_ptr(coef.device)), "vitb_clip_coef")
