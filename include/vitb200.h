@@ -80,7 +80,7 @@ typedef struct vitb_gemm_params {
   int64_t ldd;
   int32_t d_dtype;
   int32_t accumulate; /* 1: D += v via fp32 atomics (wgrad / split-K) */
-  void* D2; /* optional bf16 pre-activation output for VITB_EPI_GELU */
+  void* D2; /* optional pre-activation output for VITB_EPI_GELU, same dtype as D */
   int64_t ldd2;
   const float* bias; /* [N] or NULL */
   const float* row_bias; /* [ceil(M/row_bias_group), N] or NULL */
@@ -90,7 +90,7 @@ typedef struct vitb_gemm_params {
   int64_t ldr;
   int32_t r_dtype;
   int32_t _pad0;
-  const void* aux; /* bf16 [M,N] for VITB_EPI_GELU_BWD */
+  const void* aux; /* [M,N] pre-activation for VITB_EPI_GELU_BWD, same dtype as D */
   int64_t ldaux;
 } vitb_gemm_params;
 

@@ -164,8 +164,9 @@ def test_im2col_matches_conv2d(P):
     cols = hi.float() + lo.float()
     assert cols.shape[1] % 8 == 0 and cols.shape[1] >= K
     assert (cols[:, K:] == 0).all()
-    ref = torch.nn.functional.conv2d(img, w, stride=P).permute(0, 2, 3, 1).reshape(-1, D)
-    out = cols[:, :K] @ w.reshape(D, K).t()
+    # fp64 reference: torch's fp32 conv2d / matmul may use TF32 on this GPU
+    ref = torch.nn.functional.conv2d(img.double(), w.double(), stride=P).permute(0, 2, 3, 1).reshape(-1, D)
+    out = cols[:, :K].double() @ w.double().reshape(D, K).t()
     assert rel_l2(out, ref) < 2e-5
 
 

@@ -27,7 +27,8 @@ constexpr int BK = 64;
 constexpr int kThreads = 256;
 constexpr int kEpiWarp0 = 4;
 constexpr int A_BYTES = BM * BK * 2;                 // 16 KiB
-constexpr int kStagingFloats = 32 * 33;              // per epilogue warp, padded transpose tile
+constexpr int kStgStride = 36;                       // floats per staged row: 16B-aligned, conflict-free
+constexpr int kStagingFloats = 32 * kStgStride;      // per epilogue warp
 constexpr int kStagingBytes = 4 * kStagingFloats * 4;
 
 template <int BN>
@@ -62,6 +63,7 @@ struct GemmDev {
   int r_bf16;
   const void* aux;
   long long ldaux;
+  int vec_ok;  // 128-bit epilogue path usable (set by the host from shapes and alignment)
 };
 
 struct TileCoord {
@@ -77,6 +79,141 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmDev& p, int tile) {
   t.g0 = static_cast<int>((static_cast<long long>(split) * p.total_kblocks) / p.split_k);
   t.g1 = static_cast<int>((static_cast<long long>(split + 1) * p.total_kblocks) / p.split_k);
   return t;
+}
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_shared_f1(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+
+// Vectorised epilogue of one staged 32x32 fp32 sub-tile: lane -> (row%4 = lane/8, 4 columns = lane%8),
+// 8 steps of 4 rows; every global access is a 16-byte (fp32) or 8-byte (bf16) piece of a row segment
+// that the 8 lanes of a row cover contiguously.  All side loads of the 8 steps are issued up front.
+//   RES: 0 none, 1 fp32 residual, 2 bf16 residual.   ACC: fp32 red.global accumulation.
+template <bool OUT_BF16, int EPI, int RES, bool ACC>
+__device__ __forceinline__ void epi_vec(const GemmDev& p, uint32_t stg, int lane, int row_base, int col0,
+                                        bool lead_split) {
+  const int rsub = lane >> 3;
+  const int c4 = (lane & 7) * 4;
+  const int col = col0 + c4;
+  if (col >= p.N) return;
+  float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p.bias != nullptr && lead_split) bv = *reinterpret_cast<const float4*>(p.bias + col);
+  float4 side[8];
+  if constexpr (RES != 0 || EPI == VITB_EPI_GELU_BWD) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int m = row_base + it * 4 + rsub;
+      side[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m < p.M) {
+        if constexpr (EPI == VITB_EPI_GELU_BWD) {
+          if constexpr (OUT_BF16) {
+            const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.aux) +
+                                                            static_cast<long long>(m) * p.ldaux + col);
+            side[it] = make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
+          } else {
+            side[it] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.aux) +
+                                                        static_cast<long long>(m) * p.ldaux + col);
+          }
+        } else if constexpr (RES == 1) {
+          if (lead_split)
+            side[it] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.residual) +
+                                                        static_cast<long long>(m) * p.ldr + col);
+        } else {
+          if (lead_split) {
+            const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) +
+                                                            static_cast<long long>(m) * p.ldr + col);
+            side[it] = make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int rl = it * 4 + rsub;
+    const int m = row_base + rl;
+    if (m >= p.M) continue;
+    float4 v = ld_shared_f4(stg + rl * (kStgStride * 4) + c4 * 4);
+    v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+    if constexpr (EPI == VITB_EPI_GELU) {
+      if (p.D2 != nullptr) {
+        if constexpr (OUT_BF16) {
+          uint2 z;
+          z.x = pack_bf16x2(v.x, v.y); z.y = pack_bf16x2(v.z, v.w);
+          *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.D2) + static_cast<long long>(m) * p.ldd2 + col) = z;
+        } else {
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.D2) + static_cast<long long>(m) * p.ldd2 + col) = v;
+        }
+      }
+      v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
+    } else if constexpr (EPI == VITB_EPI_GELU_BWD) {
+      v.x *= gelu_erf_grad(side[it].x); v.y *= gelu_erf_grad(side[it].y);
+      v.z *= gelu_erf_grad(side[it].z); v.w *= gelu_erf_grad(side[it].w);
+    }
+    if constexpr (RES != 0) { v.x += side[it].x; v.y += side[it].y; v.z += side[it].z; v.w += side[it].w; }
+    if constexpr (OUT_BF16) {
+      uint2 o;
+      o.x = pack_bf16x2(v.x, v.y); o.y = pack_bf16x2(v.z, v.w);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.D) + static_cast<long long>(m) * p.ldd + col) = o;
+    } else {
+      float* dst = reinterpret_cast<float*>(p.D) + static_cast<long long>(m) * p.ldd + col;
+      if constexpr (ACC) atomicAdd(reinterpret_cast<float4*>(dst), v);
+      else *reinterpret_cast<float4*>(dst) = v;
+    }
+  }
+}
+
+// Scalar epilogue with every option (row bias, patch-embedding row remap, odd widths): lane == column.
+__device__ __noinline__ void epi_generic(const GemmDev& p, uint32_t stg, int lane, int row_base, int col0,
+                                         bool lead_split) {
+  const int col = col0 + lane;
+  if (col >= p.N) return;
+  const float bv = (p.bias != nullptr && lead_split) ? p.bias[col] : 0.f;
+  for (int rr = 0; rr < 32; ++rr) {
+    const int m = row_base + rr;
+    if (m >= p.M) break;
+    float v = ld_shared_f1(stg + rr * (kStgStride * 4) + lane * 4) + bv;
+    if (p.row_bias != nullptr && lead_split)
+      v += p.row_bias[static_cast<long long>(m / p.row_bias_group) * p.N + col];
+    if (p.epilogue == VITB_EPI_GELU) {
+      if (p.D2 != nullptr) {
+        if (p.d_bf16) reinterpret_cast<__nv_bfloat16*>(p.D2)[static_cast<long long>(m) * p.ldd2 + col] = __float2bfloat16(v);
+        else reinterpret_cast<float*>(p.D2)[static_cast<long long>(m) * p.ldd2 + col] = v;
+      }
+      v = gelu_erf(v);
+    } else if (p.epilogue == VITB_EPI_GELU_BWD) {
+      const long long ai = static_cast<long long>(m) * p.ldaux + col;
+      v *= gelu_erf_grad(p.d_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.aux)[ai])
+                                  : reinterpret_cast<const float*>(p.aux)[ai]);
+    }
+    int om = m, rm = m;
+    if (p.row_remap_group > 0) {
+      om = m + m / p.row_remap_group + 1;
+      rm = m % p.row_remap_group + 1;
+    }
+    if (p.residual != nullptr && lead_split) {
+      const long long ri = static_cast<long long>(rm) * p.ldr + col;
+      v += p.r_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.residual)[ri])
+                    : reinterpret_cast<const float*>(p.residual)[ri];
+    }
+    if (p.d_bf16) {
+      reinterpret_cast<__nv_bfloat16*>(p.D)[static_cast<long long>(om) * p.ldd + col] = __float2bfloat16(v);
+    } else {
+      float* dst = reinterpret_cast<float*>(p.D) + static_cast<long long>(om) * p.ldd + col;
+      if (p.accumulate) atomicAdd(dst, v);
+      else *dst = v;
+    }
+  }
 }
 
 template <int BN, bool A_MN, bool B_MN>
@@ -202,11 +339,11 @@ vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   } else if (warp >= kEpiWarp0) {
     // =============================== epilogue ===============================
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
-    float* stg = staging + (warp - kEpiWarp0) * kStagingFloats;
+    const uint32_t stg = smem_u32(staging) + static_cast<uint32_t>((warp - kEpiWarp0) * kStagingFloats * 4);
     int acc = 0;
     uint32_t acc_phase = 0;
-    const bool has_gelu = p.epilogue == VITB_EPI_GELU;
-    const bool has_gelu_bwd = p.epilogue == VITB_EPI_GELU_BWD;
+    const bool vec_ok = p.vec_ok != 0;
+    const int res_mode = p.residual == nullptr ? 0 : (p.r_bf16 ? 2 : 1);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile);
       const int n0 = t.n_blk * BN;
@@ -219,112 +356,33 @@ vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       for (int c = 0; c < BN / 32; ++c) {
         const int col0 = n0 + c * 32;
         if (col0 >= p.N) break;
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
-                               static_cast<uint32_t>(acc * BN + c * 32), r);
-        tmem_ld_wait();
+        {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                                 static_cast<uint32_t>(acc * BN + c * 32), r);
+          tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(r[j]);
+          for (int j = 0; j < 8; ++j)
+            st_shared_v4(stg + lane * (kStgStride * 4) + j * 16, r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+        }
         __syncwarp();
-        if (!p.d_bf16) {
-          // lane == column; each warp instruction touches 128 contiguous bytes of one row
-          const int col = col0 + lane;
-          const bool col_ok = col < p.N;
-          const float bv = (p.bias != nullptr && col_ok && lead_split) ? p.bias[col] : 0.f;
-#pragma unroll 4
-          for (int rr = 0; rr < 32; ++rr) {
-            const int m = row_base + rr;
-            if (m >= p.M) break;
-            if (!col_ok) continue;
-            float v = stg[rr * 33 + lane] + bv;
-            if (p.row_bias != nullptr && lead_split)
-              v += p.row_bias[static_cast<long long>(m / p.row_bias_group) * p.N + col];
-            if (has_gelu) {
-              if (p.D2 != nullptr)
-                reinterpret_cast<__nv_bfloat16*>(p.D2)[static_cast<long long>(m) * p.ldd2 + col] =
-                    __float2bfloat16(v);
-              v = gelu_erf(v);
-            } else if (has_gelu_bwd) {
-              const float z = __bfloat162float(
-                  reinterpret_cast<const __nv_bfloat16*>(p.aux)[static_cast<long long>(m) * p.ldaux + col]);
-              v *= gelu_erf_grad(z);
-            }
-            int om = m, rm = m;
-            if (p.row_remap_group > 0) {
-              om = m + m / p.row_remap_group + 1;
-              rm = m % p.row_remap_group + 1;
-            }
-            if (p.residual != nullptr && lead_split) {
-              const long long ri = static_cast<long long>(rm) * p.ldr + col;
-              v += p.r_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.residual)[ri])
-                            : reinterpret_cast<const float*>(p.residual)[ri];
-            }
-            float* dst = reinterpret_cast<float*>(p.D) + static_cast<long long>(om) * p.ldd + col;
-            if (p.accumulate) atomicAdd(dst, v);
-            else *dst = v;
+        if (vec_ok) {
+          if (p.accumulate) epi_vec<false, VITB_EPI_NONE, 0, true>(p, stg, lane, row_base, col0, lead_split);
+          else if (p.d_bf16) {
+            if (p.epilogue == VITB_EPI_GELU) epi_vec<true, VITB_EPI_GELU, 0, false>(p, stg, lane, row_base, col0, lead_split);
+            else if (p.epilogue == VITB_EPI_GELU_BWD) epi_vec<true, VITB_EPI_GELU_BWD, 0, false>(p, stg, lane, row_base, col0, lead_split);
+            else if (res_mode == 0) epi_vec<true, VITB_EPI_NONE, 0, false>(p, stg, lane, row_base, col0, lead_split);
+            else if (res_mode == 1) epi_vec<true, VITB_EPI_NONE, 1, false>(p, stg, lane, row_base, col0, lead_split);
+            else epi_vec<true, VITB_EPI_NONE, 2, false>(p, stg, lane, row_base, col0, lead_split);
+          } else {
+            if (p.epilogue == VITB_EPI_GELU) epi_vec<false, VITB_EPI_GELU, 0, false>(p, stg, lane, row_base, col0, lead_split);
+            else if (p.epilogue == VITB_EPI_GELU_BWD) epi_vec<false, VITB_EPI_GELU_BWD, 0, false>(p, stg, lane, row_base, col0, lead_split);
+            else if (res_mode == 0) epi_vec<false, VITB_EPI_NONE, 0, false>(p, stg, lane, row_base, col0, lead_split);
+            else if (res_mode == 1) epi_vec<false, VITB_EPI_NONE, 1, false>(p, stg, lane, row_base, col0, lead_split);
+            else epi_vec<false, VITB_EPI_NONE, 2, false>(p, stg, lane, row_base, col0, lead_split);
           }
         } else {
-          // bf16 output: lane -> (row parity, column pair); 2 rows x 64 contiguous bytes per instruction
-          const int half = lane >> 4;
-          const int cl = (lane & 15) * 2;
-          const int col = col0 + cl;
-          const bool c0_ok = col < p.N, c1_ok = (col + 1) < p.N;
-          float b0 = 0.f, b1 = 0.f;
-          if (p.bias != nullptr) {
-            if (c0_ok) b0 = p.bias[col];
-            if (c1_ok) b1 = p.bias[col + 1];
-          }
-#pragma unroll 4
-          for (int rr = 0; rr < 32; rr += 2) {
-            const int rl = rr + half;
-            const int m = row_base + rl;
-            if (m >= p.M || !c0_ok) continue;
-            float v0 = stg[rl * 33 + cl] + b0;
-            float v1 = stg[rl * 33 + cl + 1] + b1;
-            if (p.row_bias != nullptr) {
-              const float* rb = p.row_bias + static_cast<long long>(m / p.row_bias_group) * p.N + col;
-              v0 += rb[0];
-              if (c1_ok) v1 += rb[1];
-            }
-            if (has_gelu) {
-              if (p.D2 != nullptr) {
-                __nv_bfloat16* z = reinterpret_cast<__nv_bfloat16*>(p.D2) + static_cast<long long>(m) * p.ldd2 + col;
-                if (c1_ok) *reinterpret_cast<uint32_t*>(z) = pack_bf16x2(v0, v1);
-                else z[0] = __float2bfloat16(v0);
-              }
-              v0 = gelu_erf(v0);
-              v1 = gelu_erf(v1);
-            } else if (has_gelu_bwd) {
-              const __nv_bfloat16* z = reinterpret_cast<const __nv_bfloat16*>(p.aux) + static_cast<long long>(m) * p.ldaux + col;
-              if (c1_ok) {
-                const uint32_t zz = *reinterpret_cast<const uint32_t*>(z);
-                v0 *= gelu_erf_grad(bf16_lo(zz));
-                v1 *= gelu_erf_grad(bf16_hi(zz));
-              } else {
-                v0 *= gelu_erf_grad(__bfloat162float(z[0]));
-              }
-            }
-            int om = m, rm = m;
-            if (p.row_remap_group > 0) {
-              om = m + m / p.row_remap_group + 1;
-              rm = m % p.row_remap_group + 1;
-            }
-            if (p.residual != nullptr) {
-              const long long ri = static_cast<long long>(rm) * p.ldr + col;
-              if (p.r_bf16) {
-                const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + ri;
-                v0 += __bfloat162float(rp[0]);
-                if (c1_ok) v1 += __bfloat162float(rp[1]);
-              } else {
-                const float* rp = reinterpret_cast<const float*>(p.residual) + ri;
-                v0 += rp[0];
-                if (c1_ok) v1 += rp[1];
-              }
-            }
-            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.D) + static_cast<long long>(om) * p.ldd + col;
-            if (c1_ok) *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(v0, v1);
-            else dst[0] = __float2bfloat16(v0);
-          }
+          epi_generic(p, stg, lane, row_base, col0, lead_split);
         }
         __syncwarp();
       }
@@ -379,11 +437,6 @@ extern "C" int vitb_gemm(const vitb_gemm_params* p, void* stream_) {
                "vitb_gemm: GELU_BWD needs aux");
   VITB_REQUIRE(!(p->accumulate && p->epilogue != VITB_EPI_NONE && p->split_k != 1), VITB_ERR_BAD_ARG,
                "vitb_gemm: a non-linear epilogue cannot be split along K");
-  if (p->d_dtype == VITB_BF16) {
-    VITB_REQUIRE(p->ldd % 2 == 0, VITB_ERR_UNSUPPORTED_SHAPE, "vitb_gemm: bf16 D needs even ldd");
-    VITB_REQUIRE(p->D2 == nullptr || p->ldd2 % 2 == 0, VITB_ERR_UNSUPPORTED_SHAPE, "vitb_gemm: even ldd2");
-    VITB_REQUIRE(p->aux == nullptr || p->ldaux % 2 == 0, VITB_ERR_UNSUPPORTED_SHAPE, "vitb_gemm: even ldaux");
-  }
   VITB_REQUIRE(p->row_bias == nullptr || p->row_bias_group > 0, VITB_ERR_BAD_ARG,
                "vitb_gemm: row_bias_group must be > 0");
 
@@ -437,6 +490,17 @@ extern "C" int vitb_gemm(const vitb_gemm_params* p, void* stream_) {
   d.r_bf16 = p->r_dtype == VITB_BF16;
   d.aux = p->aux;
   d.ldaux = p->ldaux;
+  {
+    auto al = [](const void* q, uintptr_t a) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) % a) == 0; };
+    const uintptr_t d_al = d.d_bf16 ? 8 : 16;
+    d.vec_ok = (p->N % 4 == 0) && (p->ldd % 4 == 0) && al(p->D, d_al) && p->row_bias == nullptr &&
+               p->row_remap_group == 0 && al(p->bias, 16) &&
+               (p->residual == nullptr || (p->ldr % 4 == 0 && al(p->residual, d.r_bf16 ? 8 : 16))) &&
+               (p->D2 == nullptr || (p->ldd2 % 4 == 0 && al(p->D2, d_al))) &&
+               (p->aux == nullptr || (p->ldaux % 4 == 0 && al(p->aux, d_al))) &&
+               !(p->accumulate && (p->residual != nullptr || p->epilogue != VITB_EPI_NONE)) &&
+               !(p->epilogue != VITB_EPI_NONE && p->residual != nullptr);
+  }
 
   CUtensorMap tm[6];
   for (int s = 0; s < 3; ++s) {

@@ -67,6 +67,8 @@ def gemm(A, B, *, a_mn=False, b_mn=False, out=None, out_dtype=torch.bfloat16, bi
     p.accumulate = int(accumulate)
     if d2 is not None:
         _check_2d_rowmajor(d2, "d2")
+        if d2.dtype != out.dtype:
+            raise L.VitbError("gemm: d2 must have the dtype of the output")
         p.D2, p.ldd2 = d2.data_ptr(), d2.stride(0)
     if bias is not None:
         if bias.dtype != torch.float32 or bias.numel() != N or not bias.is_contiguous():
@@ -82,8 +84,8 @@ def gemm(A, B, *, a_mn=False, b_mn=False, out=None, out_dtype=torch.bfloat16, bi
         p.residual, p.ldr, p.r_dtype = residual.data_ptr(), residual.stride(0), L.dtype_code(residual)
     if aux is not None:
         _check_2d_rowmajor(aux, "aux")
-        if aux.dtype != torch.bfloat16:
-            raise L.VitbError("gemm: aux must be bf16")
+        if aux.dtype != out.dtype:
+            raise L.VitbError("gemm: aux must have the dtype of the output")
         p.aux, p.ldaux = aux.data_ptr(), aux.stride(0)
     L.check(L._vitb_gemm(C.byref(p), L.stream_ptr(out.device)), "vitb_gemm")
     return out
