@@ -35,6 +35,8 @@ extern "C" {
 int vitb_version(void);
 int vitb_last_error(char* buf, size_t n);
 int vitb_device_check(void);
+/* sizeof of an ABI struct as compiled into the library: 0 = vitb_gemm_params, 1 = vitb_attn_params. */
+int vitb_struct_size(int which);
 
 /* ---- dense contraction (tcgen05 / TMEM / TMA) ------------------------------------------------
  * D[M,N] = epilogue( sum_seg  A_seg[M,K_seg] * B_seg[N,K_seg]^T )
@@ -168,6 +170,9 @@ int vitb_cls_rows(float* x, int B, int N, int D, const float* cls, const float* 
  * dbias [D] += sum over patch rows; dpatch [B*(N-1), D] = bf16 patch rows (wgrad operand). */
 int vitb_embed_bwd(const float* dx, int B, int N, int D, float* dpos, float* dcls, float* dbias,
                    void* dpatch_hi, void* dpatch_lo, void* stream);
+/* out = dy * gelu_erf'(z), elementwise over n values of dtype f32 or bf16 (backward of nn.GELU(),
+ * src/model.py:33,44; res-vit/model.py:154,158,160,312). */
+int vitb_gelu_bwd(const void* dy, const void* z, void* out, int64_t n, int dtype, void* stream);
 /* out[c] += sum_r x[r,c]  (bias gradients). */
 int vitb_colsum(const void* x, int x_dtype, int rows, int cols, int64_t ld, float* out, void* stream);
 

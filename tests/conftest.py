@@ -35,3 +35,11 @@ def rel_l2(a, b):
     a = a.double().flatten()
     b = b.double().flatten()
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def grad_close(a, b, rtol, atol=1e-7):
+    """||a-b|| <= rtol*||b|| + atol*sqrt(numel): mathematically-zero gradients (e.g. the key bias, to which
+    softmax is invariant) carry only rounding noise, so a pure relative test is meaningless for them."""
+    a = a.double().flatten()
+    b = b.double().flatten()
+    return float((a - b).norm()) <= rtol * float(b.norm()) + atol * (b.numel() ** 0.5)

@@ -1,0 +1,172 @@
+"""GPU parity of the reference-shaped modules (vitb200.VisionTransformer & co.) against the oracle
+(oracle/vit_oracle.py, pinned to the real reference by tests/test_oracle.py) and against the committed
+golden vectors produced by the unmodified reference.
+
+Tolerances (BASELINE.json north_star): fp32 mode — logits and gradients within rel 1e-4;
+bf16 mode — logits within 2e-2 of the fp32 reference."""
+import os
+import sys
+
+import pytest
+import torch
+
+from conftest import grad_close, rel_l2
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import vit_oracle  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def _model_from(cfg, sd):
+    import vitb200
+    m = vitb200.VisionTransformer(**cfg)
+    m.load_state_dict(sd)
+    return m.cuda().train()
+
+
+def _run(m, img, labels, mode):
+    import vitb200
+    with vitb200.precision(mode):
+        m.zero_grad(set_to_none=True)
+        logits = m(img.cuda())
+        loss = vitb200.functional.cross_entropy(logits, labels.cuda())
+        loss.backward()
+    torch.cuda.synchronize()
+    return logits.detach().cpu(), loss.detach().cpu(), {k: p.grad.detach().cpu() for k, p in m.named_parameters()}
+
+
+def test_tiny_fp32_mode_matches_reference_golden():
+    g = torch.load(os.path.join(GOLD, "vit_tiny.pt"))
+    m = _model_from(g["cfg"], g["state_dict"])
+    logits, loss, grads = _run(m, g["img"], g["labels"], "fp32")
+    assert logits.dtype == torch.float32
+    assert rel_l2(logits, g["logits"]) < 1e-4
+    assert abs(float(loss) - float(g["loss"])) < 1e-4 * abs(float(g["loss"]))
+    for k, ref in g["grads"].items():
+        assert grad_close(grads[k], ref, 1e-4), (k, rel_l2(grads[k], ref))
+
+
+def test_tiny_bf16_mode_logits_within_2e2():
+    g = torch.load(os.path.join(GOLD, "vit_tiny.pt"))
+    m = _model_from(g["cfg"], g["state_dict"])
+    logits, loss, grads = _run(m, g["img"], g["labels"], "bf16")
+    assert rel_l2(logits, g["logits"]) < 2e-2
+    assert float((logits - g["logits"]).abs().max()) < 2e-2 * float(g["logits"].abs().max())
+    for k, ref in g["grads"].items():           # bf16 gradients: loose sanity bound, not a north-star bar
+        assert grad_close(grads[k], ref, 6e-2, atol=1e-5), (k, rel_l2(grads[k], ref))
+
+
+def _b16_case():
+    import vitb200
+    g = torch.load(os.path.join(GOLD, "vit_b16_l2.pt"))
+    torch.manual_seed(g["seed"])
+    m = vitb200.VisionTransformer(**g["cfg"])
+    sd = vit_oracle.scaled_init_({k: v.detach().clone() for k, v in m.state_dict().items()})
+    m.load_state_dict(sd)
+    gen = torch.Generator().manual_seed(g["img_seed"])
+    img = torch.randn(g["batch"], 3, 224, 224, generator=gen)
+    labels = torch.randint(0, g["cfg"]["num_classes"], (g["batch"],), generator=gen)
+    return g, m.cuda().train(), sd, img, labels
+
+
+def test_b16_geometry_fp32_mode_matches_reference_golden_and_oracle_grads():
+    g, m, sd, img, labels = _b16_case()
+    logits, loss, grads = _run(m, img, labels, "fp32")
+    assert rel_l2(logits, g["logits"]) < 1e-4
+    assert abs(float(loss) - float(g["loss"])) < 1e-4 * abs(float(g["loss"]))
+    osd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    vit_oracle.vit_loss(img, labels, osd).backward()
+    for k, v in osd.items():
+        assert grad_close(grads[k], v.grad, 1e-4), (k, rel_l2(grads[k], v.grad))
+    assert rel_l2(grads["cls_token"], g["grad_cls_token"]) < 1e-4
+
+
+def test_b16_geometry_bf16_mode_logits_within_2e2():
+    g, m, sd, img, labels = _b16_case()
+    logits, loss, grads = _run(m, img, labels, "bf16")
+    assert rel_l2(logits, g["logits"]) < 2e-2
+    assert float((logits - g["logits"]).abs().max()) < 2e-2 * float(g["logits"].abs().max())
+    for k, fp in g["grads_fp"].items():
+        n = float(grads[k].double().norm())
+        assert abs(n - fp["norm"]) <= 0.1 * fp["norm"] + 1e-5 * grads[k].numel() ** 0.5, (k, n, fp["norm"])
+
+
+@pytest.mark.parametrize("arch,img,patch", [("b32", 224, 32), ("h14-ish", 224, 14)])
+def test_other_geometries_fp32_forward(arch, img, patch):
+    """N=50 (patch 32) and N=257 / head_dim 80 / K=588 (patch 14): the non-power-of-two tails."""
+    import vitb200
+    if arch == "b32":
+        cfg = dict(image_size=(img, img), patch_size=(patch, patch), emb_dim=768, mlp_dim=3072, num_heads=12,
+                   num_layers=1, num_classes=11, attn_dropout_rate=0.0, dropout_rate=0.0)
+    else:
+        cfg = dict(image_size=(img, img), patch_size=(patch, patch), emb_dim=1280, mlp_dim=5120, num_heads=16,
+                   num_layers=1, num_classes=11, attn_dropout_rate=0.0, dropout_rate=0.0)
+    torch.manual_seed(5)
+    m = vitb200.VisionTransformer(**cfg)
+    sd = vit_oracle.scaled_init_({k: v.detach().clone() for k, v in m.state_dict().items()})
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    x = torch.randn(2, 3, img, img)
+    ref = vit_oracle.vit_logits(x, sd)
+    with torch.no_grad():
+        with vitb200.precision("fp32"):
+            out32 = m(x.cuda()).cpu()
+        with vitb200.precision("bf16"):
+            out16 = m(x.cuda()).cpu()
+    assert rel_l2(out32, ref) < 1e-4
+    assert rel_l2(out16, ref) < 2e-2
+
+
+def test_modules_standalone_default_init_fp32_mode():
+    """Per-module parity under the reference's as-constructed (randn) init — SURVEY.md F5."""
+    import vitb200
+    torch.manual_seed(0)
+    blk = vitb200.EncoderBlock(768, 3072, 12, dropout_rate=0.0, attn_dropout_rate=0.0)
+    sd = {"transformer.encoder_layers.0." + k: v.detach().clone() for k, v in blk.state_dict().items()}
+    x = torch.randn(2, 197, 768)
+    blk = blk.cuda()
+    with vitb200.precision("fp32"):
+        xc = x.cuda().requires_grad_(True)
+        y = blk(xc)
+        (y * torch.linspace(-1, 1, 768, device="cuda")).sum().backward()
+        y_attn = blk.attn(xc.detach())
+        y_mlp = blk.mlp(xc.detach())
+        q = blk.attn.query(xc.detach(), dims=([2], [0]))
+    xo = x.clone().requires_grad_(True)
+    yo = vit_oracle.encoder_block(xo, sd, "transformer.encoder_layers.0.")
+    (yo * torch.linspace(-1, 1, 768)).sum().backward()
+    assert rel_l2(y.detach().cpu(), yo.detach()) < 1e-4
+    assert rel_l2(xc.grad.cpu(), xo.grad) < 1e-4
+    assert rel_l2(y_attn.cpu(), vit_oracle.self_attention(x, sd, "transformer.encoder_layers.0.attn.")) < 1e-4
+    assert rel_l2(y_mlp.cpu(), vit_oracle.mlp(x, sd, "transformer.encoder_layers.0.mlp.")) < 1e-4
+    assert q.shape == (2, 197, 12, 64)
+    wq, bq = sd["transformer.encoder_layers.0.attn.query.weight"], sd["transformer.encoder_layers.0.attn.query.bias"]
+    assert rel_l2(q.cpu(), torch.tensordot(x, wq, dims=([2], [0])) + bq) < 1e-4
+
+
+def test_two_sgd_steps_match_oracle_fp32_mode():
+    """fwd + bwd + SGD(momentum 0.9) x2 (src/train.py:20-24,154-158) against the oracle's update."""
+    import vitb200
+    g = torch.load(os.path.join(GOLD, "vit_tiny.pt"))
+    m = _model_from(g["cfg"], g["state_dict"])
+    opt = vitb200.optim.FusedSGD(m.parameters(), lr=0.03, momentum=0.9)
+    params = {k: v.clone() for k, v in g["state_dict"].items()}
+    bufs = {}
+    for step in range(2):
+        gen = torch.Generator().manual_seed(100 + step)
+        img = torch.randn(4, 3, 32, 32, generator=gen)
+        labels = torch.randint(0, 10, (4,), generator=gen)
+        with vitb200.precision("fp32"):
+            opt.zero_grad()
+            loss = vitb200.functional.cross_entropy(m(img.cuda()), labels.cuda())
+            loss.backward()
+            opt.step()
+        leaf = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+        vit_oracle.vit_loss(img, labels, leaf).backward()
+        vit_oracle.sgd_momentum_step(params, {k: v.grad for k, v in leaf.items()}, bufs, 0.03, 0.9, first=(step == 0))
+    torch.cuda.synchronize()
+    for k, p in m.named_parameters():
+        assert grad_close(p.detach().cpu() - g["state_dict"][k], params[k] - g["state_dict"][k], 2e-4, atol=1e-8), k

@@ -76,6 +76,7 @@ def _sig(name, argtypes, restype=C.c_int):
 vitb_version = _sig("vitb_version", [])
 _vitb_last_error = _sig("vitb_last_error", [C.c_char_p, C.c_size_t])
 vitb_device_check = _sig("vitb_device_check", [])
+vitb_struct_size = _sig("vitb_struct_size", [C.c_int])
 _vitb_gemm = _sig("vitb_gemm", [C.POINTER(GemmParams), C.c_void_p])
 
 
@@ -158,6 +159,7 @@ _vitb_cast_split = _sig("vitb_cast_split", [_vp, _i64, _vp, _vp, _vp])
 _vitb_im2col = _sig("vitb_im2col", [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp])
 _vitb_cls_rows = _sig("vitb_cls_rows", [_vp, _i, _i, _i, _vp, _vp, _vp])
 _vitb_embed_bwd = _sig("vitb_embed_bwd", [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp])
+_vitb_gelu_bwd = _sig("vitb_gelu_bwd", [_vp, _vp, _vp, _i64, _i, _vp])
 _vitb_colsum = _sig("vitb_colsum", [_vp, _i, _i, _i, _i64, _vp, _vp])
 _vitb_cross_entropy = _sig("vitb_cross_entropy", [_vp, _vp, _i, _i, _vp, _vp, _vp])
 _vitb_sgd_momentum = _sig("vitb_sgd_momentum", [_vp, _vp, _vp, _i64, _f, _f, _f, _f, _i, _i, _vp, _vp, _vp])
@@ -166,9 +168,9 @@ _vitb_sumsq = _sig("vitb_sumsq", [_vp, _i64, _vp, _vp])
 _vitb_clip_coef = _sig("vitb_clip_coef", [_vp, _f, _vp, _vp, _vp])
 
 EXPORTED_SYMBOLS = [
-    "vitb_version", "vitb_last_error", "vitb_device_check", "vitb_gemm", "vitb_layernorm_fwd",
+    "vitb_version", "vitb_last_error", "vitb_device_check", "vitb_struct_size", "vitb_gemm", "vitb_layernorm_fwd",
     "vitb_layernorm_bwd", "vitb_attn_supported_tc", "vitb_attn_fwd_tc", "vitb_attn_bwd_tc",
     "vitb_attn_fwd_simt", "vitb_attn_bwd_simt", "vitb_cast_split", "vitb_im2col", "vitb_cls_rows",
     "vitb_embed_bwd", "vitb_colsum", "vitb_cross_entropy", "vitb_sgd_momentum", "vitb_adamw",
-    "vitb_sumsq", "vitb_clip_coef",
+    "vitb_sumsq", "vitb_clip_coef", "vitb_gelu_bwd",
 ]

@@ -134,4 +134,10 @@ int vitb_last_error(char* buf, size_t n) {
 
 int vitb_device_check(void) { return vitb_check_device(); }
 
+int vitb_struct_size(int which) {
+  if (which == 0) return (int)sizeof(vitb_gemm_params);
+  if (which == 1) return (int)sizeof(vitb_attn_params);
+  return -1;
+}
+
 }  // extern "C"

@@ -308,9 +308,59 @@ __global__ void clip_coef_kernel(const float* __restrict__ sumsq, float max_norm
   *coef = c < 1.f ? c : 1.f;
 }
 
+// dz = dy * gelu'(z)  (exact-erf GELU, nn.GELU() of src/model.py:33 / res-vit/model.py:154,158,160,312)
+template <bool BF16>
+__global__ void __launch_bounds__(kThreads)
+gelu_bwd_kernel(const void* __restrict__ dy_, const void* __restrict__ z_, void* __restrict__ out_, long long n) {
+  const long long n4 = n >> 2;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 d, z;
+    if constexpr (BF16) {
+      const uint2 a = reinterpret_cast<const uint2*>(dy_)[i], b = reinterpret_cast<const uint2*>(z_)[i];
+      d = make_float4(bf16_lo(a.x), bf16_hi(a.x), bf16_lo(a.y), bf16_hi(a.y));
+      z = make_float4(bf16_lo(b.x), bf16_hi(b.x), bf16_lo(b.y), bf16_hi(b.y));
+    } else {
+      d = reinterpret_cast<const float4*>(dy_)[i];
+      z = reinterpret_cast<const float4*>(z_)[i];
+    }
+    d.x *= gelu_erf_grad(z.x); d.y *= gelu_erf_grad(z.y); d.z *= gelu_erf_grad(z.z); d.w *= gelu_erf_grad(z.w);
+    if constexpr (BF16) {
+      uint2 o;
+      o.x = pack_bf16x2(d.x, d.y); o.y = pack_bf16x2(d.z, d.w);
+      reinterpret_cast<uint2*>(out_)[i] = o;
+    } else {
+      reinterpret_cast<float4*>(out_)[i] = d;
+    }
+  }
+  for (long long i = (n4 << 2) + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    if constexpr (BF16) {
+      const float d = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(dy_)[i]);
+      const float z = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(z_)[i]);
+      reinterpret_cast<__nv_bfloat16*>(out_)[i] = __float2bfloat16(d * gelu_erf_grad(z));
+    } else {
+      reinterpret_cast<float*>(out_)[i] =
+          reinterpret_cast<const float*>(dy_)[i] * gelu_erf_grad(reinterpret_cast<const float*>(z_)[i]);
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" {
+
+int vitb_gelu_bwd(const void* dy, const void* z, void* out, int64_t n, int dtype, void* stream_) {
+  int st = vitb_check_device();
+  if (st != VITB_OK) return st;
+  if (n == 0) return VITB_OK;
+  VITB_REQUIRE(dy && z && out && n > 0, VITB_ERR_BAD_ARG, "gelu_bwd: bad args");
+  if (dtype == VITB_BF16)
+    gelu_bwd_kernel<true><<<grid_for((n + 3) / 4), kThreads, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(dy, z, out, n);
+  else
+    gelu_bwd_kernel<false><<<grid_for((n + 3) / 4), kThreads, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(dy, z, out, n);
+  VITB_LAUNCH_CHECK("gelu_bwd_kernel");
+  return VITB_OK;
+}
 
 int vitb_cast_split(const float* x, int64_t n, void* hi, void* lo, void* stream_) {
   int st = vitb_check_device();

@@ -1,0 +1,627 @@
+"""torch.autograd.Function layer over the sm_100a kernels (ops.py -> C ABI -> libvitb200.so).
+
+Precision modes (vitb200.set_precision / `with vitb200.precision(...)`):
+  "bf16": GEMM/attention operands bf16, fp32 accumulation, fp32 residual stream, fp32 LayerNorm
+          statistics, fp32 master weights with bf16 shadows.   (north-star: logits within 2e-2)
+  "fp32": parity mode.  Every contraction runs on the SAME tcgen05 kernel as three bf16 segments
+          (a = a_hi + a_lo, b = b_hi + b_lo; a_hi*b_hi + a_hi*b_lo + a_lo*b_hi, error ~2^-17), attention
+          runs in fp32 on CUDA cores.                           (north-star: rel 1e-4)
+Every Function raises on non-CUDA tensors: there is no CPU or eager fallback.
+"""
+import contextlib
+import weakref
+
+import torch
+
+from . import _lib as L
+from . import ops
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+class _State:
+    precision = "bf16"
+
+
+def set_precision(p):
+    if p not in ("bf16", "fp32"):
+        raise ValueError("precision must be 'bf16' or 'fp32'")
+    _State.precision = p
+
+
+def get_precision():
+    return _State.precision
+
+
+@contextlib.contextmanager
+def precision(p):
+    old = _State.precision
+    set_precision(p)
+    try:
+        yield
+    finally:
+        _State.precision = old
+
+
+# --------------------------------------------------------------------------------------------------
+# bf16 shadows of the fp32 master weights
+# --------------------------------------------------------------------------------------------------
+class ShadowStore:
+    """bf16 (hi) and residual (lo = w - hi) copies of fp32 weights, refreshed when the master changes.
+
+    A change is detected through the tensor version counter / data pointer; the fused optimizers
+    (optim.py) update the masters through raw pointers and write the shadows in the same kernel, so
+    for them nothing is re-cast."""
+
+    def __init__(self):
+        self._e = {}
+
+    def _entry(self, w):
+        key = id(w)
+        e = self._e.get(key)
+        if e is None or e["ref"]() is not w:
+            e = {"ref": weakref.ref(w, lambda _r, k=key: self._e.pop(k, None)), "version": -1, "ptr": 0,
+                 "hi": None, "lo": None, "pad": {}}
+            self._e[key] = e
+        return e
+
+    def get(self, w, want_lo):
+        e = self._entry(w)
+        stale = (e["version"] != w._version or e["ptr"] != w.data_ptr() or e["hi"] is None
+                 or e["hi"].device != w.device or (want_lo and e["lo"] is None))
+        if stale:
+            src = w.detach()
+            if not src.is_contiguous():
+                src = src.contiguous()
+            if e["hi"] is None or e["hi"].device != w.device or e["hi"].shape != w.shape:
+                e["hi"] = torch.empty(w.shape, dtype=BF16, device=w.device)
+                e["lo"] = None
+            if want_lo and e["lo"] is None:
+                e["lo"] = torch.empty(w.shape, dtype=BF16, device=w.device)
+            ops.cast_split(src, hi=e["hi"], lo=e["lo"])
+            e["version"], e["ptr"] = w._version, w.data_ptr()
+            e["pad"] = {}
+        return e["hi"], (e["lo"] if want_lo else None)
+
+    def get_padded_2d(self, w, rows, cols, ld, want_lo):
+        """Shadow of w viewed [rows, cols], zero-padded to row length ld (TMA needs 16-byte row strides)."""
+        hi, lo = self.get(w, want_lo)
+        if ld == cols:
+            return hi.view(rows, cols), (lo.view(rows, cols) if lo is not None else None)
+        e = self._entry(w)
+        key = (ld, bool(want_lo))
+        if key not in e["pad"]:
+            ph = torch.zeros((rows, ld), dtype=BF16, device=w.device)
+            ph[:, :cols] = hi.view(rows, cols)
+            pl = None
+            if want_lo:
+                pl = torch.zeros((rows, ld), dtype=BF16, device=w.device)
+                pl[:, :cols] = lo.view(rows, cols)
+            e["pad"][key] = (ph, pl)
+        return e["pad"][key]
+
+    def attach(self, w, hi, lo=None):
+        """Use caller-owned shadow buffers (views of a flat optimizer buffer) and fill them now."""
+        e = self._entry(w)
+        e["hi"], e["lo"] = hi, lo
+        ops.cast_split(w.detach().contiguous(), hi=hi, lo=lo)
+        e["version"], e["ptr"] = w._version, w.data_ptr()
+        e["pad"] = {}
+
+    def mark_fresh(self, w):
+        e = self._entry(w)
+        e["version"], e["ptr"] = w._version, w.data_ptr()
+        e["pad"] = {}
+
+
+SHADOW = ShadowStore()
+
+
+def _fp32_mode():
+    return _State.precision == "fp32"
+
+
+def _operand(t2d):
+    """bf16 GEMM operand pieces of a 2-D activation: [hi] (bf16 mode) or [hi, lo] (fp32 mode)."""
+    if t2d.dtype == BF16:
+        if t2d.stride(1) != 1:
+            t2d = t2d.contiguous()
+        return [t2d]
+    if t2d.dtype != F32:
+        raise L.VitbError("activations must be fp32 or bf16, got %s" % t2d.dtype)
+    if not t2d.is_contiguous():
+        t2d = t2d.contiguous()
+    hi, lo = ops.cast_split(t2d, want_lo=_fp32_mode())
+    return [hi, lo] if lo is not None else [hi]
+
+
+def _weight_operand(w, shape2d):
+    hi, lo = SHADOW.get(w, _fp32_mode())
+    return [hi.view(shape2d), lo.view(shape2d)] if lo is not None else [hi.view(shape2d)]
+
+
+def _pairs(a, b):
+    """Segment lists for a ~= sum(a) times b ~= sum(b), dropping the lo*lo term."""
+    A, B = [a[0]], [b[0]]
+    if len(b) > 1:
+        A.append(a[0]); B.append(b[1])
+    if len(a) > 1:
+        A.append(a[1]); B.append(b[0])
+    return A, B
+
+
+def _act_dtype():
+    return F32 if _fp32_mode() else BF16
+
+
+def _grad_target(w):
+    """fp32 buffer to accumulate a weight gradient into directly (set by the fused optimizers / DDP)."""
+    return getattr(w, "_vitb_main_grad", None)
+
+
+def _wgrad(dy_ops, x_ops, w, shape2d, dy_is_rows_of_n):
+    """dW for a weight viewed `shape2d`.  dy_is_rows_of_n: weight is [N,K] (nn.Linear) -> dW = dY^T X;
+    else weight is [K,N] (LinearGeneral) -> dW = X^T dY.  Both operands are consumed MN-major."""
+    tgt = _grad_target(w)
+    out = tgt.view(shape2d) if tgt is not None else torch.zeros(shape2d, dtype=F32, device=w.device)
+    A, B = _pairs(dy_ops, x_ops) if dy_is_rows_of_n else _pairs(x_ops, dy_ops)
+    ops.gemm(A, B, a_mn=True, b_mn=True, out=out, accumulate=True)
+    return None if tgt is not None else out.view(w.shape)
+
+
+def _bias_grad(dy2d, b):
+    if b is None:
+        return None
+    tgt = _grad_target(b)
+    out = tgt.view(-1) if tgt is not None else torch.zeros(b.numel(), dtype=F32, device=b.device)
+    ops.colsum(dy2d, out)
+    return None if tgt is not None else out.view(b.shape)
+
+
+def _as2d(t, cols):
+    t2 = t.reshape(-1, cols)
+    if t2.stride(1) != 1 or (t2.shape[0] > 1 and t2.stride(0) < cols):
+        t2 = t2.contiguous()
+    return t2
+
+
+# --------------------------------------------------------------------------------------------------
+# Linear (nn.Linear [N,K] and LinearGeneral [K,N]) with fused bias / GELU / residual epilogue
+# --------------------------------------------------------------------------------------------------
+class _Linear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, layout, act, out_dtype):
+        L.require_cuda(x, weight)
+        kn = layout == "kn"
+        K = x.shape[-1]
+        N = weight.numel() // K
+        w2 = (K, N) if kn else (N, K)
+        x2 = _as2d(x, K)
+        xo = _operand(x2)
+        wo = _weight_operand(weight, w2)
+        A, B = _pairs(xo, wo)
+        M = x2.shape[0]
+        out = torch.empty((M, N), dtype=out_dtype, device=x.device)
+        need_z = act == "gelu" and (x.requires_grad or weight.requires_grad)
+        z = torch.empty((M, N), dtype=out_dtype, device=x.device) if need_z else None
+        res2 = _as2d(residual, N) if residual is not None else None
+        b1 = bias.detach().view(-1) if bias is not None else None
+        if act == "gelu" and residual is not None:
+            raise L.VitbError("linear: GELU and residual cannot be fused in one call")
+        ops.gemm(A, B, b_mn=kn, out=out, bias=b1, residual=res2,
+                 epilogue=ops.EPI_GELU if act == "gelu" else ops.EPI_NONE, d2=z)
+        ctx.kn, ctx.act, ctx.w2, ctx.N, ctx.K = kn, act, w2, N, K
+        ctx.x_shape, ctx.x_dtype = x.shape, x.dtype
+        ctx.has_res = residual is not None
+        ctx.res_shape = residual.shape if residual is not None else None
+        ctx.res_dtype = residual.dtype if residual is not None else None
+        ctx.weight, ctx.bias = weight, bias
+        ctx.xo, ctx.z = xo, z
+        return out.view(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        N, K, kn = ctx.N, ctx.K, ctx.kn
+        weight, bias = ctx.weight, ctx.bias
+        dy2 = _as2d(dy, N)
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        dres = None
+        if ctx.has_res and ctx.needs_input_grad[3]:
+            dres = dy.reshape(ctx.res_shape).to(ctx.res_dtype)
+        if ctx.act == "gelu":
+            dy2 = ops.gelu_bwd(dy2, ctx.z)
+        dyo = _operand(dy2)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            wo = _weight_operand(weight, ctx.w2)
+            A, B = _pairs(dyo, wo)
+            dx = ops.gemm(A, B, b_mn=not kn, out_dtype=ctx.x_dtype).view(ctx.x_shape)
+        if weight.requires_grad:
+            dw = _wgrad(dyo, ctx.xo, weight, ctx.w2, dy_is_rows_of_n=not kn)
+        if bias is not None and bias.requires_grad:
+            db = _bias_grad(dy2, bias)
+        ctx.xo = ctx.z = None
+        return dx, dw, db, dres, None, None, None
+
+
+def linear(x, weight, bias=None, *, layout="nk", act=None, residual=None, out_dtype=None):
+    """y = act(x W^T + b) (+ residual).  layout "nk": weight [N,K] (nn.Linear); "kn": weight [K,N...]
+    (LinearGeneral).  Output dtype: fp32 when a residual is fused or in fp32 mode, else bf16."""
+    if out_dtype is None:
+        out_dtype = F32 if (residual is not None or _fp32_mode()) else BF16
+    return _Linear.apply(x, weight, bias, residual, layout, act, out_dtype)
+
+
+# --------------------------------------------------------------------------------------------------
+# MLP block: fc2(GELU(fc1(x))) (+ residual), GELU' folded into the fc2 dgrad epilogue
+# --------------------------------------------------------------------------------------------------
+class _Mlp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, residual, out_dtype):
+        L.require_cuda(x, w1, w2)
+        D = x.shape[-1]
+        Mh = w1.shape[0]
+        Do = w2.shape[0]
+        x2 = _as2d(x, D)
+        xo = _operand(x2)
+        rows = x2.shape[0]
+        adt = _act_dtype()
+        h = torch.empty((rows, Mh), dtype=adt, device=x.device)
+        z = torch.empty((rows, Mh), dtype=adt, device=x.device)
+        A, B = _pairs(xo, _weight_operand(w1, (Mh, D)))
+        ops.gemm(A, B, out=h, bias=b1.detach() if b1 is not None else None, epilogue=ops.EPI_GELU, d2=z)
+        ho = _operand(h)
+        A, B = _pairs(ho, _weight_operand(w2, (Do, Mh)))
+        res2 = _as2d(residual, Do) if residual is not None else None
+        out = torch.empty((rows, Do), dtype=out_dtype, device=x.device)
+        ops.gemm(A, B, out=out, bias=b2.detach() if b2 is not None else None, residual=res2)
+        ctx.dims = (D, Mh, Do)
+        ctx.x_shape, ctx.x_dtype = x.shape, x.dtype
+        ctx.res = (residual.shape, residual.dtype) if residual is not None else None
+        ctx.params = (w1, b1, w2, b2)
+        ctx.xo, ctx.ho, ctx.z = xo, ho, z
+        return out.view(*x.shape[:-1], Do)
+
+    @staticmethod
+    def backward(ctx, dy):
+        D, Mh, Do = ctx.dims
+        w1, b1, w2, b2 = ctx.params
+        dy2 = _as2d(dy, Do)
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        dres = dy.reshape(ctx.res[0]).to(ctx.res[1]) if (ctx.res is not None and ctx.needs_input_grad[5]) else None
+        dyo = _operand(dy2)
+        # dz = (dy W2) * gelu'(z)
+        A, B = _pairs(dyo, _weight_operand(w2, (Do, Mh)))
+        dz = ops.gemm(A, B, b_mn=True, out_dtype=ctx.z.dtype, epilogue=ops.EPI_GELU_BWD, aux=ctx.z)
+        dzo = _operand(dz)
+        dw2 = _wgrad(dyo, ctx.ho, w2, (Do, Mh), True) if w2.requires_grad else None
+        db2 = _bias_grad(dy2, b2) if (b2 is not None and b2.requires_grad) else None
+        dw1 = _wgrad(dzo, ctx.xo, w1, (Mh, D), True) if w1.requires_grad else None
+        db1 = _bias_grad(dz, b1) if (b1 is not None and b1.requires_grad) else None
+        dx = None
+        if ctx.needs_input_grad[0]:
+            A, B = _pairs(dzo, _weight_operand(w1, (Mh, D)))
+            dx = ops.gemm(A, B, b_mn=True, out_dtype=ctx.x_dtype).view(ctx.x_shape)
+        ctx.xo = ctx.ho = ctx.z = None
+        return dx, dw1, db1, dw2, db2, dres, None
+
+
+def mlp(x, w1, b1, w2, b2, *, residual=None, out_dtype=None):
+    if out_dtype is None:
+        out_dtype = F32 if (residual is not None or _fp32_mode()) else BF16
+    return _Mlp.apply(x, w1, b1, w2, b2, residual, out_dtype)
+
+
+# --------------------------------------------------------------------------------------------------
+# LayerNorm
+# --------------------------------------------------------------------------------------------------
+class _LayerNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps, out_dtype):
+        L.require_cuda(x, weight, bias)
+        D = x.shape[-1]
+        x2 = x.reshape(-1, D)
+        if x2.stride(1) != 1:
+            x2 = x2.contiguous()
+        if x2.dtype != F32:
+            x2 = x2.float()
+        yf, yh, _, mean, rstd = ops.layernorm_fwd(x2, weight.detach(), bias.detach(), eps,
+                                                  want_f32=out_dtype == F32, want_bf16=out_dtype == BF16)
+        ctx.save_for_backward(x2, mean, rstd)
+        ctx.weight, ctx.bias = weight, bias
+        ctx.x_shape, ctx.x_dtype = x.shape, x.dtype
+        y = yf if out_dtype == F32 else yh
+        return y.view(*x.shape[:-1], D)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, mean, rstd = ctx.saved_tensors
+        weight, bias = ctx.weight, ctx.bias
+        D = x2.shape[1]
+        dy2 = dy.reshape(-1, D)
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        need_wb = weight.requires_grad or bias.requires_grad
+        gt, bt = _grad_target(weight), _grad_target(bias)
+        dg = (gt if gt is not None else torch.zeros(D, dtype=F32, device=x2.device)) if need_wb else None
+        db = (bt if bt is not None else torch.zeros(D, dtype=F32, device=x2.device)) if need_wb else None
+        dxf, _, _ = ops.layernorm_bwd(dy2, x2, mean, rstd, weight.detach(), want_f32=True, dgamma=dg, dbeta=db)
+        dx = dxf.view(ctx.x_shape)
+        if ctx.x_dtype != F32:
+            dx = dx.to(ctx.x_dtype)
+        return (dx if ctx.needs_input_grad[0] else None,
+                dg if (need_wb and gt is None and weight.requires_grad) else None,
+                db if (need_wb and bt is None and bias.requires_grad) else None, None, None)
+
+
+def layer_norm(x, weight, bias, eps=1e-5, *, out_dtype=None):
+    """nn.LayerNorm over the last dim.  Output: bf16 GEMM operand in bf16 mode, fp32 in fp32 mode."""
+    if out_dtype is None:
+        out_dtype = _act_dtype()
+    return _LayerNorm.apply(x, weight, bias, eps, out_dtype)
+
+
+# --------------------------------------------------------------------------------------------------
+# q/k/v projection into one packed [.., 3*HD] buffer, and attention on it
+# --------------------------------------------------------------------------------------------------
+class _QKVProj(torch.autograd.Function):
+    """qkv[..., i*HD:(i+1)*HD] = x W_i (+ b_i) (+ (x A_i^T) B_i^T for LoRA), i in (q, k, v)."""
+
+    @staticmethod
+    def forward(ctx, x, layout, wq, bq, wk, bk, wv, bv, *lora):
+        L.require_cuda(x, wq, wk, wv)
+        kn = layout == "kn"
+        K = x.shape[-1]
+        ws, bs = (wq, wk, wv), (bq, bk, bv)
+        HD = wq.numel() // K
+        w2 = (K, HD) if kn else (HD, K)
+        x2 = _as2d(x, K)
+        xo = _operand(x2)
+        rows = x2.shape[0]
+        adt = _act_dtype()
+        qkv = torch.empty((rows, 3 * HD), dtype=adt, device=x.device)
+        has_lora = len(lora) == 6 and lora[0] is not None
+        ts = []
+        for i in range(3):
+            A, B = _pairs(xo, _weight_operand(ws[i], w2))
+            out = qkv[:, i * HD:(i + 1) * HD]
+            bias = bs[i].detach().view(-1) if bs[i] is not None else None
+            if has_lora:
+                la, lb = lora[2 * i], lora[2 * i + 1]          # A [r,K], B [HD,r]  (nn.Linear layouts)
+                r = la.shape[0]
+                Ar, Br = _pairs(xo, _weight_operand(la, (r, K)))
+                t = ops.gemm(Ar, Br, out_dtype=adt)           # t = x A^T  [rows, r]
+                to = _operand(t)
+                ts.append((t, to))
+                lbo = _weight_operand(lb, (HD, r))
+                if _fp32_mode():
+                    ops.gemm(A, B, b_mn=kn, out=out, bias=bias)
+                    A2, B2 = _pairs(to, lbo)
+                    ops.gemm(A2, B2, out=out, accumulate=True)
+                else:
+                    # rank-r update accumulated in the SAME TMEM accumulator as the base projection
+                    if kn:
+                        raise L.VitbError("LoRA needs nn.Linear-layout base weights")
+                    ops.gemm(A + [to[0]], B + [lbo[0]], out=out, bias=bias)
+            else:
+                ops.gemm(A, B, b_mn=kn, out=out, bias=bias)
+        ctx.kn, ctx.K, ctx.HD, ctx.w2 = kn, K, HD, w2
+        ctx.ws, ctx.bs, ctx.lora, ctx.has_lora = ws, bs, lora, has_lora
+        ctx.xo, ctx.ts = xo, ts
+        ctx.x_shape, ctx.x_dtype = x.shape, x.dtype
+        return qkv.view(*x.shape[:-1], 3 * HD)
+
+    @staticmethod
+    def backward(ctx, dqkv):
+        kn, K, HD, w2 = ctx.kn, ctx.K, ctx.HD, ctx.w2
+        ws, bs, lora = ctx.ws, ctx.bs, ctx.lora
+        d2 = dqkv.reshape(-1, 3 * HD)
+        if not d2.is_contiguous():
+            d2 = d2.contiguous()
+        rows = d2.shape[0]
+        fp32 = _fp32_mode()
+        if d2.dtype == BF16:
+            dyo = [[d2[:, i * HD:(i + 1) * HD]] for i in range(3)]
+        else:
+            hi, lo = ops.cast_split(d2, want_lo=fp32)
+            dyo = [[hi[:, i * HD:(i + 1) * HD]] + ([lo[:, i * HD:(i + 1) * HD]] if lo is not None else [])
+                   for i in range(3)]
+        grads_w, grads_b, grads_l = [None] * 3, [None] * 3, [None] * 6
+        need_dx = ctx.needs_input_grad[0]
+        dx = None
+        if need_dx:
+            if not fp32 and not ctx.has_lora:
+                # one GEMM, three K-segments: dX = dQ Wq + dK Wk + dV Wv
+                A = [dyo[i][0] for i in range(3)]
+                B = [_weight_operand(ws[i], w2)[0] for i in range(3)]
+                dx = ops.gemm(A, B, b_mn=not kn, out_dtype=ctx.x_dtype)
+            else:
+                dx = torch.zeros((rows, K), dtype=F32, device=dqkv.device)
+                for i in range(3):
+                    A, B = _pairs(dyo[i], _weight_operand(ws[i], w2))
+                    ops.gemm(A, B, b_mn=not kn, out=dx, accumulate=True)
+        for i in range(3):
+            if ws[i].requires_grad:
+                grads_w[i] = _wgrad(dyo[i], ctx.xo, ws[i], w2, dy_is_rows_of_n=not kn)
+            if bs[i] is not None and bs[i].requires_grad:
+                grads_b[i] = _bias_grad(d2[:, i * HD:(i + 1) * HD], bs[i])
+            if ctx.has_lora:
+                la, lb = lora[2 * i], lora[2 * i + 1]
+                r = la.shape[0]
+                t, to = ctx.ts[i]
+                # dB = dY^T t ; dt = dY B ; dA = dt^T x ; dx += dt A
+                if lb.requires_grad:
+                    grads_l[2 * i + 1] = _wgrad(dyo[i], to, lb, (HD, r), True)
+                A, B = _pairs(dyo[i], _weight_operand(lb, (HD, r)))
+                dt = ops.gemm(A, B, b_mn=True, out_dtype=t.dtype)
+                dto = _operand(dt)
+                if la.requires_grad:
+                    grads_l[2 * i] = _wgrad(dto, ctx.xo, la, (r, K), True)
+                if need_dx:
+                    A, B = _pairs(dto, _weight_operand(la, (r, K)))
+                    ops.gemm(A, B, b_mn=True, out=dx, accumulate=True)
+        if need_dx:
+            if dx.dtype != ctx.x_dtype:
+                dx = dx.to(ctx.x_dtype)
+            dx = dx.view(ctx.x_shape)
+        ctx.xo = ctx.ts = None
+        return (dx, None, grads_w[0], grads_b[0], grads_w[1], grads_b[1], grads_w[2], grads_b[2], *grads_l[:len(lora)])
+
+
+def qkv_proj(x, wq, bq, wk, bk, wv, bv, *, layout, lora=None):
+    extra = ()
+    if lora is not None:
+        extra = tuple(lora)  # (Aq, Bq, Ak, Bk, Av, Bv)
+    return _QKVProj.apply(x, layout, wq, bq, wk, bk, wv, bv, *extra)
+
+
+class _AttentionPacked(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, H):
+        L.require_cuda(qkv)
+        B, N, HD3 = qkv.shape
+        HD = HD3 // 3
+        if not qkv.is_contiguous():
+            qkv = qkv.contiguous()
+        q, k, v = qkv[:, :, :HD], qkv[:, :, HD:2 * HD], qkv[:, :, 2 * HD:]
+        o, lse = ops.attn_fwd(q, k, v, H)
+        ctx.save_for_backward(qkv, o, lse)
+        ctx.H = H
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        qkv, o, lse = ctx.saved_tensors
+        H = ctx.H
+        B, N, HD3 = qkv.shape
+        HD = HD3 // 3
+        if not do.is_contiguous():
+            do = do.contiguous()
+        q, k, v = qkv[:, :, :HD], qkv[:, :, HD:2 * HD], qkv[:, :, 2 * HD:]
+        use_tc = ops.attn_supported_tc(HD // H, N, N, qkv.dtype)
+        gdt = BF16 if use_tc else F32
+        dqkv = torch.empty((B, N, HD3), dtype=gdt, device=qkv.device)
+        ops.attn_bwd(do, q, k, v, o, lse, H, use_tc=use_tc, dq=dqkv[:, :, :HD], dk=dqkv[:, :, HD:2 * HD],
+                     dv=dqkv[:, :, 2 * HD:])
+        if dqkv.dtype != qkv.dtype:
+            dqkv = dqkv.to(qkv.dtype)
+        return dqkv, None
+
+
+def attention_packed(qkv, H):
+    """softmax(q k^T / sqrt(dh)) v on a packed [B, N, 3*H*dh] projection; returns [B, N, H*dh]."""
+    return _AttentionPacked.apply(qkv, H)
+
+
+class _AttentionSeparate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, H):
+        L.require_cuda(q, k, v)
+        q, k, v = (t if t.stride(-1) == 1 else t.contiguous() for t in (q, k, v))
+        o, lse = ops.attn_fwd(q, k, v, H)
+        ctx.save_for_backward(q, k, v, o, lse)
+        ctx.H = H
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        q, k, v, o, lse = ctx.saved_tensors
+        if not do.is_contiguous():
+            do = do.contiguous()
+        dq, dk, dv = ops.attn_bwd(do, q, k, v, o, lse, ctx.H)
+        return dq.to(q.dtype), dk.to(k.dtype), dv.to(v.dtype), None
+
+
+def attention(q, k, v, H):
+    """q [B,Nq,H*dh], k/v [B,Nk,H*dh] -> [B,Nq,H*dh] (asymmetric query/key counts allowed)."""
+    return _AttentionSeparate.apply(q, k, v, H)
+
+
+# --------------------------------------------------------------------------------------------------
+# patch embedding: Conv2d(3,D,P,P) + cls token + position embedding as one GEMM with a scatter epilogue
+# --------------------------------------------------------------------------------------------------
+class _PatchEmbed(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, conv_w, conv_b, cls_token, pos):
+        L.require_cuda(img, conv_w)
+        Bsz = img.shape[0]
+        D, Cin, P, P2 = conv_w.shape
+        if P != P2:
+            raise L.VitbError("patch embedding needs square patches")
+        img = img.contiguous().float()
+        gh, gw = img.shape[2] // P, img.shape[3] // P
+        npatch = gh * gw
+        N = npatch + 1
+        K = Cin * P * P
+        fp32 = _fp32_mode()
+        hi, lo = ops.im2col(img, P, want_lo=fp32)
+        ldk = hi.shape[1]
+        whi, wlo = SHADOW.get_padded_2d(conv_w, D, K, ldk, fp32)
+        cols = [hi] + ([lo] if lo is not None else [])
+        A, Bw = _pairs(cols, [whi] + ([wlo] if wlo is not None else []))
+        x = torch.empty((Bsz, N, D), dtype=F32, device=img.device)
+        pos2 = pos.detach().reshape(-1, D)[:N].contiguous() if pos is not None else None
+        ops.gemm(A, Bw, out=x.view(Bsz * N, D), bias=conv_b.detach() if conv_b is not None else None,
+                 residual=pos2, row_remap_group=npatch)
+        ops.cls_rows(x, cls_token.detach().reshape(-1), pos2)
+        ctx.cols = cols
+        ctx.params = (conv_w, conv_b, cls_token, pos)
+        ctx.geom = (Bsz, N, D, K, ldk)
+        return x
+
+    @staticmethod
+    def backward(ctx, dx):
+        conv_w, conv_b, cls_token, pos = ctx.params
+        Bsz, N, D, K, ldk = ctx.geom
+        dx = dx.contiguous().float()
+        fp32 = _fp32_mode()
+        dev = dx.device
+        need_w = conv_w.requires_grad
+        dpos = torch.zeros((N, D), dtype=F32, device=dev) if (pos is not None and pos.requires_grad) else None
+        dcls = torch.zeros(D, dtype=F32, device=dev) if cls_token.requires_grad else None
+        dbias = torch.zeros(D, dtype=F32, device=dev) if (conv_b is not None and conv_b.requires_grad) else None
+        phi, plo = ops.embed_bwd(dx, dpos=dpos, dcls=dcls, dbias=dbias, want_patch=need_w, want_lo=fp32)
+        dw = None
+        if need_w:
+            dyo = [phi] + ([plo] if plo is not None else [])
+            A, Bm = _pairs(dyo, ctx.cols)
+            dwp = torch.zeros((D, ldk), dtype=F32, device=dev)
+            ops.gemm(A, Bm, a_mn=True, b_mn=True, out=dwp, accumulate=True)
+            dw = dwp[:, :K].reshape(conv_w.shape)
+        if dpos is not None:
+            full = torch.zeros(pos.shape, dtype=F32, device=dev)
+            full.view(-1, D)[:N] = dpos
+            dpos = full
+        ctx.cols = None
+        return (None, dw, dbias, dcls.view(cls_token.shape) if dcls is not None else None, dpos)
+
+
+def patch_embed(img, conv_w, conv_b, cls_token, pos):
+    """[B,3,H,W] -> [B, 1+np, D] fp32 = cat(cls, conv(img)) + pos   (src/model.py:197-204,17)."""
+    return _PatchEmbed.apply(img, conv_w, conv_b, cls_token, pos)
+
+
+# --------------------------------------------------------------------------------------------------
+# cross entropy
+# --------------------------------------------------------------------------------------------------
+class _CrossEntropy(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, labels):
+        L.require_cuda(logits, labels)
+        lg = logits.float().contiguous()
+        loss, dl = ops.cross_entropy(lg, labels, want_grad=logits.requires_grad)
+        ctx.save_for_backward(dl)
+        ctx.dtype = logits.dtype
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (dl,) = ctx.saved_tensors
+        return (dl * g).to(ctx.dtype), None
+
+
+def cross_entropy(logits, labels):
+    """nn.CrossEntropyLoss() (mean reduction) on [B,C] logits and int64 labels."""
+    return _CrossEntropy.apply(logits, labels)

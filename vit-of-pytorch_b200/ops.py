@@ -260,6 +260,17 @@ def embed_bwd(dx, *, dpos=None, dcls=None, dbias=None, want_patch=True, want_lo=
     return hi, lo
 
 
+def gelu_bwd(dy, z):
+    """dy * gelu'(z) elementwise (same dtype, contiguous)."""
+    L.require_cuda(dy, z)
+    if dy.dtype != z.dtype or not dy.is_contiguous() or not z.is_contiguous() or dy.shape != z.shape:
+        raise L.VitbError("gelu_bwd: dy and z must be contiguous with equal shape and dtype")
+    out = torch.empty_like(dy)
+    L.check(L._vitb_gelu_bwd(L.ptr(dy), L.ptr(z), L.ptr(out), dy.numel(), L.dtype_code(dy), L.stream_ptr(dy.device)),
+            "vitb_gelu_bwd")
+    return out
+
+
 def colsum(x, out):
     """out[c] += sum_r x[r,c]."""
     L.require_cuda(x, out)

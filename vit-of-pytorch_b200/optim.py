@@ -1,0 +1,140 @@
+"""Fused optimizers over flat buffers: one kernel per step updates every parameter, its momentum and
+the bf16 GEMM shadow of the weights (vitb_sgd_momentum / vitb_adamw in the C ABI).
+
+  FusedSGD   == torch.optim.SGD(lr, momentum, dampening, weight_decay, nesterov)   src/train.py:154-158
+  FusedAdamW == torch.optim.AdamW(lr, betas, eps, weight_decay) + clip_grad_norm_  res-vit/train.py:65,272-277
+
+Both re-home the parameters into ONE contiguous fp32 buffer, give every parameter a persistent
+gradient view into ONE contiguous fp32 gradient buffer (the autograd Functions accumulate their weight
+gradients straight into it — no per-tensor .grad allocation, one memset per step, and the data-parallel
+wrapper all-reduces slices of the same buffer), and attach views of ONE bf16 buffer as weight shadows.
+They subclass torch.optim.Optimizer so LR schedulers (OneCycleLR, cosine) drive `param_groups[...]['lr']`.
+"""
+import torch
+
+from . import functional as F
+from . import ops
+
+_ALIGN = 64  # elements: 256-byte aligned fp32 slices, 128-byte aligned bf16 slices (TMA needs 16)
+
+
+class _FlatGroup:
+    def __init__(self, params):
+        params = [p for p in params if p.requires_grad]
+        if not params:
+            raise ValueError("no trainable parameters")
+        dev = params[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("fused optimizers need the model on a CUDA (B200) device — call .cuda() first")
+        offs, total = [], 0
+        for p in params:
+            if p.device != dev or p.dtype != torch.float32:
+                raise RuntimeError("fused optimizers need fp32 parameters on one device")
+            offs.append(total)
+            total += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+        self.params, self.offsets, self.total = params, offs, total
+        self.flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_hi = torch.zeros(total, dtype=torch.bfloat16, device=dev)
+        self.flat_lo = None
+        for p, off in zip(params, offs):
+            n = p.numel()
+            self.flat_p[off:off + n].copy_(p.detach().reshape(-1))
+            p.data = self.flat_p[off:off + n].view(p.shape)
+            gview = self.flat_g[off:off + n].view(p.shape)
+            p.grad = gview
+            p._vitb_main_grad = gview
+            F.SHADOW.attach(p, self.flat_hi[off:off + n].view(p.shape))
+
+    def ensure_lo(self):
+        if self.flat_lo is None:
+            self.flat_lo = torch.zeros(self.total, dtype=torch.bfloat16, device=self.flat_p.device)
+            for p, off in zip(self.params, self.offsets):
+                n = p.numel()
+                F.SHADOW.attach(p, self.flat_hi[off:off + n].view(p.shape), self.flat_lo[off:off + n].view(p.shape))
+
+    def zero_grad(self):
+        self.flat_g.zero_()
+        for p, off in zip(self.params, self.offsets):
+            if p.grad is None or p.grad.data_ptr() != self.flat_g.data_ptr() + 4 * off:
+                p.grad = self.flat_g[off:off + p.numel()].view(p.shape)
+                p._vitb_main_grad = p.grad
+
+    def mark_fresh(self):
+        for p in self.params:
+            F.SHADOW.mark_fresh(p)
+
+
+class _FusedBase(torch.optim.Optimizer):
+    def _init_flat(self):
+        self._flat = [_FlatGroup(g["params"]) for g in self.param_groups]
+
+    def zero_grad(self, set_to_none=False):  # gradients live in the flat buffer; never set to None
+        for fg in self._flat:
+            fg.zero_grad()
+
+    def flat_grads(self):
+        """The contiguous gradient buffers (one per param group) — what the data-parallel wrapper all-reduces."""
+        return [fg.flat_g for fg in self._flat]
+
+    def flat_params(self):
+        return [fg.flat_p for fg in self._flat]
+
+
+class FusedSGD(_FusedBase):
+    def __init__(self, params, lr=1e-3, momentum=0.0, dampening=0.0, weight_decay=0.0, nesterov=False):
+        defaults = dict(lr=lr, momentum=momentum, dampening=dampening, weight_decay=weight_decay, nesterov=nesterov)
+        super().__init__(params, defaults)
+        self._init_flat()
+        self._bufs = [torch.zeros_like(fg.flat_p) if g["momentum"] != 0 else None
+                      for fg, g in zip(self._flat, self.param_groups)]
+        self._steps = 0
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        if closure is not None:
+            raise NotImplementedError("FusedSGD.step does not take a closure")
+        want_lo = F.get_precision() == "fp32"
+        for fg, g, buf in zip(self._flat, self.param_groups, self._bufs):
+            if want_lo:
+                fg.ensure_lo()
+            ops.sgd_momentum(fg.flat_p, fg.flat_g, buf, g["lr"], g["momentum"], dampening=g["dampening"],
+                             weight_decay=g["weight_decay"], nesterov=g["nesterov"], first_step=self._steps == 0,
+                             shadow_hi=fg.flat_hi, shadow_lo=fg.flat_lo)
+            fg.mark_fresh()
+        self._steps += 1
+
+
+class FusedAdamW(_FusedBase):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, max_grad_norm=None):
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        super().__init__(params, defaults)
+        self._init_flat()
+        self._m = [torch.zeros_like(fg.flat_p) for fg in self._flat]
+        self._v = [torch.zeros_like(fg.flat_p) for fg in self._flat]
+        self.max_grad_norm = max_grad_norm
+        dev = self._flat[0].flat_p.device
+        self._sumsq = torch.zeros((), dtype=torch.float32, device=dev)
+        self._coef = torch.ones((), dtype=torch.float32, device=dev)
+        self.grad_norm = torch.zeros((), dtype=torch.float32, device=dev)  # last total norm (device scalar)
+        self._steps = 0
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        if closure is not None:
+            raise NotImplementedError("FusedAdamW.step does not take a closure")
+        self._steps += 1
+        coef = None
+        if self.max_grad_norm is not None:  # clip_grad_norm_ over ALL groups, computed and applied on device
+            self._sumsq.zero_()
+            for fg in self._flat:
+                ops.sumsq(fg.flat_g, self._sumsq)
+            ops.clip_coef(self._sumsq, self.max_grad_norm, self._coef, self.grad_norm)
+            coef = self._coef
+        want_lo = F.get_precision() == "fp32"
+        for fg, g, m, v in zip(self._flat, self.param_groups, self._m, self._v):
+            if want_lo:
+                fg.ensure_lo()
+            ops.adamw(fg.flat_p, fg.flat_g, m, v, g["lr"], g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"],
+                      self._steps, grad_scale=coef, shadow_hi=fg.flat_hi, shadow_lo=fg.flat_lo)
+            fg.mark_fresh()
