@@ -83,20 +83,21 @@ class ShadowStore:
             e["pad"] = {}
         return e["hi"], (e["lo"] if want_lo else None)
 
-    def get_padded_2d(self, w, rows, cols, ld, want_lo):
-        """Shadow of w viewed [rows, cols], zero-padded to row length ld (TMA needs 16-byte row strides)."""
+    def get_padded_2d(self, w, rows, cols, rows_p, cols_p, want_lo):
+        """Shadow of w viewed [rows, cols], zero-padded to [rows_p, cols_p] (TMA needs 16-byte row strides,
+        i.e. widths that are multiples of 8 bf16 values)."""
         hi, lo = self.get(w, want_lo)
-        if ld == cols:
+        if rows_p == rows and cols_p == cols:
             return hi.view(rows, cols), (lo.view(rows, cols) if lo is not None else None)
         e = self._entry(w)
-        key = (ld, bool(want_lo))
+        key = (rows_p, cols_p, bool(want_lo))
         if key not in e["pad"]:
-            ph = torch.zeros((rows, ld), dtype=BF16, device=w.device)
-            ph[:, :cols] = hi.view(rows, cols)
+            ph = torch.zeros((rows_p, cols_p), dtype=BF16, device=w.device)
+            ph[:rows, :cols] = hi.view(rows, cols)
             pl = None
             if want_lo:
-                pl = torch.zeros((rows, ld), dtype=BF16, device=w.device)
-                pl[:, :cols] = lo.view(rows, cols)
+                pl = torch.zeros((rows_p, cols_p), dtype=BF16, device=w.device)
+                pl[:rows, :cols] = lo.view(rows, cols)
             e["pad"][key] = (ph, pl)
         return e["pad"][key]
 
@@ -189,39 +190,53 @@ def _as2d(t, cols):
 # Linear (nn.Linear [N,K] and LinearGeneral [K,N]) with fused bias / GELU / residual epilogue
 # --------------------------------------------------------------------------------------------------
 class _Linear(torch.autograd.Function):
+    """Widths that are not multiples of 8 (the classifier's num_classes) are zero-padded to the next
+    multiple of 8 on the weight side, so every TMA row stride stays 16-byte aligned."""
+
     @staticmethod
     def forward(ctx, x, weight, bias, residual, layout, act, out_dtype):
         L.require_cuda(x, weight)
         kn = layout == "kn"
         K = x.shape[-1]
         N = weight.numel() // K
+        Np = (N + 7) // 8 * 8
+        if Np != N and (kn or residual is not None or act is not None):
+            raise L.VitbError("linear: output width %d must be a multiple of 8 for this layout/epilogue" % N)
         w2 = (K, N) if kn else (N, K)
         x2 = _as2d(x, K)
         xo = _operand(x2)
-        wo = _weight_operand(weight, w2)
+        if Np != N:
+            whi, wlo = SHADOW.get_padded_2d(weight, N, K, Np, K, _fp32_mode())
+            wo = [whi] + ([wlo] if wlo is not None else [])
+        else:
+            wo = _weight_operand(weight, w2)
         A, B = _pairs(xo, wo)
         M = x2.shape[0]
-        out = torch.empty((M, N), dtype=out_dtype, device=x.device)
+        out = torch.empty((M, Np), dtype=out_dtype, device=x.device)
         need_z = act == "gelu" and (x.requires_grad or weight.requires_grad)
         z = torch.empty((M, N), dtype=out_dtype, device=x.device) if need_z else None
         res2 = _as2d(residual, N) if residual is not None else None
         b1 = bias.detach().view(-1) if bias is not None else None
+        if b1 is not None and Np != N:
+            b1 = torch.cat([b1, b1.new_zeros(Np - N)])
         if act == "gelu" and residual is not None:
             raise L.VitbError("linear: GELU and residual cannot be fused in one call")
         ops.gemm(A, B, b_mn=kn, out=out, bias=b1, residual=res2,
                  epilogue=ops.EPI_GELU if act == "gelu" else ops.EPI_NONE, d2=z)
-        ctx.kn, ctx.act, ctx.w2, ctx.N, ctx.K = kn, act, w2, N, K
+        ctx.kn, ctx.act, ctx.w2, ctx.N, ctx.K, ctx.Np = kn, act, w2, N, K, Np
         ctx.x_shape, ctx.x_dtype = x.shape, x.dtype
         ctx.has_res = residual is not None
         ctx.res_shape = residual.shape if residual is not None else None
         ctx.res_dtype = residual.dtype if residual is not None else None
         ctx.weight, ctx.bias = weight, bias
-        ctx.xo, ctx.z = xo, z
-        return out.view(*x.shape[:-1], N)
+        ctx.xo, ctx.z, ctx.wo = xo, z, wo
+        if Np != N:
+            out = out[:, :N]
+        return out.reshape(*x.shape[:-1], N)
 
     @staticmethod
     def backward(ctx, dy):
-        N, K, kn = ctx.N, ctx.K, ctx.kn
+        N, K, kn, Np = ctx.N, ctx.K, ctx.kn, ctx.Np
         weight, bias = ctx.weight, ctx.bias
         dy2 = _as2d(dy, N)
         if not dy2.is_contiguous():
@@ -231,17 +246,31 @@ class _Linear(torch.autograd.Function):
             dres = dy.reshape(ctx.res_shape).to(ctx.res_dtype)
         if ctx.act == "gelu":
             dy2 = ops.gelu_bwd(dy2, ctx.z)
+        if Np != N:
+            dyp = dy2.new_zeros((dy2.shape[0], Np))
+            dyp[:, :N] = dy2
+            dy2 = dyp
         dyo = _operand(dy2)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            wo = _weight_operand(weight, ctx.w2)
-            A, B = _pairs(dyo, wo)
+            A, B = _pairs(dyo, ctx.wo)
             dx = ops.gemm(A, B, b_mn=not kn, out_dtype=ctx.x_dtype).view(ctx.x_shape)
-        if weight.requires_grad:
-            dw = _wgrad(dyo, ctx.xo, weight, ctx.w2, dy_is_rows_of_n=not kn)
-        if bias is not None and bias.requires_grad:
-            db = _bias_grad(dy2, bias)
-        ctx.xo = ctx.z = None
+        if Np == N:
+            if weight.requires_grad:
+                dw = _wgrad(dyo, ctx.xo, weight, ctx.w2, dy_is_rows_of_n=not kn)
+            if bias is not None and bias.requires_grad:
+                db = _bias_grad(dy2, bias)
+        else:
+            if weight.requires_grad:
+                dwp = torch.zeros((Np, K), dtype=F32, device=dy.device)
+                A, B = _pairs(dyo, ctx.xo)
+                ops.gemm(A, B, a_mn=True, b_mn=True, out=dwp, accumulate=True)
+                dw = dwp[:N].reshape(weight.shape)
+            if bias is not None and bias.requires_grad:
+                dbp = torch.zeros(Np, dtype=F32, device=dy.device)
+                ops.colsum(dy2, dbp)
+                db = dbp[:N].reshape(bias.shape)
+        ctx.xo = ctx.z = ctx.wo = None
         return dx, dw, db, dres, None, None, None
 
 
@@ -558,7 +587,7 @@ class _PatchEmbed(torch.autograd.Function):
         fp32 = _fp32_mode()
         hi, lo = ops.im2col(img, P, want_lo=fp32)
         ldk = hi.shape[1]
-        whi, wlo = SHADOW.get_padded_2d(conv_w, D, K, ldk, fp32)
+        whi, wlo = SHADOW.get_padded_2d(conv_w, D, K, D, ldk, fp32)
         cols = [hi] + ([lo] if lo is not None else [])
         A, Bw = _pairs(cols, [whi] + ([wlo] if wlo is not None else []))
         x = torch.empty((Bsz, N, D), dtype=F32, device=img.device)
