@@ -86,9 +86,13 @@ def last_error():
     return buf.value.decode(errors="replace")
 
 
+LAUNCHES = [0]  # number of successful kernel-launching ABI calls (each launches exactly one kernel)
+
+
 def check(status, what):
     if status != 0:
         raise VitbError("%s failed (%d): %s" % (what, status, last_error()))
+    LAUNCHES[0] += 1
 
 
 def stream_ptr(device=None):

@@ -11,6 +11,11 @@ from . import _lib as L
 from ._lib import EPI_GELU, EPI_GELU_BWD, EPI_NONE  # noqa: F401
 
 
+# When set to a list, every gemm() call appends (start_event, end_event, flops): bench.py uses it to time
+# the dominant kernel live with CUDA events on the launching stream.
+PROFILE_GEMM = None
+
+
 def _as_list(x):
     return list(x) if isinstance(x, (list, tuple)) else [x]
 
@@ -87,6 +92,13 @@ def gemm(A, B, *, a_mn=False, b_mn=False, out=None, out_dtype=torch.bfloat16, bi
         if aux.dtype != out.dtype:
             raise L.VitbError("gemm: aux must have the dtype of the output")
         p.aux, p.ldaux = aux.data_ptr(), aux.stride(0)
+    if PROFILE_GEMM is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        L.check(L._vitb_gemm(C.byref(p), L.stream_ptr(out.device)), "vitb_gemm")
+        e1.record()
+        PROFILE_GEMM.append((e0, e1, 2.0 * M * N * sum(int(p.K[i]) for i in range(len(As)))))
+        return out
     L.check(L._vitb_gemm(C.byref(p), L.stream_ptr(out.device)), "vitb_gemm")
     return out
 
