@@ -36,6 +36,9 @@ cases = [
     # name, (A shape, a_mn), (B shape, b_mn), out dtype, extra kwargs, flops
     ("fwd qkv  [T,768]x[2304,768]^T", (T, D), False, (3 * D, D), False, bf, {}),
     ("fwd out  [T,768]x[768,768]^T f32+res", (T, D), False, (D, D), False, torch.float32, {"res": True}),
+    ("fwd fc1  [T,768]x[3072,768]^T plain", (T, D), False, (M, D), False, bf, {}),
+    ("fwd fc1  [T,768]x[3072,768]^T bias", (T, D), False, (M, D), False, bf, {"bias": True}),
+    ("fwd fc1  [T,768]x[3072,768]^T gelu no z", (T, D), False, (M, D), False, bf, {"gelu": True, "noz": True}),
     ("fwd fc1  [T,768]x[3072,768]^T gelu", (T, D), False, (M, D), False, bf, {"gelu": True}),
     ("fwd fc2  [T,3072]x[768,3072]^T f32+res", (T, M), False, (D, M), False, torch.float32, {"res": True}),
     ("dgrad fc2 [T,768]x[768,3072] gelu'", (T, D), False, (D, M), True, bf, {"gelu_bwd": True}),
@@ -56,8 +59,11 @@ for name, ash, amn, bsh, bmn, odt, kw in cases:
     args = dict(a_mn=amn, b_mn=bmn, out=out)
     if kw.get("res"):
         args.update(bias=bias, residual=torch.randn(Mm, Nn, device="cuda"))
+    if kw.get("bias"):
+        args.update(bias=bias)
     if kw.get("gelu"):
-        args.update(bias=bias, epilogue=vitb200.ops.EPI_GELU, d2=torch.empty(Mm, Nn, device="cuda", dtype=bf))
+        args.update(bias=bias, epilogue=vitb200.ops.EPI_GELU,
+                    d2=None if kw.get("noz") else torch.empty(Mm, Nn, device="cuda", dtype=bf))
     if kw.get("gelu_bwd"):
         args.update(epilogue=vitb200.ops.EPI_GELU_BWD, aux=torch.randn(Mm, Nn, device="cuda").to(bf))
     if kw.get("acc"):

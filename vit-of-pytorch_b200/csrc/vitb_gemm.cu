@@ -24,12 +24,13 @@ using namespace vitb;
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kThreads = 256;
 constexpr int kEpiWarp0 = 4;
+constexpr int kEpiWarps = 8;                         // 2 per TMEM lane quadrant, each owning half of the columns
+constexpr int kThreads = (kEpiWarp0 + kEpiWarps) * 32;
 constexpr int A_BYTES = BM * BK * 2;                 // 16 KiB
-constexpr int kStgStride = 36;                       // floats per staged row: 16B-aligned, conflict-free
+constexpr int kStgStride = 34;                       // floats per staged row: 8B-aligned, conflict-free float2 access
 constexpr int kStagingFloats = 32 * kStgStride;      // per epilogue warp
-constexpr int kStagingBytes = 4 * kStagingFloats * 4;
+constexpr int kStagingBytes = kEpiWarps * kStagingFloats * 4;
 
 template <int BN>
 struct Cfg {
@@ -37,7 +38,8 @@ struct Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : 6;
   static constexpr int TMEM_COLS = 2 * BN;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + kStagingBytes + 256 /*barriers*/ + 1024 /*align*/;
+  // no alignment slack: the dynamic shared window starts 1024-byte aligned (checked at kernel entry)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + kStagingBytes + 256 /*barriers*/;
 };
 
 struct GemmDev {
@@ -84,10 +86,39 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmDev& p, int tile) {
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
+__device__ __forceinline__ void st_shared_v2(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {  // two 8-byte loads (rows are 8B-aligned)
   float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.z), "=f"(v.w) : "r"(addr + 8) : "memory");
   return v;
+}
+// erf-GELU and its derivative from ONE rcp + ONE ex2 (Abramowitz-Stegun 7.1.26, |erf error| < 1.5e-7):
+// used where the result is rounded to bf16 anyway; fp32 outputs keep erff.
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void gelu_fast(float z, float& g, float& dg) {
+  const float u = fabsf(z) * 0.70710678118654752440f;
+  const float t = rcp_approx(fmaf(0.3275911f, u, 1.0f));
+  const float e = ex2_approx(-0.72134752044448170368f * z * z);     // exp(-z^2/2) = exp(-u^2)
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erf_abs = fmaf(-poly * t, e, 1.0f);                   // erf(|u|)
+  const float cdf = 0.5f * (1.0f + copysignf(erf_abs, z));
+  g = z * cdf;
+  dg = fmaf(z * 0.39894228040143267794f, e, cdf);
 }
 __device__ __forceinline__ float ld_shared_f1(uint32_t addr) {
   float v;
@@ -155,10 +186,22 @@ __device__ __forceinline__ void epi_vec(const GemmDev& p, uint32_t stg, int lane
           *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.D2) + static_cast<long long>(m) * p.ldd2 + col) = v;
         }
       }
-      v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
+      if constexpr (OUT_BF16) {
+        float d;
+        gelu_fast(v.x, v.x, d); gelu_fast(v.y, v.y, d); gelu_fast(v.z, v.z, d); gelu_fast(v.w, v.w, d);
+      } else {
+        v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
+      }
     } else if constexpr (EPI == VITB_EPI_GELU_BWD) {
-      v.x *= gelu_erf_grad(side[it].x); v.y *= gelu_erf_grad(side[it].y);
-      v.z *= gelu_erf_grad(side[it].z); v.w *= gelu_erf_grad(side[it].w);
+      if constexpr (OUT_BF16) {
+        float g, d0, d1, d2, d3;
+        gelu_fast(side[it].x, g, d0); gelu_fast(side[it].y, g, d1);
+        gelu_fast(side[it].z, g, d2); gelu_fast(side[it].w, g, d3);
+        v.x *= d0; v.y *= d1; v.z *= d2; v.w *= d3;
+      } else {
+        v.x *= gelu_erf_grad(side[it].x); v.y *= gelu_erf_grad(side[it].y);
+        v.z *= gelu_erf_grad(side[it].z); v.w *= gelu_erf_grad(side[it].w);
+      }
     }
     if constexpr (RES != 0) { v.x += side[it].x; v.y += side[it].y; v.z += side[it].z; v.w += side[it].w; }
     if constexpr (OUT_BF16) {
@@ -221,11 +264,14 @@ __global__ void __launch_bounds__(kThreads, 1)
 vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
                  const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
-                 const GemmDev p) {
+                 const __grid_constant__ GemmDev p) {
   using C = Cfg<BN>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) {  // SWIZZLE_128B tiles need 1024-byte aligned stage bases
+    if (threadIdx.x == 0) printf("vitb_gemm: dynamic shared memory base 0x%x is not 1024-byte aligned\n", smem_u32(smem));
+    __trap();
+  }
   float* staging = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES + kStagingBytes);
   // bars: [0,STAGES) full, [STAGES,2*STAGES) empty, then tmem_full[2], tmem_empty[2]
@@ -251,7 +297,7 @@ vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull0 + 8 * s, 1);
-      mbar_init(tempty0 + 8 * s, 4);  // one arrive per epilogue warp
+      mbar_init(tempty0 + 8 * s, kEpiWarps);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -342,8 +388,13 @@ vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const uint32_t stg = smem_u32(staging) + static_cast<uint32_t>((warp - kEpiWarp0) * kStagingFloats * 4);
     int acc = 0;
     uint32_t acc_phase = 0;
-    const bool vec_ok = p.vec_ok != 0;
-    const int res_mode = p.residual == nullptr ? 0 : (p.r_bf16 ? 2 : 1);
+    // one register-resident mode selects the epilogue instantiation (decided once, not per chunk)
+    int mode = 0;  // 0 generic
+    if (p.vec_ok) {
+      const int res_mode = p.residual == nullptr ? 0 : (p.r_bf16 ? 2 : 1);
+      const int e = p.epilogue == VITB_EPI_GELU ? 1 : (p.epilogue == VITB_EPI_GELU_BWD ? 2 : 3 + res_mode);
+      mode = p.accumulate ? 1 : (p.d_bf16 ? 1 + e : 6 + e);
+    }
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile);
       const int n0 = t.n_blk * BN;
@@ -352,8 +403,9 @@ vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       tc_fence_after();
       // bias-type terms are added exactly once: by the split that owns the first k-block
       const bool lead_split = (t.g0 == 0);
+      const int half = (warp - kEpiWarp0) >> 2;  // which half of the tile's columns this warp drains
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
         const int col0 = n0 + c * 32;
         if (col0 >= p.N) break;
         {
@@ -362,27 +414,22 @@ vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                                  static_cast<uint32_t>(acc * BN + c * 32), r);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            st_shared_v4(stg + lane * (kStgStride * 4) + j * 16, r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          for (int j = 0; j < 16; ++j) st_shared_v2(stg + lane * (kStgStride * 4) + j * 8, r[2 * j], r[2 * j + 1]);
         }
         __syncwarp();
-        if (vec_ok) {
-          if (p.accumulate) epi_vec<false, VITB_EPI_NONE, 0, true>(p, stg, lane, row_base, col0, lead_split);
-          else if (p.d_bf16) {
-            if (p.epilogue == VITB_EPI_GELU) epi_vec<true, VITB_EPI_GELU, 0, false>(p, stg, lane, row_base, col0, lead_split);
-            else if (p.epilogue == VITB_EPI_GELU_BWD) epi_vec<true, VITB_EPI_GELU_BWD, 0, false>(p, stg, lane, row_base, col0, lead_split);
-            else if (res_mode == 0) epi_vec<true, VITB_EPI_NONE, 0, false>(p, stg, lane, row_base, col0, lead_split);
-            else if (res_mode == 1) epi_vec<true, VITB_EPI_NONE, 1, false>(p, stg, lane, row_base, col0, lead_split);
-            else epi_vec<true, VITB_EPI_NONE, 2, false>(p, stg, lane, row_base, col0, lead_split);
-          } else {
-            if (p.epilogue == VITB_EPI_GELU) epi_vec<false, VITB_EPI_GELU, 0, false>(p, stg, lane, row_base, col0, lead_split);
-            else if (p.epilogue == VITB_EPI_GELU_BWD) epi_vec<false, VITB_EPI_GELU_BWD, 0, false>(p, stg, lane, row_base, col0, lead_split);
-            else if (res_mode == 0) epi_vec<false, VITB_EPI_NONE, 0, false>(p, stg, lane, row_base, col0, lead_split);
-            else if (res_mode == 1) epi_vec<false, VITB_EPI_NONE, 1, false>(p, stg, lane, row_base, col0, lead_split);
-            else epi_vec<false, VITB_EPI_NONE, 2, false>(p, stg, lane, row_base, col0, lead_split);
-          }
-        } else {
-          epi_generic(p, stg, lane, row_base, col0, lead_split);
+        switch (mode) {
+          case 1: epi_vec<false, VITB_EPI_NONE, 0, true>(p, stg, lane, row_base, col0, lead_split); break;
+          case 2: epi_vec<true, VITB_EPI_GELU, 0, false>(p, stg, lane, row_base, col0, lead_split); break;
+          case 3: epi_vec<true, VITB_EPI_GELU_BWD, 0, false>(p, stg, lane, row_base, col0, lead_split); break;
+          case 4: epi_vec<true, VITB_EPI_NONE, 0, false>(p, stg, lane, row_base, col0, lead_split); break;
+          case 5: epi_vec<true, VITB_EPI_NONE, 1, false>(p, stg, lane, row_base, col0, lead_split); break;
+          case 6: epi_vec<true, VITB_EPI_NONE, 2, false>(p, stg, lane, row_base, col0, lead_split); break;
+          case 7: epi_vec<false, VITB_EPI_GELU, 0, false>(p, stg, lane, row_base, col0, lead_split); break;
+          case 8: epi_vec<false, VITB_EPI_GELU_BWD, 0, false>(p, stg, lane, row_base, col0, lead_split); break;
+          case 9: epi_vec<false, VITB_EPI_NONE, 0, false>(p, stg, lane, row_base, col0, lead_split); break;
+          case 10: epi_vec<false, VITB_EPI_NONE, 1, false>(p, stg, lane, row_base, col0, lead_split); break;
+          case 11: epi_vec<false, VITB_EPI_NONE, 2, false>(p, stg, lane, row_base, col0, lead_split); break;
+          default: epi_generic(p, stg, lane, row_base, col0, lead_split); break;
         }
         __syncwarp();
       }
