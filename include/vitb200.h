@@ -57,7 +57,7 @@ int vitb_struct_size(int which);
  *   b_mn_major = 1: B_seg is stored [K,N] (N contiguous)  — LinearGeneral layout / dgrad / wgrad
  * Epilogue, in this order:  v = acc ; v += bias[n] ; v += row_bias[m / row_bias_group, n] ;
  *   (GELU: optionally store v to d2 (pre-activation), v = gelu_erf(v)) ;
- *   (GELU_BWD: v *= gelu_erf'(aux[m,n])) ; v += residual[rm, n] ; D[om, n] (+)= v
+ *   (GELU_BWD: v *= gelu_erf'(aux[m,n])) ; v += residual[rm, n] ; D[om, n] (+)= v ; colsum[n] += v
  * where for row_remap_group = g > 0 (patch-embedding scatter):  om = m + m/g + 1, rm = m%g + 1,
  * otherwise om = rm = m.
  */
@@ -94,6 +94,7 @@ typedef struct vitb_gemm_params {
   int32_t _pad0;
   const void* aux; /* [M,N] pre-activation for VITB_EPI_GELU_BWD, same dtype as D */
   int64_t ldaux;
+  float* colsum; /* optional [N]: += column sums of the values written to D (bias gradient of the producer) */
 } vitb_gemm_params;
 
 int vitb_gemm(const vitb_gemm_params* p, void* stream);

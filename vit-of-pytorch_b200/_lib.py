@@ -63,6 +63,7 @@ class GemmParams(C.Structure):
         ("_pad0", C.c_int32),
         ("aux", C.c_void_p),
         ("ldaux", C.c_int64),
+        ("colsum", C.c_void_p),
     ]
 
 

@@ -154,21 +154,31 @@ embed_bwd_kernel(const float* __restrict__ dx, int Bsz, int N, int D, float* __r
 // out[c] += sum_r x[r, c]; thread owns 4 columns (bf16) / 4 columns (fp32), rows split across blocks.y
 template <bool BF16>
 __global__ void __launch_bounds__(kThreads)
-colsum_kernel(const void* __restrict__ x_, int rows, int cols, long long ld, float* __restrict__ out) {
+colsum_kernel(const void* __restrict__ x_, int rows, int cols, long long ld_, float* __restrict__ out) {
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (c >= cols) return;
   const int rows_per = (rows + gridDim.y - 1) / gridDim.y;
   const int r0 = blockIdx.y * rows_per;
   const int r1 = min(rows, r0 + rows_per);
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int r = r0; r < r1; ++r) {
-    float4 v;
+  auto ld = [&](int r) {
     if constexpr (BF16) {
-      const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(x_) + static_cast<long long>(r) * ld + c);
-      v = make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
+      const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(x_) + static_cast<long long>(r) * ld_ + c);
+      return make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
     } else {
-      v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x_) + static_cast<long long>(r) * ld + c);
+      return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x_) + static_cast<long long>(r) * ld_ + c);
     }
+  };
+  int r = r0;
+  for (; r + 8 <= r1; r += 8) {  // 8 independent loads in flight per thread
+    float4 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = ld(r + j);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s.x += v[j].x; s.y += v[j].y; s.z += v[j].z; s.w += v[j].w; }
+  }
+  for (; r < r1; ++r) {
+    const float4 v = ld(r);
     s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
   }
   atomicAdd(out + c + 0, s.x); atomicAdd(out + c + 1, s.y);

@@ -66,6 +66,7 @@ struct GemmDev {
   const void* aux;
   long long ldaux;
   int vec_ok;  // 128-bit epilogue path usable (set by the host from shapes and alignment)
+  float* colsum;  // optional [N]: += column sums of the values stored to D (vectorised path only)
 };
 
 struct TileCoord {
@@ -136,16 +137,17 @@ __device__ __forceinline__ void epi_vec(const GemmDev& p, uint32_t stg, int lane
   const int rsub = lane >> 3;
   const int c4 = (lane & 7) * 4;
   const int col = col0 + c4;
-  if (col >= p.N) return;
+  const bool col_ok = col < p.N;
   float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (p.bias != nullptr && lead_split) bv = *reinterpret_cast<const float4*>(p.bias + col);
+  if (p.bias != nullptr && lead_split && col_ok) bv = *reinterpret_cast<const float4*>(p.bias + col);
+  float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);   // column sums of the stored values (bias gradients)
   float4 side[8];
   if constexpr (RES != 0 || EPI == VITB_EPI_GELU_BWD) {
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       const int m = row_base + it * 4 + rsub;
       side[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (m < p.M) {
+      if (m < p.M && col_ok) {
         if constexpr (EPI == VITB_EPI_GELU_BWD) {
           if constexpr (OUT_BF16) {
             const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.aux) +
@@ -173,7 +175,7 @@ __device__ __forceinline__ void epi_vec(const GemmDev& p, uint32_t stg, int lane
   for (int it = 0; it < 8; ++it) {
     const int rl = it * 4 + rsub;
     const int m = row_base + rl;
-    if (m >= p.M) continue;
+    if (m >= p.M || !col_ok) continue;
     float4 v = ld_shared_f4(stg + rl * (kStgStride * 4) + c4 * 4);
     v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
     if constexpr (EPI == VITB_EPI_GELU) {
@@ -204,6 +206,7 @@ __device__ __forceinline__ void epi_vec(const GemmDev& p, uint32_t stg, int lane
       }
     }
     if constexpr (RES != 0) { v.x += side[it].x; v.y += side[it].y; v.z += side[it].z; v.w += side[it].w; }
+    cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
     if constexpr (OUT_BF16) {
       uint2 o;
       o.x = pack_bf16x2(v.x, v.y); o.y = pack_bf16x2(v.z, v.w);
@@ -213,6 +216,13 @@ __device__ __forceinline__ void epi_vec(const GemmDev& p, uint32_t stg, int lane
       if constexpr (ACC) atomicAdd(reinterpret_cast<float4*>(dst), v);
       else *reinterpret_cast<float4*>(dst) = v;
     }
+  }
+  if (p.colsum != nullptr) {  // warp-uniform: fold the 4 row groups (lanes l, l+8, l+16, l+24), one red per column
+    cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 8);  cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 8);
+    cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 8);  cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 8);
+    cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 16); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 16);
+    cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 16); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 16);
+    if (lane < 8 && col_ok) atomicAdd(reinterpret_cast<float4*>(p.colsum + col), cs);
   }
 }
 
@@ -547,6 +557,9 @@ extern "C" int vitb_gemm(const vitb_gemm_params* p, void* stream_) {
                (p->aux == nullptr || (p->ldaux % 4 == 0 && al(p->aux, d_al))) &&
                !(p->accumulate && (p->residual != nullptr || p->epilogue != VITB_EPI_NONE)) &&
                !(p->epilogue != VITB_EPI_NONE && p->residual != nullptr);
+    d.colsum = p->colsum;
+    VITB_REQUIRE(p->colsum == nullptr || (d.vec_ok && al(p->colsum, 16) && !p->accumulate), VITB_ERR_UNSUPPORTED_SHAPE,
+                 "vitb_gemm: colsum needs the vectorised epilogue (N, lds multiples of 4, 16-byte aligned pointers)");
   }
 
   CUtensorMap tm[6];

@@ -654,3 +654,170 @@ class _CrossEntropy(torch.autograd.Function):
 def cross_entropy(logits, labels):
     """nn.CrossEntropyLoss() (mean reduction) on [B,C] logits and int64 labels."""
     return _CrossEntropy.apply(logits, labels)
+
+
+# --------------------------------------------------------------------------------------------------
+# fused pre-LN encoder block (bf16 mode): the whole block forward / backward as one autograd node
+# --------------------------------------------------------------------------------------------------
+# Side channel between consecutive blocks in the backward pass: the block that produces dx (fp32, for
+# autograd) also has it in bf16 (the next GEMM operand) and knows its column sums (the bias gradient of
+# the Linear that fed this block's input).  Keyed by storage pointer; consumed (popped) by the upstream
+# block's backward, so a stale entry can only be hit by a tensor occupying the very same storage with the
+# same size in the same backward pass.
+_GRAD_SIDE = {}
+
+
+def _acc(param, shape=None):
+    """(fp32 accumulator viewed `shape`, value to return to autograd) for a parameter gradient."""
+    tgt = _grad_target(param)
+    if tgt is not None:
+        return (tgt.view(shape) if shape is not None else tgt), None
+    buf = torch.zeros(param.shape, dtype=F32, device=param.device)
+    return (buf.view(shape) if shape is not None else buf), buf
+
+
+class _EncoderBlockFused(torch.autograd.Function):
+    """y = h + MLP(LN2(h)),  h = x + Attn(LN1(x))   (src/model.py:117-130), weights in LinearGeneral
+    ("kn") layout for attention and nn.Linear ("nk") layout for the MLP.
+
+    Forward: 2 LayerNorm kernels, 6 tcgen05 GEMMs (q, k, v into one packed buffer; out+residual; fc1+GELU;
+    fc2+residual), 1 tcgen05 attention.  Backward: 10 GEMMs (GELU' and bias-gradient column sums ride in
+    their epilogues), 1 attention backward, 2 LayerNorm backwards that add the residual-branch gradient,
+    emit the bf16 operand copy and the neighbouring bias gradients in the same pass."""
+
+    @staticmethod
+    def forward(ctx, x, H, eps1, eps2, n1w, n1b, wq, bq, wk, bk, wv, bv, wo, bo, n2w, n2b, w1, b1, w2, b2):
+        L.require_cuda(x)
+        Bsz, N, D = x.shape
+        T = Bsz * N
+        Mh = w1.shape[0]
+        x2 = x.reshape(T, D)
+        if x2.dtype != F32 or not x2.is_contiguous():
+            x2 = x2.float().contiguous()
+        dev = x.device
+        _, xn, _, mean1, rstd1 = ops.layernorm_fwd(x2, n1w.detach(), n1b.detach(), eps1)
+        qkv = torch.empty((T, 3 * D), dtype=BF16, device=dev)
+        for i, (w, b) in enumerate(((wq, bq), (wk, bk), (wv, bv))):
+            ops.gemm(xn, SHADOW.get(w, False)[0].view(D, D), b_mn=True, out=qkv[:, i * D:(i + 1) * D],
+                     bias=b.detach().view(-1))
+        qkv3 = qkv.view(Bsz, N, 3 * D)
+        o, lse = ops.attn_fwd(qkv3[:, :, :D], qkv3[:, :, D:2 * D], qkv3[:, :, 2 * D:], H)
+        o2 = o.view(T, D)
+        h = torch.empty((T, D), dtype=F32, device=dev)
+        ops.gemm(o2, SHADOW.get(wo, False)[0].view(D, D), b_mn=True, out=h, bias=bo.detach().view(-1), residual=x2)
+        _, hn, _, mean2, rstd2 = ops.layernorm_fwd(h, n2w.detach(), n2b.detach(), eps2)
+        a = torch.empty((T, Mh), dtype=BF16, device=dev)
+        z = torch.empty((T, Mh), dtype=BF16, device=dev)
+        ops.gemm(hn, SHADOW.get(w1, False)[0], out=a, bias=b1.detach(), epilogue=ops.EPI_GELU, d2=z)
+        y = torch.empty((T, D), dtype=F32, device=dev)
+        ops.gemm(a, SHADOW.get(w2, False)[0], out=y, bias=b2.detach(), residual=h)
+        ctx.save_for_backward(x2, xn, mean1, rstd1, qkv, o, lse, h, hn, mean2, rstd2, z, a)
+        ctx.params = (n1w, n1b, wq, bq, wk, bk, wv, bv, wo, bo, n2w, n2b, w1, b1, w2, b2)
+        ctx.geom = (Bsz, N, D, Mh, H)
+        ctx.x_shape = x.shape
+        return y.view(Bsz, N, D)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, xn, mean1, rstd1, qkv, o, lse, h, hn, mean2, rstd2, z, a = ctx.saved_tensors
+        n1w, n1b, wq, bq, wk, bk, wv, bv, wo, bo, n2w, n2b, w1, b1, w2, b2 = ctx.params
+        Bsz, N, D, Mh, H = ctx.geom
+        T = Bsz * N
+        dev = dy.device
+        dy2 = dy.reshape(T, D)
+        if dy2.dtype != F32 or not dy2.is_contiguous():
+            dy2 = dy2.float().contiguous()
+        side = _GRAD_SIDE.pop((dy2.data_ptr(), dy2.numel()), None)
+        if side is not None:
+            dyb, dy_colsum = side
+        else:
+            dyb, dy_colsum = ops.cast_split(dy2)[0], None
+        grads = {}
+
+        def ret(p, val):
+            grads[id(p)] = val
+
+        # ---- MLP ----
+        acc_b2, r = _acc(b2)
+        ret(b2, r)
+        if dy_colsum is not None:
+            acc_b2.add_(dy_colsum)
+        else:
+            ops.colsum(dy2, acc_b2)
+        acc_b1, r = _acc(b1)
+        ret(b1, r)
+        dz = torch.empty((T, Mh), dtype=BF16, device=dev)
+        ops.gemm(dyb, SHADOW.get(w2, False)[0], b_mn=True, out=dz, epilogue=ops.EPI_GELU_BWD, aux=z, colsum=acc_b1)
+        acc, r = _acc(w2)
+        ret(w2, r)
+        ops.gemm(dyb, a, a_mn=True, b_mn=True, out=acc, accumulate=True)
+        acc, r = _acc(w1)
+        ret(w1, r)
+        ops.gemm(dz, hn, a_mn=True, b_mn=True, out=acc, accumulate=True)
+        dhn = ops.gemm(dz, SHADOW.get(w1, False)[0], b_mn=True, out_dtype=BF16)
+        del dz
+        # ---- LN2 backward + residual: dh = dy + LN'(dhn); column sums of dh = d(out-proj bias) ----
+        acc_g2, rg = _acc(n2w)
+        acc_be2, rb = _acc(n2b)
+        ret(n2w, rg)
+        ret(n2b, rb)
+        acc_bo, r = _acc(bo)
+        ret(bo, r)
+        dh, dhb, _ = ops.layernorm_bwd(dhn, h, mean2, rstd2, n2w.detach(), dres=dy2, want_f32=True, want_bf16=True,
+                                       dgamma=acc_g2, dbeta=acc_be2, dcolsum=acc_bo.view(-1))
+        # ---- attention ----
+        acc, r = _acc(wo, (D, D))
+        ret(wo, r)
+        ops.gemm(o.view(T, D), dhb, a_mn=True, b_mn=True, out=acc, accumulate=True)     # dWo[K,N] = o^T dh
+        do = ops.gemm(dhb, SHADOW.get(wo, False)[0].view(D, D), b_mn=False, out_dtype=BF16)
+        qkv3 = qkv.view(Bsz, N, 3 * D)
+        dqkv = torch.empty((Bsz, N, 3 * D), dtype=BF16, device=dev)
+        ops.attn_bwd(do.view(Bsz, N, D), qkv3[:, :, :D], qkv3[:, :, D:2 * D], qkv3[:, :, 2 * D:], o, lse, H,
+                     dq=dqkv[:, :, :D], dk=dqkv[:, :, D:2 * D], dv=dqkv[:, :, 2 * D:])
+        dq2 = dqkv.view(T, 3 * D)
+        for i, (w, b) in enumerate(((wq, bq), (wk, bk), (wv, bv))):
+            sl = dq2[:, i * D:(i + 1) * D]
+            acc, r = _acc(w, (D, D))
+            ret(w, r)
+            ops.gemm(xn, sl, a_mn=True, b_mn=True, out=acc, accumulate=True)              # dW[K,N] = xn^T dQ
+            accb, r = _acc(b)
+            ret(b, r)
+            ops.colsum(sl, accb.view(-1))
+        dxn = ops.gemm([dq2[:, :D], dq2[:, D:2 * D], dq2[:, 2 * D:]],
+                       [SHADOW.get(w, False)[0].view(D, D) for w in (wq, wk, wv)], b_mn=False, out_dtype=BF16)
+        # ---- LN1 backward + residual: dx = dh + LN'(dxn) ----
+        acc_g1, rg = _acc(n1w)
+        acc_be1, rb = _acc(n1b)
+        ret(n1w, rg)
+        ret(n1b, rb)
+        need_dx = ctx.needs_input_grad[0]
+        dx = None
+        if need_dx:
+            colsum_dx = torch.zeros(D, dtype=F32, device=dev)
+            dx, dxb, _ = ops.layernorm_bwd(dxn, x2, mean1, rstd1, n1w.detach(), dres=dh, want_f32=True,
+                                           want_bf16=True, dgamma=acc_g1, dbeta=acc_be1, dcolsum=colsum_dx)
+            _GRAD_SIDE[(dx.data_ptr(), dx.numel())] = (dxb, colsum_dx)
+            dx = dx.view(ctx.x_shape)
+        else:
+            ops.layernorm_bwd(dxn, x2, mean1, rstd1, n1w.detach(), dres=dh, want_f32=False, dgamma=acc_g1,
+                              dbeta=acc_be1)
+        out = [dx, None, None, None]
+        for p in ctx.params:
+            out.append(grads.get(id(p)) if p.requires_grad else None)
+        return tuple(out)
+
+
+def encoder_block(x, H, norm1, q, k, v, o, norm2, fc1, fc2):
+    """Fused block when possible (bf16 mode, head_dim 64, <= 256 tokens), else None (caller composes ops)."""
+    D = x.shape[-1]
+    if _fp32_mode() or D % H != 0 or not ops.attn_supported_tc(D // H, x.shape[1], x.shape[1], BF16):
+        return None
+    if not all(p.requires_grad for m in (norm1, q, k, v, o, norm2, fc1, fc2) for p in m.parameters()) and torch.is_grad_enabled():
+        return None
+    return _EncoderBlockFused.apply(x, H, norm1.eps, norm2.eps, norm1.weight, norm1.bias, q.weight, q.bias, k.weight,
+                                    k.bias, v.weight, v.bias, o.weight, o.bias, norm2.weight, norm2.bias,
+                                    fc1.weight, fc1.bias, fc2.weight, fc2.bias)
+
+
+def clear_grad_side_channel():
+    _GRAD_SIDE.clear()

@@ -122,6 +122,11 @@ class EncoderBlock(nn.Module):
         if self.training:
             _dropout_supported(self.dropout_rate, "EncoderBlock")
         x = x if x.dtype == torch.float32 else x.float()
+        if x.dim() == 3:
+            y = F.encoder_block(x, self.attn.heads, self.norm1, self.attn.query, self.attn.key, self.attn.value,
+                                self.attn.out, self.norm2, self.mlp.fc1, self.mlp.fc2)
+            if y is not None:
+                return y
         out = F.layer_norm(x, self.norm1.weight, self.norm1.bias, self.norm1.eps)
         h = self.attn(out, residual=x)
         out = F.layer_norm(h, self.norm2.weight, self.norm2.bias, self.norm2.eps)

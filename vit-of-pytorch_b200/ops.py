@@ -28,7 +28,7 @@ def _check_2d_rowmajor(t, what):
 
 def gemm(A, B, *, a_mn=False, b_mn=False, out=None, out_dtype=torch.bfloat16, bias=None,
          row_bias=None, row_bias_group=0, epilogue=EPI_NONE, d2=None, residual=None, aux=None,
-         accumulate=False, split_k=0, row_remap_group=0, out_rows=None):
+         accumulate=False, split_k=0, row_remap_group=0, out_rows=None, colsum=None):
     """D[M,N] = epilogue(sum_i A_i B_i^T) on the tcgen05 GEMM (contract: include/vitb200.h).
 
     a_mn=False: A_i is [M,K_i]; a_mn=True: A_i is stored [K_i,M].  Same for B with N.
@@ -92,6 +92,10 @@ def gemm(A, B, *, a_mn=False, b_mn=False, out=None, out_dtype=torch.bfloat16, bi
         if aux.dtype != out.dtype:
             raise L.VitbError("gemm: aux must have the dtype of the output")
         p.aux, p.ldaux = aux.data_ptr(), aux.stride(0)
+    if colsum is not None:
+        if colsum.dtype != torch.float32 or colsum.numel() != N or not colsum.is_contiguous():
+            raise L.VitbError("gemm: colsum must be contiguous fp32 [N]")
+        p.colsum = colsum.data_ptr()
     if PROFILE_GEMM is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

@@ -70,6 +70,7 @@ class _FusedBase(torch.optim.Optimizer):
         self._flat = [_FlatGroup(g["params"]) for g in self.param_groups]
 
     def zero_grad(self, set_to_none=False):  # gradients live in the flat buffer; never set to None
+        F.clear_grad_side_channel()
         for fg in self._flat:
             fg.zero_grad()
 
