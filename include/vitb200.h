@@ -177,6 +177,33 @@ int vitb_gelu_bwd(const void* dy, const void* z, void* out, int64_t n, int dtype
 /* out[c] += sum_r x[r,c]  (bias gradients). */
 int vitb_colsum(const void* x, int x_dtype, int rows, int cols, int64_t ld, float* out, void* stream);
 
+/* ---- Res-ViT routing ---------------------------------------------------------------------------
+ * Decision tail of RouterModule.forward (res-vit/model.py:189-211) + _router2indices (:169-173).
+ * logits [T, bs, 2] fp32 (T = B*N tokens, token n = t %% N is "reserved" when n < reserve_initials):
+ *   soft   = softmax(logits, -1)
+ *   entropy_sum += -sum over non-reserved tokens of p*log(p + 1e-8)   (caller divides by B*(N-r0)*bs)
+ *   hard   = one_hot(argmax softmax((logits + noise)/tau))  in training (noise = Gumbel sample supplied by
+ *            the caller, exactly -log(Exponential(1)) as torch's F.gumbel_softmax draws it; ysoft saved)
+ *          = one_hot(argmax soft)                            in eval        (first index wins ties)
+ *   reserved tokens are forced to (0, 1);  indices[t] = sum_i hard[t,i,1] * 2^(bs-1-i)  (fp32 integers)
+ */
+int vitb_router_decide_fwd(const float* logits, const float* noise, int T, int N, int block_size,
+                           int reserve_initials, int training, float tau, float* soft, float* hard,
+                           float* ysoft, float* indices, float* entropy_sum, void* stream);
+/* d_logits = softmax'(soft; d_soft + d_entropy*entropy_scale*dH/dp) + (training) softmax'(ysoft; d_hard)/tau;
+ * reserved tokens receive no entropy / straight-through gradient.  d_soft, d_hard, d_entropy optional. */
+int vitb_router_decide_bwd(const float* soft, const float* ysoft, const float* d_soft, const float* d_hard,
+                           const float* d_entropy, float entropy_scale, int T, int N, int block_size,
+                           int reserve_initials, int training, float tau, float* d_logits, void* stream);
+/* Global router feature: out[b,c] = mean_{n >= reserve_initials} x[b,n,c] (res-vit/model.py:180-184); x is
+ * [B,N,C] f32/bf16.  bwd writes dx[b,n,c] = dg[b,c]/(N-r0) for n >= r0, 0 otherwise. */
+int vitb_token_mean_fwd(const void* x, int dtype, int B, int N, int C, int reserve_initials, float* out, void* stream);
+int vitb_token_mean_bwd(const float* dg, int dtype, int B, int N, int C, int reserve_initials, void* dx, void* stream);
+/* out[t,:] = ((member_mask >> (int)index[t]) & 1) ? a[t,:] : b[t,:]; a or b may be NULL (= zeros).
+ * torch.isin + blend (res-vit/model.py:469-472,487,524) and approximator row selection (:349-368). */
+int vitb_select_rows(const void* a, const void* b, const float* index, uint32_t member_mask, int rows, int cols,
+                     int dtype, void* out, void* stream);
+
 /* ---- loss and optimizer ------------------------------------------------------------------------- */
 /* nn.CrossEntropyLoss (mean) — src/train.py:151,22; res-vit/model.py:550,681.
  * loss[0] = mean_b(lse_b - logits[b,label_b]); dlogits = (softmax - onehot)/B (optional). */

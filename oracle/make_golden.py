@@ -76,3 +76,49 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def resvit_golden():
+    """Res-ViT vectors from the unmodified reference: LoRA + router + approximators, block_size 2 and 1,
+    training (seeded Gumbel draw, recorded) and eval."""
+    mod, _ = ref_loader.load_resvit_model()
+    out = {}
+    for bs in (2, 1):
+        args = mod.ModelArgs(dim=128, mlp_dim=128, n_layers=3, n_heads=2, n_kv_heads=2, lora_rank=8,
+                             dynamic_active_target=0.4, dynamic_start_layer=1, dynamic_router_hdim=64,
+                             dynamic_reserve_initials=1, low_rank_dim=32, block_size=bs, use_lora=True, use_reslr=True,
+                             image_size=(64, 64), patch_size=(16, 16), num_classes=10, device="cpu")
+        torch.manual_seed(20 + bs)
+        model = mod.Transformer(args)
+        with torch.no_grad():
+            model.pos_embedding.pos_embedding.mul_(0.02)
+            for name, p in model.named_parameters():      # make the router actually split the tokens
+                if name.endswith("router.out_conv.4.weight"):
+                    p.normal_(0, 0.5)
+                if name.endswith("router.out_conv.4.bias"):
+                    p.zero_()
+        sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+        g = torch.Generator().manual_seed(5)
+        img = torch.randn(4, 3, 64, 64, generator=g)
+        labels = torch.randint(0, 10, (4,), generator=g)
+        model.train()
+        torch.manual_seed(777)
+        c, a, d, e, metric = model(img, labels)
+        (1.0 * c + 2.0 * a + 0.5 * d + 0.1 * e).backward()
+        grads = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+        train = dict(c=c.detach(), a=a.detach(), d=d.detach(), e=e.detach(), metric=float(metric['non_low_rank_ratio']),
+                     logits=model.logits.detach().clone(), acts=torch.cat(model.acts, -1).detach().clone(), grads=grads,
+                     trainable=sorted(k for k, p in model.named_parameters() if p.requires_grad))
+        model.eval()
+        with torch.no_grad():
+            c, a, d, e, metric = model(img, labels)
+        ev = dict(c=c.detach(), e=e.detach(), metric=float(metric['non_low_rank_ratio']), logits=model.logits.detach().clone(),
+                  acts=torch.cat(model.acts, -1).detach().clone())
+        out["bs%d" % bs] = dict(args={k: getattr(args, k) for k in args.__dataclass_fields__}, state_dict=sd, img=img,
+                                labels=labels, gumbel_seed=777, train=train, eval=ev)
+    torch.save(out, os.path.join(OUT, "resvit_tiny.pt"))
+    print("resvit_tiny.pt", os.path.getsize(os.path.join(OUT, "resvit_tiny.pt")))
+
+
+if __name__ == "__main__" and ref_loader.available():
+    resvit_golden()

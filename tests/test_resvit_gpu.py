@@ -1,0 +1,160 @@
+"""GPU parity of the Res-ViT modules (router, LoRA-fused projections, approximators, Transformer) against
+the golden vectors of the unmodified reference and the oracle (oracle/resvit_oracle.py).
+north_star bars: router token indices bit-exact; fp32 mode logits/gradients within rel 1e-4; bf16 logits 2e-2."""
+import os
+import sys
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+from conftest import grad_close, rel_l2
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import resvit_oracle  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(ROOT, "tests", "golden", "resvit_tiny.pt")
+
+
+def _build(g):
+    import vitb200
+    from vitb200 import resvit
+    kw = dict(g["args"])
+    kw["device"] = "cuda"
+    m = resvit.Transformer(resvit.ModelArgs(**kw))
+    m.load_state_dict(g["state_dict"])
+    return m.cuda()
+
+
+def _replay_noise(m, g):
+    """The Gumbel samples the reference drew (seeded) — re-drawn by the oracle with the same seed."""
+    args = SimpleNamespace(**g["args"])
+    log = []
+    torch.manual_seed(g["gumbel_seed"])
+    with torch.no_grad():
+        resvit_oracle.resvit_forward(g["state_dict"], args, g["img"], g["labels"], training=True, noise_log=log)
+    it = iter(log)
+    for layer in m.layers:
+        if hasattr(layer, "router"):
+            layer.router.noise_fn = lambda logits, it=it: next(it).to(logits.device)
+
+
+@pytest.mark.parametrize("variant", ["bs2", "bs1"])
+def test_resvit_train_fp32_mode_matches_reference_golden(variant):
+    import vitb200
+    g = torch.load(GOLD)[variant]
+    m = _build(g).train()
+    _replay_noise(m, g)
+    t = g["train"]
+    with vitb200.precision("fp32"):
+        c, a, d, e, metric = m(g["img"].cuda(), g["labels"].cuda())
+        (1.0 * c + 2.0 * a + 0.5 * d + 0.1 * e).backward()
+    torch.cuda.synchronize()
+    acts = torch.cat([w.float() for w in m.acts], -1).cpu()
+    assert torch.equal(acts, t["acts"]), "router keep/skip decisions must be bit-exact"
+    assert rel_l2(m.logits.cpu(), t["logits"]) < 1e-4
+    for got, key in ((c, "c"), (a, "a"), (d, "d"), (e, "e")):
+        assert abs(float(got) - float(t[key])) < 1e-4 * max(1.0, abs(float(t[key]))), key
+    assert abs(float(metric["non_low_rank_ratio"]) - t["metric"]) < 1e-6
+    named = dict(m.named_parameters())
+    assert sorted(k for k, p in named.items() if p.requires_grad) == t["trainable"]
+    for k, ref in t["grads"].items():
+        assert named[k].grad is not None, k
+        assert grad_close(named[k].grad.cpu(), ref, 1e-4, atol=1e-8), (k, rel_l2(named[k].grad.cpu(), ref))
+    for k, p in named.items():
+        if not p.requires_grad:
+            assert p.grad is None, k
+
+
+@pytest.mark.parametrize("variant", ["bs2", "bs1"])
+def test_resvit_eval_indices_bit_exact_and_logits(variant):
+    import vitb200
+    g = torch.load(GOLD)[variant]
+    m = _build(g).eval()
+    args = SimpleNamespace(**g["args"])
+    with torch.no_grad():
+        ref = resvit_oracle.resvit_forward(g["state_dict"], args, g["img"], g["labels"], training=False)
+        with vitb200.precision("fp32"):
+            c, a, d, e, metric = m(g["img"].cuda(), g["labels"].cuda())
+            idx32 = {bid: None for bid in ref["indices"]}
+            logits32 = m.logits.cpu()
+            acts32 = torch.cat([w.float() for w in m.acts], -1).cpu()
+        with vitb200.precision("bf16"):
+            m(g["img"].cuda(), g["labels"].cuda())
+            logits16 = m.logits.cpu()
+            acts16 = torch.cat([w.float() for w in m.acts], -1).cpu()
+    assert torch.equal(acts32, g["eval"]["acts"])
+    assert rel_l2(logits32, g["eval"]["logits"]) < 1e-4
+    assert abs(float(e) - float(g["eval"]["e"])) < 1e-4
+    # bf16: decisions may only flip where the two router logits are within bf16 noise of a tie
+    agree = float((acts16 == g["eval"]["acts"]).float().mean())
+    assert agree > 0.97, agree
+    if agree == 1.0:
+        assert rel_l2(logits16, g["eval"]["logits"]) < 2e-2
+
+
+def test_router_module_standalone_indices_and_gradients():
+    import vitb200
+    from vitb200 import resvit
+    torch.manual_seed(0)
+    r = resvit.RouterModule(256, 128, 1, 1e-5, block_size=2, use_lora=False)
+    with torch.no_grad():
+        r.out_conv[-1].weight.normal_(0, 0.5)
+        r.out_conv[-1].bias.zero_()
+    sd = {"router." + k: v.detach().clone() for k, v in r.state_dict().items()}
+    args = SimpleNamespace(block_size=2, dynamic_reserve_initials=1, norm_eps=1e-5)
+    x = torch.randn(3, 50, 256)
+    log = []
+    torch.manual_seed(11)
+    xo = x.clone().requires_grad_(True)
+    leaf = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    hard, idx, ent, soft = resvit_oracle.router(xo, leaf, "router.", args, True, log)
+    wts = torch.linspace(0.5, 1.5, hard.numel()).view_as(hard)
+    ((hard * wts).sum() + 3.0 * ent + (soft * wts.flip(0)).sum()).backward()
+    r = r.cuda().train()
+    r.noise_fn = lambda logits: log[0].to(logits.device)
+    with vitb200.precision("fp32"):
+        xc = x.cuda().requires_grad_(True)
+        h2, i2, e2, s2 = r(xc)
+        ((h2 * wts.cuda()).sum() + 3.0 * e2 + (s2 * wts.flip(0).cuda()).sum()).backward()
+    assert torch.equal(i2.cpu(), idx.detach()), "packed router indices must be bit-exact"
+    assert torch.equal(h2.detach().cpu(), hard.detach().round())
+    assert rel_l2(s2.detach().cpu(), soft.detach()) < 1e-4
+    assert abs(float(e2) - float(ent)) < 1e-5
+    assert rel_l2(xc.grad.cpu(), xo.grad) < 1e-4
+    for k, p in r.named_parameters():
+        assert grad_close(p.grad.cpu(), leaf["router." + k].grad, 1e-4, atol=1e-8), k
+    r.eval()
+    with torch.no_grad(), vitb200.precision("fp32"):
+        h3, i3, _, _ = r(x.cuda())
+        ho, io, _, _ = resvit_oracle.router(x, sd, "router.", args, False, None)
+    assert torch.equal(i3.cpu(), io)
+
+
+def test_lora_module_and_attention_with_lora_match_oracle():
+    import vitb200
+    from vitb200 import resvit
+    torch.manual_seed(1)
+    args = resvit.ModelArgs(dim=256, n_heads=4, n_kv_heads=4, use_lora=True, lora_rank=8)
+    att = resvit.Attention(args)
+    with torch.no_grad():
+        for n, p in att.named_parameters():
+            if "lora" in n:
+                p.mul_(20.0)        # make the rank-8 update visible next to the base projection
+    sd = {"a." + k: v.detach().clone() for k, v in att.state_dict().items()}
+    x = torch.randn(2, 50, 256)
+    ref = resvit_oracle.attention(x, x, sd, "a.", 4, True)
+    att = att.cuda()
+    with torch.no_grad():
+        with vitb200.precision("fp32"):
+            y32 = att(x.cuda()).cpu()
+            lo = att.lora_q(x.cuda()).cpu()
+        with vitb200.precision("bf16"):
+            y16 = att(x.cuda()).float().cpu()
+            y_asym = att(x.cuda()[:, :20], x.cuda()).float().cpu()
+    assert rel_l2(y32, ref) < 1e-4
+    assert rel_l2(y16, ref) < 2e-2
+    assert rel_l2(lo, (x @ sd["a.lora_q.lora_A.weight"].t()) @ sd["a.lora_q.lora_B.weight"].t()) < 1e-4
+    assert rel_l2(y_asym, resvit_oracle.attention(x[:, :20], x, sd, "a.", 4, True)) < 2e-2

@@ -170,6 +170,11 @@ _vitb_cross_entropy = _sig("vitb_cross_entropy", [_vp, _vp, _i, _i, _vp, _vp, _v
 _vitb_sgd_momentum = _sig("vitb_sgd_momentum", [_vp, _vp, _vp, _i64, _f, _f, _f, _f, _i, _i, _vp, _vp, _vp])
 _vitb_adamw = _sig("vitb_adamw", [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _i, _vp, _vp, _vp, _vp])
 _vitb_sumsq = _sig("vitb_sumsq", [_vp, _i64, _vp, _vp])
+_vitb_router_decide_fwd = _sig("vitb_router_decide_fwd", [_vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp])
+_vitb_router_decide_bwd = _sig("vitb_router_decide_bwd", [_vp, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _i, _i, _f, _vp, _vp])
+_vitb_token_mean_fwd = _sig("vitb_token_mean_fwd", [_vp, _i, _i, _i, _i, _i, _vp, _vp])
+_vitb_token_mean_bwd = _sig("vitb_token_mean_bwd", [_vp, _i, _i, _i, _i, _i, _vp, _vp])
+_vitb_select_rows = _sig("vitb_select_rows", [_vp, _vp, _vp, C.c_uint32, _i, _i, _i, _vp, _vp])
 _vitb_clip_coef = _sig("vitb_clip_coef", [_vp, _f, _vp, _vp, _vp])
 
 EXPORTED_SYMBOLS = [
@@ -177,5 +182,6 @@ EXPORTED_SYMBOLS = [
     "vitb_layernorm_bwd", "vitb_attn_supported_tc", "vitb_attn_fwd_tc", "vitb_attn_bwd_tc",
     "vitb_attn_fwd_simt", "vitb_attn_bwd_simt", "vitb_cast_split", "vitb_im2col", "vitb_cls_rows",
     "vitb_embed_bwd", "vitb_colsum", "vitb_cross_entropy", "vitb_sgd_momentum", "vitb_adamw",
-    "vitb_sumsq", "vitb_clip_coef", "vitb_gelu_bwd",
+    "vitb_sumsq", "vitb_clip_coef", "vitb_gelu_bwd", "vitb_router_decide_fwd", "vitb_router_decide_bwd",
+    "vitb_token_mean_fwd", "vitb_token_mean_bwd", "vitb_select_rows",
 ]

@@ -1,0 +1,238 @@
+// vitb_router.cu — Res-ViT routing kernels (HBM-bound, elementwise / small reductions).
+//
+//   vitb_router_decide_fwd/bwd : the decision tail of RouterModule.forward (res-vit/model.py:189-211):
+//        2-way softmax, router entropy over the non-reserved tokens, hard keep/skip decision
+//        (Gumbel-softmax straight-through in training, argmax in eval), reserved-token override and
+//        the MSB-first bit-packing of _router2indices (:169-173) — one pass, one thread per token.
+//   vitb_token_mean_fwd/bwd    : the global feature mean(x_embed[:, r0:], dim=1) (:180-184).
+//   vitb_select_rows           : out[t,:] = member(index[t]) ? a[t,:] : b[t,:] with member() a 32-bit lookup
+//        mask over the packed index — torch.isin (:469-472) + the train/eval blend (:487,:524) and, with
+//        b = 0 and a one-bit mask, the row selection of BlockPathApproximators (:349-368) — no host sync.
+#include "../../include/vitb200.h"
+#include "vitb_common.cuh"
+
+namespace {
+using namespace vitb;
+
+constexpr int kThreads = 256;
+
+__global__ void __launch_bounds__(kThreads)
+router_decide_fwd_kernel(const float* __restrict__ logits, const float* __restrict__ noise, int T, int N, int bs,
+                         int r0, int training, float tau, float* __restrict__ soft, float* __restrict__ hard,
+                         float* __restrict__ ysoft, float* __restrict__ indices, float* __restrict__ entropy_sum) {
+  __shared__ float s_part[kThreads / 32];
+  float ent = 0.f;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x) {
+    const int n = t % N;
+    const bool reserved = n < r0;
+    float packed = 0.f;
+    for (int i = 0; i < bs; ++i) {
+      const long long o = (static_cast<long long>(t) * bs + i) * 2;
+      const float l0 = logits[o], l1 = logits[o + 1];
+      const float m = fmaxf(l0, l1);
+      const float e0 = expf(l0 - m), e1 = expf(l1 - m);
+      const float inv = 1.0f / (e0 + e1);
+      const float p0 = e0 * inv, p1 = e1 * inv;
+      soft[o] = p0;
+      soft[o + 1] = p1;
+      if (!reserved) ent -= p0 * logf(p0 + 1e-8f) + p1 * logf(p1 + 1e-8f);
+      int keep;
+      if (training) {
+        const float a0 = (l0 + noise[o]) / tau, a1 = (l1 + noise[o + 1]) / tau;
+        const float mm = fmaxf(a0, a1);
+        const float f0 = expf(a0 - mm), f1 = expf(a1 - mm);
+        const float iv = 1.0f / (f0 + f1);
+        const float y0 = f0 * iv, y1 = f1 * iv;
+        ysoft[o] = y0;
+        ysoft[o + 1] = y1;
+        keep = y1 > y0 ? 1 : 0;  // max() returns the first maximal index on ties
+      } else {
+        keep = p1 > p0 ? 1 : 0;  // argmax: first maximal index on ties
+      }
+      if (reserved) keep = 1;
+      hard[o] = keep ? 0.f : 1.f;
+      hard[o + 1] = keep ? 1.f : 0.f;
+      packed += keep ? static_cast<float>(1 << (bs - 1 - i)) : 0.f;
+    }
+    indices[t] = packed;
+  }
+  ent = warp_sum(ent);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = ent;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int w = 0; w < kThreads / 32; ++w) tot += s_part[w];
+    atomicAdd(entropy_sum, tot);
+  }
+}
+
+// d_logits from: d_soft (gradient wrt softmax(logits)), d_entropy (scalar gradient wrt the normalised
+// entropy), and in training d_hard flowing straight-through into softmax((logits+g)/tau).
+__global__ void __launch_bounds__(kThreads)
+router_decide_bwd_kernel(const float* __restrict__ soft, const float* __restrict__ ysoft,
+                         const float* __restrict__ d_soft, const float* __restrict__ d_hard,
+                         const float* __restrict__ d_entropy, float ent_scale, int T, int N, int bs, int r0,
+                         int training, float tau, float* __restrict__ d_logits) {
+  const float dent = d_entropy ? (*d_entropy) * ent_scale : 0.f;
+  const long long total = static_cast<long long>(T) * bs;
+  for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < total;
+       e += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int t = static_cast<int>(e / bs);
+    const bool reserved = (t % N) < r0;
+    const long long o = e * 2;
+    const float p0 = soft[o], p1 = soft[o + 1];
+    float g0 = d_soft ? d_soft[o] : 0.f, g1 = d_soft ? d_soft[o + 1] : 0.f;
+    if (!reserved && dent != 0.f) {
+      g0 -= dent * (logf(p0 + 1e-8f) + p0 / (p0 + 1e-8f));
+      g1 -= dent * (logf(p1 + 1e-8f) + p1 / (p1 + 1e-8f));
+    }
+    const float dot = p0 * g0 + p1 * g1;
+    float dl0 = p0 * (g0 - dot), dl1 = p1 * (g1 - dot);
+    if (training && d_hard && !reserved) {
+      const float y0 = ysoft[o], y1 = ysoft[o + 1];
+      const float h0 = d_hard[o], h1 = d_hard[o + 1];
+      const float dd = y0 * h0 + y1 * h1;
+      dl0 += y0 * (h0 - dd) / tau;
+      dl1 += y1 * (h1 - dd) / tau;
+    }
+    d_logits[o] = dl0;
+    d_logits[o + 1] = dl1;
+  }
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(kThreads)
+token_mean_fwd_kernel(const void* __restrict__ x_, int Bsz, int N, int Cc, int r0, float* __restrict__ out) {
+  const int total = Bsz * Cc;
+  const float inv = 1.0f / static_cast<float>(N - r0);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int b = i / Cc, c = i - b * Cc;
+    float s = 0.f;
+    for (int n = r0; n < N; ++n) {
+      const long long o = (static_cast<long long>(b) * N + n) * Cc + c;
+      s += BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x_)[o]) : reinterpret_cast<const float*>(x_)[o];
+    }
+    out[i] = s * inv;
+  }
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(kThreads)
+token_mean_bwd_kernel(const float* __restrict__ dg, int Bsz, int N, int Cc, int r0, void* __restrict__ dx_) {
+  const long long total = static_cast<long long>(Bsz) * N * Cc;
+  const float inv = 1.0f / static_cast<float>(N - r0);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % Cc);
+    const long long bn = i / Cc;
+    const int n = static_cast<int>(bn % N), b = static_cast<int>(bn / N);
+    const float v = n >= r0 ? dg[b * Cc + c] * inv : 0.f;
+    if (BF16) reinterpret_cast<__nv_bfloat16*>(dx_)[i] = __float2bfloat16(v);
+    else reinterpret_cast<float*>(dx_)[i] = v;
+  }
+}
+
+// out[t, :] = ((mask >> int(index[t])) & 1) ? a[t, :] : b[t, :]   (null a / b read as zero)
+template <bool BF16>
+__global__ void __launch_bounds__(kThreads)
+select_rows_kernel(const void* __restrict__ a_, const void* __restrict__ b_, const float* __restrict__ index,
+                   unsigned mask, int rows, int cols, void* __restrict__ out_) {
+  constexpr int V = BF16 ? 8 : 4;  // elements per 16-byte vector
+  const int cv = cols / V;
+  const long long total = static_cast<long long>(rows) * cv;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int t = static_cast<int>(i / cv);
+    const int idx = static_cast<int>(index[t]);
+    const bool sel = (idx >= 0 && idx < 32) ? ((mask >> idx) & 1u) : false;
+    const void* src = sel ? a_ : b_;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (src) v = reinterpret_cast<const uint4*>(src)[i];
+    reinterpret_cast<uint4*>(out_)[i] = v;
+  }
+}
+
+inline int grid_for(long long items, int per_sm = 8) {
+  long long blocks = (items + kThreads - 1) / kThreads;
+  const long long cap = static_cast<long long>(vitb_num_sms()) * per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+}  // namespace
+
+extern "C" {
+
+int vitb_router_decide_fwd(const float* logits, const float* noise, int T, int N, int block_size,
+                           int reserve_initials, int training, float tau, float* soft, float* hard,
+                           float* ysoft, float* indices, float* entropy_sum, void* stream_) {
+  int st = vitb_check_device();
+  if (st != VITB_OK) return st;
+  if (T == 0) return VITB_OK;
+  VITB_REQUIRE(logits && soft && hard && indices && entropy_sum && T > 0 && N > 0, VITB_ERR_BAD_ARG,
+               "router_decide_fwd: bad args");
+  VITB_REQUIRE(block_size >= 1 && block_size <= 5, VITB_ERR_UNSUPPORTED_SHAPE, "router_decide_fwd: block_size %d", block_size);
+  VITB_REQUIRE(!training || (noise && ysoft), VITB_ERR_BAD_ARG, "router_decide_fwd: training needs noise and ysoft");
+  router_decide_fwd_kernel<<<grid_for(T, 2), kThreads, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      logits, noise, T, N, block_size, reserve_initials, training, tau, soft, hard, ysoft, indices, entropy_sum);
+  VITB_LAUNCH_CHECK("router_decide_fwd_kernel");
+  return VITB_OK;
+}
+
+int vitb_router_decide_bwd(const float* soft, const float* ysoft, const float* d_soft, const float* d_hard,
+                           const float* d_entropy, float entropy_scale, int T, int N, int block_size,
+                           int reserve_initials, int training, float tau, float* d_logits, void* stream_) {
+  int st = vitb_check_device();
+  if (st != VITB_OK) return st;
+  if (T == 0) return VITB_OK;
+  VITB_REQUIRE(soft && d_logits && T > 0 && N > 0, VITB_ERR_BAD_ARG, "router_decide_bwd: bad args");
+  router_decide_bwd_kernel<<<grid_for(static_cast<long long>(T) * block_size, 2), kThreads, 0,
+                             reinterpret_cast<cudaStream_t>(stream_)>>>(
+      soft, ysoft, d_soft, d_hard, d_entropy, entropy_scale, T, N, block_size, reserve_initials, training, tau, d_logits);
+  VITB_LAUNCH_CHECK("router_decide_bwd_kernel");
+  return VITB_OK;
+}
+
+int vitb_token_mean_fwd(const void* x, int dtype, int B, int N, int C, int reserve_initials, float* out, void* stream_) {
+  int st = vitb_check_device();
+  if (st != VITB_OK) return st;
+  if (B == 0) return VITB_OK;
+  VITB_REQUIRE(x && out && N > reserve_initials && C > 0, VITB_ERR_BAD_ARG, "token_mean_fwd: bad args");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  if (dtype == VITB_BF16) token_mean_fwd_kernel<true><<<grid_for(static_cast<long long>(B) * C), kThreads, 0, s>>>(x, B, N, C, reserve_initials, out);
+  else token_mean_fwd_kernel<false><<<grid_for(static_cast<long long>(B) * C), kThreads, 0, s>>>(x, B, N, C, reserve_initials, out);
+  VITB_LAUNCH_CHECK("token_mean_fwd_kernel");
+  return VITB_OK;
+}
+
+int vitb_token_mean_bwd(const float* dg, int dtype, int B, int N, int C, int reserve_initials, void* dx, void* stream_) {
+  int st = vitb_check_device();
+  if (st != VITB_OK) return st;
+  if (B == 0) return VITB_OK;
+  VITB_REQUIRE(dg && dx && N > reserve_initials && C > 0, VITB_ERR_BAD_ARG, "token_mean_bwd: bad args");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  const long long total = static_cast<long long>(B) * N * C;
+  if (dtype == VITB_BF16) token_mean_bwd_kernel<true><<<grid_for(total), kThreads, 0, s>>>(dg, B, N, C, reserve_initials, dx);
+  else token_mean_bwd_kernel<false><<<grid_for(total), kThreads, 0, s>>>(dg, B, N, C, reserve_initials, dx);
+  VITB_LAUNCH_CHECK("token_mean_bwd_kernel");
+  return VITB_OK;
+}
+
+int vitb_select_rows(const void* a, const void* b, const float* index, uint32_t member_mask, int rows, int cols,
+                     int dtype, void* out, void* stream_) {
+  int st = vitb_check_device();
+  if (st != VITB_OK) return st;
+  if (rows == 0 || cols == 0) return VITB_OK;
+  VITB_REQUIRE(index && out && rows > 0, VITB_ERR_BAD_ARG, "select_rows: bad args");
+  const int V = dtype == VITB_BF16 ? 8 : 4;
+  VITB_REQUIRE(cols % V == 0, VITB_ERR_UNSUPPORTED_SHAPE, "select_rows: cols %d must be a multiple of %d", cols, V);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  const long long total = static_cast<long long>(rows) * (cols / V);
+  if (dtype == VITB_BF16) select_rows_kernel<true><<<grid_for(total), kThreads, 0, s>>>(a, b, index, member_mask, rows, cols, out);
+  else select_rows_kernel<false><<<grid_for(total), kThreads, 0, s>>>(a, b, index, member_mask, rows, cols, out);
+  VITB_LAUNCH_CHECK("select_rows_kernel");
+  return VITB_OK;
+}
+
+}  // extern "C"

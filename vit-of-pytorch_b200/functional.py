@@ -190,19 +190,31 @@ def _as2d(t, cols):
 # Linear (nn.Linear [N,K] and LinearGeneral [K,N]) with fused bias / GELU / residual epilogue
 # --------------------------------------------------------------------------------------------------
 class _Linear(torch.autograd.Function):
-    """Widths that are not multiples of 8 (the classifier's num_classes) are zero-padded to the next
-    multiple of 8 on the weight side, so every TMA row stride stays 16-byte aligned."""
+    """y = act(x W^T + b + row_bias[row // group]) (+ residual).
+
+    Widths that are not multiples of 8 (the classifier's num_classes, the router's 2*block_size logits) are
+    zero-padded to the next multiple of 8 on the weight side, so every TMA row stride stays 16-byte aligned.
+    `w_cols=(s, e)` contracts only against columns [s, e) of an nn.Linear weight (the router's split of
+    Linear(2H, H) over cat(x_embed, global) into a token GEMM plus a per-image row bias)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, residual, layout, act, out_dtype):
+    def forward(ctx, x, weight, bias, residual, row_bias, layout, act, out_dtype, w_cols, row_bias_group):
         L.require_cuda(x, weight)
         kn = layout == "kn"
         K = x.shape[-1]
-        N = weight.numel() // K
+        if w_cols is not None:
+            if kn:
+                raise L.VitbError("linear: w_cols needs an nn.Linear-layout weight")
+            N, Kfull = weight.shape
+            if w_cols[1] - w_cols[0] != K:
+                raise L.VitbError("linear: w_cols span %s does not match the input width %d" % (w_cols, K))
+        else:
+            N = weight.numel() // K
+            Kfull = K
         Np = (N + 7) // 8 * 8
-        if Np != N and (kn or residual is not None or act is not None):
+        if Np != N and (kn or residual is not None or act is not None or w_cols is not None or row_bias is not None):
             raise L.VitbError("linear: output width %d must be a multiple of 8 for this layout/epilogue" % N)
-        w2 = (K, N) if kn else (N, K)
+        w2 = (K, N) if kn else (N, Kfull)
         x2 = _as2d(x, K)
         xo = _operand(x2)
         if Np != N:
@@ -210,10 +222,12 @@ class _Linear(torch.autograd.Function):
             wo = [whi] + ([wlo] if wlo is not None else [])
         else:
             wo = _weight_operand(weight, w2)
+            if w_cols is not None:
+                wo = [w[:, w_cols[0]:w_cols[1]] for w in wo]
         A, B = _pairs(xo, wo)
         M = x2.shape[0]
         out = torch.empty((M, Np), dtype=out_dtype, device=x.device)
-        need_z = act == "gelu" and (x.requires_grad or weight.requires_grad)
+        need_z = act == "gelu" and any(ctx.needs_input_grad)
         z = torch.empty((M, N), dtype=out_dtype, device=x.device) if need_z else None
         res2 = _as2d(residual, N) if residual is not None else None
         b1 = bias.detach().view(-1) if bias is not None else None
@@ -221,9 +235,14 @@ class _Linear(torch.autograd.Function):
             b1 = torch.cat([b1, b1.new_zeros(Np - N)])
         if act == "gelu" and residual is not None:
             raise L.VitbError("linear: GELU and residual cannot be fused in one call")
-        ops.gemm(A, B, b_mn=kn, out=out, bias=b1, residual=res2,
+        rb = None
+        if row_bias is not None:
+            rb = row_bias.detach().reshape(-1, N).float().contiguous()
+        ops.gemm(A, B, b_mn=kn, out=out, bias=b1, residual=res2, row_bias=rb, row_bias_group=row_bias_group,
                  epilogue=ops.EPI_GELU if act == "gelu" else ops.EPI_NONE, d2=z)
         ctx.kn, ctx.act, ctx.w2, ctx.N, ctx.K, ctx.Np = kn, act, w2, N, K, Np
+        ctx.w_cols, ctx.rb_group = w_cols, row_bias_group
+        ctx.rb_shape = row_bias.shape if row_bias is not None else None
         ctx.x_shape, ctx.x_dtype = x.shape, x.dtype
         ctx.has_res = residual is not None
         ctx.res_shape = residual.shape if residual is not None else None
@@ -246,6 +265,10 @@ class _Linear(torch.autograd.Function):
             dres = dy.reshape(ctx.res_shape).to(ctx.res_dtype)
         if ctx.act == "gelu":
             dy2 = ops.gelu_bwd(dy2, ctx.z)
+        drb = None
+        if ctx.rb_shape is not None and ctx.needs_input_grad[4]:
+            G = dy2.shape[0] // ctx.rb_group
+            drb = (ops.token_mean_fwd(dy2.view(G, ctx.rb_group, N), 0) * float(ctx.rb_group)).reshape(ctx.rb_shape)
         if Np != N:
             dyp = dy2.new_zeros((dy2.shape[0], Np))
             dyp[:, :N] = dy2
@@ -255,9 +278,18 @@ class _Linear(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             A, B = _pairs(dyo, ctx.wo)
             dx = ops.gemm(A, B, b_mn=not kn, out_dtype=ctx.x_dtype).view(ctx.x_shape)
-        if Np == N:
+        if Np == N and ctx.w_cols is None:
             if weight.requires_grad:
                 dw = _wgrad(dyo, ctx.xo, weight, ctx.w2, dy_is_rows_of_n=not kn)
+            if bias is not None and bias.requires_grad:
+                db = _bias_grad(dy2, bias)
+        elif ctx.w_cols is not None:
+            if weight.requires_grad:
+                tgt = _grad_target(weight)
+                full = tgt if tgt is not None else torch.zeros(weight.shape, dtype=F32, device=dy.device)
+                A, B = _pairs(dyo, ctx.xo)
+                ops.gemm(A, B, a_mn=True, b_mn=True, out=full[:, ctx.w_cols[0]:ctx.w_cols[1]], accumulate=True)
+                dw = None if tgt is not None else full
             if bias is not None and bias.requires_grad:
                 db = _bias_grad(dy2, bias)
         else:
@@ -271,15 +303,16 @@ class _Linear(torch.autograd.Function):
                 ops.colsum(dy2, dbp)
                 db = dbp[:N].reshape(bias.shape)
         ctx.xo = ctx.z = ctx.wo = None
-        return dx, dw, db, dres, None, None, None
+        return dx, dw, db, dres, drb, None, None, None, None, None
 
 
-def linear(x, weight, bias=None, *, layout="nk", act=None, residual=None, out_dtype=None):
-    """y = act(x W^T + b) (+ residual).  layout "nk": weight [N,K] (nn.Linear); "kn": weight [K,N...]
-    (LinearGeneral).  Output dtype: fp32 when a residual is fused or in fp32 mode, else bf16."""
+def linear(x, weight, bias=None, *, layout="nk", act=None, residual=None, out_dtype=None, w_cols=None,
+           row_bias=None, row_bias_group=0):
+    """y = act(x W^T + b [+ row_bias]) (+ residual).  layout "nk": weight [N,K] (nn.Linear); "kn": weight
+    [K,N...] (LinearGeneral).  Output dtype: fp32 when a residual is fused or in fp32 mode, else bf16."""
     if out_dtype is None:
         out_dtype = F32 if (residual is not None or _fp32_mode()) else BF16
-    return _Linear.apply(x, weight, bias, residual, layout, act, out_dtype)
+    return _Linear.apply(x, weight, bias, residual, row_bias, layout, act, out_dtype, w_cols, row_bias_group)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -821,3 +854,94 @@ def encoder_block(x, H, norm1, q, k, v, o, norm2, fc1, fc2):
 
 def clear_grad_side_channel():
     _GRAD_SIDE.clear()
+
+
+# --------------------------------------------------------------------------------------------------
+# Res-ViT routing ops
+# --------------------------------------------------------------------------------------------------
+class _RouterDecide(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, noise, reserve_initials, training, tau):
+        L.require_cuda(logits)
+        Bsz, N, bs, two = logits.shape
+        lg = logits.float().contiguous()
+        nz = noise.float().contiguous() if (training and noise is not None) else None
+        soft, hard, ysoft, idx, ent_sum = ops.router_decide_fwd(lg.view(-1, bs, 2), nz, N, bs, reserve_initials, training, tau)
+        denom = float(Bsz * (N - reserve_initials) * bs)
+        ctx.save_for_backward(soft, ysoft if ysoft is not None else soft)
+        ctx.cfg = (Bsz, N, bs, reserve_initials, training, tau, denom, logits.dtype)
+        ctx.mark_non_differentiable(idx)
+        return hard.view(Bsz, N, bs, 2), idx.view(Bsz, N, 1), ent_sum / denom, soft.view(Bsz, N, bs, 2)
+
+    @staticmethod
+    def backward(ctx, d_hard, d_idx, d_ent, d_soft):
+        soft, ysoft = ctx.saved_tensors
+        Bsz, N, bs, r0, training, tau, denom, dt = ctx.cfg
+        dh = d_hard.float().contiguous() if d_hard is not None else None
+        ds = d_soft.float().contiguous() if d_soft is not None else None
+        de = d_ent.float().contiguous() if d_ent is not None else None
+        dl = ops.router_decide_bwd(soft, ysoft, ds, dh, de, 1.0 / denom, N, bs, r0, training, tau)
+        return dl.view(Bsz, N, bs, 2).to(dt), None, None, None, None
+
+
+def router_decide(logits, noise, reserve_initials, training, tau=1.0):
+    """-> (hard [B,N,bs,2], indices [B,N,1] fp32 integers, router_entropy scalar, soft [B,N,bs,2])."""
+    return _RouterDecide.apply(logits, noise, reserve_initials, training, tau)
+
+
+class _TokenMean(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, reserve_initials):
+        L.require_cuda(x)
+        xc = x.contiguous()
+        ctx.cfg = (x.shape[0], x.shape[1], reserve_initials, x.dtype)
+        return ops.token_mean_fwd(xc, reserve_initials)
+
+    @staticmethod
+    def backward(ctx, dg):
+        Bsz, N, r0, dt = ctx.cfg
+        return ops.token_mean_bwd(dg.float().contiguous(), Bsz, N, r0, dt), None
+
+
+def token_mean(x, reserve_initials):
+    """[B,N,C] -> [B,C] fp32: mean over the tokens n >= reserve_initials."""
+    return _TokenMean.apply(x, reserve_initials)
+
+
+class _SelectRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, index, member_mask):
+        ref = a if a is not None else b
+        L.require_cuda(ref, index)
+        cols = ref.shape[-1]
+        idx = index.detach().reshape(-1).float().contiguous()
+        a2 = a.reshape(-1, cols).contiguous() if a is not None else None
+        b2 = b.reshape(-1, cols).contiguous() if b is not None else None
+        if a2 is not None and b2 is not None and a2.dtype != b2.dtype:
+            a2, b2 = a2.float(), b2.float()
+        out = ops.select_rows(a2, b2, idx, member_mask)
+        ctx.save_for_backward(idx)
+        ctx.cfg = (member_mask, a.shape if a is not None else None, b.shape if b is not None else None,
+                   a.dtype if a is not None else None, b.dtype if b is not None else None)
+        return out.view(ref.shape)
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        mask, ash, bsh, adt, bdt = ctx.cfg
+        g2 = g.reshape(idx.numel(), -1).contiguous()
+        da = db = None
+        if ash is not None and ctx.needs_input_grad[0]:
+            da = ops.select_rows(g2, None, idx, mask).view(ash).to(adt)
+        if bsh is not None and ctx.needs_input_grad[1]:
+            db = ops.select_rows(None, g2, idx, mask).view(bsh).to(bdt)
+        return da, db, None, None
+
+
+def select_rows(a, b, index, member_ids):
+    """out[t] = a[t] if int(index[t]) in member_ids else b[t]; a or b may be None (zeros).  index: [..., 1]
+    fp32 packed router indices; member_ids: iterable of ints < 32 (torch.isin + blend, res-vit/model.py:469-487)."""
+    mask = 0
+    for i in member_ids:
+        mask |= 1 << int(i)
+    return _SelectRows.apply(a, b, index, mask)

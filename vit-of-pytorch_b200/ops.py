@@ -331,3 +331,68 @@ def sumsq(x, out):
 def clip_coef(sumsq_t, max_norm, coef, norm_out=None):
     L.check(L._vitb_clip_coef(L.ptr(sumsq_t), float(max_norm), L.ptr(coef), L.ptr(norm_out),
                               L.stream_ptr(coef.device)), "vitb_clip_coef")
+
+
+# --------------------------------------------------------------------------------------------------
+# Res-ViT routing
+# --------------------------------------------------------------------------------------------------
+def router_decide_fwd(logits, noise, N, block_size, reserve_initials, training, tau=1.0):
+    """logits [T, bs, 2] fp32 contiguous -> (soft, hard, ysoft|None, indices [T], entropy_sum scalar)."""
+    L.require_cuda(logits, noise)
+    if logits.dtype != torch.float32 or not logits.is_contiguous():
+        raise L.VitbError("router_decide_fwd: logits must be contiguous fp32")
+    T = logits.numel() // (2 * block_size)
+    dev = logits.device
+    soft = torch.empty_like(logits)
+    hard = torch.empty_like(logits)
+    ysoft = torch.empty_like(logits) if training else None
+    idx = torch.empty(T, dtype=torch.float32, device=dev)
+    ent = torch.zeros((), dtype=torch.float32, device=dev)
+    if training and (noise is None or noise.dtype != torch.float32 or not noise.is_contiguous() or noise.numel() != logits.numel()):
+        raise L.VitbError("router_decide_fwd: training needs fp32 noise shaped like logits")
+    L.check(L._vitb_router_decide_fwd(L.ptr(logits), L.ptr(noise), T, N, block_size, reserve_initials, int(training),
+                                      float(tau), L.ptr(soft), L.ptr(hard), L.ptr(ysoft), L.ptr(idx), L.ptr(ent),
+                                      L.stream_ptr(dev)), "vitb_router_decide_fwd")
+    return soft, hard, ysoft, idx, ent
+
+
+def router_decide_bwd(soft, ysoft, d_soft, d_hard, d_entropy, entropy_scale, N, block_size, reserve_initials, training,
+                      tau=1.0):
+    T = soft.numel() // (2 * block_size)
+    dl = torch.empty_like(soft)
+    L.check(L._vitb_router_decide_bwd(L.ptr(soft), L.ptr(ysoft), L.ptr(d_soft), L.ptr(d_hard), L.ptr(d_entropy),
+                                      float(entropy_scale), T, N, block_size, reserve_initials, int(training), float(tau),
+                                      L.ptr(dl), L.stream_ptr(soft.device)), "vitb_router_decide_bwd")
+    return dl
+
+
+def token_mean_fwd(x, reserve_initials):
+    """x [B,N,C] (f32/bf16 contiguous) -> [B,C] fp32 mean over tokens n >= reserve_initials."""
+    L.require_cuda(x)
+    B, N, Cc = x.shape
+    out = torch.empty((B, Cc), dtype=torch.float32, device=x.device)
+    L.check(L._vitb_token_mean_fwd(L.ptr(x), L.dtype_code(x), B, N, Cc, reserve_initials, L.ptr(out),
+                                   L.stream_ptr(x.device)), "vitb_token_mean_fwd")
+    return out
+
+
+def token_mean_bwd(dg, B, N, reserve_initials, dtype):
+    Cc = dg.shape[-1]
+    dx = torch.empty((B, N, Cc), dtype=dtype, device=dg.device)
+    L.check(L._vitb_token_mean_bwd(L.ptr(dg), L.dtype_code(dx), B, N, Cc, reserve_initials, L.ptr(dx),
+                                   L.stream_ptr(dg.device)), "vitb_token_mean_bwd")
+    return dx
+
+
+def select_rows(a, b, index, member_mask):
+    """out[t,:] = member(index[t]) ? a[t,:] : b[t,:] on 2-D contiguous tensors; a or b may be None (zeros)."""
+    ref = a if a is not None else b
+    L.require_cuda(ref, index)
+    if not ref.is_contiguous() or (a is not None and b is not None and (a.shape != b.shape or a.dtype != b.dtype or not b.is_contiguous())):
+        raise L.VitbError("select_rows: operands must be contiguous with equal shape and dtype")
+    rows = index.numel()
+    cols = ref.numel() // rows
+    out = torch.empty_like(ref)
+    L.check(L._vitb_select_rows(L.ptr(a), L.ptr(b), L.ptr(index), int(member_mask) & 0xFFFFFFFF, rows, cols,
+                                L.dtype_code(ref), L.ptr(out), L.stream_ptr(ref.device)), "vitb_select_rows")
+    return out
