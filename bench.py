@@ -49,7 +49,7 @@ def peaks():
 # clocks sampled DURING the timed region
 # ---------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -61,12 +61,14 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=self.tmp, stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Median SM clock and throttle reasons over the samples taken inside [t0, t1] (epoch seconds)."""
+        import datetime
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -83,6 +85,9 @@ class ClockSampler:
             if len(r) < 8:
                 continue
             try:
+                ts = datetime.datetime.strptime(r[0].strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                if t0 is not None and not (t0 - 0.05 <= ts <= t1 + 0.05):
+                    continue
                 sm.append(float(r[1]))
                 mx = float(r[2])
             except ValueError:
@@ -199,12 +204,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()          # started before the warm-up so samples exist for short timed regions
     for _ in range(args.warmup):
         step(img_d, lab_d)
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    t_wall0 = time.time()
     launches0 = vitb200._lib.LAUNCHES[0]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -214,7 +220,7 @@ def main():
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     launches = vitb200._lib.LAUNCHES[0] - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_wall0, time.time()) if rank == 0 else None
     barrier()
     # end to end: pinned host inputs, H2D + loss read-back inside the timed region
     img_e = torch.empty_like(img_d)
