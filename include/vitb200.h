@@ -176,6 +176,9 @@ int vitb_embed_bwd(const float* dx, int B, int N, int D, float* dpos, float* dcl
 int vitb_gelu_bwd(const void* dy, const void* z, void* out, int64_t n, int dtype, void* stream);
 /* out[c] += sum_r x[r,c]  (bias gradients). */
 int vitb_colsum(const void* x, int x_dtype, int rows, int cols, int64_t ld, float* out, void* stream);
+/* Same over a packed [rows, 3*seg_cols] buffer (dq|dk|dv): segment i accumulates into out_i[seg_cols]. */
+int vitb_colsum3(const void* x, int x_dtype, int rows, int seg_cols, int64_t ld, float* out0, float* out1,
+                 float* out2, void* stream);
 
 /* ---- Res-ViT routing ---------------------------------------------------------------------------
  * Decision tail of RouterModule.forward (res-vit/model.py:189-211) + _router2indices (:169-173).
@@ -209,8 +212,9 @@ int vitb_select_rows(const void* a, const void* b, const float* index, uint32_t 
  * loss[0] = mean_b(lse_b - logits[b,label_b]); dlogits = (softmax - onehot)/B (optional). */
 int vitb_cross_entropy(const float* logits, const int64_t* labels, int B, int C, float* loss,
                        float* dlogits, void* stream);
-/* torch.optim.SGD(momentum) over a flat buffer (src/train.py:154-158), refreshing the bf16 shadow. */
-int vitb_sgd_momentum(float* p, const float* g, float* m, int64_t n, float lr, float momentum,
+/* torch.optim.SGD(momentum) over a flat buffer (src/train.py:154-158), refreshing the bf16 shadow.
+ * lr_dev (optional device scalar) overrides lr, so an LR scheduler can drive a captured CUDA graph. */
+int vitb_sgd_momentum(float* p, const float* g, float* m, int64_t n, float lr, const float* lr_dev, float momentum,
                       float dampening, float weight_decay, int nesterov, int first_step,
                       void* shadow_hi, void* shadow_lo, void* stream);
 /* torch.optim.AdamW over a flat buffer (res-vit/train.py:272-277); grad_scale_dev (optional device

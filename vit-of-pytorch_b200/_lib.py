@@ -166,8 +166,9 @@ _vitb_cls_rows = _sig("vitb_cls_rows", [_vp, _i, _i, _i, _vp, _vp, _vp])
 _vitb_embed_bwd = _sig("vitb_embed_bwd", [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp])
 _vitb_gelu_bwd = _sig("vitb_gelu_bwd", [_vp, _vp, _vp, _i64, _i, _vp])
 _vitb_colsum = _sig("vitb_colsum", [_vp, _i, _i, _i, _i64, _vp, _vp])
+_vitb_colsum3 = _sig("vitb_colsum3", [_vp, _i, _i, _i, _i64, _vp, _vp, _vp, _vp])
 _vitb_cross_entropy = _sig("vitb_cross_entropy", [_vp, _vp, _i, _i, _vp, _vp, _vp])
-_vitb_sgd_momentum = _sig("vitb_sgd_momentum", [_vp, _vp, _vp, _i64, _f, _f, _f, _f, _i, _i, _vp, _vp, _vp])
+_vitb_sgd_momentum = _sig("vitb_sgd_momentum", [_vp, _vp, _vp, _i64, _f, _vp, _f, _f, _f, _i, _i, _vp, _vp, _vp])
 _vitb_adamw = _sig("vitb_adamw", [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _i, _vp, _vp, _vp, _vp])
 _vitb_sumsq = _sig("vitb_sumsq", [_vp, _i64, _vp, _vp])
 _vitb_router_decide_fwd = _sig("vitb_router_decide_fwd", [_vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp])
@@ -183,5 +184,5 @@ EXPORTED_SYMBOLS = [
     "vitb_attn_fwd_simt", "vitb_attn_bwd_simt", "vitb_cast_split", "vitb_im2col", "vitb_cls_rows",
     "vitb_embed_bwd", "vitb_colsum", "vitb_cross_entropy", "vitb_sgd_momentum", "vitb_adamw",
     "vitb_sumsq", "vitb_clip_coef", "vitb_gelu_bwd", "vitb_router_decide_fwd", "vitb_router_decide_bwd",
-    "vitb_token_mean_fwd", "vitb_token_mean_bwd", "vitb_select_rows",
+    "vitb_token_mean_fwd", "vitb_token_mean_bwd", "vitb_select_rows", "vitb_colsum3",
 ]

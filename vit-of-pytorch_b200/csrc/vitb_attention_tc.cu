@@ -19,6 +19,8 @@
 //   S = Q K^T ; P = exp(S*c - LSE) ; dP = dO V^T ; dS = P * (dP - D) * c
 //   dV += P^T dO ; dK += dS^T Q ; dQ = dS K            (5 tcgen05 GEMMs per query tile)
 #include "../../include/vitb200.h"
+#include <stdlib.h>
+
 #include "vitb_common.cuh"
 
 namespace {
@@ -42,6 +44,7 @@ struct AttnTc {
   long long do_bs, do_rs;
   __nv_bfloat16 *dq, *dk, *dv;
   long long dq_bs, dq_rs, dk_bs, dk_rs, dv_bs, dv_rs;
+  long long* dbg;  // optional per-phase clock64 stamps of CTA 0 (diagnostics; NULL in production)
 };
 
 // byte offset of the 16-byte unit holding keys [8u, 8u+8) of row r inside one 128B-swizzled chunk
@@ -59,11 +62,76 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
 }
 
 // ================================================================================================
+// Work split inside a CTA (both kernels): 256 threads = 8 warps.  Warp w owns TMEM lanes / query rows
+// 32*(w&3) .. +31 (the hardware's lane-quadrant rule) and the column half (w>>2): two threads share a
+// row, each handling half of the key columns; row max / row sum are exchanged through shared memory.
+// ================================================================================================
+constexpr int kAttnThreads = 256;
+#define VITB_STAMP(i) do { if (a.dbg != nullptr && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) a.dbg[i] = clock64(); } while (0)
+
+struct ColRange { int c_begin, c_end; };   // in units of 32-column chunks (the last chunk may hold 16)
+__device__ __forceinline__ ColRange my_chunks(int NK, int half) {
+  const int n = (NK + 31) >> 5;
+  const int mid = (n + 1) >> 1;
+  ColRange r;
+  r.c_begin = half ? mid : 0;
+  r.c_end = half ? n : mid;
+  return r;
+}
+
+// loads 32 (or the final 16) fp32 columns of this thread's TMEM lane; missing columns read as `fill`
+__device__ __forceinline__ void ld_chunk(uint32_t taddr, int c0, int NK, uint32_t fill, uint32_t (&v)[32]) {
+  if (c0 + 32 <= NK) {
+    tmem_ld_32x32b_x32(taddr + c0, v);
+    tmem_ld_wait();
+  } else {
+    tmem_ld_32x32b_x16(taddr + c0, reinterpret_cast<uint32_t(&)[16]>(v));   // lands in v[0..16)
+    tmem_ld_wait();                                                          // registers are valid only now
+#pragma unroll
+    for (int j = 16; j < 32; ++j) v[j] = fill;
+  }
+}
+
+// issue (without waiting) the TMEM load of a 32-column chunk (the final chunk may hold only 16 columns)
+__device__ __forceinline__ void issue_chunk(uint32_t taddr, int c0, int NK, uint32_t (&v)[32]) {
+  if (c0 + 32 <= NK) {
+    tmem_ld_32x32b_x32(taddr + c0, v);
+  } else {
+    tmem_ld_32x32b_x16(taddr + c0, reinterpret_cast<uint32_t(&)[16]>(v));   // v[16..32) stay unused (masked)
+  }
+}
+__device__ __forceinline__ float chunk_max(const uint32_t (&v)[32], int c0, int NK, int N) {
+  float m = -INFINITY;
+  if (c0 + 32 <= N) {   // interior chunk: every column is a valid key
+#pragma unroll
+    for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (c0 + j < N) m = fmaxf(m, __uint_as_float(v[j]));
+  }
+  return m;
+}
+
+__device__ __forceinline__ void st_row64_bf16(__nv_bfloat16* dst32, const uint32_t (&v)[32], float scale) {
+  uint4* d = reinterpret_cast<uint4*>(dst32);
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    uint4 w;
+    w.x = pack_bf16x2(__uint_as_float(v[8 * u + 0]) * scale, __uint_as_float(v[8 * u + 1]) * scale);
+    w.y = pack_bf16x2(__uint_as_float(v[8 * u + 2]) * scale, __uint_as_float(v[8 * u + 3]) * scale);
+    w.z = pack_bf16x2(__uint_as_float(v[8 * u + 4]) * scale, __uint_as_float(v[8 * u + 5]) * scale);
+    w.w = pack_bf16x2(__uint_as_float(v[8 * u + 6]) * scale, __uint_as_float(v[8 * u + 7]) * scale);
+    d[u] = w;
+  }
+}
+
+// ================================================================================================
 // forward
 // ================================================================================================
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kAttnThreads)
 attn_fwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-            const __grid_constant__ CUtensorMap tmV, const AttnTc a) {
+            const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnTc a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   const int NK = a.NK;
@@ -77,10 +145,13 @@ attn_fwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   uint8_t* sP = sU;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sU + u_bytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  float* red = reinterpret_cast<float*>(bars + 8);   // [2 stats][2 halves][128 rows]
   const uint32_t bar_qk = smem_u32(bars), bar_v = bar_qk + 8, bar_s = bar_qk + 16, bar_o = bar_qk + 24;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int half = warp >> 2;
   const int row0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  VITB_STAMP(0);
 
   if (tid == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
@@ -92,6 +163,7 @@ attn_fwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  VITB_STAMP(1);
 
   if (tid == 0) {
     mbar_arrive_expect_tx(bar_qk, kChunkBytes + kv_bytes);
@@ -100,6 +172,7 @@ attn_fwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     mbar_arrive_expect_tx(bar_v, kv_bytes);
     tma_load_3d(&tmV, bar_v, smem_u32(sV), h * DH, 0, b);
     mbar_wait(bar_qk, 0);
+    VITB_STAMP(2);
     tc_fence_after();
     const uint32_t idesc = umma_idesc_bf16(128, NK, false, false);
 #pragma unroll
@@ -111,52 +184,42 @@ attn_fwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   __syncwarp();
   mbar_wait(bar_s, 0);
   tc_fence_after();
+  VITB_STAMP(3);
 
-  const int r = warp * 32 + lane;  // query row within the tile == TMEM lane
-  const uint32_t trow = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-  // pass 1: row max over the valid keys
+  const int r = (warp & 3) * 32 + lane;  // query row within the tile == TMEM lane
+  const uint32_t trow = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+  const ColRange cr = my_chunks(NK, half);
+  // pass 1: row max over the valid keys of this thread's column half (two TMEM loads in flight per wait)
   float mx = -INFINITY;
-  for (int c0 = 0; c0 < NK; c0 += 32) {
-    uint32_t v[32];
-    if (c0 + 32 <= NK) {
-      tmem_ld_32x32b_x32(trow + c0, v);
-    } else {
-      uint32_t w[16];
-      tmem_ld_32x32b_x16(trow + c0, w);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) { v[j] = w[j]; v[16 + j] = 0xff800000u; }
-    }
+  for (int c = cr.c_begin; c < cr.c_end; c += 2) {
+    uint32_t v0[32], v1[32];
+    const bool two = (c + 1 < cr.c_end);
+    issue_chunk(trow, c * 32, NK, v0);
+    if (two) issue_chunk(trow, (c + 1) * 32, NK, v1);
     tmem_ld_wait();
-#pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (c0 + j < a.N) mx = fmaxf(mx, __uint_as_float(v[j]));
+    mx = fmaxf(mx, chunk_max(v0, c * 32, NK, a.N));
+    if (two) mx = fmaxf(mx, chunk_max(v1, (c + 1) * 32, NK, a.N));
   }
+  red[half * 128 + r] = mx;
+  __syncthreads();
+  VITB_STAMP(4);
+  mx = fmaxf(red[r], red[128 + r]);
   // pass 2: p = exp2((s - max) * c), row sum, bf16 P into the swizzled A-operand image
   float sum = 0.f;
   const float mxs = mx * a.scale_log2;
   const uint32_t sP_u = smem_u32(sP);
-  for (int c0 = 0; c0 < NK; c0 += 32) {
+  for (int c = cr.c_begin; c < cr.c_end; ++c) {
+    const int c0 = c * 32;
     uint32_t v[32];
-    const bool full = (c0 + 32 <= NK);
-    if (full) {
-      tmem_ld_32x32b_x32(trow + c0, v);
-    } else {
-      uint32_t w[16];
-      tmem_ld_32x32b_x16(trow + c0, w);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) { v[j] = w[j]; v[16 + j] = 0u; }
-    }
-    tmem_ld_wait();
+    ld_chunk(trow, c0, NK, 0u, v);
     float pv[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      const float e = exp2f(fmaf(__uint_as_float(v[j]), a.scale_log2, -mxs));
+      const float e = ex2_approx(fmaf(__uint_as_float(v[j]), a.scale_log2, -mxs));
       pv[j] = (c0 + j < a.N) ? e : 0.f;
       sum += pv[j];
     }
-    const int kc = c0 >> 6;
-    const int u0 = (c0 & 63) >> 3;
-    const int nunits = full ? 4 : 2;
+    const int kc = c0 >> 6, u0 = (c0 & 63) >> 3, nunits = (c0 + 32 <= NK) ? 4 : 2;
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       if (u < nunits)
@@ -165,9 +228,12 @@ attn_fwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
                      pack_bf16x2(pv[8 * u + 6], pv[8 * u + 7]));
     }
   }
+  red[256 + half * 128 + r] = sum;
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
+  sum = red[256 + r] + red[256 + 128 + r];
+  VITB_STAMP(5);
   if (tid == 0) {
     tc_fence_after();
     mbar_wait(bar_v, 0);
@@ -181,38 +247,20 @@ attn_fwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   __syncwarp();
   mbar_wait(bar_o, 0);
   tc_fence_after();
+  VITB_STAMP(6);
   const int row = row0 + r;
-  const float inv = 1.0f / sum;
   {
-    uint32_t v0[32], v1[32];
-    tmem_ld_32x32b_x32(trow, v0);
-    tmem_ld_32x32b_x32(trow + 32, v1);
+    uint32_t v[32];
+    tmem_ld_32x32b_x32(trow + half * 32, v);   // this thread's 32 of the 64 head-dim columns
     tmem_ld_wait();
     if (row < a.N) {
-      uint4* dst = reinterpret_cast<uint4*>(a.o + b * a.o_bs + static_cast<long long>(row) * a.o_rs + h * DH);
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        uint4 w;
-        w.x = pack_bf16x2(__uint_as_float(v0[8 * u + 0]) * inv, __uint_as_float(v0[8 * u + 1]) * inv);
-        w.y = pack_bf16x2(__uint_as_float(v0[8 * u + 2]) * inv, __uint_as_float(v0[8 * u + 3]) * inv);
-        w.z = pack_bf16x2(__uint_as_float(v0[8 * u + 4]) * inv, __uint_as_float(v0[8 * u + 5]) * inv);
-        w.w = pack_bf16x2(__uint_as_float(v0[8 * u + 6]) * inv, __uint_as_float(v0[8 * u + 7]) * inv);
-        dst[u] = w;
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        uint4 w;
-        w.x = pack_bf16x2(__uint_as_float(v1[8 * u + 0]) * inv, __uint_as_float(v1[8 * u + 1]) * inv);
-        w.y = pack_bf16x2(__uint_as_float(v1[8 * u + 2]) * inv, __uint_as_float(v1[8 * u + 3]) * inv);
-        w.z = pack_bf16x2(__uint_as_float(v1[8 * u + 4]) * inv, __uint_as_float(v1[8 * u + 5]) * inv);
-        w.w = pack_bf16x2(__uint_as_float(v1[8 * u + 6]) * inv, __uint_as_float(v1[8 * u + 7]) * inv);
-        dst[4 + u] = w;
-      }
-      if (a.lse) a.lse[(static_cast<long long>(b) * a.H + h) * a.N + row] = mx * a.scale + logf(sum);
+      st_row64_bf16(a.o + b * a.o_bs + static_cast<long long>(row) * a.o_rs + h * DH + half * 32, v, 1.0f / sum);
+      if (a.lse && half == 0) a.lse[(static_cast<long long>(b) * a.H + h) * a.N + row] = mx * a.scale + logf(sum);
     }
   }
   tc_fence_before();
   __syncthreads();
+  VITB_STAMP(7);
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
 }
 
@@ -220,10 +268,10 @@ attn_fwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
 // backward
 // ================================================================================================
 // TMEM columns: [0,256) S then dP then dQ ; [256,384) dK (two 128-key M tiles x 64) ; [384,512) dV
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(kAttnThreads, 1)
 attn_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
             const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
-            const AttnTc a) {
+            const __grid_constant__ AttnTc a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   const int NK = a.NK;
@@ -242,8 +290,10 @@ attn_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
                  bar_dq = bar_kv + 32, bar_fin = bar_kv + 40;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int half = warp >> 2;
   const int h = blockIdx.x, b = blockIdx.y;
-  const int r = warp * 32 + lane;
+  const int r = (warp & 3) * 32 + lane;
+  const ColRange cr = my_chunks(NK, half);
 
   if (tid == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
@@ -255,14 +305,14 @@ attn_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   {
     const uint32_t base = smem_u32(sP);
     const int total16 = 2 * nchunks * kChunkBytes / 16;
-    for (int i = tid; i < total16; i += 128) st_shared_v4(base + i * 16, 0u, 0u, 0u, 0u);
+    for (int i = tid; i < total16; i += kAttnThreads) st_shared_v4(base + i * 16, 0u, 0u, 0u, 0u);
   }
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t trow = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+  const uint32_t trow = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
   const uint32_t sP_u = smem_u32(sP), sDS_u = smem_u32(sDS);
   const uint32_t sQ_u = smem_u32(sQ), sDO_u = smem_u32(sDO), sK_u = smem_u32(sK), sV_u = smem_u32(sV);
 
@@ -290,7 +340,7 @@ attn_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
                      umma_smem_desc_sw128(sK_u + k * 32, 16, 1024), idesc, k > 0 ? 1u : 0u);
       umma_commit(bar_s);
     }
-    // D_i = rowsum(dO * O) and LSE straight from HBM while the MMA runs
+    // D_i = rowsum(dO * O) and LSE straight from HBM while the MMA runs (both threads of a row compute it)
     float Di = 0.f, lse = INFINITY;
     if (row < a.N) {
       const uint4* po = reinterpret_cast<const uint4*>(a.o_in + b * a.o_bs + static_cast<long long>(row) * a.o_rs + h * DH);
@@ -309,25 +359,17 @@ attn_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     mbar_wait(bar_s, ph);
     tc_fence_after();
     // P = exp2(S*c - LSE*log2e) -> bf16 -> sP   (rows >= N and keys >= N give exactly 0)
-    for (int c0 = 0; c0 < NK; c0 += 32) {
+    for (int c = cr.c_begin; c < cr.c_end; ++c) {
+      const int c0 = c * 32;
       uint32_t v[32];
-      const bool full = (c0 + 32 <= NK);
-      if (full) {
-        tmem_ld_32x32b_x32(trow + c0, v);
-      } else {
-        uint32_t w[16];
-        tmem_ld_32x32b_x16(trow + c0, w);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) { v[j] = w[j]; v[16 + j] = 0u; }
-      }
-      tmem_ld_wait();
+      ld_chunk(trow, c0, NK, 0u, v);
       float pv[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const float e = exp2f(fmaf(__uint_as_float(v[j]), a.scale_log2, -lse2));
+        const float e = ex2_approx(fmaf(__uint_as_float(v[j]), a.scale_log2, -lse2));
         pv[j] = (c0 + j < a.N && row < a.N) ? e : 0.f;
       }
-      const int kc = c0 >> 6, u0 = (c0 & 63) >> 3, nunits = full ? 4 : 2;
+      const int kc = c0 >> 6, u0 = (c0 & 63) >> 3, nunits = (c0 + 32 <= NK) ? 4 : 2;
 #pragma unroll
       for (int u = 0; u < 4; ++u)
         if (u < nunits)
@@ -359,19 +401,11 @@ attn_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     mbar_wait(bar_dp, ph);
     tc_fence_after();
     // dS = P * (dP - D) * c  -> bf16 -> sDS
-    for (int c0 = 0; c0 < NK; c0 += 32) {
+    for (int c = cr.c_begin; c < cr.c_end; ++c) {
+      const int c0 = c * 32;
       uint32_t v[32];
-      const bool full = (c0 + 32 <= NK);
-      if (full) {
-        tmem_ld_32x32b_x32(trow + c0, v);
-      } else {
-        uint32_t w[16];
-        tmem_ld_32x32b_x16(trow + c0, w);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) { v[j] = w[j]; v[16 + j] = 0u; }
-      }
-      tmem_ld_wait();
-      const int kc = c0 >> 6, u0 = (c0 & 63) >> 3, nunits = full ? 4 : 2;
+      ld_chunk(trow, c0, NK, 0u, v);
+      const int kc = c0 >> 6, u0 = (c0 & 63) >> 3, nunits = (c0 + 32 <= NK) ? 4 : 2;
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         if (u < nunits) {
@@ -416,31 +450,11 @@ attn_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     mbar_wait(bar_dq, ph);
     tc_fence_after();
     {
-      uint32_t v0[32], v1[32];
-      tmem_ld_32x32b_x32(trow, v0);
-      tmem_ld_32x32b_x32(trow + 32, v1);
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(trow + half * 32, v);
       tmem_ld_wait();
-      if (row < a.N) {
-        uint4* dst = reinterpret_cast<uint4*>(a.dq + b * a.dq_bs + static_cast<long long>(row) * a.dq_rs + h * DH);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          uint4 w;
-          w.x = pack_bf16x2(__uint_as_float(v0[8 * u + 0]), __uint_as_float(v0[8 * u + 1]));
-          w.y = pack_bf16x2(__uint_as_float(v0[8 * u + 2]), __uint_as_float(v0[8 * u + 3]));
-          w.z = pack_bf16x2(__uint_as_float(v0[8 * u + 4]), __uint_as_float(v0[8 * u + 5]));
-          w.w = pack_bf16x2(__uint_as_float(v0[8 * u + 6]), __uint_as_float(v0[8 * u + 7]));
-          dst[u] = w;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          uint4 w;
-          w.x = pack_bf16x2(__uint_as_float(v1[8 * u + 0]), __uint_as_float(v1[8 * u + 1]));
-          w.y = pack_bf16x2(__uint_as_float(v1[8 * u + 2]), __uint_as_float(v1[8 * u + 3]));
-          w.z = pack_bf16x2(__uint_as_float(v1[8 * u + 4]), __uint_as_float(v1[8 * u + 5]));
-          w.w = pack_bf16x2(__uint_as_float(v1[8 * u + 6]), __uint_as_float(v1[8 * u + 7]));
-          dst[4 + u] = w;
-        }
-      }
+      if (row < a.N)
+        st_row64_bf16(a.dq + b * a.dq_bs + static_cast<long long>(row) * a.dq_rs + h * DH + half * 32, v, 1.0f);
     }
     // the next query tile overwrites sQ/sDO/sP/sDS and TMEM[0,256): wait until every MMA of this
     // tile (dK included) has retired, and until all warps have drained dQ from TMEM
@@ -449,38 +463,19 @@ attn_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     __syncthreads();
     tc_fence_after();
   }
-  // dK, dV: TMEM lane = key within the M tile
+  // dK, dV: TMEM lane = key within the M tile; the two threads of a lane split the 64 head-dim columns
   for (int mt = 0; mt < mtiles; ++mt) {
     const int key = mt * 128 + r;
 #pragma unroll
     for (int which = 0; which < 2; ++which) {
-      uint32_t v0[32], v1[32];
-      const uint32_t col = (which == 0 ? 256u : 384u) + static_cast<uint32_t>(mt * 64);
-      tmem_ld_32x32b_x32(trow + col, v0);
-      tmem_ld_32x32b_x32(trow + col + 32, v1);
+      uint32_t v[32];
+      const uint32_t col = (which == 0 ? 256u : 384u) + static_cast<uint32_t>(mt * 64 + half * 32);
+      tmem_ld_32x32b_x32(trow + col, v);
       tmem_ld_wait();
       if (key < a.N) {
         __nv_bfloat16* base = which == 0 ? a.dk + b * a.dk_bs + static_cast<long long>(key) * a.dk_rs
                                          : a.dv + b * a.dv_bs + static_cast<long long>(key) * a.dv_rs;
-        uint4* dst = reinterpret_cast<uint4*>(base + h * DH);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          uint4 w;
-          w.x = pack_bf16x2(__uint_as_float(v0[8 * u + 0]), __uint_as_float(v0[8 * u + 1]));
-          w.y = pack_bf16x2(__uint_as_float(v0[8 * u + 2]), __uint_as_float(v0[8 * u + 3]));
-          w.z = pack_bf16x2(__uint_as_float(v0[8 * u + 4]), __uint_as_float(v0[8 * u + 5]));
-          w.w = pack_bf16x2(__uint_as_float(v0[8 * u + 6]), __uint_as_float(v0[8 * u + 7]));
-          dst[u] = w;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          uint4 w;
-          w.x = pack_bf16x2(__uint_as_float(v1[8 * u + 0]), __uint_as_float(v1[8 * u + 1]));
-          w.y = pack_bf16x2(__uint_as_float(v1[8 * u + 2]), __uint_as_float(v1[8 * u + 3]));
-          w.z = pack_bf16x2(__uint_as_float(v1[8 * u + 4]), __uint_as_float(v1[8 * u + 5]));
-          w.w = pack_bf16x2(__uint_as_float(v1[8 * u + 6]), __uint_as_float(v1[8 * u + 7]));
-          dst[4 + u] = w;
-        }
+        st_row64_bf16(base + h * DH + half * 32, v, 1.0f);
       }
     }
   }
@@ -531,12 +526,16 @@ extern "C" int vitb_attn_fwd_tc(const vitb_attn_params* p, void* stream_) {
   a.scale_log2 = a.scale * 1.4426950408889634f;
   a.o = reinterpret_cast<__nv_bfloat16*>(p->o); a.o_bs = p->o_batch_stride; a.o_rs = p->o_row_stride;
   a.lse = p->lse;
+  {
+    const char* e = getenv("VITB_ATTN_DBG");   // diagnostics: device pointer (decimal) for phase time stamps
+    a.dbg = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 10)) : nullptr;
+  }
   const int kv_bytes = NK * 128, nchunks = (NK + 63) / 64;
   const int u_bytes = (kChunkBytes + kv_bytes) > nchunks * kChunkBytes ? (kChunkBytes + kv_bytes) : nchunks * kChunkBytes;
-  const int smem = kv_bytes + u_bytes + 64 + 1024;
+  const int smem = kv_bytes + u_bytes + 64 + 4 * 128 * 4 + 1024;
   VITB_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   dim3 grid((N + 127) / 128, p->H, p->B);
-  attn_fwd_tc<<<grid, 128, smem, reinterpret_cast<cudaStream_t>(stream_)>>>(tq, tk, tv, a);
+  attn_fwd_tc<<<grid, kAttnThreads, smem, reinterpret_cast<cudaStream_t>(stream_)>>>(tq, tk, tv, a);
   VITB_LAUNCH_CHECK("attn_fwd_tc");
   return VITB_OK;
 }
@@ -572,7 +571,7 @@ extern "C" int vitb_attn_bwd_tc(const vitb_attn_params* p, void* stream_) {
   VITB_REQUIRE(smem <= 227 * 1024, VITB_ERR_UNSUPPORTED_SHAPE, "attn_bwd_tc: %d B of shared memory", smem);
   VITB_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   dim3 grid(p->H, p->B);
-  attn_bwd_tc<<<grid, 128, smem, reinterpret_cast<cudaStream_t>(stream_)>>>(tq, tk, tv, tdo, a);
+  attn_bwd_tc<<<grid, kAttnThreads, smem, reinterpret_cast<cudaStream_t>(stream_)>>>(tq, tk, tv, tdo, a);
   VITB_LAUNCH_CHECK("attn_bwd_tc");
   return VITB_OK;
 }

@@ -258,6 +258,16 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, bool a_mn, 
 }
 
 // ---- math -------------------------------------------------------------------------------------
+__device__ __forceinline__ float ex2_approx(float x) {   // single MUFU.EX2
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {   // single MUFU.RCP
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float gelu_erf(float z) {
   return 0.5f * z * (1.0f + erff(z * 0.70710678118654752440f));
 }

@@ -154,9 +154,12 @@ embed_bwd_kernel(const float* __restrict__ dx, int Bsz, int N, int D, float* __r
 // out[c] += sum_r x[r, c]; thread owns 4 columns (bf16) / 4 columns (fp32), rows split across blocks.y
 template <bool BF16>
 __global__ void __launch_bounds__(kThreads)
-colsum_kernel(const void* __restrict__ x_, int rows, int cols, long long ld_, float* __restrict__ out) {
+colsum_kernel(const void* __restrict__ x_, int rows, int cols, long long ld_, float* __restrict__ out0,
+              float* __restrict__ out1, float* __restrict__ out2, int seg_cols) {
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (c >= cols) return;
+  const int seg = c / seg_cols;
+  float* out = (seg == 0 ? out0 : (seg == 1 ? out1 : out2)) - static_cast<long long>(seg) * seg_cols;
   const int rows_per = (rows + gridDim.y - 1) / gridDim.y;
   const int r0 = blockIdx.y * rows_per;
   const int r1 = min(rows, r0 + rows_per);
@@ -225,8 +228,9 @@ ce_kernel(const float* __restrict__ logits, const long long* __restrict__ labels
 // refreshing the bf16 GEMM shadow (and its lo half in fp32 parity mode) in the same pass.
 __global__ void __launch_bounds__(kThreads)
 sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, long long n,
-           float lr, float momentum, float dampening, float wd, int nesterov, int first_step,
-           __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+           float lr_host, const float* __restrict__ lr_dev, float momentum, float dampening, float wd, int nesterov,
+           int first_step, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  const float lr = lr_dev ? *lr_dev : lr_host;   // device-resident lr keeps a captured CUDA graph schedulable
   const long long n4 = n >> 2;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -435,9 +439,30 @@ int vitb_colsum(const void* x, int x_dtype, int rows, int cols, int64_t ld, floa
   if (by < 1) by = 1;
   dim3 grid(bx, by);
   if (x_dtype == VITB_BF16)
-    colsum_kernel<true><<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(x, rows, cols, ld, out);
+    colsum_kernel<true><<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(x, rows, cols, ld, out, out, out, cols);
   else
-    colsum_kernel<false><<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(x, rows, cols, ld, out);
+    colsum_kernel<false><<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(x, rows, cols, ld, out, out, out, cols);
+  VITB_LAUNCH_CHECK("colsum_kernel");
+  return VITB_OK;
+}
+
+int vitb_colsum3(const void* x, int x_dtype, int rows, int seg_cols, int64_t ld, float* out0, float* out1,
+                 float* out2, void* stream_) {
+  int st = vitb_check_device();
+  if (st != VITB_OK) return st;
+  if (rows == 0 || seg_cols == 0) return VITB_OK;
+  const int cols = 3 * seg_cols;
+  VITB_REQUIRE(x && out0 && out1 && out2 && rows > 0 && seg_cols % 4 == 0 && ld % 4 == 0, VITB_ERR_UNSUPPORTED_SHAPE,
+               "colsum3: rows=%d seg_cols=%d ld=%lld", rows, seg_cols, (long long)ld);
+  const int bx = (cols / 4 + 127) / 128;
+  int by = (vitb_num_sms() * 4 + bx - 1) / bx;
+  if (by > (rows + 63) / 64) by = (rows + 63) / 64;
+  if (by < 1) by = 1;
+  dim3 grid(bx, by);
+  if (x_dtype == VITB_BF16)
+    colsum_kernel<true><<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(x, rows, cols, ld, out0, out1, out2, seg_cols);
+  else
+    colsum_kernel<false><<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(x, rows, cols, ld, out0, out1, out2, seg_cols);
   VITB_LAUNCH_CHECK("colsum_kernel");
   return VITB_OK;
 }
@@ -453,7 +478,7 @@ int vitb_cross_entropy(const float* logits, const int64_t* labels, int B, int C,
   return VITB_OK;
 }
 
-int vitb_sgd_momentum(float* p, const float* g, float* m, int64_t n, float lr, float momentum,
+int vitb_sgd_momentum(float* p, const float* g, float* m, int64_t n, float lr, const float* lr_dev, float momentum,
                       float dampening, float weight_decay, int nesterov, int first_step, void* shadow_hi,
                       void* shadow_lo, void* stream_) {
   int st = vitb_check_device();
@@ -462,7 +487,7 @@ int vitb_sgd_momentum(float* p, const float* g, float* m, int64_t n, float lr, f
   VITB_REQUIRE(p && g && n > 0 && n % 4 == 0, VITB_ERR_UNSUPPORTED_SHAPE, "sgd: n=%lld must be a multiple of 4",
                (long long)n);
   sgd_kernel<<<grid_for(n / 4), kThreads, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
-      p, g, m, n, lr, momentum, dampening, weight_decay, nesterov, first_step,
+      p, g, m, n, lr, lr_dev, momentum, dampening, weight_decay, nesterov, first_step,
       reinterpret_cast<__nv_bfloat16*>(shadow_hi), reinterpret_cast<__nv_bfloat16*>(shadow_lo));
   VITB_LAUNCH_CHECK("sgd_kernel");
   return VITB_OK;

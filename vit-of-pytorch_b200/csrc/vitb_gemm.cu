@@ -98,16 +98,6 @@ __device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {  // two 8-byte l
 }
 // erf-GELU and its derivative from ONE rcp + ONE ex2 (Abramowitz-Stegun 7.1.26, |erf error| < 1.5e-7):
 // used where the result is rounded to bf16 anyway; fp32 outputs keep erff.
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float rcp_approx(float x) {
-  float y;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 __device__ __forceinline__ void gelu_fast(float z, float& g, float& dg) {
   const float u = fabsf(z) * 0.70710678118654752440f;
   const float t = rcp_approx(fmaf(0.3275911f, u, 1.0f));

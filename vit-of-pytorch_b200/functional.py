@@ -813,9 +813,12 @@ class _EncoderBlockFused(torch.autograd.Function):
             acc, r = _acc(w, (D, D))
             ret(w, r)
             ops.gemm(xn, sl, a_mn=True, b_mn=True, out=acc, accumulate=True)              # dW[K,N] = xn^T dQ
+        accs = []
+        for b in (bq, bk, bv):
             accb, r = _acc(b)
             ret(b, r)
-            ops.colsum(sl, accb.view(-1))
+            accs.append(accb.view(-1))
+        ops.colsum3(dq2, accs[0], accs[1], accs[2])
         dxn = ops.gemm([dq2[:, :D], dq2[:, D:2 * D], dq2[:, 2 * D:]],
                        [SHADOW.get(w, False)[0].view(D, D) for w in (wq, wk, wv)], b_mn=False, out_dtype=BF16)
         # ---- LN1 backward + residual: dx = dh + LN'(dxn) ----

@@ -296,6 +296,15 @@ def colsum(x, out):
     return out
 
 
+def colsum3(x, out0, out1, out2):
+    """x: packed [rows, 3*S]; out_i[S] += column sums of segment i (q/k/v bias gradients in one pass)."""
+    L.require_cuda(x, out0, out1, out2)
+    _check_2d_rowmajor(x, "x")
+    S = x.shape[1] // 3
+    L.check(L._vitb_colsum3(L.ptr(x), L.dtype_code(x), x.shape[0], S, x.stride(0), L.ptr(out0), L.ptr(out1), L.ptr(out2),
+                            L.stream_ptr(x.device)), "vitb_colsum3")
+
+
 def cross_entropy(logits, labels, *, want_grad=True):
     L.require_cuda(logits, labels)
     if logits.dtype != torch.float32 or not logits.is_contiguous() or labels.dtype != torch.int64:
@@ -309,9 +318,9 @@ def cross_entropy(logits, labels, *, want_grad=True):
 
 
 def sgd_momentum(p, g, m, lr, momentum, *, dampening=0.0, weight_decay=0.0, nesterov=False, first_step=False,
-                 shadow_hi=None, shadow_lo=None):
+                 shadow_hi=None, shadow_lo=None, lr_dev=None):
     L.require_cuda(p, g, m)
-    L.check(L._vitb_sgd_momentum(L.ptr(p), L.ptr(g), L.ptr(m), p.numel(), float(lr), float(momentum),
+    L.check(L._vitb_sgd_momentum(L.ptr(p), L.ptr(g), L.ptr(m), p.numel(), float(lr), L.ptr(lr_dev), float(momentum),
                                  float(dampening), float(weight_decay), int(nesterov), int(first_step),
                                  L.ptr(shadow_hi), L.ptr(shadow_lo), L.stream_ptr(p.device)), "vitb_sgd_momentum")
 

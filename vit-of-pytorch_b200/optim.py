@@ -90,18 +90,31 @@ class FusedSGD(_FusedBase):
         self._bufs = [torch.zeros_like(fg.flat_p) if g["momentum"] != 0 else None
                       for fg, g in zip(self._flat, self.param_groups)]
         self._steps = 0
+        # device-resident learning rates: a captured CUDA graph of step() keeps following the LR scheduler
+        self._lr_dev = [torch.full((), float(g["lr"]), dtype=torch.float32, device=fg.flat_p.device)
+                        for fg, g in zip(self._flat, self.param_groups)]
+        self._lr_host = [float(g["lr"]) for g in self.param_groups]
+
+    def sync_lr(self):
+        """Push param_groups[...]['lr'] to the device scalars (call before replaying a captured step)."""
+        for i, g in enumerate(self.param_groups):
+            if float(g["lr"]) != self._lr_host[i]:
+                self._lr_host[i] = float(g["lr"])
+                self._lr_dev[i].fill_(self._lr_host[i])
 
     @torch.no_grad()
     def step(self, closure=None):
         if closure is not None:
             raise NotImplementedError("FusedSGD.step does not take a closure")
         want_lo = F.get_precision() == "fp32"
-        for fg, g, buf in zip(self._flat, self.param_groups, self._bufs):
+        if not torch.cuda.is_current_stream_capturing():
+            self.sync_lr()
+        for fg, g, buf, lr_dev in zip(self._flat, self.param_groups, self._bufs, self._lr_dev):
             if want_lo:
                 fg.ensure_lo()
             ops.sgd_momentum(fg.flat_p, fg.flat_g, buf, g["lr"], g["momentum"], dampening=g["dampening"],
                              weight_decay=g["weight_decay"], nesterov=g["nesterov"], first_step=self._steps == 0,
-                             shadow_hi=fg.flat_hi, shadow_lo=fg.flat_lo)
+                             shadow_hi=fg.flat_hi, shadow_lo=fg.flat_lo, lr_dev=lr_dev)
             fg.mark_fresh()
         self._steps += 1
 
