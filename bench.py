@@ -163,6 +163,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # never hang a GPU box: abort the whole process if the run has not finished in time
+    import signal
+    signal.signal(signal.SIGALRM, lambda *_: os._exit(3))
+    signal.alarm(int(os.environ.get("VITB_BENCH_TIMEOUT_S", "900")))
     if args.impl == "reference":
         run_reference(args, rank)
         return
@@ -201,7 +205,9 @@ def main():
         return loss
 
     graphed = None
-    if not args.no_graph:
+    # One CUDA graph per step at N = 1.  With NCCL in the step (N > 1) the step is launched eagerly: capturing the
+    # side-stream all-reduces hung an 8-rank run in round 1, and the eager step is already GPU-bound (2 % slower).
+    if not args.no_graph and world == 1:
         try:   # the whole step (fwd + bwd + all-reduce + SGD) as one replayable CUDA graph
             graphed = vitb200.train.GraphedTrainStep(net, opt, img_d, lab_d)
         except Exception as exc:  # noqa: BLE001 - report and measure eagerly rather than die
