@@ -132,6 +132,26 @@ class EncoderBlock(nn.Module):
         out = F.layer_norm(h, self.norm2.weight, self.norm2.bias, self.norm2.eps)
         return self.mlp(out, residual=h)
 
+    def forward_row0(self, x):
+        """Row 0 (the class token) of forward(x), for a block whose other output rows nobody reads — the
+        LAST encoder block: the reference normalises all rows and then classifies feat[:, 0] only
+        (src/model.py:155,210).  Keys and values still need every token, but the query, the output projection
+        and the whole MLP are per-row, so they run on B rows instead of B*N; every logit and every parameter
+        gradient is unchanged (the skipped rows have exactly zero gradient in the reference as well)."""
+        if self.training:
+            _dropout_supported(self.dropout_rate, "EncoderBlock")
+        x = x if x.dtype == torch.float32 else x.float()
+        a = self.attn
+        xn = F.layer_norm(x, self.norm1.weight, self.norm1.bias, self.norm1.eps)          # [B,N,D]
+        k = F.linear(xn, a.key.weight, a.key.bias, layout="kn")
+        v = F.linear(xn, a.value.weight, a.value.bias, layout="kn")
+        x0 = x[:, 0]
+        q = F.linear(xn[:, 0], a.query.weight, a.query.bias, layout="kn").unsqueeze(1)        # [B,1,D]
+        o = F.attention(q, k, v, a.heads).squeeze(1)                                          # [B,D]
+        h = F.linear(o, a.out.weight, a.out.bias, layout="kn", residual=x0)
+        hn = F.layer_norm(h, self.norm2.weight, self.norm2.bias, self.norm2.eps)
+        return self.mlp(hn, residual=h)                                                       # [B,D]
+
 
 class Encoder(nn.Module):
     """pos-emb -> L x EncoderBlock -> LayerNorm (src/model.py:133-156)."""
@@ -147,9 +167,13 @@ class Encoder(nn.Module):
 
     def forward(self, x, pos_added=False, norm_rows=None):
         out = x if pos_added else self.pos_embedding(x)
-        for layer in self.encoder_layers:
+        layers = list(self.encoder_layers)
+        row0_only = norm_rows == 0 and len(layers) > 0 and F.get_precision() == "bf16"
+        for layer in (layers[:-1] if row0_only else layers):
             out = layer(out)
-        if norm_rows is not None:
+        if row0_only:
+            out = layers[-1].forward_row0(out)          # [B, D]: only the class-token row is ever read
+        elif norm_rows is not None:
             out = out[:, norm_rows]
         return F.layer_norm(out, self.norm.weight, self.norm.bias, self.norm.eps, out_dtype=torch.float32)
 
