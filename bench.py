@@ -45,6 +45,15 @@ def peaks():
     return {"tflops_burst": 1590.0, "tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback"}
 
 
+def gemm_traffic():
+    """Average DRAM bytes (read + write) per vitb_gemm_kernel launch of one training step, from the committed
+    ncu capture profiles/gemm_traffic_r01.json (dram__bytes_read.sum + dram__bytes_write.sum); None if absent."""
+    p = os.path.join(ROOT, "profiles", "gemm_traffic_r01.json")
+    if not os.path.exists(p):
+        return None
+    return json.load(open(p)).get("dram_bytes_per_launch")
+
+
 # ---------------------------------------------------------------------------------------------------
 # clocks sampled DURING the timed region
 # ---------------------------------------------------------------------------------------------------
@@ -264,8 +273,9 @@ def main():
     torch.cuda.synchronize()
     recs = vitb200.ops.PROFILE_GEMM
     vitb200.ops.PROFILE_GEMM = None
-    gemm_ms = sum(a.elapsed_time(b) for a, b, _ in recs)
-    gemm_flop = sum(f for _, _, f in recs)
+    gemm_ms = sum(r[0].elapsed_time(r[1]) for r in recs)
+    gemm_flop = sum(r[2] for r in recs)
+    gemm_bytes = sum(r[3] for r in recs)
     if world > 1:
         t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -291,7 +301,9 @@ def main():
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "kernel": "vitb_gemm_kernel (tcgen05)", "achieved": ach,
                          "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tflops_sustained"],
-                         "peak_source": pk["source"] + " sustained cuBLAS bf16", "traffic": None,
+                         "peak_source": pk["source"] + " sustained cuBLAS bf16", "traffic": gemm_traffic(),
+                         "algorithmic_bytes_per_launch": gemm_bytes / max(1, len(recs)),
+                         "flop_per_launch": gemm_flop / max(1, len(recs)),
                          "gemm_share_of_step": (gemm_ms / 2) / (ms / args.steps), "launches_timed": len(recs)},
             "roofline_step": {"achieved": step_tf, "unit": "TFLOP/s per GPU (105.379 GFLOP/img)",
                               "frac_of_sustained": step_tf / pk["tflops_sustained"],

@@ -153,3 +153,20 @@ def test_gemm_rejects_cpu_tensors():
     import vitb200
     with pytest.raises(RuntimeError):
         vitb200.ops.gemm(torch.zeros(8, 8, dtype=torch.bfloat16), torch.zeros(8, 8, dtype=torch.bfloat16))
+
+
+def test_gemm_gelu_bwd_with_colsum_bf16():
+    """fc2-dgrad epilogue as the fused block uses it: dz = (dy W2) * gelu'(z), db1 += column sums of dz."""
+    import vitb200
+    M, N, K = 1000, 3072, 768
+    A, B, ref = _operands(M, N, K, False, True, seed=61)
+    A = (A.float() * 0.05).to(torch.bfloat16)
+    ref = A.float() @ B.float()
+    z = _mk((M, N), 62)
+    cs = torch.ones(N, device="cuda")
+    out = vitb200.ops.gemm(A, B, b_mn=True, epilogue=vitb200.ops.EPI_GELU_BWD, aux=z, colsum=cs)
+    torch.cuda.synchronize()
+    zf = z.float().requires_grad_(True)
+    torch.nn.functional.gelu(zf).backward(ref)
+    assert rel_l2(out, zf.grad) < 4e-3
+    assert rel_l2(cs, zf.grad.sum(0) + 1.0) < 4e-3

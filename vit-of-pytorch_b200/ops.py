@@ -101,7 +101,11 @@ def gemm(A, B, *, a_mn=False, b_mn=False, out=None, out_dtype=torch.bfloat16, bi
         e0.record()
         L.check(L._vitb_gemm(C.byref(p), L.stream_ptr(out.device)), "vitb_gemm")
         e1.record()
-        PROFILE_GEMM.append((e0, e1, 2.0 * M * N * sum(int(p.K[i]) for i in range(len(As)))))
+        ksum = sum(int(p.K[i]) for i in range(len(As)))
+        esz = out.element_size()
+        nbytes = 2.0 * (M + N) * ksum + M * N * esz * (1 + (d2 is not None) + (aux is not None)) + \
+            (M * N * residual.element_size() if residual is not None else 0)
+        PROFILE_GEMM.append((e0, e1, 2.0 * M * N * ksum, nbytes))
         return out
     L.check(L._vitb_gemm(C.byref(p), L.stream_ptr(out.device)), "vitb_gemm")
     return out
