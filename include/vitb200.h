@@ -218,10 +218,11 @@ int vitb_sgd_momentum(float* p, const float* g, float* m, int64_t n, float lr, c
                       float dampening, float weight_decay, int nesterov, int first_step,
                       void* shadow_hi, void* shadow_lo, void* stream);
 /* torch.optim.AdamW over a flat buffer (res-vit/train.py:272-277); grad_scale_dev (optional device
- * scalar) carries the clip_grad_norm_ coefficient (res-vit/train.py:65). */
-int vitb_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
-               float beta2, float eps, float weight_decay, int step, const float* grad_scale_dev,
-               void* shadow_hi, void* shadow_lo, void* stream);
+ * scalar) carries the clip_grad_norm_ coefficient (res-vit/train.py:65).  lr_dev / step_dev (optional device
+ * scalars) override lr / step so a captured CUDA graph follows the scheduler and the bias correction. */
+int vitb_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, const float* lr_dev, float beta1,
+               float beta2, float eps, float weight_decay, int step, const int* step_dev,
+               const float* grad_scale_dev, void* shadow_hi, void* shadow_lo, void* stream);
 int vitb_sumsq(const float* x, int64_t n, float* out, void* stream);
 int vitb_clip_coef(const float* sumsq, float max_norm, float* coef, float* norm_out, void* stream);
 

@@ -97,7 +97,17 @@ if "c5" in which:
             (c + a + d).backward()
             opt.step()
         ms = timed(step, 5, 2)
-        log("c5 Res-ViT B/16 fine-tune (router 0.4, LoRA r8, block_size 1) bs%d: %.2f ms/step, %.0f img/s" % (B, ms, B / ms * 1e3))
+        log("c5 Res-ViT B/16 fine-tune (router 0.4, LoRA r8, block_size 1) bs%d eager: %.2f ms/step, %.0f img/s" % (B, ms, B / ms * 1e3))
+        try:
+            def fl(net, x, y):
+                c, a, d, e, metric = net(x, y)
+                return c + a + d
+            gs = vitb200.train.GraphedTrainStep(m, opt, img, lab, warmup=1, forward_loss=fl)
+            ms = timed(lambda: gs(img, lab), 10, 2)
+            log("c5 Res-ViT B/16 fine-tune bs%d one CUDA graph per step (%d launches): %.2f ms/step, %.0f img/s"
+                % (B, gs.launches_per_step, ms, B / ms * 1e3))
+        except Exception as exc:  # noqa: BLE001
+            log("c5 graph capture failed:", repr(exc)[:300])
         del m, opt
         torch.cuda.empty_cache()
 os.makedirs("gpurun_out", exist_ok=True)

@@ -169,7 +169,7 @@ _vitb_colsum = _sig("vitb_colsum", [_vp, _i, _i, _i, _i64, _vp, _vp])
 _vitb_colsum3 = _sig("vitb_colsum3", [_vp, _i, _i, _i, _i64, _vp, _vp, _vp, _vp])
 _vitb_cross_entropy = _sig("vitb_cross_entropy", [_vp, _vp, _i, _i, _vp, _vp, _vp])
 _vitb_sgd_momentum = _sig("vitb_sgd_momentum", [_vp, _vp, _vp, _i64, _f, _vp, _f, _f, _f, _i, _i, _vp, _vp, _vp])
-_vitb_adamw = _sig("vitb_adamw", [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _i, _vp, _vp, _vp, _vp])
+_vitb_adamw = _sig("vitb_adamw", [_vp, _vp, _vp, _vp, _i64, _f, _vp, _f, _f, _f, _f, _i, _vp, _vp, _vp, _vp, _vp])
 _vitb_sumsq = _sig("vitb_sumsq", [_vp, _i64, _vp, _vp])
 _vitb_router_decide_fwd = _sig("vitb_router_decide_fwd", [_vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp])
 _vitb_router_decide_bwd = _sig("vitb_router_decide_bwd", [_vp, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _i, _i, _f, _vp, _vp])

@@ -272,9 +272,13 @@ sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict
 // carries the clip_grad_norm_ coefficient (res-vit/train.py:65) so no host sync is needed.
 __global__ void __launch_bounds__(kThreads)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-             float* __restrict__ v, long long n, float lr, float b1, float b2, float eps, float wd,
-             float bc1, float bc2, const float* __restrict__ grad_scale_dev,
-             __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+             float* __restrict__ v, long long n, float lr_host, const float* __restrict__ lr_dev, float b1, float b2,
+             float eps, float wd, int step_host, const int* __restrict__ step_dev,
+             const float* __restrict__ grad_scale_dev, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  // lr and the step counter may live on the device so that a captured CUDA graph keeps following them
+  const float lr = lr_dev ? *lr_dev : lr_host;
+  const float stepf = static_cast<float>(step_dev ? *step_dev : step_host);
+  const float bc1 = 1.f - powf(b1, stepf), bc2 = 1.f - powf(b2, stepf);
   const float gs = grad_scale_dev ? *grad_scale_dev : 1.f;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -493,16 +497,15 @@ int vitb_sgd_momentum(float* p, const float* g, float* m, int64_t n, float lr, c
   return VITB_OK;
 }
 
-int vitb_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
-               float eps, float weight_decay, int step, const float* grad_scale_dev, void* shadow_hi,
-               void* shadow_lo, void* stream_) {
+int vitb_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, const float* lr_dev, float beta1,
+               float beta2, float eps, float weight_decay, int step, const int* step_dev, const float* grad_scale_dev,
+               void* shadow_hi, void* shadow_lo, void* stream_) {
   int st = vitb_check_device();
   if (st != VITB_OK) return st;
   if (n == 0) return VITB_OK;
-  VITB_REQUIRE(p && g && m && v && n > 0 && step >= 1, VITB_ERR_BAD_ARG, "adamw: bad args");
-  const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+  VITB_REQUIRE(p && g && m && v && n > 0 && (step >= 1 || step_dev), VITB_ERR_BAD_ARG, "adamw: bad args");
   adamw_kernel<<<grid_for(n), kThreads, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
-      p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2, grad_scale_dev,
+      p, g, m, v, n, lr, lr_dev, beta1, beta2, eps, weight_decay, step, step_dev, grad_scale_dev,
       reinterpret_cast<__nv_bfloat16*>(shadow_hi), reinterpret_cast<__nv_bfloat16*>(shadow_lo));
   VITB_LAUNCH_CHECK("adamw_kernel");
   return VITB_OK;

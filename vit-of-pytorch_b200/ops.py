@@ -329,11 +329,14 @@ def sgd_momentum(p, g, m, lr, momentum, *, dampening=0.0, weight_decay=0.0, nest
                                  L.ptr(shadow_hi), L.ptr(shadow_lo), L.stream_ptr(p.device)), "vitb_sgd_momentum")
 
 
-def adamw(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, *, grad_scale=None, shadow_hi=None, shadow_lo=None):
+def adamw(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, *, grad_scale=None, shadow_hi=None, shadow_lo=None,
+          lr_dev=None, step_dev=None):
     L.require_cuda(p, g, m, v)
-    L.check(L._vitb_adamw(L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), p.numel(), float(lr), float(beta1), float(beta2),
-                          float(eps), float(weight_decay), int(step), L.ptr(grad_scale), L.ptr(shadow_hi),
-                          L.ptr(shadow_lo), L.stream_ptr(p.device)), "vitb_adamw")
+    if step_dev is not None and step_dev.dtype != torch.int32:
+        raise L.VitbError("adamw: step_dev must be an int32 device scalar")
+    L.check(L._vitb_adamw(L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), p.numel(), float(lr), L.ptr(lr_dev), float(beta1),
+                          float(beta2), float(eps), float(weight_decay), int(step), L.ptr(step_dev), L.ptr(grad_scale),
+                          L.ptr(shadow_hi), L.ptr(shadow_lo), L.stream_ptr(p.device)), "vitb_adamw")
 
 
 def sumsq(x, out):

@@ -132,12 +132,25 @@ class FusedAdamW(_FusedBase):
         self._coef = torch.ones((), dtype=torch.float32, device=dev)
         self.grad_norm = torch.zeros((), dtype=torch.float32, device=dev)  # last total norm (device scalar)
         self._steps = 0
+        # device-resident step counter and learning rates: step() can be captured in a CUDA graph
+        self._step_dev = torch.zeros((), dtype=torch.int32, device=dev)
+        self._lr_dev = [torch.full((), float(g["lr"]), dtype=torch.float32, device=dev) for g in self.param_groups]
+        self._lr_host = [float(g["lr"]) for g in self.param_groups]
+
+    def sync_lr(self):
+        for i, g in enumerate(self.param_groups):
+            if float(g["lr"]) != self._lr_host[i]:
+                self._lr_host[i] = float(g["lr"])
+                self._lr_dev[i].fill_(self._lr_host[i])
 
     @torch.no_grad()
     def step(self, closure=None):
         if closure is not None:
             raise NotImplementedError("FusedAdamW.step does not take a closure")
         self._steps += 1
+        if not torch.cuda.is_current_stream_capturing():
+            self.sync_lr()
+        self._step_dev += 1          # a device op: replays of a captured step keep counting
         coef = None
         if self.max_grad_norm is not None:  # clip_grad_norm_ over ALL groups, computed and applied on device
             self._sumsq.zero_()
@@ -146,9 +159,10 @@ class FusedAdamW(_FusedBase):
             ops.clip_coef(self._sumsq, self.max_grad_norm, self._coef, self.grad_norm)
             coef = self._coef
         want_lo = F.get_precision() == "fp32"
-        for fg, g, m, v in zip(self._flat, self.param_groups, self._m, self._v):
+        for fg, g, m, v, lr_dev in zip(self._flat, self.param_groups, self._m, self._v, self._lr_dev):
             if want_lo:
                 fg.ensure_lo()
             ops.adamw(fg.flat_p, fg.flat_g, m, v, g["lr"], g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"],
-                      self._steps, grad_scale=coef, shadow_hi=fg.flat_hi, shadow_lo=fg.flat_lo)
+                      self._steps, grad_scale=coef, shadow_hi=fg.flat_hi, shadow_lo=fg.flat_lo, lr_dev=lr_dev,
+                      step_dev=self._step_dev)
             fg.mark_fresh()

@@ -408,8 +408,8 @@ class Transformer(nn.Module):
         labels = labels.to(device) if labels.device != device else labels
         x = self._embed(x)
         self.acts, self.soft_routing_probs, self.routing_maps = [], [], {}
-        d_loss = torch.tensor(0.0, device=x.device)
-        r_entropy = torch.tensor(0.0, device=x.device)
+        d_loss = torch.zeros((), device=x.device)      # kernel fills (no host->device copy: graph-capturable)
+        r_entropy = torch.zeros((), device=x.device)
         block_info = {}
         teacher_x = student_x = x
         for layer in self.layers:
@@ -438,9 +438,9 @@ class Transformer(nn.Module):
             if len(self.soft_routing_probs) > 0:
                 a_loss = self.criterion_active(torch.cat(self.soft_routing_probs, dim=-1))
             else:
-                a_loss = torch.tensor(0.0, device=x.device)
+                a_loss = torch.zeros((), device=x.device)
             active_metric = self.criterion_active.metric(activation)
         else:
             a_loss, active_metric = None, None
-            r_entropy = torch.tensor(0.0, device=x.device)
+            r_entropy = torch.zeros((), device=x.device)
         return c_loss, a_loss, d_loss, r_entropy, active_metric

@@ -12,7 +12,10 @@ from . import functional as F
 
 
 class GraphedTrainStep:
-    def __init__(self, net, optimizer, example_images, example_labels, loss_fn=None, warmup=3):
+    def __init__(self, net, optimizer, example_images, example_labels, loss_fn=None, warmup=3, forward_loss=None):
+        """forward_loss(net, images, labels) -> scalar loss overrides the default loss_fn(net(images), labels)
+        (Res-ViT: `lambda net, x, y: sum_of(net(x, y)[:3])`, res-vit/train.py:30,51-52)."""
+        self.forward_loss = forward_loss
         if not example_images.is_cuda:
             raise RuntimeError("GraphedTrainStep needs CUDA (B200) tensors")
         self.net, self.opt = net, optimizer
@@ -36,7 +39,10 @@ class GraphedTrainStep:
 
     def _eager_step(self):
         self.opt.zero_grad()
-        loss = self.loss_fn(self.net(self.images), self.labels)
+        if self.forward_loss is not None:
+            loss = self.forward_loss(self.net, self.images, self.labels)
+        else:
+            loss = self.loss_fn(self.net(self.images), self.labels)
         loss.backward()
         self.opt.step()
         return loss
