@@ -73,8 +73,9 @@ int vitb_num_sms() {
   return g_dev_sms[dev] > 0 ? g_dev_sms[dev] : 148;
 }
 
-int vitb_make_tmap_nd_bf16(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims,
-                           const uint64_t* strides_bytes, const uint32_t* box) {
+namespace {
+int make_tmap(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+              const uint32_t* box, CUtensorMapSwizzle swizzle, uint32_t span_bytes) {
   int st = load_encode();
   if (st != VITB_OK) return st;
   VITB_REQUIRE(rank >= 1 && rank <= 5, VITB_ERR_BAD_ARG, "tensor map rank %d", rank);
@@ -96,11 +97,11 @@ int vitb_make_tmap_nd_bf16(CUtensorMap* out, const void* ptr, int rank, const ui
                  "TMA stride[%d]=%llu bytes is not a multiple of 16", i,
                  (unsigned long long)strides_bytes[i]);
   }
-  VITB_REQUIRE(box[0] * 2u <= 128u, VITB_ERR_BAD_ARG, "TMA inner box %u exceeds the 128B swizzle span",
-               box[0]);
+  VITB_REQUIRE(box[0] * 2u <= span_bytes, VITB_ERR_BAD_ARG, "TMA inner box %u exceeds the %uB swizzle span",
+               box[0], span_bytes);
   CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank,
                         const_cast<void*>(ptr), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     vitb_set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu,%llu box %u,%u)",
@@ -110,6 +111,12 @@ int vitb_make_tmap_nd_bf16(CUtensorMap* out, const void* ptr, int rank, const ui
   }
   return VITB_OK;
 }
+}  // namespace
+
+int vitb_make_tmap_nd_bf16(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims,
+                           const uint64_t* strides_bytes, const uint32_t* box) {
+  return make_tmap(out, ptr, rank, dims, strides_bytes, box, CU_TENSOR_MAP_SWIZZLE_128B, 128u);
+}
 
 int vitb_make_tmap_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer,
                            uint64_t outer_stride_bytes, uint32_t box_inner, uint32_t box_outer) {
@@ -117,6 +124,14 @@ int vitb_make_tmap_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, ui
   uint64_t str[1] = {outer_stride_bytes};
   uint32_t box[2] = {box_inner, box_outer};
   return vitb_make_tmap_nd_bf16(out, ptr, 2, dims, str, box);
+}
+
+int vitb_make_tmap_2d_bf16_sw64(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer,
+                                uint64_t outer_stride_bytes, uint32_t box_inner, uint32_t box_outer) {
+  uint64_t dims[2] = {inner, outer};
+  uint64_t str[1] = {outer_stride_bytes};
+  uint32_t box[2] = {box_inner, box_outer};
+  return make_tmap(out, ptr, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B, 64u);
 }
 
 extern "C" {

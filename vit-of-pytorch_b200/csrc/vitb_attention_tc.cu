@@ -15,9 +15,10 @@
 //   warps : O / rowsum -> bf16 -> HBM, LSE -> HBM
 // Because all keys fit one accumulator there is no online-softmax rescale pass at these sizes.
 //
-// Backward, one CTA per (image, head); loops over the query tiles, dK/dV accumulate in TMEM:
-//   S = Q K^T ; P = exp(S*c - LSE) ; dP = dO V^T ; dS = P * (dP - D) * c
-//   dV += P^T dO ; dK += dS^T Q ; dQ = dS K            (5 tcgen05 GEMMs per query tile)
+// Backward, one CTA per (image, head); every Q / dO / O tile of the head is fetched by TMA up front, the CTA
+// loops over the query tiles, dK/dV accumulate in TMEM:
+//   D = rowsum(dO * O) (from the smem tiles) ; S = Q K^T ; P = exp(S*c - LSE) ; dP = dO V^T ;
+//   dS = P * (dP - D) * c (in place over P) ; dV += P^T dO ; dK += dS^T Q ; dQ = dS K   (5 tcgen05 GEMMs per tile)
 #include "../../include/vitb200.h"
 #include <stdlib.h>
 
@@ -38,10 +39,7 @@ struct AttnTc {
   __nv_bfloat16* o;
   long long o_bs, o_rs;
   float* lse;  // [B,H,N]
-  // backward
-  const __nv_bfloat16* o_in;
-  const __nv_bfloat16* dout;
-  long long do_bs, do_rs;
+  // backward (q, k, v, o and dO arrive through tensor maps)
   __nv_bfloat16 *dq, *dk, *dv;
   long long dq_bs, dq_rs, dk_bs, dk_rs, dv_bs, dv_rs;
   long long* dbg;  // optional per-phase clock64 stamps of CTA 0 (diagnostics; NULL in production)
@@ -265,104 +263,127 @@ attn_fwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
 }
 
 // ================================================================================================
-// backward
+// backward.  TMEM columns: [0,256) S then dP then dQ ; [256,384) dK (two 128-key M tiles x 64) ; [384,512) dV.
+// Second generation of this kernel, restructured around what the first one's ncu source page showed
+// (profiles/ncu_attn_r01.txt: ~29 % of all warp samples sat on strided global loads of D_i = rowsum(dO * O),
+// 11 % on a serialised dK/dV drain, 4 % on the per-tile TMA wait; 0.277 -> 0.198 ms at the c2 shape):
+//   * every Q / dO / O tile of the head (<= 2 tiles of 128 queries) is fetched by TMA at kernel start, so
+//     tile 1 lands while tile 0 computes; O arrives as a third swizzled tile and D_i is reduced from
+//     shared memory (two threads per row, 4 x 16-byte units each, partials exchanged through smem)
+//   * dS overwrites P in place (one [128 x keys] image instead of two), which pays for the extra tiles
+//   * TMEM reads are issued two chunks per wait; the dK / dV drain keeps independent register blocks
 // ================================================================================================
-// TMEM columns: [0,256) S then dP then dQ ; [256,384) dK (two 128-key M tiles x 64) ; [384,512) dV
+__device__ __forceinline__ float dot8_bf16(const uint4& x, const uint4& y) {
+  return bf16_lo(x.x) * bf16_lo(y.x) + bf16_hi(x.x) * bf16_hi(y.x) + bf16_lo(x.y) * bf16_lo(y.y) +
+         bf16_hi(x.y) * bf16_hi(y.y) + bf16_lo(x.z) * bf16_lo(y.z) + bf16_hi(x.z) * bf16_hi(y.z) +
+         bf16_lo(x.w) * bf16_lo(y.w) + bf16_hi(x.w) * bf16_hi(y.w);
+}
+
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-            const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
-            const __grid_constant__ AttnTc a) {
+             const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
+             const __grid_constant__ CUtensorMap tmO, const __grid_constant__ AttnTc a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   const int NK = a.NK;
   const int kv_bytes = NK * 128;
   const int mtiles = (NK + 127) >> 7;        // 128-key M tiles of dK / dV
-  const int nchunks = mtiles * 2;            // P / dS images always hold whole M tiles
+  const int nchunks = mtiles * 2;            // the P / dS image always holds whole M tiles
+  const int qtiles = (a.N + 127) >> 7;       // <= 2 (N <= 256)
   uint8_t* sK = smem;
   uint8_t* sV = sK + kv_bytes;
-  uint8_t* sQ = sV + kv_bytes;
-  uint8_t* sDO = sQ + kChunkBytes;
-  uint8_t* sP = sDO + kChunkBytes;
-  uint8_t* sDS = sP + nchunks * kChunkBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sDS + nchunks * kChunkBytes);
+  uint8_t* sQ = sV + kv_bytes;               // [qtiles] tiles of 128 x 64 bf16
+  uint8_t* sDO = sQ + qtiles * kChunkBytes;
+  uint8_t* sO = sDO + qtiles * kChunkBytes;
+  uint8_t* sP = sO + qtiles * kChunkBytes;   // P, then dS in place
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + nchunks * kChunkBytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-  const uint32_t bar_kv = smem_u32(bars), bar_q = bar_kv + 8, bar_s = bar_kv + 16, bar_dp = bar_kv + 24,
-                 bar_dq = bar_kv + 32, bar_fin = bar_kv + 40;
+  float* red = reinterpret_cast<float*>(bars + 16);   // [2 halves][128 rows] partial D_i
+  const uint32_t bar_kv = smem_u32(bars), bar_q = bar_kv + 8 /* [2] */, bar_s = bar_kv + 24, bar_dp = bar_kv + 32,
+                 bar_dq = bar_kv + 40, bar_fin = bar_kv + 48;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int half = warp >> 2;
   const int h = blockIdx.x, b = blockIdx.y;
   const int r = (warp & 3) * 32 + lane;
   const ColRange cr = my_chunks(NK, half);
+  const uint32_t sP_u = smem_u32(sP);
+  const uint32_t sQ_u = smem_u32(sQ), sDO_u = smem_u32(sDO), sO_u = smem_u32(sO), sK_u = smem_u32(sK), sV_u = smem_u32(sV);
 
   if (tid == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
-    for (int i = 0; i < 6; ++i) mbar_init(bar_kv + 8 * i, 1);
+    tma_prefetch_desc(&tmO);
+    for (int i = 0; i < 7; ++i) mbar_init(bar_kv + 8 * i, 1);
     fence_barrier_init();
   }
-  if (warp == 0) { tmem_alloc(smem_u32(tmem_slot), 512); tmem_relinquish(); }
-  // zero the P / dS images once: key columns >= NK of the last M tile are never written again
-  {
-    const uint32_t base = smem_u32(sP);
-    const int total16 = 2 * nchunks * kChunkBytes / 16;
-    for (int i = tid; i < total16; i += kAttnThreads) st_shared_v4(base + i * 16, 0u, 0u, 0u, 0u);
-  }
-  fence_proxy_async_smem();
-  tc_fence_before();
   __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t trow = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-  const uint32_t sP_u = smem_u32(sP), sDS_u = smem_u32(sDS);
-  const uint32_t sQ_u = smem_u32(sQ), sDO_u = smem_u32(sDO), sK_u = smem_u32(sK), sV_u = smem_u32(sV);
-
   if (tid == 0) {
+    // every operand of this head is requested now (the loads fly while TMEM is allocated and the P image
+    // is zeroed); nothing is reloaded later
+    mbar_arrive_expect_tx(bar_q, 3 * kChunkBytes);
+    tma_load_3d(&tmQ, bar_q, sQ_u, h * DH, 0, b);
     mbar_arrive_expect_tx(bar_kv, 2 * kv_bytes);
     tma_load_3d(&tmK, bar_kv, sK_u, h * DH, 0, b);
     tma_load_3d(&tmV, bar_kv, sV_u, h * DH, 0, b);
+    tma_load_3d(&tmDO, bar_q, sDO_u, h * DH, 0, b);
+    tma_load_3d(&tmO, bar_q, sO_u, h * DH, 0, b);
+    if (qtiles > 1) {
+      mbar_arrive_expect_tx(bar_q + 8, 3 * kChunkBytes);
+      tma_load_3d(&tmQ, bar_q + 8, sQ_u + kChunkBytes, h * DH, 128, b);
+      tma_load_3d(&tmDO, bar_q + 8, sDO_u + kChunkBytes, h * DH, 128, b);
+      tma_load_3d(&tmO, bar_q + 8, sO_u + kChunkBytes, h * DH, 128, b);
+    }
   }
-  const int qtiles = (a.N + 127) >> 7;
+  if (warp == 0) { __syncwarp(); tmem_alloc(smem_u32(tmem_slot), 512); tmem_relinquish(); }
+  // zero the P / dS image once: key columns >= NK of the last M tile are never written again
+  {
+    const int total16 = nchunks * kChunkBytes / 16;
+    for (int i = tid; i < total16; i += kAttnThreads) st_shared_v4(sP_u + i * 16, 0u, 0u, 0u, 0u);
+  }
+  // LSE of this thread's row in tile 0 (tile 1's is prefetched one tile ahead)
+  const float* lse_row = a.lse + (static_cast<long long>(b) * a.H + h) * a.N;
+  float lse_next = (r < a.N) ? lse_row[r] : INFINITY;
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();       // barrier inits, TMEM address and the zeroed image are visible to everyone
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t trow = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+
   for (int qt = 0; qt < qtiles; ++qt) {
     const uint32_t ph = qt & 1;
     const int row0 = qt * 128;
     const int row = row0 + r;
+    const uint32_t sQ_t = sQ_u + qt * kChunkBytes, sDO_t = sDO_u + qt * kChunkBytes, sO_t = sO_u + qt * kChunkBytes;
+    const float lse2 = lse_next * 1.4426950408889634f;
+    if (qt + 1 < qtiles) lse_next = (row + 128 < a.N) ? lse_row[row + 128] : INFINITY;
     if (tid == 0) {
-      mbar_arrive_expect_tx(bar_q, 2 * kChunkBytes);
-      tma_load_3d(&tmQ, bar_q, sQ_u, h * DH, row0, b);
-      tma_load_3d(&tmDO, bar_q, sDO_u, h * DH, row0, b);
       if (qt == 0) mbar_wait(bar_kv, 0);
-      mbar_wait(bar_q, ph);
+      mbar_wait(bar_q + 8 * qt, 0);
       tc_fence_after();
       const uint32_t idesc = umma_idesc_bf16(128, NK, false, false);
 #pragma unroll
       for (int k = 0; k < DH / 16; ++k)  // S = Q K^T
-        umma_bf16_ss(tmem_base, umma_smem_desc_sw128(sQ_u + k * 32, 16, 1024),
+        umma_bf16_ss(tmem_base, umma_smem_desc_sw128(sQ_t + k * 32, 16, 1024),
                      umma_smem_desc_sw128(sK_u + k * 32, 16, 1024), idesc, k > 0 ? 1u : 0u);
       umma_commit(bar_s);
     }
-    // D_i = rowsum(dO * O) and LSE straight from HBM while the MMA runs (both threads of a row compute it)
-    float Di = 0.f, lse = INFINITY;
-    if (row < a.N) {
-      const uint4* po = reinterpret_cast<const uint4*>(a.o_in + b * a.o_bs + static_cast<long long>(row) * a.o_rs + h * DH);
-      const uint4* pg = reinterpret_cast<const uint4*>(a.dout + b * a.do_bs + static_cast<long long>(row) * a.do_rs + h * DH);
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const uint4 x = po[u], y = pg[u];
-        Di += bf16_lo(x.x) * bf16_lo(y.x) + bf16_hi(x.x) * bf16_hi(y.x) + bf16_lo(x.y) * bf16_lo(y.y) +
-              bf16_hi(x.y) * bf16_hi(y.y) + bf16_lo(x.z) * bf16_lo(y.z) + bf16_hi(x.z) * bf16_hi(y.z) +
-              bf16_lo(x.w) * bf16_lo(y.w) + bf16_hi(x.w) * bf16_hi(y.w);
-      }
-      lse = a.lse[(static_cast<long long>(b) * a.H + h) * a.N + row];
-    }
-    const float lse2 = lse * 1.4426950408889634f;
     __syncwarp();
+    // partial D_i = sum over this thread's 32 head-dim columns of dO * O, from the swizzled TMA tiles
+    mbar_wait(bar_q + 8 * qt, 0);
+    {
+      float part = 0.f;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t off = swz_unit(r, half * 4 + u);
+        part += dot8_bf16(ld_shared_v4(sO_t + off), ld_shared_v4(sDO_t + off));
+      }
+      red[half * 128 + r] = part;
+    }
     mbar_wait(bar_s, ph);
     tc_fence_after();
     // P = exp2(S*c - LSE*log2e) -> bf16 -> sP   (rows >= N and keys >= N give exactly 0)
-    for (int c = cr.c_begin; c < cr.c_end; ++c) {
-      const int c0 = c * 32;
-      uint32_t v[32];
-      ld_chunk(trow, c0, NK, 0u, v);
+    auto emit_p = [&](const uint32_t (&v)[32], int c0) {
       float pv[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
@@ -376,18 +397,27 @@ attn_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
           st_shared_v4(sP_u + kc * kChunkBytes + swz_unit(r, u0 + u), pack_bf16x2(pv[8 * u + 0], pv[8 * u + 1]),
                        pack_bf16x2(pv[8 * u + 2], pv[8 * u + 3]), pack_bf16x2(pv[8 * u + 4], pv[8 * u + 5]),
                        pack_bf16x2(pv[8 * u + 6], pv[8 * u + 7]));
+    };
+    for (int c = cr.c_begin; c < cr.c_end; c += 2) {
+      uint32_t v0[32], v1[32];
+      const bool two = (c + 1 < cr.c_end);
+      issue_chunk(trow, c * 32, NK, v0);
+      if (two) issue_chunk(trow, (c + 1) * 32, NK, v1);
+      tmem_ld_wait();
+      emit_p(v0, c * 32);
+      if (two) emit_p(v1, (c + 1) * 32);
     }
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
+    const float Di = red[r] + red[128 + r];
     if (tid == 0) {
       tc_fence_after();
       const uint32_t idesc_dp = umma_idesc_bf16(128, NK, false, false);
 #pragma unroll
       for (int k = 0; k < DH / 16; ++k)  // dP = dO V^T  (overwrites S)
-        umma_bf16_ss(tmem_base, umma_smem_desc_sw128(sDO_u + k * 32, 16, 1024),
+        umma_bf16_ss(tmem_base, umma_smem_desc_sw128(sDO_t + k * 32, 16, 1024),
                      umma_smem_desc_sw128(sV_u + k * 32, 16, 1024), idesc_dp, k > 0 ? 1u : 0u);
-      umma_commit(bar_dp);
       // dV[m-tile] += P^T dO : A = P^T (MN-major image of sP), B = dO (MN-major), K = 128 query rows
       const uint32_t idesc_t = umma_idesc_bf16(128, DH, true, true);
       for (int mt = 0; mt < mtiles; ++mt)
@@ -395,22 +425,20 @@ attn_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         for (int k = 0; k < 8; ++k)
           umma_bf16_ss(tmem_base + 384 + mt * 64,
                        umma_smem_desc_sw128(sP_u + mt * 2 * kChunkBytes + k * 2048, kChunkBytes, 1024),
-                       umma_smem_desc_sw128(sDO_u + k * 2048, 8192, 1024), idesc_t, (qt > 0 || k > 0) ? 1u : 0u);
+                       umma_smem_desc_sw128(sDO_t + k * 2048, 8192, 1024), idesc_t, (qt > 0 || k > 0) ? 1u : 0u);
+      umma_commit(bar_dp);   // after dV too: dS is written over P, which the dV MMAs read
     }
     __syncwarp();
     mbar_wait(bar_dp, ph);
     tc_fence_after();
-    // dS = P * (dP - D) * c  -> bf16 -> sDS
-    for (int c = cr.c_begin; c < cr.c_end; ++c) {
-      const int c0 = c * 32;
-      uint32_t v[32];
-      ld_chunk(trow, c0, NK, 0u, v);
+    // dS = P * (dP - D) * c  -> bf16, in place over P
+    auto emit_ds = [&](const uint32_t (&v)[32], int c0) {
       const int kc = c0 >> 6, u0 = (c0 & 63) >> 3, nunits = (c0 + 32 <= NK) ? 4 : 2;
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         if (u < nunits) {
-          const uint32_t off = kc * kChunkBytes + swz_unit(r, u0 + u);
-          const uint4 pp = ld_shared_v4(sP_u + off);
+          const uint32_t addr = sP_u + kc * kChunkBytes + swz_unit(r, u0 + u);
+          const uint4 pp = ld_shared_v4(addr);
           const float d0 = bf16_lo(pp.x) * (__uint_as_float(v[8 * u + 0]) - Di) * a.scale;
           const float d1 = bf16_hi(pp.x) * (__uint_as_float(v[8 * u + 1]) - Di) * a.scale;
           const float d2 = bf16_lo(pp.y) * (__uint_as_float(v[8 * u + 2]) - Di) * a.scale;
@@ -419,10 +447,18 @@ attn_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
           const float d5 = bf16_hi(pp.z) * (__uint_as_float(v[8 * u + 5]) - Di) * a.scale;
           const float d6 = bf16_lo(pp.w) * (__uint_as_float(v[8 * u + 6]) - Di) * a.scale;
           const float d7 = bf16_hi(pp.w) * (__uint_as_float(v[8 * u + 7]) - Di) * a.scale;
-          st_shared_v4(sDS_u + off, pack_bf16x2(d0, d1), pack_bf16x2(d2, d3), pack_bf16x2(d4, d5),
-                       pack_bf16x2(d6, d7));
+          st_shared_v4(addr, pack_bf16x2(d0, d1), pack_bf16x2(d2, d3), pack_bf16x2(d4, d5), pack_bf16x2(d6, d7));
         }
       }
+    };
+    for (int c = cr.c_begin; c < cr.c_end; c += 2) {
+      uint32_t v0[32], v1[32];
+      const bool two = (c + 1 < cr.c_end);
+      issue_chunk(trow, c * 32, NK, v0);
+      if (two) issue_chunk(trow, (c + 1) * 32, NK, v1);
+      tmem_ld_wait();
+      emit_ds(v0, c * 32);
+      if (two) emit_ds(v1, (c + 1) * 32);
     }
     fence_proxy_async_smem();
     tc_fence_before();
@@ -433,7 +469,7 @@ attn_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       const uint32_t idesc_dq = umma_idesc_bf16(128, DH, false, true);
       const int nks = NK >> 4;
       for (int t = 0; t < nks; ++t)
-        umma_bf16_ss(tmem_base, umma_smem_desc_sw128(sDS_u + (t >> 2) * kChunkBytes + (t & 3) * 32, 16, 1024),
+        umma_bf16_ss(tmem_base, umma_smem_desc_sw128(sP_u + (t >> 2) * kChunkBytes + (t & 3) * 32, 16, 1024),
                      umma_smem_desc_sw128(sK_u + t * 2048, 8192, 1024), idesc_dq, t > 0 ? 1u : 0u);
       umma_commit(bar_dq);
       // dK[m-tile] += dS^T Q
@@ -442,8 +478,8 @@ attn_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
 #pragma unroll
         for (int k = 0; k < 8; ++k)
           umma_bf16_ss(tmem_base + 256 + mt * 64,
-                       umma_smem_desc_sw128(sDS_u + mt * 2 * kChunkBytes + k * 2048, kChunkBytes, 1024),
-                       umma_smem_desc_sw128(sQ_u + k * 2048, 8192, 1024), idesc_t, (qt > 0 || k > 0) ? 1u : 0u);
+                       umma_smem_desc_sw128(sP_u + mt * 2 * kChunkBytes + k * 2048, kChunkBytes, 1024),
+                       umma_smem_desc_sw128(sQ_t + k * 2048, 8192, 1024), idesc_t, (qt > 0 || k > 0) ? 1u : 0u);
       umma_commit(bar_fin);
     }
     __syncwarp();
@@ -456,26 +492,25 @@ attn_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       if (row < a.N)
         st_row64_bf16(a.dq + b * a.dq_bs + static_cast<long long>(row) * a.dq_rs + h * DH + half * 32, v, 1.0f);
     }
-    // the next query tile overwrites sQ/sDO/sP/sDS and TMEM[0,256): wait until every MMA of this
-    // tile (dK included) has retired, and until all warps have drained dQ from TMEM
+    // the next query tile overwrites sP and TMEM[0,256): wait until every MMA of this tile (dK included)
+    // has retired, and until all warps have drained dQ from TMEM
     mbar_wait(bar_fin, ph);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
   }
   // dK, dV: TMEM lane = key within the M tile; the two threads of a lane split the 64 head-dim columns
-  for (int mt = 0; mt < mtiles; ++mt) {
-    const int key = mt * 128 + r;
 #pragma unroll
-    for (int which = 0; which < 2; ++which) {
-      uint32_t v[32];
-      const uint32_t col = (which == 0 ? 256u : 384u) + static_cast<uint32_t>(mt * 64 + half * 32);
-      tmem_ld_32x32b_x32(trow + col, v);
+  for (int mt = 0; mt < 2; ++mt) {
+    if (mt < mtiles) {
+      const int key = mt * 128 + r;
+      uint32_t vk[32], vv[32];
+      tmem_ld_32x32b_x32(trow + 256u + static_cast<uint32_t>(mt * 64 + half * 32), vk);
+      tmem_ld_32x32b_x32(trow + 384u + static_cast<uint32_t>(mt * 64 + half * 32), vv);
       tmem_ld_wait();
       if (key < a.N) {
-        __nv_bfloat16* base = which == 0 ? a.dk + b * a.dk_bs + static_cast<long long>(key) * a.dk_rs
-                                         : a.dv + b * a.dv_bs + static_cast<long long>(key) * a.dv_rs;
-        st_row64_bf16(base + h * DH + half * 32, v, 1.0f);
+        st_row64_bf16(a.dk + b * a.dk_bs + static_cast<long long>(key) * a.dk_rs + h * DH + half * 32, vk, 1.0f);
+        st_row64_bf16(a.dv + b * a.dv_bs + static_cast<long long>(key) * a.dv_rs + h * DH + half * 32, vv, 1.0f);
       }
     }
   }
@@ -560,18 +595,19 @@ extern "C" int vitb_attn_bwd_tc(const vitb_attn_params* p, void* stream_) {
   a.N = N; a.NK = NK; a.H = p->H;
   a.scale = 1.0f / sqrtf((float)DH);
   a.scale_log2 = a.scale * 1.4426950408889634f;
-  a.o_in = reinterpret_cast<const __nv_bfloat16*>(p->o); a.o_bs = p->o_batch_stride; a.o_rs = p->o_row_stride;
   a.lse = p->lse;
-  a.dout = reinterpret_cast<const __nv_bfloat16*>(p->dout); a.do_bs = p->do_batch_stride; a.do_rs = p->do_row_stride;
   a.dq = reinterpret_cast<__nv_bfloat16*>(p->dq); a.dq_bs = p->dq_batch_stride; a.dq_rs = p->dq_row_stride;
   a.dk = reinterpret_cast<__nv_bfloat16*>(p->dk); a.dk_bs = p->dk_batch_stride; a.dk_rs = p->dk_row_stride;
   a.dv = reinterpret_cast<__nv_bfloat16*>(p->dv); a.dv_bs = p->dv_batch_stride; a.dv_rs = p->dv_row_stride;
-  const int kv_bytes = NK * 128, mtiles = (NK + 127) / 128, nchunks = 2 * mtiles;
-  const int smem = 2 * kv_bytes + 2 * kChunkBytes + 2 * nchunks * kChunkBytes + 128 + 1024;
+  CUtensorMap to;
+  if ((st = make_head_map(&to, p->o, p->H, N, p->B, p->o_row_stride, p->o_batch_stride, 128)) != VITB_OK) return st;
+  const int kv_bytes = NK * 128, mtiles = (NK + 127) / 128, nchunks = 2 * mtiles, qtiles = (N + 127) / 128;
+  // K, V | Q, dO, O tiles of every query tile | one P/dS image | barriers + TMEM slot | D_i partials | alignment slack
+  const int smem = 2 * kv_bytes + 3 * qtiles * kChunkBytes + nchunks * kChunkBytes + 128 + 1024 + 1024;
   VITB_REQUIRE(smem <= 227 * 1024, VITB_ERR_UNSUPPORTED_SHAPE, "attn_bwd_tc: %d B of shared memory", smem);
   VITB_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   dim3 grid(p->H, p->B);
-  attn_bwd_tc<<<grid, kAttnThreads, smem, reinterpret_cast<cudaStream_t>(stream_)>>>(tq, tk, tv, tdo, a);
+  attn_bwd_tc<<<grid, kAttnThreads, smem, reinterpret_cast<cudaStream_t>(stream_)>>>(tq, tk, tv, tdo, to, a);
   VITB_LAUNCH_CHECK("attn_bwd_tc");
   return VITB_OK;
 }

@@ -142,6 +142,20 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* m, uint32_t bar, 
       : "memory");
 }
 
+// shared -> global tile store (bulk async group of the issuing thread); out-of-bounds elements are clipped
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {   // <= N groups of this thread still reading shared memory
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // ---- tcgen05 / TMEM ------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem),
@@ -302,6 +316,9 @@ __device__ __forceinline__ float warp_max(float v) {
 // 2-D bf16 tensor, inner dim contiguous, SWIZZLE_128B, zero OOB fill.
 int vitb_make_tmap_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer,
                            uint64_t outer_stride_bytes, uint32_t box_inner, uint32_t box_outer);
+// Same with SWIZZLE_64B (inner box <= 32 elements): the epilogue's TMA-store staging tiles of 32 x 32 bf16.
+int vitb_make_tmap_2d_bf16_sw64(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer,
+                                uint64_t outer_stride_bytes, uint32_t box_inner, uint32_t box_outer);
 // N-D (rank<=5) bf16 tensor, SWIZZLE_128B; strides[] has rank-1 entries (bytes) for dims 1..
 int vitb_make_tmap_nd_bf16(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims,
                            const uint64_t* strides_bytes, const uint32_t* box);

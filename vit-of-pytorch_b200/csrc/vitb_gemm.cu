@@ -69,7 +69,7 @@ struct GemmDev {
   long long ldaux;
   int vec_ok;  // 128-bit epilogue path usable (set by the host from shapes and alignment)
   float* colsum;  // optional [N]: += column sums of the values stored to D (vectorised path only)
-  int rows_bf16_ok;  // register-layout bf16 epilogue usable (N % 8 == 0, 16-byte aligned aux rows / bias)
+  int tma_store;     // bf16 outputs leave through cp.async.bulk.tensor stores (tmD / tmD2 are valid)
 };
 
 struct TileCoord {
@@ -114,6 +114,20 @@ __device__ __forceinline__ void gelu_fast(float z, float& g, float& dg) {
   g = z * cdf;
   dg = fmaf(z * 0.39894228040143267794f, e, cdf);
 }
+// Forward only, 13 instructions: the 0.5 of the cdf is folded into the polynomial and the sign into |z|:
+//   gelu(z) = 0.5 z + |z| * (0.5 erf(|z|/sqrt2)),  0.5 erf(u) = 0.5 - (0.5 poly(t) t) exp(-u^2)
+__device__ __forceinline__ float gelu_fast_fwd(float z) {
+  const float az = fabsf(z);
+  const float t = rcp_approx(fmaf(0.23164189f, az, 1.0f));          // 1 / (1 + 0.3275911 |z| / sqrt2)
+  const float w = 0.84932180f * z;                                   // sqrt(log2(e) / 2) z
+  const float e = ex2_approx(-w * w);                                // exp(-z^2 / 2)
+  float poly = fmaf(0.5307027145f, t, -0.7265760135f);
+  poly = fmaf(poly, t, 0.7107068705f);
+  poly = fmaf(poly, t, -0.142248368f);
+  poly = fmaf(poly, t, 0.127414796f);
+  const float half_erf = fmaf(-poly * t, e, 0.5f);                   // 0.5 erf(|z| / sqrt2)
+  return fmaf(az, half_erf, 0.5f * z);
+}
 __device__ __forceinline__ float ld_shared_f1(uint32_t addr) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
@@ -124,91 +138,97 @@ __device__ __forceinline__ float ld_shared_f1(uint32_t addr) {
 // 8 steps of 4 rows; every global access is a 16-byte (fp32) or 8-byte (bf16) piece of a row segment
 // that the 8 lanes of a row cover contiguously.  All side loads of the 8 steps are issued up front.
 //   RES: 0 none, 1 fp32 residual, 2 bf16 residual.   ACC: fp32 red.global accumulation.
-template <bool OUT_BF16, int EPI, int RES, bool ACC>
-__device__ __forceinline__ void epi_vec(const GemmDev& p, uint32_t stg, int lane, int row_base, int col0,
-                                        bool lead_split) {
+// FULL: all 32 rows and all 32 columns of the chunk are inside the matrix (the common case: no per-row
+// predicates, running row pointers instead of a 64-bit multiply per access).
+template <bool OUT_BF16, int EPI, int RES, bool ACC, bool FULL>
+__device__ __forceinline__ void epi_vec_body(const GemmDev& p, uint32_t stg, int lane, int row_base, int col0,
+                                             bool lead_split) {
   const int rsub = lane >> 3;
   const int c4 = (lane & 7) * 4;
   const int col = col0 + c4;
-  const bool col_ok = col < p.N;
+  const bool col_ok = FULL || col < p.N;
   float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
   if (p.bias != nullptr && lead_split && col_ok) bv = *reinterpret_cast<const float4*>(p.bias + col);
   float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);   // column sums of the stored values (bias gradients)
+  const long long r0 = static_cast<long long>(row_base + rsub);
   float4 side[8];
   if constexpr (RES != 0 || EPI == VITB_EPI_GELU_BWD) {
+    constexpr bool SIDE_BF16 = (EPI == VITB_EPI_GELU_BWD) ? OUT_BF16 : (RES == 2);
+    const long long lds = (EPI == VITB_EPI_GELU_BWD) ? p.ldaux : p.ldr;
+    const char* sp = reinterpret_cast<const char*>((EPI == VITB_EPI_GELU_BWD) ? p.aux : p.residual) +
+                     (r0 * lds + col) * (SIDE_BF16 ? 2 : 4);
+    const long long sstep = 4 * lds * (SIDE_BF16 ? 2 : 4);
+    const bool want = (EPI == VITB_EPI_GELU_BWD) || lead_split;
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
-      const int m = row_base + it * 4 + rsub;
       side[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (m < p.M && col_ok) {
-        if constexpr (EPI == VITB_EPI_GELU_BWD) {
-          if constexpr (OUT_BF16) {
-            const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.aux) +
-                                                            static_cast<long long>(m) * p.ldaux + col);
-            side[it] = make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
-          } else {
-            side[it] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.aux) +
-                                                        static_cast<long long>(m) * p.ldaux + col);
-          }
-        } else if constexpr (RES == 1) {
-          if (lead_split)
-            side[it] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.residual) +
-                                                        static_cast<long long>(m) * p.ldr + col);
+      if (want && col_ok && (FULL || row_base + it * 4 + rsub < p.M)) {
+        if constexpr (SIDE_BF16) {
+          const uint2 u = *reinterpret_cast<const uint2*>(sp);
+          side[it] = make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
         } else {
-          if (lead_split) {
-            const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) +
-                                                            static_cast<long long>(m) * p.ldr + col);
-            side[it] = make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
-          }
+          side[it] = *reinterpret_cast<const float4*>(sp);
         }
       }
+      sp += sstep;
     }
   }
+  char* dp = reinterpret_cast<char*>(p.D) + (r0 * p.ldd + col) * (OUT_BF16 ? 2 : 4);
+  const long long dstep = 4 * p.ldd * (OUT_BF16 ? 2 : 4);
+  char* d2p = nullptr;
+  long long d2step = 0;
+  if constexpr (EPI == VITB_EPI_GELU) {
+    if (p.D2 != nullptr) {
+      d2p = reinterpret_cast<char*>(p.D2) + (r0 * p.ldd2 + col) * (OUT_BF16 ? 2 : 4);
+      d2step = 4 * p.ldd2 * (OUT_BF16 ? 2 : 4);
+    }
+  }
+  uint32_t sa = stg + static_cast<uint32_t>(rsub * (kStgStride * 4) + c4 * 4);
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
-    const int rl = it * 4 + rsub;
-    const int m = row_base + rl;
-    if (m >= p.M || !col_ok) continue;
-    float4 v = ld_shared_f4(stg + rl * (kStgStride * 4) + c4 * 4);
-    v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
-    if constexpr (EPI == VITB_EPI_GELU) {
-      if (p.D2 != nullptr) {
+    if (col_ok && (FULL || row_base + it * 4 + rsub < p.M)) {
+      float4 v = ld_shared_f4(sa);
+      v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+      if constexpr (EPI == VITB_EPI_GELU) {
+        if (d2p != nullptr) {
+          if constexpr (OUT_BF16) {
+            uint2 z;
+            z.x = pack_bf16x2(v.x, v.y); z.y = pack_bf16x2(v.z, v.w);
+            *reinterpret_cast<uint2*>(d2p) = z;
+          } else {
+            *reinterpret_cast<float4*>(d2p) = v;
+          }
+        }
         if constexpr (OUT_BF16) {
-          uint2 z;
-          z.x = pack_bf16x2(v.x, v.y); z.y = pack_bf16x2(v.z, v.w);
-          *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.D2) + static_cast<long long>(m) * p.ldd2 + col) = z;
+          v.x = gelu_fast_fwd(v.x); v.y = gelu_fast_fwd(v.y); v.z = gelu_fast_fwd(v.z); v.w = gelu_fast_fwd(v.w);
         } else {
-          *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.D2) + static_cast<long long>(m) * p.ldd2 + col) = v;
+          v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
+        }
+      } else if constexpr (EPI == VITB_EPI_GELU_BWD) {
+        if constexpr (OUT_BF16) {
+          float g, d0, d1, d2, d3;
+          gelu_fast(side[it].x, g, d0); gelu_fast(side[it].y, g, d1);
+          gelu_fast(side[it].z, g, d2); gelu_fast(side[it].w, g, d3);
+          v.x *= d0; v.y *= d1; v.z *= d2; v.w *= d3;
+        } else {
+          v.x *= gelu_erf_grad(side[it].x); v.y *= gelu_erf_grad(side[it].y);
+          v.z *= gelu_erf_grad(side[it].z); v.w *= gelu_erf_grad(side[it].w);
         }
       }
+      if constexpr (RES != 0) { v.x += side[it].x; v.y += side[it].y; v.z += side[it].z; v.w += side[it].w; }
+      cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
       if constexpr (OUT_BF16) {
-        float d;
-        gelu_fast(v.x, v.x, d); gelu_fast(v.y, v.y, d); gelu_fast(v.z, v.z, d); gelu_fast(v.w, v.w, d);
+        uint2 o;
+        o.x = pack_bf16x2(v.x, v.y); o.y = pack_bf16x2(v.z, v.w);
+        *reinterpret_cast<uint2*>(dp) = o;
       } else {
-        v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
-      }
-    } else if constexpr (EPI == VITB_EPI_GELU_BWD) {
-      if constexpr (OUT_BF16) {
-        float g, d0, d1, d2, d3;
-        gelu_fast(side[it].x, g, d0); gelu_fast(side[it].y, g, d1);
-        gelu_fast(side[it].z, g, d2); gelu_fast(side[it].w, g, d3);
-        v.x *= d0; v.y *= d1; v.z *= d2; v.w *= d3;
-      } else {
-        v.x *= gelu_erf_grad(side[it].x); v.y *= gelu_erf_grad(side[it].y);
-        v.z *= gelu_erf_grad(side[it].z); v.w *= gelu_erf_grad(side[it].w);
+        if constexpr (ACC) atomicAdd(reinterpret_cast<float4*>(dp), v);
+        else *reinterpret_cast<float4*>(dp) = v;
       }
     }
-    if constexpr (RES != 0) { v.x += side[it].x; v.y += side[it].y; v.z += side[it].z; v.w += side[it].w; }
-    cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
-    if constexpr (OUT_BF16) {
-      uint2 o;
-      o.x = pack_bf16x2(v.x, v.y); o.y = pack_bf16x2(v.z, v.w);
-      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.D) + static_cast<long long>(m) * p.ldd + col) = o;
-    } else {
-      float* dst = reinterpret_cast<float*>(p.D) + static_cast<long long>(m) * p.ldd + col;
-      if constexpr (ACC) atomicAdd(reinterpret_cast<float4*>(dst), v);
-      else *reinterpret_cast<float4*>(dst) = v;
-    }
+    sa += 4 * (kStgStride * 4);
+    dp += dstep;
+    if constexpr (EPI == VITB_EPI_GELU) d2p += d2step;
   }
   if (p.colsum != nullptr) {  // warp-uniform: fold the 4 row groups (lanes l, l+8, l+16, l+24), one red per column
     cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 8);  cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 8);
@@ -219,56 +239,53 @@ __device__ __forceinline__ void epi_vec(const GemmDev& p, uint32_t stg, int lane
   }
 }
 
-__device__ __forceinline__ uint2 ld_shared_u2(uint32_t addr) {
-  uint2 v;
-  asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
-  return v;
+template <bool OUT_BF16, int EPI, int RES, bool ACC>
+__device__ __forceinline__ void epi_vec(const GemmDev& p, uint32_t stg, int lane, int row_base, int col0,
+                                        bool lead_split) {
+  if (row_base + 32 <= p.M && col0 + 32 <= p.N)   // warp-uniform
+    epi_vec_body<OUT_BF16, EPI, RES, ACC, true>(p, stg, lane, row_base, col0, lead_split);
+  else
+    epi_vec_body<OUT_BF16, EPI, RES, ACC, false>(p, stg, lane, row_base, col0, lead_split);
 }
 
-constexpr int kRowBytesBf16 = 72;   // staged bf16 row: 64 B of data + 8 B pad (conflict-free 8-byte accesses)
 
-// One thread's row of 32 values -> bf16 -> padded smem -> coalesced 8-byte pieces of 4 rows per instruction.
-__device__ __forceinline__ void stage_store_bf16(uint32_t stg, int lane, const float (&v)[32], __nv_bfloat16* out,
-                                                 long long ld, int row_base, int col0, int M, int N,
-                                                 float* colsum = nullptr) {
-#pragma unroll
-  for (int j = 0; j < 8; ++j)
-    st_shared_v2(stg + lane * kRowBytesBf16 + j * 8, pack_bf16x2(v[4 * j], v[4 * j + 1]),
-                 pack_bf16x2(v[4 * j + 2], v[4 * j + 3]));
+// ---- bf16 outputs through TMA stores -------------------------------------------------------------------
+// bf16 outputs without residual / column sums do their element-wise math in the TMEM register layout (thread =
+// row, 32 columns).  The first version of this path staged packed bf16 through padded shared memory and wrote
+// 8-byte row pieces with ld.shared + st.global; its SASS spent ~15 instructions per store on 64-bit row
+// addressing and bounds predicates (profiles/ncu_gemm_r01.txt).  Here the thread that owns a row writes its 32
+// packed values (64 B) into a 64B-swizzled 32 x 32 staging tile with four conflict-free 16-byte shared stores,
+// and one lane hands the tile to the TMA unit, which does the addressing, the coalescing and the M / N
+// clipping.  Two tiles per warp alternate, so a store is only waited for when its tile comes up for reuse two
+// stores later.  Measured (profiles/gemm_bench_r01b.txt): fc1+GELU 0.167 -> 0.132 ms, fc1+bias 0.114 -> 0.105 ms.
+constexpr int kTmaTileBytes = 32 * 64;
+
+__device__ __forceinline__ void tma_store_rows_bf16(const CUtensorMap* tm, uint32_t tbuf, int& which, int lane,
+                                                    const float (&v)[32], int row_base, int col0) {
+  const uint32_t buf = tbuf + static_cast<uint32_t>(which) * kTmaTileBytes;
+  which ^= 1;
+  if (lane == 0) bulk_wait_read<1>();     // the store that last read this tile (two stores ago) has drained
   __syncwarp();
-  const int rsub = lane >> 3;
-  const int col = col0 + (lane & 7) * 4;
-  float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (col < N) {
-    __nv_bfloat16* base = out + static_cast<long long>(row_base + rsub) * ld + col;
+  const uint32_t rowaddr = buf + static_cast<uint32_t>(lane) * 64u;
+  const uint32_t x = (static_cast<uint32_t>(lane) >> 1) & 3u;   // SWIZZLE_64B: 16-byte unit ^= address bits [7,9)
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int rl = it * 4 + rsub;
-      if (row_base + rl < M) {
-        const uint2 o = ld_shared_u2(stg + rl * kRowBytesBf16 + (lane & 7) * 8);
-        *reinterpret_cast<uint2*>(base + static_cast<long long>(it * 4) * ld) = o;
-        if (colsum != nullptr) { cs.x += bf16_lo(o.x); cs.y += bf16_hi(o.x); cs.z += bf16_lo(o.y); cs.w += bf16_hi(o.y); }
-      }
-    }
-  }
-  if (colsum != nullptr) {   // warp-uniform: column sums of the stored (bf16-rounded) values
-    cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 8);  cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 8);
-    cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 8);  cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 8);
-    cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 16); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 16);
-    cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 16); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 16);
-    if (lane < 8 && col < N) atomicAdd(reinterpret_cast<float4*>(colsum + col), cs);
-  }
+  for (int j = 0; j < 4; ++j)
+    st_shared_v4(rowaddr + ((static_cast<uint32_t>(j) ^ x) << 4), pack_bf16x2(v[8 * j], v[8 * j + 1]),
+                 pack_bf16x2(v[8 * j + 2], v[8 * j + 3]), pack_bf16x2(v[8 * j + 4], v[8 * j + 5]),
+                 pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+  fence_proxy_async_smem();               // generic-proxy writes -> visible to the async proxy (TMA)
   __syncwarp();
+  if (lane == 0) {
+    tma_store_2d(tm, buf, col0, row_base);
+    bulk_commit();
+  }
 }
 
-// bf16-output epilogue with the element-wise math done in the TMEM register layout (thread = row, 32 columns):
-// bias arrives through uniform 16-byte loads, GELU' reads this row's 64 bytes of pre-activations, and only the
-// packed bf16 results go through shared memory.  ~40 % fewer instructions per element than staging fp32 first.
-// Requires N % 8 == 0 (checked on the host: rows_bf16_ok).
+// One 32-row x 32-column chunk of a bf16 output: bias / GELU in the TMEM register layout, then TMA stores.
 template <int EPI>
-__device__ __forceinline__ void epi_rows_bf16(const GemmDev& p, uint32_t stg, int lane, int row_base, int col0,
-                                              const uint32_t (&r)[32]) {
-  const int m = row_base + lane;
+__device__ __forceinline__ void epi_rows_bf16_tma(const GemmDev& p, const CUtensorMap* tmD, const CUtensorMap* tmD2,
+                                                  uint32_t tbuf, int& which, int lane, int row_base, int col0,
+                                                  const uint32_t (&r)[32]) {
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
@@ -281,37 +298,12 @@ __device__ __forceinline__ void epi_rows_bf16(const GemmDev& p, uint32_t stg, in
       }
     }
   }
-  if constexpr (EPI == VITB_EPI_GELU_BWD) {
-    if (m < p.M) {
-      const uint4* zrow = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.aux) +
-                                                         static_cast<long long>(m) * p.ldaux + col0);
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (col0 + 8 * u < p.N) {
-          const uint4 z = zrow[u];
-          float g, d;
-          gelu_fast(bf16_lo(z.x), g, d); v[8 * u + 0] *= d;
-          gelu_fast(bf16_hi(z.x), g, d); v[8 * u + 1] *= d;
-          gelu_fast(bf16_lo(z.y), g, d); v[8 * u + 2] *= d;
-          gelu_fast(bf16_hi(z.y), g, d); v[8 * u + 3] *= d;
-          gelu_fast(bf16_lo(z.z), g, d); v[8 * u + 4] *= d;
-          gelu_fast(bf16_hi(z.z), g, d); v[8 * u + 5] *= d;
-          gelu_fast(bf16_lo(z.w), g, d); v[8 * u + 6] *= d;
-          gelu_fast(bf16_hi(z.w), g, d); v[8 * u + 7] *= d;
-        }
-      }
-    }
-  }
   if constexpr (EPI == VITB_EPI_GELU) {
-    if (p.D2 != nullptr)
-      stage_store_bf16(stg, lane, v, reinterpret_cast<__nv_bfloat16*>(p.D2), p.ldd2, row_base, col0, p.M, p.N);
+    if (p.D2 != nullptr) tma_store_rows_bf16(tmD2, tbuf, which, lane, v, row_base, col0);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      float d;
-      gelu_fast(v[j], v[j], d);
-    }
+    for (int j = 0; j < 32; ++j) v[j] = gelu_fast_fwd(v[j]);
   }
-  stage_store_bf16(stg, lane, v, reinterpret_cast<__nv_bfloat16*>(p.D), p.ldd, row_base, col0, p.M, p.N, p.colsum);
+  tma_store_rows_bf16(tmD, tbuf, which, lane, v, row_base, col0);
 }
 
 // Scalar epilogue with every option (row bias, patch-embedding row remap, odd widths): lane == column.
@@ -362,6 +354,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
                  const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+                 const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmD2,
                  const __grid_constant__ GemmDev p) {
   using C = Cfg<BN>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -495,7 +488,10 @@ vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
     // measured (profiles/gemm_bench_r01.txt): the register-layout epilogue wins for plain / bias / GELU outputs,
     // but GELU' is faster with coalesced pre-activation loads in the staged layout
-    const bool rows_path = p.rows_bf16_ok && (mode == 2 || mode == 4);
+    const bool tma_path = p.tma_store != 0 && (mode == 2 || mode == 4);
+    const uint32_t tbuf = (stg + 511u) & ~511u;   // two 2 KiB 64B-swizzled tiles inside this warp's staging slice
+    int tma_which = 0;
+    if (tma_path && lane == 0) { tma_prefetch_desc(&tmD); if (p.D2 != nullptr) tma_prefetch_desc(&tmD2); }
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile);
       const int n0 = t.n_blk * BN;
@@ -513,9 +509,9 @@ vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                                static_cast<uint32_t>(acc * BN + c * 32), r);
         tmem_ld_wait();
-        if (rows_path) {   // bf16 outputs without residual: math in registers, only packed bf16 is staged
-          if (mode == 2) epi_rows_bf16<VITB_EPI_GELU>(p, stg, lane, row_base, col0, r);
-          else epi_rows_bf16<VITB_EPI_NONE>(p, stg, lane, row_base, col0, r);
+        if (tma_path) {    // bf16 outputs without residual / column sums: math in registers, tiles leave by TMA
+          if (mode == 2) epi_rows_bf16_tma<VITB_EPI_GELU>(p, &tmD, &tmD2, tbuf, tma_which, lane, row_base, col0, r);
+          else epi_rows_bf16_tma<VITB_EPI_NONE>(p, &tmD, &tmD2, tbuf, tma_which, lane, row_base, col0, r);
           continue;
         }
 #pragma unroll
@@ -543,6 +539,7 @@ vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
+    if (tma_path && lane == 0) bulk_wait_all();   // staging tiles must outlive the stores that read them
   }
 
   tc_fence_before();
@@ -558,7 +555,7 @@ int launch(const CUtensorMap* tm, const GemmDev& d, int grid, cudaStream_t strea
   auto kern = vitb_gemm_kernel<BN, A_MN, B_MN>;
   VITB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg<BN>::SMEM_BYTES));
-  kern<<<grid, kThreads, Cfg<BN>::SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], d);
+  kern<<<grid, kThreads, Cfg<BN>::SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], tm[6], tm[7], d);
   VITB_LAUNCH_CHECK("vitb_gemm_kernel");
   return VITB_OK;
 }
@@ -652,13 +649,11 @@ extern "C" int vitb_gemm(const vitb_gemm_params* p, void* stream_) {
                !(p->accumulate && (p->residual != nullptr || p->epilogue != VITB_EPI_NONE)) &&
                !(p->epilogue != VITB_EPI_NONE && p->residual != nullptr);
     d.colsum = p->colsum;
-    d.rows_bf16_ok = d.vec_ok && d.d_bf16 && (p->N % 8 == 0) && (p->aux == nullptr || (p->ldaux % 8 == 0 && al(p->aux, 16))) &&
-                     (getenv("VITB_GEMM_OLD_EPILOGUE") == nullptr);
     VITB_REQUIRE(p->colsum == nullptr || (d.vec_ok && al(p->colsum, 16) && !p->accumulate), VITB_ERR_UNSUPPORTED_SHAPE,
                  "vitb_gemm: colsum needs the vectorised epilogue (N, lds multiples of 4, 16-byte aligned pointers)");
   }
 
-  CUtensorMap tm[6];
+  CUtensorMap tm[8];
   for (int s = 0; s < 3; ++s) {
     const int src = s < p->num_segments ? s : 0;
     const uint64_t K = (uint64_t)p->K[src];
@@ -672,6 +667,22 @@ extern "C" int vitb_gemm(const vitb_gemm_params* p, void* stream_) {
     else
       st = vitb_make_tmap_2d_bf16(&tm[2 * s + 1], p->B[src], (uint64_t)p->N, K, (uint64_t)p->ldb[src] * 2, 64, BK);
     if (st != VITB_OK) return st;
+  }
+  // bf16 outputs of the register-layout epilogue leave through TMA stores (32 x 32 tiles, SWIZZLE_64B);
+  // anything that does not meet TMA's 16-byte rules takes the staged epi_vec path
+  d.tma_store = 0;
+  tm[6] = tm[0];
+  tm[7] = tm[0];
+  if (d.vec_ok && d.d_bf16 && p->N % 8 == 0 && p->colsum == nullptr && p->residual == nullptr && !p->accumulate &&
+      p->epilogue != VITB_EPI_GELU_BWD && p->ldd % 8 == 0 && (reinterpret_cast<uintptr_t>(p->D) & 15u) == 0 &&
+      (p->D2 == nullptr || (p->ldd2 % 8 == 0 && (reinterpret_cast<uintptr_t>(p->D2) & 15u) == 0))) {
+    st = vitb_make_tmap_2d_bf16_sw64(&tm[6], p->D, (uint64_t)p->N, (uint64_t)p->M, (uint64_t)p->ldd * 2, 32, 32);
+    if (st != VITB_OK) return st;
+    if (p->D2 != nullptr) {
+      st = vitb_make_tmap_2d_bf16_sw64(&tm[7], p->D2, (uint64_t)p->N, (uint64_t)p->M, (uint64_t)p->ldd2 * 2, 32, 32);
+      if (st != VITB_OK) return st;
+    }
+    d.tma_store = 1;
   }
   const long long total_tiles = (long long)d.m_tiles * d.n_tiles * d.split_k;
   const int grid = (int)(total_tiles < sms ? total_tiles : sms);
