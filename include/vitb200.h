@@ -57,13 +57,16 @@ int vitb_struct_size(int which);
  *   b_mn_major = 1: B_seg is stored [K,N] (N contiguous)  — LinearGeneral layout / dgrad / wgrad
  * Epilogue, in this order:  v = acc ; v += bias[n] ; v += row_bias[m / row_bias_group, n] ;
  *   (GELU: optionally store v to d2 (pre-activation), v = gelu_erf(v)) ;
- *   (GELU_BWD: v *= gelu_erf'(aux[m,n])) ; v += residual[rm, n] ; D[om, n] (+)= v ; colsum[n] += v
+ *   (GELU_DG: store gelu_erf'(v) to d2, v = gelu_erf(v)) ; (GELU_BWD: v *= gelu_erf'(aux[m,n])) ;
+ *   (MUL_AUX: v *= aux[m,n]) ; v += residual[rm, n] ; D[om, n] (+)= v ; colsum[n] += v
  * where for row_remap_group = g > 0 (patch-embedding scatter):  om = m + m/g + 1, rm = m%g + 1,
  * otherwise om = rm = m.
  */
 #define VITB_EPI_NONE 0
 #define VITB_EPI_GELU 1
 #define VITB_EPI_GELU_BWD 2
+#define VITB_EPI_GELU_DG 3  /* like GELU, but d2 receives gelu_erf'(v): the backward then only multiplies */
+#define VITB_EPI_MUL_AUX 4  /* v *= aux[m,n]  (aux = the d2 of a VITB_EPI_GELU_DG forward) */
 
 typedef struct vitb_gemm_params {
   int32_t struct_bytes; /* sizeof(vitb_gemm_params) — ABI guard */
@@ -82,7 +85,7 @@ typedef struct vitb_gemm_params {
   int64_t ldd;
   int32_t d_dtype;
   int32_t accumulate; /* 1: D += v via fp32 atomics (wgrad / split-K) */
-  void* D2; /* optional pre-activation output for VITB_EPI_GELU, same dtype as D */
+  void* D2; /* pre-activation (VITB_EPI_GELU, optional) or derivative (VITB_EPI_GELU_DG) output, same dtype as D */
   int64_t ldd2;
   const float* bias; /* [N] or NULL */
   const float* row_bias; /* [ceil(M/row_bias_group), N] or NULL */
@@ -92,7 +95,7 @@ typedef struct vitb_gemm_params {
   int64_t ldr;
   int32_t r_dtype;
   int32_t _pad0;
-  const void* aux; /* [M,N] pre-activation for VITB_EPI_GELU_BWD, same dtype as D */
+  const void* aux; /* [M,N] pre-activation (VITB_EPI_GELU_BWD) or derivative (VITB_EPI_MUL_AUX), same dtype as D */
   int64_t ldaux;
   float* colsum; /* optional [N]: += column sums of the values written to D (bias gradient of the producer) */
 } vitb_gemm_params;

@@ -170,3 +170,52 @@ def test_gemm_gelu_bwd_with_colsum_bf16():
     torch.nn.functional.gelu(zf).backward(ref)
     assert rel_l2(out, zf.grad) < 4e-3
     assert rel_l2(cs, zf.grad.sum(0) + 1.0) < 4e-3
+
+
+@pytest.mark.parametrize("M,N", [(777, 3072), (300, 200)])
+def test_gemm_gelu_dg_then_mul_aux_equals_gelu_backward(M, N):
+    """bf16 MLP as the fused block runs it: the forward epilogue stores gelu'(z) (VITB_EPI_GELU_DG), the fc2
+    dgrad epilogue multiplies by it (VITB_EPI_MUL_AUX) and accumulates the fc1 bias gradient."""
+    import vitb200
+    K = 768
+    A, B, _ = _operands(M, N, K, False, False, seed=71)
+    A = (A.float() * 0.05).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda") * 0.1
+    zr = (A.float() @ B.float().t() + bias).requires_grad_(True)
+    dg = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device="cuda")
+    out = vitb200.ops.gemm(A, B, bias=bias, epilogue=vitb200.ops.EPI_GELU_DG, d2=dg)
+    torch.cuda.synchronize()
+    g = torch.nn.functional.gelu(zr)
+    g.backward(torch.ones_like(g))
+    assert rel_l2(out, g.detach()) < 4e-3
+    assert rel_l2(dg, zr.grad) < 4e-3            # gelu'(z) itself, rounded to bf16
+    # backward: dz = (dy W2) * dg, column sums -> bias gradient
+    Kb = 256
+    dy, W2, ref = _operands(M, N, Kb, False, True, seed=72)
+    cs = torch.ones(N, device="cuda")
+    dz = vitb200.ops.gemm(dy, W2, b_mn=True, epilogue=vitb200.ops.EPI_MUL_AUX, aux=dg, colsum=cs if N % 4 == 0 else None)
+    torch.cuda.synchronize()
+    want = ref * dg.float()
+    assert rel_l2(dz, want) < 4e-3
+    if N % 4 == 0:
+        assert rel_l2(cs, want.sum(0) + 1.0) < 4e-3
+
+
+def test_gemm_bf16_tma_store_respects_row_and_column_tails_and_strided_outputs():
+    """bf16 outputs leave through 32x32 TMA-store tiles: rows >= M / columns >= N are clipped by the tensor map,
+    and a column slice of a wider buffer (the packed q|k|v projection output) keeps its neighbours intact."""
+    import vitb200
+    M, N, K = 1000, 768, 768
+    A, B, ref = _operands(M, N, K, False, False, seed=81)
+    bias = torch.randn(N, device="cuda")
+    big = torch.full((M + 8, 3 * N), 7.0, dtype=torch.bfloat16, device="cuda")
+    vitb200.ops.gemm(A, B, bias=bias, out=big[:M, N:2 * N])
+    torch.cuda.synchronize()
+    assert rel_l2(big[:M, N:2 * N], ref + bias) < 4e-3
+    assert bool((big[:M, :N] == 7.0).all()) and bool((big[:M, 2 * N:] == 7.0).all()) and bool((big[M:] == 7.0).all())
+    M2, N2, K2 = 300, 200, 128                      # BN = 128 tiles, 200 = 6 full 32-column chunks + 8 columns
+    A, B, ref = _operands(M2, N2, K2, False, False, seed=82)
+    out = torch.full((M2 + 4, N2), 7.0, dtype=torch.bfloat16, device="cuda")
+    vitb200.ops.gemm(A, B, out=out[:M2])
+    torch.cuda.synchronize()
+    assert rel_l2(out[:M2], ref) < 4e-3 and bool((out[M2:] == 7.0).all())

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvitb200.so")
 
 F32, BF16 = 0, 1
-EPI_NONE, EPI_GELU, EPI_GELU_BWD = 0, 1, 2
+EPI_NONE, EPI_GELU, EPI_GELU_BWD, EPI_GELU_DG, EPI_MUL_AUX = 0, 1, 2, 3, 4
 
 
 class VitbError(RuntimeError):

@@ -2,6 +2,7 @@
 // TMA descriptor encoding.  See include/vitb200.h.
 #include <mutex>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/vitb200.h"
@@ -64,6 +65,11 @@ int vitb_check_device() {
   g_dev_ok[dev] = 1;
   g_dev_sms[dev] = sms;
   return VITB_OK;
+}
+
+bool vitb_pdl_enabled() {
+  const char* e = getenv("VITB_PDL");
+  return e != nullptr && atoi(e) != 0;
 }
 
 int vitb_num_sms() {

@@ -42,7 +42,6 @@ struct AttnTc {
   // backward (q, k, v, o and dO arrive through tensor maps)
   __nv_bfloat16 *dq, *dk, *dv;
   long long dq_bs, dq_rs, dk_bs, dk_rs, dv_bs, dv_rs;
-  long long* dbg;  // optional per-phase clock64 stamps of CTA 0 (diagnostics; NULL in production)
 };
 
 // byte offset of the 16-byte unit holding keys [8u, 8u+8) of row r inside one 128B-swizzled chunk
@@ -65,7 +64,6 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
 // row, each handling half of the key columns; row max / row sum are exchanged through shared memory.
 // ================================================================================================
 constexpr int kAttnThreads = 256;
-#define VITB_STAMP(i) do { if (a.dbg != nullptr && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) a.dbg[i] = clock64(); } while (0)
 
 struct ColRange { int c_begin, c_end; };   // in units of 32-column chunks (the last chunk may hold 16)
 __device__ __forceinline__ ColRange my_chunks(int NK, int half) {
@@ -149,7 +147,7 @@ attn_fwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int half = warp >> 2;
   const int row0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
-  VITB_STAMP(0);
+  pdl_trigger();
 
   if (tid == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
@@ -161,7 +159,7 @@ attn_fwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  VITB_STAMP(1);
+  pdl_wait();   // first global access (the TMA loads) comes after the previous grid has completed
 
   if (tid == 0) {
     mbar_arrive_expect_tx(bar_qk, kChunkBytes + kv_bytes);
@@ -170,7 +168,6 @@ attn_fwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     mbar_arrive_expect_tx(bar_v, kv_bytes);
     tma_load_3d(&tmV, bar_v, smem_u32(sV), h * DH, 0, b);
     mbar_wait(bar_qk, 0);
-    VITB_STAMP(2);
     tc_fence_after();
     const uint32_t idesc = umma_idesc_bf16(128, NK, false, false);
 #pragma unroll
@@ -182,7 +179,6 @@ attn_fwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   __syncwarp();
   mbar_wait(bar_s, 0);
   tc_fence_after();
-  VITB_STAMP(3);
 
   const int r = (warp & 3) * 32 + lane;  // query row within the tile == TMEM lane
   const uint32_t trow = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
@@ -200,7 +196,6 @@ attn_fwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   }
   red[half * 128 + r] = mx;
   __syncthreads();
-  VITB_STAMP(4);
   mx = fmaxf(red[r], red[128 + r]);
   // pass 2: p = exp2((s - max) * c), row sum, bf16 P into the swizzled A-operand image
   float sum = 0.f;
@@ -211,11 +206,19 @@ attn_fwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     uint32_t v[32];
     ld_chunk(trow, c0, NK, 0u, v);
     float pv[32];
+    if (c0 + 32 <= a.N) {   // interior chunk: every column is a valid key
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float e = ex2_approx(fmaf(__uint_as_float(v[j]), a.scale_log2, -mxs));
-      pv[j] = (c0 + j < a.N) ? e : 0.f;
-      sum += pv[j];
+      for (int j = 0; j < 32; ++j) {
+        pv[j] = ex2_approx(fmaf(__uint_as_float(v[j]), a.scale_log2, -mxs));
+        sum += pv[j];
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float e = ex2_approx(fmaf(__uint_as_float(v[j]), a.scale_log2, -mxs));
+        pv[j] = (c0 + j < a.N) ? e : 0.f;
+        sum += pv[j];
+      }
     }
     const int kc = c0 >> 6, u0 = (c0 & 63) >> 3, nunits = (c0 + 32 <= NK) ? 4 : 2;
 #pragma unroll
@@ -231,7 +234,6 @@ attn_fwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   tc_fence_before();
   __syncthreads();
   sum = red[256 + r] + red[256 + 128 + r];
-  VITB_STAMP(5);
   if (tid == 0) {
     tc_fence_after();
     mbar_wait(bar_v, 0);
@@ -245,7 +247,6 @@ attn_fwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   __syncwarp();
   mbar_wait(bar_o, 0);
   tc_fence_after();
-  VITB_STAMP(6);
   const int row = row0 + r;
   {
     uint32_t v[32];
@@ -258,7 +259,6 @@ attn_fwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   }
   tc_fence_before();
   __syncthreads();
-  VITB_STAMP(7);
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
 }
 
@@ -302,6 +302,7 @@ attn_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   const uint32_t bar_kv = smem_u32(bars), bar_q = bar_kv + 8 /* [2] */, bar_s = bar_kv + 24, bar_dp = bar_kv + 32,
                  bar_dq = bar_kv + 40, bar_fin = bar_kv + 48;
 
+  pdl_trigger();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int half = warp >> 2;
   const int h = blockIdx.x, b = blockIdx.y;
@@ -317,6 +318,7 @@ attn_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     fence_barrier_init();
   }
   __syncthreads();
+  pdl_wait();   // first global access (the TMA loads, the LSE reads) comes after the previous grid has completed
   if (tid == 0) {
     // every operand of this head is requested now (the loads fly while TMEM is allocated and the P image
     // is zeroed); nothing is reloaded later
@@ -384,11 +386,16 @@ attn_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     tc_fence_after();
     // P = exp2(S*c - LSE*log2e) -> bf16 -> sP   (rows >= N and keys >= N give exactly 0)
     auto emit_p = [&](const uint32_t (&v)[32], int c0) {
-      float pv[32];
+      float pv[32];   // rows >= N carry LSE = +inf, so exp2(-inf) zeroes them without a row predicate
+      if (c0 + 32 <= a.N) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float e = ex2_approx(fmaf(__uint_as_float(v[j]), a.scale_log2, -lse2));
-        pv[j] = (c0 + j < a.N && row < a.N) ? e : 0.f;
+        for (int j = 0; j < 32; ++j) pv[j] = ex2_approx(fmaf(__uint_as_float(v[j]), a.scale_log2, -lse2));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float e = ex2_approx(fmaf(__uint_as_float(v[j]), a.scale_log2, -lse2));
+          pv[j] = (c0 + j < a.N) ? e : 0.f;
+        }
       }
       const int kc = c0 >> 6, u0 = (c0 & 63) >> 3, nunits = (c0 + 32 <= NK) ? 4 : 2;
 #pragma unroll
@@ -431,7 +438,7 @@ attn_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     __syncwarp();
     mbar_wait(bar_dp, ph);
     tc_fence_after();
-    // dS = P * (dP - D) * c  -> bf16, in place over P
+    // dS / c = P * (dP - D)  -> bf16, in place over P  (the softmax scale c is applied when dQ / dK are drained)
     auto emit_ds = [&](const uint32_t (&v)[32], int c0) {
       const int kc = c0 >> 6, u0 = (c0 & 63) >> 3, nunits = (c0 + 32 <= NK) ? 4 : 2;
 #pragma unroll
@@ -439,14 +446,14 @@ attn_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         if (u < nunits) {
           const uint32_t addr = sP_u + kc * kChunkBytes + swz_unit(r, u0 + u);
           const uint4 pp = ld_shared_v4(addr);
-          const float d0 = bf16_lo(pp.x) * (__uint_as_float(v[8 * u + 0]) - Di) * a.scale;
-          const float d1 = bf16_hi(pp.x) * (__uint_as_float(v[8 * u + 1]) - Di) * a.scale;
-          const float d2 = bf16_lo(pp.y) * (__uint_as_float(v[8 * u + 2]) - Di) * a.scale;
-          const float d3 = bf16_hi(pp.y) * (__uint_as_float(v[8 * u + 3]) - Di) * a.scale;
-          const float d4 = bf16_lo(pp.z) * (__uint_as_float(v[8 * u + 4]) - Di) * a.scale;
-          const float d5 = bf16_hi(pp.z) * (__uint_as_float(v[8 * u + 5]) - Di) * a.scale;
-          const float d6 = bf16_lo(pp.w) * (__uint_as_float(v[8 * u + 6]) - Di) * a.scale;
-          const float d7 = bf16_hi(pp.w) * (__uint_as_float(v[8 * u + 7]) - Di) * a.scale;
+          const float d0 = bf16_lo(pp.x) * (__uint_as_float(v[8 * u + 0]) - Di);
+          const float d1 = bf16_hi(pp.x) * (__uint_as_float(v[8 * u + 1]) - Di);
+          const float d2 = bf16_lo(pp.y) * (__uint_as_float(v[8 * u + 2]) - Di);
+          const float d3 = bf16_hi(pp.y) * (__uint_as_float(v[8 * u + 3]) - Di);
+          const float d4 = bf16_lo(pp.z) * (__uint_as_float(v[8 * u + 4]) - Di);
+          const float d5 = bf16_hi(pp.z) * (__uint_as_float(v[8 * u + 5]) - Di);
+          const float d6 = bf16_lo(pp.w) * (__uint_as_float(v[8 * u + 6]) - Di);
+          const float d7 = bf16_hi(pp.w) * (__uint_as_float(v[8 * u + 7]) - Di);
           st_shared_v4(addr, pack_bf16x2(d0, d1), pack_bf16x2(d2, d3), pack_bf16x2(d4, d5), pack_bf16x2(d6, d7));
         }
       }
@@ -490,7 +497,7 @@ attn_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       tmem_ld_32x32b_x32(trow + half * 32, v);
       tmem_ld_wait();
       if (row < a.N)
-        st_row64_bf16(a.dq + b * a.dq_bs + static_cast<long long>(row) * a.dq_rs + h * DH + half * 32, v, 1.0f);
+        st_row64_bf16(a.dq + b * a.dq_bs + static_cast<long long>(row) * a.dq_rs + h * DH + half * 32, v, a.scale);
     }
     // the next query tile overwrites sP and TMEM[0,256): wait until every MMA of this tile (dK included)
     // has retired, and until all warps have drained dQ from TMEM
@@ -509,7 +516,7 @@ attn_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       tmem_ld_32x32b_x32(trow + 384u + static_cast<uint32_t>(mt * 64 + half * 32), vv);
       tmem_ld_wait();
       if (key < a.N) {
-        st_row64_bf16(a.dk + b * a.dk_bs + static_cast<long long>(key) * a.dk_rs + h * DH + half * 32, vk, 1.0f);
+        st_row64_bf16(a.dk + b * a.dk_bs + static_cast<long long>(key) * a.dk_rs + h * DH + half * 32, vk, a.scale);
         st_row64_bf16(a.dv + b * a.dv_bs + static_cast<long long>(key) * a.dv_rs + h * DH + half * 32, vv, 1.0f);
       }
     }
@@ -561,16 +568,13 @@ extern "C" int vitb_attn_fwd_tc(const vitb_attn_params* p, void* stream_) {
   a.scale_log2 = a.scale * 1.4426950408889634f;
   a.o = reinterpret_cast<__nv_bfloat16*>(p->o); a.o_bs = p->o_batch_stride; a.o_rs = p->o_row_stride;
   a.lse = p->lse;
-  {
-    const char* e = getenv("VITB_ATTN_DBG");   // diagnostics: device pointer (decimal) for phase time stamps
-    a.dbg = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 10)) : nullptr;
-  }
   const int kv_bytes = NK * 128, nchunks = (NK + 63) / 64;
   const int u_bytes = (kChunkBytes + kv_bytes) > nchunks * kChunkBytes ? (kChunkBytes + kv_bytes) : nchunks * kChunkBytes;
   const int smem = kv_bytes + u_bytes + 64 + 4 * 128 * 4 + 1024;
   VITB_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   dim3 grid((N + 127) / 128, p->H, p->B);
-  attn_fwd_tc<<<grid, kAttnThreads, smem, reinterpret_cast<cudaStream_t>(stream_)>>>(tq, tk, tv, a);
+  VITB_CUDA_CHECK(vitb_launch(attn_fwd_tc, grid, dim3(kAttnThreads), smem, reinterpret_cast<cudaStream_t>(stream_), tq, tk,
+                              tv, a));
   VITB_LAUNCH_CHECK("attn_fwd_tc");
   return VITB_OK;
 }
@@ -607,7 +611,8 @@ extern "C" int vitb_attn_bwd_tc(const vitb_attn_params* p, void* stream_) {
   VITB_REQUIRE(smem <= 227 * 1024, VITB_ERR_UNSUPPORTED_SHAPE, "attn_bwd_tc: %d B of shared memory", smem);
   VITB_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   dim3 grid(p->H, p->B);
-  attn_bwd_tc<<<grid, kAttnThreads, smem, reinterpret_cast<cudaStream_t>(stream_)>>>(tq, tk, tv, tdo, to, a);
+  VITB_CUDA_CHECK(vitb_launch(attn_bwd_tc, grid, dim3(kAttnThreads), smem, reinterpret_cast<cudaStream_t>(stream_), tq, tk,
+                              tv, tdo, to, a));
   VITB_LAUNCH_CHECK("attn_bwd_tc");
   return VITB_OK;
 }

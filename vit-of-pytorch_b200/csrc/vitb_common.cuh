@@ -55,6 +55,30 @@ void vitb_set_error(const char* fmt, ...);  // defined in vitb_api.cu (thread-sa
 int vitb_check_device();   // defined in vitb_api.cu; caches per device
 int vitb_num_sms();        // SM count of the current device
 
+// Programmatic dependent launch: the heavy kernels of a step (GEMM, attention, LayerNorm, column sums) are
+// launched with cudaLaunchAttributeProgrammaticStreamSerialization.  Each of them executes
+// griddepcontrol.launch_dependents on entry and griddepcontrol.wait after its prologue (barrier init, TMEM
+// allocation, descriptor prefetch) and BEFORE its first global-memory access, so the next kernel's CTAs are
+// scheduled and set up while the previous grid drains, yet never touch memory before it has completed and
+// flushed.  Kernels launched without the attribute (torch's, the small element-wise ones) serialise as usual.
+bool vitb_pdl_enabled();   // vitb_api.cu: environment switch VITB_PDL (round-1 validation)
+
+template <typename... Exp, typename... Act>
+inline cudaError_t vitb_launch(void (*kernel)(Exp...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                               Act&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = vitb_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<Act&&>(args)...);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Device helpers
 // ---------------------------------------------------------------------------------------------
@@ -65,6 +89,10 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+
+// ---- programmatic dependent launch (see vitb_launch) --------------------------------------------
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ---- mbarrier ---------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {

@@ -70,6 +70,8 @@ struct GemmDev {
   int vec_ok;  // 128-bit epilogue path usable (set by the host from shapes and alignment)
   float* colsum;  // optional [N]: += column sums of the values stored to D (vectorised path only)
   int tma_store;     // bf16 outputs leave through cp.async.bulk.tensor stores (tmD / tmD2 are valid)
+  int d2_grad;       // VITB_EPI_GELU_DG: D2 receives gelu'(v) instead of v
+  int aux_grad;      // VITB_EPI_MUL_AUX: aux already holds gelu'(z); the epilogue only multiplies
 };
 
 struct TileCoord {
@@ -127,6 +129,21 @@ __device__ __forceinline__ float gelu_fast_fwd(float z) {
   poly = fmaf(poly, t, 0.127414796f);
   const float half_erf = fmaf(-poly * t, e, 0.5f);                   // 0.5 erf(|z| / sqrt2)
   return fmaf(az, half_erf, 0.5f * z);
+}
+// Forward value and derivative together (17 instructions): used when the forward stores gelu'(z) for the
+// backward (VITB_EPI_GELU_DG) instead of the pre-activation z.
+__device__ __forceinline__ void gelu_fast_both(float z, float& g, float& dg) {
+  const float az = fabsf(z);
+  const float t = rcp_approx(fmaf(0.23164189f, az, 1.0f));
+  const float w = 0.84932180f * z;
+  const float e = ex2_approx(-w * w);                                // exp(-z^2 / 2)
+  float poly = fmaf(0.5307027145f, t, -0.7265760135f);
+  poly = fmaf(poly, t, 0.7107068705f);
+  poly = fmaf(poly, t, -0.142248368f);
+  poly = fmaf(poly, t, 0.127414796f);
+  const float half_erf = fmaf(-poly * t, e, 0.5f);                   // 0.5 erf(|z| / sqrt2)
+  g = fmaf(az, half_erf, 0.5f * z);
+  dg = fmaf(z * 0.39894228040143267794f, e, 0.5f + copysignf(half_erf, z));   // Phi(z) + z phi(z)
 }
 __device__ __forceinline__ float ld_shared_f1(uint32_t addr) {
   float v;
@@ -190,22 +207,31 @@ __device__ __forceinline__ void epi_vec_body(const GemmDev& p, uint32_t stg, int
       float4 v = ld_shared_f4(sa);
       v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
       if constexpr (EPI == VITB_EPI_GELU) {
+        float4 s2 = v;   // what D2 receives: the pre-activation, or gelu'(pre-activation)
+        if constexpr (OUT_BF16) {
+          if (p.d2_grad) {
+            gelu_fast_both(v.x, v.x, s2.x); gelu_fast_both(v.y, v.y, s2.y);
+            gelu_fast_both(v.z, v.z, s2.z); gelu_fast_both(v.w, v.w, s2.w);
+          } else {
+            v.x = gelu_fast_fwd(v.x); v.y = gelu_fast_fwd(v.y); v.z = gelu_fast_fwd(v.z); v.w = gelu_fast_fwd(v.w);
+          }
+        } else {
+          if (p.d2_grad) s2 = make_float4(gelu_erf_grad(v.x), gelu_erf_grad(v.y), gelu_erf_grad(v.z), gelu_erf_grad(v.w));
+          v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
+        }
         if (d2p != nullptr) {
           if constexpr (OUT_BF16) {
             uint2 z;
-            z.x = pack_bf16x2(v.x, v.y); z.y = pack_bf16x2(v.z, v.w);
+            z.x = pack_bf16x2(s2.x, s2.y); z.y = pack_bf16x2(s2.z, s2.w);
             *reinterpret_cast<uint2*>(d2p) = z;
           } else {
-            *reinterpret_cast<float4*>(d2p) = v;
+            *reinterpret_cast<float4*>(d2p) = s2;
           }
         }
-        if constexpr (OUT_BF16) {
-          v.x = gelu_fast_fwd(v.x); v.y = gelu_fast_fwd(v.y); v.z = gelu_fast_fwd(v.z); v.w = gelu_fast_fwd(v.w);
-        } else {
-          v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
-        }
       } else if constexpr (EPI == VITB_EPI_GELU_BWD) {
-        if constexpr (OUT_BF16) {
+        if (p.aux_grad) {
+          v.x *= side[it].x; v.y *= side[it].y; v.z *= side[it].z; v.w *= side[it].w;
+        } else if constexpr (OUT_BF16) {
           float g, d0, d1, d2, d3;
           gelu_fast(side[it].x, g, d0); gelu_fast(side[it].y, g, d1);
           gelu_fast(side[it].z, g, d2); gelu_fast(side[it].w, g, d3);
@@ -260,25 +286,37 @@ __device__ __forceinline__ void epi_vec(const GemmDev& p, uint32_t stg, int lane
 // stores later.  Measured (profiles/gemm_bench_r01b.txt): fc1+GELU 0.167 -> 0.132 ms, fc1+bias 0.114 -> 0.105 ms.
 constexpr int kTmaTileBytes = 32 * 64;
 
-__device__ __forceinline__ void tma_store_rows_bf16(const CUtensorMap* tm, uint32_t tbuf, int& which, int lane,
-                                                    const float (&v)[32], int row_base, int col0) {
+// acquire the next staging tile of this warp: the store that last read it (two stores ago) has drained
+__device__ __forceinline__ uint32_t tma_tile_acquire(uint32_t tbuf, int& which, int lane) {
   const uint32_t buf = tbuf + static_cast<uint32_t>(which) * kTmaTileBytes;
   which ^= 1;
-  if (lane == 0) bulk_wait_read<1>();     // the store that last read this tile (two stores ago) has drained
+  if (lane == 0) bulk_wait_read<1>();
   __syncwarp();
-  const uint32_t rowaddr = buf + static_cast<uint32_t>(lane) * 64u;
+  return buf;
+}
+// this thread's row: 16-byte unit j (columns 8j .. 8j+7) of the 64B-swizzled tile
+__device__ __forceinline__ void tma_tile_write_unit(uint32_t buf, int lane, int j, float a0, float a1, float a2, float a3,
+                                                    float a4, float a5, float a6, float a7) {
   const uint32_t x = (static_cast<uint32_t>(lane) >> 1) & 3u;   // SWIZZLE_64B: 16-byte unit ^= address bits [7,9)
-#pragma unroll
-  for (int j = 0; j < 4; ++j)
-    st_shared_v4(rowaddr + ((static_cast<uint32_t>(j) ^ x) << 4), pack_bf16x2(v[8 * j], v[8 * j + 1]),
-                 pack_bf16x2(v[8 * j + 2], v[8 * j + 3]), pack_bf16x2(v[8 * j + 4], v[8 * j + 5]),
-                 pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+  st_shared_v4(buf + static_cast<uint32_t>(lane) * 64u + ((static_cast<uint32_t>(j) ^ x) << 4), pack_bf16x2(a0, a1),
+               pack_bf16x2(a2, a3), pack_bf16x2(a4, a5), pack_bf16x2(a6, a7));
+}
+__device__ __forceinline__ void tma_tile_release(const CUtensorMap* tm, uint32_t buf, int lane, int row_base, int col0) {
   fence_proxy_async_smem();               // generic-proxy writes -> visible to the async proxy (TMA)
   __syncwarp();
   if (lane == 0) {
     tma_store_2d(tm, buf, col0, row_base);
     bulk_commit();
   }
+}
+__device__ __forceinline__ void tma_store_rows_bf16(const CUtensorMap* tm, uint32_t tbuf, int& which, int lane,
+                                                    const float (&v)[32], int row_base, int col0) {
+  const uint32_t buf = tma_tile_acquire(tbuf, which, lane);
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    tma_tile_write_unit(buf, lane, j, v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3], v[8 * j + 4], v[8 * j + 5],
+                        v[8 * j + 6], v[8 * j + 7]);
+  tma_tile_release(tm, buf, lane, row_base, col0);
 }
 
 // One 32-row x 32-column chunk of a bf16 output: bias / GELU in the TMEM register layout, then TMA stores.
@@ -299,9 +337,22 @@ __device__ __forceinline__ void epi_rows_bf16_tma(const GemmDev& p, const CUtens
     }
   }
   if constexpr (EPI == VITB_EPI_GELU) {
-    if (p.D2 != nullptr) tma_store_rows_bf16(tmD2, tbuf, which, lane, v, row_base, col0);
+    if (p.D2 != nullptr && p.d2_grad) {
+      // D2 = gelu'(v), D = gelu(v): the derivative goes to its tile 8 columns at a time while v becomes gelu(v)
+      const uint32_t buf = tma_tile_acquire(tbuf, which, lane);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = gelu_fast_fwd(v[j]);
+      for (int j = 0; j < 4; ++j) {
+        float d[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) gelu_fast_both(v[8 * j + i], v[8 * j + i], d[i]);
+        tma_tile_write_unit(buf, lane, j, d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7]);
+      }
+      tma_tile_release(tmD2, buf, lane, row_base, col0);
+    } else {
+      if (p.D2 != nullptr) tma_store_rows_bf16(tmD2, tbuf, which, lane, v, row_base, col0);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = gelu_fast_fwd(v[j]);
+    }
   }
   tma_store_rows_bf16(tmD, tbuf, which, lane, v, row_base, col0);
 }
@@ -320,14 +371,16 @@ __device__ __noinline__ void epi_generic(const GemmDev& p, uint32_t stg, int lan
       v += p.row_bias[static_cast<long long>(m / p.row_bias_group) * p.N + col];
     if (p.epilogue == VITB_EPI_GELU) {
       if (p.D2 != nullptr) {
-        if (p.d_bf16) reinterpret_cast<__nv_bfloat16*>(p.D2)[static_cast<long long>(m) * p.ldd2 + col] = __float2bfloat16(v);
-        else reinterpret_cast<float*>(p.D2)[static_cast<long long>(m) * p.ldd2 + col] = v;
+        const float s2 = p.d2_grad ? gelu_erf_grad(v) : v;
+        if (p.d_bf16) reinterpret_cast<__nv_bfloat16*>(p.D2)[static_cast<long long>(m) * p.ldd2 + col] = __float2bfloat16(s2);
+        else reinterpret_cast<float*>(p.D2)[static_cast<long long>(m) * p.ldd2 + col] = s2;
       }
       v = gelu_erf(v);
     } else if (p.epilogue == VITB_EPI_GELU_BWD) {
       const long long ai = static_cast<long long>(m) * p.ldaux + col;
-      v *= gelu_erf_grad(p.d_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.aux)[ai])
-                                  : reinterpret_cast<const float*>(p.aux)[ai]);
+      const float ax = p.d_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.aux)[ai])
+                                : reinterpret_cast<const float*>(p.aux)[ai];
+      v *= p.aux_grad ? ax : gelu_erf_grad(ax);
     }
     int om = m, rm = m;
     if (p.row_remap_group > 0) {
@@ -357,6 +410,7 @@ vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                  const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmD2,
                  const __grid_constant__ GemmDev p) {
   using C = Cfg<BN>;
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem) & 1023u) != 0) {  // SWIZZLE_128B tiles need 1024-byte aligned stage bases
@@ -400,6 +454,7 @@ vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // nothing above touches global memory; everything below may
 
   const int total_tiles = p.m_tiles * p.n_tiles * p.split_k;
 
@@ -555,7 +610,8 @@ int launch(const CUtensorMap* tm, const GemmDev& d, int grid, cudaStream_t strea
   auto kern = vitb_gemm_kernel<BN, A_MN, B_MN>;
   VITB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg<BN>::SMEM_BYTES));
-  kern<<<grid, kThreads, Cfg<BN>::SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], tm[6], tm[7], d);
+  VITB_CUDA_CHECK(vitb_launch(kern, dim3(grid), dim3(kThreads), Cfg<BN>::SMEM_BYTES, stream, tm[0], tm[1], tm[2], tm[3],
+                              tm[4], tm[5], tm[6], tm[7], d));
   VITB_LAUNCH_CHECK("vitb_gemm_kernel");
   return VITB_OK;
 }
@@ -580,9 +636,10 @@ extern "C" int vitb_gemm(const vitb_gemm_params* p, void* stream_) {
                "vitb_gemm: accumulate needs an fp32 D");
   VITB_REQUIRE(!(p->split_k > 1 && !p->accumulate), VITB_ERR_BAD_ARG,
                "vitb_gemm: split_k > 1 needs accumulate = 1");
-  VITB_REQUIRE(p->epilogue >= 0 && p->epilogue <= 2, VITB_ERR_BAD_ARG, "vitb_gemm: epilogue %d", p->epilogue);
-  VITB_REQUIRE(!(p->epilogue == VITB_EPI_GELU_BWD && p->aux == nullptr), VITB_ERR_BAD_ARG,
-               "vitb_gemm: GELU_BWD needs aux");
+  VITB_REQUIRE(p->epilogue >= 0 && p->epilogue <= 4, VITB_ERR_BAD_ARG, "vitb_gemm: epilogue %d", p->epilogue);
+  VITB_REQUIRE(!((p->epilogue == VITB_EPI_GELU_BWD || p->epilogue == VITB_EPI_MUL_AUX) && p->aux == nullptr),
+               VITB_ERR_BAD_ARG, "vitb_gemm: GELU_BWD / MUL_AUX need aux");
+  VITB_REQUIRE(!(p->epilogue == VITB_EPI_GELU_DG && p->D2 == nullptr), VITB_ERR_BAD_ARG, "vitb_gemm: GELU_DG needs D2");
   VITB_REQUIRE(!(p->accumulate && p->epilogue != VITB_EPI_NONE && p->split_k != 1), VITB_ERR_BAD_ARG,
                "vitb_gemm: a non-linear epilogue cannot be split along K");
   VITB_REQUIRE(p->row_bias == nullptr || p->row_bias_group > 0, VITB_ERR_BAD_ARG,
@@ -622,7 +679,10 @@ extern "C" int vitb_gemm(const vitb_gemm_params* p, void* stream_) {
   VITB_REQUIRE(split <= d.total_kblocks, VITB_ERR_BAD_ARG, "vitb_gemm: split_k %d > k-blocks %d", split,
                d.total_kblocks);
   d.split_k = split;
-  d.epilogue = p->epilogue;
+  // the two "derivative carried by the forward" flavours reuse the GELU / GELU_BWD code paths
+  d.d2_grad = p->epilogue == VITB_EPI_GELU_DG;
+  d.aux_grad = p->epilogue == VITB_EPI_MUL_AUX;
+  d.epilogue = d.d2_grad ? VITB_EPI_GELU : (d.aux_grad ? VITB_EPI_GELU_BWD : p->epilogue);
   d.D = p->D;
   d.ldd = p->ldd;
   d.d_bf16 = p->d_dtype == VITB_BF16;
@@ -646,8 +706,8 @@ extern "C" int vitb_gemm(const vitb_gemm_params* p, void* stream_) {
                (p->residual == nullptr || (p->ldr % 4 == 0 && al(p->residual, d.r_bf16 ? 8 : 16))) &&
                (p->D2 == nullptr || (p->ldd2 % 4 == 0 && al(p->D2, d_al))) &&
                (p->aux == nullptr || (p->ldaux % 4 == 0 && al(p->aux, d_al))) &&
-               !(p->accumulate && (p->residual != nullptr || p->epilogue != VITB_EPI_NONE)) &&
-               !(p->epilogue != VITB_EPI_NONE && p->residual != nullptr);
+               !(p->accumulate && (p->residual != nullptr || d.epilogue != VITB_EPI_NONE)) &&
+               !(d.epilogue != VITB_EPI_NONE && p->residual != nullptr);
     d.colsum = p->colsum;
     VITB_REQUIRE(p->colsum == nullptr || (d.vec_ok && al(p->colsum, 16) && !p->accumulate), VITB_ERR_UNSUPPORTED_SHAPE,
                  "vitb_gemm: colsum needs the vectorised epilogue (N, lds multiples of 4, 16-byte aligned pointers)");
@@ -674,7 +734,7 @@ extern "C" int vitb_gemm(const vitb_gemm_params* p, void* stream_) {
   tm[6] = tm[0];
   tm[7] = tm[0];
   if (d.vec_ok && d.d_bf16 && p->N % 8 == 0 && p->colsum == nullptr && p->residual == nullptr && !p->accumulate &&
-      p->epilogue != VITB_EPI_GELU_BWD && p->ldd % 8 == 0 && (reinterpret_cast<uintptr_t>(p->D) & 15u) == 0 &&
+      d.epilogue != VITB_EPI_GELU_BWD && p->ldd % 8 == 0 && (reinterpret_cast<uintptr_t>(p->D) & 15u) == 0 &&
       (p->D2 == nullptr || (p->ldd2 % 8 == 0 && (reinterpret_cast<uintptr_t>(p->D2) & 15u) == 0))) {
     st = vitb_make_tmap_2d_bf16_sw64(&tm[6], p->D, (uint64_t)p->N, (uint64_t)p->M, (uint64_t)p->ldd * 2, 32, 32);
     if (st != VITB_OK) return st;

@@ -38,6 +38,8 @@ ln_fwd_kernel(const void* __restrict__ x_, long long x_stride, int rows, const f
               __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo,
               float* __restrict__ mean_out, float* __restrict__ rstd_out) {
   constexpr int D = NV * 128;
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int gw = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   const int nw = gridDim.x * kWarpsPerBlock;
@@ -96,8 +98,10 @@ ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, long lo
               float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dcolsum) {
   constexpr int D = NV * 128;
   extern __shared__ float s_acc[];  // [3][D] block-level accumulators
+  pdl_trigger();
   for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) s_acc[i] = 0.f;
   __syncthreads();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int gw = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   const int nw = gridDim.x * kWarpsPerBlock;
@@ -207,13 +211,15 @@ extern "C" int vitb_layernorm_fwd(const void* x, int x_dtype, int64_t x_row_stri
   const int nv = D / 128;
   __nv_bfloat16* yh = reinterpret_cast<__nv_bfloat16*>(y_bf16);
   __nv_bfloat16* yl = reinterpret_cast<__nv_bfloat16*>(y_bf16_lo);
+  cudaError_t lerr = cudaSuccess;
   if (x_dtype == VITB_BF16) {
-    VITB_NV_SWITCH(nv, (ln_fwd_kernel<NV, true><<<grid, kWarpsPerBlock * 32, 0, stream>>>(
-                           x, x_row_stride, rows, gamma, beta, eps, y_f32, yh, yl, mean, rstd)));
+    VITB_NV_SWITCH(nv, (lerr = vitb_launch(ln_fwd_kernel<NV, true>, dim3(grid), dim3(kWarpsPerBlock * 32), 0, stream,
+                                           x, x_row_stride, rows, gamma, beta, eps, y_f32, yh, yl, mean, rstd)));
   } else {
-    VITB_NV_SWITCH(nv, (ln_fwd_kernel<NV, false><<<grid, kWarpsPerBlock * 32, 0, stream>>>(
-                           x, x_row_stride, rows, gamma, beta, eps, y_f32, yh, yl, mean, rstd)));
+    VITB_NV_SWITCH(nv, (lerr = vitb_launch(ln_fwd_kernel<NV, false>, dim3(grid), dim3(kWarpsPerBlock * 32), 0, stream,
+                                           x, x_row_stride, rows, gamma, beta, eps, y_f32, yh, yl, mean, rstd)));
   }
+  VITB_CUDA_CHECK(lerr);
   VITB_LAUNCH_CHECK("ln_fwd_kernel");
   return VITB_OK;
 }
@@ -240,15 +246,17 @@ extern "C" int vitb_layernorm_bwd(const void* dy, int dy_dtype, const float* x, 
   __nv_bfloat16* dh = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
   __nv_bfloat16* dl = reinterpret_cast<__nv_bfloat16*>(dx_bf16_lo);
 #define VITB_LNB(DYB, CS)                                                                        \
-  VITB_NV_SWITCH(nv, (ln_bwd_kernel<NV, DYB, CS><<<grid, kWarpsPerBlock * 32, smem, stream>>>(   \
-                         dy, x, x_row_stride, mean, rstd, gamma, rows, dres, dres_row_stride,    \
-                         dx_f32, dx_row_stride, dh, dl, dgamma, dbeta, dcolsum)))
+  VITB_NV_SWITCH(nv, (lerr = vitb_launch(ln_bwd_kernel<NV, DYB, CS>, dim3(grid), dim3(kWarpsPerBlock * 32), smem,  \
+                                         stream, dy, x, x_row_stride, mean, rstd, gamma, rows, dres,              \
+                                         dres_row_stride, dx_f32, dx_row_stride, dh, dl, dgamma, dbeta, dcolsum)))
+  cudaError_t lerr = cudaSuccess;
   if (dy_dtype == VITB_BF16) {
     if (dcolsum) { VITB_LNB(true, true); } else { VITB_LNB(true, false); }
   } else {
     if (dcolsum) { VITB_LNB(false, true); } else { VITB_LNB(false, false); }
   }
 #undef VITB_LNB
+  VITB_CUDA_CHECK(lerr);
   VITB_LAUNCH_CHECK("ln_bwd_kernel");
   return VITB_OK;
 }

@@ -332,7 +332,11 @@ class _Mlp(torch.autograd.Function):
         h = torch.empty((rows, Mh), dtype=adt, device=x.device)
         z = torch.empty((rows, Mh), dtype=adt, device=x.device)
         A, B = _pairs(xo, _weight_operand(w1, (Mh, D)))
-        ops.gemm(A, B, out=h, bias=b1.detach() if b1 is not None else None, epilogue=ops.EPI_GELU, d2=z)
+        # bf16 activations: the forward epilogue stores gelu'(z) in place of z (it has exp(-z^2/2) and the cdf at
+        # hand anyway), so the fc2 dgrad epilogue is a plain multiply instead of 17 instructions per element
+        ctx.z_is_grad = adt == BF16
+        ops.gemm(A, B, out=h, bias=b1.detach() if b1 is not None else None,
+                 epilogue=ops.EPI_GELU_DG if ctx.z_is_grad else ops.EPI_GELU, d2=z)
         ho = _operand(h)
         A, B = _pairs(ho, _weight_operand(w2, (Do, Mh)))
         res2 = _as2d(residual, Do) if residual is not None else None
@@ -356,7 +360,8 @@ class _Mlp(torch.autograd.Function):
         dyo = _operand(dy2)
         # dz = (dy W2) * gelu'(z)
         A, B = _pairs(dyo, _weight_operand(w2, (Do, Mh)))
-        dz = ops.gemm(A, B, b_mn=True, out_dtype=ctx.z.dtype, epilogue=ops.EPI_GELU_BWD, aux=ctx.z)
+        dz = ops.gemm(A, B, b_mn=True, out_dtype=ctx.z.dtype,
+                      epilogue=ops.EPI_MUL_AUX if ctx.z_is_grad else ops.EPI_GELU_BWD, aux=ctx.z)
         dzo = _operand(dz)
         dw2 = _wgrad(dyo, ctx.ho, w2, (Do, Mh), True) if w2.requires_grad else None
         db2 = _bias_grad(dy2, b2) if (b2 is not None and b2.requires_grad) else None
@@ -741,7 +746,8 @@ class _EncoderBlockFused(torch.autograd.Function):
         _, hn, _, mean2, rstd2 = ops.layernorm_fwd(h, n2w.detach(), n2b.detach(), eps2)
         a = torch.empty((T, Mh), dtype=BF16, device=dev)
         z = torch.empty((T, Mh), dtype=BF16, device=dev)
-        ops.gemm(hn, SHADOW.get(w1, False)[0], out=a, bias=b1.detach(), epilogue=ops.EPI_GELU, d2=z)
+        # z holds gelu'(fc1 pre-activation), not the pre-activation itself (VITB_EPI_GELU_DG / VITB_EPI_MUL_AUX)
+        ops.gemm(hn, SHADOW.get(w1, False)[0], out=a, bias=b1.detach(), epilogue=ops.EPI_GELU_DG, d2=z)
         y = torch.empty((T, D), dtype=F32, device=dev)
         ops.gemm(a, SHADOW.get(w2, False)[0], out=y, bias=b2.detach(), residual=h)
         ctx.save_for_backward(x2, xn, mean1, rstd1, qkv, o, lse, h, hn, mean2, rstd2, z, a)
@@ -780,7 +786,7 @@ class _EncoderBlockFused(torch.autograd.Function):
         acc_b1, r = _acc(b1)
         ret(b1, r)
         dz = torch.empty((T, Mh), dtype=BF16, device=dev)
-        ops.gemm(dyb, SHADOW.get(w2, False)[0], b_mn=True, out=dz, epilogue=ops.EPI_GELU_BWD, aux=z, colsum=acc_b1)
+        ops.gemm(dyb, SHADOW.get(w2, False)[0], b_mn=True, out=dz, epilogue=ops.EPI_MUL_AUX, aux=z, colsum=acc_b1)
         acc, r = _acc(w2)
         ret(w2, r)
         ops.gemm(dyb, a, a_mn=True, b_mn=True, out=acc, accumulate=True)

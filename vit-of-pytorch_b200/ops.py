@@ -8,7 +8,7 @@ import ctypes as C
 import torch
 
 from . import _lib as L
-from ._lib import EPI_GELU, EPI_GELU_BWD, EPI_NONE  # noqa: F401
+from ._lib import EPI_GELU, EPI_GELU_BWD, EPI_GELU_DG, EPI_MUL_AUX, EPI_NONE  # noqa: F401
 
 
 # When set to a list, every gemm() call appends (start_event, end_event, flops): bench.py uses it to time
