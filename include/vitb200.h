@@ -155,7 +155,8 @@ typedef struct vitb_attn_params {
   int64_t dv_batch_stride, dv_row_stride;
 } vitb_attn_params;
 
-int vitb_attn_supported_tc(int head_dim, int Nq, int Nk);
+int vitb_attn_supported_tc(int head_dim, int Nq, int Nk);      /* forward AND backward on tcgen05 (head_dim 64, <= 256 tokens) */
+int vitb_attn_fwd_supported_tc(int head_dim, int Nq, int Nk);  /* forward only: also 64 < head_dim <= 128, <= 320 tokens (ViT-H/14) */
 int vitb_attn_fwd_tc(const vitb_attn_params* p, void* stream);
 int vitb_attn_bwd_tc(const vitb_attn_params* p, void* stream);
 int vitb_attn_fwd_simt(const vitb_attn_params* p, void* stream);

@@ -104,6 +104,35 @@ def test_attn_tc_fwd_bwd_packed_qkv(N):
     assert rel_l2(dk, kf.grad) < 1.5e-2
 
 
+@pytest.mark.parametrize("dh,N,H,simt", [(80, 257, 16, True), (128, 130, 3, True), (96, 300, 2, False),
+                                         (80, 50, 4, True), (112, 256, 2, False)])
+def test_attn_tc_wide_heads_forward(dh, N, H, simt):
+    """tcgen05 forward for 64 < head_dim <= 128 (ViT-H/14: head_dim 80, 257 tokens, i.e. two MMAs per S row
+    block and a partially used second head-dim chunk); the backward of these shapes stays on the SIMT kernel."""
+    import vitb200
+    B = 2
+    D = H * dh
+    qkv = _randn((B, N, 3 * D), 300 + N + dh, 1.0, torch.bfloat16)
+    q, k, v = qkv[:, :, :D], qkv[:, :, D:2 * D], qkv[:, :, 2 * D:]
+    assert vitb200.ops.attn_fwd_supported_tc(dh, N, N, torch.bfloat16)
+    assert not vitb200.ops.attn_supported_tc(dh, N, N, torch.bfloat16)
+    o, lse = vitb200.ops.attn_fwd(q, k, v, H)
+    ro, rlse = _attn_ref(q, k, v, H)
+    torch.cuda.synchronize()
+    assert rel_l2(o, ro) < 1e-2
+    assert rel_l2(lse, rlse) < 1e-4
+    if not simt:      # larger than the CUDA-core kernel's shared-memory budget: forward only
+        return
+    o_s, lse_s = vitb200.ops.attn_fwd(q, k, v, H, use_tc=False)
+    assert rel_l2(o, o_s) < 1e-2 and rel_l2(lse, lse_s) < 1e-4
+    # the SIMT backward consumes this forward's o / lse
+    do = _randn((B, N, D), 7, 1.0, torch.bfloat16)
+    qf, kf, vf = (t.float().detach().requires_grad_(True) for t in (q, k, v))
+    _attn_ref(qf, kf, vf, H)[0].backward(do.float())
+    dq, dk, dv = vitb200.ops.attn_bwd(do, q, k, v, o, lse, H)
+    assert rel_l2(dq, qf.grad) < 4e-2 and rel_l2(dk, kf.grad) < 4e-2 and rel_l2(dv, vf.grad) < 4e-2
+
+
 def test_attn_tc_c2_size_runs_and_matches_on_a_slice():
     import vitb200
     B, N, H, dh = 128, 197, 12, 64

@@ -73,7 +73,7 @@ if "c4" in which:
     img = torch.randn(B, 3, 224, 224, device="cuda")
     with torch.no_grad():
         ms = timed(lambda: m(img), 5, 2)
-    log("c4 ViT-H/14 inference bs256 (N=257, head_dim 80 -> CUDA-core attention): %.2f ms/batch, %.0f img/s, %.0f TFLOP/s (334.588 GFLOP/img)"
+    log("c4 ViT-H/14 inference bs256 (N=257, head_dim 80, tcgen05 wide-head attention): %.2f ms/batch, %.0f img/s, %.0f TFLOP/s (334.588 GFLOP/img)"
         % (ms, B / ms * 1e3, B / ms * 334.588))
     del m
     torch.cuda.empty_cache()

@@ -156,6 +156,7 @@ _vitb_layernorm_fwd = _sig("vitb_layernorm_fwd", [_vp, _i, _i64, _i, _i, _vp, _v
 _vitb_layernorm_bwd = _sig("vitb_layernorm_bwd", [_vp, _i, _vp, _i64, _vp, _vp, _vp, _i, _i, _vp, _i64, _vp, _i64,
                                                    _vp, _vp, _vp, _vp, _vp, _vp])
 vitb_attn_supported_tc = _sig("vitb_attn_supported_tc", [_i, _i, _i])
+vitb_attn_fwd_supported_tc = _sig("vitb_attn_fwd_supported_tc", [_i, _i, _i])
 _vitb_attn_fwd_tc = _sig("vitb_attn_fwd_tc", [C.POINTER(AttnParams), _vp])
 _vitb_attn_bwd_tc = _sig("vitb_attn_bwd_tc", [C.POINTER(AttnParams), _vp])
 _vitb_attn_fwd_simt = _sig("vitb_attn_fwd_simt", [C.POINTER(AttnParams), _vp])
@@ -180,7 +181,7 @@ _vitb_clip_coef = _sig("vitb_clip_coef", [_vp, _f, _vp, _vp, _vp])
 
 EXPORTED_SYMBOLS = [
     "vitb_version", "vitb_last_error", "vitb_device_check", "vitb_struct_size", "vitb_gemm", "vitb_layernorm_fwd",
-    "vitb_layernorm_bwd", "vitb_attn_supported_tc", "vitb_attn_fwd_tc", "vitb_attn_bwd_tc",
+    "vitb_layernorm_bwd", "vitb_attn_supported_tc", "vitb_attn_fwd_supported_tc", "vitb_attn_fwd_tc", "vitb_attn_bwd_tc",
     "vitb_attn_fwd_simt", "vitb_attn_bwd_simt", "vitb_cast_split", "vitb_im2col", "vitb_cls_rows",
     "vitb_embed_bwd", "vitb_colsum", "vitb_cross_entropy", "vitb_sgd_momentum", "vitb_adamw",
     "vitb_sumsq", "vitb_clip_coef", "vitb_gelu_bwd", "vitb_router_decide_fwd", "vitb_router_decide_bwd",

@@ -166,7 +166,13 @@ def _head_strides(t, H, dh, what):
 
 
 def attn_supported_tc(dh, Nq, Nk, dtype):
+    """tcgen05 forward AND backward (head_dim 64, <= 256 tokens)."""
     return dtype == torch.bfloat16 and bool(L.vitb_attn_supported_tc(dh, Nq, Nk))
+
+
+def attn_fwd_supported_tc(dh, Nq, Nk, dtype):
+    """tcgen05 forward: the above plus wide heads (64 < head_dim <= 128, <= 320 tokens: ViT-H/14)."""
+    return dtype == torch.bfloat16 and bool(L.vitb_attn_fwd_supported_tc(dh, Nq, Nk))
 
 
 def _attn_params(q, k, v, o, lse, H):
@@ -191,7 +197,7 @@ def attn_fwd(q, k, v, H, *, use_tc=None):
     B, Nq, HD = q.shape
     dh = HD // H
     if use_tc is None:
-        use_tc = attn_supported_tc(dh, Nq, k.shape[1], q.dtype)
+        use_tc = attn_fwd_supported_tc(dh, Nq, k.shape[1], q.dtype)
     o = torch.empty((B, Nq, HD), dtype=q.dtype, device=q.device)
     lse = torch.empty((B, H, Nq), dtype=torch.float32, device=q.device)
     p = _attn_params(q, k, v, o, lse, H)
