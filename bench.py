@@ -34,6 +34,8 @@ CLASSES = 100
 BATCH_PER_GPU = 128
 GFLOP_PER_IMG_TRAIN = 105.379   # 3 x 35.126 GFLOP (dense contractions only)
 CPU_SAMPLE_BATCH = 8
+LR, TRAIN_STEPS, WARMUP_STEPS = 0.03, 15000, 500   # src/config.py:39-42 defaults
+WORKLOAD = "ViT-B/16 224px train step (fwd+bwd+SGD momentum 0.9, OneCycleLR), batch %d/GPU, C=100"
 
 
 def peaks():
@@ -125,12 +127,24 @@ def cpu_train_steps(steps, warmup, batch=CPU_SAMPLE_BATCH):
     img = torch.randn(batch, 3, IMG, IMG, generator=g)
     labels = torch.randint(0, CLASSES, (batch,), generator=g)
     times = []
+    probe = torch.optim.SGD([torch.zeros(1, requires_grad=True)], lr=LR, momentum=0.9)
+    probe_sched = torch.optim.lr_scheduler.OneCycleLR(probe, max_lr=LR, pct_start=WARMUP_STEPS / TRAIN_STEPS,
+                                                      total_steps=TRAIN_STEPS)
+    lrs = []
+    for _ in range(warmup + steps):
+        lrs.append(probe.param_groups[0]["lr"])
+        probe.step()
+        probe_sched.step()
+
+    def lr_at(i):
+        return lrs[i]
+
     for i in range(warmup + steps):
         t0 = time.perf_counter()
         leaf = {k: v.detach().requires_grad_(True) for k, v in params.items()}
         loss = vit_oracle.vit_loss(img, labels, leaf)
         loss.backward()
-        vit_oracle.sgd_momentum_step(params, {k: v.grad for k, v in leaf.items()}, bufs, 0.03, 0.9, first=(i == 0))
+        vit_oracle.sgd_momentum_step(params, {k: v.grad for k, v in leaf.items()}, bufs, lr_at(i), 0.9, first=(i == 0))
         float(loss.detach())
         if i >= warmup:
             times.append(time.perf_counter() - t0)
@@ -146,8 +160,11 @@ def run_reference(args, rank):
         "impl": "reference", "metric": "train images/sec", "value": ips, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "ViT-B/16 224px train step (fwd+bwd+SGD), C=100, host cores",
-                   "sample": "batch %d per step" % CPU_SAMPLE_BATCH},
+        "config": {"workload": WORKLOAD % BATCH_PER_GPU, "parallelism": "dp%d" % args.gpus,
+                   "global_batch": args.gpus * BATCH_PER_GPU, "launch": "torch CPU fp32 on the host cores (rank 0 only)",
+                   "sample": "each step is a bounded sample of the workload: batch %d instead of %d"
+                             % (CPU_SAMPLE_BATCH, BATCH_PER_GPU),
+                   "weights": "reference constructor, seed 0, attention/pos weights x0.02 (SURVEY F5)"},
         "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
                          "sample": "%d steps of batch %d (oracle/vit_oracle.py, torch CPU fp32)" % (args.steps, CPU_SAMPLE_BATCH)},
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -197,7 +214,10 @@ def main():
                            "pos_embedding.pos_embedding")):
                 v.mul_(0.02)
     model = model.to(dev).train()
-    opt = vitb200.optim.FusedSGD(model.parameters(), lr=0.03, momentum=0.9)
+    opt = vitb200.optim.FusedSGD(model.parameters(), lr=LR, momentum=0.9)
+    # the reference's schedule (src/train.py:159-163, config defaults src/config.py:39-42): the step starts at
+    # max_lr / 25 and the learning rate reaches the kernels through a device scalar, so it also drives the graph
+    sched = torch.optim.lr_scheduler.OneCycleLR(opt, max_lr=LR, pct_start=WARMUP_STEPS / TRAIN_STEPS, total_steps=TRAIN_STEPS)
     net = vitb200.ddp.DataParallel(model, opt) if world > 1 else model
     B = args.batch
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
@@ -211,6 +231,7 @@ def main():
         loss = vitb200.functional.cross_entropy(net(img), labels)
         loss.backward()
         opt.step()
+        sched.step()
         return loss
 
     graphed = None
@@ -224,7 +245,13 @@ def main():
                 print("bench: CUDA-graph capture failed (%r); timing the eager step" % (exc,), file=sys.stderr)
             graphed = None
             torch.cuda.synchronize()
-    step = graphed if graphed is not None else eager_step
+    if graphed is not None:
+        def step(img, labels):          # src/train.py:19-25: ... optimizer.step(); lr_scheduler.step()
+            loss = graphed(img, labels)
+            sched.step()
+            return loss
+    else:
+        step = eager_step
 
     def barrier():
         if world > 1:
@@ -290,7 +317,7 @@ def main():
             "metric": "train images/sec", "value": ips, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "ViT-B/16 224px train step (fwd+bwd+SGD momentum 0.9), batch %d/GPU, C=100" % B,
+            "config": {"workload": WORKLOAD % B,
                        "parallelism": "dp%d" % world, "global_batch": world * B,
                        "launch": "one CUDA graph per step" if graphed is not None else "eager (Python launches)",
                        "l2": "per-step working set (~8 GB of activations) exceeds the 126 MB L2; no flush needed",
