@@ -105,10 +105,13 @@ def test_attn_tc_fwd_bwd_packed_qkv(N):
 
 
 @pytest.mark.parametrize("dh,N,H,simt", [(80, 257, 16, True), (128, 130, 3, True), (96, 300, 2, False),
-                                         (80, 50, 4, True), (112, 256, 2, False)])
-def test_attn_tc_wide_heads_forward(dh, N, H, simt):
-    """tcgen05 forward for 64 < head_dim <= 128 (ViT-H/14: head_dim 80, 257 tokens, i.e. two MMAs per S row
-    block and a partially used second head-dim chunk); the backward of these shapes stays on the SIMT kernel."""
+                                         (80, 50, 4, True), (112, 256, 2, False),
+                                         (64, 577, 12, False), (80, 730, 2, False), (64, 321, 2, False), (128, 640, 1, False)])
+def test_attn_tc_general_shapes_forward(dh, N, H, simt):
+    """tcgen05 forward for 64 <= head_dim <= 128 and any token count: ViT-H/14 at 224 px (head_dim 80, 257 tokens:
+    two MMAs per S row block, a partially used second head-dim chunk) and the 384 px evaluation resolution
+    (577 tokens for */16, 730 for h14: several key blocks, online softmax).  The backward of these shapes stays on
+    the SIMT kernel."""
     import vitb200
     B = 2
     D = H * dh
@@ -117,6 +120,7 @@ def test_attn_tc_wide_heads_forward(dh, N, H, simt):
     assert vitb200.ops.attn_fwd_supported_tc(dh, N, N, torch.bfloat16)
     assert not vitb200.ops.attn_supported_tc(dh, N, N, torch.bfloat16)
     o, lse = vitb200.ops.attn_fwd(q, k, v, H)
+    assert o.dtype == torch.bfloat16
     ro, rlse = _attn_ref(q, k, v, H)
     torch.cuda.synchronize()
     assert rel_l2(o, ro) < 1e-2

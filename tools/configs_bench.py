@@ -2,6 +2,7 @@
   c3  ViT-L/16 224 bf16 train step, batch 64
   c4  ViT-H/14 224 bf16 inference, batch 256 (N = 257 tokens)
   c5  Res-ViT B/16 fine-tune step, router target 0.4, LoRA rank 8, bf16, batch 128 (and 32)
+  e384  ViT-B/16 384 px inference, batch 64 (N = 577 tokens: the reference's default evaluation resolution)
 Writes gpurun_out/configs_bench.txt."""
 import os
 import sys
@@ -75,6 +76,20 @@ if "c4" in which:
         ms = timed(lambda: m(img), 5, 2)
     log("c4 ViT-H/14 inference bs256 (N=257, head_dim 80, tcgen05 wide-head attention): %.2f ms/batch, %.0f img/s, %.0f TFLOP/s (334.588 GFLOP/img)"
         % (ms, B / ms * 1e3, B / ms * 334.588))
+    del m
+    torch.cuda.empty_cache()
+if "e384" in which:
+    torch.manual_seed(0)
+    m = vitb200.build_vit("b16", 384, 1000)
+    scale_attn(m)
+    m = m.cuda().eval()
+    B = 64
+    img = torch.randn(B, 3, 384, 384, device="cuda")
+    with torch.no_grad():
+        ms = timed(lambda: m(img), 5, 2)
+        out = m(img)
+    log("e384 ViT-B/16 384px inference bs64 (N=577, multi-block tcgen05 attention): %.2f ms/batch, %.0f img/s, logits finite %s"
+        % (ms, B / ms * 1e3, bool(torch.isfinite(out).all())))
     del m
     torch.cuda.empty_cache()
 if "c5" in which:

@@ -263,18 +263,25 @@ attn_fwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
 }
 
 // ================================================================================================
-// forward, wide heads: 64 < head_dim <= 128 (multiple of 16) and up to 320 keys — ViT-H/14 at 224 px is
-// head_dim 80 x 257 tokens (src/config.py:93-104).  Same plan as attn_fwd_tc with two changes:
+// forward, general shapes: 64 <= head_dim <= 128 (multiple of 16) and ANY number of keys — ViT-H/14 is
+// head_dim 80 x 257 tokens at 224 px (src/config.py:93-104); the reference's default evaluation resolution of
+// 384 px (src/config.py:12) gives 577 tokens for */16 and 730 for h14.  Same plan as attn_fwd_tc, plus:
 //   * the head dimension spans two 64-column 128B-swizzled chunks; the second TMA box reads 64 columns even
 //     when head_dim < 128 (the surplus belongs to the next head or is zero-filled past the row), but the
 //     MMAs only ever consume head_dim columns: K-extent head_dim/16 steps for S, N = head_dim for O
-//   * more than 256 keys do not fit one MMA: S is issued as N = 256 plus N = NK - 256 into adjacent TMEM
-//     columns, still one accumulator row per query, so the softmax needs no online rescale
-// TMEM: S in columns [0, NK), O in [384, 384 + head_dim); one CTA per SM.
+//   * keys are processed in blocks of up to 320 (one block for ViT-H/14 at 224 px).  More than 256 keys do
+//     not fit one MMA: S is issued as N = 256 plus the rest into adjacent TMEM columns, still one
+//     accumulator row per query
+//   * with several key blocks the running row max / row sum follow the online-softmax recurrence and O is
+//     accumulated in registers: O <- O * exp2((m_old - m_new) c) + P_blk V_blk, each block's product read
+//     back from TMEM (no TMEM read-modify-write)
+// TMEM: S in columns [0, 320), O_blk in [384, 384 + head_dim); one CTA per SM.
 // ================================================================================================
-struct AttnWide {
-  int N, NK, H, dh;
-  int kv_loads, kv_rows;   // K / V chunks arrive as kv_loads boxes of kv_rows rows (TMA boxes hold <= 256 rows)
+struct AttnGen {
+  int N, H, dh;
+  int KB;                  // keys per block (multiple of 16, <= 320); smem chunk stride = KB * 128 bytes
+  int nblocks;
+  int kv_loads, kv_rows;   // K / V chunks of a block arrive as kv_loads boxes of kv_rows rows (boxes hold <= 256 rows)
   float scale, scale_log2;
   __nv_bfloat16* o;
   long long o_bs, o_rs;
@@ -282,21 +289,22 @@ struct AttnWide {
 };
 
 __global__ void __launch_bounds__(kAttnThreads, 1)
-attn_fwd_tc_wide(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnWide a) {
+attn_fwd_tc_gen(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnGen a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  const int NK = a.NK, dh = a.dh;
-  const int kvc = NK * 128;                       // one 64-column chunk of K or V: [NK rows x 128 B]
-  const int npchunks = (NK + 63) >> 6;            // 64-key chunks of the P image
-  const int u_bytes = max(2 * kChunkBytes + 2 * kvc, npchunks * kChunkBytes);
-  uint8_t* sV = smem;                             // [2 chunks][NK x 64]
-  uint8_t* sU = smem + 2 * kvc;                   // Q (2 chunks) | K (2 chunks), later overwritten by P
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sU + u_bytes);
+  const int dh = a.dh;
+  const int kvc = a.KB * 128;                     // one 64-column chunk of a K or V block: [KB rows x 128 B]
+  const int npchunks = (a.KB + 63) >> 6;          // 64-key chunks of the P image
+  const int kp_bytes = max(2 * kvc, npchunks * kChunkBytes);
+  uint8_t* sV = smem;                             // [2 chunks][KB x 64]
+  uint8_t* sQ = sV + 2 * kvc;                     // [2 chunks][128 x 64], kept for every key block
+  uint8_t* sK = sQ + 2 * kChunkBytes;             // [2 chunks][KB x 64], overwritten by P once S is in TMEM
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sK + kp_bytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
   float* red = reinterpret_cast<float*>(bars + 8);   // [2 stats][2 halves][128 rows]
   const uint32_t bar_qk = smem_u32(bars), bar_v = bar_qk + 8, bar_s = bar_qk + 16, bar_o = bar_qk + 24;
-  const uint32_t sV_u = smem_u32(sV), sQ_u = smem_u32(sU), sK_u = sQ_u + 2 * kChunkBytes, sP_u = sQ_u;
+  const uint32_t sV_u = smem_u32(sV), sQ_u = smem_u32(sQ), sK_u = smem_u32(sK), sP_u = sK_u;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int half = warp >> 2;
@@ -316,130 +324,174 @@ attn_fwd_tc_wide(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const uint32_t tmem_o = tmem_base + 384u;
   pdl_wait();
 
-  const int ksteps = dh >> 4;                     // head-dim steps of 16 for S = Q K^T
-  if (tid == 0) {
-    mbar_arrive_expect_tx(bar_qk, 2 * kChunkBytes + 2 * kvc);
-    for (int c = 0; c < 2; ++c) {
-      tma_load_3d(&tmQ, bar_qk, sQ_u + c * kChunkBytes, h * dh + 64 * c, row0, b);
-      for (int l = 0; l < a.kv_loads; ++l)
-        tma_load_3d(&tmK, bar_qk, sK_u + c * kvc + l * a.kv_rows * 128, h * dh + 64 * c, l * a.kv_rows, b);
-    }
-    mbar_arrive_expect_tx(bar_v, 2 * kvc);
-    for (int c = 0; c < 2; ++c)
-      for (int l = 0; l < a.kv_loads; ++l)
-        tma_load_3d(&tmV, bar_v, sV_u + c * kvc + l * a.kv_rows * 128, h * dh + 64 * c, l * a.kv_rows, b);
-    mbar_wait(bar_qk, 0);
-    tc_fence_after();
-    const int n0 = NK > 256 ? 256 : NK, n1 = NK - n0;
-    const uint32_t idesc0 = umma_idesc_bf16(128, n0, false, false);
-    const uint32_t idesc1 = umma_idesc_bf16(128, n1 > 0 ? n1 : 16, false, false);
-    for (int ks = 0; ks < ksteps; ++ks) {
-      const uint32_t qa = sQ_u + (ks >> 2) * kChunkBytes + (ks & 3) * 32;
-      const uint32_t ka = sK_u + (ks >> 2) * kvc + (ks & 3) * 32;
-      umma_bf16_ss(tmem_base, umma_smem_desc_sw128(qa, 16, 1024), umma_smem_desc_sw128(ka, 16, 1024), idesc0,
-                   ks > 0 ? 1u : 0u);
-      if (n1 > 0)   // keys 256 .. NK-1: B rows start 256 * 128 B further, D columns start at 256
-        umma_bf16_ss(tmem_base + 256u, umma_smem_desc_sw128(qa, 16, 1024),
-                     umma_smem_desc_sw128(ka + 256 * 128, 16, 1024), idesc1, ks > 0 ? 1u : 0u);
-    }
-    umma_commit(bar_s);
-  }
-  __syncwarp();
-  mbar_wait(bar_s, 0);
-  tc_fence_after();
-
   const int r = (warp & 3) * 32 + lane;  // query row within the tile == TMEM lane
   const uint32_t trow = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-  const ColRange cr = my_chunks(NK, half);
-  // pass 1: row max over the valid keys of this thread's column half
-  float mx = -INFINITY;
-  for (int c = cr.c_begin; c < cr.c_end; c += 2) {
-    uint32_t v0[32], v1[32];
-    const bool two = (c + 1 < cr.c_end);
-    issue_chunk(trow, c * 32, NK, v0);
-    if (two) issue_chunk(trow, (c + 1) * 32, NK, v1);
-    tmem_ld_wait();
-    mx = fmaxf(mx, chunk_max(v0, c * 32, NK, a.N));
-    if (two) mx = fmaxf(mx, chunk_max(v1, (c + 1) * 32, NK, a.N));
-  }
-  red[half * 128 + r] = mx;
-  __syncthreads();
-  mx = fmaxf(red[r], red[128 + r]);
-  // pass 2: p = exp2((s - max) * c), row sum, bf16 P into the swizzled A-operand image (over Q | K)
-  float sum = 0.f;
-  const float mxs = mx * a.scale_log2;
-  for (int c = cr.c_begin; c < cr.c_end; ++c) {
-    const int c0 = c * 32;
-    uint32_t v[32];
-    ld_chunk(trow, c0, NK, 0u, v);
-    float pv[32];
+  const int ksteps = dh >> 4;                     // head-dim steps of 16 for S = Q K^T
+  // 16-column units of the head dimension owned by this thread: half 0 the first ceil(n/2), half 1 the rest
+  const int nun = dh >> 4, umid = (nun + 1) >> 1;
+  const int ub = half ? umid : 0, ue = half ? nun : umid;
+  const bool multi = a.nblocks > 1;
+  float o_acc[4][16];                             // running O (only used with several key blocks)
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float e = ex2_approx(fmaf(__uint_as_float(v[j]), a.scale_log2, -mxs));
-      pv[j] = (c0 + j < a.N) ? e : 0.f;
-      sum += pv[j];
-    }
-    const int kc = c0 >> 6, u0 = (c0 & 63) >> 3, nunits = (c0 + 32 <= NK) ? 4 : 2;
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (u < nunits)
-        st_shared_v4(sP_u + kc * kChunkBytes + swz_unit(r, u0 + u), pack_bf16x2(pv[8 * u + 0], pv[8 * u + 1]),
-                     pack_bf16x2(pv[8 * u + 2], pv[8 * u + 3]), pack_bf16x2(pv[8 * u + 4], pv[8 * u + 5]),
-                     pack_bf16x2(pv[8 * u + 6], pv[8 * u + 7]));
+    for (int j = 0; j < 16; ++j) o_acc[i][j] = 0.f;
+  float m_run = -INFINITY;                        // running row max (identical in both halves of a row)
+  float sum = 0.f;                                // this half's running row sum
+
+  for (int kb = 0; kb < a.nblocks; ++kb) {
+    const uint32_t ph = kb & 1;
+    const int key0 = kb * a.KB;
+    const int valid = min(a.N - key0, a.KB);      // keys of this block that exist
+    const int NK = (valid + 15) & ~15;            // MMA / softmax extent of this block
+    if (tid == 0) {
+      mbar_arrive_expect_tx(bar_qk, (kb == 0 ? 2 * kChunkBytes : 0) + 2 * kvc);
+      for (int c = 0; c < 2; ++c) {
+        if (kb == 0) tma_load_3d(&tmQ, bar_qk, sQ_u + c * kChunkBytes, h * dh + 64 * c, row0, b);
+        for (int l = 0; l < a.kv_loads; ++l)
+          tma_load_3d(&tmK, bar_qk, sK_u + c * kvc + l * a.kv_rows * 128, h * dh + 64 * c, key0 + l * a.kv_rows, b);
+      }
+      mbar_arrive_expect_tx(bar_v, 2 * kvc);
+      for (int c = 0; c < 2; ++c)
+        for (int l = 0; l < a.kv_loads; ++l)
+          tma_load_3d(&tmV, bar_v, sV_u + c * kvc + l * a.kv_rows * 128, h * dh + 64 * c, key0 + l * a.kv_rows, b);
+      mbar_wait(bar_qk, ph);
+      tc_fence_after();
+      const int n0 = NK > 256 ? 256 : NK, n1 = NK - n0;
+      const uint32_t idesc0 = umma_idesc_bf16(128, n0, false, false);
+      const uint32_t idesc1 = umma_idesc_bf16(128, n1 > 0 ? n1 : 16, false, false);
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const uint32_t qa = sQ_u + (ks >> 2) * kChunkBytes + (ks & 3) * 32;
+        const uint32_t ka = sK_u + (ks >> 2) * kvc + (ks & 3) * 32;
+        umma_bf16_ss(tmem_base, umma_smem_desc_sw128(qa, 16, 1024), umma_smem_desc_sw128(ka, 16, 1024), idesc0,
+                     ks > 0 ? 1u : 0u);
+        if (n1 > 0)   // keys 256 .. NK-1: B rows start 256 * 128 B further, D columns start at 256
+          umma_bf16_ss(tmem_base + 256u, umma_smem_desc_sw128(qa, 16, 1024),
+                       umma_smem_desc_sw128(ka + 256 * 128, 16, 1024), idesc1, ks > 0 ? 1u : 0u);
+      }
+      umma_commit(bar_s);
     }
-  }
-  red[256 + half * 128 + r] = sum;
-  fence_proxy_async_smem();
-  tc_fence_before();
-  __syncthreads();
-  sum = red[256 + r] + red[256 + 128 + r];
-  if (tid == 0) {
+    __syncwarp();
+    mbar_wait(bar_s, ph);
     tc_fence_after();
-    mbar_wait(bar_v, 0);
-    // O = P V : A = P (K-major over keys), B = V consumed MN-major ([keys x head_dim], head_dim contiguous,
-    // the two 64-column chunks kvc bytes apart)
-    const uint32_t idesc = umma_idesc_bf16(128, dh, false, true);
-    const int nks = NK >> 4;
-    for (int t = 0; t < nks; ++t)
-      umma_bf16_ss(tmem_o, umma_smem_desc_sw128(sP_u + (t >> 2) * kChunkBytes + (t & 3) * 32, 16, 1024),
-                   umma_smem_desc_sw128(sV_u + t * 2048, kvc, 1024), idesc, t > 0 ? 1u : 0u);
-    umma_commit(bar_o);
-  }
-  __syncwarp();
-  mbar_wait(bar_o, 0);
-  tc_fence_after();
-  const int row = row0 + r;
-  {
-    // 16-column units of the head dimension: half 0 drains the first ceil(n/2), half 1 the rest
-    const int nun = dh >> 4, mid = (nun + 1) >> 1;
-    const int ub = half ? mid : 0, ue = half ? nun : mid;
-    const float inv = 1.0f / sum;
-    for (int u = ub; u < ue; ++u) {
-      uint32_t v[16];
-      tmem_ld_32x32b_x16(trow + 384u + static_cast<uint32_t>(u * 16), v);
+
+    const ColRange cr = my_chunks(NK, half);
+    // pass 1: row max over the valid keys of this thread's column half
+    float mx = -INFINITY;
+    for (int c = cr.c_begin; c < cr.c_end; c += 2) {
+      uint32_t v0[32], v1[32];
+      const bool two = (c + 1 < cr.c_end);
+      issue_chunk(trow, c * 32, NK, v0);
+      if (two) issue_chunk(trow, (c + 1) * 32, NK, v1);
       tmem_ld_wait();
-      if (row < a.N) {
-        uint4* d = reinterpret_cast<uint4*>(a.o + b * a.o_bs + static_cast<long long>(row) * a.o_rs + h * dh + u * 16);
-        uint4 w0, w1;
-        w0.x = pack_bf16x2(__uint_as_float(v[0]) * inv, __uint_as_float(v[1]) * inv);
-        w0.y = pack_bf16x2(__uint_as_float(v[2]) * inv, __uint_as_float(v[3]) * inv);
-        w0.z = pack_bf16x2(__uint_as_float(v[4]) * inv, __uint_as_float(v[5]) * inv);
-        w0.w = pack_bf16x2(__uint_as_float(v[6]) * inv, __uint_as_float(v[7]) * inv);
-        w1.x = pack_bf16x2(__uint_as_float(v[8]) * inv, __uint_as_float(v[9]) * inv);
-        w1.y = pack_bf16x2(__uint_as_float(v[10]) * inv, __uint_as_float(v[11]) * inv);
-        w1.z = pack_bf16x2(__uint_as_float(v[12]) * inv, __uint_as_float(v[13]) * inv);
-        w1.w = pack_bf16x2(__uint_as_float(v[14]) * inv, __uint_as_float(v[15]) * inv);
-        d[0] = w0;
-        d[1] = w1;
+      mx = fmaxf(mx, chunk_max(v0, c * 32, NK, valid));
+      if (two) mx = fmaxf(mx, chunk_max(v1, (c + 1) * 32, NK, valid));
+    }
+    red[half * 128 + r] = mx;
+    __syncthreads();
+    const float m_new = fmaxf(m_run, fmaxf(red[r], red[128 + r]));
+    const float alpha = ex2_approx((m_run - m_new) * a.scale_log2);   // 0 on the first block (m_run = -inf)
+    m_run = m_new;
+    // pass 2: p = exp2((s - max) * c), row sum, bf16 P into the swizzled A-operand image (over the K block)
+    sum *= alpha;
+    const float mxs = m_new * a.scale_log2;
+    for (int c = cr.c_begin; c < cr.c_end; ++c) {
+      const int c0 = c * 32;
+      uint32_t v[32];
+      ld_chunk(trow, c0, NK, 0u, v);
+      float pv[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float e = ex2_approx(fmaf(__uint_as_float(v[j]), a.scale_log2, -mxs));
+        pv[j] = (c0 + j < valid) ? e : 0.f;
+        sum += pv[j];
+      }
+      const int kc = c0 >> 6, u0 = (c0 & 63) >> 3, nunits = (c0 + 32 <= NK) ? 4 : 2;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (u < nunits)
+          st_shared_v4(sP_u + kc * kChunkBytes + swz_unit(r, u0 + u), pack_bf16x2(pv[8 * u + 0], pv[8 * u + 1]),
+                       pack_bf16x2(pv[8 * u + 2], pv[8 * u + 3]), pack_bf16x2(pv[8 * u + 4], pv[8 * u + 5]),
+                       pack_bf16x2(pv[8 * u + 6], pv[8 * u + 7]));
       }
     }
-    if (row < a.N && a.lse && half == 0) a.lse[(static_cast<long long>(b) * a.H + h) * a.N + row] = mx * a.scale + logf(sum);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      mbar_wait(bar_v, ph);
+      // O_blk = P V : A = P (K-major over keys), B = V consumed MN-major ([keys x head_dim], head_dim
+      // contiguous, the two 64-column chunks kvc bytes apart)
+      const uint32_t idesc = umma_idesc_bf16(128, dh, false, true);
+      const int nks = NK >> 4;
+      for (int t = 0; t < nks; ++t)
+        umma_bf16_ss(tmem_o, umma_smem_desc_sw128(sP_u + (t >> 2) * kChunkBytes + (t & 3) * 32, 16, 1024),
+                     umma_smem_desc_sw128(sV_u + t * 2048, kvc, 1024), idesc, t > 0 ? 1u : 0u);
+      umma_commit(bar_o);
+    }
+    __syncwarp();
+    mbar_wait(bar_o, ph);
+    tc_fence_after();
+    if (multi) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int u = ub + i;
+        if (u < ue) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(trow + 384u + static_cast<uint32_t>(u * 16), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) o_acc[i][j] = fmaf(o_acc[i][j], alpha, __uint_as_float(v[j]));
+        }
+      }
+      // the next block overwrites K / P / V and both TMEM regions: every warp has to be done reading them
+      tc_fence_before();
+      __syncthreads();
+      tc_fence_after();
+    }
+  }
+
+  red[256 + half * 128 + r] = sum;
+  __syncthreads();
+  sum = red[256 + r] + red[256 + 128 + r];
+  const int row = row0 + r;
+  {
+    const float inv = 1.0f / sum;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int u = ub + i;
+      if (u < ue) {
+        float f[16];
+        if (multi) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = o_acc[i][j] * inv;
+        } else {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(trow + 384u + static_cast<uint32_t>(u * 16), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) * inv;
+        }
+        if (row < a.N) {
+          uint4* d = reinterpret_cast<uint4*>(a.o + b * a.o_bs + static_cast<long long>(row) * a.o_rs + h * dh + u * 16);
+          uint4 w0, w1;
+          w0.x = pack_bf16x2(f[0], f[1]);   w0.y = pack_bf16x2(f[2], f[3]);
+          w0.z = pack_bf16x2(f[4], f[5]);   w0.w = pack_bf16x2(f[6], f[7]);
+          w1.x = pack_bf16x2(f[8], f[9]);   w1.y = pack_bf16x2(f[10], f[11]);
+          w1.z = pack_bf16x2(f[12], f[13]); w1.w = pack_bf16x2(f[14], f[15]);
+          d[0] = w0;
+          d[1] = w1;
+        }
+      }
+    }
+    if (row < a.N && a.lse && half == 0)
+      a.lse[(static_cast<long long>(b) * a.H + h) * a.N + row] = m_run * a.scale + logf(sum);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
-
 
 // ================================================================================================
 // backward.  TMEM columns: [0,256) S then dP then dQ ; [256,384) dK (two 128-key M tiles x 64) ; [384,512) dV.
@@ -713,14 +765,14 @@ int make_head_map(CUtensorMap* m, const void* base, int H, int N, int B, long lo
   return vitb_make_tmap_nd_bf16(m, base, 3, dims, str, box);
 }
 
-bool wide_ok(int head_dim, int Nq, int Nk) {   // attn_fwd_tc_wide
-  return head_dim > DH && head_dim <= 128 && head_dim % 16 == 0 && Nq == Nk && Nk >= 1 && Nk <= 320;
+bool gen_ok(int head_dim, int Nq, int Nk) {   // attn_fwd_tc_gen: any head_dim in [64, 128] % 16, any token count
+  return head_dim >= DH && head_dim <= 128 && head_dim % 16 == 0 && Nq == Nk && Nk >= 1;
 }
 
 int check_common(const vitb_attn_params* p, const char* who, bool allow_wide = false) {
   VITB_REQUIRE(p && p->struct_bytes == (int)sizeof(vitb_attn_params), VITB_ERR_BAD_ARG, "%s: ABI mismatch", who);
   VITB_REQUIRE(p->dtype == VITB_BF16, VITB_ERR_UNSUPPORTED_SHAPE, "%s: bf16 only", who);
-  if (allow_wide && wide_ok(p->head_dim, p->Nq, p->Nk)) {
+  if (allow_wide && gen_ok(p->head_dim, p->Nq, p->Nk)) {
     VITB_REQUIRE(p->q && p->k && p->v && p->o, VITB_ERR_BAD_ARG, "%s: null tensor", who);
     VITB_REQUIRE(p->o_row_stride % 8 == 0 && p->o_batch_stride % 8 == 0, VITB_ERR_UNSUPPORTED_SHAPE, "%s: o strides %% 8", who);
     return VITB_OK;
@@ -740,16 +792,19 @@ extern "C" int vitb_attn_supported_tc(int head_dim, int Nq, int Nk) {
 }
 
 extern "C" int vitb_attn_fwd_supported_tc(int head_dim, int Nq, int Nk) {
-  return vitb_attn_supported_tc(head_dim, Nq, Nk) || wide_ok(head_dim, Nq, Nk);
+  return vitb_attn_supported_tc(head_dim, Nq, Nk) || gen_ok(head_dim, Nq, Nk);
 }
 
 namespace {
-int launch_fwd_wide(const vitb_attn_params* p, cudaStream_t stream) {
-  const int N = p->Nk, NK = (N + 15) & ~15, dh = p->head_dim;
-  AttnWide a{};
-  a.N = N; a.NK = NK; a.H = p->H; a.dh = dh;
-  a.kv_loads = NK > 256 ? 2 : 1;
-  a.kv_rows = NK / a.kv_loads;          // NK is a multiple of 16, so halves stay multiples of 8 (swizzle atom)
+int launch_fwd_gen(const vitb_attn_params* p, cudaStream_t stream) {
+  const int N = p->Nk, dh = p->head_dim;
+  const int NKall = (N + 15) & ~15;
+  AttnGen a{};
+  a.N = N; a.H = p->H; a.dh = dh;
+  a.KB = NKall < 320 ? NKall : 320;
+  a.nblocks = (N + a.KB - 1) / a.KB;
+  a.kv_loads = a.KB > 256 ? 2 : 1;
+  a.kv_rows = a.KB / a.kv_loads;        // KB is a multiple of 16, so halves stay multiples of 8 (swizzle atom)
   a.scale = 1.0f / sqrtf((float)dh);
   a.scale_log2 = a.scale * 1.4426950408889634f;
   a.o = reinterpret_cast<__nv_bfloat16*>(p->o); a.o_bs = p->o_batch_stride; a.o_rs = p->o_row_stride;
@@ -759,14 +814,15 @@ int launch_fwd_wide(const vitb_attn_params* p, cudaStream_t stream) {
   if ((st = make_head_map(&tq, p->q, p->H, N, p->B, p->q_row_stride, p->q_batch_stride, 128, dh)) != VITB_OK) return st;
   if ((st = make_head_map(&tk, p->k, p->H, N, p->B, p->k_row_stride, p->k_batch_stride, a.kv_rows, dh)) != VITB_OK) return st;
   if ((st = make_head_map(&tv, p->v, p->H, N, p->B, p->v_row_stride, p->v_batch_stride, a.kv_rows, dh)) != VITB_OK) return st;
-  const int kvc = NK * 128, npchunks = (NK + 63) / 64;
-  const int u_bytes = (2 * kChunkBytes + 2 * kvc) > npchunks * kChunkBytes ? (2 * kChunkBytes + 2 * kvc) : npchunks * kChunkBytes;
-  const int smem = 2 * kvc + u_bytes + 64 + 4 * 128 * 4 + 1024;
-  VITB_REQUIRE(smem <= 227 * 1024, VITB_ERR_UNSUPPORTED_SHAPE, "attn_fwd_tc_wide: %d B of shared memory", smem);
-  VITB_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_tc_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int kvc = a.KB * 128, npchunks = (a.KB + 63) / 64;
+  const int kp_bytes = 2 * kvc > npchunks * kChunkBytes ? 2 * kvc : npchunks * kChunkBytes;
+  // V block | Q | K block / P | barriers + TMEM slot | row statistics | alignment slack
+  const int smem = 2 * kvc + 2 * kChunkBytes + kp_bytes + 64 + 4 * 128 * 4 + 1024;
+  VITB_REQUIRE(smem <= 227 * 1024, VITB_ERR_UNSUPPORTED_SHAPE, "attn_fwd_tc_gen: %d B of shared memory", smem);
+  VITB_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_tc_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   dim3 grid((N + 127) / 128, p->H, p->B);
-  VITB_CUDA_CHECK(vitb_launch(attn_fwd_tc_wide, grid, dim3(kAttnThreads), smem, stream, tq, tk, tv, a));
-  VITB_LAUNCH_CHECK("attn_fwd_tc_wide");
+  VITB_CUDA_CHECK(vitb_launch(attn_fwd_tc_gen, grid, dim3(kAttnThreads), smem, stream, tq, tk, tv, a));
+  VITB_LAUNCH_CHECK("attn_fwd_tc_gen");
   return VITB_OK;
 }
 }  // namespace
@@ -777,7 +833,7 @@ extern "C" int vitb_attn_fwd_tc(const vitb_attn_params* p, void* stream_) {
   st = check_common(p, "attn_fwd_tc", true);
   if (st != VITB_OK) return st;
   if (p->B == 0) return VITB_OK;
-  if (p->head_dim != DH) return launch_fwd_wide(p, reinterpret_cast<cudaStream_t>(stream_));
+  if (p->head_dim != DH || p->Nk > 256) return launch_fwd_gen(p, reinterpret_cast<cudaStream_t>(stream_));
   const int N = p->Nk, NK = (N + 15) & ~15;
   CUtensorMap tq, tk, tv;
   if ((st = make_head_map(&tq, p->q, p->H, N, p->B, p->q_row_stride, p->q_batch_stride, 128)) != VITB_OK) return st;
