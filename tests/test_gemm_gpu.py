@@ -219,3 +219,26 @@ def test_gemm_bf16_tma_store_respects_row_and_column_tails_and_strided_outputs()
     vitb200.ops.gemm(A, B, out=out[:M2])
     torch.cuda.synchronize()
     assert rel_l2(out[:M2], ref) < 4e-3 and bool((out[M2:] == 7.0).all())
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (512, 256, 300), (768, 768, 2048), (3072, 768, 1000), (304, 520, 777)])
+def test_gemm_wgrad_on_cta_pairs(M, N, K):
+    """Weight gradients with M, N >= 256 run on the cta_group::2 pair kernel (256 x 256 tiles, automatic split-K,
+    fp32 red.global accumulation); VITB_GEMM_PAIR=0 keeps the single-CTA kernel, both must agree with torch."""
+    import os
+    import vitb200
+    A = _mk((K, M), 91, 0.5)
+    B = _mk((K, N), 92, 0.5)
+    ref = A.float().t() @ B.float() + 1.0
+    outs = []
+    for flag in ("1", "0"):
+        os.environ["VITB_GEMM_PAIR"] = flag
+        try:
+            out = torch.ones(M, N, device="cuda")
+            vitb200.ops.gemm(A, B, a_mn=True, b_mn=True, out=out, accumulate=True)
+            torch.cuda.synchronize()
+        finally:
+            os.environ.pop("VITB_GEMM_PAIR", None)
+        assert rel_l2(out, ref) < 2e-5
+        outs.append(out)
+    assert rel_l2(outs[0], outs[1]) < 1e-6

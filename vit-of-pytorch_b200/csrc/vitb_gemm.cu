@@ -605,6 +605,193 @@ vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   }
 }
 
+// ================================================================================================
+// Weight-gradient GEMM on CTA pairs (tcgen05 cta_group::2): dW[M,N] += A[K,M]^T B[K,N], both operands
+// MN-major, K = tokens, fp32 red.global accumulation, split along K.
+//
+// The weight-gradient shapes are the ones a pair tiles exactly (M, N in {768, 3072}: multiples of 256) and
+// the ones furthest from cuBLAS in round 1 (1.10-1.16 vs 1.33-1.37 PFLOP/s, profiles/gemm_bench_r01.txt):
+// with K = 25,216 the mainloop is everything, and a 256 x 256 pair tile fetches 128 + 128 operand rows per SM
+// and k-block instead of 128 + 256 — a third less L2 -> SM traffic and shared-memory fill per FLOP.
+// (The token-major GEMMs stay on the single-CTA kernel: T = 197 x 128 rows leave half a pair tile over, which
+// costs a whole extra wave at N = 768.)
+//
+// Protocol (per k-block stage s, 6 stages of 32 KiB per CTA):
+//   both CTAs : producer lane waits its OWN empty[s], then TMA-loads its A and B halves with
+//               .cta_group::2 completion on the LEADER's full[s]; the leader alone arms expect_tx (2 x stage)
+//   leader    : waits full[s], issues 4 x tcgen05.mma.cta_group::2 (256 x 256 x 16), commits with
+//               .multicast::cluster to empty[s] of BOTH CTAs; after the last k-block to tmem_full[acc] of both
+//   both CTAs : epilogue warps drain their own 128 TMEM lanes (rows 128*rank ..) and arrive on the LEADER's
+//               tmem_empty[acc] (count = 2 x 8 warps)
+// ================================================================================================
+constexpr int kPairStages = 6;
+constexpr int kPairStageBytes = 2 * A_BYTES;   // A half 128 x 64 + B half 128 x 64, bf16
+constexpr int kPairSmemBytes = kPairStages * kPairStageBytes + kStagingBytes + 256;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+vitb_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                       const __grid_constant__ GemmDev p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) {
+    if (threadIdx.x == 0) printf("vitb_wgrad_pair: dynamic shared memory base 0x%x is not 1024-byte aligned\n", smem_u32(smem));
+    __trap();
+  }
+  float* staging = reinterpret_cast<float*>(smem + kPairStages * kPairStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kPairStages * kPairStageBytes + kStagingBytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kPairStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const uint32_t full0 = smem_u32(bars);
+  const uint32_t empty0 = smem_u32(bars + kPairStages);
+  const uint32_t tfull0 = smem_u32(bars + 2 * kPairStages);
+  const uint32_t tempty0 = smem_u32(bars + 2 * kPairStages + 2);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kPairStages; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull0 + 8 * s, 1);
+      mbar_init(tempty0 + 8 * s, 2 * kEpiWarps);   // the epilogue warps of BOTH CTAs arrive on the leader's copy
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_pair(smem_u32(tmem_slot), 512);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  cluster_sync_all();     // barriers of both CTAs initialised, TMEM allocated in both
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = p.m_tiles * p.n_tiles * p.split_k;     // pair tiles (256 x 256 x K-split)
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  if (warp == 0) {
+    // =============================== TMA producer (both CTAs) ===============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < total_tiles; tile += npairs) {
+        const TileCoord t = decode_tile(p, tile);
+        const int m0 = t.m_blk * 256 + static_cast<int>(rank) * 128;
+        const int n0 = t.n_blk * 256 + static_cast<int>(rank) * 128;
+        for (int g = t.g0; g < t.g1; ++g) {
+          mbar_wait(empty0 + 8 * stage, phase ^ 1u);
+          if (leader) mbar_arrive_expect_tx(full0 + 8 * stage, 2 * kPairStageBytes);
+          const uint32_t fb = mapa_shared(full0 + 8 * stage, 0);   // the leader's barrier collects both halves
+          const uint32_t sA = smem_u32(smem + stage * kPairStageBytes);
+          const uint32_t sB = sA + A_BYTES;
+#pragma unroll
+          for (int i = 0; i < 2; ++i) tma_load_2d_pair(&tmA, fb, sA + i * 8192, m0 + 64 * i, g * BK);
+#pragma unroll
+          for (int i = 0; i < 2; ++i) tma_load_2d_pair(&tmB, fb, sB + i * 8192, n0 + 64 * i, g * BK);
+          if (++stage == kPairStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer (leader CTA only) ===============================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(256, 256, true, true);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = pair; tile < total_tiles; tile += npairs) {
+        const TileCoord t = decode_tile(p, tile);
+        mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * 256);
+        for (int g = t.g0; g < t.g1; ++g) {
+          mbar_wait(full0 + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sA = smem_u32(smem + stage * kPairStageBytes);
+          const uint32_t sB = sA + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16_ss_pair(d_tmem, umma_smem_desc_sw128(sA + k * 2048, BK * 128, 1024),
+                              umma_smem_desc_sw128(sB + k * 2048, BK * 128, 1024), idesc, (g > t.g0 || k > 0) ? 1u : 0u);
+          umma_commit_pair(empty0 + 8 * stage, 3);                    // both CTAs' smem slots free once MMAs retire
+          if (g == t.g1 - 1) umma_commit_pair(tfull0 + 8 * acc, 3);   // both CTAs' accumulator halves ready
+          if (++stage == kPairStages) { stage = 0; phase ^= 1u; }
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // =============================== epilogue (both CTAs): fp32 red.global accumulation ===============================
+    const int q = warp & 3;
+    const uint32_t stg = smem_u32(staging) + static_cast<uint32_t>((warp - kEpiWarp0) * kStagingFloats * 4);
+    const uint32_t tempty_leader = mapa_shared(tempty0, 0);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = pair; tile < total_tiles; tile += npairs) {
+      const TileCoord t = decode_tile(p, tile);
+      const int n0 = t.n_blk * 256;
+      const int row_base = t.m_blk * 256 + static_cast<int>(rank) * 128 + q * 32;
+      mbar_wait(tfull0 + 8 * acc, acc_phase);
+      tc_fence_after();
+      const bool lead_split = (t.g0 == 0);
+      const int half = (warp - kEpiWarp0) >> 2;
+#pragma unroll 1
+      for (int c = half * 4; c < (half + 1) * 4; ++c) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= p.N) break;
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * 256 + c * 32), r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) st_shared_v2(stg + lane * (kStgStride * 4) + j * 8, r[2 * j], r[2 * j + 1]);
+        __syncwarp();
+        epi_vec<false, VITB_EPI_NONE, 0, true>(p, stg, lane, row_base, col0, lead_split);
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty_leader + 8 * acc);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();     // the peer's shared memory and TMEM are in use until the leader's last MMA has retired
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
+int launch_wgrad_pair(const CUtensorMap* tm, GemmDev d, int M, int N, cudaStream_t stream) {
+  const int sms = vitb_num_sms();
+  const int npairs = sms / 2;
+  d.m_tiles = (M + 255) / 256;
+  d.n_tiles = (N + 255) / 256;
+  const int tiles = d.m_tiles * d.n_tiles;
+  int split = npairs / (tiles > 0 ? tiles : 1);
+  if (split > d.total_kblocks / 4) split = d.total_kblocks / 4;
+  if (split < 1) split = 1;
+  d.split_k = split;
+  const long long total = (long long)tiles * split;
+  const int grid = 2 * (int)(total < npairs ? total : npairs);
+  VITB_CUDA_CHECK(cudaFuncSetAttribute(vitb_wgrad_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes));
+  vitb_wgrad_pair_kernel<<<grid, kThreads, kPairSmemBytes, stream>>>(tm[0], tm[1], d);
+  VITB_LAUNCH_CHECK("vitb_wgrad_pair_kernel");
+  return VITB_OK;
+}
+
 template <int BN, bool A_MN, bool B_MN>
 int launch(const CUtensorMap* tm, const GemmDev& d, int grid, cudaStream_t stream) {
   auto kern = vitb_gemm_kernel<BN, A_MN, B_MN>;
@@ -743,6 +930,16 @@ extern "C" int vitb_gemm(const vitb_gemm_params* p, void* stream_) {
       if (st != VITB_OK) return st;
     }
     d.tma_store = 1;
+  }
+  // weight gradients (both operands MN-major, fp32 accumulation, one K segment) run on CTA pairs
+  // (measured, profiles/gemm_bench_r01b.txt: dW fc1 0.099 -> 0.090 ms, dW fc2 0.104 -> 0.089 ms, i.e. 1.33 PFLOP/s)
+  {
+    const char* pair_env = getenv("VITB_GEMM_PAIR");   // VITB_GEMM_PAIR=0 keeps the single-CTA kernel (A/B measurements)
+    const bool pair_on = pair_env == nullptr || atoi(pair_env) != 0;
+    if (pair_on && p->a_mn_major && p->b_mn_major && p->accumulate && p->num_segments == 1 &&
+        d.epilogue == VITB_EPI_NONE && !d.d_bf16 && d.vec_ok && p->bias == nullptr && p->colsum == nullptr &&
+        p->split_k <= 0 && p->M >= 256 && p->N >= 256 && sms >= 2)
+      return launch_wgrad_pair(tm, d, p->M, p->N, stream);
   }
   const long long total_tiles = (long long)d.m_tiles * d.n_tiles * d.split_k;
   const int grid = (int)(total_tiles < sms ? total_tiles : sms);
