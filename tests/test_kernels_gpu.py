@@ -177,6 +177,30 @@ def test_attn_simt_asymmetric_queries():
     assert rel_l2(o, ro) < 2e-5
 
 
+@pytest.mark.parametrize("dtype,dh,Nk,tol", [(torch.bfloat16, 64, 197, 1e-2), (torch.float32, 64, 197, 2e-5),
+                                             (torch.bfloat16, 80, 257, 1e-2), (torch.bfloat16, 64, 577, 1e-2),
+                                             (torch.float32, 128, 50, 2e-5)])
+def test_attn_single_query_fwd_bwd(dtype, dh, Nk, tol):
+    """One query per (image, head) — the class-token-only last block (EncoderBlock.forward_row0) — runs on the
+    dedicated attn_q1 kernels (any key count, K / V read once from HBM)."""
+    import vitb200
+    B, H = 3, 4
+    D = H * dh
+    q = _randn((B, 1, D), 1, 1.0, dtype); k = _randn((B, Nk, D), 2, 1.0, dtype); v = _randn((B, Nk, D), 3, 1.0, dtype)
+    o, lse = vitb200.ops.attn_fwd(q, k, v, H, use_tc=False)
+    qf, kf, vf = (t.float().detach().requires_grad_(True) for t in (q, k, v))
+    ro, rlse = _attn_ref(qf, kf, vf, H)
+    assert o.shape == (B, 1, D) and lse.shape == (B, H, 1)
+    assert rel_l2(o, ro) < tol
+    assert rel_l2(lse, rlse) < 1e-5
+    do = _randn((B, 1, D), 4, 1.0, dtype)
+    ro.backward(do.float())
+    dq, dk, dv = vitb200.ops.attn_bwd(do, q, k, v, o, lse, H, use_tc=False)
+    torch.cuda.synchronize()
+    btol = tol * (4 if dtype == torch.bfloat16 else 2)
+    assert rel_l2(dq, qf.grad) < btol and rel_l2(dk, kf.grad) < btol and rel_l2(dv, vf.grad) < btol
+
+
 # ---------------------------------------------------------------------------------- elementwise etc.
 def test_cast_split():
     import vitb200

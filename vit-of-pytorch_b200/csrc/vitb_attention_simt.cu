@@ -191,6 +191,165 @@ attn_bwd_simt(const AttnDev a) {
   }
 }
 
+
+// ================================================================================================
+// One query per (image, head): the class-token-only attention of the last encoder block
+// (EncoderBlock.forward_row0; the reference classifies feat[:, 0] only, src/model.py:155,210).
+// The general kernels above stage K and V transposed in shared memory and leave one warp working when
+// Nq = 1 (round-1 launch list: 0.22 ms forward + 0.53 ms backward per step for a few MFLOP).  Here every
+// K / V row is read exactly once, straight from HBM, a warp per key with lanes over the head dimension
+// (4- or 8-byte loads, 128 B or more per warp), so both kernels are bound by the K/V read and the dK/dV write.
+// ================================================================================================
+constexpr int kQ1Warps = 4;
+
+template <bool BF16>
+__device__ __forceinline__ float2 ld2(const void* p, long long i) {   // elements i, i+1 (i even)
+  if constexpr (BF16) {
+    const uint32_t u = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const __nv_bfloat16*>(p) + i);
+    return make_float2(bf16_lo(u), bf16_hi(u));
+  } else {
+    return *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(p) + i);
+  }
+}
+
+__device__ __forceinline__ float block_reduce_q1(float v, float* red, bool is_max) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  v = is_max ? warp_max(v) : warp_sum(v);
+  __syncthreads();                 // red may still be read from the previous reduction
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float r = red[0];
+#pragma unroll
+  for (int w = 1; w < kQ1Warps; ++w) r = is_max ? fmaxf(r, red[w]) : r + red[w];
+  return r;
+}
+
+// grid: B*H blocks of 4 warps.  smem: q[dh] | s[Nk] | part[4][dh] | red[4]
+template <bool BF16>
+__global__ void __launch_bounds__(kQ1Warps * 32)
+attn_q1_fwd(const AttnDev a) {
+  extern __shared__ float sm[];
+  float* qs = sm;
+  float* sc = qs + a.dh;
+  float* part = sc + a.Nk;
+  float* red = part + kQ1Warps * a.dh;
+  const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int d = threadIdx.x; d < a.dh; d += blockDim.x) qs[d] = ldf<BF16>(a.q, b * a.q_bs + h * a.dh + d);
+  __syncthreads();
+  const long long kb = b * a.k_bs + h * a.dh, vb = b * a.v_bs + h * a.dh;
+  for (int j = warp; j < a.Nk; j += kQ1Warps) {
+    float acc = 0.f;
+    for (int d = 2 * lane; d < a.dh; d += 64) {
+      const float2 kv = ld2<BF16>(a.k, kb + j * a.k_rs + d);
+      acc = fmaf(qs[d], kv.x, fmaf(qs[d + 1], kv.y, acc));
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) sc[j] = acc * a.scale;
+  }
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int j = threadIdx.x; j < a.Nk; j += blockDim.x) mx = fmaxf(mx, sc[j]);
+  mx = block_reduce_q1(mx, red, true);
+  float sum = 0.f;
+  for (int j = threadIdx.x; j < a.Nk; j += blockDim.x) {
+    const float e = expf(sc[j] - mx);
+    sc[j] = e;
+    sum += e;
+  }
+  sum = block_reduce_q1(sum, red, false);   // its barriers also publish the exponentials
+  const float inv = 1.0f / sum;
+  if (threadIdx.x == 0 && a.lse) a.lse[static_cast<long long>(b) * a.H + h] = mx + logf(sum);
+  // o = sum_j p_j V[j]: warp w takes keys w, w+4, ...; lanes hold pairs of head-dim columns
+  float2 o0 = make_float2(0.f, 0.f), o1 = make_float2(0.f, 0.f);   // columns 2*lane(+1) and 64 + 2*lane(+1)
+  for (int j = warp; j < a.Nk; j += kQ1Warps) {
+    const float pj = sc[j] * inv;
+    const int d = 2 * lane;
+    if (d < a.dh) { const float2 v = ld2<BF16>(a.v, vb + j * a.v_rs + d); o0.x = fmaf(pj, v.x, o0.x); o0.y = fmaf(pj, v.y, o0.y); }
+    if (d + 64 < a.dh) { const float2 v = ld2<BF16>(a.v, vb + j * a.v_rs + d + 64); o1.x = fmaf(pj, v.x, o1.x); o1.y = fmaf(pj, v.y, o1.y); }
+  }
+  {
+    const int d = 2 * lane;
+    if (d < a.dh) { part[warp * a.dh + d] = o0.x; part[warp * a.dh + d + 1] = o0.y; }
+    if (d + 64 < a.dh) { part[warp * a.dh + d + 64] = o1.x; part[warp * a.dh + d + 65] = o1.y; }
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < a.dh; d += blockDim.x) {
+    float acc = 0.f;
+#pragma unroll
+    for (int w = 0; w < kQ1Warps; ++w) acc += part[w * a.dh + d];
+    stf<BF16>(a.o, b * a.o_bs + h * a.dh + d, acc);
+  }
+}
+
+// grid: B*H blocks of 4 warps.  smem: q[dh] | do[dh] | part[4][dh] | red[4].  dq / dk / dv are fp32 (SIMT ABI).
+template <bool BF16>
+__global__ void __launch_bounds__(kQ1Warps * 32)
+attn_q1_bwd(const AttnDev a) {
+  extern __shared__ float sm[];
+  float* qs = sm;
+  float* gs = qs + a.dh;
+  float* part = gs + a.dh;
+  float* red = part + kQ1Warps * a.dh;
+  const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float dsum = 0.f;
+  for (int d = threadIdx.x; d < a.dh; d += blockDim.x) {
+    const float qv = ldf<BF16>(a.q, b * a.q_bs + h * a.dh + d);
+    const float gv = ldf<BF16>(a.dout, b * a.do_bs + h * a.dh + d);
+    const float ov = ldf<BF16>(a.o, b * a.o_bs + h * a.dh + d);
+    qs[d] = qv;
+    gs[d] = gv;
+    dsum = fmaf(gv, ov, dsum);
+  }
+  const float Di = block_reduce_q1(dsum, red, false);   // also publishes qs / gs
+  const float lse = a.lse[static_cast<long long>(b) * a.H + h];
+  const long long kb = b * a.k_bs + h * a.dh, vb = b * a.v_bs + h * a.dh;
+  const long long dkb = b * a.dk_bs + h * a.dh, dvb = b * a.dv_bs + h * a.dh;
+  const int d0 = 2 * lane, d1 = 2 * lane + 64;
+  const bool has0 = d0 < a.dh, has1 = d1 < a.dh;
+  float2 q0 = make_float2(0.f, 0.f), q1 = q0, g0 = q0, g1 = q0;
+  if (has0) { q0 = make_float2(qs[d0], qs[d0 + 1]); g0 = make_float2(gs[d0], gs[d0 + 1]); }
+  if (has1) { q1 = make_float2(qs[d1], qs[d1 + 1]); g1 = make_float2(gs[d1], gs[d1 + 1]); }
+  float2 dq0 = make_float2(0.f, 0.f), dq1 = dq0;
+  for (int j = warp; j < a.Nk; j += kQ1Warps) {
+    float2 k0 = make_float2(0.f, 0.f), k1 = k0, v0 = k0, v1 = k0;
+    if (has0) { k0 = ld2<BF16>(a.k, kb + j * a.k_rs + d0); v0 = ld2<BF16>(a.v, vb + j * a.v_rs + d0); }
+    if (has1) { k1 = ld2<BF16>(a.k, kb + j * a.k_rs + d1); v1 = ld2<BF16>(a.v, vb + j * a.v_rs + d1); }
+    float s = q0.x * k0.x + q0.y * k0.y + q1.x * k1.x + q1.y * k1.y;
+    float dp = g0.x * v0.x + g0.y * v0.y + g1.x * v1.x + g1.y * v1.y;
+    s = warp_sum(s);
+    dp = warp_sum(dp);
+    const float pj = expf(s * a.scale - lse);
+    const float ds = pj * (dp - Di) * a.scale;
+    if (has0) {
+      *reinterpret_cast<float2*>(a.dk + dkb + j * a.dk_rs + d0) = make_float2(ds * q0.x, ds * q0.y);
+      *reinterpret_cast<float2*>(a.dv + dvb + j * a.dv_rs + d0) = make_float2(pj * g0.x, pj * g0.y);
+      dq0.x = fmaf(ds, k0.x, dq0.x); dq0.y = fmaf(ds, k0.y, dq0.y);
+    }
+    if (has1) {
+      *reinterpret_cast<float2*>(a.dk + dkb + j * a.dk_rs + d1) = make_float2(ds * q1.x, ds * q1.y);
+      *reinterpret_cast<float2*>(a.dv + dvb + j * a.dv_rs + d1) = make_float2(pj * g1.x, pj * g1.y);
+      dq1.x = fmaf(ds, k1.x, dq1.x); dq1.y = fmaf(ds, k1.y, dq1.y);
+    }
+  }
+  if (has0) { part[warp * a.dh + d0] = dq0.x; part[warp * a.dh + d0 + 1] = dq0.y; }
+  if (has1) { part[warp * a.dh + d1] = dq1.x; part[warp * a.dh + d1 + 1] = dq1.y; }
+  __syncthreads();
+  for (int d = threadIdx.x; d < a.dh; d += blockDim.x) {
+    float acc = 0.f;
+#pragma unroll
+    for (int w = 0; w < kQ1Warps; ++w) acc += part[w * a.dh + d];
+    a.dq[b * a.dq_bs + h * a.dh + d] = acc;
+  }
+}
+
+// single-query shapes these kernels take: head_dim even and <= 128, 8-byte aligned fp32 gradient rows
+bool q1_ok(const vitb_attn_params* p) {
+  return p->Nq == 1 && p->head_dim % 2 == 0 && p->head_dim <= 128 && p->k_row_stride % 2 == 0 && p->v_row_stride % 2 == 0 &&
+         p->k_batch_stride % 2 == 0 && p->v_batch_stride % 2 == 0;
+}
+
 }  // namespace
 
 extern "C" int vitb_attn_fwd_simt(const vitb_attn_params* p, void* stream_) {
@@ -199,13 +358,28 @@ extern "C" int vitb_attn_fwd_simt(const vitb_attn_params* p, void* stream_) {
   VITB_REQUIRE(p && p->struct_bytes == (int)sizeof(vitb_attn_params), VITB_ERR_BAD_ARG, "attn_fwd_simt: ABI mismatch");
   if (p->B == 0 || p->Nq == 0) return VITB_OK;
   VITB_REQUIRE(p->q && p->k && p->v && p->o, VITB_ERR_BAD_ARG, "attn_fwd_simt: null tensor");
-  VITB_REQUIRE(p->Nk >= 1 && p->Nk <= 32 * kMaxKT, VITB_ERR_UNSUPPORTED_SHAPE, "attn_fwd_simt: Nk=%d (max %d)", p->Nk, 32 * kMaxKT);
+  VITB_REQUIRE(p->Nk >= 1, VITB_ERR_UNSUPPORTED_SHAPE, "attn_fwd_simt: Nk=%d", p->Nk);
   AttnDev a{};
   a.q = p->q; a.k = p->k; a.v = p->v; a.o = p->o; a.lse = p->lse;
   a.q_bs = p->q_batch_stride; a.q_rs = p->q_row_stride; a.k_bs = p->k_batch_stride; a.k_rs = p->k_row_stride;
   a.v_bs = p->v_batch_stride; a.v_rs = p->v_row_stride; a.o_bs = p->o_batch_stride; a.o_rs = p->o_row_stride;
   a.B = p->B; a.H = p->H; a.Nq = p->Nq; a.Nk = p->Nk; a.dh = p->head_dim;
   a.scale = 1.0f / sqrtf((float)p->head_dim);
+  if (q1_ok(p)) {
+    const size_t sm1 = sizeof(float) * ((size_t)a.dh + a.Nk + kQ1Warps * a.dh + kQ1Warps);
+    VITB_REQUIRE(sm1 <= 200 * 1024, VITB_ERR_UNSUPPORTED_SHAPE, "attn_q1_fwd: Nk=%d", p->Nk);
+    cudaStream_t s1 = reinterpret_cast<cudaStream_t>(stream_);
+    if (p->dtype == VITB_BF16) {
+      VITB_CUDA_CHECK(cudaFuncSetAttribute(attn_q1_fwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
+      attn_q1_fwd<true><<<p->B * p->H, kQ1Warps * 32, sm1, s1>>>(a);
+    } else {
+      VITB_CUDA_CHECK(cudaFuncSetAttribute(attn_q1_fwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
+      attn_q1_fwd<false><<<p->B * p->H, kQ1Warps * 32, sm1, s1>>>(a);
+    }
+    VITB_LAUNCH_CHECK("attn_q1_fwd");
+    return VITB_OK;
+  }
+  VITB_REQUIRE(p->Nk <= 32 * kMaxKT, VITB_ERR_UNSUPPORTED_SHAPE, "attn_fwd_simt: Nk=%d (max %d)", p->Nk, 32 * kMaxKT);
   const int Ns = p->Nk | 1;
   const size_t smem = sizeof(float) * (2 * (size_t)a.dh * Ns + kWarps * (a.dh + Ns));
   VITB_REQUIRE(smem <= 227 * 1024, VITB_ERR_UNSUPPORTED_SHAPE, "attn_fwd_simt: needs %zu B of shared memory", smem);
@@ -242,6 +416,15 @@ extern "C" int vitb_attn_bwd_simt(const vitb_attn_params* p, void* stream_) {
   a.dq = reinterpret_cast<float*>(p->dq); a.dk = reinterpret_cast<float*>(p->dk); a.dv = reinterpret_cast<float*>(p->dv);
   a.dq_bs = p->dq_batch_stride; a.dq_rs = p->dq_row_stride; a.dk_bs = p->dk_batch_stride; a.dk_rs = p->dk_row_stride;
   a.dv_bs = p->dv_batch_stride; a.dv_rs = p->dv_row_stride;
+  if (q1_ok(p) && p->dk_row_stride % 2 == 0 && p->dv_row_stride % 2 == 0 && p->dk_batch_stride % 2 == 0 &&
+      p->dv_batch_stride % 2 == 0) {
+    const size_t sm1 = sizeof(float) * (2 * (size_t)a.dh + kQ1Warps * a.dh + kQ1Warps);
+    cudaStream_t s1 = reinterpret_cast<cudaStream_t>(stream_);
+    if (p->dtype == VITB_BF16) attn_q1_bwd<true><<<p->B * p->H, kQ1Warps * 32, sm1, s1>>>(a);
+    else attn_q1_bwd<false><<<p->B * p->H, kQ1Warps * 32, sm1, s1>>>(a);
+    VITB_LAUNCH_CHECK("attn_q1_bwd");
+    return VITB_OK;
+  }
   // key chunk so that 4 transposed [dh][chunk] arrays + per-warp rows fit in shared memory
   int chunk = p->Nk;
   for (;;) {

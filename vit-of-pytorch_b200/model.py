@@ -168,8 +168,7 @@ class Encoder(nn.Module):
     def forward(self, x, pos_added=False, norm_rows=None):
         out = x if pos_added else self.pos_embedding(x)
         layers = list(self.encoder_layers)
-        # the class-token-only last block uses the asymmetric (1 query x N keys) CUDA-core attention: <= 320 keys
-        row0_only = norm_rows == 0 and len(layers) > 0 and F.get_precision() == "bf16" and out.shape[1] <= 320
+        row0_only = norm_rows == 0 and len(layers) > 0 and F.get_precision() == "bf16"
         for layer in (layers[:-1] if row0_only else layers):
             out = layer(out)
         if row0_only:
