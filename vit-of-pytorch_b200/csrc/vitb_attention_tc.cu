@@ -36,12 +36,7 @@ struct AttnTc {
   int H;
   float scale;       // 1/sqrt(dh)
   float scale_log2;  // scale * log2(e)
-  __nv_bfloat16* o;
-  long long o_bs, o_rs;
-  float* lse;  // [B,H,N]
-  // backward (q, k, v, o and dO arrive through tensor maps)
-  __nv_bfloat16 *dq, *dk, *dv;
-  long long dq_bs, dq_rs, dk_bs, dk_rs, dv_bs, dv_rs;
+  float* lse;  // [B,H,N]   (q, k, v, o, dO and the gradients move through tensor maps)
 };
 
 // byte offset of the 16-byte unit holding keys [8u, 8u+8) of row r inside one 128B-swizzled chunk
@@ -109,17 +104,17 @@ __device__ __forceinline__ float chunk_max(const uint32_t (&v)[32], int c0, int 
   return m;
 }
 
-__device__ __forceinline__ void st_row64_bf16(__nv_bfloat16* dst32, const uint32_t (&v)[32], float scale) {
-  uint4* d = reinterpret_cast<uint4*>(dst32);
+
+// this thread's 32 of the 64 head-dim columns of row r -> bf16 -> a 128B-swizzled [128 rows x 64] staging tile that a
+// TMA store then writes out (whole 128-byte rows, rows past the token count clipped by the tensor map)
+__device__ __forceinline__ void stage_row32_bf16(uint32_t tile, int r, int half, const uint32_t (&v)[32], float scale) {
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    uint4 w;
-    w.x = pack_bf16x2(__uint_as_float(v[8 * u + 0]) * scale, __uint_as_float(v[8 * u + 1]) * scale);
-    w.y = pack_bf16x2(__uint_as_float(v[8 * u + 2]) * scale, __uint_as_float(v[8 * u + 3]) * scale);
-    w.z = pack_bf16x2(__uint_as_float(v[8 * u + 4]) * scale, __uint_as_float(v[8 * u + 5]) * scale);
-    w.w = pack_bf16x2(__uint_as_float(v[8 * u + 6]) * scale, __uint_as_float(v[8 * u + 7]) * scale);
-    d[u] = w;
-  }
+  for (int u = 0; u < 4; ++u)
+    st_shared_v4(tile + swz_unit(r, half * 4 + u),
+                 pack_bf16x2(__uint_as_float(v[8 * u + 0]) * scale, __uint_as_float(v[8 * u + 1]) * scale),
+                 pack_bf16x2(__uint_as_float(v[8 * u + 2]) * scale, __uint_as_float(v[8 * u + 3]) * scale),
+                 pack_bf16x2(__uint_as_float(v[8 * u + 4]) * scale, __uint_as_float(v[8 * u + 5]) * scale),
+                 pack_bf16x2(__uint_as_float(v[8 * u + 6]) * scale, __uint_as_float(v[8 * u + 7]) * scale));
 }
 
 // ================================================================================================
@@ -127,7 +122,8 @@ __device__ __forceinline__ void st_row64_bf16(__nv_bfloat16* dst32, const uint32
 // ================================================================================================
 __global__ void __launch_bounds__(kAttnThreads)
 attn_fwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-            const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnTc a) {
+            const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
+            const __grid_constant__ AttnTc a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   const int NK = a.NK;
@@ -252,14 +248,18 @@ attn_fwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     uint32_t v[32];
     tmem_ld_32x32b_x32(trow + half * 32, v);   // this thread's 32 of the 64 head-dim columns
     tmem_ld_wait();
-    if (row < a.N) {
-      st_row64_bf16(a.o + b * a.o_bs + static_cast<long long>(row) * a.o_rs + h * DH + half * 32, v, 1.0f / sum);
-      if (a.lse && half == 0) a.lse[(static_cast<long long>(b) * a.H + h) * a.N + row] = mx * a.scale + logf(sum);
-    }
+    stage_row32_bf16(sP_u, r, half, v, 1.0f / sum);   // the P image is dead: the PV MMA has retired
+    if (row < a.N && a.lse && half == 0) a.lse[(static_cast<long long>(b) * a.H + h) * a.N + row] = mx * a.scale + logf(sum);
   }
+  fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
+  if (tid == 0) {   // O tile [128 x 64] leaves as one TMA store (rows >= N clipped)
+    tma_store_3d(&tmO, sP_u, h * DH, row0, b);
+    bulk_commit();
+    bulk_wait_all();
+  }
+  if (warp == 0) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem_base, 256); }
 }
 
 // ================================================================================================
@@ -513,7 +513,9 @@ __device__ __forceinline__ float dot8_bf16(const uint4& x, const uint4& y) {
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
              const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
-             const __grid_constant__ CUtensorMap tmO, const __grid_constant__ AttnTc a) {
+             const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmDQ,
+             const __grid_constant__ CUtensorMap tmDK, const __grid_constant__ CUtensorMap tmDV,
+             const __grid_constant__ AttnTc a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   const int NK = a.NK;
@@ -727,34 +729,45 @@ attn_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       uint32_t v[32];
       tmem_ld_32x32b_x32(trow + half * 32, v);
       tmem_ld_wait();
-      if (row < a.N)
-        st_row64_bf16(a.dq + b * a.dq_bs + static_cast<long long>(row) * a.dq_rs + h * DH + half * 32, v, a.scale);
+      stage_row32_bf16(sO_t, r, half, v, a.scale);   // this tile's O buffer is dead once D_i is known
     }
+    fence_proxy_async_smem();
     // the next query tile overwrites sP and TMEM[0,256): wait until every MMA of this tile (dK included)
     // has retired, and until all warps have drained dQ from TMEM
     mbar_wait(bar_fin, ph);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (tid == 0) {   // dQ tile [128 x 64] leaves as one TMA store (rows >= N clipped)
+      tma_store_3d(&tmDQ, sO_t, h * DH, row0, b);
+      bulk_commit();
+    }
   }
   // dK, dV: TMEM lane = key within the M tile; the two threads of a lane split the 64 head-dim columns
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt) {
     if (mt < mtiles) {
-      const int key = mt * 128 + r;
       uint32_t vk[32], vv[32];
       tmem_ld_32x32b_x32(trow + 256u + static_cast<uint32_t>(mt * 64 + half * 32), vk);
       tmem_ld_32x32b_x32(trow + 384u + static_cast<uint32_t>(mt * 64 + half * 32), vv);
       tmem_ld_wait();
-      if (key < a.N) {
-        st_row64_bf16(a.dk + b * a.dk_bs + static_cast<long long>(key) * a.dk_rs + h * DH + half * 32, vk, a.scale);
-        st_row64_bf16(a.dv + b * a.dv_bs + static_cast<long long>(key) * a.dv_rs + h * DH + half * 32, vv, 1.0f);
-      }
+      // every MMA has retired, so the P / dS image is free: it stages the dK and dV tiles of both M tiles
+      stage_row32_bf16(sP_u + (2 * mt) * kChunkBytes, r, half, vk, a.scale);
+      stage_row32_bf16(sP_u + (2 * mt + 1) * kChunkBytes, r, half, vv, 1.0f);
     }
   }
+  fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+  if (tid == 0) {
+    for (int mt = 0; mt < mtiles; ++mt) {
+      tma_store_3d(&tmDK, sP_u + (2 * mt) * kChunkBytes, h * DH, mt * 128, b);
+      tma_store_3d(&tmDV, sP_u + (2 * mt + 1) * kChunkBytes, h * DH, mt * 128, b);
+    }
+    bulk_commit();
+    bulk_wait_all();   // dQ stores included: shared memory must outlive the reads
+  }
+  if (warp == 0) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
 int make_head_map(CUtensorMap* m, const void* base, int H, int N, int B, long long row_stride, long long batch_stride,
@@ -843,15 +856,16 @@ extern "C" int vitb_attn_fwd_tc(const vitb_attn_params* p, void* stream_) {
   a.N = N; a.NK = NK; a.H = p->H;
   a.scale = 1.0f / sqrtf((float)DH);
   a.scale_log2 = a.scale * 1.4426950408889634f;
-  a.o = reinterpret_cast<__nv_bfloat16*>(p->o); a.o_bs = p->o_batch_stride; a.o_rs = p->o_row_stride;
   a.lse = p->lse;
   const int kv_bytes = NK * 128, nchunks = (NK + 63) / 64;
   const int u_bytes = (kChunkBytes + kv_bytes) > nchunks * kChunkBytes ? (kChunkBytes + kv_bytes) : nchunks * kChunkBytes;
   const int smem = kv_bytes + u_bytes + 64 + 4 * 128 * 4 + 1024;
   VITB_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   dim3 grid((N + 127) / 128, p->H, p->B);
+  CUtensorMap to;
+  if ((st = make_head_map(&to, p->o, p->H, N, p->B, p->o_row_stride, p->o_batch_stride, 128)) != VITB_OK) return st;
   VITB_CUDA_CHECK(vitb_launch(attn_fwd_tc, grid, dim3(kAttnThreads), smem, reinterpret_cast<cudaStream_t>(stream_), tq, tk,
-                              tv, a));
+                              tv, to, a));
   VITB_LAUNCH_CHECK("attn_fwd_tc");
   return VITB_OK;
 }
@@ -877,9 +891,6 @@ extern "C" int vitb_attn_bwd_tc(const vitb_attn_params* p, void* stream_) {
   a.scale = 1.0f / sqrtf((float)DH);
   a.scale_log2 = a.scale * 1.4426950408889634f;
   a.lse = p->lse;
-  a.dq = reinterpret_cast<__nv_bfloat16*>(p->dq); a.dq_bs = p->dq_batch_stride; a.dq_rs = p->dq_row_stride;
-  a.dk = reinterpret_cast<__nv_bfloat16*>(p->dk); a.dk_bs = p->dk_batch_stride; a.dk_rs = p->dk_row_stride;
-  a.dv = reinterpret_cast<__nv_bfloat16*>(p->dv); a.dv_bs = p->dv_batch_stride; a.dv_rs = p->dv_row_stride;
   CUtensorMap to;
   if ((st = make_head_map(&to, p->o, p->H, N, p->B, p->o_row_stride, p->o_batch_stride, 128)) != VITB_OK) return st;
   const int kv_bytes = NK * 128, mtiles = (NK + 127) / 128, nchunks = 2 * mtiles, qtiles = (N + 127) / 128;
@@ -888,8 +899,14 @@ extern "C" int vitb_attn_bwd_tc(const vitb_attn_params* p, void* stream_) {
   VITB_REQUIRE(smem <= 227 * 1024, VITB_ERR_UNSUPPORTED_SHAPE, "attn_bwd_tc: %d B of shared memory", smem);
   VITB_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   dim3 grid(p->H, p->B);
+  VITB_REQUIRE(p->dq_batch_stride % 8 == 0 && p->dk_batch_stride % 8 == 0 && p->dv_batch_stride % 8 == 0,
+               VITB_ERR_UNSUPPORTED_SHAPE, "attn_bwd_tc: gradient batch strides %% 8");
+  CUtensorMap tdq, tdk, tdv;
+  if ((st = make_head_map(&tdq, p->dq, p->H, N, p->B, p->dq_row_stride, p->dq_batch_stride, 128)) != VITB_OK) return st;
+  if ((st = make_head_map(&tdk, p->dk, p->H, N, p->B, p->dk_row_stride, p->dk_batch_stride, 128)) != VITB_OK) return st;
+  if ((st = make_head_map(&tdv, p->dv, p->H, N, p->B, p->dv_row_stride, p->dv_batch_stride, 128)) != VITB_OK) return st;
   VITB_CUDA_CHECK(vitb_launch(attn_bwd_tc, grid, dim3(kAttnThreads), smem, reinterpret_cast<cudaStream_t>(stream_), tq, tk,
-                              tv, tdo, to, a));
+                              tv, tdo, to, tdq, tdk, tdv, a));
   VITB_LAUNCH_CHECK("attn_bwd_tc");
   return VITB_OK;
 }

@@ -157,9 +157,61 @@ __device__ __forceinline__ float ld_shared_f1(uint32_t addr) {
 //   RES: 0 none, 1 fp32 residual, 2 bf16 residual.   ACC: fp32 red.global accumulation.
 // FULL: all 32 rows and all 32 columns of the chunk are inside the matrix (the common case: no per-row
 // predicates, running row pointers instead of a 64-bit multiply per access).
+// Side operand of the staged epilogue (the residual, or the aux tensor of GELU_BWD / MUL_AUX), kept in its raw
+// form: lane (row%4, 4 columns) holds 8 bytes (bf16) or 16 bytes (fp32) for each of its 8 rows.
+#pragma nv_diag_suppress 177   // members unused in the instantiations without a side operand
+template <bool OUT_BF16, int EPI, int RES>
+struct SideOf {
+  static constexpr bool HAS = (RES != 0 || EPI == VITB_EPI_GELU_BWD);
+  static constexpr bool BF16 = (EPI == VITB_EPI_GELU_BWD) ? OUT_BF16 : (RES == 2);
+  static constexpr int ESIZE = BF16 ? 2 : 4;
+  __device__ static __forceinline__ const void* base(const GemmDev& p) { return (EPI == VITB_EPI_GELU_BWD) ? p.aux : p.residual; }
+  __device__ static __forceinline__ long long ld(const GemmDev& p) { return (EPI == VITB_EPI_GELU_BWD) ? p.ldaux : p.ldr; }
+  __device__ static __forceinline__ uint4 load(const char* sp) {
+    if constexpr (BF16) {
+      const uint2 u = *reinterpret_cast<const uint2*>(sp);
+      return make_uint4(u.x, u.y, 0u, 0u);
+    } else {
+      return *reinterpret_cast<const uint4*>(sp);
+    }
+  }
+  __device__ static __forceinline__ float4 value(const uint4& r) {
+    if constexpr (BF16) return make_float4(bf16_lo(r.x), bf16_hi(r.x), bf16_lo(r.y), bf16_hi(r.y));
+    else return make_float4(__uint_as_float(r.x), __uint_as_float(r.y), __uint_as_float(r.z), __uint_as_float(r.w));
+  }
+};
+#pragma nv_diag_default 177
+
+// All 8 side loads of one chunk (predicated; absent elements read as zero).  Used for the first chunk of a tile,
+// BEFORE the accumulator barrier is waited on: the side operand does not depend on the MMA.
+template <bool OUT_BF16, int EPI, int RES>
+__device__ __forceinline__ void side_fetch(const GemmDev& p, int lane, int row_base, int col0, bool lead_split,
+                                           uint4 (&raw)[8]) {
+  using S = SideOf<OUT_BF16, EPI, RES>;
+  if constexpr (S::HAS) {
+    const int rsub = lane >> 3;
+    const int col = col0 + (lane & 7) * 4;
+    const bool want = ((EPI == VITB_EPI_GELU_BWD) || lead_split) && col < p.N;
+    const long long lds = S::ld(p);
+    const char* sp = reinterpret_cast<const char*>(S::base(p)) + (static_cast<long long>(row_base + rsub) * lds + col) * S::ESIZE;
+    const long long sstep = 4 * lds * S::ESIZE;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      raw[it] = make_uint4(0u, 0u, 0u, 0u);
+      if (want && row_base + it * 4 + rsub < p.M) raw[it] = S::load(sp);
+      sp += sstep;
+    }
+  }
+}
+
+// `raw` holds this chunk's side operand on entry.  While the chunk is processed, each consumed slot is refilled
+// with the same rows of the NEXT chunk (columns next_col0 .., or none when next_col0 < 0): the loads fly during
+// the rest of this chunk and the next chunk's TMEM read / staging, with no extra registers — the eight warps of
+// the epilogue cannot hide HBM latency by occupancy (round-1 ncu: GELU' GEMM at 31 % issue-active, 2.3 TB/s).
 template <bool OUT_BF16, int EPI, int RES, bool ACC, bool FULL>
 __device__ __forceinline__ void epi_vec_body(const GemmDev& p, uint32_t stg, int lane, int row_base, int col0,
-                                             bool lead_split) {
+                                             bool lead_split, uint4 (&raw)[8], int next_col0) {
+  using S = SideOf<OUT_BF16, EPI, RES>;
   const int rsub = lane >> 3;
   const int c4 = (lane & 7) * 4;
   const int col = col0 + c4;
@@ -168,27 +220,14 @@ __device__ __forceinline__ void epi_vec_body(const GemmDev& p, uint32_t stg, int
   if (p.bias != nullptr && lead_split && col_ok) bv = *reinterpret_cast<const float4*>(p.bias + col);
   float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);   // column sums of the stored values (bias gradients)
   const long long r0 = static_cast<long long>(row_base + rsub);
-  float4 side[8];
-  if constexpr (RES != 0 || EPI == VITB_EPI_GELU_BWD) {
-    constexpr bool SIDE_BF16 = (EPI == VITB_EPI_GELU_BWD) ? OUT_BF16 : (RES == 2);
-    const long long lds = (EPI == VITB_EPI_GELU_BWD) ? p.ldaux : p.ldr;
-    const char* sp = reinterpret_cast<const char*>((EPI == VITB_EPI_GELU_BWD) ? p.aux : p.residual) +
-                     (r0 * lds + col) * (SIDE_BF16 ? 2 : 4);
-    const long long sstep = 4 * lds * (SIDE_BF16 ? 2 : 4);
-    const bool want = (EPI == VITB_EPI_GELU_BWD) || lead_split;
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      side[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (want && col_ok && (FULL || row_base + it * 4 + rsub < p.M)) {
-        if constexpr (SIDE_BF16) {
-          const uint2 u = *reinterpret_cast<const uint2*>(sp);
-          side[it] = make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
-        } else {
-          side[it] = *reinterpret_cast<const float4*>(sp);
-        }
-      }
-      sp += sstep;
-    }
+  const char* spn = nullptr;      // this lane's first row of the next chunk's side operand
+  long long sstep = 0;
+  bool next_ok = false;
+  if constexpr (S::HAS) {
+    next_ok = next_col0 >= 0 && ((EPI == VITB_EPI_GELU_BWD) || lead_split) && (next_col0 + c4 < p.N);
+    const long long lds = S::ld(p);
+    spn = reinterpret_cast<const char*>(S::base(p)) + (r0 * lds + (next_col0 + c4)) * S::ESIZE;
+    sstep = 4 * lds * S::ESIZE;
   }
   char* dp = reinterpret_cast<char*>(p.D) + (r0 * p.ldd + col) * (OUT_BF16 ? 2 : 4);
   const long long dstep = 4 * p.ldd * (OUT_BF16 ? 2 : 4);
@@ -229,19 +268,23 @@ __device__ __forceinline__ void epi_vec_body(const GemmDev& p, uint32_t stg, int
           }
         }
       } else if constexpr (EPI == VITB_EPI_GELU_BWD) {
+        const float4 sd = S::value(raw[it]);
         if (p.aux_grad) {
-          v.x *= side[it].x; v.y *= side[it].y; v.z *= side[it].z; v.w *= side[it].w;
+          v.x *= sd.x; v.y *= sd.y; v.z *= sd.z; v.w *= sd.w;
         } else if constexpr (OUT_BF16) {
           float g, d0, d1, d2, d3;
-          gelu_fast(side[it].x, g, d0); gelu_fast(side[it].y, g, d1);
-          gelu_fast(side[it].z, g, d2); gelu_fast(side[it].w, g, d3);
+          gelu_fast(sd.x, g, d0); gelu_fast(sd.y, g, d1);
+          gelu_fast(sd.z, g, d2); gelu_fast(sd.w, g, d3);
           v.x *= d0; v.y *= d1; v.z *= d2; v.w *= d3;
         } else {
-          v.x *= gelu_erf_grad(side[it].x); v.y *= gelu_erf_grad(side[it].y);
-          v.z *= gelu_erf_grad(side[it].z); v.w *= gelu_erf_grad(side[it].w);
+          v.x *= gelu_erf_grad(sd.x); v.y *= gelu_erf_grad(sd.y);
+          v.z *= gelu_erf_grad(sd.z); v.w *= gelu_erf_grad(sd.w);
         }
       }
-      if constexpr (RES != 0) { v.x += side[it].x; v.y += side[it].y; v.z += side[it].z; v.w += side[it].w; }
+      if constexpr (RES != 0) {
+        const float4 sd = S::value(raw[it]);
+        v.x += sd.x; v.y += sd.y; v.z += sd.z; v.w += sd.w;
+      }
       cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
       if constexpr (OUT_BF16) {
         uint2 o;
@@ -251,6 +294,10 @@ __device__ __forceinline__ void epi_vec_body(const GemmDev& p, uint32_t stg, int
         if constexpr (ACC) atomicAdd(reinterpret_cast<float4*>(dp), v);
         else *reinterpret_cast<float4*>(dp) = v;
       }
+    }
+    if constexpr (S::HAS) {   // slot `it` is consumed: refill it with the same row of the next chunk
+      if (next_ok && (FULL || row_base + it * 4 + rsub < p.M)) raw[it] = S::load(spn);
+      spn += sstep;
     }
     sa += 4 * (kStgStride * 4);
     dp += dstep;
@@ -267,11 +314,11 @@ __device__ __forceinline__ void epi_vec_body(const GemmDev& p, uint32_t stg, int
 
 template <bool OUT_BF16, int EPI, int RES, bool ACC>
 __device__ __forceinline__ void epi_vec(const GemmDev& p, uint32_t stg, int lane, int row_base, int col0,
-                                        bool lead_split) {
+                                        bool lead_split, uint4 (&raw)[8], int next_col0) {
   if (row_base + 32 <= p.M && col0 + 32 <= p.N)   // warp-uniform
-    epi_vec_body<OUT_BF16, EPI, RES, ACC, true>(p, stg, lane, row_base, col0, lead_split);
+    epi_vec_body<OUT_BF16, EPI, RES, ACC, true>(p, stg, lane, row_base, col0, lead_split, raw, next_col0);
   else
-    epi_vec_body<OUT_BF16, EPI, RES, ACC, false>(p, stg, lane, row_base, col0, lead_split);
+    epi_vec_body<OUT_BF16, EPI, RES, ACC, false>(p, stg, lane, row_base, col0, lead_split, raw, next_col0);
 }
 
 
@@ -544,6 +591,7 @@ vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     // measured (profiles/gemm_bench_r01.txt): the register-layout epilogue wins for plain / bias / GELU outputs,
     // but GELU' is faster with coalesced pre-activation loads in the staged layout
     const bool tma_path = p.tma_store != 0 && (mode == 2 || mode == 4);
+    uint4 side_raw[8];                            // staged epilogue: side operand of the chunk in flight (see epi_vec_body)
     const uint32_t tbuf = (stg + 511u) & ~511u;   // two 2 KiB 64B-swizzled tiles inside this warp's staging slice
     int tma_which = 0;
     if (tma_path && lane == 0) { tma_prefetch_desc(&tmD); if (p.D2 != nullptr) tma_prefetch_desc(&tmD2); }
@@ -551,15 +599,30 @@ vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const TileCoord t = decode_tile(p, tile);
       const int n0 = t.n_blk * BN;
       const int row_base = t.m_blk * BM + q * 32;
-      mbar_wait(tfull0 + 8 * acc, acc_phase);
-      tc_fence_after();
       // bias-type terms are added exactly once: by the split that owns the first k-block
       const bool lead_split = (t.g0 == 0);
       const int half = (warp - kEpiWarp0) >> 2;  // which half of the tile's columns this warp drains
+      {   // the side operand of this warp's first chunk is requested before the accumulator is waited for
+        const int colf = n0 + half * (BN / 64) * 32;
+        if (colf < p.N) {
+          switch (mode) {
+            case 3: side_fetch<true, VITB_EPI_GELU_BWD, 0>(p, lane, row_base, colf, lead_split, side_raw); break;
+            case 5: side_fetch<true, VITB_EPI_NONE, 1>(p, lane, row_base, colf, lead_split, side_raw); break;
+            case 6: side_fetch<true, VITB_EPI_NONE, 2>(p, lane, row_base, colf, lead_split, side_raw); break;
+            case 8: side_fetch<false, VITB_EPI_GELU_BWD, 0>(p, lane, row_base, colf, lead_split, side_raw); break;
+            case 10: side_fetch<false, VITB_EPI_NONE, 1>(p, lane, row_base, colf, lead_split, side_raw); break;
+            case 11: side_fetch<false, VITB_EPI_NONE, 2>(p, lane, row_base, colf, lead_split, side_raw); break;
+            default: break;
+          }
+        }
+      }
+      mbar_wait(tfull0 + 8 * acc, acc_phase);
+      tc_fence_after();
 #pragma unroll 1
       for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
         const int col0 = n0 + c * 32;
         if (col0 >= p.N) break;
+        const int next_col0 = (c + 1 < (half + 1) * (BN / 64) && col0 + 32 < p.N) ? col0 + 32 : -1;
         uint32_t r[32];
         tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                                static_cast<uint32_t>(acc * BN + c * 32), r);
@@ -573,17 +636,17 @@ vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         for (int j = 0; j < 16; ++j) st_shared_v2(stg + lane * (kStgStride * 4) + j * 8, r[2 * j], r[2 * j + 1]);
         __syncwarp();
         switch (mode) {
-          case 1: epi_vec<false, VITB_EPI_NONE, 0, true>(p, stg, lane, row_base, col0, lead_split); break;
-          case 2: epi_vec<true, VITB_EPI_GELU, 0, false>(p, stg, lane, row_base, col0, lead_split); break;
-          case 3: epi_vec<true, VITB_EPI_GELU_BWD, 0, false>(p, stg, lane, row_base, col0, lead_split); break;
-          case 4: epi_vec<true, VITB_EPI_NONE, 0, false>(p, stg, lane, row_base, col0, lead_split); break;
-          case 5: epi_vec<true, VITB_EPI_NONE, 1, false>(p, stg, lane, row_base, col0, lead_split); break;
-          case 6: epi_vec<true, VITB_EPI_NONE, 2, false>(p, stg, lane, row_base, col0, lead_split); break;
-          case 7: epi_vec<false, VITB_EPI_GELU, 0, false>(p, stg, lane, row_base, col0, lead_split); break;
-          case 8: epi_vec<false, VITB_EPI_GELU_BWD, 0, false>(p, stg, lane, row_base, col0, lead_split); break;
-          case 9: epi_vec<false, VITB_EPI_NONE, 0, false>(p, stg, lane, row_base, col0, lead_split); break;
-          case 10: epi_vec<false, VITB_EPI_NONE, 1, false>(p, stg, lane, row_base, col0, lead_split); break;
-          case 11: epi_vec<false, VITB_EPI_NONE, 2, false>(p, stg, lane, row_base, col0, lead_split); break;
+          case 1: epi_vec<false, VITB_EPI_NONE, 0, true>(p, stg, lane, row_base, col0, lead_split, side_raw, next_col0); break;
+          case 2: epi_vec<true, VITB_EPI_GELU, 0, false>(p, stg, lane, row_base, col0, lead_split, side_raw, next_col0); break;
+          case 3: epi_vec<true, VITB_EPI_GELU_BWD, 0, false>(p, stg, lane, row_base, col0, lead_split, side_raw, next_col0); break;
+          case 4: epi_vec<true, VITB_EPI_NONE, 0, false>(p, stg, lane, row_base, col0, lead_split, side_raw, next_col0); break;
+          case 5: epi_vec<true, VITB_EPI_NONE, 1, false>(p, stg, lane, row_base, col0, lead_split, side_raw, next_col0); break;
+          case 6: epi_vec<true, VITB_EPI_NONE, 2, false>(p, stg, lane, row_base, col0, lead_split, side_raw, next_col0); break;
+          case 7: epi_vec<false, VITB_EPI_GELU, 0, false>(p, stg, lane, row_base, col0, lead_split, side_raw, next_col0); break;
+          case 8: epi_vec<false, VITB_EPI_GELU_BWD, 0, false>(p, stg, lane, row_base, col0, lead_split, side_raw, next_col0); break;
+          case 9: epi_vec<false, VITB_EPI_NONE, 0, false>(p, stg, lane, row_base, col0, lead_split, side_raw, next_col0); break;
+          case 10: epi_vec<false, VITB_EPI_NONE, 1, false>(p, stg, lane, row_base, col0, lead_split, side_raw, next_col0); break;
+          case 11: epi_vec<false, VITB_EPI_NONE, 2, false>(p, stg, lane, row_base, col0, lead_split, side_raw, next_col0); break;
           default: epi_generic(p, stg, lane, row_base, col0, lead_split); break;
         }
         __syncwarp();
@@ -735,6 +798,7 @@ vitb_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     const int q = warp & 3;
     const uint32_t stg = smem_u32(staging) + static_cast<uint32_t>((warp - kEpiWarp0) * kStagingFloats * 4);
     const uint32_t tempty_leader = mapa_shared(tempty0, 0);
+    uint4 no_side[8];   // accumulate mode has no side operand (never read)
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = pair; tile < total_tiles; tile += npairs) {
@@ -755,7 +819,7 @@ vitb_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 #pragma unroll
         for (int j = 0; j < 16; ++j) st_shared_v2(stg + lane * (kStgStride * 4) + j * 8, r[2 * j], r[2 * j + 1]);
         __syncwarp();
-        epi_vec<false, VITB_EPI_NONE, 0, true>(p, stg, lane, row_base, col0, lead_split);
+        epi_vec<false, VITB_EPI_NONE, 0, true>(p, stg, lane, row_base, col0, lead_split, no_side, -1);
         __syncwarp();
       }
       tc_fence_before();
