@@ -38,6 +38,15 @@ LR, TRAIN_STEPS, WARMUP_STEPS = 0.03, 15000, 500   # src/config.py:39-42 default
 WORKLOAD = "ViT-B/16 224px train step (fwd+bwd+SGD momentum 0.9, OneCycleLR), batch %d/GPU, C=100"
 
 
+_RESULT_FD = None
+
+
+def emit(result):
+    line = (json.dumps(result) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_RESULT_FD if _RESULT_FD is not None else 1, line)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -170,7 +179,7 @@ def run_reference(args, rank):
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -186,6 +195,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of one CUDA graph")
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON result: anything libraries print there while the job runs (NCCL's
+    # version banner at N > 1, for one) is sent to stderr instead
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -326,7 +341,7 @@ def main():
             "e2e": {"value": ips_e2e, "unit": "images/s", "h2d_bytes_per_step": img_h.numel() * 4 + lab_h.numel() * 8,
                     "d2h_bytes_per_step": 4, "last_loss": last},
             "gpu_launches": launches,
-            "roofline": {"bound": "tensor", "kernel": "vitb_gemm_kernel (tcgen05)", "achieved": ach,
+            "roofline": {"bound": "tensor", "kernel": "tcgen05 GEMMs: vitb_gemm_kernel + vitb_wgrad_pair_kernel (cta_group::2)", "achieved": ach,
                          "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tflops_sustained"],
                          "peak_source": pk["source"] + " sustained cuBLAS bf16", "traffic": gemm_traffic(),
                          "algorithmic_bytes_per_launch": gemm_bytes / max(1, len(recs)),
@@ -340,7 +355,7 @@ def main():
             cips, csec, threads = cpu_train_steps(2, 1)
             out["cpu_baseline"] = {"value": cips, "unit": "images/s", "cores": threads, "kind": "port",
                                    "sample": "2 timed steps of batch %d after 1 warm-up (oracle port, torch CPU fp32)" % CPU_SAMPLE_BATCH}
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
