@@ -101,3 +101,42 @@ def test_resvit_adamw_step_matches_torch_adamw_on_oracle_grads():
         delta_ref = p.detach() - g["state_dict"][k]
         delta = named[k].detach().cpu() - g["state_dict"][k]
         assert grad_close(delta, delta_ref, 5e-3, atol=2e-5), (k, rel_l2(delta, delta_ref))
+
+
+def test_input_prefetcher_delivers_batches_in_order_into_the_graph_buffers():
+    """Batches staged from pinned host memory on the side stream arrive in order, and with `into=` they land in the
+    static buffers a GraphedTrainStep captured (so the replay needs no further copy)."""
+    import vitb200
+    g = torch.Generator().manual_seed(11)
+    m = _tiny()
+    opt = vitb200.optim.FusedSGD(m.parameters(), lr=0.01, momentum=0.9)
+    img = torch.randn(8, 3, 64, 64, generator=g).cuda()
+    lab = torch.randint(0, 16, (8,), generator=g).cuda()
+    step = vitb200.train.GraphedTrainStep(m, opt, img, lab, warmup=1)
+    pre = vitb200.train.InputPrefetcher(img, lab, into=(step.images, step.labels))
+    host = [(torch.randn(8, 3, 64, 64, generator=g).pin_memory(), torch.randint(0, 16, (8,), generator=g).pin_memory())
+            for _ in range(5)]
+    with pytest.raises(RuntimeError):
+        pre.get()
+    pre.start(*host[0])
+    losses = []
+    for i in range(5):
+        x, y = pre.get()
+        assert x.data_ptr() == step.images.data_ptr()
+        if i + 1 < 5:
+            pre.start(*host[i + 1])
+        losses.append(step(x, y))
+        torch.cuda.synchronize()
+        assert torch.equal(step.images.cpu(), host[i][0]) and torch.equal(step.labels.cpu(), host[i][1])
+    assert all(torch.isfinite(l) for l in losses)
+    # without `into` the prefetcher owns the buffers it hands out
+    pre2 = vitb200.train.InputPrefetcher(img, lab)
+    pre2.start(*host[3]); pre2.start(*host[4])
+    with pytest.raises(RuntimeError):
+        pre2.start(*host[0])
+    a, _ = pre2.get()
+    torch.cuda.synchronize()
+    assert torch.equal(a.cpu(), host[3][0])
+    b, _ = pre2.get()
+    torch.cuda.synchronize()
+    assert torch.equal(b.cpu(), host[4][0])
