@@ -123,18 +123,18 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port on host cores
 # ---------------------------------------------------------------------------------------------------
-def cpu_train_steps(steps, warmup, batch=CPU_SAMPLE_BATCH):
+def cpu_train_steps(steps, warmup, batch=CPU_SAMPLE_BATCH, device="cpu", autocast=False):
     """fwd + bwd + SGD(momentum .9, lr .03) of ViT-B/16 in plain torch fp32 on the host (oracle port of
     src/model.py + src/train.py:20-24,154-158).  Returns (images/s, seconds per step, threads)."""
     from oracle import vit_init, vit_oracle
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     sd = vit_init.reference_state_dict(vit_init.arch_cfg(ARCH, IMG, CLASSES), seed=0, scaled=True)
-    params = {k: v.clone() for k, v in sd.items()}
+    params = {k: v.clone().to(device) for k, v in sd.items()}
     bufs = {}
     g = torch.Generator().manual_seed(1234)
-    img = torch.randn(batch, 3, IMG, IMG, generator=g)
-    labels = torch.randint(0, CLASSES, (batch,), generator=g)
+    img = torch.randn(batch, 3, IMG, IMG, generator=g).to(device)
+    labels = torch.randint(0, CLASSES, (batch,), generator=g).to(device)
     times = []
     probe = torch.optim.SGD([torch.zeros(1, requires_grad=True)], lr=LR, momentum=0.9)
     probe_sched = torch.optim.lr_scheduler.OneCycleLR(probe, max_lr=LR, pct_start=WARMUP_STEPS / TRAIN_STEPS,
@@ -151,7 +151,8 @@ def cpu_train_steps(steps, warmup, batch=CPU_SAMPLE_BATCH):
     for i in range(warmup + steps):
         t0 = time.perf_counter()
         leaf = {k: v.detach().requires_grad_(True) for k, v in params.items()}
-        loss = vit_oracle.vit_loss(img, labels, leaf)
+        with torch.autocast(device_type="cuda" if device != "cpu" else "cpu", dtype=torch.bfloat16, enabled=autocast):
+            loss = vit_oracle.vit_loss(img, labels, leaf)
         loss.backward()
         vit_oracle.sgd_momentum_step(params, {k: v.grad for k, v in leaf.items()}, bufs, lr_at(i), 0.9, first=(i == 0))
         float(loss.detach())
@@ -163,6 +164,16 @@ def cpu_train_steps(steps, warmup, batch=CPU_SAMPLE_BATCH):
 
 def run_reference(args, rank):
     if rank != 0:
+        return
+    if args.ref_device != "cpu":
+        # comparator only (SURVEY 8d "stock PyTorch GPU"): the same plain-torch port on the B200 through ATen / cuBLAS,
+        # full batch, optionally under autocast(bf16).  Not the reference arm the driver runs.
+        ips, sec, _ = cpu_train_steps(args.steps, args.warmup, batch=BATCH_PER_GPU, device=args.ref_device,
+                                      autocast=args.ref_autocast)
+        emit({"impl": "stock-torch-gpu", "metric": "train images/sec", "value": ips, "unit": "images/s", "n_gpus": 1,
+              "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+              "dtype": "bf16 autocast" if args.ref_autocast else "f32",
+              "config": {"workload": WORKLOAD % BATCH_PER_GPU, "launch": "oracle port (plain torch ops) on %s" % args.ref_device}})
         return
     ips, sec, threads = cpu_train_steps(args.steps, args.warmup)
     out = {
@@ -194,6 +205,8 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of one CUDA graph")
+    ap.add_argument("--ref-device", default="cpu", help="--impl reference only: 'cuda' times the plain-torch port on the GPU (comparator)")
+    ap.add_argument("--ref-autocast", action="store_true", help="--impl reference --ref-device cuda: under torch.autocast(bf16)")
     args = ap.parse_args()
     # stdout carries exactly ONE line, the JSON result: anything libraries print there while the job runs (NCCL's
     # version banner at N > 1, for one) is sent to stderr instead
