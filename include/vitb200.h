@@ -211,6 +211,33 @@ int vitb_token_mean_bwd(const float* dg, int dtype, int B, int N, int C, int res
 int vitb_select_rows(const void* a, const void* b, const float* index, uint32_t member_mask, int rows, int cols,
                      int dtype, void* out, void* stream);
 
+/* ---- input transform in front of the encoder --------------------------------------
+ * The per-sample CPU work of the reference's loaders — transforms.Compose([Resize(S), RandomHorizontalFlip(),
+ * ToTensor(), Normalize(mean, std)]) at src/data_loaders.py:36-48 (CIFAR-10), :69-82 (CIFAR-100), :102-114
+ * (ImageNet, Resize((S,S))) — on the device, bit-exact with torchvision + Pillow: the resize is Pillow's 8-bit
+ * bilinear resample (22-bit fixed-point weights, horizontal pass rounded to a byte before the vertical pass).
+ *
+ * vitb_resize_tables_host is HOST code (no device work): the windows and weights of one axis in_size -> out_size,
+ * Pillow's precompute_coeffs + normalize_coeffs_8bpc.  bounds_host [out_size, 2] = (first source index, taps),
+ * coeffs_host [out_size, ksize]; *ksize_host = taps per window.  With both table pointers NULL it only reports ksize.
+ * The caller uploads the tables once per (in_size, out_size) and keeps them on the device.
+ *
+ * vitb_image_prep: src [B,H,W,C] uint8 (C <= 4) -> any of
+ *   out_img  [B,C,out_h,out_w] fp32  — what the reference's loader yields and VisionTransformer.forward consumes,
+ *   cols_hi  [B*gh*gw, ldk] bf16     — the patch-embedding GEMM operand (same layout as vitb_im2col; cols_lo = the
+ *                                      bf16x3 low half); columns >= C*P*P are NOT written (zero them once),
+ *   out_u8   [B,out_h,out_w,C] uint8 — the resized bytes after the flip.
+ * x/y tables must be NULL exactly when that axis keeps its size (Pillow skips the pass).  flip [B] (optional):
+ * non-zero mirrors the width axis — the caller draws it (torch.rand(1) < 0.5 per image, as RandomHorizontalFlip does).
+ * lut [C,256] fp32: the normalised value of each byte, ((v/255) - mean_c)/std_c evaluated by the caller in the
+ * reference's arithmetic. */
+int vitb_resize_tables_host(int in_size, int out_size, int32_t* bounds_host, int32_t* coeffs_host,
+                            int coeffs_capacity, int* ksize_host);
+int vitb_image_prep(const uint8_t* src, int B, int H, int W, int C, int out_h, int out_w, const int32_t* xbounds,
+                    const int32_t* xcoeffs, int xksize, const int32_t* ybounds, const int32_t* ycoeffs, int yksize,
+                    const uint8_t* flip, const float* lut, float* out_img, int P, int ldk, void* cols_hi,
+                    void* cols_lo, uint8_t* out_u8, void* stream);
+
 /* ---- loss and optimizer ------------------------------------------------------------------------- */
 /* nn.CrossEntropyLoss (mean) — src/train.py:151,22; res-vit/model.py:550,681.
  * loss[0] = mean_b(lse_b - logits[b,label_b]); dlogits = (softmax - onehot)/B (optional). */

@@ -1,0 +1,89 @@
+"""Pins oracle/image_prep_oracle.py (the input transform in front of the encoder).
+
+Golden vectors: tests/golden/image_prep.npz, produced by oracle/make_golden_prep.py running the reference's own
+loader classes (src/data_loaders.py:62-124) through the installed torchvision / Pillow.  Bar: BIT-EXACT — the
+resize is integer arithmetic and the normalisation is a function of the resized byte."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import image_prep_oracle as O
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "image_prep.npz")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(GOLD)
+
+
+@pytest.mark.parametrize("case,src,size", [("cifar_train", "cifar_in", 224), ("cifar_eval", "cifar_in", 64),
+                                           ("inet_train", "inet_in", (64, 64))])
+def test_oracle_matches_reference_loader_output(gold, case, src, size):
+    order = gold[case + "_order"]
+    flip = gold[case + "_flip"] if case + "_flip" in gold.files else None
+    x = gold[src][order]
+    _, out = O.image_prep(x, size, flip=flip)
+    ref = gold[case + "_out"]
+    assert out.dtype == np.float32 and out.shape == ref.shape
+    assert np.array_equal(out, ref)
+
+
+def test_golden_flips_are_exercised(gold):
+    assert gold["cifar_train_flip"].any() or gold["inet_train_flip"].any()
+    assert not (gold["cifar_train_flip"].all() and gold["inet_train_flip"].all())
+
+
+def test_tables_upsampling_window_is_three_taps():
+    ksize, bounds, coeffs = O.resample_tables(32, 224)
+    assert ksize == 3 and bounds.shape == (224, 2) and coeffs.shape == (224, 3)
+    assert (bounds[:, 1] >= 1).all() and (bounds[:, 1] <= 3).all()
+    assert (bounds[:, 0] + bounds[:, 1] <= 32).all()
+    s = coeffs.sum(1)
+    assert (np.abs(s - (1 << O.PRECISION_BITS)) <= 2).all()      # fixed-point weights sum to one (rounding)
+
+
+def test_identity_and_constant_images():
+    rng = np.random.default_rng(1)
+    x = rng.integers(0, 256, (2, 17, 23, 3), dtype=np.uint8)
+    assert np.array_equal(O.resize_bilinear_u8(x, 17, 23), x)                  # neither pass runs
+    c = np.full((1, 9, 9, 3), 200, dtype=np.uint8)
+    assert (O.resize_bilinear_u8(c, 50, 31) == 200).all()
+
+
+def test_resize_target_matches_torchvision_rule():
+    assert O.resize_target(32, 32, 224) == (224, 224)
+    assert O.resize_target(375, 500, 224) == (224, 298)
+    assert O.resize_target(500, 333, 224) == (336, 224)
+    assert O.resize_target(75, 100, (64, 64)) == (64, 64)
+
+
+def test_against_live_torchvision_when_importable():
+    tv = pytest.importorskip("torchvision")
+    pil = pytest.importorskip("PIL.Image")
+    import torch
+    from torchvision.transforms import transforms
+
+    rng = np.random.default_rng(5)
+    for (h, w, size) in [(32, 32, 224), (32, 32, 384), (40, 30, 56), (7, 5, (96, 96)), (130, 97, (64, 80))]:
+        x = rng.integers(0, 256, (2, h, w, 3), dtype=np.uint8)
+        tf = transforms.Compose([transforms.Resize(size), transforms.ToTensor(),
+                                 transforms.Normalize([0.5, 0.5, 0.5], [0.5, 0.5, 0.5])])
+        ref = torch.stack([tf(pil.fromarray(im)) for im in x]).numpy()
+        _, out = O.image_prep(x, size)
+        assert np.array_equal(out, ref), (h, w, size)
+
+
+def test_patch_columns_is_the_conv_flattening():
+    import torch
+
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal((2, 3, 32, 48)).astype(np.float32)
+    w = rng.standard_normal((5, 3, 16, 16)).astype(np.float32)
+    cols = O.patch_columns(x, 16, ldk=776)
+    assert cols.shape == (2 * 2 * 3, 776) and (cols[:, 768:] == 0).all()
+    y = cols[:, :768] @ w.reshape(5, -1).T
+    ref = torch.nn.functional.conv2d(torch.from_numpy(x), torch.from_numpy(w), stride=16)
+    ref = ref.permute(0, 2, 3, 1).reshape(-1, 5).numpy()
+    assert np.allclose(y, ref, rtol=1e-4, atol=1e-4)

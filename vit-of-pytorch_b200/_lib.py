@@ -96,6 +96,12 @@ def check(status, what):
     LAUNCHES[0] += 1
 
 
+def check_host(status, what):
+    """Status check of a host-only entry point (launches nothing)."""
+    if status != 0:
+        raise VitbError("%s failed (%d): %s" % (what, status, last_error()))
+
+
 def stream_ptr(device=None):
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
@@ -178,6 +184,9 @@ _vitb_token_mean_fwd = _sig("vitb_token_mean_fwd", [_vp, _i, _i, _i, _i, _i, _vp
 _vitb_token_mean_bwd = _sig("vitb_token_mean_bwd", [_vp, _i, _i, _i, _i, _i, _vp, _vp])
 _vitb_select_rows = _sig("vitb_select_rows", [_vp, _vp, _vp, C.c_uint32, _i, _i, _i, _vp, _vp])
 _vitb_clip_coef = _sig("vitb_clip_coef", [_vp, _f, _vp, _vp, _vp])
+_vitb_resize_tables_host = _sig("vitb_resize_tables_host", [_i, _i, _vp, _vp, _i, C.POINTER(C.c_int)])
+_vitb_image_prep = _sig("vitb_image_prep", [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _i,
+                                            _vp, _vp, _vp, _vp])
 
 EXPORTED_SYMBOLS = [
     "vitb_version", "vitb_last_error", "vitb_device_check", "vitb_struct_size", "vitb_gemm", "vitb_layernorm_fwd",
@@ -186,4 +195,5 @@ EXPORTED_SYMBOLS = [
     "vitb_embed_bwd", "vitb_colsum", "vitb_cross_entropy", "vitb_sgd_momentum", "vitb_adamw",
     "vitb_sumsq", "vitb_clip_coef", "vitb_gelu_bwd", "vitb_router_decide_fwd", "vitb_router_decide_bwd",
     "vitb_token_mean_fwd", "vitb_token_mean_bwd", "vitb_select_rows", "vitb_colsum3",
+    "vitb_resize_tables_host", "vitb_image_prep",
 ]

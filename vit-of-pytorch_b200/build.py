@@ -20,6 +20,8 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC",
+    # host code only: the resize tables are double arithmetic that must round exactly as Pillow's C does
+    "-Xcompiler", "-ffp-contract=off",
     "--expt-relaxed-constexpr",
     "-Xptxas", "-v",
 ]

@@ -609,26 +609,60 @@ def attention(q, k, v, H):
 # --------------------------------------------------------------------------------------------------
 # patch embedding: Conv2d(3,D,P,P) + cls token + position embedding as one GEMM with a scatter epilogue
 # --------------------------------------------------------------------------------------------------
+class PatchColumns:
+    """The patch-embedding GEMM operand of a batch, produced without an fp32 image by
+    input_pipeline.DeviceImageTransform.patch_columns: hi (and lo in fp32 mode) are bf16 [B*gh*gw, ldk] with rows
+    (b, py, px) and k = (c, ph, pw) — exactly what vitb_im2col makes of the loader's fp32 batch."""
+
+    def __init__(self, hi, lo, batch, gh, gw, patch, channels):
+        self.hi, self.lo = hi, lo
+        self.batch, self.gh, self.gw, self.patch, self.channels = batch, gh, gw, patch, channels
+
+    @property
+    def shape(self):
+        """Shape of the image batch these columns were cut from: [B, C, gh*P, gw*P]."""
+        return (self.batch, self.channels, self.gh * self.patch, self.gw * self.patch)
+
+    @property
+    def device(self):
+        return self.hi.device
+
+    def to(self, device):
+        if torch.device(device) != self.hi.device:
+            raise L.VitbError("PatchColumns live on %s; re-create them on %s" % (self.hi.device, device))
+        return self
+
+
 class _PatchEmbed(torch.autograd.Function):
     @staticmethod
     def forward(ctx, img, conv_w, conv_b, cls_token, pos):
-        L.require_cuda(img, conv_w)
-        Bsz = img.shape[0]
         D, Cin, P, P2 = conv_w.shape
         if P != P2:
             raise L.VitbError("patch embedding needs square patches")
-        img = img.contiguous().float()
-        gh, gw = img.shape[2] // P, img.shape[3] // P
-        npatch = gh * gw
-        N = npatch + 1
         K = Cin * P * P
         fp32 = _fp32_mode()
-        hi, lo = ops.im2col(img, P, want_lo=fp32)
+        if isinstance(img, PatchColumns):
+            L.require_cuda(img.hi, conv_w)
+            if img.patch != P or img.channels != Cin:
+                raise L.VitbError("PatchColumns were cut for patch %d x %d channels, the embedding is %d x %d"
+                                  % (img.patch, img.channels, P, Cin))
+            if fp32 and img.lo is None:
+                raise L.VitbError("fp32 mode needs PatchColumns made in fp32 mode (low half missing)")
+            Bsz, gh, gw = img.batch, img.gh, img.gw
+            hi, lo = img.hi, (img.lo if fp32 else None)
+        else:
+            L.require_cuda(img, conv_w)
+            Bsz = img.shape[0]
+            img = img.contiguous().float()
+            gh, gw = img.shape[2] // P, img.shape[3] // P
+            hi, lo = ops.im2col(img, P, want_lo=fp32)
+        npatch = gh * gw
+        N = npatch + 1
         ldk = hi.shape[1]
         whi, wlo = SHADOW.get_padded_2d(conv_w, D, K, D, ldk, fp32)
         cols = [hi] + ([lo] if lo is not None else [])
         A, Bw = _pairs(cols, [whi] + ([wlo] if wlo is not None else []))
-        x = torch.empty((Bsz, N, D), dtype=F32, device=img.device)
+        x = torch.empty((Bsz, N, D), dtype=F32, device=hi.device)
         pos2 = pos.detach().reshape(-1, D)[:N].contiguous() if pos is not None else None
         ops.gemm(A, Bw, out=x.view(Bsz * N, D), bias=conv_b.detach() if conv_b is not None else None,
                  residual=pos2, row_remap_group=npatch)

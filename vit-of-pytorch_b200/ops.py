@@ -267,6 +267,73 @@ def im2col(img, P, *, want_lo=False):
     return hi, lo
 
 
+def resize_tables(in_size, out_size):
+    """Host tables of one resize axis (Pillow 8-bit bilinear): (ksize, bounds int32 [out,2], coeffs int32 [out,ksize])
+    as CPU tensors — vitb_resize_tables_host is host code inside the library, no device work."""
+    import ctypes as C
+    k = C.c_int(0)
+    L.check_host(L._vitb_resize_tables_host(in_size, out_size, None, None, 0, C.byref(k)), "vitb_resize_tables_host")
+    bounds = torch.zeros((out_size, 2), dtype=torch.int32)
+    coeffs = torch.zeros((out_size, k.value), dtype=torch.int32)
+    L.check_host(L._vitb_resize_tables_host(in_size, out_size, C.c_void_p(bounds.data_ptr()), C.c_void_p(coeffs.data_ptr()),
+                                            coeffs.numel(), C.byref(k)), "vitb_resize_tables_host")
+    return k.value, bounds, coeffs
+
+
+def image_prep(src, out_hw, xtab, ytab, lut, *, flip=None, want_img=True, P=None, want_lo=False, want_u8=False,
+               out_img=None, cols=None):
+    """src uint8 [B,H,W,C] (device) -> (img fp32 [B,C,oh,ow] | None, hi | None, lo | None, u8 | None).
+
+    xtab / ytab: (bounds, coeffs) device int32 tensors from resize_tables, or None when that axis keeps its size.
+    cols=(hi, lo): persistent, caller-zeroed patch-operand buffers to write into (their padding columns stay zero)."""
+    L.require_cuda(src, lut, flip)
+    if src.dtype != torch.uint8 or src.dim() != 4 or not src.is_contiguous():
+        raise L.VitbError("image_prep: src must be contiguous uint8 [B,H,W,C]")
+    B, H, W, Cn = src.shape
+    oh, ow = out_hw
+    if lut.dtype != torch.float32 or tuple(lut.shape) != (Cn, 256) or not lut.is_contiguous():
+        raise L.VitbError("image_prep: lut must be contiguous fp32 [C,256]")
+    if flip is not None and (flip.dtype != torch.uint8 or flip.numel() != B or not flip.is_contiguous()):
+        raise L.VitbError("image_prep: flip must be contiguous uint8 [B]")
+    for name, tab, n_out in (("x", xtab, ow), ("y", ytab, oh)):
+        if tab is not None:
+            b, c = tab
+            L.require_cuda(b, c)
+            if (b.dtype != torch.int32 or c.dtype != torch.int32 or tuple(b.shape) != (n_out, 2) or c.shape[0] != n_out
+                    or not b.is_contiguous() or not c.is_contiguous()):
+                raise L.VitbError("image_prep: %s tables must be contiguous int32 [%d,2] / [%d,k]" % (name, n_out, n_out))
+    dev = src.device
+    img = None
+    if want_img:
+        img = out_img if out_img is not None else torch.empty((B, Cn, oh, ow), dtype=torch.float32, device=dev)
+        if img.dtype != torch.float32 or tuple(img.shape) != (B, Cn, oh, ow) or not img.is_contiguous():
+            raise L.VitbError("image_prep: out_img must be contiguous fp32 [B,C,oh,ow]")
+    hi = lo = None
+    ldk = 0
+    if P:
+        K = Cn * P * P
+        ldk = (K + 7) // 8 * 8
+        rows = B * (oh // P) * (ow // P)
+        if cols is not None:
+            hi, lo = cols
+            if tuple(hi.shape) != (rows, ldk) or hi.dtype != torch.bfloat16 or (want_lo and lo is None):
+                raise L.VitbError("image_prep: cols buffers must be bf16 [%d,%d]" % (rows, ldk))
+        else:
+            alloc = torch.zeros if ldk != K else torch.empty
+            hi = alloc((rows, ldk), dtype=torch.bfloat16, device=dev)
+            lo = alloc((rows, ldk), dtype=torch.bfloat16, device=dev) if want_lo else None
+        if not want_lo:
+            lo = None
+    u8 = torch.empty((B, oh, ow, Cn), dtype=torch.uint8, device=dev) if want_u8 else None
+    xb, xc = xtab if xtab is not None else (None, None)
+    yb, yc = ytab if ytab is not None else (None, None)
+    L.check(L._vitb_image_prep(L.ptr(src), B, H, W, Cn, oh, ow, L.ptr(xb), L.ptr(xc), xc.shape[1] if xc is not None else 0,
+                               L.ptr(yb), L.ptr(yc), yc.shape[1] if yc is not None else 0, L.ptr(flip), L.ptr(lut),
+                               L.ptr(img), P or 0, ldk, L.ptr(hi), L.ptr(lo), L.ptr(u8), L.stream_ptr(dev)),
+            "vitb_image_prep")
+    return img, hi, lo, u8
+
+
 def cls_rows(x, cls, pos):
     """x: [B,N,D] fp32 contiguous; writes x[:,0,:] = cls + pos[0]."""
     L.require_cuda(x, cls, pos)
