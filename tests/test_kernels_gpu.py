@@ -252,6 +252,36 @@ def test_colsum(dtype):
     assert rel_l2(out, x.float().sum(0) + 1) < 1e-4
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("rows,cols", [(25216, 768), (197, 3072), (1, 8), (333, 100), (4097, 36), (130, 2304)])
+def test_colsum_shapes(dtype, rows, cols):
+    """16-byte / 8-byte column groups, widths that are not a multiple of 8, single rows, ragged row slices."""
+    import vitb200
+    x = _randn((rows, cols), 3, 1.0, dtype)
+    out = torch.full((cols,), 2.0, device="cuda")
+    vitb200.ops.colsum(x, out)
+    assert rel_l2(out, x.float().sum(0) + 2) < 1e-4
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_colsum_strided_view_and_three_segments(dtype):
+    import vitb200
+    big = _randn((1000, 3 * 768 + 64), 4, 1.0, dtype)
+    x = big[:, 8:8 + 3 * 768]                      # row stride > width, base offset of 8 elements
+    outs = [torch.zeros(768, device="cuda") for _ in range(3)]
+    vitb200.ops.colsum3(x, *outs)
+    ref = x.float().sum(0)
+    for i in range(3):
+        assert rel_l2(outs[i], ref[i * 768:(i + 1) * 768]) < 1e-4
+    x4 = big[:, 4:4 + 3 * 100]                     # segments of 100 columns: the 4-column path, 8-byte alignment only
+    o = [torch.zeros(100, device="cuda") for _ in range(3)]
+    if dtype == torch.bfloat16:
+        vitb200.ops.colsum3(x4, *o)
+        r4 = x4.float().sum(0)
+        for i in range(3):
+            assert rel_l2(o[i], r4[i * 100:(i + 1) * 100]) < 1e-4
+
+
 def test_cross_entropy():
     import vitb200
     B, Ccls = 128, 100

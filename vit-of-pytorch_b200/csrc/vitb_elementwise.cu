@@ -151,41 +151,103 @@ embed_bwd_kernel(const float* __restrict__ dx, int Bsz, int N, int D, float* __r
   }
 }
 
-// out[c] += sum_r x[r, c]; thread owns 4 columns (bf16) / 4 columns (fp32), rows split across blocks.y
-template <bool BF16>
-__global__ void __launch_bounds__(kThreads)
+// out[c] += sum_r x[r, c].  A thread owns 16 bytes of a row (8 bf16 / 4 fp32 columns; 4 bf16 columns when the width
+// is not a multiple of 8).  Block = (column groups) x (NY row lanes); the block's row slice is walked NY rows at a
+// time with 8 independent loads per thread, the NY partial sums meet in shared memory and one atomic per column and
+// block goes out.  HBM-bound: rows * cols * esize bytes read once; ptxas keeps the kernel at 32 registers, so the
+// loads in flight come from occupancy (64 warps per SM), and the grid is sized for exactly that.
+constexpr int kColsumThreads = 512;
+template <bool BF16, int VEC>   // VEC = columns per thread: 8 or 4 (bf16), 4 (fp32)
+__global__ void __launch_bounds__(kColsumThreads)
 colsum_kernel(const void* __restrict__ x_, int rows, int cols, long long ld_, float* __restrict__ out0,
               float* __restrict__ out1, float* __restrict__ out2, int seg_cols) {
-  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  if (c >= cols) return;
-  const int seg = c / seg_cols;
-  float* out = (seg == 0 ? out0 : (seg == 1 ? out1 : out2)) - static_cast<long long>(seg) * seg_cols;
+  extern __shared__ float colsum_part[];   // [blockDim.y][blockDim.x * VEC]
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+  const bool live = c < cols;
   const int rows_per = (rows + gridDim.y - 1) / gridDim.y;
   const int r0 = blockIdx.y * rows_per;
   const int r1 = min(rows, r0 + rows_per);
-  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-  auto ld = [&](int r) {
-    if constexpr (BF16) {
-      const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(x_) + static_cast<long long>(r) * ld_ + c);
-      return make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
+  const int ny = blockDim.y;
+  float s[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) s[j] = 0.f;
+  constexpr int ESIZE = BF16 ? 2 : 4;
+  const char* base = reinterpret_cast<const char*>(x_) + static_cast<long long>(c) * ESIZE;
+  const long long pitch = ld_ * ESIZE;
+  auto acc = [&](const uint4& u) {
+    if constexpr (!BF16) {
+      s[0] += __uint_as_float(u.x); s[1] += __uint_as_float(u.y); s[2] += __uint_as_float(u.z); s[3] += __uint_as_float(u.w);
     } else {
-      return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x_) + static_cast<long long>(r) * ld_ + c);
+      s[0] += bf16_lo(u.x); s[1] += bf16_hi(u.x); s[2] += bf16_lo(u.y); s[3] += bf16_hi(u.y);
+      if constexpr (VEC == 8) { s[4] += bf16_lo(u.z); s[5] += bf16_hi(u.z); s[6] += bf16_lo(u.w); s[7] += bf16_hi(u.w); }
     }
   };
-  int r = r0;
-  for (; r + 8 <= r1; r += 8) {  // 8 independent loads in flight per thread
-    float4 v[8];
+  auto ld = [&](int r) {
+    const char* p = base + static_cast<long long>(r) * pitch;
+    if constexpr (BF16 && VEC == 4) {
+      const uint2 u = *reinterpret_cast<const uint2*>(p);
+      return make_uint4(u.x, u.y, 0u, 0u);
+    } else {
+      return *reinterpret_cast<const uint4*>(p);
+    }
+  };
+  if (live) {
+    int r = r0 + threadIdx.y;
+    for (; r + 7 * ny < r1; r += 8 * ny) {
+      uint4 v[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = ld(r + j);
+      for (int j = 0; j < 8; ++j) v[j] = ld(r + j * ny);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { s.x += v[j].x; s.y += v[j].y; s.z += v[j].z; s.w += v[j].w; }
+      for (int j = 0; j < 8; ++j) acc(v[j]);
+    }
+    for (; r < r1; r += ny) acc(ld(r));
   }
-  for (; r < r1; ++r) {
-    const float4 v = ld(r);
-    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  const int width = blockDim.x * VEC;
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) colsum_part[threadIdx.y * width + threadIdx.x * VEC + j] = s[j];
+  __syncthreads();
+  if (threadIdx.y == 0 && live) {
+    const int seg = c / seg_cols;     // seg_cols is a multiple of VEC: a thread never straddles two segments
+    float* out = (seg == 0 ? out0 : (seg == 1 ? out1 : out2)) - static_cast<long long>(seg) * seg_cols;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      float t = s[j];
+      for (int y = 1; y < ny; ++y) t += colsum_part[y * width + threadIdx.x * VEC + j];
+      atomicAdd(out + c + j, t);
+    }
   }
-  atomicAdd(out + c + 0, s.x); atomicAdd(out + c + 1, s.y);
-  atomicAdd(out + c + 2, s.z); atomicAdd(out + c + 3, s.w);
+}
+
+// grid for the above: x over column groups with the block width that wastes the fewest lanes (2304 bf16 columns are
+// 288 groups = 3 blocks of 96 x 5), y over row slices of >= 32 rows per row lane, 64 warps per SM in total
+template <bool BF16, int VEC>
+static void colsum_launch(const void* x, int rows, int cols, long long ld, float* o0, float* o1, float* o2, int seg_cols,
+                          cudaStream_t stream) {
+  const int groups = cols / VEC;
+  int tb = 32, waste = 1 << 30;
+  for (int cand = 256; cand >= 32; cand -= 32) {
+    const int w = (groups + cand - 1) / cand * cand - groups;
+    if (w < waste) { waste = w; tb = cand; }
+  }
+  const int ny = kColsumThreads / tb;                 // >= 2 row lanes share a block (and one atomic per column)
+  const int bx = (groups + tb - 1) / tb;
+  const int warps_per_block = tb * ny / 32;
+  int by = (vitb_num_sms() * 64 + bx * warps_per_block - 1) / (bx * warps_per_block);
+  const int max_by = (rows + 32 * ny - 1) / (32 * ny);
+  if (by > max_by) by = max_by;
+  if (by < 1) by = 1;
+  const size_t smem = static_cast<size_t>(ny) * tb * VEC * sizeof(float);
+  colsum_kernel<BF16, VEC><<<dim3(bx, by), dim3(tb, ny), smem, stream>>>(x, rows, cols, ld, o0, o1, o2, seg_cols);
+}
+static void colsum_dispatch(const void* x, int x_dtype, int rows, int cols, long long ld, float* o0, float* o1, float* o2,
+                            int seg_cols, cudaStream_t stream) {
+  if (x_dtype == VITB_BF16) {
+    const bool v8 = seg_cols % 8 == 0 && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15u) == 0;
+    if (v8) colsum_launch<true, 8>(x, rows, cols, ld, o0, o1, o2, seg_cols, stream);
+    else colsum_launch<true, 4>(x, rows, cols, ld, o0, o1, o2, seg_cols, stream);
+  } else {
+    colsum_launch<false, 4>(x, rows, cols, ld, o0, o1, o2, seg_cols, stream);
+  }
 }
 
 // Cross entropy (mean) forward + gradient in one block: nn.CrossEntropyLoss, src/train.py:151,22;
@@ -437,15 +499,7 @@ int vitb_colsum(const void* x, int x_dtype, int rows, int cols, int64_t ld, floa
   if (rows == 0 || cols == 0) return VITB_OK;
   VITB_REQUIRE(x && out && rows > 0 && cols > 0 && cols % 4 == 0 && ld % 4 == 0, VITB_ERR_UNSUPPORTED_SHAPE,
                "colsum: rows=%d cols=%d ld=%lld (cols, ld must be multiples of 4)", rows, cols, (long long)ld);
-  const int bx = (cols / 4 + 127) / 128;
-  int by = (vitb_num_sms() * 4 + bx - 1) / bx;
-  if (by > (rows + 63) / 64) by = (rows + 63) / 64;
-  if (by < 1) by = 1;
-  dim3 grid(bx, by);
-  if (x_dtype == VITB_BF16)
-    colsum_kernel<true><<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(x, rows, cols, ld, out, out, out, cols);
-  else
-    colsum_kernel<false><<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(x, rows, cols, ld, out, out, out, cols);
+  colsum_dispatch(x, x_dtype, rows, cols, ld, out, out, out, cols, reinterpret_cast<cudaStream_t>(stream_));
   VITB_LAUNCH_CHECK("colsum_kernel");
   return VITB_OK;
 }
@@ -458,15 +512,7 @@ int vitb_colsum3(const void* x, int x_dtype, int rows, int seg_cols, int64_t ld,
   const int cols = 3 * seg_cols;
   VITB_REQUIRE(x && out0 && out1 && out2 && rows > 0 && seg_cols % 4 == 0 && ld % 4 == 0, VITB_ERR_UNSUPPORTED_SHAPE,
                "colsum3: rows=%d seg_cols=%d ld=%lld", rows, seg_cols, (long long)ld);
-  const int bx = (cols / 4 + 127) / 128;
-  int by = (vitb_num_sms() * 4 + bx - 1) / bx;
-  if (by > (rows + 63) / 64) by = (rows + 63) / 64;
-  if (by < 1) by = 1;
-  dim3 grid(bx, by);
-  if (x_dtype == VITB_BF16)
-    colsum_kernel<true><<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(x, rows, cols, ld, out0, out1, out2, seg_cols);
-  else
-    colsum_kernel<false><<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(x, rows, cols, ld, out0, out1, out2, seg_cols);
+  colsum_dispatch(x, x_dtype, rows, cols, ld, out0, out1, out2, seg_cols, reinterpret_cast<cudaStream_t>(stream_));
   VITB_LAUNCH_CHECK("colsum_kernel");
   return VITB_OK;
 }
