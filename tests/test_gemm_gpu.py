@@ -201,6 +201,36 @@ def test_gemm_gelu_dg_then_mul_aux_equals_gelu_backward(M, N):
         assert rel_l2(cs, want.sum(0) + 1.0) < 4e-3
 
 
+@pytest.mark.parametrize("M,N,with_bias", [(777, 3072, True), (300, 200, True), (1000, 768, False), (25216, 3072, True)])
+def test_gemm_gelu_dg_packed_pair_epilogue(M, N, with_bias, monkeypatch):
+    """VITB_EPI_PACKED=1: the GELU + GELU' epilogue on packed fp32 pairs (FFMA2), bias staged in shared memory.
+    Same bar as the scalar epilogue against the torch reference, and the two epilogues agree with each other to
+    bf16 rounding (gelu = z * Phi(z) on the packed path, |z| * half_erf + z/2 on the scalar one)."""
+    import vitb200
+    K = 768
+    A, B, _ = _operands(M, N, K, False, False, seed=91)
+    A = (A.float() * 0.05).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda") * 0.1 if with_bias else None
+    z = A.float() @ B.float().t()
+    if with_bias:
+        z = z + bias
+    zr = z.requires_grad_(True)
+    g = torch.nn.functional.gelu(zr)
+    g.backward(torch.ones_like(g))
+    outs = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("VITB_EPI_PACKED", flag)
+        dg = torch.full((M + 3, N), float("nan"), dtype=torch.bfloat16, device="cuda")
+        out = torch.full((M + 3, N), 7.0, dtype=torch.bfloat16, device="cuda")
+        vitb200.ops.gemm(A, B, bias=bias, epilogue=vitb200.ops.EPI_GELU_DG, d2=dg[:M], out=out[:M])
+        torch.cuda.synchronize()
+        assert rel_l2(out[:M], g.detach()) < 4e-3, flag
+        assert rel_l2(dg[:M], zr.grad) < 4e-3, flag
+        assert bool((out[M:] == 7.0).all()) and bool(dg[M:].isnan().all()), flag     # rows past M untouched
+        outs[flag] = (out[:M].float(), dg[:M].float())
+    assert rel_l2(outs["1"][0], outs["0"][0]) < 2e-3 and rel_l2(outs["1"][1], outs["0"][1]) < 2e-3
+
+
 def test_gemm_bf16_tma_store_respects_row_and_column_tails_and_strided_outputs():
     """bf16 outputs leave through 32x32 TMA-store tiles: rows >= M / columns >= N are clipped by the tensor map,
     and a column slice of a wider buffer (the packed q|k|v projection output) keeps its neighbours intact."""

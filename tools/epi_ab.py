@@ -1,0 +1,56 @@
+"""A/B of epilogue switches on the ViT-B/16 batch-128 fc1 forward (GELU + GELU' outputs):
+VITB_EPI_PACKED = 0 / 1 in one process (the library reads the switch at every call).  Diagnostic only."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import vitb200  # noqa: E402
+
+
+def timeit(fn, iters=30, warm=5):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+T, D, M = 25216, 768, 3072
+bf = torch.bfloat16
+A = torch.randn(T, D, device="cuda").to(bf)
+B = torch.randn(M, D, device="cuda").to(bf)
+out = torch.empty(T, M, device="cuda", dtype=bf)
+d2 = torch.empty_like(out)
+bias = torch.randn(M, device="cuda")
+fl = 2.0 * T * M * D
+lines = []
+for rep in range(2):
+    for flag in ("0", "1"):
+        os.environ["VITB_EPI_PACKED"] = flag
+        ms = timeit(lambda: vitb200.ops.gemm(A, B, out=out, bias=bias, epilogue=vitb200.ops.EPI_GELU_DG, d2=d2))
+        lines.append("fc1 gelu+gelu' VITB_EPI_PACKED=%s  %.4f ms  %.0f TF" % (flag, ms, fl / ms / 1e9))
+        print(lines[-1], flush=True)
+x = torch.randn(T, 3 * D, device="cuda").to(bf)
+o3 = [torch.zeros(D, device="cuda") for _ in range(3)]
+ms = timeit(lambda: vitb200.ops.colsum3(x, *o3))
+lines.append("colsum3 [25216, 2304] bf16  %.4f ms  %.0f GB/s" % (ms, x.numel() * 2 / ms / 1e6))
+print(lines[-1], flush=True)
+u8 = torch.randint(0, 256, (128, 32, 32, 3), dtype=torch.uint8, device="cuda")
+tf = vitb200.DeviceImageTransform((32, 32), 224, device="cuda")
+buf = torch.empty(128, 3, 224, 224, device="cuda")
+ms = timeit(lambda: tf(u8, out=buf))
+lines.append("image_prep 128 x 32x32 -> 224 fp32  %.4f ms  %.0f GB/s written" % (ms, buf.numel() * 4 / ms / 1e6))
+print(lines[-1], flush=True)
+ms = timeit(lambda: tf.patch_columns(u8, 16))
+lines.append("image_prep 128 x 32x32 -> bf16 patch operand  %.4f ms  %.0f GB/s written" % (ms, buf.numel() * 2 / ms / 1e6))
+print(lines[-1], flush=True)
+os.makedirs("gpurun_out", exist_ok=True)
+with open("gpurun_out/epi_ab.txt", "w") as fh:
+    fh.write("\n".join(lines) + "\n")

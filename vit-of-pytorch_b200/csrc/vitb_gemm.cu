@@ -72,6 +72,7 @@ struct GemmDev {
   int tma_store;     // bf16 outputs leave through cp.async.bulk.tensor stores (tmD / tmD2 are valid)
   int d2_grad;       // VITB_EPI_GELU_DG: D2 receives gelu'(v) instead of v
   int aux_grad;      // VITB_EPI_MUL_AUX: aux already holds gelu'(z); the epilogue only multiplies
+  int packed_epi;    // GELU + GELU' epilogue on packed fp32 pairs with the bias staged in shared memory (VITB_EPI_PACKED)
 };
 
 struct TileCoord {
@@ -144,6 +145,38 @@ __device__ __forceinline__ void gelu_fast_both(float z, float& g, float& dg) {
   const float half_erf = fmaf(-poly * t, e, 0.5f);                   // 0.5 erf(|z| / sqrt2)
   g = fmaf(az, half_erf, 0.5f * z);
   dg = fmaf(z * 0.39894228040143267794f, e, 0.5f + copysignf(half_erf, z));   // Phi(z) + z phi(z)
+}
+// The same value / derivative pair for TWO pre-activations at once on packed fp32 pairs (FFMA2 / FMUL2 / FADD2):
+// 13 FMA-pipe issue slots per pair instead of 30, 4 LOP3 on the ALU pipe, 4 MUFU.  gelu(z) = z Phi(z) here
+// (Phi is needed for the derivative anyway), the polynomial carries its sign in the coefficients.
+__device__ __forceinline__ void gelu_fast_both2(float z0, float z1, uint64_t& g, uint64_t& dg) {
+  const uint64_t z = pk2(z0, z1);
+  const uint64_t az = pk2(fabsf(z0), fabsf(z1));
+  float ti0, ti1;
+  upk2(fma2(az, pk2(0.23164189f), pk2(1.0f)), ti0, ti1);
+  const uint64_t t = pk2(rcp_approx(ti0), rcp_approx(ti1));       // 1 / (1 + 0.3275911 |z| / sqrt2)
+  float ei0, ei1;
+  upk2(mul2(mul2(z, z), pk2(-0.72134752044448170368f)), ei0, ei1);
+  const uint64_t e = pk2(ex2_approx(ei0), ex2_approx(ei1));       // exp(-z^2 / 2)
+  uint64_t np = fma2(pk2(-0.5307027145f), t, pk2(0.7265760135f)); // -(0.5 poly(t))
+  np = fma2(np, t, pk2(-0.7107068705f));
+  np = fma2(np, t, pk2(0.142248368f));
+  np = fma2(np, t, pk2(-0.127414796f));
+  float he0, he1;
+  upk2(fma2(mul2(np, t), e, pk2(0.5f)), he0, he1);                // 0.5 erf(|z| / sqrt2) >= 0 up to 1.5e-7
+  const uint64_t phi = add2(pk2(copysignf(he0, z0), copysignf(he1, z1)), pk2(0.5f));   // Phi(z)
+  g = mul2(z, phi);
+  dg = fma2(mul2(z, pk2(0.39894228040143267794f)), e, phi);      // Phi(z) + z phi(z)
+}
+__device__ __forceinline__ uint32_t pack_bf16x2_pair(uint64_t v) {
+  float lo, hi;
+  upk2(v, lo, hi);
+  return pack_bf16x2(lo, hi);
+}
+__device__ __forceinline__ float4 ld_shared_f4_16(uint32_t addr) {   // one 16-byte load (16-byte aligned address)
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
 }
 __device__ __forceinline__ float ld_shared_f1(uint32_t addr) {
   float v;
@@ -404,6 +437,48 @@ __device__ __forceinline__ void epi_rows_bf16_tma(const GemmDev& p, const CUtens
   tma_store_rows_bf16(tmD, tbuf, which, lane, v, row_base, col0);
 }
 
+// GELU + GELU' chunk on packed pairs.  The 32 bias values of the chunk sit in this warp's shared-memory slot
+// (published by the epilogue loop one chunk ahead: with 227 KB of shared memory in use there is no L1 left, and
+// the per-chunk __ldg of the bias paid an L2 round trip in front of the math — profiles/ncu_r01c.txt).
+__device__ __forceinline__ void epi_rows_gelu_dg_packed(const CUtensorMap* tmD, const CUtensorMap* tmD2, uint32_t tbuf,
+                                                        int& which, int lane, int row_base, int col0,
+                                                        const uint32_t (&r)[32], uint32_t bias_slot, bool has_bias) {
+  const uint32_t bufd = tma_tile_acquire(tbuf, which, lane);   // derivative tile
+  uint32_t gq[16];                                               // gelu(v) as packed bf16 pairs, stored after the loop
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {                                  // 8 columns per 16-byte unit
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[8 * j + i]);
+    if (has_bias) {
+      const float4 b0 = ld_shared_f4_16(bias_slot + j * 32), b1 = ld_shared_f4_16(bias_slot + j * 32 + 16);
+      uint64_t s;
+      s = add2(pk2(v[0], v[1]), pk2(b0.x, b0.y)); upk2(s, v[0], v[1]);
+      s = add2(pk2(v[2], v[3]), pk2(b0.z, b0.w)); upk2(s, v[2], v[3]);
+      s = add2(pk2(v[4], v[5]), pk2(b1.x, b1.y)); upk2(s, v[4], v[5]);
+      s = add2(pk2(v[6], v[7]), pk2(b1.z, b1.w)); upk2(s, v[6], v[7]);
+    }
+    uint32_t dq[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint64_t g, dg;
+      gelu_fast_both2(v[2 * i], v[2 * i + 1], g, dg);
+      gq[4 * j + i] = pack_bf16x2_pair(g);
+      dq[i] = pack_bf16x2_pair(dg);
+    }
+    const uint32_t x = (static_cast<uint32_t>(lane) >> 1) & 3u;   // SWIZZLE_64B, as tma_tile_write_unit
+    st_shared_v4(bufd + static_cast<uint32_t>(lane) * 64u + ((static_cast<uint32_t>(j) ^ x) << 4), dq[0], dq[1], dq[2], dq[3]);
+  }
+  tma_tile_release(tmD2, bufd, lane, row_base, col0);
+  const uint32_t bufg = tma_tile_acquire(tbuf, which, lane);   // value tile
+  const uint32_t x = (static_cast<uint32_t>(lane) >> 1) & 3u;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    st_shared_v4(bufg + static_cast<uint32_t>(lane) * 64u + ((static_cast<uint32_t>(j) ^ x) << 4), gq[4 * j], gq[4 * j + 1],
+                 gq[4 * j + 2], gq[4 * j + 3]);
+  tma_tile_release(tmD, bufg, lane, row_base, col0);
+}
+
 // Scalar epilogue with every option (row bias, patch-embedding row remap, odd widths): lane == column.
 __device__ __noinline__ void epi_generic(const GemmDev& p, uint32_t stg, int lane, int row_base, int col0,
                                          bool lead_split) {
@@ -595,6 +670,11 @@ vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const uint32_t tbuf = (stg + 511u) & ~511u;   // two 2 KiB 64B-swizzled tiles inside this warp's staging slice
     int tma_which = 0;
     if (tma_path && lane == 0) { tma_prefetch_desc(&tmD); if (p.D2 != nullptr) tma_prefetch_desc(&tmD2); }
+    // packed GELU + GELU' path: the two 2 KiB store tiles leave 256 B of this warp's 4352 B slice unused (before the
+    // tiles when the slice starts 256 B past a 512 B boundary, after them otherwise): two 32-float bias slots
+    const bool packed = tma_path && mode == 2 && p.packed_epi != 0 && p.D2 != nullptr && p.d2_grad != 0;
+    const uint32_t bias_slots = (tbuf == stg) ? stg + 2u * kTmaTileBytes : stg;
+    const bool has_bias = p.bias != nullptr;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile);
       const int n0 = t.n_blk * BN;
@@ -616,6 +696,11 @@ vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           }
         }
       }
+      float bias_next = 0.f;   // packed path: lane j carries bias[col0 + j] of the chunk that comes next
+      if (packed && has_bias) {
+        const int colb = n0 + half * (BN / 64) * 32 + lane;
+        if (colb < p.N) bias_next = __ldg(p.bias + colb);
+      }
       mbar_wait(tfull0 + 8 * acc, acc_phase);
       tc_fence_after();
 #pragma unroll 1
@@ -626,6 +711,20 @@ vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         uint32_t r[32];
         tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                                static_cast<uint32_t>(acc * BN + c * 32), r);
+        if (packed) {
+          const uint32_t slot = bias_slots + static_cast<uint32_t>(c & 1) * 128u;
+          if (has_bias) {
+            // publish this chunk's bias (requested a chunk ago) and request the next chunk's: the L2 round trip
+            // runs under this chunk's math
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(slot + static_cast<uint32_t>(lane) * 4u), "f"(bias_next) : "memory");
+            bias_next = 0.f;
+            if (next_col0 >= 0 && next_col0 + lane < p.N) bias_next = __ldg(p.bias + next_col0 + lane);
+            __syncwarp();
+          }
+          tmem_ld_wait();
+          epi_rows_gelu_dg_packed(&tmD, &tmD2, tbuf, tma_which, lane, row_base, col0, r, slot, has_bias);
+          continue;
+        }
         tmem_ld_wait();
         if (tma_path) {    // bf16 outputs without residual / column sums: math in registers, tiles leave by TMA
           if (mode == 2) epi_rows_bf16_tma<VITB_EPI_GELU>(p, &tmD, &tmD2, tbuf, tma_which, lane, row_base, col0, r);
@@ -982,6 +1081,10 @@ extern "C" int vitb_gemm(const vitb_gemm_params* p, void* stream_) {
   // bf16 outputs of the register-layout epilogue leave through TMA stores (32 x 32 tiles, SWIZZLE_64B);
   // anything that does not meet TMA's 16-byte rules takes the staged epi_vec path
   d.tma_store = 0;
+  {
+    const char* pe = getenv("VITB_EPI_PACKED");     // A/B switch of the packed-pair GELU + GELU' epilogue
+    d.packed_epi = (pe != nullptr && atoi(pe) != 0) ? 1 : 0;
+  }
   tm[6] = tm[0];
   tm[7] = tm[0];
   if (d.vec_ok && d.d_bf16 && p->N % 8 == 0 && p->colsum == nullptr && p->residual == nullptr && !p->accumulate &&
