@@ -67,6 +67,33 @@ def test_layernorm_bwd(D, dy_dtype):
     assert rel_l2(dcol, ref_dx.sum(0)) < 1e-4
 
 
+@pytest.mark.parametrize("rows,D,dy_dtype,extras", [(25216, 768, torch.bfloat16, True), (25216, 768, torch.float32, False),
+                                                     (5, 768, torch.bfloat16, True), (12608, 1024, torch.bfloat16, True),
+                                                     (4000, 384, torch.bfloat16, False)])
+def test_layernorm_bwd_many_rows_per_warp(rows, D, dy_dtype, extras):
+    """Full-size token counts (many rows per warp, the per-warp shared-memory partial sums carry across rows), tiny row
+    counts (most warps idle), and the variants without residual gradient / column sums."""
+    import vitb200
+    x = (_randn((rows, D), 17, 2.0) + 0.3).requires_grad_(True)
+    g = _randn((D,), 18).requires_grad_(True)
+    b = _randn((D,), 19).requires_grad_(True)
+    dy = _randn((rows, D), 20, 1.0, dy_dtype)
+    dres = _randn((rows, D), 21) if extras else None
+    torch.nn.functional.layer_norm(x, (D,), g, b, 1e-5).backward(dy.float())
+    _, _, _, mean, rstd = vitb200.ops.layernorm_fwd(x.detach(), g.detach(), b.detach(), 1e-5, want_bf16=False)
+    dgamma = torch.ones(D, device="cuda"); dbeta = torch.ones(D, device="cuda")
+    dcol = torch.ones(D, device="cuda") if extras else None
+    dxf, dxh, _ = vitb200.ops.layernorm_bwd(dy, x.detach(), mean, rstd, g.detach(), dres=dres, want_f32=True, want_bf16=True,
+                                            dgamma=dgamma, dbeta=dbeta, dcolsum=dcol)
+    ref_dx = x.grad + (dres if extras else 0)
+    assert rel_l2(dxf, ref_dx) < 1e-5
+    assert rel_l2(dxh, ref_dx) < 4e-3
+    assert rel_l2(dgamma, g.grad + 1) < 1e-4          # accumulated (+=) into the caller's buffers
+    assert rel_l2(dbeta, b.grad + 1) < 1e-4
+    if extras:
+        assert rel_l2(dcol, ref_dx.sum(0) + 1) < 1e-4
+
+
 # ---------------------------------------------------------------------------------------- attention
 def _attn_ref(q, k, v, H):
     B, Nq, HD = q.shape

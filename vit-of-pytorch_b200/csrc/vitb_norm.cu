@@ -88,8 +88,21 @@ ln_fwd_kernel(const void* __restrict__ x_, long long x_stride, int rows, const f
   }
 }
 
+// Backward.  One warp per row, the row in registers.  HBM-bound (16 D bytes per row), and what buys bandwidth is
+// rows in flight per SM, i.e. warps per SM, i.e. registers per thread.  The first version kept the warp's partial
+// dgamma / dbeta / dcolsum sums (12 D bytes per warp) and gamma in registers: 240 registers, 8 warps per SM, 74 % of
+// the measured HBM peak (profiles/launches_r01c_summary.txt).  Here the partial sums live in a per-warp slice of
+// shared memory (plain 16-byte read-modify-write, no atomics: the slice is private to the warp and every lane owns
+// its columns), gamma is re-read from L1 per row (3 KB, always resident) and a bf16 dy stays packed between the two
+// phases: 16 warps per SM for D <= 768 (12 for wider rows, whose slices are larger).
+template <int NV>
+struct LnBwdCfg {
+  static constexpr int WARPS = NV <= 6 ? 16 : 12;
+  static constexpr size_t SMEM = static_cast<size_t>(WARPS) * 3 * NV * 128 * sizeof(float);
+};
+
 template <int NV, bool DY_BF16, bool COLSUM>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 1)
+__global__ void __launch_bounds__(LnBwdCfg<NV>::WARPS * 32, 1)
 ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, long long x_stride,
               const float* __restrict__ mean, const float* __restrict__ rstd,
               const float* __restrict__ gamma, int rows, const float* __restrict__ dres,
@@ -97,57 +110,79 @@ ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, long lo
               __nv_bfloat16* __restrict__ dx_hi, __nv_bfloat16* __restrict__ dx_lo,
               float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dcolsum) {
   constexpr int D = NV * 128;
-  extern __shared__ float s_acc[];  // [3][D] block-level accumulators
+  constexpr int WARPS = LnBwdCfg<NV>::WARPS;
+  extern __shared__ __align__(16) float s_acc[];   // [WARPS][3][D]: dgamma | dbeta | dcolsum partial sums per warp
   pdl_trigger();
-  for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) s_acc[i] = 0.f;
-  __syncthreads();
-  pdl_wait();
   const int lane = threadIdx.x & 31;
-  const int gw = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-  const int nw = gridDim.x * kWarpsPerBlock;
-  float4 gam[NV], dg[NV], db[NV], dc[COLSUM ? NV : 1];
+  const int warp = threadIdx.x >> 5;
+  float* acc = s_acc + static_cast<size_t>(warp) * 3 * D;
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    gam[i] = ld4(gamma + (i * 32 + lane) * 4);
-    dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if constexpr (COLSUM) dc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
+  for (int i = 0; i < 3 * NV; ++i)
+    *reinterpret_cast<float4*>(acc + (i * 32 + lane) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncwarp();
+  pdl_wait();
+  const int gw = blockIdx.x * WARPS + warp;
+  const int nw = gridDim.x * WARPS;
+  // dy of the row between the two phases: raw bf16x4 (two registers) or fp32x4
+  struct DyKeep { uint32_t a, b, c, d; };
+  auto dy_value = [](const DyKeep& k) {
+    if constexpr (DY_BF16) return make_float4(bf16_lo(k.a), bf16_hi(k.a), bf16_lo(k.b), bf16_hi(k.b));
+    else return make_float4(__uint_as_float(k.a), __uint_as_float(k.b), __uint_as_float(k.c), __uint_as_float(k.d));
+  };
+  auto add4 = [](float* p, float a, float b, float c, float d) {
+    float4 v = *reinterpret_cast<float4*>(p);
+    v.x += a; v.y += b; v.z += c; v.w += d;
+    *reinterpret_cast<float4*>(p) = v;
+  };
   for (int row = gw; row < rows; row += nw) {
     const float mu = mean[row], rs = rstd[row];
-    float4 xh[NV], gy[NV];
+    float4 xh[NV];
+    DyKeep keep[NV];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = (i * 32 + lane) * 4;
       float4 xv = ld4(x + static_cast<long long>(row) * x_stride + c);
-      float4 dyv;
-      if constexpr (DY_BF16) dyv = ld4_bf16(reinterpret_cast<const __nv_bfloat16*>(dy_) + static_cast<long long>(row) * D + c);
-      else dyv = ld4(reinterpret_cast<const float*>(dy_) + static_cast<long long>(row) * D + c);
+      if constexpr (DY_BF16) {
+        const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(dy_) + static_cast<long long>(row) * D + c);
+        keep[i].a = u.x; keep[i].b = u.y; keep[i].c = 0u; keep[i].d = 0u;
+      } else {
+        const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(dy_) + static_cast<long long>(row) * D + c);
+        keep[i].a = u.x; keep[i].b = u.y; keep[i].c = u.z; keep[i].d = u.w;
+      }
       xv.x = (xv.x - mu) * rs; xv.y = (xv.y - mu) * rs; xv.z = (xv.z - mu) * rs; xv.w = (xv.w - mu) * rs;
-      dg[i].x += dyv.x * xv.x; dg[i].y += dyv.y * xv.y; dg[i].z += dyv.z * xv.z; dg[i].w += dyv.w * xv.w;
-      db[i].x += dyv.x; db[i].y += dyv.y; db[i].z += dyv.z; db[i].w += dyv.w;
-      dyv.x *= gam[i].x; dyv.y *= gam[i].y; dyv.z *= gam[i].z; dyv.w *= gam[i].w;
+      xh[i] = xv;
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      float4 dyv = dy_value(keep[i]);
+      const float4 xv = xh[i];
+      add4(acc + c, dyv.x * xv.x, dyv.y * xv.y, dyv.z * xv.z, dyv.w * xv.w);        // dgamma
+      add4(acc + D + c, dyv.x, dyv.y, dyv.z, dyv.w);                                 // dbeta
+      const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + c));
+      dyv.x *= gm.x; dyv.y *= gm.y; dyv.z *= gm.z; dyv.w *= gm.w;
       s1 += (dyv.x + dyv.y) + (dyv.z + dyv.w);
       s2 += (dyv.x * xv.x + dyv.y * xv.y) + (dyv.z * xv.z + dyv.w * xv.w);
-      xh[i] = xv;
-      gy[i] = dyv;
     }
     s1 = warp_sum(s1) * (1.0f / D);
     s2 = warp_sum(s2) * (1.0f / D);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = (i * 32 + lane) * 4;
+      const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + c));
+      float4 gy = dy_value(keep[i]);
+      gy.x *= gm.x; gy.y *= gm.y; gy.z *= gm.z; gy.w *= gm.w;    // the same products phase 1 summed
       float4 d;
-      d.x = rs * (gy[i].x - s1 - xh[i].x * s2);
-      d.y = rs * (gy[i].y - s1 - xh[i].y * s2);
-      d.z = rs * (gy[i].z - s1 - xh[i].z * s2);
-      d.w = rs * (gy[i].w - s1 - xh[i].w * s2);
+      d.x = rs * (gy.x - s1 - xh[i].x * s2);
+      d.y = rs * (gy.y - s1 - xh[i].y * s2);
+      d.z = rs * (gy.z - s1 - xh[i].z * s2);
+      d.w = rs * (gy.w - s1 - xh[i].w * s2);
       if (dres) {
         const float4 r = ld4(dres + static_cast<long long>(row) * dres_stride + c);
         d.x += r.x; d.y += r.y; d.z += r.z; d.w += r.w;
       }
-      if constexpr (COLSUM) { dc[i].x += d.x; dc[i].y += d.y; dc[i].z += d.z; dc[i].w += d.w; }
+      if constexpr (COLSUM) add4(acc + 2 * D + c, d.x, d.y, d.z, d.w);
       if (dx_f32) *reinterpret_cast<float4*>(dx_f32 + static_cast<long long>(row) * dx_stride + c) = d;
       const long long off = static_cast<long long>(row) * D + c;
       if (dx_hi) st4_bf16(dx_hi + off, d.x, d.y, d.z, d.w);
@@ -156,24 +191,16 @@ ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, long lo
                  d.w - bf16_round(d.w));
     }
   }
-  // block-level combine in shared memory (distinct banks per lane), then one global atomic per column
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int c = (i * 32 + lane) * 4;
-    atomicAdd(&s_acc[c + 0], dg[i].x); atomicAdd(&s_acc[c + 1], dg[i].y);
-    atomicAdd(&s_acc[c + 2], dg[i].z); atomicAdd(&s_acc[c + 3], dg[i].w);
-    atomicAdd(&s_acc[D + c + 0], db[i].x); atomicAdd(&s_acc[D + c + 1], db[i].y);
-    atomicAdd(&s_acc[D + c + 2], db[i].z); atomicAdd(&s_acc[D + c + 3], db[i].w);
-    if constexpr (COLSUM) {
-      atomicAdd(&s_acc[2 * D + c + 0], dc[i].x); atomicAdd(&s_acc[2 * D + c + 1], dc[i].y);
-      atomicAdd(&s_acc[2 * D + c + 2], dc[i].z); atomicAdd(&s_acc[2 * D + c + 3], dc[i].w);
-    }
-  }
+  // fold the warps' slices, then one global atomic per column and block
   __syncthreads();
-  for (int i = threadIdx.x; i < D; i += blockDim.x) {
-    if (dgamma) atomicAdd(dgamma + i, s_acc[i]);
-    if (dbeta) atomicAdd(dbeta + i, s_acc[D + i]);
-    if constexpr (COLSUM) atomicAdd(dcolsum + i, s_acc[2 * D + i]);
+  constexpr int NSUM = COLSUM ? 3 : 2;
+  for (int i = threadIdx.x; i < NSUM * D; i += blockDim.x) {
+    float t = 0.f;
+#pragma unroll 4
+    for (int w = 0; w < WARPS; ++w) t += s_acc[static_cast<size_t>(w) * 3 * D + i];
+    if (i < D) { if (dgamma) atomicAdd(dgamma + i, t); }
+    else if (i < 2 * D) { if (dbeta) atomicAdd(dbeta + i - D, t); }
+    else atomicAdd(dcolsum + i - 2 * D, t);
   }
 }
 
@@ -238,15 +265,19 @@ extern "C" int vitb_layernorm_bwd(const void* dy, int dy_dtype, const float* x, 
   VITB_REQUIRE(x_row_stride % 4 == 0 && dres_row_stride % 4 == 0 && dx_row_stride % 4 == 0,
                VITB_ERR_UNSUPPORTED_SHAPE, "layernorm_bwd: row strides must be multiples of 4");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  const int blocks_needed = (rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  const int max_blocks = vitb_num_sms() * 2;
-  const int grid = blocks_needed < max_blocks ? blocks_needed : max_blocks;
   const int nv = D / 128;
-  const size_t smem = 3 * static_cast<size_t>(D) * sizeof(float);
+  const int bw = nv <= 6 ? 16 : 12;                // LnBwdCfg<NV>::WARPS
+  const int blocks_needed = (rows + bw - 1) / bw;
+  const int max_blocks = vitb_num_sms();          // one block per SM (the warps' slices take 147-184 KB)
+  const int grid = blocks_needed < max_blocks ? blocks_needed : max_blocks;
+  const size_t smem = static_cast<size_t>(bw) * 3 * D * sizeof(float);
   __nv_bfloat16* dh = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
   __nv_bfloat16* dl = reinterpret_cast<__nv_bfloat16*>(dx_bf16_lo);
 #define VITB_LNB(DYB, CS)                                                                        \
-  VITB_NV_SWITCH(nv, (lerr = vitb_launch(ln_bwd_kernel<NV, DYB, CS>, dim3(grid), dim3(kWarpsPerBlock * 32), smem,  \
+  VITB_NV_SWITCH(nv, (lerr = cudaFuncSetAttribute(ln_bwd_kernel<NV, DYB, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                                  static_cast<int>(LnBwdCfg<NV>::SMEM)),                          \
+                      lerr = (lerr != cudaSuccess) ? lerr :                                                       \
+                             vitb_launch(ln_bwd_kernel<NV, DYB, CS>, dim3(grid), dim3(LnBwdCfg<NV>::WARPS * 32), smem,  \
                                          stream, dy, x, x_row_stride, mean, rstd, gamma, rows, dres,              \
                                          dres_row_stride, dx_f32, dx_row_stride, dh, dl, dgamma, dbeta, dcolsum)))
   cudaError_t lerr = cudaSuccess;
