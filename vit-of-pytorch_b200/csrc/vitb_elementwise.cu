@@ -60,6 +60,9 @@ im2col_kernel(const float* __restrict__ img, int Bsz, int Cin, int H, int W, int
   const int kgroups = ldk >> 3;
   const long long total = static_cast<long long>(Bsz) * gh * gw * kgroups;
   const int Kreal = Cin * P * P;
+  // 16-byte loads need every group start 16-byte aligned: patch width a multiple of 8 pixels, row pitch a multiple of
+  // 4 floats, aligned base
+  const bool vec8 = (P % 8 == 0) && (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(img) & 15u) == 0);
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
     const int kg = static_cast<int>(i % kgroups);
@@ -68,17 +71,29 @@ im2col_kernel(const float* __restrict__ img, int Bsz, int Cin, int H, int W, int
     const int py = static_cast<int>((r / gw) % gh);
     const int b = static_cast<int>(r / (static_cast<long long>(gw) * gh));
     float v[8];
+    if (vec8 && kg * 8 + 8 <= Kreal) {
+      // P % 8 == 0: the eight k of this group are eight consecutive pixels of one patch row -> two 16-byte loads
+      const int k = kg * 8;
+      const int c = k / (P * P);
+      const int rem = k - c * P * P;
+      const int ph = rem / P, pw = rem - ph * P;
+      const float4* src = reinterpret_cast<const float4*>(
+          img + ((static_cast<long long>(b) * Cin + c) * H + (py * P + ph)) * W + (px * P + pw));
+      const float4 a0 = __ldg(src), a1 = __ldg(src + 1);
+      v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
+    } else {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int k = kg * 8 + j;
-      float val = 0.f;
-      if (k < Kreal) {
-        const int c = k / (P * P);
-        const int rem = k - c * P * P;
-        const int ph = rem / P, pw = rem - ph * P;
-        val = img[((static_cast<long long>(b) * Cin + c) * H + (py * P + ph)) * W + (px * P + pw)];
+      for (int j = 0; j < 8; ++j) {
+        const int k = kg * 8 + j;
+        float val = 0.f;
+        if (k < Kreal) {
+          const int c = k / (P * P);
+          const int rem = k - c * P * P;
+          const int ph = rem / P, pw = rem - ph * P;
+          val = img[((static_cast<long long>(b) * Cin + c) * H + (py * P + ph)) * W + (px * P + pw)];
+        }
+        v[j] = val;
       }
-      v[j] = val;
     }
     uint4 h;
     h.x = pack_bf16x2(v[0], v[1]); h.y = pack_bf16x2(v[2], v[3]);
