@@ -231,6 +231,31 @@ def test_gemm_gelu_dg_packed_pair_epilogue(M, N, with_bias, monkeypatch):
     assert rel_l2(outs["1"][0], outs["0"][0]) < 2e-3 and rel_l2(outs["1"][1], outs["0"][1]) < 2e-3
 
 
+@pytest.mark.parametrize("M,N,with_colsum", [(777, 3072, True), (300, 200, True), (1000, 768, False), (25216, 3072, True)])
+def test_gemm_mul_aux_register_layout_epilogue(M, N, with_colsum, monkeypatch):
+    """VITB_EPI_ROWMUL=1: v *= aux in the TMEM register layout (aux rows prefetched a chunk ahead, TMA stores, column
+    sums by a warp transpose-reduce) against the same reference and the staged epilogue."""
+    import vitb200
+    K = 256
+    dy, W2, ref = _operands(M, N, K, False, True, seed=93)
+    aux = torch.full((M + 5, N), float("nan"), dtype=torch.bfloat16, device="cuda")     # rows past M must not be read into the sums
+    aux[:M] = _mk((M, N), 94)
+    want = ref * aux[:M].float()
+    res = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("VITB_EPI_ROWMUL", flag)
+        cs = torch.ones(N, device="cuda") if with_colsum else None
+        out = torch.full((M + 3, N), 7.0, dtype=torch.bfloat16, device="cuda")
+        vitb200.ops.gemm(dy, W2, b_mn=True, epilogue=vitb200.ops.EPI_MUL_AUX, aux=aux[:M], colsum=cs, out=out[:M])
+        torch.cuda.synchronize()
+        assert rel_l2(out[:M], want) < 4e-3, flag
+        assert bool((out[M:] == 7.0).all()), flag
+        if with_colsum:
+            assert rel_l2(cs, want.sum(0) + 1.0) < 4e-3, flag
+        res[flag] = out[:M].clone()
+    assert torch.equal(res["0"], res["1"])          # same fp32 product, same rounding: bit-identical tiles
+
+
 def test_gemm_bf16_tma_store_respects_row_and_column_tails_and_strided_outputs():
     """bf16 outputs leave through 32x32 TMA-store tiles: rows >= M / columns >= N are clipped by the tensor map,
     and a column slice of a wider buffer (the packed q|k|v projection output) keeps its neighbours intact."""

@@ -37,6 +37,16 @@ for rep in range(2):
         ms = timeit(lambda: vitb200.ops.gemm(A, B, out=out, bias=bias, epilogue=vitb200.ops.EPI_GELU_DG, d2=d2))
         lines.append("fc1 gelu+gelu' VITB_EPI_PACKED=%s  %.4f ms  %.0f TF" % (flag, ms, fl / ms / 1e9))
         print(lines[-1], flush=True)
+dy = torch.randn(T, D, device="cuda").to(bf)
+W2 = torch.randn(D, M, device="cuda").to(bf)
+aux = torch.randn(T, M, device="cuda").to(bf)
+cs = torch.zeros(M, device="cuda")
+for rep in range(2):
+    for flag in ("0", "1"):
+        os.environ["VITB_EPI_ROWMUL"] = flag
+        ms = timeit(lambda: vitb200.ops.gemm(dy, W2, b_mn=True, out=out, epilogue=vitb200.ops.EPI_MUL_AUX, aux=aux, colsum=cs))
+        lines.append("fc2 dgrad * gelu' + colsum VITB_EPI_ROWMUL=%s  %.4f ms  %.0f TF" % (flag, ms, fl / ms / 1e9))
+        print(lines[-1], flush=True)
 x = torch.randn(T, 3 * D, device="cuda").to(bf)
 o3 = [torch.zeros(D, device="cuda") for _ in range(3)]
 ms = timeit(lambda: vitb200.ops.colsum3(x, *o3))

@@ -73,6 +73,7 @@ struct GemmDev {
   int d2_grad;       // VITB_EPI_GELU_DG: D2 receives gelu'(v) instead of v
   int aux_grad;      // VITB_EPI_MUL_AUX: aux already holds gelu'(z); the epilogue only multiplies
   int packed_epi;    // GELU + GELU' epilogue on packed fp32 pairs with the bias staged in shared memory (VITB_EPI_PACKED)
+  int rowmul;        // VITB_EPI_MUL_AUX in the TMEM register layout: aux rows prefetched a chunk ahead, TMA stores (VITB_EPI_ROWMUL)
 };
 
 struct TileCoord {
@@ -479,6 +480,72 @@ __device__ __forceinline__ void epi_rows_gelu_dg_packed(const CUtensorMap* tmD, 
   tma_tile_release(tmD, bufg, lane, row_base, col0);
 }
 
+// ---- v *= aux in the TMEM register layout (the fc2 dgrad of the fused block: dz = (dy W2) * gelu'(z)) ------------
+// The staged version of this epilogue transposes every 32 x 32 chunk through padded fp32 shared memory so that the
+// aux loads and the stores are row-coalesced; its eight warps then sit on a chain of dependent shared-memory round
+// trips per chunk (profiles/ncu_r01c.txt: 31 % issue-active, 0.161 ms against 0.095 ms for the bare GEMM).  Here the
+// thread that owns accumulator row r reads its own 64 bytes of aux (four 16-byte loads, requested one chunk ahead),
+// multiplies in registers, and the bf16 tile leaves through the TMA store path of the plain epilogue.  The column
+// sums (bias gradient of fc1) come from a transpose-reduce across the warp: 31 shuffles leave column j's sum over
+// the 32 rows in lane j, one 128-byte red per chunk.
+__device__ __forceinline__ void aux_rows_load(const GemmDev& p, int lane, int row_base, int col0, uint4 (&dst)[4]) {
+  const int row = row_base + lane;
+  const char* ap = reinterpret_cast<const char*>(p.aux) + (static_cast<long long>(row) * p.ldaux + col0) * 2;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    dst[u] = make_uint4(0u, 0u, 0u, 0u);
+    if (row < p.M && col0 + 8 * u < p.N) dst[u] = __ldg(reinterpret_cast<const uint4*>(ap) + u);
+  }
+}
+// in: v[j] = this lane's row, column j.  out: the sum over the warp's 32 rows of column `lane`.
+__device__ __forceinline__ float warp_transpose_sum32(const float (&v)[32], int lane) {
+  float a[16], b[8], c[4], d[2];
+  const bool h16 = (lane & 16) != 0, h8 = (lane & 8) != 0, h4 = (lane & 4) != 0, h2 = (lane & 2) != 0, h1 = (lane & 1) != 0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float keep = h16 ? v[j + 16] : v[j], send = h16 ? v[j] : v[j + 16];
+    a[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float keep = h8 ? a[j + 8] : a[j], send = h8 ? a[j] : a[j + 8];
+    b[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float keep = h4 ? b[j + 4] : b[j], send = h4 ? b[j] : b[j + 4];
+    c[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const float keep = h2 ? c[j + 2] : c[j], send = h2 ? c[j] : c[j + 2];
+    d[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  const float keep = h1 ? d[1] : d[0], send = h1 ? d[0] : d[1];
+  return keep + __shfl_xor_sync(0xffffffffu, send, 1);
+}
+__device__ __forceinline__ void epi_rows_mul_aux(const GemmDev& p, const CUtensorMap* tmD, uint32_t tbuf, int& which,
+                                                 int lane, int row_base, int col0, const uint32_t (&r)[32],
+                                                 const uint4 (&ax)[4]) {
+  float v[32];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    v[8 * u + 0] = __uint_as_float(r[8 * u + 0]) * bf16_lo(ax[u].x);
+    v[8 * u + 1] = __uint_as_float(r[8 * u + 1]) * bf16_hi(ax[u].x);
+    v[8 * u + 2] = __uint_as_float(r[8 * u + 2]) * bf16_lo(ax[u].y);
+    v[8 * u + 3] = __uint_as_float(r[8 * u + 3]) * bf16_hi(ax[u].y);
+    v[8 * u + 4] = __uint_as_float(r[8 * u + 4]) * bf16_lo(ax[u].z);
+    v[8 * u + 5] = __uint_as_float(r[8 * u + 5]) * bf16_hi(ax[u].z);
+    v[8 * u + 6] = __uint_as_float(r[8 * u + 6]) * bf16_lo(ax[u].w);
+    v[8 * u + 7] = __uint_as_float(r[8 * u + 7]) * bf16_hi(ax[u].w);
+  }
+  if (p.colsum != nullptr) {   // rows >= M and columns >= N hold exact zeros (zero-filled operands, zeroed aux)
+    const float s = warp_transpose_sum32(v, lane);
+    if (col0 + lane < p.N) atomicAdd(p.colsum + col0 + lane, s);
+  }
+  tma_store_rows_bf16(tmD, tbuf, which, lane, v, row_base, col0);
+}
+
 // Scalar epilogue with every option (row bias, patch-embedding row remap, odd widths): lane == column.
 __device__ __noinline__ void epi_generic(const GemmDev& p, uint32_t stg, int lane, int row_base, int col0,
                                          bool lead_split) {
@@ -675,6 +742,9 @@ vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const bool packed = tma_path && mode == 2 && p.packed_epi != 0 && p.D2 != nullptr && p.d2_grad != 0;
     const uint32_t bias_slots = (tbuf == stg) ? stg + 2u * kTmaTileBytes : stg;
     const bool has_bias = p.bias != nullptr;
+    const bool rowmul = p.rowmul != 0 && mode == 3;   // bf16 MUL_AUX without bias: register layout + TMA stores
+    uint4 aux_next[4];                                  // this lane's 64 bytes of aux for the chunk that comes next
+    if (rowmul && lane == 0) tma_prefetch_desc(&tmD);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile);
       const int n0 = t.n_blk * BN;
@@ -682,7 +752,9 @@ vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       // bias-type terms are added exactly once: by the split that owns the first k-block
       const bool lead_split = (t.g0 == 0);
       const int half = (warp - kEpiWarp0) >> 2;  // which half of the tile's columns this warp drains
-      {   // the side operand of this warp's first chunk is requested before the accumulator is waited for
+      if (rowmul) {
+        aux_rows_load(p, lane, row_base, n0 + half * (BN / 64) * 32, aux_next);
+      } else {   // the side operand of this warp's first chunk is requested before the accumulator is waited for
         const int colf = n0 + half * (BN / 64) * 32;
         if (colf < p.N) {
           switch (mode) {
@@ -725,6 +797,15 @@ vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           epi_rows_gelu_dg_packed(&tmD, &tmD2, tbuf, tma_which, lane, row_base, col0, r, slot, has_bias);
           continue;
         }
+        if (rowmul) {
+          uint4 aux_cur[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) aux_cur[u] = aux_next[u];
+          if (next_col0 >= 0) aux_rows_load(p, lane, row_base, next_col0, aux_next);   // flies during this chunk
+          tmem_ld_wait();
+          epi_rows_mul_aux(p, &tmD, tbuf, tma_which, lane, row_base, col0, r, aux_cur);
+          continue;
+        }
         tmem_ld_wait();
         if (tma_path) {    // bf16 outputs without residual / column sums: math in registers, tiles leave by TMA
           if (mode == 2) epi_rows_bf16_tma<VITB_EPI_GELU>(p, &tmD, &tmD2, tbuf, tma_which, lane, row_base, col0, r);
@@ -756,7 +837,7 @@ vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
-    if (tma_path && lane == 0) bulk_wait_all();   // staging tiles must outlive the stores that read them
+    if ((tma_path || rowmul) && lane == 0) bulk_wait_all();   // staging tiles must outlive the stores that read them
   }
 
   tc_fence_before();
@@ -1097,6 +1178,19 @@ extern "C" int vitb_gemm(const vitb_gemm_params* p, void* stream_) {
       if (st != VITB_OK) return st;
     }
     d.tma_store = 1;
+  }
+  d.rowmul = 0;
+  {
+    const char* re = getenv("VITB_EPI_ROWMUL");     // A/B switch of the register-layout MUL_AUX epilogue
+    const bool want = re != nullptr && atoi(re) != 0;
+    if (want && d.aux_grad && d.vec_ok && d.d_bf16 && p->N % 8 == 0 && p->residual == nullptr && !p->accumulate &&
+        p->bias == nullptr && p->D2 == nullptr && p->ldd % 8 == 0 && (reinterpret_cast<uintptr_t>(p->D) & 15u) == 0 &&
+        p->ldaux % 8 == 0 && (reinterpret_cast<uintptr_t>(p->aux) & 15u) == 0 &&
+        (p->colsum == nullptr || (reinterpret_cast<uintptr_t>(p->colsum) & 3u) == 0)) {
+      st = vitb_make_tmap_2d_bf16_sw64(&tm[6], p->D, (uint64_t)p->N, (uint64_t)p->M, (uint64_t)p->ldd * 2, 32, 32);
+      if (st != VITB_OK) return st;
+      d.rowmul = 1;
+    }
   }
   // weight gradients (both operands MN-major, fp32 accumulation, one K segment) run on CTA pairs
   // (measured, profiles/gemm_bench_r01b.txt: dW fc1 0.099 -> 0.090 ms, dW fc2 0.104 -> 0.089 ms, i.e. 1.33 PFLOP/s)
