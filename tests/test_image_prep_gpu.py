@@ -108,7 +108,7 @@ def test_model_on_patch_columns_equals_model_on_loader_batch(mode):
         vitb200.functional.cross_entropy(lb, labels).backward()
         gb = net.embedding.weight.grad.clone()
     assert torch.equal(la, lb)
-    assert rel_l2(gb, ga) < 1e-6          # wgrad accumulates with fp32 atomics: order may differ
+    assert rel_l2(gb, ga) < 1e-5          # wgrad accumulates with fp32 atomics (split-K): the order differs run to run
 
 
 def test_bad_arguments_raise():
