@@ -47,6 +47,22 @@ for rep in range(2):
         ms = timeit(lambda: vitb200.ops.gemm(dy, W2, b_mn=True, out=out, epilogue=vitb200.ops.EPI_MUL_AUX, aux=aux, colsum=cs))
         lines.append("fc2 dgrad * gelu' + colsum VITB_EPI_ROWMUL=%s  %.4f ms  %.0f TF" % (flag, ms, fl / ms / 1e9))
         print(lines[-1], flush=True)
+a2 = torch.randn(T, M, device="cuda").to(bf)
+w2 = torch.randn(D, M, device="cuda").to(bf)
+res = torch.randn(T, D, device="cuda")
+o32 = torch.empty(T, D, device="cuda")
+b2 = torch.randn(D, device="cuda")
+wo = torch.randn(D, D, device="cuda").to(bf)
+for rep in range(2):
+    for flag in ("0", "1"):                      # experimental: fp32 + residual epilogue in the register layout
+        os.environ["VITB_EPI_ROWRES"] = flag
+        ms = timeit(lambda: vitb200.ops.gemm(a2, w2, out=o32, bias=b2, residual=res))
+        lines.append("fc2 fwd f32+res VITB_EPI_ROWRES=%s  %.4f ms  %.0f TF" % (flag, ms, fl / ms / 1e9))
+        print(lines[-1], flush=True)
+        ms = timeit(lambda: vitb200.ops.gemm(A, wo, b_mn=True, out=o32, bias=b2, residual=res))
+        lines.append("out-proj f32+res VITB_EPI_ROWRES=%s  %.4f ms  %.0f TF" % (flag, ms, 2.0 * T * D * D / ms / 1e9))
+        print(lines[-1], flush=True)
+os.environ["VITB_EPI_ROWRES"] = "0"
 x = torch.randn(T, 3 * D, device="cuda").to(bf)
 o3 = [torch.zeros(D, device="cuda") for _ in range(3)]
 ms = timeit(lambda: vitb200.ops.colsum3(x, *o3))

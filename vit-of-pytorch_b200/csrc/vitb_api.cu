@@ -81,7 +81,8 @@ int vitb_num_sms() {
 
 namespace {
 int make_tmap(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-              const uint32_t* box, CUtensorMapSwizzle swizzle, uint32_t span_bytes) {
+              const uint32_t* box, CUtensorMapSwizzle swizzle, uint32_t span_bytes,
+              CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, uint32_t esize = 2u) {
   int st = load_encode();
   if (st != VITB_OK) return st;
   VITB_REQUIRE(rank >= 1 && rank <= 5, VITB_ERR_BAD_ARG, "tensor map rank %d", rank);
@@ -103,9 +104,9 @@ int make_tmap(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims,
                  "TMA stride[%d]=%llu bytes is not a multiple of 16", i,
                  (unsigned long long)strides_bytes[i]);
   }
-  VITB_REQUIRE(box[0] * 2u <= span_bytes, VITB_ERR_BAD_ARG, "TMA inner box %u exceeds the %uB swizzle span",
+  VITB_REQUIRE(box[0] * esize <= span_bytes, VITB_ERR_BAD_ARG, "TMA inner box %u exceeds the %uB swizzle span",
                box[0], span_bytes);
-  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank,
+  CUresult r = g_encode(out, dtype, (cuuint32_t)rank,
                         const_cast<void*>(ptr), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -138,6 +139,14 @@ int vitb_make_tmap_2d_bf16_sw64(CUtensorMap* out, const void* ptr, uint64_t inne
   uint64_t str[1] = {outer_stride_bytes};
   uint32_t box[2] = {box_inner, box_outer};
   return make_tmap(out, ptr, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B, 64u);
+}
+
+int vitb_make_tmap_2d_f32_sw64(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer,
+                               uint64_t outer_stride_bytes, uint32_t box_inner, uint32_t box_outer) {
+  uint64_t dims[2] = {inner, outer};
+  uint64_t str[1] = {outer_stride_bytes};
+  uint32_t box[2] = {box_inner, box_outer};
+  return make_tmap(out, ptr, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B, 64u, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4u);
 }
 
 extern "C" {

@@ -440,6 +440,9 @@ int vitb_make_tmap_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, ui
 // Same with SWIZZLE_64B (inner box <= 32 elements): the epilogue's TMA-store staging tiles of 32 x 32 bf16.
 int vitb_make_tmap_2d_bf16_sw64(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer,
                                 uint64_t outer_stride_bytes, uint32_t box_inner, uint32_t box_outer);
+// fp32 tensor, SWIZZLE_64B (inner box <= 16 elements): 32 x 16 fp32 TMA-store staging tiles (same 2 KiB tile geometry).
+int vitb_make_tmap_2d_f32_sw64(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer,
+                               uint64_t outer_stride_bytes, uint32_t box_inner, uint32_t box_outer);
 // N-D (rank<=5) bf16 tensor, SWIZZLE_128B; strides[] has rank-1 entries (bytes) for dims 1..
 int vitb_make_tmap_nd_bf16(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims,
                            const uint64_t* strides_bytes, const uint32_t* box);
