@@ -563,10 +563,11 @@ __device__ __forceinline__ void res_rows_load(const GemmDev& p, int lane, int ro
 }
 __device__ __forceinline__ void epi_rows_res_f32(const CUtensorMap* tmD, uint32_t tbuf, int& which, int lane, int row_base,
                                                  int col0, const uint32_t (&r)[32], const uint4 (&res)[8],
-                                                 uint32_t bias_slot, bool has_bias) {
+                                                 uint32_t bias_slot, bool has_bias, int cols_left) {
   const uint32_t x = (static_cast<uint32_t>(lane) >> 1) & 3u;   // SWIZZLE_64B: 16-byte unit ^= address bits [7,9)
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
+    if (h * 16 >= cols_left) break;   // warp-uniform: the second half-tile lies wholly past column N
     const uint32_t buf = tma_tile_acquire(tbuf, which, lane);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -857,7 +858,7 @@ vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           for (int u = 0; u < 8; ++u) res_cur[u] = res_next[u];
           if (next_col0 >= 0) res_rows_load(p, lane, row_base, next_col0, res_next);   // flies during this chunk
           tmem_ld_wait();
-          epi_rows_res_f32(&tmD, tbuf, tma_which, lane, row_base, col0, r, res_cur, slot, has_bias);
+          epi_rows_res_f32(&tmD, tbuf, tma_which, lane, row_base, col0, r, res_cur, slot, has_bias, p.N - col0);
           continue;
         }
         if (rowmul) {
