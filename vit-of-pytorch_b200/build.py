@@ -34,6 +34,13 @@ def _nvcc():
     raise RuntimeError("nvcc not found (set NVCC)")
 
 
+# extra objects compiled from the same source with other macros: (source, object stem, extra flags)
+VARIANTS = [
+    # ablation build of the GEMM (entry points vitb_gemm_diag / vitb_gemm_diag_mask, tools/epi_ablate.py)
+    ("vitb_gemm.cu", "vitb_gemm_diag", ["-DVITB_GEMM_DIAG=1"]),
+]
+
+
 def sources():
     return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
 
@@ -49,14 +56,14 @@ def _digest(path, flags):
     return h.hexdigest()
 
 
-def _compile_one(nvcc, src, verbose):
+def _compile_one(nvcc, src, verbose, stem=None, extra=()):
     path = os.path.join(CSRC, src)
-    obj = os.path.join(OBJ, src[:-3] + ".o")
+    obj = os.path.join(OBJ, (stem or src[:-3]) + ".o")
     stamp = obj + ".sha"
-    dig = _digest(path, NVCC_FLAGS)
+    dig = _digest(path, NVCC_FLAGS + list(extra))
     if os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == dig:
         return obj, ""
-    cmd = [nvcc] + NVCC_FLAGS + ["-I", INCLUDE, "-c", path, "-o", obj]
+    cmd = [nvcc] + NVCC_FLAGS + list(extra) + ["-I", INCLUDE, "-c", path, "-o", obj]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, res.stdout, res.stderr))
@@ -71,9 +78,9 @@ def build(verbose=False, force=False):
     if force:
         for f in os.listdir(OBJ):
             os.remove(os.path.join(OBJ, f))
-    srcs = sources()
-    with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
-        results = list(ex.map(lambda s: _compile_one(nvcc, s, verbose), srcs))
+    jobs = [(s, None, ()) for s in sources()] + [(s, stem, tuple(extra)) for s, stem, extra in VARIANTS]
+    with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
+        results = list(ex.map(lambda j: _compile_one(nvcc, j[0], verbose, j[1], j[2]), jobs))
     objs = [r[0] for r in results]
     for _, log in results:
         if log:

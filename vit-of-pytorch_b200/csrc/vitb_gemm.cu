@@ -20,6 +20,21 @@
 #include "../../include/vitb200.h"
 #include "vitb_common.cuh"
 
+// Ablation build (vit-of-pytorch_b200/build.py compiles this file a second time with -DVITB_GEMM_DIAG=1 into the
+// entry points vitb_gemm_diag / vitb_gemm_diag_mask): a bit mask switches parts of the epilogue OFF so that one GPU
+// call can time the kernel without them (tools/epi_ablate.py).  Results are then WRONG by construction; the product
+// entry point vitb_gemm is compiled without the macro and contains none of this.
+//   1 no TMA store issue   2 no epilogue math   4 no TMEM load   8 no staging-tile writes   16 no side / bias loads
+//   32 no per-chunk work at all (handshakes only: the bare mainloop)   64 no async-proxy fence   128 no column sums
+#ifdef VITB_GEMM_DIAG
+__device__ __constant__ int g_diag_mask;
+#define VITB_DIAG(bit) ((g_diag_mask & (bit)) != 0)
+#define VITB_GEMM_ENTRY vitb_gemm_diag
+#else
+#define VITB_DIAG(bit) false
+#define VITB_GEMM_ENTRY vitb_gemm
+#endif
+
 namespace {
 
 using namespace vitb;
@@ -380,13 +395,14 @@ __device__ __forceinline__ uint32_t tma_tile_acquire(uint32_t tbuf, int& which, 
 __device__ __forceinline__ void tma_tile_write_unit(uint32_t buf, int lane, int j, float a0, float a1, float a2, float a3,
                                                     float a4, float a5, float a6, float a7) {
   const uint32_t x = (static_cast<uint32_t>(lane) >> 1) & 3u;   // SWIZZLE_64B: 16-byte unit ^= address bits [7,9)
+  if (VITB_DIAG(8)) return;
   st_shared_v4(buf + static_cast<uint32_t>(lane) * 64u + ((static_cast<uint32_t>(j) ^ x) << 4), pack_bf16x2(a0, a1),
                pack_bf16x2(a2, a3), pack_bf16x2(a4, a5), pack_bf16x2(a6, a7));
 }
 __device__ __forceinline__ void tma_tile_release(const CUtensorMap* tm, uint32_t buf, int lane, int row_base, int col0) {
-  fence_proxy_async_smem();               // generic-proxy writes -> visible to the async proxy (TMA)
+  if (!VITB_DIAG(64)) fence_proxy_async_smem();   // generic-proxy writes -> visible to the async proxy (TMA)
   __syncwarp();
-  if (lane == 0) {
+  if (lane == 0 && !VITB_DIAG(1)) {
     tma_store_2d(tm, buf, col0, row_base);
     bulk_commit();
   }
@@ -452,7 +468,7 @@ __device__ __forceinline__ void epi_rows_gelu_dg_packed(const CUtensorMap* tmD, 
     float v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[8 * j + i]);
-    if (has_bias) {
+    if (has_bias && !VITB_DIAG(16)) {
       const float4 b0 = ld_shared_f4_16(bias_slot + j * 32), b1 = ld_shared_f4_16(bias_slot + j * 32 + 16);
       uint64_t s;
       s = add2(pk2(v[0], v[1]), pk2(b0.x, b0.y)); upk2(s, v[0], v[1]);
@@ -464,20 +480,23 @@ __device__ __forceinline__ void epi_rows_gelu_dg_packed(const CUtensorMap* tmD, 
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       uint64_t g, dg;
-      gelu_fast_both2(v[2 * i], v[2 * i + 1], g, dg);
+      if (VITB_DIAG(2)) { g = pk2(v[2 * i], v[2 * i + 1]); dg = g; }
+      else gelu_fast_both2(v[2 * i], v[2 * i + 1], g, dg);
       gq[4 * j + i] = pack_bf16x2_pair(g);
       dq[i] = pack_bf16x2_pair(dg);
     }
     const uint32_t x = (static_cast<uint32_t>(lane) >> 1) & 3u;   // SWIZZLE_64B, as tma_tile_write_unit
-    st_shared_v4(bufd + static_cast<uint32_t>(lane) * 64u + ((static_cast<uint32_t>(j) ^ x) << 4), dq[0], dq[1], dq[2], dq[3]);
+    if (!VITB_DIAG(8))
+      st_shared_v4(bufd + static_cast<uint32_t>(lane) * 64u + ((static_cast<uint32_t>(j) ^ x) << 4), dq[0], dq[1], dq[2], dq[3]);
   }
   tma_tile_release(tmD2, bufd, lane, row_base, col0);
   const uint32_t bufg = tma_tile_acquire(tbuf, which, lane);   // value tile
   const uint32_t x = (static_cast<uint32_t>(lane) >> 1) & 3u;
 #pragma unroll
   for (int j = 0; j < 4; ++j)
-    st_shared_v4(bufg + static_cast<uint32_t>(lane) * 64u + ((static_cast<uint32_t>(j) ^ x) << 4), gq[4 * j], gq[4 * j + 1],
-                 gq[4 * j + 2], gq[4 * j + 3]);
+    if (!VITB_DIAG(8))
+      st_shared_v4(bufg + static_cast<uint32_t>(lane) * 64u + ((static_cast<uint32_t>(j) ^ x) << 4), gq[4 * j], gq[4 * j + 1],
+                   gq[4 * j + 2], gq[4 * j + 3]);
   tma_tile_release(tmD, bufg, lane, row_base, col0);
 }
 
@@ -495,7 +514,7 @@ __device__ __forceinline__ void aux_rows_load(const GemmDev& p, int lane, int ro
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
     dst[u] = make_uint4(0u, 0u, 0u, 0u);
-    if (row < p.M && col0 + 8 * u < p.N) dst[u] = __ldg(reinterpret_cast<const uint4*>(ap) + u);
+    if (row < p.M && col0 + 8 * u < p.N && !VITB_DIAG(16)) dst[u] = __ldg(reinterpret_cast<const uint4*>(ap) + u);
   }
 }
 // in: v[j] = this lane's row, column j.  out: the sum over the warp's 32 rows of column `lane`.
@@ -540,7 +559,7 @@ __device__ __forceinline__ void epi_rows_mul_aux(const GemmDev& p, const CUtenso
     v[8 * u + 6] = __uint_as_float(r[8 * u + 6]) * bf16_lo(ax[u].w);
     v[8 * u + 7] = __uint_as_float(r[8 * u + 7]) * bf16_hi(ax[u].w);
   }
-  if (p.colsum != nullptr) {   // rows >= M and columns >= N hold exact zeros (zero-filled operands, zeroed aux)
+  if (p.colsum != nullptr && !VITB_DIAG(128)) {   // rows >= M and columns >= N hold exact zeros (zero-filled operands, zeroed aux)
     const float s = warp_transpose_sum32(v, lane);
     if (col0 + lane < p.N) atomicAdd(p.colsum + col0 + lane, s);
   }
@@ -558,7 +577,7 @@ __device__ __forceinline__ void res_rows_load(const GemmDev& p, int lane, int ro
 #pragma unroll
   for (int u = 0; u < 8; ++u) {
     dst[u] = make_uint4(0u, 0u, 0u, 0u);
-    if (row < p.M && col0 + 4 * u < p.N) dst[u] = __ldg(reinterpret_cast<const uint4*>(rp) + u);
+    if (row < p.M && col0 + 4 * u < p.N && !VITB_DIAG(16)) dst[u] = __ldg(reinterpret_cast<const uint4*>(rp) + u);
   }
 }
 __device__ __forceinline__ void epi_rows_res_f32(const CUtensorMap* tmD, uint32_t tbuf, int& which, int lane, int row_base,
@@ -829,6 +848,13 @@ vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         if (col0 >= p.N) break;
         const int next_col0 = (c + 1 < (half + 1) * (BN / 64) && col0 + 32 < p.N) ? col0 + 32 : -1;
         uint32_t r[32];
+#ifdef VITB_GEMM_DIAG
+        if (VITB_DIAG(32)) continue;
+        if (VITB_DIAG(4)) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = 0u;
+        } else
+#endif
         tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                                static_cast<uint32_t>(acc * BN + c * 32), r);
         if (packed) {
@@ -1113,7 +1139,14 @@ int launch(const CUtensorMap* tm, const GemmDev& d, int grid, cudaStream_t strea
 
 }  // namespace
 
-extern "C" int vitb_gemm(const vitb_gemm_params* p, void* stream_) {
+#ifdef VITB_GEMM_DIAG
+extern "C" int vitb_gemm_diag_mask(int mask) {   // synchronising; ablation tool only
+  VITB_CUDA_CHECK(cudaMemcpyToSymbol(g_diag_mask, &mask, sizeof(int)));
+  return VITB_OK;
+}
+#endif
+
+extern "C" int VITB_GEMM_ENTRY(const vitb_gemm_params* p, void* stream_) {
   VITB_REQUIRE(p != nullptr, VITB_ERR_BAD_ARG, "vitb_gemm: null params");
   VITB_REQUIRE(p->struct_bytes == (int)sizeof(vitb_gemm_params), VITB_ERR_BAD_ARG,
                "vitb_gemm: struct_bytes %d != %d (ABI mismatch)", p->struct_bytes,

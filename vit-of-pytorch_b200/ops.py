@@ -26,6 +26,9 @@ def _check_2d_rowmajor(t, what):
                           % (what, tuple(t.shape), tuple(t.stride())))
 
 
+GEMM_ABLATION = False   # set by tools/epi_ablate.py: route ops.gemm to vitb_gemm_diag
+
+
 def gemm(A, B, *, a_mn=False, b_mn=False, out=None, out_dtype=torch.bfloat16, bias=None,
          row_bias=None, row_bias_group=0, epilogue=EPI_NONE, d2=None, residual=None, aux=None,
          accumulate=False, split_k=0, row_remap_group=0, out_rows=None, colsum=None):
@@ -106,6 +109,9 @@ def gemm(A, B, *, a_mn=False, b_mn=False, out=None, out_dtype=torch.bfloat16, bi
         nbytes = 2.0 * (M + N) * ksum + M * N * esz * (1 + (d2 is not None) + (aux is not None)) + \
             (M * N * residual.element_size() if residual is not None else 0)
         PROFILE_GEMM.append((e0, e1, 2.0 * M * N * ksum, nbytes))
+        return out
+    if GEMM_ABLATION:      # tools/epi_ablate.py only: the ablation build of the kernel (results wrong by construction)
+        L.check(L._vitb_gemm_diag(C.byref(p), L.stream_ptr(out.device)), "vitb_gemm_diag")
         return out
     L.check(L._vitb_gemm(C.byref(p), L.stream_ptr(out.device)), "vitb_gemm")
     return out
