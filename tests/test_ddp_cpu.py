@@ -71,3 +71,62 @@ def test_grad_reducer_gloo_world_size_2():
         assert p.exitcode == 0
     assert all(ok for _, ok, _ in res), res
     assert all(order == [1, 0] for _, _, order in res), res
+
+
+def _active_loss_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import vitb200
+        from vitb200.resvit import ActiveLoss
+        g = torch.Generator().manual_seed(5)
+        x = torch.randn(4, 9, 3, generator=g)                       # global batch: 4 images, 9 tokens, 3 dynamic layers
+        theta = torch.tensor([0.3, -0.2, 0.1], requires_grad=True)  # the replicated "router parameters"
+        shard = x[rank * 2:(rank + 1) * 2]
+        loss = ActiveLoss(0.4, 1, sync_group=True)(torch.sigmoid(shard * theta))
+        loss.backward()
+        grad = theta.grad.clone()
+        dist.all_reduce(grad)                                       # what the data-parallel wrapper does: average
+        grad /= world
+        local = ActiveLoss(0.4, 1)(torch.sigmoid(shard * theta.detach()))
+        q.put((rank, float(loss), grad, float(local)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_active_loss_global_batch_semantics_gloo_world_size_2():
+    """ActiveLoss(sync_group=...) reproduces the loss AND, after the wrapper's gradient averaging, the gradient of the global
+    batch (res-vit/model.py:80-83 is (batch mean - target)^2, not linear in the batch mean); without it every replica sees
+    its own shard."""
+    from vitb200.resvit import ActiveLoss
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_active_loss_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(4, 9, 3, generator=g)
+    theta = torch.tensor([0.3, -0.2, 0.1], requires_grad=True)
+    ref = ActiveLoss(0.4, 1)(torch.sigmoid(x * theta))              # single process, whole batch
+    ref.backward()
+    for rank, loss, grad, local in res:
+        assert abs(loss - float(ref)) < 1e-7
+        assert torch.allclose(grad, theta.grad, atol=1e-7)
+    assert abs(res[0][3] - res[1][3]) > 1e-6                        # the per-replica losses do differ from each other
+    assert abs(0.5 * (res[0][3] + res[1][3]) - float(ref)) > 1e-8   # and their average is not the global loss
+
+
+def test_active_loss_without_a_process_group_is_the_reference_formula():
+    from vitb200.resvit import ActiveLoss
+    g = torch.Generator().manual_seed(6)
+    a = torch.rand(3, 7, 2, generator=g)
+    want = (a[:, 1:, :].mean() - 0.6) ** 2
+    assert torch.equal(ActiveLoss(0.6, 1)(a), want)
+    assert torch.equal(ActiveLoss(0.6, 1, sync_group=True)(a), want)      # no process group initialised: local semantics

@@ -107,9 +107,15 @@ class DataParallel(nn.Module):
     """module + fused optimizer -> data-parallel replica.  Call like the module; call optimizer.step()
     as usual (its pre-hook waits for the gradient all-reduce)."""
 
-    def __init__(self, module, optimizer, bucket_modules=None, process_group=None, broadcast=True):
+    def __init__(self, module, optimizer, bucket_modules=None, process_group=None, broadcast=True,
+                 global_active_loss=False):
+        """global_active_loss: Res-ViT's ActiveLoss is (batch mean - target)^2 (res-vit/model.py:80-83), not linear in
+        the batch mean; True makes it the loss of the GLOBAL batch (one scalar all-reduce per step, see
+        resvit.ActiveLoss) instead of each replica's own shard."""
         super().__init__()
         self.module = module
+        if global_active_loss and hasattr(module, "criterion_active"):
+            module.criterion_active.sync_group = process_group if process_group is not None else True
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed is not initialised (launch with torchrun)")
         if len(optimizer._flat) != 1:

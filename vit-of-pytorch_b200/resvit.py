@@ -69,12 +69,21 @@ class DistillLoss(nn.Module):
 
 
 class ActiveLoss(nn.Module):
-    """(mean keep-probability over non-reserved tokens - target)^2 (res-vit/model.py:61-85)."""
+    """(mean keep-probability over non-reserved tokens - target)^2 (res-vit/model.py:61-85).
 
-    def __init__(self, target, reserve_initials):
+    The loss is not linear in the batch mean, so under data parallelism the average of the per-replica losses is not the
+    loss of the global batch.  `sync_group` selects the semantics:
+      None (default)  per-replica, i.e. what each process computes on its shard;
+      a process group (or True for the default group)  the GLOBAL batch: one scalar all-reduce of the shard means, and a
+      surrogate whose value is (m - t)^2 with m the global mean and whose gradient, once the data-parallel wrapper has
+      averaged the replicas' gradients, is exactly d/dtheta (m - t)^2 — equal shard sizes assumed, as in the wrapper.
+    """
+
+    def __init__(self, target, reserve_initials, sync_group=None):
         super().__init__()
         self.target = target
         self.reserve_initials = reserve_initials
+        self.sync_group = sync_group
 
     @torch.no_grad()
     def metric(self, activation):
@@ -83,6 +92,13 @@ class ActiveLoss(nn.Module):
 
     def forward(self, activation):
         ratio = activation[:, self.reserve_initials:, :].float().mean()
+        if self.sync_group is not None and torch.distributed.is_available() and torch.distributed.is_initialized():
+            group = None if self.sync_group is True else self.sync_group
+            world = torch.distributed.get_world_size(group)
+            if world > 1:
+                m = ratio.detach().clone()
+                torch.distributed.all_reduce(m, op=torch.distributed.ReduceOp.SUM, group=group)
+                ratio = ratio + (m / world - ratio.detach())     # value: global mean; gradient: this shard's
         return (ratio - self.target) ** 2
 
 
