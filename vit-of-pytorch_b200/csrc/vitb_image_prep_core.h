@@ -96,54 +96,58 @@ VITB_HD Band band_of(const Args& a, int block) {
 }
 
 // Phase 1: horizontal pass of the band's source rows into scratch (planar per row: [r][c][x]); table copy.
+// A warp owns one (source row, channel) line at a time and its lanes walk the output columns, so the only integer
+// division is one per line (nthreads is a multiple of 32).
 VITB_HD void phase1(const Args& a, int block, int tid, int nthreads, uint8_t* scratch) {
   const Band bd = band_of(a, block);
   float* lut_s = reinterpret_cast<float*>(scratch + tmp_bytes(a.rows_cap, a.C, a.out_w));
   for (int i = tid; i < a.C * 256; i += nthreads) lut_s[i] = a.lut[i];
-  const int per_row = a.C * a.out_w;
-  const int total = bd.rows * per_row;
+  const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
+  const int lines = bd.rows * a.C;
   const uint8_t* img = a.src + static_cast<size_t>(bd.b) * a.H * a.W * a.C;
-  for (int i = tid; i < total; i += nthreads) {
-    const int r = i / per_row;
-    const int rem = i - r * per_row;
-    const int c = rem / a.out_w;
-    const int sx = rem - c * a.out_w;
+  for (int ln = warp; ln < lines; ln += nwarps) {
+    const int r = ln / a.C;
+    const int c = ln - r * a.C;
     const uint8_t* row = img + static_cast<size_t>(bd.r0 + r) * a.W * a.C + c;
-    int v;
-    if (a.xb) {
-      const int first = a.xb[2 * sx], n = a.xb[2 * sx + 1];
-      const int32_t* w = a.xc + static_cast<size_t>(sx) * a.xk;
-      int acc = 1 << (kPrecisionBits - 1);
-      for (int t = 0; t < n && t < a.xk; ++t) {
-        int xi = first + t;
-        xi = xi < 0 ? 0 : (xi >= a.W ? a.W - 1 : xi);
-        acc += static_cast<int>(row[static_cast<size_t>(xi) * a.C]) * w[t];
+    uint8_t* dst = scratch + static_cast<size_t>(ln) * a.out_w;
+    for (int sx = lane; sx < a.out_w; sx += 32) {
+      int v;
+      if (a.xb) {
+        const int first = a.xb[2 * sx], n = a.xb[2 * sx + 1];
+        const int32_t* w = a.xc + static_cast<size_t>(sx) * a.xk;
+        int acc = 1 << (kPrecisionBits - 1);
+        for (int t = 0; t < n && t < a.xk; ++t) {
+          int xi = first + t;
+          xi = xi < 0 ? 0 : (xi >= a.W ? a.W - 1 : xi);
+          acc += static_cast<int>(row[static_cast<size_t>(xi) * a.C]) * w[t];
+        }
+        v = clip8(acc);
+      } else {
+        v = row[static_cast<size_t>(sx) * a.C];
       }
-      v = clip8(acc);
-    } else {
-      v = row[static_cast<size_t>(sx) * a.C];
+      dst[sx] = static_cast<uint8_t>(v);
     }
-    scratch[i] = static_cast<uint8_t>(v);
   }
 }
 
 VITB_HD float bf16_round_f(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
-// Phase 2: vertical pass, flip, table lookup, and the three optional outputs.  Four consecutive output
-// columns per thread-iteration: one 16-byte store into the image, one 8-byte store into the patch operand.
+// Phase 2: vertical pass, flip, table lookup, and the three optional outputs.  A warp owns one (output row, channel)
+// line at a time — its window, weights and patch coordinates are computed once per line — and each lane produces four
+// consecutive output columns per step: one 16-byte store into the image (512 contiguous bytes per warp and step), one
+// 8-byte store into the patch operand.
 VITB_HD void phase2(const Args& a, int block, int tid, int nthreads, const uint8_t* scratch) {
   const Band bd = band_of(a, block);
   const float* lut_s = reinterpret_cast<const float*>(scratch + tmp_bytes(a.rows_cap, a.C, a.out_w));
   const int nq = (a.out_w + 3) >> 2;
-  const int total = (bd.oy1 - bd.oy0) * a.C * nq;
   const bool flip = a.flip != nullptr && a.flip[bd.b] != 0;
   const int per_row = a.C * a.out_w;
   const bool vec_cols = (a.P & 3) == 0 && (a.ldk & 3) == 0;
-  for (int i = tid; i < total; i += nthreads) {
-    const int q = i % nq;
-    const int rest = i / nq;
-    const int c = rest % a.C;
-    const int oy = bd.oy0 + rest / a.C;
+  const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
+  const int lines = (bd.oy1 - bd.oy0) * a.C;
+  for (int ln = warp; ln < lines; ln += nwarps) {
+    const int c = ln % a.C;
+    const int oy = bd.oy0 + ln / a.C;
     int yfirst = oy, yn = 1;
     const int32_t* w = nullptr;
     if (a.yb) {
@@ -152,73 +156,84 @@ VITB_HD void phase2(const Args& a, int block, int tid, int nthreads, const uint8
       yn = yn > a.yk ? a.yk : yn;
       w = a.yc + static_cast<size_t>(oy) * a.yk;
     }
-    int v8[4];
-    float val[4];
-    const int ox0 = q << 2;
-    const int cnt = a.out_w - ox0 < 4 ? a.out_w - ox0 : 4;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      v8[j] = 0;
-      val[j] = 0.f;
-      if (j < cnt) {
-        const int ox = ox0 + j;
-        const int sx = flip ? a.out_w - 1 - ox : ox;
-        int v;
-        if (w) {
-          int acc = 1 << (kPrecisionBits - 1);
-          for (int t = 0; t < yn; ++t) {
-            int rr = yfirst + t - bd.r0;
-            rr = rr < 0 ? 0 : (rr >= bd.rows ? bd.rows - 1 : rr);
-            acc += static_cast<int>(scratch[rr * per_row + c * a.out_w + sx]) * w[t];
-          }
-          v = clip8(acc);
-        } else {
-          v = scratch[(oy - bd.r0) * per_row + c * a.out_w + sx];
-        }
-        v8[j] = v;
-        val[j] = lut_s[c * 256 + v];
-      }
-    }
-    if (a.out_img) {
-      float* dst = a.out_img + ((static_cast<size_t>(bd.b) * a.C + c) * a.out_h + oy) * a.out_w + ox0;
-      if (cnt == 4 && a.vec4_img) {
-        *reinterpret_cast<float4*>(dst) = make_float4(val[0], val[1], val[2], val[3]);
-      } else {
-        for (int j = 0; j < cnt; ++j) dst[j] = val[j];
-      }
-    }
-    if (a.out_u8) {
-      uint8_t* dst = a.out_u8 + ((static_cast<size_t>(bd.b) * a.out_h + oy) * a.out_w + ox0) * a.C + c;
-      for (int j = 0; j < cnt; ++j) dst[static_cast<size_t>(j) * a.C] = static_cast<uint8_t>(v8[j]);
-    }
-    if (a.cols_hi && oy < a.gh * a.P) {
+    const float* lut_c = lut_s + c * 256;
+    const uint8_t* col_base = scratch + c * a.out_w;       // + row * per_row + sx
+    float* img_row = a.out_img ? a.out_img + ((static_cast<size_t>(bd.b) * a.C + c) * a.out_h + oy) * a.out_w : nullptr;
+    uint8_t* u8_row = a.out_u8 ? a.out_u8 + (static_cast<size_t>(bd.b) * a.out_h + oy) * a.out_w * a.C + c : nullptr;
+    const bool cols_line = a.cols_hi != nullptr && oy < a.gh * a.P;
+    size_t cols_row_base = 0;
+    int kbase = 0;
+    if (cols_line) {
       const int py = oy / a.P, ph = oy - py * a.P;
-      const size_t row_base = (static_cast<size_t>(bd.b) * a.gh + py) * a.gw;
-      const int kbase = (c * a.P + ph) * a.P;
-      if (vec_cols && cnt == 4 && ox0 + 3 < a.gw * a.P) {
-        const int px = ox0 / a.P, pw = ox0 - px * a.P;   // P % 4 == 0: the four columns share a patch
-        const size_t off = (row_base + px) * a.ldk + kbase + pw;
-        __nv_bfloat162 h01 = __floats2bfloat162_rn(val[0], val[1]);
-        __nv_bfloat162 h23 = __floats2bfloat162_rn(val[2], val[3]);
-        uint2 pk;
-        pk.x = *reinterpret_cast<uint32_t*>(&h01);
-        pk.y = *reinterpret_cast<uint32_t*>(&h23);
-        *reinterpret_cast<uint2*>(a.cols_hi + off) = pk;
-        if (a.cols_lo) {
-          __nv_bfloat162 l01 = __floats2bfloat162_rn(val[0] - bf16_round_f(val[0]), val[1] - bf16_round_f(val[1]));
-          __nv_bfloat162 l23 = __floats2bfloat162_rn(val[2] - bf16_round_f(val[2]), val[3] - bf16_round_f(val[3]));
-          pk.x = *reinterpret_cast<uint32_t*>(&l01);
-          pk.y = *reinterpret_cast<uint32_t*>(&l23);
-          *reinterpret_cast<uint2*>(a.cols_lo + off) = pk;
-        }
-      } else {
-        for (int j = 0; j < cnt; ++j) {
+      cols_row_base = (static_cast<size_t>(bd.b) * a.gh + py) * a.gw;
+      kbase = (c * a.P + ph) * a.P;
+    }
+    for (int q = lane; q < nq; q += 32) {
+      int v8[4];
+      float val[4];
+      const int ox0 = q << 2;
+      const int cnt = a.out_w - ox0 < 4 ? a.out_w - ox0 : 4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v8[j] = 0;
+        val[j] = 0.f;
+        if (j < cnt) {
           const int ox = ox0 + j;
-          if (ox >= a.gw * a.P) break;
-          const int px = ox / a.P, pw = ox - px * a.P;
-          const size_t off = (row_base + px) * a.ldk + kbase + pw;
-          a.cols_hi[off] = __float2bfloat16_rn(val[j]);
-          if (a.cols_lo) a.cols_lo[off] = __float2bfloat16_rn(val[j] - bf16_round_f(val[j]));
+          const int sx = flip ? a.out_w - 1 - ox : ox;
+          int v;
+          if (w) {
+            int acc = 1 << (kPrecisionBits - 1);
+            for (int t = 0; t < yn; ++t) {
+              int rr = yfirst + t - bd.r0;
+              rr = rr < 0 ? 0 : (rr >= bd.rows ? bd.rows - 1 : rr);
+              acc += static_cast<int>(col_base[rr * per_row + sx]) * w[t];
+            }
+            v = clip8(acc);
+          } else {
+            v = col_base[(oy - bd.r0) * per_row + sx];
+          }
+          v8[j] = v;
+          val[j] = lut_c[v];
+        }
+      }
+      if (img_row) {
+        float* dst = img_row + ox0;
+        if (cnt == 4 && a.vec4_img) {
+          *reinterpret_cast<float4*>(dst) = make_float4(val[0], val[1], val[2], val[3]);
+        } else {
+          for (int j = 0; j < cnt; ++j) dst[j] = val[j];
+        }
+      }
+      if (u8_row) {
+        uint8_t* dst = u8_row + static_cast<size_t>(ox0) * a.C;
+        for (int j = 0; j < cnt; ++j) dst[static_cast<size_t>(j) * a.C] = static_cast<uint8_t>(v8[j]);
+      }
+      if (cols_line) {
+        if (vec_cols && cnt == 4 && ox0 + 3 < a.gw * a.P) {
+          const int px = ox0 / a.P, pw = ox0 - px * a.P;   // P % 4 == 0: the four columns share a patch
+          const size_t off = (cols_row_base + px) * a.ldk + kbase + pw;
+          __nv_bfloat162 h01 = __floats2bfloat162_rn(val[0], val[1]);
+          __nv_bfloat162 h23 = __floats2bfloat162_rn(val[2], val[3]);
+          uint2 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&h01);
+          pk.y = *reinterpret_cast<uint32_t*>(&h23);
+          *reinterpret_cast<uint2*>(a.cols_hi + off) = pk;
+          if (a.cols_lo) {
+            __nv_bfloat162 l01 = __floats2bfloat162_rn(val[0] - bf16_round_f(val[0]), val[1] - bf16_round_f(val[1]));
+            __nv_bfloat162 l23 = __floats2bfloat162_rn(val[2] - bf16_round_f(val[2]), val[3] - bf16_round_f(val[3]));
+            pk.x = *reinterpret_cast<uint32_t*>(&l01);
+            pk.y = *reinterpret_cast<uint32_t*>(&l23);
+            *reinterpret_cast<uint2*>(a.cols_lo + off) = pk;
+          }
+        } else {
+          for (int j = 0; j < cnt; ++j) {
+            const int ox = ox0 + j;
+            if (ox >= a.gw * a.P) break;
+            const int px = ox / a.P, pw = ox - px * a.P;
+            const size_t off = (cols_row_base + px) * a.ldk + kbase + pw;
+            a.cols_hi[off] = __float2bfloat16_rn(val[j]);
+            if (a.cols_lo) a.cols_lo[off] = __float2bfloat16_rn(val[j] - bf16_round_f(val[j]));
+          }
         }
       }
     }
