@@ -3,12 +3,16 @@
 //   D[M,N] = epilogue( sum_seg A_seg[M,K_seg] * B_seg[N,K_seg]^T )        (contract: vitb200.h)
 //
 // Design (B200-first, not a port of anything in the reference — the reference only calls ATen):
-//   * persistent CTAs (one per SM), static tile scheduler, 256 threads, warp-specialised:
-//       warp 0   : TMA producer (cp.async.bulk.tensor, SWIZZLE_128B) into a 4/6-stage smem ring
-//       warp 1   : one elected thread issues tcgen05.mma (128 x BN x 16, bf16 -> fp32 in TMEM)
-//       warp 2   : TMEM allocator (2 accumulator stages so the epilogue overlaps the next tile)
-//       warps 4-7: epilogue — tcgen05.ld TMEM->registers, transpose through padded smem so that
-//                  every global access of the fused epilogue is row-coalesced
+//   * persistent CTAs (one per SM), static tile scheduler, 384 threads, warp-specialised:
+//       warp 0    : TMA producer (cp.async.bulk.tensor, SWIZZLE_128B) into a 4/6-stage smem ring
+//       warp 1    : one elected thread issues tcgen05.mma (128 x BN x 16, bf16 -> fp32 in TMEM)
+//       warp 2    : TMEM allocator (2 accumulator stages so the epilogue overlaps the next tile)
+//       warps 4-11: epilogue (two per TMEM lane quadrant, each draining half of the tile's columns in 32 x 32
+//                   chunks) — tcgen05.ld TMEM->registers, then one of two families:
+//                   (a) register layout (thread = accumulator row): bias / GELU + GELU' on packed fp32 pairs /
+//                       x aux, bf16 tiles through 64B-swizzled staging and TMA stores;
+//                   (b) staged: transpose through padded fp32 smem so that the side operand (residual, aux) and
+//                       the fp32 / accumulating outputs move in row-coalesced 16-byte pieces
 //   * K-major and MN-major operands are both fed straight from their HBM layout through the UMMA
 //     shared-memory descriptors (no transposition pass for dgrad / wgrad / LinearGeneral weights)
 //   * up to 3 (A,B,K) segments accumulate in the same TMEM tile: LoRA rank-r update, bf16x3 split
