@@ -205,6 +205,9 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of one CUDA graph")
+    ap.add_argument("--graph-ddp", action="store_true",
+                    help="N > 1 (experimental): fwd+bwd graph, one eager all-reduce of the flat gradients, optimizer graph "
+                         "(train.GraphedDataParallelStep) instead of the eager overlapped wrapper")
     ap.add_argument("--ref-device", default="cpu", help="--impl reference only: 'cuda' times the plain-torch port on the GPU (comparator)")
     ap.add_argument("--ref-autocast", action="store_true", help="--impl reference --ref-device cuda: under torch.autocast(bf16)")
     args = ap.parse_args()
@@ -246,7 +249,8 @@ def main():
     # the reference's schedule (src/train.py:159-163, config defaults src/config.py:39-42): the step starts at
     # max_lr / 25 and the learning rate reaches the kernels through a device scalar, so it also drives the graph
     sched = torch.optim.lr_scheduler.OneCycleLR(opt, max_lr=LR, pct_start=WARMUP_STEPS / TRAIN_STEPS, total_steps=TRAIN_STEPS)
-    net = vitb200.ddp.DataParallel(model, opt) if world > 1 else model
+    graph_ddp = world > 1 and args.graph_ddp and not args.no_graph
+    net = vitb200.ddp.DataParallel(model, opt) if (world > 1 and not graph_ddp) else model
     B = args.batch
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     img_d = torch.randn(B, 3, IMG, IMG, generator=gen, device=dev)
@@ -265,7 +269,9 @@ def main():
     graphed = None
     # One CUDA graph per step at N = 1.  With NCCL in the step (N > 1) the step is launched eagerly: capturing the
     # side-stream all-reduces hung an 8-rank run in round 1, and the eager step is already GPU-bound (2 % slower).
-    if not args.no_graph and world == 1:
+    if graph_ddp:
+        graphed = vitb200.train.GraphedDataParallelStep(net, opt, img_d, lab_d)
+    elif not args.no_graph and world == 1:
         try:   # the whole step (fwd + bwd + all-reduce + SGD) as one replayable CUDA graph
             graphed = vitb200.train.GraphedTrainStep(net, opt, img_d, lab_d)
         except Exception as exc:  # noqa: BLE001 - report and measure eagerly rather than die
@@ -350,7 +356,8 @@ def main():
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD % B,
                        "parallelism": "dp%d" % world, "global_batch": world * B,
-                       "launch": "one CUDA graph per step" if graphed is not None else "eager (Python launches)",
+                       "launch": ("fwd+bwd graph, one eager all-reduce, optimizer graph" if graph_ddp else "one CUDA graph per step")
+                       if graphed is not None else "eager (Python launches)",
                        "l2": "per-step working set (~8 GB of activations) exceeds the 126 MB L2; no flush needed",
                        "weights": "reference constructor, seed 0, attention/pos weights x0.02 (SURVEY F5)"},
             "clocks": clocks,

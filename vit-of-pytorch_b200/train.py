@@ -112,3 +112,82 @@ class GraphedTrainStep:
             self.opt.sync_lr()
         self.graph.replay()
         return self.loss
+
+
+class GraphedDataParallelStep:
+    """Data-parallel training step as TWO CUDA graphs with ONE eager collective between them:
+
+        graph A: zero_grad + forward + loss + backward      (no collective inside: every rank captures on its own)
+        eager  : all_reduce(AVG) of the fused optimizer's flat fp32 gradient buffer on the current stream
+        graph B: optimizer step
+
+    `ddp.DataParallel` overlaps per-block all-reduces with the backward pass but has to be launched kernel by kernel from
+    Python (capturing its side-stream all-reduces hung an 8-rank run in round 1); with eight ranks sharing the host cores
+    that launch path is what limits scaling once the step itself is fast.  Here the gradient exchange is exposed
+    (344 MB for ViT-B/16, about 0.5 ms at the measured 725 GB/s all-reduce bus bandwidth, ~3 % of an 18 ms step) and the
+    ~300 launches per step are replayed by the GPU front end.  Same averaged-gradient semantics as the wrapper.
+
+    EXPERIMENTAL: written after round 1's GPU budget was spent, exercised only by `bench.py --graph-ddp` so far.
+    Pass the BARE module (not wrapped in ddp.DataParallel) and a fused optimizer with one flat buffer.
+    """
+
+    def __init__(self, net, optimizer, example_images, example_labels, loss_fn=None, warmup=3, process_group=None,
+                 broadcast=True):
+        import torch.distributed as dist
+        if not example_images.is_cuda:
+            raise RuntimeError("GraphedDataParallelStep needs CUDA (B200) tensors")
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised (launch with torchrun)")
+        if len(optimizer._flat) != 1:
+            raise NotImplementedError("GraphedDataParallelStep expects a fused optimizer with one parameter group")
+        self.dist, self.group = dist, process_group
+        self.net, self.opt = net, optimizer
+        self.loss_fn = loss_fn if loss_fn is not None else F.cross_entropy
+        self.images = example_images.clone()
+        self.labels = example_labels.clone()
+        fg = optimizer._flat[0]
+        self.flat_g = fg.flat_g
+        if broadcast:
+            dist.broadcast(fg.flat_p, src=0, group=process_group)
+            for p in fg.params:
+                F.SHADOW.attach(p, F.SHADOW.get(p, False)[0])   # re-cast the bf16 shadows from the broadcast masters
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):          # warm-up outside capture: lazily built state, first_step flag
+            for _ in range(warmup):
+                self._fwd_bwd()
+                self._exchange()
+                self.opt.step()
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        from . import _lib
+        n0 = _lib.LAUNCHES[0]
+        self.graph_a = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_a):
+            self.loss = self._fwd_bwd()
+        self.graph_b = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_b):
+            self.opt.step()
+        self.launches_per_step = _lib.LAUNCHES[0] - n0
+
+    def _fwd_bwd(self):
+        self.opt.zero_grad()
+        loss = self.loss_fn(self.net(self.images), self.labels)
+        loss.backward()
+        return loss
+
+    def _exchange(self):
+        self.dist.all_reduce(self.flat_g, op=self.dist.ReduceOp.AVG, group=self.group)
+
+    def __call__(self, images, labels):
+        if images.data_ptr() != self.images.data_ptr():
+            self.images.copy_(images, non_blocking=True)
+        if labels.data_ptr() != self.labels.data_ptr():
+            self.labels.copy_(labels, non_blocking=True)
+        if hasattr(self.opt, "sync_lr"):
+            self.opt.sync_lr()
+        self.graph_a.replay()
+        self._exchange()
+        self.graph_b.replay()
+        return self.loss
