@@ -22,6 +22,28 @@ def timeit(fn, iters=30, warm=5):
     return e0.elapsed_time(e1) / iters
 
 
+def timeit_graph(fn, reps=20):
+    """Small kernels: 20 launches captured in one CUDA graph, so the Python / ctypes launch cost is not what is timed."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        fn()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(reps):
+            fn()
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
 T, D, M = 25216, 768, 3072
 bf = torch.bfloat16
 A = torch.randn(T, D, device="cuda").to(bf)
@@ -65,17 +87,29 @@ for rep in range(2):
 os.environ["VITB_EPI_ROWRES"] = "0"
 x = torch.randn(T, 3 * D, device="cuda").to(bf)
 o3 = [torch.zeros(D, device="cuda") for _ in range(3)]
-ms = timeit(lambda: vitb200.ops.colsum3(x, *o3))
-lines.append("colsum3 [25216, 2304] bf16  %.4f ms  %.0f GB/s" % (ms, x.numel() * 2 / ms / 1e6))
+ms = timeit_graph(lambda: vitb200.ops.colsum3(x, *o3))
+lines.append("colsum3 [25216, 2304] bf16 (graph)  %.4f ms  %.0f GB/s" % (ms, x.numel() * 2 / ms / 1e6))
 print(lines[-1], flush=True)
 u8 = torch.randint(0, 256, (128, 32, 32, 3), dtype=torch.uint8, device="cuda")
 tf = vitb200.DeviceImageTransform((32, 32), 224, device="cuda")
 buf = torch.empty(128, 3, 224, 224, device="cuda")
-ms = timeit(lambda: tf(u8, out=buf))
-lines.append("image_prep 128 x 32x32 -> 224 fp32  %.4f ms  %.0f GB/s written" % (ms, buf.numel() * 4 / ms / 1e6))
+ms = timeit_graph(lambda: tf(u8, out=buf))
+lines.append("image_prep 128 x 32x32 -> 224 fp32 (graph)  %.4f ms  %.0f GB/s written" % (ms, buf.numel() * 4 / ms / 1e6))
 print(lines[-1], flush=True)
-ms = timeit(lambda: tf.patch_columns(u8, 16))
-lines.append("image_prep 128 x 32x32 -> bf16 patch operand  %.4f ms  %.0f GB/s written" % (ms, buf.numel() * 2 / ms / 1e6))
+ms = timeit_graph(lambda: tf.patch_columns(u8, 16))
+lines.append("image_prep 128 x 32x32 -> bf16 patch operand (graph)  %.4f ms  %.0f GB/s written" % (ms, buf.numel() * 2 / ms / 1e6))
+xl = torch.randn(T, D, device="cuda")
+gl, bl = torch.randn(D, device="cuda"), torch.randn(D, device="cuda")
+dyl = torch.randn(T, D, device="cuda").to(bf)
+drl = torch.randn(T, D, device="cuda")
+_, _, _, mean, rstd = vitb200.ops.layernorm_fwd(xl, gl, bl, 1e-5, want_bf16=False)
+accl = [torch.zeros(D, device="cuda") for _ in range(3)]
+ms = timeit_graph(lambda: vitb200.ops.layernorm_bwd(dyl, xl, mean, rstd, gl, dres=drl, want_f32=True, want_bf16=True,
+                                                   dgamma=accl[0], dbeta=accl[1], dcolsum=accl[2]))
+lines.append("layernorm_bwd [25216, 768] bf16 dy (graph)  %.4f ms  %.0f GB/s" % (ms, T * D * 16 / ms / 1e6))
+print(lines[-1], flush=True)
+ms = timeit_graph(lambda: vitb200.ops.layernorm_fwd(xl, gl, bl, 1e-5))
+lines.append("layernorm_fwd [25216, 768] (graph)  %.4f ms  %.0f GB/s" % (ms, T * D * 6 / ms / 1e6))
 print(lines[-1], flush=True)
 os.makedirs("gpurun_out", exist_ok=True)
 with open("gpurun_out/epi_ab.txt", "w") as fh:
