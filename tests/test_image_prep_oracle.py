@@ -87,3 +87,38 @@ def test_patch_columns_is_the_conv_flattening():
     ref = torch.nn.functional.conv2d(torch.from_numpy(x), torch.from_numpy(w), stride=16)
     ref = ref.permute(0, 2, 3, 1).reshape(-1, 5).numpy()
     assert np.allclose(y, ref, rtol=1e-4, atol=1e-4)
+
+
+# ---- host side of the product's input pipeline (no device work): tables, draws, target sizes -------------------------
+def test_product_host_helpers_match_oracle_and_torchvision():
+    import importlib
+
+    import torch
+
+    ip = importlib.import_module("vit-of-pytorch_b200.input_pipeline")
+    for mean, std in [((0.5, 0.5, 0.5), (0.5, 0.5, 0.5)), ((0.485, 0.456, 0.406), (0.229, 0.224, 0.225))]:
+        assert np.array_equal(ip.normalize_lut(mean, std).numpy(), O.normalize_lut(mean, std))
+    for h, w, size in [(32, 32, 224), (375, 500, 224), (500, 333, 224), (75, 100, (64, 64)), (7, 5, 3)]:
+        assert ip.resize_target(h, w, size) == O.resize_target(h, w, size)
+    with pytest.raises(ValueError):
+        ip.normalize_lut((0.5,), (0.0,))
+    with pytest.raises(RuntimeError):
+        ip.DeviceImageTransform((32, 32), 224, device="cpu")        # no CPU path
+
+
+def test_draw_flips_replays_torchvision_random_horizontal_flip():
+    tvt = pytest.importorskip("torchvision.transforms")
+    pil = pytest.importorskip("PIL.Image")
+    import importlib
+
+    import torch
+
+    ip = importlib.import_module("vit-of-pytorch_b200.input_pipeline")
+    img = np.zeros((4, 6, 3), dtype=np.uint8)
+    img[:, 0] = 255                                                   # a marker column: lands on the right when flipped
+    flipper = tvt.RandomHorizontalFlip()
+    torch.manual_seed(123)
+    seen = [int(np.array(flipper(pil.fromarray(img)))[0, -1, 0] == 255) for _ in range(40)]
+    torch.manual_seed(123)
+    drawn = ip.draw_flips(40).tolist()
+    assert drawn == seen and 0 < sum(seen) < 40
