@@ -119,3 +119,24 @@ def test_bad_arguments_raise():
         tf(torch.zeros((2, 16, 32, 3), dtype=torch.uint8, device=DEV))           # wrong source size
     with pytest.raises(RuntimeError):
         tf(torch.zeros((2, 32, 32, 3), dtype=torch.float32, device=DEV))         # not bytes
+
+
+@pytest.mark.skipif(os.environ.get("VITB_TEST_EXPERIMENTAL") != "1",
+                    reason="loader glue written after the round's GPU budget was spent (VITB_TEST_EXPERIMENTAL=1)")
+@pytest.mark.parametrize("patch", [None, 16])
+def test_batch_loader_on_device_matches_reference_loader(patch):
+    """DeviceBatchLoader end to end on the GPU (pinned staging, device transform) against the reference loader's batches."""
+    g = np.load(GOLD)
+    data = g["cifar_in"]
+    loader = vitb200.DeviceBatchLoader(data, np.arange(len(data)), split="train", image_size=224, batch_size=3, seed=42,
+                                       device=DEV, patch=patch)
+    torch.manual_seed(7)
+    xs, ys = zip(*list(loader))
+    assert np.array_equal(torch.cat(ys).cpu().numpy(), g["cifar_train_order"])
+    want = g["cifar_train_out"]
+    if patch is None:
+        assert torch.equal(torch.cat(xs).cpu(), torch.from_numpy(want))
+    else:
+        hi = torch.cat([pc.hi for pc in xs]).cpu()
+        cols = O.patch_columns(want, patch, hi.shape[1])
+        assert torch.equal(hi.view(torch.int16), bf16_bits(cols))

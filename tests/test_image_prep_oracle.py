@@ -122,3 +122,54 @@ def test_draw_flips_replays_torchvision_random_horizontal_flip():
     torch.manual_seed(123)
     drawn = ip.draw_flips(40).tolist()
     assert drawn == seen and 0 < sum(seen) < 40
+
+
+class _OracleTransform:
+    """CPU stand-in for DeviceImageTransform in the loader tests: the oracle's transform on CPU tensors."""
+
+    def __init__(self, size):
+        self.size = size
+
+    def __call__(self, u8, flip=None):
+        import torch
+        _, out = O.image_prep(u8.numpy(), self.size, flip=None if flip is None else flip.numpy())
+        return torch.from_numpy(out)
+
+
+@pytest.mark.parametrize("case,src,split,size,bs", [("cifar_train", "cifar_in", "train", 224, 3), ("cifar_eval", "cifar_in", "val", 64, 4)])
+def test_batch_loader_reproduces_the_reference_loader(gold, case, src, split, size, bs):
+    """Order (seeded shuffle), flips (global-RNG draws, replayed with the seed the golden script used) and batching of
+    DeviceBatchLoader against the batches the reference's own CIFAR100DataLoader produced (oracle/make_golden_prep.py)."""
+    import importlib
+
+    import torch
+
+    ip = importlib.import_module("vit-of-pytorch_b200.input_pipeline")
+    data = gold[src]
+    loader = ip.DeviceBatchLoader(data, np.arange(len(data)), split=split, image_size=size, batch_size=bs, seed=42, device="cpu",
+                                  transform=_OracleTransform(size))
+    torch.manual_seed(7)                                              # FLIP_SEED of oracle/make_golden_prep.py
+    xs, ys = zip(*list(loader))
+    assert [x.shape[0] for x in xs] == [min(bs, len(data) - i) for i in range(0, len(data), bs)]
+    assert np.array_equal(torch.cat(ys).numpy(), gold[case + "_order"])
+    assert np.array_equal(torch.cat(xs).numpy(), gold[case + "_out"])
+
+
+def test_batch_loader_order_follows_torch_dataloader_across_epochs():
+    import importlib
+
+    import torch
+    from torch.utils.data import DataLoader, TensorDataset
+
+    ip = importlib.import_module("vit-of-pytorch_b200.input_pipeline")
+    n, bs = 37, 5
+    g = torch.Generator()
+    g.manual_seed(42)
+    ref = DataLoader(TensorDataset(torch.arange(n)), batch_size=bs, shuffle=True, generator=g, num_workers=0)
+    loader = ip.DeviceBatchLoader(np.zeros((n, 2, 2, 3), dtype=np.uint8), np.arange(n), split="train", image_size=2, batch_size=bs,
+                                  seed=42, device="cpu", transform=lambda u8, flip=None: u8)
+    for _ in range(3):
+        want = [b[0].tolist() for b in ref]
+        got = [y.tolist() for _, y in loader]
+        assert got == want
+    assert len(loader) == len(ref)

@@ -10,7 +10,7 @@ from .functional import set_precision, get_precision, precision, SHADOW  # noqa:
 from .model import (VisionTransformer, Encoder, EncoderBlock, SelfAttention, MlpBlock, MLPBlock,  # noqa: F401
                     LinearGeneral, PositionEmbs, PositionEmbedding)
 from .config import ARCHS, get_arch, build_vit  # noqa: F401
-from .input_pipeline import DeviceImageTransform, draw_flips  # noqa: F401
+from .input_pipeline import DeviceImageTransform, DeviceBatchLoader, draw_flips  # noqa: F401
 from .functional import PatchColumns  # noqa: F401
 
 __version__ = "0.1.0"

@@ -99,3 +99,80 @@ class DeviceImageTransform:
         _, hi, lo, _ = ops.image_prep(u8, self.out_hw, self.xtab, self.ytab, self.lut, flip=flip, want_img=False,
                                       P=patch, want_lo=fp32)
         return F.PatchColumns(hi, lo, B, oh // patch, ow // patch, patch, Cn)
+
+
+class DeviceBatchLoader:
+    """The reference's `CIFAR10DataLoader` / `CIFAR100DataLoader` (src/data_loaders.py:32-92) over an in-memory uint8
+    dataset, with the per-sample transform moved to the device.
+
+        loader = DeviceBatchLoader(cifar.data, cifar.targets, split='train', image_size=224, batch_size=128, seed=42)
+        for images, labels in loader:      # images fp32 [B,3,224,224] on the device — what the reference loader yields
+
+    What is kept from the reference: `split='train'` shuffles with `torch.Generator().manual_seed(seed)` exactly as
+    `DataLoader(shuffle=True, generator=generator)` does (one `random_()` draw for the iterator's base seed, the epoch's
+    `randperm`, and the sampler's trailing `randperm` — so the sample order is the reference's, epoch after epoch) and flips
+    with one `torch.rand(1) < 0.5` per image from the global RNG in batch order (what `RandomHorizontalFlip` draws with
+    `num_workers=0`); other splits keep the dataset order and never flip; the last batch may be short (`drop_last=False`).
+    What changes: the host only gathers the batch's uint8 images into pinned memory (3 KB per CIFAR image); resize, flip,
+    ToTensor and Normalize run in `vitb_image_prep`.  `patch=P` yields `PatchColumns` (the patch-embedding GEMM operand)
+    instead of the fp32 batch.  `transform=` replaces the device transform (tests inject a CPU stand-in to check the order
+    and flip logic without a GPU).
+    """
+
+    def __init__(self, images_u8, labels, split='train', image_size=224, batch_size=16, seed=42, device="cuda",
+                 mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5), patch=None, transform=None):
+        self.images = torch.as_tensor(images_u8)
+        if self.images.dtype != torch.uint8 or self.images.dim() != 4:
+            raise ValueError("images_u8 must be a uint8 [N,H,W,C] array (what torchvision's CIFAR datasets hold in .data)")
+        self.labels = torch.as_tensor(labels, dtype=torch.int64)
+        if self.labels.shape[0] != self.images.shape[0]:
+            raise ValueError("labels and images disagree on the number of samples")
+        self.train = split == 'train'
+        self.batch_size = int(batch_size)
+        self.patch = patch
+        self.generator = torch.Generator()
+        self.generator.manual_seed(seed)
+        self.device = torch.device(device)
+        if transform is None:
+            transform = DeviceImageTransform(self.images.shape[1:3], image_size, mean, std, device=self.device)
+        self.transform = transform
+        self._pinned = None
+
+    def __len__(self):
+        return (self.images.shape[0] + self.batch_size - 1) // self.batch_size
+
+    def epoch_order(self):
+        """Sample order of the next epoch, advancing the generator exactly as the reference's DataLoader would."""
+        n = self.images.shape[0]
+        if not self.train:
+            return torch.arange(n)
+        torch.empty((), dtype=torch.int64).random_(generator=self.generator)      # _BaseDataLoaderIter: base seed
+        order = torch.randperm(n, generator=self.generator)                        # RandomSampler: the epoch's permutation
+        torch.randperm(n, generator=self.generator)                                # ... and its (empty) remainder draw
+        return order
+
+    def _stage(self, idx):
+        if self.device.type != "cuda":
+            return self.images[idx]
+        B = idx.numel()
+        if self._pinned is None or self._pinned.shape[0] < B:
+            self._pinned = torch.empty((max(B, self.batch_size),) + tuple(self.images.shape[1:]), dtype=torch.uint8).pin_memory()
+        buf = self._pinned[:B]
+        torch.index_select(self.images, 0, idx, out=buf)
+        dev = buf.to(self.device, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()     # the pinned buffer is reused by the next batch
+        return dev
+
+    def __iter__(self):
+        order = self.epoch_order()
+        for i in range(0, order.numel(), self.batch_size):
+            idx = order[i:i + self.batch_size]
+            u8 = self._stage(idx)
+            flip = draw_flips(idx.numel()) if self.train else None
+            labels = self.labels[idx]
+            if self.device.type == "cuda":
+                labels = labels.to(self.device, non_blocking=True)
+            if self.patch is not None:
+                yield self.transform.patch_columns(u8, self.patch, flip=flip), labels
+            else:
+                yield self.transform(u8, flip=flip), labels
