@@ -65,6 +65,44 @@ class InputPrefetcher:
         return self.cur
 
 
+class DeviceMetrics:
+    """loss / acc@1 / acc@5 of the reference's loops (src/train.py:27-32,53-65: `accuracy(pred, target, topk=(1, 5))` from
+    src/utils.py:28-40 and a MetricTracker that averages the PER-BATCH values with equal weight) accumulated in device
+    tensors.  The reference reads three scalars back with `.item()` every step, i.e. three device syncs per step;
+    `update` only enqueues a few small kernels, and `result()` syncs once, when the caller wants the numbers.
+
+        meter = DeviceMetrics(device); ...; meter.update(loss, logits, labels) each step; meter.result() per epoch
+    """
+
+    def __init__(self, device=None, topk=(1, 5)):
+        self.topk = tuple(topk)
+        self.sums = torch.zeros(1 + len(self.topk), dtype=torch.float64, device=device)
+        self.steps = 0
+
+    def reset(self):
+        self.sums.zero_()
+        self.steps = 0
+
+    @torch.no_grad()
+    def update(self, loss, logits, labels):
+        maxk = min(max(self.topk), logits.shape[1])
+        _, pred = logits.topk(maxk, 1, True, True)                      # the reference's call, ties included
+        correct = pred.eq(labels.view(-1, 1))                            # [B, maxk]
+        vals = [loss.detach().double().reshape(())]
+        for k in self.topk:
+            vals.append(correct[:, :min(k, maxk)].double().sum() * (100.0 / labels.shape[0]))
+        self.sums += torch.stack(vals)
+        self.steps += 1
+
+    def result(self):
+        """{'loss', 'acc1', 'acc5'} averaged over the batches seen since reset() — one device-to-host read."""
+        avg = (self.sums / max(self.steps, 1)).tolist()
+        out = {'loss': avg[0]}
+        for k, v in zip(self.topk, avg[1:]):
+            out['acc%d' % k] = v
+        return out
+
+
 class GraphedTrainStep:
     def __init__(self, net, optimizer, example_images, example_labels, loss_fn=None, warmup=3, forward_loss=None):
         """forward_loss(net, images, labels) -> scalar loss overrides the default loss_fn(net(images), labels)
@@ -96,7 +134,8 @@ class GraphedTrainStep:
         if self.forward_loss is not None:
             loss = self.forward_loss(self.net, self.images, self.labels)
         else:
-            loss = self.loss_fn(self.net(self.images), self.labels)
+            self.logits = self.net(self.images)      # static output of the captured step (for DeviceMetrics)
+            loss = self.loss_fn(self.logits, self.labels)
         loss.backward()
         self.opt.step()
         return loss
