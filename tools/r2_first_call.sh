@@ -8,7 +8,7 @@ mkdir -p gpurun_out
 R=${ROUND_TAG:-r02a}
 timeout 300 python -m pytest tests -x -q -m gpu > gpurun_out/${R}_pytest.log 2>&1; echo "pytest rc=$?"; tail -n 2 gpurun_out/${R}_pytest.log
 # experimental paths (skipped by default): fp32 + residual epilogue in the register layout
-VITB_TEST_EXPERIMENTAL=1 timeout 120 python -m pytest tests/test_gemm_gpu.py tests/test_image_prep_gpu.py -q -k "register_layout or batch_loader" > gpurun_out/${R}_pytest_exp.log 2>&1
+VITB_TEST_EXPERIMENTAL=1 timeout 240 python -m pytest tests/test_gemm_gpu.py tests/test_image_prep_gpu.py tests/test_model_gpu.py -q -k "register_layout or batch_loader or l16_geometry" > gpurun_out/${R}_pytest_exp.log 2>&1
 echo "pytest experimental rc=$?"; tail -n 3 gpurun_out/${R}_pytest_exp.log
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${R}_smoke.log 2>&1; echo "smoke rc=$?"; tail -n 1 gpurun_out/${R}_smoke.log
 timeout 300 python bench.py > gpurun_out/${R}_bench_n1.json 2> gpurun_out/${R}_bench_n1.err; echo "bench rc=$?"; cut -c1-260 gpurun_out/${R}_bench_n1.json
