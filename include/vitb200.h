@@ -166,6 +166,11 @@ int vitb_attn_supported_tc(int head_dim, int Nq, int Nk);      /* forward AND ba
 int vitb_attn_fwd_supported_tc(int head_dim, int Nq, int Nk);  /* forward only: also 64 < head_dim <= 128, <= 320 tokens (ViT-H/14) */
 int vitb_attn_fwd_tc(const vitb_attn_params* p, void* stream);
 int vitb_attn_bwd_tc(const vitb_attn_params* p, void* stream);
+/* EXPERIMENTAL (not yet run on a GPU; nothing selects it unless VITB_ATTN_BWD2=1): the tcgen05 backward split by KEY tile
+ * over the two CTAs of a cluster (256 TMEM columns and ~98 KB of shared memory per CTA -> two CTAs per SM; the dQ partials
+ * of the two key tiles meet through distributed shared memory).  Same contract as vitb_attn_bwd_tc, 128 < N <= 256. */
+int vitb_attn_bwd_tc2_supported(int head_dim, int Nq, int Nk);
+int vitb_attn_bwd_tc2(const vitb_attn_params* p, void* stream);
 int vitb_attn_fwd_simt(const vitb_attn_params* p, void* stream);
 int vitb_attn_bwd_simt(const vitb_attn_params* p, void* stream);
 

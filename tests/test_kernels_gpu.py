@@ -2,6 +2,7 @@
 Tolerances are stated per test: fp32 paths 1e-5 rel-L2 (accumulation order only); bf16 outputs 4e-3
 (one bf16 rounding); bf16 attention 1e-2 (P and dS are rounded to bf16 before the second MMA)."""
 import math
+import os
 
 import pytest
 import torch
@@ -129,6 +130,36 @@ def test_attn_tc_fwd_bwd_packed_qkv(N):
     assert rel_l2(dv, vf.grad) < 1.5e-2
     assert rel_l2(dq, qf.grad) < 1.5e-2
     assert rel_l2(dk, kf.grad) < 1.5e-2
+
+
+@pytest.mark.skipif(os.environ.get("VITB_TEST_EXPERIMENTAL") != "1",
+                    reason="experimental key-split CTA-pair backward, not yet run on a GPU (VITB_TEST_EXPERIMENTAL=1)")
+@pytest.mark.parametrize("N,B,H", [(197, 3, 12), (129, 2, 2), (256, 2, 3), (200, 128, 12)])
+def test_attn_bwd_key_split_cta_pairs(N, B, H, monkeypatch):
+    """VITB_ATTN_BWD2=1: attn_bwd_tc2 (two CTAs per head, dQ partials through distributed shared memory) against the torch
+    reference and the one-CTA kernel."""
+    import vitb200
+    dh = 64
+    D = H * dh
+    qkv = _randn((B, N, 3 * D), 40 + N, 1.0, torch.bfloat16)
+    q, k, v = qkv[:, :, :D], qkv[:, :, D:2 * D], qkv[:, :, 2 * D:]
+    o, lse = vitb200.ops.attn_fwd(q, k, v, H)
+    do = _randn((B, N, D), 98, 1.0, torch.bfloat16)
+    res = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("VITB_ATTN_BWD2", flag)
+        dqkv = torch.full_like(qkv, float("nan"))
+        vitb200.ops.attn_bwd(do, q, k, v, o, lse, H, dq=dqkv[:, :, :D], dk=dqkv[:, :, D:2 * D], dv=dqkv[:, :, 2 * D:])
+        torch.cuda.synchronize()
+        assert not bool(dqkv.isnan().any()), flag
+        res[flag] = dqkv
+    if B * H <= 64:
+        qf, kf, vf = (t.float().detach().requires_grad_(True) for t in (q, k, v))
+        ro, _ = _attn_ref(qf, kf, vf, H)
+        ro.backward(do.float())
+        ref = torch.cat([qf.grad, kf.grad, vf.grad], dim=2)
+        assert rel_l2(res["1"], ref) < 1.5e-2
+    assert rel_l2(res["1"], res["0"]) < 5e-3          # same math; the dQ partials are summed in fp32 instead of in TMEM
 
 
 @pytest.mark.parametrize("dh,N,H,simt", [(80, 257, 16, True), (128, 130, 3, True), (96, 300, 2, False),

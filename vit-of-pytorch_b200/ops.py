@@ -4,6 +4,7 @@ Every function takes torch CUDA tensors, checks layout, and launches on torch's 
 Outputs are allocated with torch (the library never allocates device memory).
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -240,6 +241,8 @@ def attn_bwd(dout, q, k, v, o, lse, H, *, use_tc=None, dq=None, dk=None, dv=None
     p.dk_batch_stride, p.dk_row_stride = _head_strides(dk, H, dh, "dk")
     p.dv_batch_stride, p.dv_row_stride = _head_strides(dv, H, dh, "dv")
     fn = L._vitb_attn_bwd_tc if use_tc else L._vitb_attn_bwd_simt
+    if use_tc and os.environ.get("VITB_ATTN_BWD2") == "1" and L.vitb_attn_bwd_tc2_supported(dh, Nq, Nk):
+        fn = L._vitb_attn_bwd_tc2       # experimental key-split CTA-pair kernel (off unless VITB_ATTN_BWD2=1)
     L.check(fn(C.byref(p), L.stream_ptr(q.device)), "vitb_attn_bwd")
     return dq, dk, dv
 
