@@ -7,15 +7,12 @@ cd "$(dirname "$0")/.." || exit 1
 mkdir -p gpurun_out
 R=${ROUND_TAG:-r02a}
 timeout 300 python -m pytest tests -x -q -m gpu > gpurun_out/${R}_pytest.log 2>&1; echo "pytest rc=$?"; tail -n 2 gpurun_out/${R}_pytest.log
-# experimental paths (skipped by default): fp32 + residual epilogue in the register layout
-VITB_TEST_EXPERIMENTAL=1 timeout 240 python -m pytest tests/test_gemm_gpu.py tests/test_image_prep_gpu.py tests/test_model_gpu.py tests/test_kernels_gpu.py -q -k "register_layout or batch_loader or l16_geometry or key_split" > gpurun_out/${R}_pytest_exp.log 2>&1
-echo "pytest experimental rc=$?"; tail -n 3 gpurun_out/${R}_pytest_exp.log
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${R}_smoke.log 2>&1; echo "smoke rc=$?"; tail -n 1 gpurun_out/${R}_smoke.log
 timeout 300 python bench.py > gpurun_out/${R}_bench_n1.json 2> gpurun_out/${R}_bench_n1.err; echo "bench rc=$?"; cut -c1-260 gpurun_out/${R}_bench_n1.json
 timeout 120 python tools/epi_ab.py > gpurun_out/${R}_epi_ab.log 2>&1; echo "epi_ab rc=$?"; tail -n 20 gpurun_out/${R}_epi_ab.log
 timeout 200 python tools/epi_ablate.py > gpurun_out/${R}_epi_ablate.log 2>&1; echo "epi_ablate rc=$?"; tail -n 8 gpurun_out/${R}_epi_ablate.log
 timeout 120 python tools/gemm_bench.py > gpurun_out/${R}_gemm_bench.log 2>&1; echo "gemm_bench rc=$?"
-VITB_BENCH_EXPERIMENTAL=1 timeout 90 python tools/attn_bench.py > gpurun_out/${R}_attn_bench.log 2>&1; echo "attn_bench rc=$?"; tail -n 4 gpurun_out/${R}_attn_bench.log
+timeout 60 python tools/attn_bench.py > gpurun_out/${R}_attn_bench.log 2>&1; echo "attn_bench rc=$?"; tail -n 4 gpurun_out/${R}_attn_bench.log
 # ncu: the launch list of a step (same command exited 0 just above, modulo the launch mode), then full captures
 timeout 200 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph > gpurun_out/${R}_bench_nograph.json 2> /dev/null && \
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches_${R}.csv \
@@ -29,3 +26,8 @@ for job in "gemm_fc1_gelu_dg:tools/gemm_one.py:fc1_gelu_dg:regex:vitb_gemm" "gem
     python "$script" $arg > "gpurun_out/${R}_ncu_${name}.log" 2>&1; echo "ncu $name rc=$?"
 done
 ls -la gpurun_out/*_${R}.ncu-rep 2>/dev/null
+# LAST, because they have never run on a GPU and a protocol bug could wedge the device: the experimental paths
+VITB_TEST_EXPERIMENTAL=1 timeout 240 python -m pytest tests/test_gemm_gpu.py tests/test_image_prep_gpu.py tests/test_model_gpu.py tests/test_kernels_gpu.py -q -k "register_layout or batch_loader or l16_geometry or key_split" > gpurun_out/${R}_pytest_exp.log 2>&1
+echo "pytest experimental rc=$?"; tail -n 3 gpurun_out/${R}_pytest_exp.log
+VITB_BENCH_EXPERIMENTAL=1 timeout 60 python tools/attn_bench.py > gpurun_out/${R}_attn_bench_exp.log 2>&1; echo "attn_bench experimental rc=$?"; tail -n 4 gpurun_out/${R}_attn_bench_exp.log
+
