@@ -889,6 +889,12 @@ attn_bwd_tc2(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
 #pragma unroll 1
     for (int c = 2 * half; c < 2 * half + 2; ++c) {
       const int c0 = c * 32;
+      const int kc = c0 >> 6, u0 = (c0 & 63) >> 3;
+      if (c0 >= nk_valid) {   // warp-uniform: no key of this tile in the chunk (rank 1 at N = 197 owns 69 keys) -> zeros
+#pragma unroll
+        for (int u = 0; u < 4; ++u) st_shared_v4(sP_u + kc * kChunkBytes + swz_unit(r, u0 + u), 0u, 0u, 0u, 0u);
+        continue;
+      }
       uint32_t v[32];
       tmem_ld_32x32b_x32(trow + c0, v);
       tmem_ld_wait();
@@ -898,7 +904,6 @@ attn_bwd_tc2(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
         const float e = ex2_approx(fmaf(__uint_as_float(v[j]), a.scale_log2, -lse2));
         pv[j] = (c0 + j < nk_valid) ? e : 0.f;
       }
-      const int kc = c0 >> 6, u0 = (c0 & 63) >> 3;
 #pragma unroll
       for (int u = 0; u < 4; ++u)
         st_shared_v4(sP_u + kc * kChunkBytes + swz_unit(r, u0 + u), pack_bf16x2(pv[8 * u + 0], pv[8 * u + 1]),
@@ -927,6 +932,7 @@ attn_bwd_tc2(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
 #pragma unroll 1
     for (int c = 2 * half; c < 2 * half + 2; ++c) {
       const int c0 = c * 32;
+      if (c0 >= nk_valid) continue;   // P is zero there, so dS = P * (dP - D) already is
       uint32_t v[32];
       tmem_ld_32x32b_x32(trow + c0, v);
       tmem_ld_wait();
