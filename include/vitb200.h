@@ -171,6 +171,13 @@ int vitb_attn_bwd_tc(const vitb_attn_params* p, void* stream);
  * of the two key tiles meet through distributed shared memory).  Same contract as vitb_attn_bwd_tc, 128 < N <= 256. */
 int vitb_attn_bwd_tc2_supported(int head_dim, int Nq, int Nk);
 int vitb_attn_bwd_tc2(const vitb_attn_params* p, void* stream);
+/* Persistent warp-specialised generation of the tcgen05 kernels (vitb_attention_ws.cu): one resident CTA per SM walks a
+ * contiguous range of (image, head[, query tile]) items; a TMA producer warp, a single-thread tcgen05 issuer and eight
+ * CUDA-core warps overlap the loads, MMAs and softmax arithmetic of neighbouring items.  Same contract and shapes as
+ * vitb_attn_fwd_tc / vitb_attn_bwd_tc (bf16, head_dim 64, Nq == Nk <= 256). */
+int vitb_attn_ws_supported(int head_dim, int Nq, int Nk);
+int vitb_attn_fwd_ws(const vitb_attn_params* p, void* stream);
+int vitb_attn_bwd_ws(const vitb_attn_params* p, void* stream);
 int vitb_attn_fwd_simt(const vitb_attn_params* p, void* stream);
 int vitb_attn_bwd_simt(const vitb_attn_params* p, void* stream);
 

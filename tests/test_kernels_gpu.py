@@ -162,6 +162,41 @@ def test_attn_bwd_key_split_cta_pairs(N, B, H, monkeypatch):
     assert rel_l2(res["1"], res["0"]) < 5e-3          # same math; the dQ partials are summed in fp32 instead of in TMEM
 
 
+@pytest.mark.parametrize("N,B,H", [(197, 3, 12), (50, 3, 12), (256, 2, 3), (16, 2, 2), (129, 2, 2), (128, 5, 4), (130, 40, 12),
+                                   (197, 128, 12)])
+def test_attn_ws_persistent_kernels(N, B, H, monkeypatch):
+    """VITB_ATTN_WS=1: the persistent warp-specialised forward / backward (vitb_attention_ws.cu) against the torch reference
+    (small cases) and against the one-CTA-per-tile kernels (all cases, incl. several items per resident CTA)."""
+    import vitb200
+    dh = 64
+    D = H * dh
+    qkv = _randn((B, N, 3 * D), 60 + N, 1.0 if B * H <= 64 else 0.5, torch.bfloat16)
+    q, k, v = qkv[:, :, :D], qkv[:, :, D:2 * D], qkv[:, :, 2 * D:]
+    do = _randn((B, N, D), 97, 1.0, torch.bfloat16)
+    res = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("VITB_ATTN_WS", flag)
+        o, lse = vitb200.ops.attn_fwd(q, k, v, H)
+        dqkv = torch.full_like(qkv, float("nan"))
+        vitb200.ops.attn_bwd(do, q, k, v, o, lse, H, dq=dqkv[:, :, :D], dk=dqkv[:, :, D:2 * D], dv=dqkv[:, :, 2 * D:])
+        torch.cuda.synchronize()
+        assert not bool(o.isnan().any()) and not bool(dqkv.isnan().any()), flag
+        res[flag] = (o, lse, dqkv)
+    assert rel_l2(res["1"][0], res["0"][0]) < 4e-3
+    assert rel_l2(res["1"][1], res["0"][1]) < 1e-5
+    assert rel_l2(res["1"][2], res["0"][2]) < 6e-3
+    if B * H <= 64:
+        qf, kf, vf = (t.float().detach().requires_grad_(True) for t in (q, k, v))
+        ro, rlse = _attn_ref(qf, kf, vf, H)
+        ro.backward(do.float())
+        o, lse, dqkv = res["1"]
+        assert rel_l2(o, ro) < 1e-2
+        assert rel_l2(lse, rlse) < 1e-4
+        assert rel_l2(dqkv[:, :, :D], qf.grad) < 1.5e-2
+        assert rel_l2(dqkv[:, :, D:2 * D], kf.grad) < 1.5e-2
+        assert rel_l2(dqkv[:, :, 2 * D:], vf.grad) < 1.5e-2
+
+
 @pytest.mark.parametrize("dh,N,H,simt", [(80, 257, 16, True), (128, 130, 3, True), (96, 300, 2, False),
                                          (80, 50, 4, True), (112, 256, 2, False),
                                          (64, 577, 12, False), (80, 730, 2, False), (64, 321, 2, False), (128, 640, 1, False)])

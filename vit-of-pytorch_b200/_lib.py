@@ -169,6 +169,9 @@ _vitb_attn_fwd_tc = _sig("vitb_attn_fwd_tc", [C.POINTER(AttnParams), _vp])
 _vitb_attn_bwd_tc = _sig("vitb_attn_bwd_tc", [C.POINTER(AttnParams), _vp])
 vitb_attn_bwd_tc2_supported = _sig("vitb_attn_bwd_tc2_supported", [_i, _i, _i])
 _vitb_attn_bwd_tc2 = _sig("vitb_attn_bwd_tc2", [C.POINTER(AttnParams), _vp])       # experimental key-split CTA pairs
+vitb_attn_ws_supported = _sig("vitb_attn_ws_supported", [_i, _i, _i])
+_vitb_attn_fwd_ws = _sig("vitb_attn_fwd_ws", [C.POINTER(AttnParams), _vp])         # persistent warp-specialised kernels
+_vitb_attn_bwd_ws = _sig("vitb_attn_bwd_ws", [C.POINTER(AttnParams), _vp])
 _vitb_attn_fwd_simt = _sig("vitb_attn_fwd_simt", [C.POINTER(AttnParams), _vp])
 _vitb_attn_bwd_simt = _sig("vitb_attn_bwd_simt", [C.POINTER(AttnParams), _vp])
 _vitb_cast_split = _sig("vitb_cast_split", [_vp, _i64, _vp, _vp, _vp])
@@ -200,5 +203,5 @@ EXPORTED_SYMBOLS = [
     "vitb_sumsq", "vitb_clip_coef", "vitb_gelu_bwd", "vitb_router_decide_fwd", "vitb_router_decide_bwd",
     "vitb_token_mean_fwd", "vitb_token_mean_bwd", "vitb_select_rows", "vitb_colsum3",
     "vitb_resize_tables_host", "vitb_image_prep", "vitb_gemm_diag", "vitb_gemm_diag_mask",
-    "vitb_attn_bwd_tc2_supported", "vitb_attn_bwd_tc2",
+    "vitb_attn_bwd_tc2_supported", "vitb_attn_bwd_tc2", "vitb_attn_ws_supported", "vitb_attn_fwd_ws", "vitb_attn_bwd_ws",
 ]

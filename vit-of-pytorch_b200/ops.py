@@ -182,6 +182,11 @@ def attn_fwd_supported_tc(dh, Nq, Nk, dtype):
     return dtype == torch.bfloat16 and bool(L.vitb_attn_fwd_supported_tc(dh, Nq, Nk))
 
 
+def _attn_ws_enabled():
+    """VITB_ATTN_WS (read per call): 1 = the persistent warp-specialised attention kernels, 0 = one CTA per tile."""
+    return os.environ.get("VITB_ATTN_WS", "0") != "0"
+
+
 def _attn_params(q, k, v, o, lse, H):
     B, Nq, HD = q.shape
     Nk = k.shape[1]
@@ -209,6 +214,8 @@ def attn_fwd(q, k, v, H, *, use_tc=None):
     lse = torch.empty((B, H, Nq), dtype=torch.float32, device=q.device)
     p = _attn_params(q, k, v, o, lse, H)
     fn = L._vitb_attn_fwd_tc if use_tc else L._vitb_attn_fwd_simt
+    if use_tc and _attn_ws_enabled() and L.vitb_attn_ws_supported(dh, Nq, k.shape[1]):
+        fn = L._vitb_attn_fwd_ws        # persistent warp-specialised kernel
     L.check(fn(C.byref(p), L.stream_ptr(q.device)), "vitb_attn_fwd")
     return o, lse
 
@@ -243,6 +250,8 @@ def attn_bwd(dout, q, k, v, o, lse, H, *, use_tc=None, dq=None, dk=None, dv=None
     fn = L._vitb_attn_bwd_tc if use_tc else L._vitb_attn_bwd_simt
     if use_tc and os.environ.get("VITB_ATTN_BWD2") == "1" and L.vitb_attn_bwd_tc2_supported(dh, Nq, Nk):
         fn = L._vitb_attn_bwd_tc2       # experimental key-split CTA-pair kernel (off unless VITB_ATTN_BWD2=1)
+    if use_tc and _attn_ws_enabled() and L.vitb_attn_ws_supported(dh, Nq, Nk):
+        fn = L._vitb_attn_bwd_ws        # persistent warp-specialised kernel
     L.check(fn(C.byref(p), L.stream_ptr(q.device)), "vitb_attn_bwd")
     return dq, dk, dv
 
