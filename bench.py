@@ -10,9 +10,10 @@
 Prints ONE JSON line (rank 0).  `value` = whole-job images/s with inputs resident in HBM; `e2e` = the
 same through the public module API with pinned-host inputs (H2D inside the timed region, loss read back
 every step); `roofline` = the dominant kernel (tcgen05 GEMM) timed live with CUDA events against the
-measured dense-bf16 peak; `cpu_baseline` = the oracle port (plain torch fp32, oracle/vit_oracle.py) timed
-on this box's host cores on a bounded sample.  The oracle is only ever the checker / baseline here —
-never the measured product path.
+measured dense-bf16 peak; `cpu_baseline` = the UNMODIFIED reference module (src/model.py, staged byte for byte into the
+git-ignored baseline/_ref/ by __graft_entry__.build()) in the reference's own training step, timed on this box's host
+cores on a bounded sample (the oracle port only if the staged copy is missing).  The oracle is only ever the checker /
+baseline here — never the measured product path.
 """
 import argparse
 import json
@@ -121,72 +122,111 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle port on host cores
+# reference arm / cpu baseline: the UNMODIFIED reference module (baseline/_ref, staged by build()) on host cores;
+# the oracle port only when the staged copy is missing
 # ---------------------------------------------------------------------------------------------------
+def _lr_schedule(n):
+    probe = torch.optim.SGD([torch.zeros(1, requires_grad=True)], lr=LR, momentum=0.9)
+    sched = torch.optim.lr_scheduler.OneCycleLR(probe, max_lr=LR, pct_start=WARMUP_STEPS / TRAIN_STEPS, total_steps=TRAIN_STEPS)
+    out = []
+    for _ in range(n):
+        out.append(probe.param_groups[0]["lr"])
+        probe.step()
+        sched.step()
+    return out
+
+
+def reference_kind():
+    from oracle import ref_loader
+    return "reference" if ref_loader.available() else "port"
+
+
 def cpu_train_steps(steps, warmup, batch=CPU_SAMPLE_BATCH, device="cpu", autocast=False):
-    """fwd + bwd + SGD(momentum .9, lr .03) of ViT-B/16 in plain torch fp32 on the host (oracle port of
-    src/model.py + src/train.py:20-24,154-158).  Returns (images/s, seconds per step, threads)."""
-    from oracle import vit_init, vit_oracle
+    """fwd + bwd + SGD(momentum .9, lr .03, OneCycleLR) of ViT-B/16 — the reference's own training step
+    (src/train.py:16-25,154-163) on the reference's own module (src/model.py:159-211, loaded unmodified from
+    baseline/_ref or /root/reference), plain torch fp32 on the host cores (or `device`).  Without the staged reference:
+    the oracle port (oracle/vit_oracle.py).  Returns (images/s, seconds per step, threads, kind)."""
+    from oracle import ref_loader, vit_init, vit_oracle
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    sd = vit_init.reference_state_dict(vit_init.arch_cfg(ARCH, IMG, CLASSES), seed=0, scaled=True)
-    params = {k: v.clone().to(device) for k, v in sd.items()}
-    bufs = {}
+    cfg = vit_init.arch_cfg(ARCH, IMG, CLASSES)
+    sd = vit_init.reference_state_dict(cfg, seed=0, scaled=True)
     g = torch.Generator().manual_seed(1234)
     img = torch.randn(batch, 3, IMG, IMG, generator=g).to(device)
     labels = torch.randint(0, CLASSES, (batch,), generator=g).to(device)
+    dev_type = "cuda" if device != "cpu" else "cpu"
     times = []
-    probe = torch.optim.SGD([torch.zeros(1, requires_grad=True)], lr=LR, momentum=0.9)
-    probe_sched = torch.optim.lr_scheduler.OneCycleLR(probe, max_lr=LR, pct_start=WARMUP_STEPS / TRAIN_STEPS,
-                                                      total_steps=TRAIN_STEPS)
-    lrs = []
-    for _ in range(warmup + steps):
-        lrs.append(probe.param_groups[0]["lr"])
-        probe.step()
-        probe_sched.step()
-
-    def lr_at(i):
-        return lrs[i]
-
-    for i in range(warmup + steps):
-        t0 = time.perf_counter()
-        leaf = {k: v.detach().requires_grad_(True) for k, v in params.items()}
-        with torch.autocast(device_type="cuda" if device != "cpu" else "cpu", dtype=torch.bfloat16, enabled=autocast):
-            loss = vit_oracle.vit_loss(img, labels, leaf)
-        loss.backward()
-        vit_oracle.sgd_momentum_step(params, {k: v.grad for k, v in leaf.items()}, bufs, lr_at(i), 0.9, first=(i == 0))
-        float(loss.detach())
-        if i >= warmup:
-            times.append(time.perf_counter() - t0)
+    if ref_loader.available():
+        ref = ref_loader.load_src_model()
+        model = ref.VisionTransformer(attn_dropout_rate=0.0, dropout_rate=0.0, **cfg)
+        model.load_state_dict(sd)
+        model = model.to(device).train()
+        opt = torch.optim.SGD(model.parameters(), lr=LR, weight_decay=0.0, momentum=0.9)        # src/train.py:154-158
+        sched = torch.optim.lr_scheduler.OneCycleLR(opt, max_lr=LR, pct_start=WARMUP_STEPS / TRAIN_STEPS, total_steps=TRAIN_STEPS)
+        crit = torch.nn.CrossEntropyLoss()
+        for i in range(warmup + steps):
+            if device != "cpu":
+                torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            opt.zero_grad()
+            with torch.autocast(device_type=dev_type, dtype=torch.bfloat16, enabled=autocast):
+                loss = crit(model(img), labels)
+            loss.backward()
+            opt.step()
+            sched.step()
+            float(loss.detach())
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+        kind = "reference"
+    else:
+        params = {k: v.clone().to(device) for k, v in sd.items()}
+        bufs = {}
+        lrs = _lr_schedule(warmup + steps)
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            leaf = {k: v.detach().requires_grad_(True) for k, v in params.items()}
+            with torch.autocast(device_type=dev_type, dtype=torch.bfloat16, enabled=autocast):
+                loss = vit_oracle.vit_loss(img, labels, leaf)
+            loss.backward()
+            vit_oracle.sgd_momentum_step(params, {k: v.grad for k, v in leaf.items()}, bufs, lrs[i], 0.9, first=(i == 0))
+            float(loss.detach())
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+        kind = "port"
     sec = sum(times) / len(times)
-    return batch / sec, sec, threads
+    return batch / sec, sec, threads, kind
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
     if args.ref_device != "cpu":
-        # comparator only (SURVEY 8d "stock PyTorch GPU"): the same plain-torch port on the B200 through ATen / cuBLAS,
+        # comparator only (SURVEY 8d "stock PyTorch GPU"): the same unmodified module on the B200 through ATen / cuBLAS,
         # full batch, optionally under autocast(bf16).  Not the reference arm the driver runs.
-        ips, sec, _ = cpu_train_steps(args.steps, args.warmup, batch=BATCH_PER_GPU, device=args.ref_device,
-                                      autocast=args.ref_autocast)
+        ips, sec, _, kind = cpu_train_steps(args.steps, args.warmup, batch=args.ref_batch or BATCH_PER_GPU, device=args.ref_device,
+                                            autocast=args.ref_autocast)
         emit({"impl": "stock-torch-gpu", "metric": "train images/sec", "value": ips, "unit": "images/s", "n_gpus": 1,
               "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
               "dtype": "bf16 autocast" if args.ref_autocast else "f32",
-              "config": {"workload": WORKLOAD % BATCH_PER_GPU, "launch": "oracle port (plain torch ops) on %s" % args.ref_device}})
+              "config": {"workload": WORKLOAD % (args.ref_batch or BATCH_PER_GPU),
+                         "launch": "%s on %s" % ("unmodified reference src/model.py (baseline/_ref)" if kind == "reference"
+                                                 else "oracle port (plain torch ops)", args.ref_device)}})
         return
-    ips, sec, threads = cpu_train_steps(args.steps, args.warmup)
+    batch = args.ref_batch or CPU_SAMPLE_BATCH
+    ips, sec, threads, kind = cpu_train_steps(args.steps, args.warmup, batch=batch)
+    what = ("unmodified reference src/model.py + torch.optim.SGD + OneCycleLR (baseline/_ref)" if kind == "reference"
+            else "oracle port (oracle/vit_oracle.py)")
     out = {
         "impl": "reference", "metric": "train images/sec", "value": ips, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD % BATCH_PER_GPU, "parallelism": "dp%d" % args.gpus,
-                   "global_batch": args.gpus * BATCH_PER_GPU, "launch": "torch CPU fp32 on the host cores (rank 0 only)",
-                   "sample": "each step is a bounded sample of the workload: batch %d instead of %d"
-                             % (CPU_SAMPLE_BATCH, BATCH_PER_GPU),
+                   "global_batch": args.gpus * BATCH_PER_GPU, "launch": "torch CPU fp32 on the host cores (rank 0 only): " + what,
+                   "sample": "each step is a bounded sample of the workload: batch %d instead of %d "
+                             "(--ref-batch changes it)" % (batch, BATCH_PER_GPU),
                    "weights": "reference constructor, seed 0, attention/pos weights x0.02 (SURVEY F5)"},
-        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
-                         "sample": "%d steps of batch %d (oracle/vit_oracle.py, torch CPU fp32)" % (args.steps, CPU_SAMPLE_BATCH)},
+        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": kind,
+                         "sample": "%d steps of batch %d (%s, torch CPU fp32)" % (args.steps, batch, what)},
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -205,9 +245,13 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of one CUDA graph")
-    ap.add_argument("--graph-ddp", action="store_true",
-                    help="N > 1 (experimental): fwd+bwd graph, one eager all-reduce of the flat gradients, optimizer graph "
-                         "(train.GraphedDataParallelStep) instead of the eager overlapped wrapper")
+    ap.add_argument("--ddp-mode", default="graph1", choices=["graph1", "graph2", "overlap"],
+                    help="N > 1: graph1 = the whole step incl. one gradient all-reduce as ONE CUDA graph (default, same launch "
+                         "mode as N = 1); graph2 = fwd+bwd graph, one eager all-reduce, optimizer graph "
+                         "(train.GraphedDataParallelStep); overlap = eager launches, per-block all-reduces overlapped with "
+                         "the backward pass on a side stream (ddp.DataParallel)")
+    ap.add_argument("--graph-ddp", action="store_true", help="alias of --ddp-mode graph2")
+    ap.add_argument("--ref-batch", type=int, default=0, help="--impl reference only: batch of the reference step (default 8 on the CPU, 128 on a GPU)")
     ap.add_argument("--ref-device", default="cpu", help="--impl reference only: 'cuda' times the plain-torch port on the GPU (comparator)")
     ap.add_argument("--ref-autocast", action="store_true", help="--impl reference --ref-device cuda: under torch.autocast(bf16)")
     args = ap.parse_args()
@@ -249,8 +293,13 @@ def main():
     # the reference's schedule (src/train.py:159-163, config defaults src/config.py:39-42): the step starts at
     # max_lr / 25 and the learning rate reaches the kernels through a device scalar, so it also drives the graph
     sched = torch.optim.lr_scheduler.OneCycleLR(opt, max_lr=LR, pct_start=WARMUP_STEPS / TRAIN_STEPS, total_steps=TRAIN_STEPS)
-    graph_ddp = world > 1 and args.graph_ddp and not args.no_graph
-    net = vitb200.ddp.DataParallel(model, opt) if (world > 1 and not graph_ddp) else model
+    if args.graph_ddp:
+        args.ddp_mode = "graph2"
+    if args.no_graph and world > 1:
+        args.ddp_mode = "overlap"
+    graph_ddp = world > 1 and args.ddp_mode == "graph2"
+    graph_one = world > 1 and args.ddp_mode == "graph1"
+    net = vitb200.ddp.DataParallel(model, opt) if (world > 1 and args.ddp_mode == "overlap") else model
     B = args.batch
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     img_d = torch.randn(B, 3, IMG, IMG, generator=gen, device=dev)
@@ -267,14 +316,15 @@ def main():
         return loss
 
     graphed = None
-    # One CUDA graph per step at N = 1.  With NCCL in the step (N > 1) the step is launched eagerly: capturing the
-    # side-stream all-reduces hung an 8-rank run in round 1, and the eager step is already GPU-bound (2 % slower).
+    # One CUDA graph per step: fwd + bwd (+ ONE gradient all-reduce on the capture stream at N > 1) + SGD.
     if graph_ddp:
         graphed = vitb200.train.GraphedDataParallelStep(net, opt, img_d, lab_d)
-    elif not args.no_graph and world == 1:
+    elif not args.no_graph and (world == 1 or graph_one):
         try:   # the whole step (fwd + bwd + all-reduce + SGD) as one replayable CUDA graph
-            graphed = vitb200.train.GraphedTrainStep(net, opt, img_d, lab_d)
+            graphed = vitb200.train.GraphedTrainStep(net, opt, img_d, lab_d, data_parallel=graph_one)
         except Exception as exc:  # noqa: BLE001 - report and measure eagerly rather than die
+            if world > 1:
+                raise     # the eager fallback below has no gradient exchange
             if rank == 0:
                 print("bench: CUDA-graph capture failed (%r); timing the eager step" % (exc,), file=sys.stderr)
             graphed = None
@@ -358,6 +408,10 @@ def main():
                        "parallelism": "dp%d" % world, "global_batch": world * B,
                        "launch": ("fwd+bwd graph, one eager all-reduce, optimizer graph" if graph_ddp else "one CUDA graph per step")
                        if graphed is not None else "eager (Python launches)",
+                       "grad_exchange": (None if world == 1 else
+                                         {"graph1": "one NCCL all-reduce (AVG) of the flat fp32 gradient buffer, a node of the step graph",
+                                          "graph2": "one eager NCCL all-reduce between two graphs",
+                                          "overlap": "per-block NCCL all-reduces on a side stream, overlapped with backward"}[args.ddp_mode]),
                        "l2": "per-step working set (~8 GB of activations) exceeds the 126 MB L2; no flush needed",
                        "weights": "reference constructor, seed 0, attention/pos weights x0.02 (SURVEY F5)"},
             "clocks": clocks,
@@ -375,9 +429,11 @@ def main():
                               "frac_of_burst": step_tf / pk["tflops_burst"], "frac_of_spec_2250": step_tf / 2250.0},
         }
         if world == 1 and not args.no_cpu_baseline:
-            cips, csec, threads = cpu_train_steps(2, 1)
-            out["cpu_baseline"] = {"value": cips, "unit": "images/s", "cores": threads, "kind": "port",
-                                   "sample": "2 timed steps of batch %d after 1 warm-up (oracle port, torch CPU fp32)" % CPU_SAMPLE_BATCH}
+            cips, csec, threads, kind = cpu_train_steps(2, 1)
+            out["cpu_baseline"] = {"value": cips, "unit": "images/s", "cores": threads, "kind": kind,
+                                   "sample": "2 timed steps of batch %d after 1 warm-up (%s, torch CPU fp32)"
+                                             % (CPU_SAMPLE_BATCH, "unmodified reference src/model.py, baseline/_ref" if kind == "reference"
+                                                else "oracle port")}
         emit(out)
     if world > 1:
         dist.destroy_process_group()

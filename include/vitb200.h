@@ -98,6 +98,16 @@ typedef struct vitb_gemm_params {
   const void* aux; /* [M,N] pre-activation (VITB_EPI_GELU_BWD) or derivative (VITB_EPI_MUL_AUX), same dtype as D */
   int64_t ldaux;
   float* colsum; /* optional [N]: += column sums of the values written to D (bias gradient of the producer) */
+  /* Column groups (the merged q|k|v projection and its weight gradient): N = n_groups * Ng.  Column n belongs to group
+   * g = n / Ng; its B rows / columns live at B_seg + g * b_group_stride (elements; every segment uses the same stride),
+   * i.e. the n_groups weight matrices only have to sit at a uniform distance, not in one [K, N] array.  With
+   * d_group_stride != 0 the output is grouped the same way: D(m, n) at D + g * d_group_stride + m * ldd + (n - g * Ng)
+   * (fp32 accumulate outputs only: the n_groups weight gradients).  n_groups <= 1: plain GEMM.  Ng must be a multiple
+   * of the N tile (256, or 128 when that pads N less). */
+  int32_t n_groups;
+  int32_t _pad1;
+  int64_t b_group_stride;
+  int64_t d_group_stride;
 } vitb_gemm_params;
 
 int vitb_gemm(const vitb_gemm_params* p, void* stream);
@@ -174,8 +184,8 @@ int vitb_attn_bwd_tc2(const vitb_attn_params* p, void* stream);
 /* Persistent warp-specialised generation of the tcgen05 kernels (vitb_attention_ws.cu): one resident CTA per SM walks a
  * contiguous range of (image, head[, query tile]) items; a TMA producer warp, a single-thread tcgen05 issuer and eight
  * CUDA-core warps overlap the loads, MMAs and softmax arithmetic of neighbouring items.  Same contract and shapes as
- * vitb_attn_fwd_tc / vitb_attn_bwd_tc (bf16, head_dim 64, Nq == Nk <= 256). */
-int vitb_attn_ws_supported(int head_dim, int Nq, int Nk);
+ * vitb_attn_fwd_tc / vitb_attn_bwd_tc (bf16, head_dim 64, Nq == Nk <= 256; the forward up to 240 tokens). */
+int vitb_attn_ws_supported(int which /* 0 forward, 1 backward */, int head_dim, int Nq, int Nk);
 int vitb_attn_fwd_ws(const vitb_attn_params* p, void* stream);
 int vitb_attn_bwd_ws(const vitb_attn_params* p, void* stream);
 int vitb_attn_fwd_simt(const vitb_attn_params* p, void* stream);
@@ -263,14 +273,16 @@ int vitb_image_prep(const uint8_t* src, int B, int H, int W, int C, int out_h, i
 int vitb_cross_entropy(const float* logits, const int64_t* labels, int B, int C, float* loss,
                        float* dlogits, void* stream);
 /* torch.optim.SGD(momentum) over a flat buffer (src/train.py:154-158), refreshing the bf16 shadow.
- * lr_dev (optional device scalar) overrides lr, so an LR scheduler can drive a captured CUDA graph. */
-int vitb_sgd_momentum(float* p, const float* g, float* m, int64_t n, float lr, const float* lr_dev, float momentum,
+ * hyper_dev (optional DEVICE array of 4 floats {lr, momentum, dampening, weight_decay}) overrides the by-value arguments,
+ * so an LR scheduler (OneCycleLR cycles lr AND momentum) keeps driving a captured CUDA graph. */
+int vitb_sgd_momentum(float* p, const float* g, float* m, int64_t n, float lr, const float* hyper_dev, float momentum,
                       float dampening, float weight_decay, int nesterov, int first_step,
                       void* shadow_hi, void* shadow_lo, void* stream);
 /* torch.optim.AdamW over a flat buffer (res-vit/train.py:272-277); grad_scale_dev (optional device
- * scalar) carries the clip_grad_norm_ coefficient (res-vit/train.py:65).  lr_dev / step_dev (optional device
- * scalars) override lr / step so a captured CUDA graph follows the scheduler and the bias correction. */
-int vitb_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, const float* lr_dev, float beta1,
+ * scalar) carries the clip_grad_norm_ coefficient (res-vit/train.py:65).  hyper_dev (optional DEVICE array of 4 floats
+ * {lr, beta1, beta2, weight_decay}) / step_dev (optional device scalar) override the by-value arguments so a captured
+ * CUDA graph follows the scheduler and the bias correction. */
+int vitb_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, const float* hyper_dev, float beta1,
                float beta2, float eps, float weight_decay, int step, const int* step_dev,
                const float* grad_scale_dev, void* shadow_hi, void* shadow_lo, void* stream);
 int vitb_sumsq(const float* x, int64_t n, float* out, void* stream);

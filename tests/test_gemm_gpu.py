@@ -321,3 +321,45 @@ def test_gemm_wgrad_on_cta_pairs(M, N, K):
         assert rel_l2(out, ref) < 2e-5
         outs.append(out)
     assert rel_l2(outs[0], outs[1]) < 1e-6
+
+
+@pytest.mark.parametrize("b_mn", [True, False])
+@pytest.mark.parametrize("M,Ng,K,gap", [(200, 256, 192, 0), (1000, 768, 768, 768), (25216, 768, 768, 64)])
+def test_gemm_column_groups_merged_qkv(M, Ng, K, gap, b_mn):
+    """n_groups = 3: q | k | v as ONE GEMM against three weight matrices that only sit at a uniform distance (`gap` extra
+    elements between them, as the biases do in a parameter-ordered flat buffer) — src/model.py:86-88."""
+    import vitb200
+    G = 3
+    A = _mk((M, K), 11)
+    flat = _mk((G * (K * Ng + gap),), 12)
+    Bst = torch.as_strided(flat, (G, K, Ng) if b_mn else (G, Ng, K), (K * Ng + gap, Ng if b_mn else K, 1))
+    bias = torch.randn(G * Ng, device="cuda")
+    out = vitb200.ops.gemm(A, Bst, b_mn=b_mn, bias=bias)
+    torch.cuda.synchronize()
+    assert out.shape == (M, G * Ng)
+    for g in range(G):
+        Bf = Bst[g].float() if b_mn else Bst[g].float().t()
+        ref = A.float() @ Bf + bias[g * Ng:(g + 1) * Ng]
+        assert rel_l2(out[:, g * Ng:(g + 1) * Ng], ref) < 4e-3, g
+
+
+@pytest.mark.parametrize("pair", ["1", "0"])
+@pytest.mark.parametrize("T,Kin,Ng,gap", [(1000, 256, 256, 256), (25216, 768, 768, 0), (4000, 768, 768, 768)])
+def test_gemm_grouped_output_merged_qkv_wgrad(T, Kin, Ng, gap, pair, monkeypatch):
+    """The three weight gradients dW_g[Kin, Ng] += X^T dY[:, g] of a merged projection as ONE GEMM whose output groups sit
+    at a uniform distance (views of a flat gradient buffer), on CTA pairs and on the single-CTA kernel."""
+    import vitb200
+    monkeypatch.setenv("VITB_GEMM_PAIR", pair)
+    G = 3
+    X = _mk((T, Kin), 21, 0.5)
+    dY = _mk((T, G * Ng), 22, 0.5)
+    flat = torch.full((G * (Kin * Ng + gap),), 0.25, device="cuda")
+    out = torch.as_strided(flat, (G, Kin, Ng), (Kin * Ng + gap, Ng, 1))
+    vitb200.ops.gemm(X, dY, a_mn=True, b_mn=True, out=out, accumulate=True)
+    torch.cuda.synchronize()
+    for g in range(G):
+        ref = X.float().t() @ dY[:, g * Ng:(g + 1) * Ng].float() + 0.25
+        assert rel_l2(out[g], ref) < 2e-5, g
+    if gap:     # nothing was written between the groups
+        between = torch.as_strided(flat, (G, gap), (Kin * Ng + gap, 1), Kin * Ng)
+        assert bool((between == 0.25).all())

@@ -91,8 +91,10 @@ def test_resvit_eval_indices_bit_exact_and_logits(variant):
     # bf16: decisions may only flip where the two router logits are within bf16 noise of a tie
     agree = float((acts16 == g["eval"]["acts"]).float().mean())
     assert agree > 0.97, agree
-    if agree == 1.0:
-        assert rel_l2(logits16, g["eval"]["logits"]) < 2e-2
+    # images are independent of each other: every image whose decisions all agree must meet the 2e-2 bar
+    same = (acts16 == g["eval"]["acts"]).flatten(1).all(1)
+    assert int(same.sum()) >= 1, "no image kept all of its decisions"
+    assert rel_l2(logits16[same], g["eval"]["logits"][same]) < 2e-2
 
 
 def test_router_module_standalone_indices_and_gradients():
@@ -158,3 +160,108 @@ def test_lora_module_and_attention_with_lora_match_oracle():
     assert rel_l2(y16, ref) < 2e-2
     assert rel_l2(lo, (x @ sd["a.lora_q.lora_A.weight"].t()) @ sd["a.lora_q.lora_B.weight"].t()) < 1e-4
     assert rel_l2(y_asym, resvit_oracle.attention(x[:, :20], x, sd, "a.", 4, True)) < 2e-2
+
+
+# ---------------------------------------------------------------------------------------------------
+# BASELINE.json configs[4] geometry (D = 768, 197 tokens, router hidden 512, approximator rank 256, LoRA rank 8)
+# ---------------------------------------------------------------------------------------------------
+GOLD_C5 = os.path.join(ROOT, "tests", "golden", "resvit_c5.pt")
+
+
+def _build_c5(g):
+    """Re-creates the golden run's weights: the product's constructors reproduce the reference state_dict bit for bit
+    under the same seed (tests/test_resvit_oracle.py); the fingerprints stored with the golden vectors are checked."""
+    from vitb200 import resvit
+    from oracle.make_golden_c5 import c5_edit_
+    torch.manual_seed(g["seed"])
+    m = resvit.Transformer(resvit.ModelArgs(**g["args"]))
+    c5_edit_(m, g["edit_seed"])
+    for k, v in m.state_dict().items():
+        fp = g["weights_fp"][k]
+        assert tuple(v.shape) == fp["shape"] and abs(float(v.double().sum()) - fp["sum"]) <= 1e-6 * max(1.0, fp["abs"]), k
+    return m.cuda()
+
+
+def _replay_c5_noise(m, g):
+    it = iter(g["train"]["noise"])
+    for layer in m.layers:
+        if hasattr(layer, "router"):
+            layer.router.noise_fn = lambda logits, it=it: next(it).to(logits.device)
+
+
+def _fp_close(t, fp, rtol, atol=1e-8):
+    """gradient vs its stored fingerprint: norm and the first 16 values."""
+    n = float(t.double().norm())
+    if abs(n - fp["norm"]) > rtol * fp["norm"] + atol * (t.numel() ** 0.5):
+        return False
+    head = t.detach().flatten()[:16].float().cpu()
+    return float((head - fp["head"]).norm()) <= rtol * max(float(fp["head"].norm()), fp["norm"] / (t.numel() ** 0.5)) * 4 + atol
+
+
+@pytest.mark.parametrize("variant", ["bs1", "bs2"])
+def test_resvit_c5_geometry_train_fp32_mode(variant):
+    import vitb200
+    from conftest import grad_close
+    from oracle import make_golden_c5
+    g = torch.load(GOLD_C5)[variant]
+    m = _build_c5(g).train()
+    _replay_c5_noise(m, g)
+    img, labels = make_golden_c5.c5_inputs()
+    t = g["train"]
+    with vitb200.precision("fp32"):
+        c, a, d, e, metric = m(img.cuda(), labels.cuda())
+        (1.0 * c + 2.0 * a + 0.5 * d + 0.1 * e).backward()
+    torch.cuda.synchronize()
+    acts = torch.cat([w.float() for w in m.acts], -1).cpu()
+    assert torch.equal(acts, t["acts"]), "router keep/skip decisions must be bit-exact"
+    assert rel_l2(m.logits.cpu(), t["logits"]) < 1e-4
+    for got, key in ((c, "c"), (a, "a"), (d, "d"), (e, "e")):
+        assert abs(float(got) - float(t[key])) < 1e-4 * max(1.0, abs(float(t[key]))), key
+    assert abs(float(metric["non_low_rank_ratio"]) - t["metric"]) < 1e-6
+    named = dict(m.named_parameters())
+    assert sorted(k for k, p in named.items() if p.requires_grad) == t["trainable"]
+    for k, fp in t["grads_fp"].items():
+        assert named[k].grad is not None, k
+        assert _fp_close(named[k].grad, fp, 2e-4), (k, float(named[k].grad.double().norm()), fp["norm"])
+    for k, ref in t["grads"].items():
+        assert grad_close(named[k].grad.cpu(), ref, 2e-4, atol=1e-8), (k, rel_l2(named[k].grad.cpu(), ref))
+
+
+@pytest.mark.parametrize("variant", ["bs1", "bs2"])
+def test_resvit_c5_geometry_bf16_train_and_eval(variant):
+    """bf16 mode at the benchmarked geometry: decisions may flip only where the two router logits are within bf16 noise
+    of a tie; every image that kept all its decisions meets the 2e-2 logits bar (train with the replayed Gumbel draw,
+    and eval); the losses follow."""
+    import vitb200
+    from oracle import make_golden_c5
+    g = torch.load(GOLD_C5)[variant]
+    m = _build_c5(g)
+    img, labels = make_golden_c5.c5_inputs()
+    for mode in ("train", "eval"):
+        t = g[mode]
+        m.train(mode == "train")
+        if mode == "train":
+            _replay_c5_noise(m, g)
+        with vitb200.precision("bf16"):
+            if mode == "train":
+                c, a, d, e, metric = m(img.cuda(), labels.cuda())
+                (1.0 * c + 2.0 * a + 0.5 * d + 0.1 * e).backward()
+            else:
+                with torch.no_grad():
+                    c, a, d, e, metric = m(img.cuda(), labels.cuda())
+        torch.cuda.synchronize()
+        acts = torch.cat([w.float() for w in m.acts], -1).cpu()
+        agree = float((acts == t["acts"]).float().mean())
+        assert agree > 0.97, (mode, agree)
+        same = (acts == t["acts"]).flatten(1).all(1)
+        if int(same.sum()) > 0:
+            assert rel_l2(m.logits.float().cpu()[same], t["logits"][same]) < 2e-2, mode
+        assert abs(float(metric["non_low_rank_ratio"]) - t["metric"]) < 0.02
+        if agree == 1.0:
+            assert abs(float(c) - float(t["c"])) < 2e-2 * max(1.0, abs(float(t["c"]))), mode
+        if mode == "train":
+            for k, p in m.named_parameters():
+                assert (p.grad is not None) == p.requires_grad, k
+                if p.grad is not None:
+                    assert bool(torch.isfinite(p.grad).all()), k
+            m.zero_grad(set_to_none=True)

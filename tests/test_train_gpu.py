@@ -140,3 +140,113 @@ def test_input_prefetcher_delivers_batches_in_order_into_the_graph_buffers():
     b, _ = pre2.get()
     torch.cuda.synchronize()
     assert torch.equal(b.cpu(), host[4][0])
+
+
+def test_graphed_step_follows_onecycle_momentum():
+    """OneCycleLR (the reference's schedule, src/train.py:159-163) cycles the MOMENTUM as well as the learning rate; the
+    captured step reads both from device scalars, so replayed training equals eager training."""
+    import vitb200
+    g = torch.Generator().manual_seed(5)
+    img = torch.randn(8, 3, 64, 64, generator=g).cuda()
+    lab = torch.randint(0, 16, (8,), generator=g).cuda()
+
+    def make():
+        m = _tiny()
+        opt = vitb200.optim.FusedSGD(m.parameters(), lr=0.05, momentum=0.9)
+        sched = torch.optim.lr_scheduler.OneCycleLR(opt, max_lr=0.05, total_steps=8, pct_start=0.4)
+        return m, opt, sched
+
+    m, opt, sched = make()
+    moms = []
+    for i in range(6):
+        moms.append(opt.param_groups[0]["momentum"])
+        opt.zero_grad()
+        vitb200.functional.cross_entropy(m(img), lab).backward()
+        opt.step()
+        sched.step()
+    assert max(moms) - min(moms) > 0.05, "the schedule is expected to move the momentum"
+    w_eager = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    m, opt, sched = make()
+    step = vitb200.train.GraphedTrainStep(m, opt, img, lab, warmup=1)
+    sched.step()
+    for i in range(5):
+        step(img, lab)
+        sched.step()
+    torch.cuda.synchronize()
+    for k, v in m.state_dict().items():
+        assert rel_l2(v, w_eager[k]) < 2e-3, (k, rel_l2(v, w_eager[k]))
+
+
+def test_backward_side_channel_hits_and_survives_a_second_consumer(monkeypatch):
+    """The bf16 copy / column sums that a fused block leaves for the block upstream are used when that block receives
+    exactly the tensor (3 blocks -> 2 hits), and are rejected when autograd has added a second consumer's gradient into
+    the buffer (an auxiliary loss on a block's input): gradients then still equal the run without the side channel."""
+    import vitb200
+    from vitb200 import functional as F
+    g = torch.Generator().manual_seed(9)
+    img = torch.randn(4, 3, 64, 64, generator=g).cuda()
+    lab = torch.randint(0, 16, (4,), generator=g).cuda()
+
+    def run(aux, side):
+        monkeypatch.setenv("VITB_GRAD_SIDE", side)
+        m = _tiny(seed=1)
+        feats = []
+        if aux:
+            m.transformer.encoder_layers[1].register_forward_hook(lambda mod, inp, out: feats.append(out))
+        F.SIDE_STATS[0] = F.SIDE_STATS[1] = 0
+        loss = vitb200.functional.cross_entropy(m(img), lab)
+        if aux:
+            loss = loss + 0.01 * feats[0].float().pow(2).mean()
+        loss.backward()
+        torch.cuda.synchronize()
+        return {k: p.grad.detach().clone() for k, p in m.named_parameters()}, tuple(F.SIDE_STATS)
+
+    # the last block computes only the class-token row (no fused node), so 2 fused blocks -> 1 hand-over
+    g_on, stats = run(False, "1")
+    assert stats[0] >= 1, stats
+    g_off, _ = run(False, "0")
+    for k in g_on:
+        assert grad_close(g_on[k], g_off[k], 2e-2, atol=1e-6), k
+    g_aux_on, stats_aux = run(True, "1")
+    g_aux_off, _ = run(True, "0")
+    for k in g_aux_on:
+        assert grad_close(g_aux_on[k], g_aux_off[k], 2e-2, atol=1e-6), (k, stats_aux)
+
+
+def test_fused_optimizer_state_dict_round_trip_and_zero_grad_misuse():
+    import vitb200
+    g = torch.Generator().manual_seed(4)
+    img = torch.randn(4, 3, 64, 64, generator=g).cuda()
+    lab = torch.randint(0, 16, (4,), generator=g).cuda()
+
+    def steps(m, opt, n):
+        for _ in range(n):
+            opt.zero_grad()
+            vitb200.functional.cross_entropy(m(img), lab).backward()
+            opt.step()
+
+    for make in (lambda ps: vitb200.optim.FusedSGD(ps, lr=0.05, momentum=0.9),
+                 lambda ps: vitb200.optim.FusedAdamW(ps, lr=1e-3, weight_decay=0.05, max_grad_norm=1.0)):
+        m1 = _tiny()
+        o1 = make(m1.parameters())
+        steps(m1, o1, 2)
+        sd_m = {k: v.detach().clone() for k, v in m1.state_dict().items()}
+        sd_o = o1.state_dict()
+        assert len(sd_o["state"]) == len(list(m1.parameters()))
+        steps(m1, o1, 2)
+        m2 = _tiny()
+        o2 = make(m2.parameters())
+        m2.load_state_dict(sd_m)
+        o2.load_state_dict(sd_o)
+        steps(m2, o2, 2)
+        torch.cuda.synchronize()
+        for (k, a), (_, b) in zip(m1.state_dict().items(), m2.state_dict().items()):
+            assert rel_l2(b, a) < 1e-5, k
+    # model.zero_grad() hides the flat gradient buffer without zeroing it: step() must refuse
+    m = _tiny()
+    opt = vitb200.optim.FusedSGD(m.parameters(), lr=0.05, momentum=0.9)
+    steps(m, opt, 1)
+    m.zero_grad(set_to_none=True)
+    vitb200.functional.cross_entropy(m(img), lab).backward()
+    with pytest.raises(RuntimeError, match="optimizer.zero_grad"):
+        opt.step()

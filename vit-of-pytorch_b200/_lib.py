@@ -64,6 +64,10 @@ class GemmParams(C.Structure):
         ("aux", C.c_void_p),
         ("ldaux", C.c_int64),
         ("colsum", C.c_void_p),
+        ("n_groups", C.c_int32),
+        ("_pad1", C.c_int32),
+        ("b_group_stride", C.c_int64),
+        ("d_group_stride", C.c_int64),
     ]
 
 
@@ -169,7 +173,7 @@ _vitb_attn_fwd_tc = _sig("vitb_attn_fwd_tc", [C.POINTER(AttnParams), _vp])
 _vitb_attn_bwd_tc = _sig("vitb_attn_bwd_tc", [C.POINTER(AttnParams), _vp])
 vitb_attn_bwd_tc2_supported = _sig("vitb_attn_bwd_tc2_supported", [_i, _i, _i])
 _vitb_attn_bwd_tc2 = _sig("vitb_attn_bwd_tc2", [C.POINTER(AttnParams), _vp])       # experimental key-split CTA pairs
-vitb_attn_ws_supported = _sig("vitb_attn_ws_supported", [_i, _i, _i])
+vitb_attn_ws_supported = _sig("vitb_attn_ws_supported", [_i, _i, _i, _i])
 _vitb_attn_fwd_ws = _sig("vitb_attn_fwd_ws", [C.POINTER(AttnParams), _vp])         # persistent warp-specialised kernels
 _vitb_attn_bwd_ws = _sig("vitb_attn_bwd_ws", [C.POINTER(AttnParams), _vp])
 _vitb_attn_fwd_simt = _sig("vitb_attn_fwd_simt", [C.POINTER(AttnParams), _vp])

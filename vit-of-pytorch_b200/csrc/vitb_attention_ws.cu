@@ -7,15 +7,15 @@
 // Why a second generation: the one-CTA-per-tile kernels of vitb_attention_tc.cu run every phase of their chain
 // (TMA -> MMA -> CUDA-core pass -> CTA barrier -> MMA -> store) exposed; ncu showed 12-14 % tensor-pipe activity and
 // 23-46 % issue utilisation (profiles/ncu_r01c.txt), i.e. latency-bound.  Here ONE CTA per SM stays resident and
-// walks a contiguous range of work items; a TMA producer warp, a single-thread tcgen05 issuer warp and eight
+// walks a contiguous range of work items; a TMA producer warp, a single-thread tcgen05 issuer warp and the
 // CUDA-core warps run as a pipeline connected by mbarriers, so loads, MMAs and the softmax arithmetic of
 // neighbouring items overlap:
 //
-//   forward  (attn_fwd_ws)  item = (image, head, 128-query tile).  Two softmax groups of 128 threads (one thread per
-//            query row, no cross-thread max / sum exchange) alternate over the items; each owns a 256-column TMEM
-//            buffer (S, later O in its first 64 columns) and a P image in shared memory.  K / V are loaded once per
-//            head and shared by its tiles.  While group g does the softmax of item i, the issuer has S(i+1) in flight
-//            for the other group and P(i-1) V behind it.
+//   forward  (attn_fwd_ws)  item = (image, head, 128-query tile).  Two softmax groups of 8 warps (two threads per
+//            query row, each half of the keys) alternate over the items; each group owns a 256-column TMEM buffer
+//            (S, later O in its first 64 columns) and a P image in shared memory.  K / V are loaded once per head and
+//            shared by its tiles.  While group g does the softmax of item i, the issuer has S(i+1) in flight for the
+//            other group and P(i-1) V behind it.
 //   backward (attn_bwd_ws)  item = (image, head); iterations (key tile kt, query tile qt), kt outer.  TMEM: S | dP |
 //            dQ[2 query tiles] | dK | dV = 512 columns.  Eight warps (two threads per query row) turn S into P and
 //            dP into dS; the issuer runs S(i+1) and dV(i) behind P(i), dP(i+1), dK(i), dQ(i) behind dS(i); finished
@@ -31,7 +31,6 @@ namespace {
 using namespace vitb;
 using namespace vitb::attn;
 
-constexpr int kWsThreads = 320;          // warps 0-7: CUDA-core work, warp 8: TMA producer, warp 9: tcgen05 issuer
 constexpr float kLog2e = 1.4426950408889634f;
 
 __device__ __forceinline__ void named_bar_sync(int id, int count) {
@@ -50,18 +49,57 @@ struct WsParams {
   float* lse;     // [B,H,N]
 };
 
+// UMMA shared-memory descriptors are built once per buffer; k-steps advance the 14-bit start-address field (16-byte
+// units; shared memory ends below 256 KiB, so the field cannot carry into its neighbours)
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t addr) { return umma_smem_desc_sw128(addr, 16, 1024); }
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t addr, uint32_t lbo) { return umma_smem_desc_sw128(addr, lbo, 1024); }
+
 // ================================================================================================
 // forward
 // ================================================================================================
-// barriers (8 bytes each)
-enum FwdBar { FB_K = 0, FB_V = 1, FB_Q = 2 /*[2]*/, FB_S = 4 /*[2]*/, FB_P = 6 /*[2]*/, FB_O = 8 /*[2]*/, FB_D = 10 /*[2]*/, FB_COUNT = 12 };
+constexpr int kFwdThreads = 576;         // warps 0-15: two softmax groups of 8; warp 16: TMA producer; warp 17: tcgen05 issuer
+enum FwdBar { FB_K = 0, FB_V = 1, FB_Q = 2 /*[2]*/, FB_S = 4 /*[2]*/, FB_P = 6 /*[2] 256*/, FB_O = 8 /*[2]*/, FB_D = 10 /*[2] 256*/, FB_COUNT = 12 };
 
-__global__ void __launch_bounds__(kWsThreads, 1)
+// W (16 or 32) score columns of this thread's row, already in registers -> p = exp2(s*c - m*c) -> row-sum partial,
+// bf16 -> the 128B-swizzled P image (keys c .. c+W-1 of row r).  MASK: columns >= n_valid (relative to the chunk) are
+// padding keys -> p = 0.
+template <int W, bool MASK>
+__device__ __forceinline__ void softmax_chunk(const uint32_t (&v)[32], uint64_t sc2, uint64_t nm2, int n_valid, uint64_t& sum2a,
+                                              uint64_t& sum2b, uint32_t image, int r, int rx, int c) {
+  uint32_t pk[W / 2];
+#pragma unroll
+  for (int j = 0; j < W / 2; ++j) {
+    float x0, x1;
+    upk2(fma2(pk2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), sc2, nm2), x0, x1);
+    float e0 = ex2_approx(x0), e1 = ex2_approx(x1);
+    if (MASK) {
+      e0 = (2 * j < n_valid) ? e0 : 0.f;
+      e1 = (2 * j + 1 < n_valid) ? e1 : 0.f;
+    }
+    const uint64_t e2 = pk2(e0, e1);
+    if (j & 1) sum2b = add2(sum2b, e2); else sum2a = add2(sum2a, e2);
+    pk[j] = pack_bf16x2(e0, e1);
+  }
+  // 16 keys (two 16-byte units) never straddle a 64-key chunk of the image, 32 keys may (c is a multiple of 16)
+#pragma unroll
+  for (int q = 0; q < W / 16; ++q) {
+    const int cq = c + 16 * q;
+    const uint32_t row_addr = image + static_cast<uint32_t>((cq >> 6) * kChunkBytes + r * 128);
+    const int u8 = (cq & 63) >> 3;
+    st_shared_v4(row_addr + static_cast<uint32_t>((u8 ^ rx) << 4), pk[8 * q], pk[8 * q + 1], pk[8 * q + 2], pk[8 * q + 3]);
+    st_shared_v4(row_addr + static_cast<uint32_t>(((u8 + 1) ^ rx) << 4), pk[8 * q + 4], pk[8 * q + 5], pk[8 * q + 6], pk[8 * q + 7]);
+  }
+}
+
+__global__ void __launch_bounds__(kFwdThreads, 1)
 attn_fwd_ws(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
             const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
             const __grid_constant__ WsParams a) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) {  // SWIZZLE_128B tiles need 1024-byte aligned bases
+    if (threadIdx.x == 0) printf("attn_fwd_ws: dynamic shared memory base 0x%x is not 1024-byte aligned\n", smem_u32(smem));
+    __trap();
+  }
   const int NK = a.NK;
   const int kv_bytes = NK * 128;                 // [NK keys x 64] bf16, 128B-swizzled rows
   const int pchunks = (NK + 63) >> 6;            // 64-key chunks of a P image
@@ -70,8 +108,10 @@ attn_fwd_ws(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   const uint32_t sV_u = sK_u + kv_bytes;
   const uint32_t sQ_u = sV_u + kv_bytes;         // [2] query tiles, one per softmax group
   const uint32_t sP_u = sQ_u + 2 * kChunkBytes;  // [2] P images; chunk 0 doubles as the O staging tile
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kv_bytes + 2 * kChunkBytes + 2 * p_bytes);
+  uint8_t* tail = smem + 2 * kv_bytes + 2 * kChunkBytes + 2 * p_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + FB_COUNT);
+  float* red = reinterpret_cast<float*>(bars + FB_COUNT + 2);   // [2 groups][max | sum][2 halves][128 rows]
   const uint32_t bar0 = smem_u32(bars);
   auto bar = [&](int i) { return bar0 + 8u * static_cast<uint32_t>(i); };
 
@@ -79,10 +119,10 @@ attn_fwd_ws(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   pdl_trigger();
   if (tid == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmO);
-    for (int i = 0; i < FB_COUNT; ++i) mbar_init(bar(i), (i >= FB_P && i < FB_O) || i >= FB_D ? 128 : 1);
+    for (int i = 0; i < FB_COUNT; ++i) mbar_init(bar(i), ((i >= FB_P && i < FB_O) || i >= FB_D) ? 256 : 1);
     fence_barrier_init();
   }
-  if (warp == 9) { __syncwarp(); tmem_alloc(smem_u32(tmem_slot), 512); tmem_relinquish(); }
+  if (warp == 17) { __syncwarp(); tmem_alloc(smem_u32(tmem_slot), 512); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -95,12 +135,12 @@ attn_fwd_ws(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   const int n = t_end - t_begin;
   const int QT = a.qtiles;
 
-  if (warp == 8) {
+  if (warp == 16) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
       int q_issued = 0;
-      auto wait_s = [&](int i) { mbar_wait(bar(FB_S + (i & 1)), static_cast<uint32_t>((i >> 1) & 1)); };
-      auto wait_o = [&](int i) { mbar_wait(bar(FB_O + (i & 1)), static_cast<uint32_t>((i >> 1) & 1)); };
+      auto wait_s = [&](int i) { mbar_wait_backoff(bar(FB_S + (i & 1)), static_cast<uint32_t>((i >> 1) & 1), 64); };
+      auto wait_o = [&](int i) { mbar_wait_backoff(bar(FB_O + (i & 1)), static_cast<uint32_t>((i >> 1) & 1), 64); };
       auto issue_q = [&](int upto) {
         while (q_issued <= upto && q_issued < n) {
           const int i = q_issued;
@@ -128,124 +168,126 @@ attn_fwd_ws(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == 17) {
     // =============================== tcgen05 issuer ===============================
     if (lane == 0) {
       const uint32_t idesc_s = umma_idesc_bf16(128, NK, false, false);
       const uint32_t idesc_o = umma_idesc_bf16(128, DH, false, true);
       const int nks = NK >> 4;
+      const uint64_t dK = desc_kmajor(sK_u), dV = desc_mnmajor(sV_u, 8192);
       uint32_t k_heads = 0, v_heads = 0;           // heads whose K / V have been waited for
       for (int i = 0; i <= n; ++i) {
         if (i < n) {                               // S(i) = Q K^T into this group's TMEM buffer
           const int t = t_begin + i, head = t / QT, qt = t - head * QT, g = i & 1;
-          if (i == 0 || qt == 0) { mbar_wait(bar(FB_K), k_heads & 1u); ++k_heads; }
-          mbar_wait(bar(FB_Q + g), static_cast<uint32_t>((i >> 1) & 1));
-          if (i >= 2) mbar_wait(bar(FB_D + g), static_cast<uint32_t>(((i - 2) >> 1) & 1));   // O(i-2) drained
+          if (i == 0 || qt == 0) { mbar_wait_backoff(bar(FB_K), k_heads & 1u, 32); ++k_heads; }
+          mbar_wait_backoff(bar(FB_Q + g), static_cast<uint32_t>((i >> 1) & 1), 32);
+          if (i >= 2) mbar_wait_backoff(bar(FB_D + g), static_cast<uint32_t>(((i - 2) >> 1) & 1), 32);   // O(i-2) drained
           tc_fence_after();
           const uint32_t d = tmem_base + static_cast<uint32_t>(g * 256);
-          const uint32_t q = sQ_u + g * kChunkBytes;
+          const uint64_t dQ = desc_kmajor(sQ_u + g * kChunkBytes);
 #pragma unroll
-          for (int k = 0; k < DH / 16; ++k)
-            umma_bf16_ss(d, umma_smem_desc_sw128(q + k * 32, 16, 1024), umma_smem_desc_sw128(sK_u + k * 32, 16, 1024),
-                         idesc_s, k > 0 ? 1u : 0u);
+          for (int k = 0; k < DH / 16; ++k) umma_bf16_ss(d, dQ + 2 * k, dK + 2 * k, idesc_s, k > 0 ? 1u : 0u);
           umma_commit(bar(FB_S + g));
         }
         if (i >= 1) {                              // O(j) = P(j) V over the first 64 columns of S(j)'s buffer
           const int j = i - 1, t = t_begin + j, head = t / QT, qt = t - head * QT, g = j & 1;
-          if (j == 0 || qt == 0) { mbar_wait(bar(FB_V), v_heads & 1u); ++v_heads; }
-          mbar_wait(bar(FB_P + g), static_cast<uint32_t>((j >> 1) & 1));
+          if (j == 0 || qt == 0) { mbar_wait_backoff(bar(FB_V), v_heads & 1u, 32); ++v_heads; }
+          mbar_wait_backoff(bar(FB_P + g), static_cast<uint32_t>((j >> 1) & 1), 32);
           tc_fence_after();
           const uint32_t d = tmem_base + static_cast<uint32_t>(g * 256);
-          const uint32_t p = sP_u + g * p_bytes;
-          for (int t16 = 0; t16 < nks; ++t16)
-            umma_bf16_ss(d, umma_smem_desc_sw128(p + (t16 >> 2) * kChunkBytes + (t16 & 3) * 32, 16, 1024),
-                         umma_smem_desc_sw128(sV_u + t16 * 2048, 8192, 1024), idesc_o, t16 > 0 ? 1u : 0u);
+          const uint64_t dP = desc_kmajor(sP_u + g * p_bytes);
+          for (int t16 = 0; t16 < nks; ++t16)      // 16 keys per step: 32 B inside a 64-key chunk, 16 KiB between chunks
+            umma_bf16_ss(d, dP + static_cast<uint64_t>((t16 >> 2) * (kChunkBytes >> 4) + (t16 & 3) * 2), dV + static_cast<uint64_t>(t16 * 128),
+                         idesc_o, t16 > 0 ? 1u : 0u);
           umma_commit(bar(FB_O + g));
         }
       }
     }
   } else {
     // =============================== softmax groups ===============================
-    const int g = warp >> 2;                       // group 0: items 0, 2, 4, ...; group 1: items 1, 3, 5, ...
+    const int g = warp >> 3;                       // group 0: items 0, 2, 4, ...; group 1: items 1, 3, 5, ...
+    const int half = (warp >> 2) & 1;              // two threads per query row: which half of the keys / head-dim columns
     const int r = (warp & 3) * 32 + lane;          // query row within the tile == TMEM lane
-    const bool elected = (r == 0);
+    const int rx = r & 7;
+    const bool elected = (r == 0 && half == 0);
     const uint32_t trow = tmem_base + static_cast<uint32_t>(g * 256) + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     const uint32_t sPg = sP_u + g * p_bytes;
-    const int nch = (NK + 31) >> 5;
+    float* red_max = red + g * 512;                // [2 halves][128]
+    float* red_sum = red_max + 256;
+    // this thread's key columns [cb, ce): the 16-key units are split between the two halves of a row
+    const int nunits = NK >> 4, umid = (nunits + 1) >> 1;
+    const int cb = half ? umid * 16 : 0, ce = half ? NK : umid * 16;
+    const uint64_t sc2 = pk2(a.scale_log2);
     for (int i = g; i < n; i += 2) {
       const uint32_t ph = static_cast<uint32_t>((i >> 1) & 1);
       const int t = t_begin + i, head = t / QT, qt = t - head * QT;
       const int b = head / a.H, h = head - b * a.H;
       mbar_wait(bar(FB_S + g), ph);
       tc_fence_after();
-      // pass 1: row max over the valid keys (two TMEM loads in flight per wait)
+      // pass 1: row max over this thread's valid keys
       float mx = -INFINITY;
-      for (int c = 0; c < nch; c += 2) {
-        uint32_t v0[32], v1[32];
-        const bool two = (c + 1 < nch);
-        issue_chunk(trow, c * 32, NK, v0);
-        if (two) issue_chunk(trow, (c + 1) * 32, NK, v1);
-        tmem_ld_wait();
-        mx = fmaxf(mx, chunk_max(v0, c * 32, NK, a.N));
-        if (two) mx = fmaxf(mx, chunk_max(v1, (c + 1) * 32, NK, a.N));
-      }
-      // the TMA store of this group's previous O tile has finished reading the staging tile (chunk 0 of the P image)
-      if (i >= 2) {
-        if (elected) bulk_wait_read<0>();
-        named_bar_sync(1 + g, 128);
-      }
-      // pass 2: p = exp2((s - max) * c), row sum, bf16 P into the swizzled A-operand image
-      const float mxs = mx * a.scale_log2;
-      const uint64_t sc2 = pk2(a.scale_log2), nm2 = pk2(-mxs);
-      uint64_t sum2a = pk2(0.f), sum2b = pk2(0.f);
-      for (int c = 0; c < nch; ++c) {
-        const int c0 = c * 32;
+      for (int c = cb; c < ce; c += 32) {
         uint32_t v[32];
-        ld_chunk(trow, c0, NK, 0u, v);
-        uint32_t pk[16];
-        const bool interior = (c0 + 32 <= a.N);    // every column of the chunk is a valid key
+        if (c + 32 <= ce) {
+          tmem_ld_32x32b_x32(trow + c, v);
+          tmem_ld_wait();
+          if (c + 32 <= a.N) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float x0, x1;
-          upk2(fma2(pk2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), sc2, nm2), x0, x1);
-          float e0 = ex2_approx(x0), e1 = ex2_approx(x1);
-          if (!interior) {
-            e0 = (c0 + 2 * j < a.N) ? e0 : 0.f;
-            e1 = (c0 + 2 * j + 1 < a.N) ? e1 : 0.f;
+            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, (c + j < a.N) ? __uint_as_float(v[j]) : -INFINITY);
           }
-          const uint64_t e2 = pk2(e0, e1);
-          if (j & 1) sum2b = add2(sum2b, e2); else sum2a = add2(sum2a, e2);
-          pk[j] = pack_bf16x2(e0, e1);
-        }
-        const int kc = c0 >> 6, u0 = (c0 & 63) >> 3, nunits = (c0 + 32 <= NK) ? 4 : 2;
+        } else {
+          tmem_ld_32x32b_x16(trow + c, reinterpret_cast<uint32_t(&)[16]>(v));
+          tmem_ld_wait();
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (u < nunits)
-            st_shared_v4(sPg + kc * kChunkBytes + swz_unit(r, u0 + u), pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+          for (int j = 0; j < 16; ++j) mx = fmaxf(mx, (c + j < a.N) ? __uint_as_float(v[j]) : -INFINITY);
+        }
       }
-      fence_proxy_async_smem();
-      tc_fence_before();
-      mbar_arrive(bar(FB_P + g));
+      red_max[half * 128 + r] = mx;
+      // the TMA store of this group's previous O tile has finished reading the staging tile (chunk 0 of the P image)
+      if (elected) bulk_wait_read<0>();
+      named_bar_sync(1 + g, 256);
+      mx = fmaxf(mx, red_max[(half ^ 1) * 128 + r]);
+      // pass 2: p = exp2((s - max) * c), row sum, bf16 P into the swizzled A-operand image
+      const uint64_t nm2 = pk2(-mx * a.scale_log2);
+      uint64_t sum2a = pk2(0.f), sum2b = pk2(0.f);
+      for (int c = cb; c < ce; c += 32) {
+        uint32_t v[32];
+        if (c + 32 <= ce) {
+          tmem_ld_32x32b_x32(trow + c, v);
+          tmem_ld_wait();
+          if (c + 32 <= a.N) softmax_chunk<32, false>(v, sc2, nm2, 32, sum2a, sum2b, sPg, r, rx, c);
+          else softmax_chunk<32, true>(v, sc2, nm2, a.N - c, sum2a, sum2b, sPg, r, rx, c);
+        } else {
+          tmem_ld_32x32b_x16(trow + c, reinterpret_cast<uint32_t(&)[16]>(v));
+          tmem_ld_wait();
+          softmax_chunk<16, true>(v, sc2, nm2, a.N - c, sum2a, sum2b, sPg, r, rx, c);
+        }
+      }
       float s0, s1, s2, s3;
       upk2(sum2a, s0, s1);
       upk2(sum2b, s2, s3);
-      const float sum = (s0 + s1) + (s2 + s3);
+      float sum = (s0 + s1) + (s2 + s3);
+      red_sum[half * 128 + r] = sum;               // read by the other half after the P V barrier (release / acquire chain)
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar(FB_P + g));
       // O = P V
       mbar_wait(bar(FB_O + g), ph);
       tc_fence_after();
-      uint32_t o0[32], o1[32];
-      tmem_ld_32x32b_x32(trow, o0);
-      tmem_ld_32x32b_x32(trow + 32u, o1);
+      uint32_t o[32];
+      tmem_ld_32x32b_x32(trow + static_cast<uint32_t>(half * 32), o);   // this thread's 32 of the 64 head-dim columns
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(bar(FB_D + g));                  // the buffer may receive S(i+2)
-      const float inv = 1.0f / sum;
-      stage_row32_bf16(sPg, r, 0, o0, inv);        // the P image is dead: the P V MMAs have retired
-      stage_row32_bf16(sPg, r, 1, o1, inv);
+      sum += red_sum[(half ^ 1) * 128 + r];
+      stage_row32_bf16(sPg, r, half, o, 1.0f / sum);   // the P image is dead: the P V MMAs have retired
       const int row = qt * 128 + r;
-      if (row < a.N && a.lse) a.lse[(static_cast<long long>(b) * a.H + h) * a.N + row] = mx * a.scale + logf(sum);
+      if (half == 0 && row < a.N && a.lse) a.lse[(static_cast<long long>(b) * a.H + h) * a.N + row] = mx * a.scale + logf(sum);
       fence_proxy_async_smem();
-      named_bar_sync(1 + g, 128);
+      named_bar_sync(1 + g, 256);
       if (elected) {                               // O tile [128 x 64] leaves as one TMA store (rows >= N clipped)
         tma_store_3d(&tmO, sPg, h * DH, qt * 128, b);
         bulk_commit();
@@ -256,12 +298,13 @@ attn_fwd_ws(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+  if (warp == 17) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
 // ================================================================================================
 // backward
 // ================================================================================================
+constexpr int kBwdThreads = 320;         // warps 0-7: P / dS / drains, warp 8: TMA producer, warp 9: tcgen05 issuer
 // TMEM columns
 constexpr uint32_t T_S = 0, T_DP = 128, T_DQ = 256 /* + 64 qt */, T_DK = 384, T_DV = 448;
 
@@ -272,14 +315,38 @@ enum BwdBar {
   BB_DVDR = 16 /*256: dV accumulator drained*/, BB_DKDR = 17 /*256*/, BB_DQDR = 18 /*[2] 256*/, BB_COUNT = 20
 };
 
-__global__ void __launch_bounds__(kWsThreads, 1)
+// One finished accumulator tile [128 x 64]: TMEM -> registers (the accumulator is released to the issuer) -> bf16
+// staging tile -> TMA store.  Called by all 256 CUDA-core threads; kept out of line (six call sites per head, and the
+// instruction cache is what the first version of this kernel was short of).
+__device__ __noinline__ void drain_tile(uint32_t taddr, uint32_t drained_bar, float scale, const CUtensorMap* tm,
+                                        uint32_t stage, int r, int half, bool elected, int col, int row0, int b) {
+  uint32_t v[32];
+  tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(half * 32), v);
+  tmem_ld_wait();
+  tc_fence_before();
+  mbar_arrive(drained_bar);
+  if (elected) bulk_wait_read<0>();            // the previous store has finished reading the staging tile
+  named_bar_sync(1, 256);
+  stage_row32_bf16(stage, r, half, v, scale);
+  fence_proxy_async_smem();
+  named_bar_sync(1, 256);
+  if (elected) {
+    tma_store_3d(tm, stage, col, row0, b);
+    bulk_commit();
+  }
+}
+
+__global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_ws(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
             const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
             const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmDQ,
             const __grid_constant__ CUtensorMap tmDK, const __grid_constant__ CUtensorMap tmDV,
             const __grid_constant__ WsParams a) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) {
+    if (threadIdx.x == 0) printf("attn_bwd_ws: dynamic shared memory base 0x%x is not 1024-byte aligned\n", smem_u32(smem));
+    __trap();
+  }
   // shared memory: K,V stages [2][K | V] | Q,dO stages [2][Q | dO] | O tile | staging tile | P image (2 chunks) | dS image
   const uint32_t sKV_u = smem_u32(smem);
   const uint32_t sQD_u = sKV_u + 4 * kChunkBytes;
@@ -321,26 +388,26 @@ attn_bwd_ws(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   if (warp == 8) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
+      int hl = 0, kt = 0, qt = 0, b = h_begin / a.H, h = h_begin - b * a.H;
       for (int i = 0; i < n; ++i) {
-        const int hl = i / per_head, rem = i - hl * per_head, kt = rem / QT, qt = rem - kt * QT;
-        const int head = h_begin + hl, b = head / a.H, h = head - b * a.H;
         if (qt == 0) {                             // a new key tile: K, V into stage kc & 1
           const int kc = hl * KT + kt, st = kc & 1;
-          if (kc >= 2) mbar_wait(bar(BB_KVFREE + st), static_cast<uint32_t>(((kc >> 1) - 1) & 1));
+          if (kc >= 2) mbar_wait_backoff(bar(BB_KVFREE + st), static_cast<uint32_t>(((kc >> 1) - 1) & 1), 64);
           mbar_arrive_expect_tx(bar(BB_KV + st), 2 * kChunkBytes);
           tma_load_3d(&tmK, bar(BB_KV + st), sKV_u + st * 2 * kChunkBytes, h * DH, kt * 128, b);
           tma_load_3d(&tmV, bar(BB_KV + st), sKV_u + st * 2 * kChunkBytes + kChunkBytes, h * DH, kt * 128, b);
         }
         if (kt == 0) {                             // first use of this query tile: Q, dO into stage qc & 1, O into its tile
           const int qc = hl * QT + qt, st = qc & 1;
-          if (qc >= 2) mbar_wait(bar(BB_QFREE + st), static_cast<uint32_t>(((qc >> 1) - 1) & 1));
+          if (qc >= 2) mbar_wait_backoff(bar(BB_QFREE + st), static_cast<uint32_t>(((qc >> 1) - 1) & 1), 64);
           mbar_arrive_expect_tx(bar(BB_QDO + st), 2 * kChunkBytes);
           tma_load_3d(&tmQ, bar(BB_QDO + st), sQD_u + st * 2 * kChunkBytes, h * DH, qt * 128, b);
           tma_load_3d(&tmDO, bar(BB_QDO + st), sQD_u + st * 2 * kChunkBytes + kChunkBytes, h * DH, qt * 128, b);
-          if (qc >= 1) mbar_wait(bar(BB_OFREE), static_cast<uint32_t>((qc - 1) & 1));
+          if (qc >= 1) mbar_wait_backoff(bar(BB_OFREE), static_cast<uint32_t>((qc - 1) & 1), 64);
           mbar_arrive_expect_tx(bar(BB_O), kChunkBytes);
           tma_load_3d(&tmO, bar(BB_O), sO_u, h * DH, qt * 128, b);
         }
+        if (++qt == QT) { qt = 0; if (++kt == KT) { kt = 0; ++hl; if (++h == a.H) { h = 0; ++b; } } }
       }
     }
   } else if (warp == 9) {
@@ -348,149 +415,132 @@ attn_bwd_ws(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     if (lane == 0 && n > 0) {
       constexpr uint32_t idesc_t = umma_idesc_bf16(128, DH, true, true);     // dV, dK: A = P^T / dS^T (MN-major), B MN-major
       constexpr uint32_t idesc_dq = umma_idesc_bf16(128, DH, false, true);   // dQ: A = dS (K-major), B = K (MN-major)
-      // operands of iteration i
-      auto coords = [&](int i, int& hl, int& kt, int& qt) {
-        hl = i / per_head;
-        const int rem = i - hl * per_head;
-        kt = rem / QT;
-        qt = rem - kt * QT;
-      };
-      auto nkp_of = [&](int kt) { const int left = a.N - kt * 128; return left >= 128 ? 128 : ((left + 15) & ~15); };
-      // S(i) = Q K^T and dP(i) = dO V^T  (N = this key tile's padded key count)
-      auto wait_operands = [&](int i) {
-        int hl, kt, qt;
-        coords(i, hl, kt, qt);
-        const int kc = hl * KT + kt, qc = hl * QT + qt;
-        if (qt == 0) mbar_wait(bar(BB_KV + (kc & 1)), static_cast<uint32_t>((kc >> 1) & 1));
-        if (kt == 0) mbar_wait(bar(BB_QDO + (qc & 1)), static_cast<uint32_t>((qc >> 1) & 1));
+      const int nkp_last = ((a.N - (KT - 1) * 128) + 15) & ~15;              // padded key count of the last key tile
+      const uint32_t idesc_full = umma_idesc_bf16(128, 128, false, false), idesc_last = umma_idesc_bf16(128, nkp_last, false, false);
+      // descriptors of the fixed buffers
+      const uint64_t dPt = desc_mnmajor(sP_u, kChunkBytes), dDSt = desc_mnmajor(sDS_u, kChunkBytes), dDSk = desc_kmajor(sDS_u);
+      // stage-dependent operands: K-major and MN-major views of the same tiles (stage stride = 2 tiles)
+      const uint64_t dK0 = desc_kmajor(sKV_u), dKt0 = desc_mnmajor(sKV_u, 8192), dV0 = desc_kmajor(sKV_u + kChunkBytes);
+      const uint64_t dQ0 = desc_kmajor(sQD_u), dQt0 = desc_mnmajor(sQD_u, 8192);
+      const uint64_t dDO0 = desc_kmajor(sQD_u + kChunkBytes), dDOt0 = desc_mnmajor(sQD_u + kChunkBytes, 8192);
+      constexpr uint64_t kStage = (2 * kChunkBytes) >> 4;
+      // the coordinates of the iteration whose S / dP are issued next
+      int s_hl = 0, s_kt = 0, s_qt = 0;
+      auto issue_s_dp_wait = [&]() {               // operands of iteration (s_hl, s_kt, s_qt) have landed
+        const int kc = s_hl * KT + s_kt, qc = s_hl * QT + s_qt;
+        if (s_qt == 0) mbar_wait_backoff(bar(BB_KV + (kc & 1)), static_cast<uint32_t>((kc >> 1) & 1), 32);
+        if (s_kt == 0) mbar_wait_backoff(bar(BB_QDO + (qc & 1)), static_cast<uint32_t>((qc >> 1) & 1), 32);
         tc_fence_after();
       };
-      auto issue_s = [&](int i) {
-        int hl, kt, qt;
-        coords(i, hl, kt, qt);
-        const int kc = hl * KT + kt, qc = hl * QT + qt;
-        const uint32_t sK = sKV_u + (kc & 1) * 2 * kChunkBytes, sQ = sQD_u + (qc & 1) * 2 * kChunkBytes;
-        const uint32_t idesc = umma_idesc_bf16(128, nkp_of(kt), false, false);
+      auto issue_s = [&]() {                       // S = Q K^T (N = this key tile's padded key count)
+        const int kc = s_hl * KT + s_kt, qc = s_hl * QT + s_qt;
+        const uint64_t dQ = dQ0 + (qc & 1) * kStage, dK = dK0 + (kc & 1) * kStage;
+        const uint32_t idesc = (s_kt == KT - 1) ? idesc_last : idesc_full;
 #pragma unroll
-        for (int k = 0; k < DH / 16; ++k)
-          umma_bf16_ss(tmem_base + T_S, umma_smem_desc_sw128(sQ + k * 32, 16, 1024), umma_smem_desc_sw128(sK + k * 32, 16, 1024),
-                       idesc, k > 0 ? 1u : 0u);
+        for (int k = 0; k < DH / 16; ++k) umma_bf16_ss(tmem_base + T_S, dQ + 2 * k, dK + 2 * k, idesc, k > 0 ? 1u : 0u);
         umma_commit(bar(BB_S));
       };
-      auto issue_dp = [&](int i) {
-        int hl, kt, qt;
-        coords(i, hl, kt, qt);
-        const int kc = hl * KT + kt, qc = hl * QT + qt;
-        const uint32_t sV = sKV_u + (kc & 1) * 2 * kChunkBytes + kChunkBytes, sDO = sQD_u + (qc & 1) * 2 * kChunkBytes + kChunkBytes;
-        const uint32_t idesc = umma_idesc_bf16(128, nkp_of(kt), false, false);
+      auto issue_dp = [&]() {                      // dP = dO V^T
+        const int kc = s_hl * KT + s_kt, qc = s_hl * QT + s_qt;
+        const uint64_t dDO = dDO0 + (qc & 1) * kStage, dV = dV0 + (kc & 1) * kStage;
+        const uint32_t idesc = (s_kt == KT - 1) ? idesc_last : idesc_full;
 #pragma unroll
-        for (int k = 0; k < DH / 16; ++k)
-          umma_bf16_ss(tmem_base + T_DP, umma_smem_desc_sw128(sDO + k * 32, 16, 1024), umma_smem_desc_sw128(sV + k * 32, 16, 1024),
-                       idesc, k > 0 ? 1u : 0u);
+        for (int k = 0; k < DH / 16; ++k) umma_bf16_ss(tmem_base + T_DP, dDO + 2 * k, dV + 2 * k, idesc, k > 0 ? 1u : 0u);
         umma_commit(bar(BB_DP));
       };
-      wait_operands(0);
-      issue_s(0);
-      issue_dp(0);
+      auto advance_s = [&]() { if (++s_qt == QT) { s_qt = 0; if (++s_kt == KT) { s_kt = 0; ++s_hl; } } };
+      issue_s_dp_wait();
+      issue_s();
+      issue_dp();
+      int hl = 0, kt = 0, qt = 0;
       for (int i = 0; i < n; ++i) {
-        int hl, kt, qt;
-        coords(i, hl, kt, qt);
         const int kc = hl * KT + kt, qc = hl * QT + qt;
         const uint32_t ph = static_cast<uint32_t>(i & 1);
-        const uint32_t sK = sKV_u + (kc & 1) * 2 * kChunkBytes;
-        const uint32_t sQ = sQD_u + (qc & 1) * 2 * kChunkBytes, sDO = sQ + kChunkBytes;
-        const int nkp = nkp_of(kt);
+        const uint64_t dKt = dKt0 + (kc & 1) * kStage, dQt = dQt0 + (qc & 1) * kStage, dDOt = dDOt0 + (qc & 1) * kStage;
+        const int nks = (kt == KT - 1 ? nkp_last : 128) >> 4;
+        advance_s();                               // (s_*) = iteration i + 1
         // ---- P(i) is in shared memory (and S has been read): S(i+1), then dV += P^T dO
-        mbar_wait(bar(BB_P), ph);
+        mbar_wait_backoff(bar(BB_P), ph, 20);
         tc_fence_after();
-        if (i + 1 < n) { wait_operands(i + 1); issue_s(i + 1); }
-        if (qt == 0 && kc > 0) { mbar_wait(bar(BB_DVDR), static_cast<uint32_t>((kc - 1) & 1)); tc_fence_after(); }
+        if (i + 1 < n) { issue_s_dp_wait(); issue_s(); }
+        if (qt == 0 && kc > 0) { mbar_wait_backoff(bar(BB_DVDR), static_cast<uint32_t>((kc - 1) & 1), 20); tc_fence_after(); }
 #pragma unroll
         for (int k = 0; k < 8; ++k)        // K = 128 query rows; A = P^T (MN-major image of sP), B = dO (MN-major)
-          umma_bf16_ss(tmem_base + T_DV, umma_smem_desc_sw128(sP_u + k * 2048, kChunkBytes, 1024),
-                       umma_smem_desc_sw128(sDO + k * 2048, 8192, 1024), idesc_t, (qt > 0 || k > 0) ? 1u : 0u);
+          umma_bf16_ss(tmem_base + T_DV, dPt + 128 * k, dDOt + 128 * k, idesc_t, (qt > 0 || k > 0) ? 1u : 0u);
         umma_commit(bar(BB_PFREE));
         // ---- dS(i) is in shared memory (and dP has been read): dP(i+1), then dK += dS^T Q, dQ += dS K
-        mbar_wait(bar(BB_DS), ph);
+        mbar_wait_backoff(bar(BB_DS), ph, 20);
         tc_fence_after();
-        if (i + 1 < n) issue_dp(i + 1);
-        if (qt == 0 && kc > 0) { mbar_wait(bar(BB_DKDR), static_cast<uint32_t>((kc - 1) & 1)); tc_fence_after(); }
+        if (i + 1 < n) issue_dp();
+        if (qt == 0 && kc > 0) { mbar_wait_backoff(bar(BB_DKDR), static_cast<uint32_t>((kc - 1) & 1), 20); tc_fence_after(); }
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-          umma_bf16_ss(tmem_base + T_DK, umma_smem_desc_sw128(sDS_u + k * 2048, kChunkBytes, 1024),
-                       umma_smem_desc_sw128(sQ + k * 2048, 8192, 1024), idesc_t, (qt > 0 || k > 0) ? 1u : 0u);
-        if (kt == 0 && hl > 0) { mbar_wait(bar(BB_DQDR + qt), static_cast<uint32_t>((hl - 1) & 1)); tc_fence_after(); }
-        const int nks = nkp >> 4;
+          umma_bf16_ss(tmem_base + T_DK, dDSt + 128 * k, dQt + 128 * k, idesc_t, (qt > 0 || k > 0) ? 1u : 0u);
+        if (kt == 0 && hl > 0) { mbar_wait_backoff(bar(BB_DQDR + qt), static_cast<uint32_t>((hl - 1) & 1), 20); tc_fence_after(); }
         for (int t16 = 0; t16 < nks; ++t16)   // K = this tile's keys; A = dS (K-major over keys), B = K (MN-major: keys x dh)
           umma_bf16_ss(tmem_base + T_DQ + static_cast<uint32_t>(qt * 64),
-                       umma_smem_desc_sw128(sDS_u + (t16 >> 2) * kChunkBytes + (t16 & 3) * 32, 16, 1024),
-                       umma_smem_desc_sw128(sK + t16 * 2048, 8192, 1024), idesc_dq, (kt > 0 || t16 > 0) ? 1u : 0u);
+                       dDSk + static_cast<uint64_t>((t16 >> 2) * (kChunkBytes >> 4) + (t16 & 3) * 2), dKt + static_cast<uint64_t>(t16 * 128),
+                       idesc_dq, (kt > 0 || t16 > 0) ? 1u : 0u);
         umma_commit(bar(BB_DSFREE));
         if (qt == QT - 1) umma_commit(bar(BB_KVFREE + (kc & 1)));   // last user of this K, V stage
         if (kt == KT - 1) umma_commit(bar(BB_QFREE + (qc & 1)));    // last user of this Q, dO stage
+        if (++qt == QT) { qt = 0; if (++kt == KT) { kt = 0; ++hl; } }
       }
     }
   } else {
     // =============================== CUDA-core warps: P, dS, drains ===============================
-    const int half = warp >> 2;                    // two threads per query row; `half` picks the 16-key units
+    const int half = warp >> 2;                    // two threads per query row; `half` picks the keys
     const int r = (warp & 3) * 32 + lane;          // query row within the tile == TMEM lane
+    const int rx = r & 7;
     const bool elected = (tid == 0);
     const uint32_t trow = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-    float lse2_q[2] = {0.f, 0.f}, d_q[2] = {0.f, 0.f};   // per query tile: LSE * log2(e) and D_i of this thread's row
+    const uint32_t row_off = static_cast<uint32_t>(r * 128);
+    float lse2_q0 = 0.f, lse2_q1 = 0.f, d_q0 = 0.f, d_q1 = 0.f;   // per query tile: LSE * log2(e) and D_i of this thread's row
     // accumulators waiting to be drained: (image, head) and tile they belong to
-    bool pend_dv = false, pend_dk = false, pend_dq[2] = {false, false};
-    int pend_kv_b = 0, pend_kv_h = 0, pend_kv_kt = 0, pend_dq_b[2] = {0, 0}, pend_dq_h[2] = {0, 0};
+    bool pend_dv = false, pend_dk = false, pend_dq0 = false, pend_dq1 = false;
+    int pend_kv_b = 0, pend_kv_h = 0, pend_kv_kt = 0, pend_dq0_b = 0, pend_dq0_h = 0, pend_dq1_b = 0, pend_dq1_h = 0;
+    const uint64_t sc2 = pk2(a.scale_log2);
 
-    // one accumulator tile: TMEM -> registers (the accumulator is released) -> bf16 staging tile -> TMA store
-    auto drain = [&](uint32_t tcol, int drained_bar, float scale, const CUtensorMap* tm, int row0, int b, int h) {
-      uint32_t v[32];
-      tmem_ld_32x32b_x32(trow + tcol + static_cast<uint32_t>(half * 32), v);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(bar(drained_bar));
-      if (elected) bulk_wait_read<0>();            // the previous store has finished reading the staging tile
-      named_bar_sync(1, 256);
-      stage_row32_bf16(sStage_u, r, half, v, scale);
-      fence_proxy_async_smem();
-      named_bar_sync(1, 256);
-      if (elected) {
-        tma_store_3d(tm, sStage_u, h * DH, row0, b);
-        bulk_commit();
-      }
-    };
     auto drain_dv = [&]() {
-      drain(T_DV, BB_DVDR, 1.0f, &tmDV, pend_kv_kt * 128, pend_kv_b, pend_kv_h);
+      drain_tile(trow + T_DV, bar(BB_DVDR), 1.0f, &tmDV, sStage_u, r, half, elected, pend_kv_h * DH, pend_kv_kt * 128, pend_kv_b);
       pend_dv = false;
     };
     auto drain_dk = [&]() {
-      drain(T_DK, BB_DKDR, a.scale, &tmDK, pend_kv_kt * 128, pend_kv_b, pend_kv_h);
+      drain_tile(trow + T_DK, bar(BB_DKDR), a.scale, &tmDK, sStage_u, r, half, elected, pend_kv_h * DH, pend_kv_kt * 128, pend_kv_b);
       pend_dk = false;
     };
-    auto drain_dq = [&](int q) {
-      drain(T_DQ + static_cast<uint32_t>(q * 64), BB_DQDR + q, a.scale, &tmDQ, q * 128, pend_dq_b[q], pend_dq_h[q]);
-      pend_dq[q] = false;
+    auto drain_dq0 = [&]() {
+      drain_tile(trow + T_DQ, bar(BB_DQDR), a.scale, &tmDQ, sStage_u, r, half, elected, pend_dq0_h * DH, 0, pend_dq0_b);
+      pend_dq0 = false;
+    };
+    auto drain_dq1 = [&]() {
+      drain_tile(trow + T_DQ + 64u, bar(BB_DQDR + 1), a.scale, &tmDQ, sStage_u, r, half, elected, pend_dq1_h * DH, 128, pend_dq1_b);
+      pend_dq1 = false;
     };
 
+    int hl = 0, kt = 0, qt = 0, b = h_begin / a.H, h = h_begin - b * a.H;
+    float lse_pref = INFINITY;                     // LSE of this thread's row for the next iteration that starts a query tile
+    if (n > 0 && r < a.N) lse_pref = a.lse[(static_cast<long long>(b) * a.H + h) * a.N + r];
     for (int i = 0; i < n; ++i) {
-      const int hl = i / per_head, rem = i - hl * per_head, kt = rem / QT, qt = rem - kt * QT;
-      const int head = h_begin + hl, b = head / a.H, h = head - b * a.H;
       const int qc = hl * QT + qt;
       const uint32_t ph = static_cast<uint32_t>(i & 1);
-      const int nk_valid = min(128, a.N - kt * 128);          // keys of this tile that exist
-      const int nunits = (nk_valid + 15) >> 4;                // 16-key units carrying at least one key
-      const int umid = (nunits + 1) >> 1;
-      const int ub = half ? umid : 0, ue = half ? nunits : umid;   // this thread's units (<= 4)
+      // coordinates of the next iteration; its LSE is requested now if it starts a query tile
+      int nqt = qt + 1, nkt = kt, nhl = hl, nb = b, nh = h;
+      if (nqt == QT) { nqt = 0; if (++nkt == KT) { nkt = 0; ++nhl; if (++nh == a.H) { nh = 0; ++nb; } } }
+      float lse_next = INFINITY;
+      if (i + 1 < n && nkt == 0) {
+        const int row = nqt * 128 + r;
+        if (row < a.N) lse_next = a.lse[(static_cast<long long>(nb) * a.H + nh) * a.N + row];
+      }
       if (kt == 0) {
-        // D_i = rowsum(dO * O) of this query tile from the swizzled tiles; LSE of this thread's row
-        const int row = qt * 128 + r;
-        const float lse = (row < a.N) ? a.lse[(static_cast<long long>(b) * a.H + h) * a.N + row] : INFINITY;
+        // D_i = rowsum(dO * O) of this query tile from the swizzled tiles
         mbar_wait(bar(BB_QDO + (qc & 1)), static_cast<uint32_t>((qc >> 1) & 1));
         mbar_wait(bar(BB_O), static_cast<uint32_t>(qc & 1));
         const uint32_t sDO = sQD_u + (qc & 1) * 2 * kChunkBytes + kChunkBytes;
         float part = 0.f;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const uint32_t off = swz_unit(r, half * 4 + u);
+          const uint32_t off = row_off + static_cast<uint32_t>(((half * 4 + u) ^ rx) << 4);
           part += dot8_bf16(ld_shared_v4(sO_u + off), ld_shared_v4(sDO + off));
         }
         red[half * 128 + r] = part;
@@ -498,40 +548,62 @@ attn_bwd_ws(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         const float di = red[r] + red[128 + r];
         mbar_arrive(bar(BB_OFREE));                // the O tile may be replaced
         named_bar_sync(1, 256);                    // red[] may be rewritten by the next query tile
-        if (qt == 0) { d_q[0] = di; lse2_q[0] = lse * kLog2e; } else { d_q[1] = di; lse2_q[1] = lse * kLog2e; }
+        if (qt == 0) { d_q0 = di; lse2_q0 = lse_pref * kLog2e; } else { d_q1 = di; lse2_q1 = lse_pref * kLog2e; }
       }
-      const float lse2 = qt == 0 ? lse2_q[0] : lse2_q[1];
-      const float Di = qt == 0 ? d_q[0] : d_q[1];
-      // ---- P = exp2(S*c - LSE*log2e) for this thread's units -> bf16 -> sP (rows >= N: LSE = +inf -> 0; keys >= N -> 0)
+      if (nkt == 0) lse_pref = lse_next;
+      const float lse2 = qt == 0 ? lse2_q0 : lse2_q1;
+      const float Di = qt == 0 ? d_q0 : d_q1;
+      const int nk_valid = min(128, a.N - kt * 128);          // keys of this tile that exist
       mbar_wait(bar(BB_S), ph);
       if (i >= 1) mbar_wait(bar(BB_PFREE), static_cast<uint32_t>((i - 1) & 1));   // dV(i-1) has read the previous P
       tc_fence_after();
-      uint32_t pk[4][8];
+      const bool full = (nk_valid == 128);
+      const int nunits = (nk_valid + 15) >> 4;                // partial tile: 16-key units carrying at least one key,
+      const int umid = (nunits + 1) >> 1;                     // split between the two halves of a row
+      const int ub = half ? umid : 0, ue = half ? nunits : umid;
+      const uint64_t nl2 = pk2(-lse2);
+      uint32_t p[64];                                         // full tile: P of this thread's 64 keys (fp32), kept for dS
+      // ---- P = exp2(S*c - LSE*log2e) -> bf16 -> sP  (rows >= N: LSE = +inf -> 0; padding keys -> 0)
+      if (full) {      // this thread owns the 64 keys of chunk `half`
+        tmem_ld_32x32b_x32(trow + T_S + static_cast<uint32_t>(half * 64), reinterpret_cast<uint32_t(&)[32]>(p[0]));
+        tmem_ld_32x32b_x32(trow + T_S + static_cast<uint32_t>(half * 64 + 32), reinterpret_cast<uint32_t(&)[32]>(p[32]));
+        tmem_ld_wait();
+        const uint32_t prow = sP_u + static_cast<uint32_t>(half * kChunkBytes) + row_off;
 #pragma unroll
-      for (int ul = 0; ul < 4; ++ul) {
-        const int u = ub + ul;
-        if (u < ue) {
+        for (int u = 0; u < 8; ++u) {
+          uint32_t w[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float x0, x1;
+            upk2(fma2(pk2(__uint_as_float(p[8 * u + 2 * j]), __uint_as_float(p[8 * u + 2 * j + 1])), sc2, nl2), x0, x1);
+            const float e0 = ex2_approx(x0), e1 = ex2_approx(x1);
+            p[8 * u + 2 * j] = __float_as_uint(e0);
+            p[8 * u + 2 * j + 1] = __float_as_uint(e1);
+            w[j] = pack_bf16x2(e0, e1);
+          }
+          st_shared_v4(prow + static_cast<uint32_t>((u ^ rx) << 4), w[0], w[1], w[2], w[3]);
+        }
+      } else {
+#pragma unroll 1
+        for (int u = ub; u < ue; ++u) {
           uint32_t v[16];
           tmem_ld_32x32b_x16(trow + T_S + static_cast<uint32_t>(u * 16), v);
           tmem_ld_wait();
           const int c0 = u * 16;
-          const bool interior = (c0 + 16 <= nk_valid);
-          const uint64_t sc2 = pk2(a.scale_log2), nl2 = pk2(-lse2);
+          uint32_t w[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float x0, x1;
             upk2(fma2(pk2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), sc2, nl2), x0, x1);
             float e0 = ex2_approx(x0), e1 = ex2_approx(x1);
-            if (!interior) {
-              e0 = (c0 + 2 * j < nk_valid) ? e0 : 0.f;
-              e1 = (c0 + 2 * j + 1 < nk_valid) ? e1 : 0.f;
-            }
-            pk[ul][j] = pack_bf16x2(e0, e1);
+            e0 = (c0 + 2 * j < nk_valid) ? e0 : 0.f;
+            e1 = (c0 + 2 * j + 1 < nk_valid) ? e1 : 0.f;
+            w[j] = pack_bf16x2(e0, e1);
           }
-          const uint32_t base = sP_u + (c0 >> 6) * kChunkBytes;
+          const uint32_t prow = sP_u + static_cast<uint32_t>((c0 >> 6) * kChunkBytes) + row_off;
           const int u8 = (c0 & 63) >> 3;
-          st_shared_v4(base + swz_unit(r, u8), pk[ul][0], pk[ul][1], pk[ul][2], pk[ul][3]);
-          st_shared_v4(base + swz_unit(r, u8 + 1), pk[ul][4], pk[ul][5], pk[ul][6], pk[ul][7]);
+          st_shared_v4(prow + static_cast<uint32_t>((u8 ^ rx) << 4), w[0], w[1], w[2], w[3]);
+          st_shared_v4(prow + static_cast<uint32_t>(((u8 + 1) ^ rx) << 4), w[4], w[5], w[6], w[7]);
         }
       }
       fence_proxy_async_smem();
@@ -540,29 +612,49 @@ attn_bwd_ws(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       // ---- slot after P: the MMAs of iteration i-1 have retired by now; drain what they completed
       if (i >= 1) { mbar_wait(bar(BB_DSFREE), static_cast<uint32_t>((i - 1) & 1)); tc_fence_after(); }
       if (pend_dv) drain_dv();
-      else if (pend_dq[qt ^ 1]) drain_dq(qt ^ 1);
+      else if (qt == 1 && pend_dq0) drain_dq0();
+      else if (qt == 0 && pend_dq1) drain_dq1();
       // ---- dS / c = P * (dP - D) -> bf16 -> sdS  (the softmax scale c is applied when dQ / dK are drained)
       mbar_wait(bar(BB_DP), ph);
       tc_fence_after();
+      if (full) {
+        uint32_t d[64];
+        tmem_ld_32x32b_x32(trow + T_DP + static_cast<uint32_t>(half * 64), reinterpret_cast<uint32_t(&)[32]>(d[0]));
+        tmem_ld_32x32b_x32(trow + T_DP + static_cast<uint32_t>(half * 64 + 32), reinterpret_cast<uint32_t(&)[32]>(d[32]));
+        tmem_ld_wait();
+        const uint64_t nd2 = pk2(-Di);
+        const uint32_t drow = sDS_u + static_cast<uint32_t>(half * kChunkBytes) + row_off;
 #pragma unroll
-      for (int ul = 0; ul < 4; ++ul) {
-        const int u = ub + ul;
-        if (u < ue) {
+        for (int u = 0; u < 8; ++u) {
+          uint32_t w[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint64_t t2 = add2(pk2(__uint_as_float(d[8 * u + 2 * j]), __uint_as_float(d[8 * u + 2 * j + 1])), nd2);
+            float y0, y1;
+            upk2(mul2(pk2(__uint_as_float(p[8 * u + 2 * j]), __uint_as_float(p[8 * u + 2 * j + 1])), t2), y0, y1);
+            w[j] = pack_bf16x2(y0, y1);
+          }
+          st_shared_v4(drow + static_cast<uint32_t>((u ^ rx) << 4), w[0], w[1], w[2], w[3]);
+        }
+      } else {
+#pragma unroll 1
+        for (int u = ub; u < ue; ++u) {
           uint32_t v[16];
           tmem_ld_32x32b_x16(trow + T_DP + static_cast<uint32_t>(u * 16), v);
-          tmem_ld_wait();
-          uint32_t ds[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float d0 = bf16_lo(pk[ul][j]) * (__uint_as_float(v[2 * j]) - Di);
-            const float d1 = bf16_hi(pk[ul][j]) * (__uint_as_float(v[2 * j + 1]) - Di);
-            ds[j] = pack_bf16x2(d0, d1);
-          }
           const int c0 = u * 16;
-          const uint32_t base = sDS_u + (c0 >> 6) * kChunkBytes;
+          const uint32_t prow = sP_u + static_cast<uint32_t>((c0 >> 6) * kChunkBytes) + row_off;
+          const uint32_t drow = sDS_u + static_cast<uint32_t>((c0 >> 6) * kChunkBytes) + row_off;
           const int u8 = (c0 & 63) >> 3;
-          st_shared_v4(base + swz_unit(r, u8), ds[0], ds[1], ds[2], ds[3]);
-          st_shared_v4(base + swz_unit(r, u8 + 1), ds[4], ds[5], ds[6], ds[7]);
+          const uint4 pa = ld_shared_v4(prow + static_cast<uint32_t>((u8 ^ rx) << 4));         // this thread's own P (bf16)
+          const uint4 pb = ld_shared_v4(prow + static_cast<uint32_t>(((u8 + 1) ^ rx) << 4));
+          tmem_ld_wait();
+          const uint32_t pp[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+          uint32_t w[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            w[j] = pack_bf16x2(bf16_lo(pp[j]) * (__uint_as_float(v[2 * j]) - Di), bf16_hi(pp[j]) * (__uint_as_float(v[2 * j + 1]) - Di));
+          st_shared_v4(drow + static_cast<uint32_t>((u8 ^ rx) << 4), w[0], w[1], w[2], w[3]);
+          st_shared_v4(drow + static_cast<uint32_t>(((u8 + 1) ^ rx) << 4), w[4], w[5], w[6], w[7]);
         }
       }
       fence_proxy_async_smem();
@@ -570,21 +662,23 @@ attn_bwd_ws(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       mbar_arrive(bar(BB_DS));
       // ---- slot after dS
       if (pend_dk) drain_dk();
-      if (pend_dq[qt]) drain_dq(qt);
+      if (qt == 0 && pend_dq0) drain_dq0();
+      if (qt == 1 && pend_dq1) drain_dq1();
       // what this iteration completes (drained one slot later, once its MMAs have retired)
       if (qt == QT - 1) { pend_dv = pend_dk = true; pend_kv_b = b; pend_kv_h = h; pend_kv_kt = kt; }
       if (kt == KT - 1) {
-        if (qt == 0) { pend_dq[0] = true; pend_dq_b[0] = b; pend_dq_h[0] = h; }
-        else { pend_dq[1] = true; pend_dq_b[1] = b; pend_dq_h[1] = h; }
+        if (qt == 0) { pend_dq0 = true; pend_dq0_b = b; pend_dq0_h = h; }
+        else { pend_dq1 = true; pend_dq1_b = b; pend_dq1_h = h; }
       }
+      qt = nqt; kt = nkt; hl = nhl; b = nb; h = nh;
     }
     if (n > 0) {
       mbar_wait(bar(BB_DSFREE), static_cast<uint32_t>((n - 1) & 1));
       tc_fence_after();
       if (pend_dv) drain_dv();
       if (pend_dk) drain_dk();
-      if (pend_dq[0]) drain_dq(0);
-      if (pend_dq[1]) drain_dq(1);
+      if (pend_dq0) drain_dq0();
+      if (pend_dq1) drain_dq1();
     }
     if (elected) bulk_wait_all();                  // shared memory must outlive the reads of the last store
   }
@@ -604,6 +698,13 @@ int head_map(CUtensorMap* m, const void* base, int H, int N, int B, long long ro
   return vitb_make_tmap_nd_bf16(m, base, 3, dims, str, box);
 }
 
+int fwd_smem_bytes(int N) {
+  const int NK = (N + 15) & ~15;
+  const int kv_bytes = NK * 128, pchunks = (NK + 63) / 64;
+  // K | V | 2 query tiles | 2 P images | barriers + TMEM slot | row max / sum exchange
+  return 2 * kv_bytes + 2 * kChunkBytes + 2 * pchunks * kChunkBytes + 8 * (FB_COUNT + 2) + 2 * 512 * 4;
+}
+
 int check_ws(const vitb_attn_params* p, const char* who) {
   VITB_REQUIRE(p && p->struct_bytes == (int)sizeof(vitb_attn_params), VITB_ERR_BAD_ARG, "%s: ABI mismatch", who);
   VITB_REQUIRE(p->dtype == VITB_BF16, VITB_ERR_UNSUPPORTED_SHAPE, "%s: bf16 only", who);
@@ -617,8 +718,12 @@ int check_ws(const vitb_attn_params* p, const char* who) {
 
 }  // namespace
 
-extern "C" int vitb_attn_ws_supported(int head_dim, int Nq, int Nk) {
-  return head_dim == DH && Nq == Nk && Nk >= 1 && Nk <= 256;
+/* which: 0 = forward, 1 = backward.  The forward keeps two P images next to K, V and the query tiles: more than 240
+ * keys do not fit the 227 KiB of shared memory (such shapes stay on vitb_attn_fwd_tc). */
+extern "C" int vitb_attn_ws_supported(int which, int head_dim, int Nq, int Nk) {
+  if (!(head_dim == DH && Nq == Nk && Nk >= 1 && Nk <= 256)) return 0;
+  if (which == 0) return fwd_smem_bytes(Nk) <= 227 * 1024;
+  return 1;
 }
 
 extern "C" int vitb_attn_fwd_ws(const vitb_attn_params* p, void* stream_) {
@@ -628,6 +733,8 @@ extern "C" int vitb_attn_fwd_ws(const vitb_attn_params* p, void* stream_) {
   if (st != VITB_OK) return st;
   if (p->B == 0) return VITB_OK;
   const int N = p->Nk, NK = (N + 15) & ~15;
+  const int smem = fwd_smem_bytes(N);
+  VITB_REQUIRE(smem <= 227 * 1024, VITB_ERR_UNSUPPORTED_SHAPE, "attn_fwd_ws: %d keys need %d B of shared memory", N, smem);
   CUtensorMap tq, tk, tv, to;
   if ((st = head_map(&tq, p->q, p->H, N, p->B, p->q_row_stride, p->q_batch_stride, 128)) != VITB_OK) return st;
   if ((st = head_map(&tk, p->k, p->H, N, p->B, p->k_row_stride, p->k_batch_stride, NK)) != VITB_OK) return st;
@@ -641,14 +748,10 @@ extern "C" int vitb_attn_fwd_ws(const vitb_attn_params* p, void* stream_) {
   a.scale = 1.0f / sqrtf((float)DH);
   a.scale_log2 = a.scale * kLog2e;
   a.lse = p->lse;
-  const int kv_bytes = NK * 128, pchunks = (NK + 63) / 64;
-  // K | V | 2 query tiles | 2 P images | barriers + TMEM slot | alignment slack
-  const int smem = 2 * kv_bytes + 2 * kChunkBytes + 2 * pchunks * kChunkBytes + 256 + 1024;
-  VITB_REQUIRE(smem <= 227 * 1024, VITB_ERR_UNSUPPORTED_SHAPE, "attn_fwd_ws: %d B of shared memory", smem);
   VITB_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int sms = vitb_num_sms();
   const int grid = a.total < sms ? a.total : sms;
-  VITB_CUDA_CHECK(vitb_launch(attn_fwd_ws, dim3(grid), dim3(kWsThreads), smem, reinterpret_cast<cudaStream_t>(stream_), tq, tk,
+  VITB_CUDA_CHECK(vitb_launch(attn_fwd_ws, dim3(grid), dim3(kFwdThreads), smem, reinterpret_cast<cudaStream_t>(stream_), tq, tk,
                               tv, to, a));
   VITB_LAUNCH_CHECK("attn_fwd_ws");
   return VITB_OK;
@@ -683,13 +786,13 @@ extern "C" int vitb_attn_bwd_ws(const vitb_attn_params* p, void* stream_) {
   a.scale = 1.0f / sqrtf((float)DH);
   a.scale_log2 = a.scale * kLog2e;
   a.lse = p->lse;
-  // 14 tiles of 16 KiB | barriers + TMEM slot + D_i partials | alignment slack
-  const int smem = 14 * kChunkBytes + 8 * (BB_COUNT + 2) + 2 * 128 * 4 + 1024;
+  // 14 tiles of 16 KiB | barriers + TMEM slot | D_i partials
+  const int smem = 14 * kChunkBytes + 8 * (BB_COUNT + 2) + 2 * 128 * 4;
   VITB_REQUIRE(smem <= 227 * 1024, VITB_ERR_UNSUPPORTED_SHAPE, "attn_bwd_ws: %d B of shared memory", smem);
   VITB_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int sms = vitb_num_sms();
   const int grid = a.total < sms ? a.total : sms;
-  VITB_CUDA_CHECK(vitb_launch(attn_bwd_ws, dim3(grid), dim3(kWsThreads), smem, reinterpret_cast<cudaStream_t>(stream_), tq, tk,
+  VITB_CUDA_CHECK(vitb_launch(attn_bwd_ws, dim3(grid), dim3(kBwdThreads), smem, reinterpret_cast<cudaStream_t>(stream_), tq, tk,
                               tv, tdo, to, tdq, tdk, tdv, a));
   VITB_LAUNCH_CHECK("attn_bwd_ws");
   return VITB_OK;

@@ -305,9 +305,12 @@ ce_kernel(const float* __restrict__ logits, const long long* __restrict__ labels
 // refreshing the bf16 GEMM shadow (and its lo half in fp32 parity mode) in the same pass.
 __global__ void __launch_bounds__(kThreads)
 sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, long long n,
-           float lr_host, const float* __restrict__ lr_dev, float momentum, float dampening, float wd, int nesterov,
+           float lr_host, const float* __restrict__ hyper_dev, float momentum, float dampening, float wd, int nesterov,
            int first_step, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
-  const float lr = lr_dev ? *lr_dev : lr_host;   // device-resident lr keeps a captured CUDA graph schedulable
+  // device-resident hyper-parameters {lr, momentum, dampening, weight_decay} keep a captured CUDA graph following the
+  // LR scheduler (OneCycleLR cycles the momentum as well as the learning rate)
+  const float lr = hyper_dev ? hyper_dev[0] : lr_host;
+  if (hyper_dev) { momentum = hyper_dev[1]; dampening = hyper_dev[2]; wd = hyper_dev[3]; }
   const long long n4 = n >> 2;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -349,11 +352,13 @@ sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict
 // carries the clip_grad_norm_ coefficient (res-vit/train.py:65) so no host sync is needed.
 __global__ void __launch_bounds__(kThreads)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-             float* __restrict__ v, long long n, float lr_host, const float* __restrict__ lr_dev, float b1, float b2,
+             float* __restrict__ v, long long n, float lr_host, const float* __restrict__ hyper_dev, float b1, float b2,
              float eps, float wd, int step_host, const int* __restrict__ step_dev,
              const float* __restrict__ grad_scale_dev, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
-  // lr and the step counter may live on the device so that a captured CUDA graph keeps following them
-  const float lr = lr_dev ? *lr_dev : lr_host;
+  // {lr, beta1, beta2, weight_decay} and the step counter may live on the device so that a captured CUDA graph keeps
+  // following the scheduler (OneCycleLR cycles beta1)
+  const float lr = hyper_dev ? hyper_dev[0] : lr_host;
+  if (hyper_dev) { b1 = hyper_dev[1]; b2 = hyper_dev[2]; wd = hyper_dev[3]; }
   const float stepf = static_cast<float>(step_dev ? *step_dev : step_host);
   const float bc1 = 1.f - powf(b1, stepf), bc2 = 1.f - powf(b2, stepf);
   const float gs = grad_scale_dev ? *grad_scale_dev : 1.f;
@@ -543,7 +548,7 @@ int vitb_cross_entropy(const float* logits, const int64_t* labels, int B, int C,
   return VITB_OK;
 }
 
-int vitb_sgd_momentum(float* p, const float* g, float* m, int64_t n, float lr, const float* lr_dev, float momentum,
+int vitb_sgd_momentum(float* p, const float* g, float* m, int64_t n, float lr, const float* hyper_dev, float momentum,
                       float dampening, float weight_decay, int nesterov, int first_step, void* shadow_hi,
                       void* shadow_lo, void* stream_) {
   int st = vitb_check_device();
@@ -552,13 +557,13 @@ int vitb_sgd_momentum(float* p, const float* g, float* m, int64_t n, float lr, c
   VITB_REQUIRE(p && g && n > 0 && n % 4 == 0, VITB_ERR_UNSUPPORTED_SHAPE, "sgd: n=%lld must be a multiple of 4",
                (long long)n);
   sgd_kernel<<<grid_for(n / 4), kThreads, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
-      p, g, m, n, lr, lr_dev, momentum, dampening, weight_decay, nesterov, first_step,
+      p, g, m, n, lr, hyper_dev, momentum, dampening, weight_decay, nesterov, first_step,
       reinterpret_cast<__nv_bfloat16*>(shadow_hi), reinterpret_cast<__nv_bfloat16*>(shadow_lo));
   VITB_LAUNCH_CHECK("sgd_kernel");
   return VITB_OK;
 }
 
-int vitb_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, const float* lr_dev, float beta1,
+int vitb_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, const float* hyper_dev, float beta1,
                float beta2, float eps, float weight_decay, int step, const int* step_dev, const float* grad_scale_dev,
                void* shadow_hi, void* shadow_lo, void* stream_) {
   int st = vitb_check_device();
@@ -566,7 +571,7 @@ int vitb_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr
   if (n == 0) return VITB_OK;
   VITB_REQUIRE(p && g && m && v && n > 0 && (step >= 1 || step_dev), VITB_ERR_BAD_ARG, "adamw: bad args");
   adamw_kernel<<<grid_for(n), kThreads, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
-      p, g, m, v, n, lr, lr_dev, beta1, beta2, eps, weight_decay, step, step_dev, grad_scale_dev,
+      p, g, m, v, n, lr, hyper_dev, beta1, beta2, eps, weight_decay, step, step_dev, grad_scale_dev,
       reinterpret_cast<__nv_bfloat16*>(shadow_hi), reinterpret_cast<__nv_bfloat16*>(shadow_lo));
   VITB_LAUNCH_CHECK("adamw_kernel");
   return VITB_OK;

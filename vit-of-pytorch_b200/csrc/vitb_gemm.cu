@@ -94,6 +94,8 @@ struct GemmDev {
   int packed_epi;    // GELU + GELU' epilogue on packed fp32 pairs with the bias staged in shared memory (VITB_EPI_PACKED)
   int rowmul;        // VITB_EPI_MUL_AUX in the TMEM register layout: aux rows prefetched a chunk ahead, TMA stores (VITB_EPI_ROWMUL)
   int rowres;        // fp32 output + fp32 residual in the register layout, 32 x 16 fp32 TMA-store tiles (VITB_EPI_ROWRES, experimental)
+  int group_cols;    // Ng of a column-grouped B (merged q|k|v): tile column n0 -> group n0 / Ng; 0 = one group
+  long long d_gs;    // distance (elements) between the groups of a grouped fp32 accumulate output; 0 = contiguous D
 };
 
 struct TileCoord {
@@ -264,7 +266,7 @@ __device__ __forceinline__ void side_fetch(const GemmDev& p, int lane, int row_b
 // the epilogue cannot hide HBM latency by occupancy (round-1 ncu: GELU' GEMM at 31 % issue-active, 2.3 TB/s).
 template <bool OUT_BF16, int EPI, int RES, bool ACC, bool FULL>
 __device__ __forceinline__ void epi_vec_body(const GemmDev& p, uint32_t stg, int lane, int row_base, int col0,
-                                             bool lead_split, uint4 (&raw)[8], int next_col0) {
+                                             bool lead_split, uint4 (&raw)[8], int next_col0, long long d_off) {
   using S = SideOf<OUT_BF16, EPI, RES>;
   const int rsub = lane >> 3;
   const int c4 = (lane & 7) * 4;
@@ -283,7 +285,7 @@ __device__ __forceinline__ void epi_vec_body(const GemmDev& p, uint32_t stg, int
     spn = reinterpret_cast<const char*>(S::base(p)) + (r0 * lds + (next_col0 + c4)) * S::ESIZE;
     sstep = 4 * lds * S::ESIZE;
   }
-  char* dp = reinterpret_cast<char*>(p.D) + (r0 * p.ldd + col) * (OUT_BF16 ? 2 : 4);
+  char* dp = reinterpret_cast<char*>(p.D) + (r0 * p.ldd + col + d_off) * (OUT_BF16 ? 2 : 4);   // d_off: grouped output
   const long long dstep = 4 * p.ldd * (OUT_BF16 ? 2 : 4);
   char* d2p = nullptr;
   long long d2step = 0;
@@ -368,11 +370,11 @@ __device__ __forceinline__ void epi_vec_body(const GemmDev& p, uint32_t stg, int
 
 template <bool OUT_BF16, int EPI, int RES, bool ACC>
 __device__ __forceinline__ void epi_vec(const GemmDev& p, uint32_t stg, int lane, int row_base, int col0,
-                                        bool lead_split, uint4 (&raw)[8], int next_col0) {
+                                        bool lead_split, uint4 (&raw)[8], int next_col0, long long d_off = 0) {
   if (row_base + 32 <= p.M && col0 + 32 <= p.N)   // warp-uniform
-    epi_vec_body<OUT_BF16, EPI, RES, ACC, true>(p, stg, lane, row_base, col0, lead_split, raw, next_col0);
+    epi_vec_body<OUT_BF16, EPI, RES, ACC, true>(p, stg, lane, row_base, col0, lead_split, raw, next_col0, d_off);
   else
-    epi_vec_body<OUT_BF16, EPI, RES, ACC, false>(p, stg, lane, row_base, col0, lead_split, raw, next_col0);
+    epi_vec_body<OUT_BF16, EPI, RES, ACC, false>(p, stg, lane, row_base, col0, lead_split, raw, next_col0, d_off);
 }
 
 
@@ -723,6 +725,8 @@ vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         const TileCoord t = decode_tile(p, tile);
         const int m0 = t.m_blk * BM;
         const int n0 = t.n_blk * BN;
+        const int bg = p.group_cols > 0 ? n0 / p.group_cols : 0;     // column group of this tile (tiles never straddle groups)
+        const int nloc = n0 - bg * p.group_cols;
         for (int g = t.g0; g < t.g1; ++g) {
           int seg = 0, kb = g;
           if (kb >= p.kblocks[0]) { kb -= p.kblocks[0]; seg = 1; }
@@ -740,11 +744,12 @@ vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #pragma unroll
             for (int i = 0; i < BM / 64; ++i) tma_load_2d(ma, fb, sA + i * 8192, m0 + 64 * i, kb * BK);
           }
+          // B maps are 3-D: (k, n within the column group, group); a plain GEMM has one group
           if constexpr (!B_MN) {
-            tma_load_2d(mb, fb, sB, kb * BK, n0);
+            tma_load_3d(mb, fb, sB, kb * BK, nloc, bg);
           } else {
 #pragma unroll
-            for (int i = 0; i < BN / 64; ++i) tma_load_2d(mb, fb, sB + i * 8192, n0 + 64 * i, kb * BK);
+            for (int i = 0; i < BN / 64; ++i) tma_load_3d(mb, fb, sB + i * 8192, nloc + 64 * i, kb * BK, bg);
           }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -821,6 +826,8 @@ vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       // bias-type terms are added exactly once: by the split that owns the first k-block
       const bool lead_split = (t.g0 == 0);
       const int half = (warp - kEpiWarp0) >> 2;  // which half of the tile's columns this warp drains
+      // grouped fp32 accumulate output: group g of the columns starts d_gs (not Ng) elements after group g - 1
+      const long long d_off = (p.d_gs != 0 && p.group_cols > 0) ? static_cast<long long>(n0 / p.group_cols) * (p.d_gs - p.group_cols) : 0;
       if (rowmul) {
         aux_rows_load(p, lane, row_base, n0 + half * (BN / 64) * 32, aux_next);
       } else if (rowres) {
@@ -910,7 +917,7 @@ vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         for (int j = 0; j < 16; ++j) st_shared_v2(stg + lane * (kStgStride * 4) + j * 8, r[2 * j], r[2 * j + 1]);
         __syncwarp();
         switch (mode) {
-          case 1: epi_vec<false, VITB_EPI_NONE, 0, true>(p, stg, lane, row_base, col0, lead_split, side_raw, next_col0); break;
+          case 1: epi_vec<false, VITB_EPI_NONE, 0, true>(p, stg, lane, row_base, col0, lead_split, side_raw, next_col0, d_off); break;
           case 2: epi_vec<true, VITB_EPI_GELU, 0, false>(p, stg, lane, row_base, col0, lead_split, side_raw, next_col0); break;
           case 3: epi_vec<true, VITB_EPI_GELU_BWD, 0, false>(p, stg, lane, row_base, col0, lead_split, side_raw, next_col0); break;
           case 4: epi_vec<true, VITB_EPI_NONE, 0, false>(p, stg, lane, row_base, col0, lead_split, side_raw, next_col0); break;
@@ -1083,6 +1090,7 @@ vitb_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       tc_fence_after();
       const bool lead_split = (t.g0 == 0);
       const int half = (warp - kEpiWarp0) >> 2;
+      const long long d_off = (p.d_gs != 0 && p.group_cols > 0) ? static_cast<long long>(n0 / p.group_cols) * (p.d_gs - p.group_cols) : 0;
 #pragma unroll 1
       for (int c = half * 4; c < (half + 1) * 4; ++c) {
         const int col0 = n0 + c * 32;
@@ -1093,7 +1101,7 @@ vitb_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 #pragma unroll
         for (int j = 0; j < 16; ++j) st_shared_v2(stg + lane * (kStgStride * 4) + j * 8, r[2 * j], r[2 * j + 1]);
         __syncwarp();
-        epi_vec<false, VITB_EPI_NONE, 0, true>(p, stg, lane, row_base, col0, lead_split, no_side, -1);
+        epi_vec<false, VITB_EPI_NONE, 0, true>(p, stg, lane, row_base, col0, lead_split, no_side, -1, d_off);
         __syncwarp();
       }
       tc_fence_before();
@@ -1176,6 +1184,12 @@ extern "C" int VITB_GEMM_ENTRY(const vitb_gemm_params* p, void* stream_) {
                "vitb_gemm: a non-linear epilogue cannot be split along K");
   VITB_REQUIRE(p->row_bias == nullptr || p->row_bias_group > 0, VITB_ERR_BAD_ARG,
                "vitb_gemm: row_bias_group must be > 0");
+  const int ngroups = p->n_groups > 1 ? p->n_groups : 1;
+  VITB_REQUIRE(p->N % ngroups == 0, VITB_ERR_BAD_ARG, "vitb_gemm: N %d is not a multiple of n_groups %d", p->N, ngroups);
+  VITB_REQUIRE(ngroups == 1 || p->b_group_stride % 8 == 0, VITB_ERR_UNSUPPORTED_SHAPE, "vitb_gemm: b_group_stride %% 8");
+  VITB_REQUIRE(p->d_group_stride == 0 || (ngroups > 1 && p->accumulate && p->d_dtype == VITB_F32 && p->epilogue == VITB_EPI_NONE &&
+                                          p->d_group_stride % 4 == 0),
+               VITB_ERR_BAD_ARG, "vitb_gemm: a grouped output needs n_groups > 1, accumulate = 1, fp32 D, no epilogue");
 
   GemmDev d{};
   d.M = p->M;
@@ -1193,6 +1207,11 @@ extern "C" int VITB_GEMM_ENTRY(const vitb_gemm_params* p, void* stream_) {
   const int pad256 = ((p->N + 255) / 256) * 256 - p->N;
   const int pad128 = ((p->N + 127) / 128) * 128 - p->N;
   const int BN = (pad256 <= pad128) ? 256 : 128;
+  const int Ng = p->N / ngroups;
+  VITB_REQUIRE(ngroups == 1 || Ng % BN == 0, VITB_ERR_UNSUPPORTED_SHAPE,
+               "vitb_gemm: group width %d is not a multiple of the %d-column tile", Ng, BN);
+  d.group_cols = ngroups > 1 ? Ng : 0;
+  d.d_gs = ngroups > 1 ? p->d_group_stride : 0;
   d.m_tiles = (p->M + BM - 1) / BM;
   d.n_tiles = (p->N + BN - 1) / BN;
   const int sms = vitb_num_sms();
@@ -1241,6 +1260,8 @@ extern "C" int VITB_GEMM_ENTRY(const vitb_gemm_params* p, void* stream_) {
                !(p->accumulate && (p->residual != nullptr || d.epilogue != VITB_EPI_NONE)) &&
                !(d.epilogue != VITB_EPI_NONE && p->residual != nullptr);
     d.colsum = p->colsum;
+    VITB_REQUIRE(d.d_gs == 0 || d.vec_ok, VITB_ERR_UNSUPPORTED_SHAPE,
+                 "vitb_gemm: a grouped output needs the vectorised epilogue (N, ldd multiples of 4, 16-byte aligned D)");
     VITB_REQUIRE(p->colsum == nullptr || (d.vec_ok && al(p->colsum, 16) && !p->accumulate), VITB_ERR_UNSUPPORTED_SHAPE,
                  "vitb_gemm: colsum needs the vectorised epilogue (N, lds multiples of 4, 16-byte aligned pointers)");
   }
@@ -1254,10 +1275,17 @@ extern "C" int VITB_GEMM_ENTRY(const vitb_gemm_params* p, void* stream_) {
     else
       st = vitb_make_tmap_2d_bf16(&tm[2 * s], p->A[src], (uint64_t)p->M, K, (uint64_t)p->lda[src] * 2, 64, BK);
     if (st != VITB_OK) return st;
-    if (!p->b_mn_major)
-      st = vitb_make_tmap_2d_bf16(&tm[2 * s + 1], p->B[src], K, (uint64_t)p->N, (uint64_t)p->ldb[src] * 2, BK, BN);
-    else
-      st = vitb_make_tmap_2d_bf16(&tm[2 * s + 1], p->B[src], (uint64_t)p->N, K, (uint64_t)p->ldb[src] * 2, 64, BK);
+    {
+      // 3-D: (inner, outer, column group).  One group: the group stride is never used (any 16-byte multiple will do).
+      const uint64_t gs_bytes = ngroups > 1 ? (uint64_t)p->b_group_stride * 2 : 16;
+      uint64_t dims[3], str[2] = {(uint64_t)p->ldb[src] * 2, gs_bytes};
+      uint32_t box[3];
+      if (!p->b_mn_major) { dims[0] = K; dims[1] = (uint64_t)Ng; box[0] = BK; box[1] = (uint32_t)BN; }
+      else { dims[0] = (uint64_t)Ng; dims[1] = K; box[0] = 64; box[1] = BK; }
+      dims[2] = (uint64_t)ngroups;
+      box[2] = 1;
+      st = vitb_make_tmap_nd_bf16(&tm[2 * s + 1], p->B[src], 3, dims, str, box);
+    }
     if (st != VITB_OK) return st;
   }
   // bf16 outputs of the register-layout epilogue leave through TMA stores (32 x 32 tiles, SWIZZLE_64B);
@@ -1316,8 +1344,15 @@ extern "C" int VITB_GEMM_ENTRY(const vitb_gemm_params* p, void* stream_) {
     const bool pair_on = pair_env == nullptr || atoi(pair_env) != 0;
     if (pair_on && p->a_mn_major && p->b_mn_major && p->accumulate && p->num_segments == 1 &&
         d.epilogue == VITB_EPI_NONE && !d.d_bf16 && d.vec_ok && p->bias == nullptr && p->colsum == nullptr &&
-        p->split_k <= 0 && p->M >= 256 && p->N >= 256 && sms >= 2)
+        p->split_k <= 0 && p->M >= 256 && p->N >= 256 && sms >= 2 && (ngroups == 1 || (p->d_group_stride != 0 && Ng % 256 == 0))) {
+      // the pair kernel reads B through a plain 2-D map: a grouped OUTPUT is fine, a grouped B is not needed here
+      // (the merged weight gradient contracts against the packed [T, 3 Ng] dqkv buffer)
+      VITB_REQUIRE(ngroups == 1 || p->b_group_stride == Ng, VITB_ERR_UNSUPPORTED_SHAPE,
+                   "vitb_gemm: the weight-gradient pair kernel needs a column-contiguous B (b_group_stride == N / n_groups)");
+      st = vitb_make_tmap_2d_bf16(&tm[1], p->B[0], (uint64_t)p->N, (uint64_t)p->K[0], (uint64_t)p->ldb[0] * 2, 64, BK);
+      if (st != VITB_OK) return st;
       return launch_wgrad_pair(tm, d, p->M, p->N, stream);
+    }
   }
   const long long total_tiles = (long long)d.m_tiles * d.n_tiles * d.split_k;
   const int grid = (int)(total_tiles < sms ? total_tiles : sms);

@@ -118,6 +118,84 @@ class ShadowStore:
 SHADOW = ShadowStore()
 
 
+# --------------------------------------------------------------------------------------------------
+# parameter packs: tensors that one grouped GEMM reads / writes as G matrices at a uniform distance
+# --------------------------------------------------------------------------------------------------
+def mark_packed(*tensors):
+    """Declare that `tensors` (same shape) should be laid out back to back by the fused optimizers' flat buffers, so that
+    the merged q|k|v projection finds its three weights / biases / gradients at a uniform stride."""
+    group = tuple(tensors)
+    for t in group:
+        t._vitb_pack = group
+
+
+def packed_order(params):
+    """`params` with the members of every pack moved next to the pack's first member (order otherwise unchanged)."""
+    ids = {id(p) for p in params}
+    out, placed = [], set()
+    for p in params:
+        if id(p) in placed:
+            continue
+        group = getattr(p, "_vitb_pack", None)
+        if group is not None and all(id(t) in ids for t in group) and not any(id(t) in placed for t in group):
+            for t in group:
+                out.append(t)
+                placed.add(id(t))
+        else:
+            out.append(p)
+            placed.add(id(p))
+    return out
+
+
+def _uniform_stack(ts):
+    """A [G, *shape] strided view over G same-shape contiguous tensors that sit at one distance in ONE storage
+    (views of a flat buffer), or None."""
+    t0 = ts[0]
+    if any(t.shape != t0.shape or t.dtype != t0.dtype or not t.is_contiguous() or t.device != t0.device
+           or t.untyped_storage().data_ptr() != t0.untyped_storage().data_ptr() for t in ts):
+        return None
+    es = t0.element_size()
+    step = ts[1].data_ptr() - t0.data_ptr()
+    if step < t0.numel() * es or step % es != 0:
+        return None
+    if any(ts[i].data_ptr() - t0.data_ptr() != i * step for i in range(len(ts))):
+        return None
+    return torch.as_strided(t0, (len(ts),) + tuple(t0.shape), (step // es,) + tuple(t0.stride()))
+
+
+class _PackedShadows:
+    """bf16 copies of G weights as one [G, ...] tensor for callers without a flat optimizer buffer (inference):
+    refreshed when any of the masters changes."""
+
+    def __init__(self):
+        self._e = {}
+
+    def get(self, ws):
+        key = tuple(id(w) for w in ws)
+        sig = tuple((w._version, w.data_ptr()) for w in ws)
+        e = self._e.get(key)
+        if e is None or e[0] != sig or any(r() is not w for r, w in zip(e[2], ws)) or e[1].device != ws[0].device:
+            buf = torch.empty((len(ws),) + tuple(ws[0].shape), dtype=BF16, device=ws[0].device)
+            for i, w in enumerate(ws):
+                ops.cast_split(w.detach().contiguous(), hi=buf[i])
+            e = (sig, buf, tuple(weakref.ref(w, lambda _r, k=key: self._e.pop(k, None)) for w in ws))
+            self._e[key] = e
+        return e[1]
+
+
+_PACKED = _PackedShadows()
+
+
+def packed_weight_operand(ws, shape2d):
+    """[G, *shape2d] bf16 operand of the grouped GEMM for the G weights `ws` (bf16 mode): a strided view over the flat
+    shadow buffer when the fused optimizer laid them out at one distance, else a cached packed copy."""
+    his = [SHADOW.get(w, False)[0] for w in ws]
+    st = _uniform_stack(his)
+    if st is None:
+        st = _PACKED.get(ws)
+    return st.view(len(ws), *shape2d)
+
+
 def _fp32_mode():
     return _State.precision == "fp32"
 
@@ -451,7 +529,10 @@ class _QKVProj(torch.autograd.Function):
         qkv = torch.empty((rows, 3 * HD), dtype=adt, device=x.device)
         has_lora = len(lora) == 6 and lora[0] is not None
         ts = []
-        for i in range(3):
+        merged = not has_lora and not _fp32_mode() and len(xo) == 1
+        if merged:
+            _qkv_forward(xo[0], ws, bs, K, HD, qkv, kn=kn)
+        for i in range(0 if not merged else 3, 3):
             A, B = _pairs(xo, _weight_operand(ws[i], w2))
             out = qkv[:, i * HD:(i + 1) * HD]
             bias = bs[i].detach().view(-1) if bs[i] is not None else None
@@ -677,6 +758,7 @@ class _PatchEmbed(torch.autograd.Function):
         conv_w, conv_b, cls_token, pos = ctx.params
         Bsz, N, D, K, ldk = ctx.geom
         dx = dx.contiguous().float()
+        _side_take(dx.reshape(-1, D))      # block 0 left its bf16 copy / column sums for a consumer that does not exist
         fp32 = _fp32_mode()
         dev = dx.device
         need_w = conv_w.requires_grad
@@ -731,12 +813,32 @@ def cross_entropy(logits, labels):
 # --------------------------------------------------------------------------------------------------
 # fused pre-LN encoder block (bf16 mode): the whole block forward / backward as one autograd node
 # --------------------------------------------------------------------------------------------------
-# Side channel between consecutive blocks in the backward pass: the block that produces dx (fp32, for
-# autograd) also has it in bf16 (the next GEMM operand) and knows its column sums (the bias gradient of
-# the Linear that fed this block's input).  Keyed by storage pointer; consumed (popped) by the upstream
-# block's backward, so a stale entry can only be hit by a tensor occupying the very same storage with the
-# same size in the same backward pass.
+# Side channel between consecutive blocks in the backward pass: the block that produces dx (fp32, for autograd) also
+# has it in bf16 (the next GEMM operand) and knows its column sums (the bias gradient of the Linear that fed this block's
+# input).  An entry is keyed by the storage address of dx and stays valid only while (a) the dx tensor is alive — the
+# entry holds a weak reference and disappears with it, so a recycled address can never hit a stale entry — and (b) nobody
+# has written into it since (autograd accumulates a second consumer's gradient IN PLACE into a uniquely held buffer,
+# which bumps the version counter): the consumer then falls back to casting / summing the tensor it was actually given.
 _GRAD_SIDE = {}
+SIDE_STATS = [0, 0]     # [entries consumed, entries rejected or missing] — observable by the tests
+
+
+def _side_put(dx, dxb, colsum):
+    import os
+    if os.environ.get("VITB_GRAD_SIDE", "1") == "0":
+        return
+    key = (dx.data_ptr(), dx.numel())
+    _GRAD_SIDE[key] = (weakref.ref(dx, lambda _r, k=key: _GRAD_SIDE.pop(k, None)), dx._version, dxb, colsum)
+
+
+def _side_take(dy2):
+    e = _GRAD_SIDE.pop((dy2.data_ptr(), dy2.numel()), None)
+    src = e[0]() if e is not None else None
+    if src is None or src._version != e[1] or dy2._version != e[1]:
+        SIDE_STATS[1] += 1
+        return None
+    SIDE_STATS[0] += 1
+    return e[2], e[3]
 
 
 def _acc(param, shape=None):
@@ -746,6 +848,30 @@ def _acc(param, shape=None):
         return (tgt.view(shape) if shape is not None else tgt), None
     buf = torch.zeros(param.shape, dtype=F32, device=param.device)
     return (buf.view(shape) if shape is not None else buf), buf
+
+
+def _qkv_merge_enabled():
+    import os
+    return os.environ.get("VITB_QKV_MERGE", "1") != "0"
+
+
+def _qkv_forward(xn, ws, bs, K, HD, qkv, kn=True):
+    """qkv[:, g*HD:(g+1)*HD] = xn W_g + b_g for ws = (wq, wk, wv) in LinearGeneral ("kn": [K, HD]) or nn.Linear ([HD, K])
+    layout: one grouped GEMM [T, K] x [K, 3 HD] (src/model.py:86-88 / res-vit/model.py:265-271 as a single contraction)
+    when the tile width divides HD, else three GEMMs.  bf16 mode only (callers check)."""
+    w2 = (K, HD) if kn else (HD, K)
+    if _qkv_merge_enabled() and HD % 256 == 0:
+        Bst = packed_weight_operand(ws, w2)
+        bias = None
+        if bs[0] is not None:
+            flat = [b.detach().reshape(-1) for b in bs]
+            st = _uniform_stack(flat)
+            bias = st.reshape(-1) if (st is not None and st.stride(0) == HD) else torch.cat(flat)
+        ops.gemm(xn, Bst, b_mn=kn, out=qkv, bias=bias)
+        return
+    for i, (w, b) in enumerate(zip(ws, bs)):
+        ops.gemm(xn, SHADOW.get(w, False)[0].view(w2), b_mn=kn, out=qkv[:, i * HD:(i + 1) * HD],
+                 bias=b.detach().view(-1) if b is not None else None)
 
 
 class _EncoderBlockFused(torch.autograd.Function):
@@ -769,9 +895,7 @@ class _EncoderBlockFused(torch.autograd.Function):
         dev = x.device
         _, xn, _, mean1, rstd1 = ops.layernorm_fwd(x2, n1w.detach(), n1b.detach(), eps1)
         qkv = torch.empty((T, 3 * D), dtype=BF16, device=dev)
-        for i, (w, b) in enumerate(((wq, bq), (wk, bk), (wv, bv))):
-            ops.gemm(xn, SHADOW.get(w, False)[0].view(D, D), b_mn=True, out=qkv[:, i * D:(i + 1) * D],
-                     bias=b.detach().view(-1))
+        _qkv_forward(xn, (wq, wk, wv), (bq, bk, bv), D, D, qkv)
         qkv3 = qkv.view(Bsz, N, 3 * D)
         o, lse = ops.attn_fwd(qkv3[:, :, :D], qkv3[:, :, D:2 * D], qkv3[:, :, 2 * D:], H)
         o2 = o.view(T, D)
@@ -800,7 +924,7 @@ class _EncoderBlockFused(torch.autograd.Function):
         dy2 = dy.reshape(T, D)
         if dy2.dtype != F32 or not dy2.is_contiguous():
             dy2 = dy2.float().contiguous()
-        side = _GRAD_SIDE.pop((dy2.data_ptr(), dy2.numel()), None)
+        side = _side_take(dy2)
         if side is not None:
             dyb, dy_colsum = side
         else:
@@ -848,11 +972,17 @@ class _EncoderBlockFused(torch.autograd.Function):
         ops.attn_bwd(do.view(Bsz, N, D), qkv3[:, :, :D], qkv3[:, :, D:2 * D], qkv3[:, :, 2 * D:], o, lse, H,
                      dq=dqkv[:, :, :D], dk=dqkv[:, :, D:2 * D], dv=dqkv[:, :, 2 * D:])
         dq2 = dqkv.view(T, 3 * D)
-        for i, (w, b) in enumerate(((wq, bq), (wk, bk), (wv, bv))):
-            sl = dq2[:, i * D:(i + 1) * D]
+        accs_w = []
+        for w in (wq, wk, wv):
             acc, r = _acc(w, (D, D))
             ret(w, r)
-            ops.gemm(xn, sl, a_mn=True, b_mn=True, out=acc, accumulate=True)              # dW[K,N] = xn^T dQ
+            accs_w.append(acc)
+        gstack = _uniform_stack(accs_w) if _qkv_merge_enabled() and D % 256 == 0 else None
+        if gstack is not None:      # the three weight gradients as ONE GEMM: dW[3][K,N] = xn^T [dQ | dK | dV]
+            ops.gemm(xn, dq2, a_mn=True, b_mn=True, out=gstack, accumulate=True)
+        else:
+            for i, acc in enumerate(accs_w):
+                ops.gemm(xn, dq2[:, i * D:(i + 1) * D], a_mn=True, b_mn=True, out=acc, accumulate=True)   # dW[K,N] = xn^T dQ
         accs = []
         for b in (bq, bk, bv):
             accb, r = _acc(b)
@@ -872,7 +1002,7 @@ class _EncoderBlockFused(torch.autograd.Function):
             colsum_dx = torch.zeros(D, dtype=F32, device=dev)
             dx, dxb, _ = ops.layernorm_bwd(dxn, x2, mean1, rstd1, n1w.detach(), dres=dh, want_f32=True,
                                            want_bf16=True, dgamma=acc_g1, dbeta=acc_be1, dcolsum=colsum_dx)
-            _GRAD_SIDE[(dx.data_ptr(), dx.numel())] = (dxb, colsum_dx)
+            _side_put(dx, dxb, colsum_dx)
             dx = dx.view(ctx.x_shape)
         else:
             ops.layernorm_bwd(dxn, x2, mean1, rstd1, n1w.detach(), dres=dh, want_f32=False, dgamma=acc_g1,

@@ -96,6 +96,10 @@ class SelfAttention(nn.Module):
         self.out = LinearGeneral((self.heads, self.head_dim), (in_dim,))
         # the reference constructs a Dropout here but never applies it (src/model.py:78-81,83-101)
         self.dropout = None
+        # q, k, v run as ONE GEMM [T, D] x [D, 3D] when their weights sit at a uniform distance in memory: the fused
+        # optimizers lay these three (and their biases) out back to back in the flat buffers
+        F.mark_packed(self.query.weight, self.key.weight, self.value.weight)
+        F.mark_packed(self.query.bias, self.key.bias, self.value.bias)
 
     def forward(self, x, residual=None):
         b, n, _ = x.shape

@@ -44,6 +44,15 @@ def gemm(A, B, *, a_mn=False, b_mn=False, out=None, out_dtype=torch.bfloat16, bi
     p = L.GemmParams()
     p.struct_bytes = C.sizeof(L.GemmParams)
     M = N = None
+    # column groups (merged q|k|v): B_i given as [G, K, Ng] (b_mn) / [G, Ng, K] — G matrices at a uniform distance
+    groups = 1
+    if Bs[0].dim() == 3:
+        groups = Bs[0].shape[0]
+        for b in Bs:
+            if b.dim() != 3 or b.shape[0] != groups or b.stride(0) != Bs[0].stride(0) or b.stride(2) != 1:
+                raise L.VitbError("gemm: grouped B segments must be [G, ., .] with one group stride and unit inner stride")
+        p.n_groups, p.b_group_stride = groups, Bs[0].stride(0)
+        Bs = [b[0] for b in Bs]
     for i, (a, b) in enumerate(zip(As, Bs)):
         if a.dtype != torch.bfloat16 or b.dtype != torch.bfloat16:
             raise L.VitbError("gemm: operands must be bf16")
@@ -51,6 +60,7 @@ def gemm(A, B, *, a_mn=False, b_mn=False, out=None, out_dtype=torch.bfloat16, bi
         _check_2d_rowmajor(b, "B[%d]" % i)
         m, ka = (a.shape[1], a.shape[0]) if a_mn else (a.shape[0], a.shape[1])
         n, kb = (b.shape[1], b.shape[0]) if b_mn else (b.shape[0], b.shape[1])
+        n *= groups
         if ka != kb:
             raise L.VitbError("gemm: K mismatch in segment %d: %d vs %d" % (i, ka, kb))
         if M is None:
@@ -69,10 +79,16 @@ def gemm(A, B, *, a_mn=False, b_mn=False, out=None, out_dtype=torch.bfloat16, bi
     if out is None:
         rows = out_rows if out_rows is not None else M
         out = torch.empty((rows, N), dtype=out_dtype, device=As[0].device)
-    _check_2d_rowmajor(out, "out")
-    if out.shape[1] != N:
-        raise L.VitbError("gemm: out has %d columns, expected %d" % (out.shape[1], N))
-    p.D, p.ldd, p.d_dtype = out.data_ptr(), out.stride(0), L.dtype_code(out)
+    if out.dim() == 3:      # grouped output [G, M, Ng]: the G weight gradients of a merged projection
+        if out.shape[0] != groups or groups * out.shape[2] != N or out.stride(2) != 1:
+            raise L.VitbError("gemm: a grouped output must be [n_groups, M, N / n_groups] with unit inner stride")
+        p.d_group_stride = out.stride(0)
+        p.D, p.ldd, p.d_dtype = out.data_ptr(), out.stride(1), L.dtype_code(out)
+    else:
+        _check_2d_rowmajor(out, "out")
+        if out.shape[1] != N:
+            raise L.VitbError("gemm: out has %d columns, expected %d" % (out.shape[1], N))
+        p.D, p.ldd, p.d_dtype = out.data_ptr(), out.stride(0), L.dtype_code(out)
     p.accumulate = int(accumulate)
     if d2 is not None:
         _check_2d_rowmajor(d2, "d2")
@@ -214,7 +230,7 @@ def attn_fwd(q, k, v, H, *, use_tc=None):
     lse = torch.empty((B, H, Nq), dtype=torch.float32, device=q.device)
     p = _attn_params(q, k, v, o, lse, H)
     fn = L._vitb_attn_fwd_tc if use_tc else L._vitb_attn_fwd_simt
-    if use_tc and _attn_ws_enabled() and L.vitb_attn_ws_supported(dh, Nq, k.shape[1]):
+    if use_tc and _attn_ws_enabled() and L.vitb_attn_ws_supported(0, dh, Nq, k.shape[1]):
         fn = L._vitb_attn_fwd_ws        # persistent warp-specialised kernel
     L.check(fn(C.byref(p), L.stream_ptr(q.device)), "vitb_attn_fwd")
     return o, lse
@@ -250,7 +266,7 @@ def attn_bwd(dout, q, k, v, o, lse, H, *, use_tc=None, dq=None, dk=None, dv=None
     fn = L._vitb_attn_bwd_tc if use_tc else L._vitb_attn_bwd_simt
     if use_tc and os.environ.get("VITB_ATTN_BWD2") == "1" and L.vitb_attn_bwd_tc2_supported(dh, Nq, Nk):
         fn = L._vitb_attn_bwd_tc2       # experimental key-split CTA-pair kernel (off unless VITB_ATTN_BWD2=1)
-    if use_tc and _attn_ws_enabled() and L.vitb_attn_ws_supported(dh, Nq, Nk):
+    if use_tc and _attn_ws_enabled() and L.vitb_attn_ws_supported(1, dh, Nq, Nk):
         fn = L._vitb_attn_bwd_ws        # persistent warp-specialised kernel
     L.check(fn(C.byref(p), L.stream_ptr(q.device)), "vitb_attn_bwd")
     return dq, dk, dv
@@ -412,20 +428,29 @@ def cross_entropy(logits, labels, *, want_grad=True):
     return loss, dl
 
 
+def _check_hyper(h):
+    if h is not None and (h.dtype != torch.float32 or h.numel() != 4 or not h.is_contiguous() or not h.is_cuda):
+        raise L.VitbError("hyper_dev must be a contiguous fp32 CUDA tensor of 4 values")
+
+
 def sgd_momentum(p, g, m, lr, momentum, *, dampening=0.0, weight_decay=0.0, nesterov=False, first_step=False,
-                 shadow_hi=None, shadow_lo=None, lr_dev=None):
+                 shadow_hi=None, shadow_lo=None, hyper_dev=None):
+    """hyper_dev: optional device tensor of 4 floats {lr, momentum, dampening, weight_decay} overriding the scalars."""
     L.require_cuda(p, g, m)
-    L.check(L._vitb_sgd_momentum(L.ptr(p), L.ptr(g), L.ptr(m), p.numel(), float(lr), L.ptr(lr_dev), float(momentum),
+    _check_hyper(hyper_dev)
+    L.check(L._vitb_sgd_momentum(L.ptr(p), L.ptr(g), L.ptr(m), p.numel(), float(lr), L.ptr(hyper_dev), float(momentum),
                                  float(dampening), float(weight_decay), int(nesterov), int(first_step),
                                  L.ptr(shadow_hi), L.ptr(shadow_lo), L.stream_ptr(p.device)), "vitb_sgd_momentum")
 
 
 def adamw(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, *, grad_scale=None, shadow_hi=None, shadow_lo=None,
-          lr_dev=None, step_dev=None):
+          hyper_dev=None, step_dev=None):
+    """hyper_dev: optional device tensor of 4 floats {lr, beta1, beta2, weight_decay} overriding the scalars."""
     L.require_cuda(p, g, m, v)
+    _check_hyper(hyper_dev)
     if step_dev is not None and step_dev.dtype != torch.int32:
         raise L.VitbError("adamw: step_dev must be an int32 device scalar")
-    L.check(L._vitb_adamw(L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), p.numel(), float(lr), L.ptr(lr_dev), float(beta1),
+    L.check(L._vitb_adamw(L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), p.numel(), float(lr), L.ptr(hyper_dev), float(beta1),
                           float(beta2), float(eps), float(weight_decay), int(step), L.ptr(step_dev), L.ptr(grad_scale),
                           L.ptr(shadow_hi), L.ptr(shadow_lo), L.stream_ptr(p.device)), "vitb_adamw")
 

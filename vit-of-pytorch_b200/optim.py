@@ -20,7 +20,7 @@ _ALIGN = 64  # elements: 256-byte aligned fp32 slices, 128-byte aligned bf16 sli
 
 class _FlatGroup:
     def __init__(self, params):
-        params = [p for p in params if p.requires_grad]
+        params = F.packed_order([p for p in params if p.requires_grad])
         if not params:
             raise ValueError("no trainable parameters")
         dev = params[0].device
@@ -68,11 +68,44 @@ class _FlatGroup:
 class _FusedBase(torch.optim.Optimizer):
     def _init_flat(self):
         self._flat = [_FlatGroup(g["params"]) for g in self.param_groups]
+        # device-resident hyper-parameters (4 floats per group, see _hyper): a captured CUDA graph of step() keeps
+        # following whatever an LR scheduler writes into param_groups (OneCycleLR cycles lr AND momentum / beta1)
+        self._hyper_host = [self._hyper(g) for g in self.param_groups]
+        self._hyper_dev = [torch.tensor(h, dtype=torch.float32, device=fg.flat_p.device)
+                           for h, fg in zip(self._hyper_host, self._flat)]
+
+    def _hyper(self, group):          # -> 4 floats, the layout the kernel expects
+        raise NotImplementedError
+
+    def sync_lr(self):
+        """Push param_groups[...] (lr, momentum / betas, weight decay) to the device scalars; called by step() outside
+        stream capture and by GraphedTrainStep before every replay."""
+        for i, g in enumerate(self.param_groups):
+            h, old = self._hyper(g), self._hyper_host[i]
+            if h != old:
+                for j in range(4):      # asynchronous element fills (a host -> device copy would sync the stream)
+                    if old is None or h[j] != old[j]:
+                        self._hyper_dev[i][j].fill_(h[j])
+                self._hyper_host[i] = h
+
+    sync_hyper = sync_lr
 
     def zero_grad(self, set_to_none=False):  # gradients live in the flat buffer; never set to None
         F.clear_grad_side_channel()
         for fg in self._flat:
             fg.zero_grad()
+
+    def _check_grad_views(self):
+        """Weight gradients are accumulated straight into the flat buffer through p._vitb_main_grad; `model.zero_grad()`
+        or `p.grad = None` would leave that buffer un-zeroed while hiding it from view.  Refuse to step on such a state."""
+        for fg in self._flat:
+            base = fg.flat_g.data_ptr()
+            for p, off in zip(fg.params, fg.offsets):
+                if p.grad is None or p.grad.data_ptr() != base + 4 * off:
+                    raise RuntimeError(
+                        "fused optimizer: a parameter's .grad no longer aliases the flat gradient buffer — clear gradients "
+                        "with optimizer.zero_grad() (not model.zero_grad() / p.grad = None): the kernels accumulate weight "
+                        "gradients into the optimizer's flat buffer, which only optimizer.zero_grad() zeroes")
 
     def flat_grads(self):
         """The contiguous gradient buffers (one per param group) — what the data-parallel wrapper all-reduces."""
@@ -80,6 +113,64 @@ class _FusedBase(torch.optim.Optimizer):
 
     def flat_params(self):
         return [fg.flat_p for fg in self._flat]
+
+    # ---- checkpointing: the moments live in flat buffers outside Optimizer.state; export / import them per parameter
+    # in torch.optim's own layout so that a resumed run continues exactly (and torch.optim can read the file)
+    def _state_buffers(self):         # -> {state key: [flat buffer or None per group]}
+        raise NotImplementedError
+
+    def _extra_state(self):
+        return {}
+
+    def _load_extra_state(self, extra):
+        pass
+
+    def state_dict(self):
+        sd = super().state_dict()
+        state, idx = {}, 0
+        bufs = self._state_buffers()
+        for gi, fg in enumerate(self._flat):
+            order = {id(p): i for i, p in enumerate(fg.params)}
+            for p in self.param_groups[gi]["params"]:
+                j = order.get(id(p))
+                if j is not None:
+                    off, n = fg.offsets[j], p.numel()
+                    entry = {k: b[gi][off:off + n].view(p.shape).clone() for k, b in bufs.items() if b[gi] is not None}
+                    entry.update({k: (v.clone() if torch.is_tensor(v) else v) for k, v in self._extra_state().items()})
+                    if entry:
+                        state[idx] = entry
+                idx += 1
+        sd["state"] = state
+        return sd
+
+    def load_state_dict(self, state_dict):
+        groups = state_dict["param_groups"]
+        if len(groups) != len(self.param_groups):
+            raise ValueError("loaded state dict has a different number of parameter groups")
+        for g, saved in zip(self.param_groups, groups):
+            if len(saved["params"]) != len(g["params"]):
+                raise ValueError("loaded state dict contains a parameter group that doesn't match the size of optimizer's group")
+            for k, v in saved.items():
+                if k != "params":
+                    g[k] = v
+        bufs = self._state_buffers()
+        idx, extra = 0, None
+        for gi, fg in enumerate(self._flat):
+            order = {id(p): i for i, p in enumerate(fg.params)}
+            for p in self.param_groups[gi]["params"]:
+                entry = state_dict["state"].get(idx)
+                j = order.get(id(p))
+                if entry is not None and j is not None:
+                    off, n = fg.offsets[j], p.numel()
+                    for k, b in bufs.items():
+                        if b[gi] is not None and k in entry:
+                            b[gi][off:off + n].copy_(entry[k].reshape(-1).to(b[gi].device, torch.float32))
+                    extra = entry
+                idx += 1
+        if extra is not None:
+            self._load_extra_state(extra)
+        self._hyper_host = [None] * len(self.param_groups)   # force a refresh of the device scalars
+        self.sync_lr()
 
 
 class FusedSGD(_FusedBase):
@@ -90,17 +181,18 @@ class FusedSGD(_FusedBase):
         self._bufs = [torch.zeros_like(fg.flat_p) if g["momentum"] != 0 else None
                       for fg, g in zip(self._flat, self.param_groups)]
         self._steps = 0
-        # device-resident learning rates: a captured CUDA graph of step() keeps following the LR scheduler
-        self._lr_dev = [torch.full((), float(g["lr"]), dtype=torch.float32, device=fg.flat_p.device)
-                        for fg, g in zip(self._flat, self.param_groups)]
-        self._lr_host = [float(g["lr"]) for g in self.param_groups]
 
-    def sync_lr(self):
-        """Push param_groups[...]['lr'] to the device scalars (call before replaying a captured step)."""
-        for i, g in enumerate(self.param_groups):
-            if float(g["lr"]) != self._lr_host[i]:
-                self._lr_host[i] = float(g["lr"])
-                self._lr_dev[i].fill_(self._lr_host[i])
+    def _hyper(self, g):
+        return [float(g["lr"]), float(g["momentum"]), float(g["dampening"]), float(g["weight_decay"])]
+
+    def _state_buffers(self):
+        return {"momentum_buffer": self._bufs}
+
+    def _extra_state(self):
+        return {"vitb_steps": self._steps}
+
+    def _load_extra_state(self, extra):
+        self._steps = int(extra.get("vitb_steps", 1 if "momentum_buffer" in extra else 0))
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -109,12 +201,13 @@ class FusedSGD(_FusedBase):
         want_lo = F.get_precision() == "fp32"
         if not torch.cuda.is_current_stream_capturing():
             self.sync_lr()
-        for fg, g, buf, lr_dev in zip(self._flat, self.param_groups, self._bufs, self._lr_dev):
+            self._check_grad_views()
+        for fg, g, buf, hyper in zip(self._flat, self.param_groups, self._bufs, self._hyper_dev):
             if want_lo:
                 fg.ensure_lo()
             ops.sgd_momentum(fg.flat_p, fg.flat_g, buf, g["lr"], g["momentum"], dampening=g["dampening"],
                              weight_decay=g["weight_decay"], nesterov=g["nesterov"], first_step=self._steps == 0,
-                             shadow_hi=fg.flat_hi, shadow_lo=fg.flat_lo, lr_dev=lr_dev)
+                             shadow_hi=fg.flat_hi, shadow_lo=fg.flat_lo, hyper_dev=hyper)
             fg.mark_fresh()
         self._steps += 1
 
@@ -132,16 +225,22 @@ class FusedAdamW(_FusedBase):
         self._coef = torch.ones((), dtype=torch.float32, device=dev)
         self.grad_norm = torch.zeros((), dtype=torch.float32, device=dev)  # last total norm (device scalar)
         self._steps = 0
-        # device-resident step counter and learning rates: step() can be captured in a CUDA graph
+        # device-resident step counter: step() can be captured in a CUDA graph
         self._step_dev = torch.zeros((), dtype=torch.int32, device=dev)
-        self._lr_dev = [torch.full((), float(g["lr"]), dtype=torch.float32, device=dev) for g in self.param_groups]
-        self._lr_host = [float(g["lr"]) for g in self.param_groups]
 
-    def sync_lr(self):
-        for i, g in enumerate(self.param_groups):
-            if float(g["lr"]) != self._lr_host[i]:
-                self._lr_host[i] = float(g["lr"])
-                self._lr_dev[i].fill_(self._lr_host[i])
+    def _hyper(self, g):
+        return [float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["weight_decay"])]
+
+    def _state_buffers(self):
+        return {"exp_avg": self._m, "exp_avg_sq": self._v}
+
+    def _extra_state(self):
+        return {"step": torch.tensor(float(self._step_dev.item()))}
+
+    def _load_extra_state(self, extra):
+        step = int(float(extra.get("step", 0)))
+        self._steps = step
+        self._step_dev.fill_(step)
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -150,6 +249,7 @@ class FusedAdamW(_FusedBase):
         self._steps += 1
         if not torch.cuda.is_current_stream_capturing():
             self.sync_lr()
+            self._check_grad_views()
         self._step_dev += 1          # a device op: replays of a captured step keep counting
         coef = None
         if self.max_grad_norm is not None:  # clip_grad_norm_ over ALL groups, computed and applied on device
@@ -159,10 +259,10 @@ class FusedAdamW(_FusedBase):
             ops.clip_coef(self._sumsq, self.max_grad_norm, self._coef, self.grad_norm)
             coef = self._coef
         want_lo = F.get_precision() == "fp32"
-        for fg, g, m, v, lr_dev in zip(self._flat, self.param_groups, self._m, self._v, self._lr_dev):
+        for fg, g, m, v, hyper in zip(self._flat, self.param_groups, self._m, self._v, self._hyper_dev):
             if want_lo:
                 fg.ensure_lo()
             ops.adamw(fg.flat_p, fg.flat_g, m, v, g["lr"], g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"],
-                      self._steps, grad_scale=coef, shadow_hi=fg.flat_hi, shadow_lo=fg.flat_lo, lr_dev=lr_dev,
+                      self._steps, grad_scale=coef, shadow_hi=fg.flat_hi, shadow_lo=fg.flat_lo, hyper_dev=hyper,
                       step_dev=self._step_dev)
             fg.mark_fresh()
