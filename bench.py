@@ -38,6 +38,55 @@ CPU_SAMPLE_BATCH = 8
 LR, TRAIN_STEPS, WARMUP_STEPS = 0.03, 15000, 500   # src/config.py:39-42 defaults
 WORKLOAD = "ViT-B/16 224px train step (fwd+bwd+SGD momentum 0.9, OneCycleLR), batch %d/GPU, C=100"
 
+# arch geometry (src/config.py:57-104): patch, D, M, H, L
+_GEO = {"b16": (16, 768, 3072, 12, 12), "l16": (16, 1024, 4096, 16, 24), "h14": (14, 1280, 5120, 16, 32)}
+
+
+def vit_gflop(arch, image=224, classes=100):
+    """dense contractions only, per image.  Returns (forward GFLOP of the reference algorithm, forward
+    GFLOP this repo executes).  The two differ because the last block is evaluated on the class-token row only (the
+    reference computes all N rows and reads row 0, src/model.py:155,210): its query / attention / output projection /
+    MLP run on 1 row instead of N; K and V still need every token."""
+    P, D, M, H, L = _GEO[arch]
+    n_p = (image // P) ** 2
+    N = n_p + 1
+    qkv, attn, out, fc = 6.0 * N * D * D, 4.0 * N * N * D, 2.0 * N * D * D, 4.0 * N * D * M
+    layer = qkv + attn + out + fc
+    patch = 2.0 * n_p * 3 * P * P * D
+    head = 2.0 * D * classes
+    fwd = patch + L * layer + head
+    last_exec = qkv * 2.0 / 3.0 + (qkv / 3.0 + attn + out + fc) / N
+    return fwd / 1e9, (fwd - layer + last_exec) / 1e9
+
+
+def resvit_train_gflop(N=197, D=768, M=3072, L=12, start=2, hdim=512, low_rank=256, r=8, active=0.4, P=16, classes=100):
+    """FLOPs of one Res-ViT fine-tune step per image in the REFERENCE's semantics: the base weights are
+    frozen, so every base GEMM costs forward + dgrad (2x) and no wgrad; in a dynamic layer the teacher path is forward
+    only and the student path forward + dgrad; router, LoRA and approximators are trainable (3x), the approximators run
+    on the skipped rows (1 - active)."""
+    layer = 8.0 * N * D * D + 4.0 * N * N * D + 4.0 * N * D * M
+    lora = 3 * 2.0 * N * (D * r + r * D)
+    router = 2.0 * N * (D * hdim + 2 * hdim * hdim + hdim * (hdim // 2) + (hdim // 2) * 2)
+    approx = 2.0 * N * (1.0 - active) * 2 * D * low_rank
+    plain = start * (2 * layer + 3 * lora)
+    dyn = (L - start) * (layer + 2 * layer + 3 * lora + 3 * router + 3 * approx)
+    patch = 2.0 * (N - 1) * 3 * P * P * D
+    head = 3 * 2.0 * D * classes
+    return (patch + plain + dyn + head) / 1e9
+
+
+CONFIGS = {   # BASELINE.json configs[1..4]
+    "c2": dict(kind="vit_train", arch="b16", batch=128, classes=100,
+               workload="ViT-B/16 224px train step (fwd+bwd+SGD momentum 0.9, OneCycleLR), batch %d/GPU, C=100"),
+    "c3": dict(kind="vit_train", arch="l16", batch=64, classes=100,
+               workload="ViT-L/16 224px train step (fwd+bwd+SGD momentum 0.9, OneCycleLR), batch %d/GPU, C=100"),
+    "c4": dict(kind="vit_infer", arch="h14", batch=256, classes=1000,
+               workload="ViT-H/14 224px inference (N=257 tokens, head_dim 80), batch %d/GPU, C=1000"),
+    "c5": dict(kind="resvit_train", arch="b16", batch=128, classes=100,
+               workload="Res-ViT B/16 224px fine-tune step (router target 0.4, LoRA rank 8, approximator rank 256, block_size 1; "
+                        "CE + active + distill losses, AdamW + clip 1.0), batch %d/GPU, C=100"),
+}
+
 
 _RESULT_FD = None
 
@@ -59,8 +108,8 @@ def peaks():
 
 def gemm_traffic():
     """Average DRAM bytes (read + write) per vitb_gemm_kernel launch of one training step, from the committed
-    ncu capture profiles/gemm_traffic_r01.json (dram__bytes_read.sum + dram__bytes_write.sum); None if absent."""
-    p = os.path.join(ROOT, "profiles", "gemm_traffic_r01.json")
+    ncu capture profiles/gemm_traffic_r02.json (dram__bytes_read.sum + dram__bytes_write.sum); None if absent."""
+    p = os.path.join(ROOT, "profiles", "gemm_traffic_r02.json")
     if not os.path.exists(p):
         return None
     return json.load(open(p)).get("dram_bytes_per_launch")
@@ -242,7 +291,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="vitb200", choices=["vitb200", "reference"])
-    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS),
+                    help="BASELINE.json config: c2 ViT-B/16 train bs128 (default, the headline), c3 ViT-L/16 train bs64, "
+                         "c4 ViT-H/14 inference bs256, c5 Res-ViT B/16 fine-tune bs128")
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the config's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of one CUDA graph")
     ap.add_argument("--ddp-mode", default="graph1", choices=["graph1", "graph2", "overlap"],
@@ -276,52 +328,91 @@ def main():
     import torch.distributed as dist
     import vitb200
 
+    cfg = CONFIGS[args.config]
+    kind, arch, classes = cfg["kind"], cfg["arch"], cfg["classes"]
+    B = args.batch if args.batch > 0 else cfg["batch"]
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     vitb200.set_precision("bf16")
     torch.manual_seed(0)                     # same constructor RNG sequence as the reference (tests/test_oracle.py)
-    model = vitb200.build_vit(ARCH, IMG, CLASSES)
-    with torch.no_grad():                    # SURVEY.md F5 recipe: trained-like scale for attention / pos weights
-        for k, v in model.state_dict().items():
-            if k.endswith(("attn.query.weight", "attn.key.weight", "attn.value.weight", "attn.out.weight",
-                           "pos_embedding.pos_embedding")):
-                v.mul_(0.02)
-    model = model.to(dev).train()
-    opt = vitb200.optim.FusedSGD(model.parameters(), lr=LR, momentum=0.9)
-    # the reference's schedule (src/train.py:159-163, config defaults src/config.py:39-42): the step starts at
-    # max_lr / 25 and the learning rate reaches the kernels through a device scalar, so it also drives the graph
-    sched = torch.optim.lr_scheduler.OneCycleLR(opt, max_lr=LR, pct_start=WARMUP_STEPS / TRAIN_STEPS, total_steps=TRAIN_STEPS)
+    train = kind != "vit_infer"
+    if kind == "resvit_train":
+        # res-vit/config.py presets + the fine-tune switches of BASELINE.json configs[4] (res-vit/ft_resvit.sh)
+        from vitb200 import resvit
+        margs = resvit.ModelArgs(use_lora=True, use_reslr=True, block_size=1, dynamic_active_target=0.4, lora_rank=8,
+                                 num_classes=classes, device="cuda")
+        model = resvit.Transformer(margs)
+        with torch.no_grad():
+            model.pos_embedding.pos_embedding.mul_(0.02)
+        model = model.to(dev).train()
+        # res-vit/train.py:272-277,65: AdamW(1e-4, wd 0.05) over the trainable set + clip_grad_norm_(1.0)
+        opt = vitb200.optim.FusedAdamW([q for q in model.parameters() if q.requires_grad], lr=1e-4, weight_decay=0.05,
+                                       max_grad_norm=1.0)
+        sched = None
+        gflop_ref = gflop_exec = resvit_train_gflop(classes=classes)
+        if world > 1:   # ActiveLoss is (batch mean - target)^2: make it the loss of the GLOBAL batch (one scalar all-reduce)
+            model.criterion_active.sync_group = True
+
+        def forward_loss(net, img, labels):        # res-vit/train.py:30,51-52: c_loss + a_loss + d_loss
+            c, a, d, e, metric = net(img, labels)
+            return c + a + d
+    else:
+        model = vitb200.build_vit(arch, IMG, classes)
+        with torch.no_grad():                    # SURVEY.md F5 recipe: trained-like scale for attention / pos weights
+            for k, v in model.state_dict().items():
+                if k.endswith(("attn.query.weight", "attn.key.weight", "attn.value.weight", "attn.out.weight",
+                               "pos_embedding.pos_embedding")):
+                    v.mul_(0.02)
+        model = model.to(dev)
+        model.train(train)
+        fwd_ref, fwd_exec = vit_gflop(arch, IMG, classes)
+        gflop_ref, gflop_exec = (3 * fwd_ref, 3 * fwd_exec) if train else (fwd_ref, fwd_exec)
+        opt = sched = None
+        if train:
+            opt = vitb200.optim.FusedSGD(model.parameters(), lr=LR, momentum=0.9)
+            # the reference's schedule (src/train.py:159-163, config defaults src/config.py:39-42): the step starts at
+            # max_lr / 25; lr AND the cycled momentum reach the kernels through device scalars, so they also drive the graph
+            sched = torch.optim.lr_scheduler.OneCycleLR(opt, max_lr=LR, pct_start=WARMUP_STEPS / TRAIN_STEPS, total_steps=TRAIN_STEPS)
+
+        def forward_loss(net, img, labels):
+            return vitb200.functional.cross_entropy(net(img), labels)
     if args.graph_ddp:
         args.ddp_mode = "graph2"
     if args.no_graph and world > 1:
         args.ddp_mode = "overlap"
+    if not train:
+        args.ddp_mode = "replicas"           # inference: independent replicas, no exchange
     graph_ddp = world > 1 and args.ddp_mode == "graph2"
     graph_one = world > 1 and args.ddp_mode == "graph1"
     net = vitb200.ddp.DataParallel(model, opt) if (world > 1 and args.ddp_mode == "overlap") else model
-    B = args.batch
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     img_d = torch.randn(B, 3, IMG, IMG, generator=gen, device=dev)
-    lab_d = torch.randint(0, CLASSES, (B,), generator=gen, device=dev)
+    lab_d = torch.randint(0, classes, (B,), generator=gen, device=dev)
     img_h = img_d.cpu().pin_memory()
     lab_h = lab_d.cpu().pin_memory()
 
     def eager_step(img, labels):
+        if not train:
+            with torch.no_grad():
+                return net(img)[:, 0].sum()          # a scalar of the result (read back in the e2e leg)
         opt.zero_grad()
-        loss = vitb200.functional.cross_entropy(net(img), labels)
+        loss = forward_loss(net, img, labels)
         loss.backward()
         opt.step()
-        sched.step()
+        if sched is not None:
+            sched.step()
         return loss
 
     graphed = None
-    # One CUDA graph per step: fwd + bwd (+ ONE gradient all-reduce on the capture stream at N > 1) + SGD.
+    # One CUDA graph per step: fwd + bwd (+ ONE gradient all-reduce on the capture stream at N > 1) + optimizer.
     if graph_ddp:
         graphed = vitb200.train.GraphedDataParallelStep(net, opt, img_d, lab_d)
-    elif not args.no_graph and (world == 1 or graph_one):
-        try:   # the whole step (fwd + bwd + all-reduce + SGD) as one replayable CUDA graph
-            graphed = vitb200.train.GraphedTrainStep(net, opt, img_d, lab_d, data_parallel=graph_one)
+    elif train and not args.no_graph and (world == 1 or graph_one):
+        try:   # the whole step (fwd + bwd + all-reduce + optimizer) as one replayable CUDA graph
+            graphed = vitb200.train.GraphedTrainStep(net, opt, img_d, lab_d, data_parallel=graph_one,
+                                                     forward_loss=forward_loss if kind == "resvit_train" else None)
         except Exception as exc:  # noqa: BLE001 - report and measure eagerly rather than die
             if world > 1:
                 raise     # the eager fallback below has no gradient exchange
@@ -332,7 +423,8 @@ def main():
     if graphed is not None:
         def step(img, labels):          # src/train.py:19-25: ... optimizer.step(); lr_scheduler.step()
             loss = graphed(img, labels)
-            sched.step()
+            if sched is not None:
+                sched.step()
             return loss
     else:
         step = eager_step
@@ -399,20 +491,21 @@ def main():
         ips = world * B * args.steps / (ms / 1e3)
         ips_e2e = world * B * args.steps / (ms_e2e / 1e3)
         ach = gemm_flop / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
-        step_tf = ips / world * GFLOP_PER_IMG_TRAIN / 1e3
+        step_tf = ips / world * gflop_ref / 1e3
+        step_tf_exec = ips / world * gflop_exec / 1e3
         out = {
-            "metric": "train images/sec", "value": ips, "unit": "images/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD % B,
-                       "parallelism": "dp%d" % world, "global_batch": world * B,
+            "metric": "train images/sec" if train else "inference images/sec", "value": ips, "unit": "images/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": cfg["workload"] % B, "baseline_config": args.config,
+                       "parallelism": ("dp%d" % world) if train else ("%d replicas" % world), "global_batch": world * B,
                        "launch": ("fwd+bwd graph, one eager all-reduce, optimizer graph" if graph_ddp else "one CUDA graph per step")
                        if graphed is not None else "eager (Python launches)",
-                       "grad_exchange": (None if world == 1 else
+                       "grad_exchange": (None if (world == 1 or not train) else
                                          {"graph1": "one NCCL all-reduce (AVG) of the flat fp32 gradient buffer, a node of the step graph",
                                           "graph2": "one eager NCCL all-reduce between two graphs",
                                           "overlap": "per-block NCCL all-reduces on a side stream, overlapped with backward"}[args.ddp_mode]),
-                       "l2": "per-step working set (~8 GB of activations) exceeds the 126 MB L2; no flush needed",
+                       "l2": "per-step working set (GBs of activations) exceeds the 126 MB L2; no flush needed",
                        "weights": "reference constructor, seed 0, attention/pos weights x0.02 (SURVEY F5)"},
             "clocks": clocks,
             "e2e": {"value": ips_e2e, "unit": "images/s", "h2d_bytes_per_step": img_h.numel() * 4 + lab_h.numel() * 8,
@@ -421,18 +514,26 @@ def main():
             "roofline": {"bound": "tensor", "kernel": "tcgen05 GEMMs: vitb_gemm_kernel + vitb_wgrad_pair_kernel (cta_group::2)", "achieved": ach,
                          "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tflops_sustained"],
                          "peak_source": pk["source"] + " sustained cuBLAS bf16", "traffic": gemm_traffic(),
+                         "traffic_source": "profiles/gemm_traffic_r02.json (ncu dram__bytes over the GEMM launches of one step of this "
+                                           "command; null when the capture is missing)",
                          "algorithmic_bytes_per_launch": gemm_bytes / max(1, len(recs)),
                          "flop_per_launch": gemm_flop / max(1, len(recs)),
                          "gemm_share_of_step": (gemm_ms / 2) / (ms / args.steps), "launches_timed": len(recs)},
-            "roofline_step": {"achieved": step_tf, "unit": "TFLOP/s per GPU (105.379 GFLOP/img)",
+            "roofline_step": {"achieved": step_tf, "unit": "TFLOP/s per GPU at %.3f GFLOP/img (the reference algorithm's dense "
+                                                             "contractions, SURVEY.md App. A)" % gflop_ref,
                               "frac_of_sustained": step_tf / pk["tflops_sustained"],
-                              "frac_of_burst": step_tf / pk["tflops_burst"], "frac_of_spec_2250": step_tf / 2250.0},
+                              "frac_of_burst": step_tf / pk["tflops_burst"], "frac_of_spec_2250": step_tf / 2250.0,
+                              "executed": {"achieved": step_tf_exec, "gflop_per_img": gflop_exec,
+                                           "frac_of_sustained": step_tf_exec / pk["tflops_sustained"],
+                                           "note": "FLOPs this repo executes: the last block runs on the class-token row only"}},
         }
-        if world == 1 and not args.no_cpu_baseline:
-            cips, csec, threads, kind = cpu_train_steps(2, 1)
-            out["cpu_baseline"] = {"value": cips, "unit": "images/s", "cores": threads, "kind": kind,
+        if not train:
+            out["latency_ms_per_batch"] = ms / args.steps
+        if world == 1 and not args.no_cpu_baseline and args.config == "c2":
+            cips, csec, threads, kind_ = cpu_train_steps(2, 1)
+            out["cpu_baseline"] = {"value": cips, "unit": "images/s", "cores": threads, "kind": kind_,
                                    "sample": "2 timed steps of batch %d after 1 warm-up (%s, torch CPU fp32)"
-                                             % (CPU_SAMPLE_BATCH, "unmodified reference src/model.py, baseline/_ref" if kind == "reference"
+                                             % (CPU_SAMPLE_BATCH, "unmodified reference src/model.py, baseline/_ref" if kind_ == "reference"
                                                 else "oracle port")}
         emit(out)
     if world > 1:

@@ -170,6 +170,12 @@ typedef struct vitb_attn_params {
   int64_t dq_batch_stride, dq_row_stride;
   int64_t dk_batch_stride, dk_row_stride;
   int64_t dv_batch_stride, dv_row_stride;
+  /* optional [H * head_dim] fp32, ACCUMULATED (+=): column sums over all (image, token) rows of dq / dk / dv — the bias
+   * gradients of the q / k / v projections, taken from the fp32 accumulators while they are drained (vitb_attn_bwd_ws
+   * only; the other backward kernels ignore them — check vitb_attn_ws_supported and fall back to vitb_colsum3). */
+  float* dq_colsum;
+  float* dk_colsum;
+  float* dv_colsum;
 } vitb_attn_params;
 
 int vitb_attn_supported_tc(int head_dim, int Nq, int Nk);      /* forward AND backward on tcgen05 (head_dim 64, <= 256 tokens) */

@@ -185,6 +185,19 @@ def test_attn_ws_persistent_kernels(N, B, H, monkeypatch):
     assert rel_l2(res["1"][0], res["0"][0]) < 4e-3
     assert rel_l2(res["1"][1], res["0"][1]) < 1e-5
     assert rel_l2(res["1"][2], res["0"][2]) < 6e-3
+    # the persistent backward also accumulates the column sums of dq / dk / dv (projection bias gradients), in fp32
+    assert vitb200.ops.attn_bwd_fuses_colsums(dh, N, N, torch.bfloat16)
+    cs = [torch.full((D,), 0.5, device="cuda") for _ in range(3)]
+    o, lse, _ = res["1"]
+    dqkv = torch.empty_like(qkv)
+    vitb200.ops.attn_bwd(do, q, k, v, o, lse, H, dq=dqkv[:, :, :D], dk=dqkv[:, :, D:2 * D], dv=dqkv[:, :, 2 * D:], colsums=tuple(cs))
+    torch.cuda.synchronize()
+    for i in range(3):
+        part = dqkv[:, :, i * D:(i + 1) * D].float()
+        ref = part.sum((0, 1)) + 0.5
+        # the reference sums bf16-rounded values (2^-9 relative each), the kernel its fp32 accumulators
+        noise = 4.0 * float(part.pow(2).mean().sqrt()) * (B * N * D) ** 0.5 * 2.0 ** -9
+        assert float((cs[i] - ref).norm()) <= 1e-3 * float(ref.norm()) + noise, (i, float((cs[i] - ref).norm()), noise)
     if B * H <= 64:
         qf, kf, vf = (t.float().detach().requires_grad_(True) for t in (q, k, v))
         ro, rlse = _attn_ref(qf, kf, vf, H)

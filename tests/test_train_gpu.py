@@ -173,8 +173,8 @@ def test_graphed_step_follows_onecycle_momentum():
         step(img, lab)
         sched.step()
     torch.cuda.synchronize()
-    for k, v in m.state_dict().items():
-        assert rel_l2(v, w_eager[k]) < 2e-3, (k, rel_l2(v, w_eager[k]))
+    for k, v in m.state_dict().items():   # (the key bias only ever receives rounding noise: softmax is invariant to it)
+        assert grad_close(v, w_eager[k], 2e-3, atol=1e-6), (k, rel_l2(v, w_eager[k]))
 
 
 def test_backward_side_channel_hits_and_survives_a_second_consumer(monkeypatch):

@@ -160,6 +160,7 @@ class AttnParams(C.Structure):
         ("dq_batch_stride", C.c_int64), ("dq_row_stride", C.c_int64),
         ("dk_batch_stride", C.c_int64), ("dk_row_stride", C.c_int64),
         ("dv_batch_stride", C.c_int64), ("dv_row_stride", C.c_int64),
+        ("dq_colsum", C.c_void_p), ("dk_colsum", C.c_void_p), ("dv_colsum", C.c_void_p),
     ]
 
 

@@ -125,6 +125,11 @@ int vitb_make_tmap_nd_bf16(CUtensorMap* out, const void* ptr, int rank, const ui
   return make_tmap(out, ptr, rank, dims, strides_bytes, box, CU_TENSOR_MAP_SWIZZLE_128B, 128u);
 }
 
+int vitb_make_tmap_nd_bf16_sw64(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims,
+                                const uint64_t* strides_bytes, const uint32_t* box) {
+  return make_tmap(out, ptr, rank, dims, strides_bytes, box, CU_TENSOR_MAP_SWIZZLE_64B, 64u);
+}
+
 int vitb_make_tmap_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer,
                            uint64_t outer_stride_bytes, uint32_t box_inner, uint32_t box_outer) {
   uint64_t dims[2] = {inner, outer};

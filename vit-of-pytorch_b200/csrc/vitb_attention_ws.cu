@@ -44,9 +44,12 @@ struct WsParams {
   int qtiles;     // 128-query tiles per head (1 or 2)
   int ktiles;     // 128-key tiles per head (backward)
   int total;      // work items: forward (head, query tile) pairs; backward heads
+  int s_stride;   // forward: TMEM columns between the two groups' S buffers
+  int o_col;      // forward: TMEM column of the shared O accumulator, or -1: O overwrites the first 64 columns of S
   float scale;       // 1/sqrt(dh)
   float scale_log2;  // scale * log2(e)
   float* lse;     // [B,H,N]
+  float* colsum[3];   // backward, optional: += column sums of dV, dK, dQ ([H * 64] fp32 each; index = accumulator kind)
 };
 
 // UMMA shared-memory descriptors are built once per buffer; k-steps advance the 14-bit start-address field (16-byte
@@ -60,22 +63,30 @@ __device__ __forceinline__ uint64_t desc_mnmajor(uint32_t addr, uint32_t lbo) { 
 constexpr int kFwdThreads = 576;         // warps 0-15: two softmax groups of 8; warp 16: TMA producer; warp 17: tcgen05 issuer
 enum FwdBar { FB_K = 0, FB_V = 1, FB_Q = 2 /*[2]*/, FB_S = 4 /*[2]*/, FB_P = 6 /*[2] 256*/, FB_O = 8 /*[2]*/, FB_D = 10 /*[2] 256*/, FB_COUNT = 12 };
 
-// W (16 or 32) score columns of this thread's row, already in registers -> p = exp2(s*c - m*c) -> row-sum partial,
-// bf16 -> the 128B-swizzled P image (keys c .. c+W-1 of row r).  MASK: columns >= n_valid (relative to the chunk) are
-// padding keys -> p = 0.
-template <int W, bool MASK>
-__device__ __forceinline__ void softmax_chunk(const uint32_t (&v)[32], uint64_t sc2, uint64_t nm2, int n_valid, uint64_t& sum2a,
+// Padding keys (columns N .. NK-1, at most 15, all inside the last 16-key unit) are switched off by ADDING a register
+// vector of 0 / -inf to the scores of that unit: exp2(-inf) = 0 and max(-inf, .) ignore them without a compare + select
+// per element (the first version of this kernel spent as many instructions on its one masked chunk as on seven plain ones).
+__device__ __forceinline__ void add_mask16(uint32_t* v, const uint64_t (&am)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float x0, x1;
+    upk2(add2(pk2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), am[j]), x0, x1);
+    v[2 * j] = __float_as_uint(x0);
+    v[2 * j + 1] = __float_as_uint(x1);
+  }
+}
+
+// W (16 or 32) score columns of this thread's row, already in registers (padding already at -inf) ->
+// p = exp2(s*c - m*c) -> row-sum partial, bf16 -> the 128B-swizzled P image (keys c .. c+W-1 of row r).
+template <int W>
+__device__ __forceinline__ void softmax_chunk(const uint32_t (&v)[32], uint64_t sc2, uint64_t nm2, uint64_t& sum2a,
                                               uint64_t& sum2b, uint32_t image, int r, int rx, int c) {
   uint32_t pk[W / 2];
 #pragma unroll
   for (int j = 0; j < W / 2; ++j) {
     float x0, x1;
     upk2(fma2(pk2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), sc2, nm2), x0, x1);
-    float e0 = ex2_approx(x0), e1 = ex2_approx(x1);
-    if (MASK) {
-      e0 = (2 * j < n_valid) ? e0 : 0.f;
-      e1 = (2 * j + 1 < n_valid) ? e1 : 0.f;
-    }
+    const float e0 = ex2_approx(x0), e1 = ex2_approx(x1);
     const uint64_t e2 = pk2(e0, e1);
     if (j & 1) sum2b = add2(sum2b, e2); else sum2a = add2(sum2a, e2);
     pk[j] = pack_bf16x2(e0, e1);
@@ -96,10 +107,7 @@ attn_fwd_ws(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
             const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
             const __grid_constant__ WsParams a) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  if ((smem_u32(smem) & 1023u) != 0) {  // SWIZZLE_128B tiles need 1024-byte aligned bases
-    if (threadIdx.x == 0) printf("attn_fwd_ws: dynamic shared memory base 0x%x is not 1024-byte aligned\n", smem_u32(smem));
-    __trap();
-  }
+  if ((smem_u32(smem) & 1023u) != 0) __trap();   // SWIZZLE_128B tiles need 1024-byte aligned bases
   const int NK = a.NK;
   const int kv_bytes = NK * 128;                 // [NK keys x 64] bf16, 128B-swizzled rows
   const int pchunks = (NK + 63) >> 6;            // 64-key chunks of a P image
@@ -170,36 +178,67 @@ attn_fwd_ws(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     }
   } else if (warp == 17) {
     // =============================== tcgen05 issuer ===============================
+    // Two independent cursors — the next O = P V and the next S = Q K^T — each issued as soon as ITS operands are
+    // there (non-blocking probes).  With up to 224 keys the two S buffers (2 x 224 columns) leave room for one shared O
+    // accumulator (64 columns): S(i+2) then only needs P(i) written (S(i) consumed), not O(i) drained, so it is in
+    // flight while the group still waits for and drains O(i).  Wider rows fall back to O overwriting S's first columns.
     if (lane == 0) {
       const uint32_t idesc_s = umma_idesc_bf16(128, NK, false, false);
       const uint32_t idesc_o = umma_idesc_bf16(128, DH, false, true);
       const int nks = NK >> 4;
+      const bool split = a.o_col >= 0;
       const uint64_t dK = desc_kmajor(sK_u), dV = desc_mnmajor(sV_u, 8192);
-      uint32_t k_heads = 0, v_heads = 0;           // heads whose K / V have been waited for
-      for (int i = 0; i <= n; ++i) {
-        if (i < n) {                               // S(i) = Q K^T into this group's TMEM buffer
-          const int t = t_begin + i, head = t / QT, qt = t - head * QT, g = i & 1;
-          if (i == 0 || qt == 0) { mbar_wait_backoff(bar(FB_K), k_heads & 1u, 32); ++k_heads; }
-          mbar_wait_backoff(bar(FB_Q + g), static_cast<uint32_t>((i >> 1) & 1), 32);
-          if (i >= 2) mbar_wait_backoff(bar(FB_D + g), static_cast<uint32_t>(((i - 2) >> 1) & 1), 32);   // O(i-2) drained
-          tc_fence_after();
-          const uint32_t d = tmem_base + static_cast<uint32_t>(g * 256);
-          const uint64_t dQ = desc_kmajor(sQ_u + g * kChunkBytes);
-#pragma unroll
-          for (int k = 0; k < DH / 16; ++k) umma_bf16_ss(d, dQ + 2 * k, dK + 2 * k, idesc_s, k > 0 ? 1u : 0u);
-          umma_commit(bar(FB_S + g));
+      uint32_t k_heads = 0, v_heads = 0;           // heads whose K / V have been consumed
+      int s_next = 0, pv_next = 0;
+      bool s_k = false, s_q = false, s_d = false, p_v = false, p_p = false, p_o = false;
+      long long t_idle = clock64();
+      while (pv_next < n) {
+        bool did = false;
+        if (pv_next < s_next) {                            // O(j) = P(j) V
+          const int j = pv_next, t = t_begin + j, head = t / QT, qt = t - head * QT, g = j & 1;
+          const bool newh = (j == 0 || qt == 0);
+          if (!p_v) p_v = !newh || mbar_try_wait(bar(FB_V), v_heads & 1u);
+          if (!p_p) p_p = mbar_try_wait(bar(FB_P + g), static_cast<uint32_t>((j >> 1) & 1));
+          if (!p_o) p_o = !split || j == 0 || mbar_try_wait(bar(FB_D + ((j - 1) & 1)), static_cast<uint32_t>(((j - 1) >> 1) & 1));
+          if (p_v && p_p && p_o) {
+            if (newh) ++v_heads;
+            tc_fence_after();
+            const uint32_t d = tmem_base + static_cast<uint32_t>(split ? a.o_col : g * a.s_stride);
+            const uint64_t dP = desc_kmajor(sP_u + g * p_bytes);
+            for (int t16 = 0; t16 < nks; ++t16)    // 16 keys per step: 32 B inside a 64-key chunk, 16 KiB between chunks
+              umma_bf16_ss(d, dP + static_cast<uint64_t>((t16 >> 2) * (kChunkBytes >> 4) + (t16 & 3) * 2), dV + static_cast<uint64_t>(t16 * 128),
+                           idesc_o, t16 > 0 ? 1u : 0u);
+            umma_commit(bar(FB_O + g));
+            ++pv_next;
+            p_v = p_p = p_o = false;
+            did = true;
+          }
         }
-        if (i >= 1) {                              // O(j) = P(j) V over the first 64 columns of S(j)'s buffer
-          const int j = i - 1, t = t_begin + j, head = t / QT, qt = t - head * QT, g = j & 1;
-          if (j == 0 || qt == 0) { mbar_wait_backoff(bar(FB_V), v_heads & 1u, 32); ++v_heads; }
-          mbar_wait_backoff(bar(FB_P + g), static_cast<uint32_t>((j >> 1) & 1), 32);
-          tc_fence_after();
-          const uint32_t d = tmem_base + static_cast<uint32_t>(g * 256);
-          const uint64_t dP = desc_kmajor(sP_u + g * p_bytes);
-          for (int t16 = 0; t16 < nks; ++t16)      // 16 keys per step: 32 B inside a 64-key chunk, 16 KiB between chunks
-            umma_bf16_ss(d, dP + static_cast<uint64_t>((t16 >> 2) * (kChunkBytes >> 4) + (t16 & 3) * 2), dV + static_cast<uint64_t>(t16 * 128),
-                         idesc_o, t16 > 0 ? 1u : 0u);
-          umma_commit(bar(FB_O + g));
+        if (s_next < n && (split || s_next <= pv_next + 1)) {   // S(i) into group (i & 1)'s buffer
+          const int i = s_next, t = t_begin + i, head = t / QT, qt = t - head * QT, g = i & 1;
+          const bool newh = (i == 0 || qt == 0);
+          if (!s_k) s_k = !newh || mbar_try_wait(bar(FB_K), k_heads & 1u);
+          if (!s_q) s_q = mbar_try_wait(bar(FB_Q + g), static_cast<uint32_t>((i >> 1) & 1));
+          // the buffer is free once S(i-2) has been read (split: P(i-2) written) / once O(i-2), which overwrote it, is drained
+          if (!s_d) s_d = i < 2 || mbar_try_wait(bar((split ? FB_P : FB_D) + g), static_cast<uint32_t>(((i - 2) >> 1) & 1));
+          if (s_k && s_q && s_d) {
+            if (newh) ++k_heads;
+            tc_fence_after();
+            const uint32_t d = tmem_base + static_cast<uint32_t>(g * a.s_stride);
+            const uint64_t dQ = desc_kmajor(sQ_u + g * kChunkBytes);
+#pragma unroll
+            for (int k = 0; k < DH / 16; ++k) umma_bf16_ss(d, dQ + 2 * k, dK + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+            umma_commit(bar(FB_S + g));
+            ++s_next;
+            s_k = s_q = s_d = false;
+            did = true;
+          }
+        }
+        if (did) {
+          t_idle = clock64();
+        } else {
+          __nanosleep(20);
+          if (clock64() - t_idle > 4000000000ll) __trap();   // a protocol bug must trap, never hang the GPU box
         }
       }
     }
@@ -210,7 +249,9 @@ attn_fwd_ws(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     const int r = (warp & 3) * 32 + lane;          // query row within the tile == TMEM lane
     const int rx = r & 7;
     const bool elected = (r == 0 && half == 0);
-    const uint32_t trow = tmem_base + static_cast<uint32_t>(g * 256) + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    const uint32_t tquad = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t trow = tmem_base + static_cast<uint32_t>(g * a.s_stride) + tquad;
+    const uint32_t torow = a.o_col >= 0 ? tmem_base + static_cast<uint32_t>(a.o_col) + tquad : trow;   // where O(i) lands
     const uint32_t sPg = sP_u + g * p_bytes;
     float* red_max = red + g * 512;                // [2 halves][128]
     float* red_sum = red_max + 256;
@@ -218,31 +259,34 @@ attn_fwd_ws(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     const int nunits = NK >> 4, umid = (nunits + 1) >> 1;
     const int cb = half ? umid * 16 : 0, ce = half ? NK : umid * 16;
     const uint64_t sc2 = pk2(a.scale_log2);
+    // additive mask of the last 16-key unit (0 for keys < N, -inf for padding); mask_c0 < 0: no padding
+    const int mask_c0 = (a.N < NK) ? NK - 16 : -1;
+    uint64_t am[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      am[j] = pk2((NK - 16 + 2 * j < a.N) ? 0.f : -INFINITY, (NK - 16 + 2 * j + 1 < a.N) ? 0.f : -INFINITY);
     for (int i = g; i < n; i += 2) {
       const uint32_t ph = static_cast<uint32_t>((i >> 1) & 1);
       const int t = t_begin + i, head = t / QT, qt = t - head * QT;
       const int b = head / a.H, h = head - b * a.H;
-      mbar_wait(bar(FB_S + g), ph);
+      mbar_wait_backoff(bar(FB_S + g), ph, 20);
       tc_fence_after();
-      // pass 1: row max over this thread's valid keys
+      // pass 1: row max over this thread's keys
       float mx = -INFINITY;
       for (int c = cb; c < ce; c += 32) {
         uint32_t v[32];
         if (c + 32 <= ce) {
           tmem_ld_32x32b_x32(trow + c, v);
           tmem_ld_wait();
-          if (c + 32 <= a.N) {
+          if (c + 16 == mask_c0) add_mask16(v + 16, am);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, (c + j < a.N) ? __uint_as_float(v[j]) : -INFINITY);
-          }
+          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
         } else {
           tmem_ld_32x32b_x16(trow + c, reinterpret_cast<uint32_t(&)[16]>(v));
           tmem_ld_wait();
+          if (c == mask_c0) add_mask16(v, am);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) mx = fmaxf(mx, (c + j < a.N) ? __uint_as_float(v[j]) : -INFINITY);
+          for (int j = 0; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
         }
       }
       red_max[half * 128 + r] = mx;
@@ -258,12 +302,13 @@ attn_fwd_ws(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         if (c + 32 <= ce) {
           tmem_ld_32x32b_x32(trow + c, v);
           tmem_ld_wait();
-          if (c + 32 <= a.N) softmax_chunk<32, false>(v, sc2, nm2, 32, sum2a, sum2b, sPg, r, rx, c);
-          else softmax_chunk<32, true>(v, sc2, nm2, a.N - c, sum2a, sum2b, sPg, r, rx, c);
+          if (c + 16 == mask_c0) add_mask16(v + 16, am);
+          softmax_chunk<32>(v, sc2, nm2, sum2a, sum2b, sPg, r, rx, c);
         } else {
           tmem_ld_32x32b_x16(trow + c, reinterpret_cast<uint32_t(&)[16]>(v));
           tmem_ld_wait();
-          softmax_chunk<16, true>(v, sc2, nm2, a.N - c, sum2a, sum2b, sPg, r, rx, c);
+          if (c == mask_c0) add_mask16(v, am);
+          softmax_chunk<16>(v, sc2, nm2, sum2a, sum2b, sPg, r, rx, c);
         }
       }
       float s0, s1, s2, s3;
@@ -275,15 +320,29 @@ attn_fwd_ws(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       tc_fence_before();
       mbar_arrive(bar(FB_P + g));
       // O = P V
-      mbar_wait(bar(FB_O + g), ph);
+      mbar_wait_backoff(bar(FB_O + g), ph, 20);
       tc_fence_after();
       uint32_t o[32];
-      tmem_ld_32x32b_x32(trow + static_cast<uint32_t>(half * 32), o);   // this thread's 32 of the 64 head-dim columns
+      tmem_ld_32x32b_x32(torow + static_cast<uint32_t>(half * 32), o);   // this thread's 32 of the 64 head-dim columns
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(bar(FB_D + g));                  // the buffer may receive S(i+2)
+      mbar_arrive(bar(FB_D + g));                  // O has been read: the accumulator may be overwritten
       sum += red_sum[(half ^ 1) * 128 + r];
-      stage_row32_bf16(sPg, r, half, o, 1.0f / sum);   // the P image is dead: the P V MMAs have retired
+      {                                            // O / sum -> bf16 -> staging tile (the P image is dead: P V has retired)
+        const uint64_t inv2 = pk2(1.0f / sum);
+        const uint32_t row_addr = sPg + static_cast<uint32_t>(r * 128);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          uint32_t w[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float y0, y1;
+            upk2(mul2(pk2(__uint_as_float(o[8 * u + 2 * j]), __uint_as_float(o[8 * u + 2 * j + 1])), inv2), y0, y1);
+            w[j] = pack_bf16x2(y0, y1);
+          }
+          st_shared_v4(row_addr + static_cast<uint32_t>(((half * 4 + u) ^ rx) << 4), w[0], w[1], w[2], w[3]);
+        }
+      }
       const int row = qt * 128 + r;
       if (half == 0 && row < a.N && a.lse) a.lse[(static_cast<long long>(b) * a.H + h) * a.N + row] = mx * a.scale + logf(sum);
       fence_proxy_async_smem();
@@ -315,24 +374,83 @@ enum BwdBar {
   BB_DVDR = 16 /*256: dV accumulator drained*/, BB_DKDR = 17 /*256*/, BB_DQDR = 18 /*[2] 256*/, BB_COUNT = 20
 };
 
-// One finished accumulator tile [128 x 64]: TMEM -> registers (the accumulator is released to the issuer) -> bf16
-// staging tile -> TMA store.  Called by all 256 CUDA-core threads; kept out of line (six call sites per head, and the
-// instruction cache is what the first version of this kernel was short of).
-__device__ __noinline__ void drain_tile(uint32_t taddr, uint32_t drained_bar, float scale, const CUtensorMap* tm,
-                                        uint32_t stage, int r, int half, bool elected, int col, int row0, int b) {
+// One finished accumulator tile [128 x 64]: TMEM -> registers (the accumulator is released to the issuer) -> bf16 ->
+// TMA store.  Every warp drains its own 32 rows x 32 columns through its own 2 KiB 64B-swizzled staging tile and its
+// own bulk-store group: no CTA-wide barrier (the first versions synchronised all eight warps twice per drain, 12 times
+// per head: 15 % of the warp samples sat there).  Inlined at three places only (see `drain` in the kernel).
+__device__ __forceinline__ void drain_warp(uint32_t taddr, uint32_t drained_bar, const CUtensorMap* tm, uint32_t stage_w,
+                                        int lane, int col, int row0, int b, float* colsum, int rows_valid) {
   uint32_t v[32];
-  tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(half * 32), v);
+  tmem_ld_32x32b_x32(taddr, v);
   tmem_ld_wait();
   tc_fence_before();
   mbar_arrive(drained_bar);
-  if (elected) bulk_wait_read<0>();            // the previous store has finished reading the staging tile
-  named_bar_sync(1, 256);
-  stage_row32_bf16(stage, r, half, v, scale);
+  if (colsum != nullptr) {   // bias gradient of the projection: this warp's 32 rows x 32 columns summed over the rows
+    float f[32];
+    const bool row_ok = row0 + lane < rows_valid;      // rows past the token count hold padding (dK / dV: garbage)
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = row_ok ? __uint_as_float(v[j]) : 0.f;
+    const float sum = warp_transpose_sum32(f, lane);   // lane j: column j
+    atomicAdd(colsum + col + lane, sum);
+  }
+  if (lane == 0) bulk_wait_read<0>();          // this warp's previous store has finished reading the staging tile
+  __syncwarp();
+  const uint32_t x = (static_cast<uint32_t>(lane) >> 1) & 3u;   // SWIZZLE_64B: 16-byte unit ^= address bits [7,9)
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    st_shared_v4(stage_w + static_cast<uint32_t>(lane) * 64u + ((static_cast<uint32_t>(j) ^ x) << 4),
+                 pack_bf16x2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1])),
+                 pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])),
+                 pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
+                 pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
   fence_proxy_async_smem();
-  named_bar_sync(1, 256);
-  if (elected) {
-    tma_store_3d(tm, stage, col, row0, b);
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_3d(tm, stage_w, col, row0, b);   // rows >= N clipped by the tensor map
     bulk_commit();
+  }
+}
+
+// exp2 of 2 x N packed scores in place (x <- exp2(x * c + nl)), optionally with the padding mask added to the 16 values
+// at `mask_at`, then bf16 -> the 128B-swizzled image at key columns c0 .. c0 + W - 1 of row r
+template <int W>
+__device__ __forceinline__ void p_block(uint32_t* x, uint64_t sc2, uint64_t nl2, bool masked, int mask_at, const uint64_t (&am)[8],
+                                        uint32_t image, uint32_t row_off, int rx, int c0) {
+  if (masked) add_mask16(x + mask_at, am);
+#pragma unroll
+  for (int q = 0; q < W / 8; ++q) {
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float x0, x1;
+      upk2(fma2(pk2(__uint_as_float(x[8 * q + 2 * j]), __uint_as_float(x[8 * q + 2 * j + 1])), sc2, nl2), x0, x1);
+      const float e0 = ex2_approx(x0), e1 = ex2_approx(x1);
+      x[8 * q + 2 * j] = __float_as_uint(e0);
+      x[8 * q + 2 * j + 1] = __float_as_uint(e1);
+      w[j] = pack_bf16x2(e0, e1);
+    }
+    const int c = c0 + 8 * q;
+    st_shared_v4(image + static_cast<uint32_t>((c >> 6) * kChunkBytes) + row_off + static_cast<uint32_t>((((c & 63) >> 3) ^ rx) << 4),
+                 w[0], w[1], w[2], w[3]);
+  }
+}
+// dS = P * (c dP - c D) -> bf16 -> image (the softmax scale c rides in here, so dQ / dK need no scaling when drained)
+template <int W>
+__device__ __forceinline__ void ds_block(const uint32_t* pv, const uint32_t* d, uint64_t c2, uint64_t ndc2, uint32_t image,
+                                         uint32_t row_off, int rx, int c0) {
+#pragma unroll
+  for (int q = 0; q < W / 8; ++q) {
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint64_t t2 = fma2(pk2(__uint_as_float(d[8 * q + 2 * j]), __uint_as_float(d[8 * q + 2 * j + 1])), c2, ndc2);
+      float y0, y1;
+      upk2(mul2(pk2(__uint_as_float(pv[8 * q + 2 * j]), __uint_as_float(pv[8 * q + 2 * j + 1])), t2), y0, y1);
+      w[j] = pack_bf16x2(y0, y1);
+    }
+    const int c = c0 + 8 * q;
+    st_shared_v4(image + static_cast<uint32_t>((c >> 6) * kChunkBytes) + row_off + static_cast<uint32_t>((((c & 63) >> 3) ^ rx) << 4),
+                 w[0], w[1], w[2], w[3]);
   }
 }
 
@@ -343,10 +461,7 @@ attn_bwd_ws(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
             const __grid_constant__ CUtensorMap tmDK, const __grid_constant__ CUtensorMap tmDV,
             const __grid_constant__ WsParams a) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  if ((smem_u32(smem) & 1023u) != 0) {
-    if (threadIdx.x == 0) printf("attn_bwd_ws: dynamic shared memory base 0x%x is not 1024-byte aligned\n", smem_u32(smem));
-    __trap();
-  }
+  if ((smem_u32(smem) & 1023u) != 0) __trap();   // SWIZZLE_128B tiles need 1024-byte aligned bases
   // shared memory: K,V stages [2][K | V] | Q,dO stages [2][Q | dO] | O tile | staging tile | P image (2 chunks) | dS image
   const uint32_t sKV_u = smem_u32(smem);
   const uint32_t sQD_u = sKV_u + 4 * kChunkBytes;
@@ -492,50 +607,59 @@ attn_bwd_ws(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     const int half = warp >> 2;                    // two threads per query row; `half` picks the keys
     const int r = (warp & 3) * 32 + lane;          // query row within the tile == TMEM lane
     const int rx = r & 7;
-    const bool elected = (tid == 0);
     const uint32_t trow = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     const uint32_t row_off = static_cast<uint32_t>(r * 128);
-    float lse2_q0 = 0.f, lse2_q1 = 0.f, d_q0 = 0.f, d_q1 = 0.f;   // per query tile: LSE * log2(e) and D_i of this thread's row
+    const uint32_t stage_w = sStage_u + static_cast<uint32_t>(warp * 2048);   // this warp's 32 x 32 bf16 store tile
+    const int drain_col = half * 32, drain_row = (warp & 3) * 32;             // its corner inside a [128 x 64] tile
+    float lse2_q0 = 0.f, lse2_q1 = 0.f, d_q0 = 0.f, d_q1 = 0.f;   // per query tile: LSE * log2(e) and c * D_i of this thread's row
     // accumulators waiting to be drained: (image, head) and tile they belong to
     bool pend_dv = false, pend_dk = false, pend_dq0 = false, pend_dq1 = false;
     int pend_kv_b = 0, pend_kv_h = 0, pend_kv_kt = 0, pend_dq0_b = 0, pend_dq0_h = 0, pend_dq1_b = 0, pend_dq1_h = 0;
-    const uint64_t sc2 = pk2(a.scale_log2);
+    const uint64_t sc2 = pk2(a.scale_log2), c2 = pk2(a.scale);
+    // additive mask of the last 16-key unit of the last key tile (0 for keys < N, -inf for padding)
+    const int last_valid = a.N - (KT - 1) * 128;                  // keys of the last key tile (1 .. 128)
+    const int last_unit0 = ((last_valid + 15) & ~15) - 16;        // first key of its last unit
+    uint64_t am[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      am[j] = pk2((last_unit0 + 2 * j < last_valid) ? 0.f : -INFINITY, (last_unit0 + 2 * j + 1 < last_valid) ? 0.f : -INFINITY);
 
-    auto drain_dv = [&]() {
-      drain_tile(trow + T_DV, bar(BB_DVDR), 1.0f, &tmDV, sStage_u, r, half, elected, pend_kv_h * DH, pend_kv_kt * 128, pend_kv_b);
-      pend_dv = false;
-    };
-    auto drain_dk = [&]() {
-      drain_tile(trow + T_DK, bar(BB_DKDR), a.scale, &tmDK, sStage_u, r, half, elected, pend_kv_h * DH, pend_kv_kt * 128, pend_kv_b);
-      pend_dk = false;
-    };
-    auto drain_dq0 = [&]() {
-      drain_tile(trow + T_DQ, bar(BB_DQDR), a.scale, &tmDQ, sStage_u, r, half, elected, pend_dq0_h * DH, 0, pend_dq0_b);
-      pend_dq0 = false;
-    };
-    auto drain_dq1 = [&]() {
-      drain_tile(trow + T_DQ + 64u, bar(BB_DQDR + 1), a.scale, &tmDQ, sStage_u, r, half, elected, pend_dq1_h * DH, 128, pend_dq1_b);
-      pend_dq1 = false;
+    // accumulator w: 0 dV, 1 dK, 2 dQ of query tile 0, 3 dQ of query tile 1 (their "drained" barriers are consecutive)
+    auto drain = [&](int w) {
+      const uint32_t tcol = w == 0 ? T_DV : (w == 1 ? T_DK : T_DQ + static_cast<uint32_t>((w - 2) * 64));
+      const CUtensorMap* tm = w == 0 ? &tmDV : (w == 1 ? &tmDK : &tmDQ);
+      const int hh = w < 2 ? pend_kv_h : (w == 2 ? pend_dq0_h : pend_dq1_h);
+      const int bb = w < 2 ? pend_kv_b : (w == 2 ? pend_dq0_b : pend_dq1_b);
+      const int row0 = w < 2 ? pend_kv_kt * 128 : (w - 2) * 128;
+      float* cs = w == 0 ? a.colsum[0] : (w == 1 ? a.colsum[1] : a.colsum[2]);
+      drain_warp(trow + tcol + static_cast<uint32_t>(drain_col), bar(BB_DVDR + w), tm, stage_w, lane, hh * DH + drain_col,
+                 row0 + drain_row, bb, cs, a.N);
+      if (w == 0) pend_dv = false;
+      else if (w == 1) pend_dk = false;
+      else if (w == 2) pend_dq0 = false;
+      else pend_dq1 = false;
     };
 
     int hl = 0, kt = 0, qt = 0, b = h_begin / a.H, h = h_begin - b * a.H;
-    float lse_pref = INFINITY;                     // LSE of this thread's row for the next iteration that starts a query tile
-    if (n > 0 && r < a.N) lse_pref = a.lse[(static_cast<long long>(b) * a.H + h) * a.N + r];
+    // LSE of this thread's row for the next iteration that starts a query tile: requested one iteration ahead and only
+    // touched when that iteration begins, so the load never stalls the pipeline
+    float lse_carry = INFINITY;
+    if (n > 0 && r < a.N) lse_carry = a.lse[(static_cast<long long>(b) * a.H + h) * a.N + r];
     for (int i = 0; i < n; ++i) {
       const int qc = hl * QT + qt;
       const uint32_t ph = static_cast<uint32_t>(i & 1);
+      const float lse_cur = lse_carry;
       // coordinates of the next iteration; its LSE is requested now if it starts a query tile
       int nqt = qt + 1, nkt = kt, nhl = hl, nb = b, nh = h;
       if (nqt == QT) { nqt = 0; if (++nkt == KT) { nkt = 0; ++nhl; if (++nh == a.H) { nh = 0; ++nb; } } }
-      float lse_next = INFINITY;
       if (i + 1 < n && nkt == 0) {
         const int row = nqt * 128 + r;
-        if (row < a.N) lse_next = a.lse[(static_cast<long long>(nb) * a.H + nh) * a.N + row];
+        lse_carry = (row < a.N) ? a.lse[(static_cast<long long>(nb) * a.H + nh) * a.N + row] : INFINITY;
       }
       if (kt == 0) {
         // D_i = rowsum(dO * O) of this query tile from the swizzled tiles
-        mbar_wait(bar(BB_QDO + (qc & 1)), static_cast<uint32_t>((qc >> 1) & 1));
-        mbar_wait(bar(BB_O), static_cast<uint32_t>(qc & 1));
+        mbar_wait_backoff(bar(BB_QDO + (qc & 1)), static_cast<uint32_t>((qc >> 1) & 1), 20);
+        mbar_wait_backoff(bar(BB_O), static_cast<uint32_t>(qc & 1), 20);
         const uint32_t sDO = sQD_u + (qc & 1) * 2 * kChunkBytes + kChunkBytes;
         float part = 0.f;
 #pragma unroll
@@ -545,125 +669,78 @@ attn_bwd_ws(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         }
         red[half * 128 + r] = part;
         named_bar_sync(1, 256);
-        const float di = red[r] + red[128 + r];
+        const float di = (red[r] + red[128 + r]) * a.scale;
         mbar_arrive(bar(BB_OFREE));                // the O tile may be replaced
         named_bar_sync(1, 256);                    // red[] may be rewritten by the next query tile
-        if (qt == 0) { d_q0 = di; lse2_q0 = lse_pref * kLog2e; } else { d_q1 = di; lse2_q1 = lse_pref * kLog2e; }
+        if (qt == 0) { d_q0 = di; lse2_q0 = lse_cur * kLog2e; } else { d_q1 = di; lse2_q1 = lse_cur * kLog2e; }
       }
-      if (nkt == 0) lse_pref = lse_next;
       const float lse2 = qt == 0 ? lse2_q0 : lse2_q1;
-      const float Di = qt == 0 ? d_q0 : d_q1;
-      const int nk_valid = min(128, a.N - kt * 128);          // keys of this tile that exist
-      mbar_wait(bar(BB_S), ph);
-      if (i >= 1) mbar_wait(bar(BB_PFREE), static_cast<uint32_t>((i - 1) & 1));   // dV(i-1) has read the previous P
-      tc_fence_after();
-      const bool full = (nk_valid == 128);
-      const int nunits = (nk_valid + 15) >> 4;                // partial tile: 16-key units carrying at least one key,
-      const int umid = (nunits + 1) >> 1;                     // split between the two halves of a row
-      const int ub = half ? umid : 0, ue = half ? nunits : umid;
+      const float Dc = qt == 0 ? d_q0 : d_q1;
+      // this thread's keys: 32-key pairs go to the halves in turn (pair p -> half p & 1: slot 0 = pair `half`, slot 1 = pair
+      // `half + 2`), an odd last 16-key unit to the half with fewer pairs (its slot 1); only the tile's last unit is masked
+      const int nk_valid = min(128, a.N - kt * 128);
+      const int nunits = (nk_valid + 15) >> 4, npairs = nunits >> 1;
+      const bool part_last = (nk_valid & 15) != 0;
+      const bool s0 = half < npairs;
+      const bool s1p = half + 2 < npairs;
+      const bool s1u = !s1p && (nunits & 1) && ((npairs & 1) == half);
+      const int c_s0 = 32 * half, c_s1 = s1p ? 64 + 32 * half : 16 * (nunits - 1);
+      const bool m0 = s0 && part_last && (2 * half + 1 == nunits - 1);        // the mask applies to the pair's second unit
+      const bool m1p = s1p && part_last && (2 * (half + 2) + 1 == nunits - 1);
+      const bool m1u = s1u && part_last;
       const uint64_t nl2 = pk2(-lse2);
-      uint32_t p[64];                                         // full tile: P of this thread's 64 keys (fp32), kept for dS
+      uint32_t p[64];                                         // P of this thread's keys (fp32), kept for dS
       // ---- P = exp2(S*c - LSE*log2e) -> bf16 -> sP  (rows >= N: LSE = +inf -> 0; padding keys -> 0)
-      if (full) {      // this thread owns the 64 keys of chunk `half`
-        tmem_ld_32x32b_x32(trow + T_S + static_cast<uint32_t>(half * 64), reinterpret_cast<uint32_t(&)[32]>(p[0]));
-        tmem_ld_32x32b_x32(trow + T_S + static_cast<uint32_t>(half * 64 + 32), reinterpret_cast<uint32_t(&)[32]>(p[32]));
-        tmem_ld_wait();
-        const uint32_t prow = sP_u + static_cast<uint32_t>(half * kChunkBytes) + row_off;
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          uint32_t w[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float x0, x1;
-            upk2(fma2(pk2(__uint_as_float(p[8 * u + 2 * j]), __uint_as_float(p[8 * u + 2 * j + 1])), sc2, nl2), x0, x1);
-            const float e0 = ex2_approx(x0), e1 = ex2_approx(x1);
-            p[8 * u + 2 * j] = __float_as_uint(e0);
-            p[8 * u + 2 * j + 1] = __float_as_uint(e1);
-            w[j] = pack_bf16x2(e0, e1);
-          }
-          st_shared_v4(prow + static_cast<uint32_t>((u ^ rx) << 4), w[0], w[1], w[2], w[3]);
-        }
-      } else {
-#pragma unroll 1
-        for (int u = ub; u < ue; ++u) {
-          uint32_t v[16];
-          tmem_ld_32x32b_x16(trow + T_S + static_cast<uint32_t>(u * 16), v);
-          tmem_ld_wait();
-          const int c0 = u * 16;
-          uint32_t w[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float x0, x1;
-            upk2(fma2(pk2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), sc2, nl2), x0, x1);
-            float e0 = ex2_approx(x0), e1 = ex2_approx(x1);
-            e0 = (c0 + 2 * j < nk_valid) ? e0 : 0.f;
-            e1 = (c0 + 2 * j + 1 < nk_valid) ? e1 : 0.f;
-            w[j] = pack_bf16x2(e0, e1);
-          }
-          const uint32_t prow = sP_u + static_cast<uint32_t>((c0 >> 6) * kChunkBytes) + row_off;
-          const int u8 = (c0 & 63) >> 3;
-          st_shared_v4(prow + static_cast<uint32_t>((u8 ^ rx) << 4), w[0], w[1], w[2], w[3]);
-          st_shared_v4(prow + static_cast<uint32_t>(((u8 + 1) ^ rx) << 4), w[4], w[5], w[6], w[7]);
-        }
-      }
+      mbar_wait_backoff(bar(BB_S), ph, 20);
+      if (i >= 1) mbar_wait_backoff(bar(BB_PFREE), static_cast<uint32_t>((i - 1) & 1), 20);   // dV(i-1) has read the previous P
+      tc_fence_after();
+      if (s0) tmem_ld_32x32b_x32(trow + T_S + static_cast<uint32_t>(c_s0), reinterpret_cast<uint32_t(&)[32]>(p[0]));
+      if (s1p) tmem_ld_32x32b_x32(trow + T_S + static_cast<uint32_t>(c_s1), reinterpret_cast<uint32_t(&)[32]>(p[32]));
+      else if (s1u) tmem_ld_32x32b_x16(trow + T_S + static_cast<uint32_t>(c_s1), reinterpret_cast<uint32_t(&)[16]>(p[32]));
+      tmem_ld_wait();
+      if (s0) p_block<32>(p, sc2, nl2, m0, 16, am, sP_u, row_off, rx, c_s0);
+      if (s1p) p_block<32>(p + 32, sc2, nl2, m1p, 16, am, sP_u, row_off, rx, c_s1);
+      else if (s1u) p_block<16>(p + 32, sc2, nl2, m1u, 0, am, sP_u, row_off, rx, c_s1);
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(bar(BB_P));
       // ---- slot after P: the MMAs of iteration i-1 have retired by now; drain what they completed
-      if (i >= 1) { mbar_wait(bar(BB_DSFREE), static_cast<uint32_t>((i - 1) & 1)); tc_fence_after(); }
-      if (pend_dv) drain_dv();
-      else if (qt == 1 && pend_dq0) drain_dq0();
-      else if (qt == 0 && pend_dq1) drain_dq1();
-      // ---- dS / c = P * (dP - D) -> bf16 -> sdS  (the softmax scale c is applied when dQ / dK are drained)
-      mbar_wait(bar(BB_DP), ph);
+      if (i >= 1) { mbar_wait_backoff(bar(BB_DSFREE), static_cast<uint32_t>((i - 1) & 1), 20); tc_fence_after(); }
+      {
+        const int w = pend_dv ? 0 : ((qt == 1 && pend_dq0) ? 2 : ((qt == 0 && pend_dq1) ? 3 : -1));
+        if (w >= 0) drain(w);
+      }
+      // ---- dS = P * c (dP - D) -> bf16 -> sdS
+      mbar_wait_backoff(bar(BB_DP), ph, 20);
       tc_fence_after();
-      if (full) {
-        uint32_t d[64];
-        tmem_ld_32x32b_x32(trow + T_DP + static_cast<uint32_t>(half * 64), reinterpret_cast<uint32_t(&)[32]>(d[0]));
-        tmem_ld_32x32b_x32(trow + T_DP + static_cast<uint32_t>(half * 64 + 32), reinterpret_cast<uint32_t(&)[32]>(d[32]));
-        tmem_ld_wait();
-        const uint64_t nd2 = pk2(-Di);
-        const uint32_t drow = sDS_u + static_cast<uint32_t>(half * kChunkBytes) + row_off;
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          uint32_t w[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint64_t t2 = add2(pk2(__uint_as_float(d[8 * u + 2 * j]), __uint_as_float(d[8 * u + 2 * j + 1])), nd2);
-            float y0, y1;
-            upk2(mul2(pk2(__uint_as_float(p[8 * u + 2 * j]), __uint_as_float(p[8 * u + 2 * j + 1])), t2), y0, y1);
-            w[j] = pack_bf16x2(y0, y1);
-          }
-          st_shared_v4(drow + static_cast<uint32_t>((u ^ rx) << 4), w[0], w[1], w[2], w[3]);
-        }
-      } else {
-#pragma unroll 1
-        for (int u = ub; u < ue; ++u) {
-          uint32_t v[16];
-          tmem_ld_32x32b_x16(trow + T_DP + static_cast<uint32_t>(u * 16), v);
-          const int c0 = u * 16;
-          const uint32_t prow = sP_u + static_cast<uint32_t>((c0 >> 6) * kChunkBytes) + row_off;
-          const uint32_t drow = sDS_u + static_cast<uint32_t>((c0 >> 6) * kChunkBytes) + row_off;
-          const int u8 = (c0 & 63) >> 3;
-          const uint4 pa = ld_shared_v4(prow + static_cast<uint32_t>((u8 ^ rx) << 4));         // this thread's own P (bf16)
-          const uint4 pb = ld_shared_v4(prow + static_cast<uint32_t>(((u8 + 1) ^ rx) << 4));
+      {
+        // one slot at a time: P (64 registers) stays live, and the register file of a 320-thread CTA ends at 168
+        const uint64_t ndc2 = pk2(-Dc);
+        uint32_t d[32];
+        if (s0) {
+          tmem_ld_32x32b_x32(trow + T_DP + static_cast<uint32_t>(c_s0), d);
           tmem_ld_wait();
-          const uint32_t pp[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
-          uint32_t w[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            w[j] = pack_bf16x2(bf16_lo(pp[j]) * (__uint_as_float(v[2 * j]) - Di), bf16_hi(pp[j]) * (__uint_as_float(v[2 * j + 1]) - Di));
-          st_shared_v4(drow + static_cast<uint32_t>((u8 ^ rx) << 4), w[0], w[1], w[2], w[3]);
-          st_shared_v4(drow + static_cast<uint32_t>(((u8 + 1) ^ rx) << 4), w[4], w[5], w[6], w[7]);
+          ds_block<32>(p, d, c2, ndc2, sDS_u, row_off, rx, c_s0);
+        }
+        if (s1p) {
+          tmem_ld_32x32b_x32(trow + T_DP + static_cast<uint32_t>(c_s1), d);
+          tmem_ld_wait();
+          ds_block<32>(p + 32, d, c2, ndc2, sDS_u, row_off, rx, c_s1);
+        } else if (s1u) {
+          tmem_ld_32x32b_x16(trow + T_DP + static_cast<uint32_t>(c_s1), reinterpret_cast<uint32_t(&)[16]>(d));
+          tmem_ld_wait();
+          ds_block<16>(p + 32, d, c2, ndc2, sDS_u, row_off, rx, c_s1);
         }
       }
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(bar(BB_DS));
       // ---- slot after dS
-      if (pend_dk) drain_dk();
-      if (qt == 0 && pend_dq0) drain_dq0();
-      if (qt == 1 && pend_dq1) drain_dq1();
+#pragma unroll 1
+      for (int k = 0; k < 2; ++k) {
+        const int w = k == 0 ? (pend_dk ? 1 : -1) : ((qt == 0 && pend_dq0) ? 2 : ((qt == 1 && pend_dq1) ? 3 : -1));
+        if (w >= 0) drain(w);
+      }
       // what this iteration completes (drained one slot later, once its MMAs have retired)
       if (qt == QT - 1) { pend_dv = pend_dk = true; pend_kv_b = b; pend_kv_h = h; pend_kv_kt = kt; }
       if (kt == KT - 1) {
@@ -673,14 +750,13 @@ attn_bwd_ws(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       qt = nqt; kt = nkt; hl = nhl; b = nb; h = nh;
     }
     if (n > 0) {
-      mbar_wait(bar(BB_DSFREE), static_cast<uint32_t>((n - 1) & 1));
+      mbar_wait_backoff(bar(BB_DSFREE), static_cast<uint32_t>((n - 1) & 1), 20);
       tc_fence_after();
-      if (pend_dv) drain_dv();
-      if (pend_dk) drain_dk();
-      if (pend_dq0) drain_dq0();
-      if (pend_dq1) drain_dq1();
+#pragma unroll 1
+      for (int w = 0; w < 4; ++w)
+        if (w == 0 ? pend_dv : (w == 1 ? pend_dk : (w == 2 ? pend_dq0 : pend_dq1))) drain(w);
     }
-    if (elected) bulk_wait_all();                  // shared memory must outlive the reads of the last store
+    if (lane == 0) bulk_wait_all();                // shared memory must outlive the reads of this warp's last store
   }
 
   tc_fence_before();
@@ -696,6 +772,14 @@ int head_map(CUtensorMap* m, const void* base, int H, int N, int B, long long ro
   uint64_t str[2] = {(uint64_t)row_stride * 2, (uint64_t)batch_stride * 2};
   uint32_t box[3] = {DH, (uint32_t)box_rows, 1};
   return vitb_make_tmap_nd_bf16(m, base, 3, dims, str, box);
+}
+
+// per-warp gradient stores of the backward: 32 rows x 32 head-dim columns, SWIZZLE_64B
+int store_map32(CUtensorMap* m, const void* base, int H, int N, int B, long long row_stride, long long batch_stride) {
+  uint64_t dims[3] = {(uint64_t)H * DH, (uint64_t)N, (uint64_t)B};
+  uint64_t str[2] = {(uint64_t)row_stride * 2, (uint64_t)batch_stride * 2};
+  uint32_t box[3] = {32, 32, 1};
+  return vitb_make_tmap_nd_bf16_sw64(m, base, 3, dims, str, box);
 }
 
 int fwd_smem_bytes(int N) {
@@ -748,6 +832,8 @@ extern "C" int vitb_attn_fwd_ws(const vitb_attn_params* p, void* stream_) {
   a.scale = 1.0f / sqrtf((float)DH);
   a.scale_log2 = a.scale * kLog2e;
   a.lse = p->lse;
+  // TMEM: up to 224 keys -> S buffers at columns 0 and 224, one shared O accumulator at 448; else S at 0 / 256, O over S
+  if (NK <= 224) { a.s_stride = 224; a.o_col = 448; } else { a.s_stride = 256; a.o_col = -1; }
   VITB_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int sms = vitb_num_sms();
   const int grid = a.total < sms ? a.total : sms;
@@ -775,9 +861,9 @@ extern "C" int vitb_attn_bwd_ws(const vitb_attn_params* p, void* stream_) {
   if ((st = head_map(&tv, p->v, p->H, N, p->B, p->v_row_stride, p->v_batch_stride, 128)) != VITB_OK) return st;
   if ((st = head_map(&tdo, p->dout, p->H, N, p->B, p->do_row_stride, p->do_batch_stride, 128)) != VITB_OK) return st;
   if ((st = head_map(&to, p->o, p->H, N, p->B, p->o_row_stride, p->o_batch_stride, 128)) != VITB_OK) return st;
-  if ((st = head_map(&tdq, p->dq, p->H, N, p->B, p->dq_row_stride, p->dq_batch_stride, 128)) != VITB_OK) return st;
-  if ((st = head_map(&tdk, p->dk, p->H, N, p->B, p->dk_row_stride, p->dk_batch_stride, 128)) != VITB_OK) return st;
-  if ((st = head_map(&tdv, p->dv, p->H, N, p->B, p->dv_row_stride, p->dv_batch_stride, 128)) != VITB_OK) return st;
+  if ((st = store_map32(&tdq, p->dq, p->H, N, p->B, p->dq_row_stride, p->dq_batch_stride)) != VITB_OK) return st;
+  if ((st = store_map32(&tdk, p->dk, p->H, N, p->B, p->dk_row_stride, p->dk_batch_stride)) != VITB_OK) return st;
+  if ((st = store_map32(&tdv, p->dv, p->H, N, p->B, p->dv_row_stride, p->dv_batch_stride)) != VITB_OK) return st;
   WsParams a{};
   a.N = N; a.NK = (N + 15) & ~15; a.H = p->H;
   a.qtiles = (N + 127) / 128;
@@ -786,6 +872,7 @@ extern "C" int vitb_attn_bwd_ws(const vitb_attn_params* p, void* stream_) {
   a.scale = 1.0f / sqrtf((float)DH);
   a.scale_log2 = a.scale * kLog2e;
   a.lse = p->lse;
+  a.colsum[0] = p->dv_colsum; a.colsum[1] = p->dk_colsum; a.colsum[2] = p->dq_colsum;
   // 14 tiles of 16 KiB | barriers + TMEM slot | D_i partials
   const int smem = 14 * kChunkBytes + 8 * (BB_COUNT + 2) + 2 * 128 * 4;
   VITB_REQUIRE(smem <= 227 * 1024, VITB_ERR_UNSUPPORTED_SHAPE, "attn_bwd_ws: %d B of shared memory", smem);

@@ -139,15 +139,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 
 // Same, for the single-thread roles of a persistent kernel (TMA producer, tcgen05 issuer): back off between probes so
 // that the polling loop does not take issue slots from the working warps that share the scheduler.
+// (No printf on the timeout path: a call site inside a register-heavy loop makes ptxas spill around it; the trap alone
+// turns a protocol bug into a context error instead of a hung GPU.)
 __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity, unsigned ns) {
   if (mbar_try_wait(bar, parity)) return;
   long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     __nanosleep(ns);
-    if (clock64() - t0 > 4000000000ll) {
-      printf("vitb: mbarrier timeout block %d thread %d bar 0x%x parity %u\n", blockIdx.x, threadIdx.x, bar, parity);
-      __trap();
-    }
+    if (clock64() - t0 > 4000000000ll) __trap();
   }
 }
 
@@ -443,6 +442,34 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// in: v[j] = this lane's row, column j.  out: the sum over the warp's 32 rows of column `lane`.
+__device__ __forceinline__ float warp_transpose_sum32(const float (&v)[32], int lane) {
+  float a[16], b[8], c[4], d[2];
+  const bool h16 = (lane & 16) != 0, h8 = (lane & 8) != 0, h4 = (lane & 4) != 0, h2 = (lane & 2) != 0, h1 = (lane & 1) != 0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float keep = h16 ? v[j + 16] : v[j], send = h16 ? v[j] : v[j + 16];
+    a[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float keep = h8 ? a[j + 8] : a[j], send = h8 ? a[j] : a[j + 8];
+    b[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float keep = h4 ? b[j + 4] : b[j], send = h4 ? b[j] : b[j + 4];
+    c[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const float keep = h2 ? c[j + 2] : c[j], send = h2 ? c[j] : c[j + 2];
+    d[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  const float keep = h1 ? d[1] : d[0], send = h1 ? d[0] : d[1];
+  return keep + __shfl_xor_sync(0xffffffffu, send, 1);
+}
+
 }  // namespace vitb
 
 // ---------------------------------------------------------------------------------------------
@@ -460,3 +487,6 @@ int vitb_make_tmap_2d_f32_sw64(CUtensorMap* out, const void* ptr, uint64_t inner
 // N-D (rank<=5) bf16 tensor, SWIZZLE_128B; strides[] has rank-1 entries (bytes) for dims 1..
 int vitb_make_tmap_nd_bf16(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims,
                            const uint64_t* strides_bytes, const uint32_t* box);
+// Same with SWIZZLE_64B (inner box <= 32 elements): per-warp 32 x 32 bf16 TMA-store staging tiles of the attention backward.
+int vitb_make_tmap_nd_bf16_sw64(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims,
+                                const uint64_t* strides_bytes, const uint32_t* box);

@@ -523,33 +523,6 @@ __device__ __forceinline__ void aux_rows_load(const GemmDev& p, int lane, int ro
     if (row < p.M && col0 + 8 * u < p.N && !VITB_DIAG(16)) dst[u] = __ldg(reinterpret_cast<const uint4*>(ap) + u);
   }
 }
-// in: v[j] = this lane's row, column j.  out: the sum over the warp's 32 rows of column `lane`.
-__device__ __forceinline__ float warp_transpose_sum32(const float (&v)[32], int lane) {
-  float a[16], b[8], c[4], d[2];
-  const bool h16 = (lane & 16) != 0, h8 = (lane & 8) != 0, h4 = (lane & 4) != 0, h2 = (lane & 2) != 0, h1 = (lane & 1) != 0;
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const float keep = h16 ? v[j + 16] : v[j], send = h16 ? v[j] : v[j + 16];
-    a[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-  }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float keep = h8 ? a[j + 8] : a[j], send = h8 ? a[j] : a[j + 8];
-    b[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-  }
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float keep = h4 ? b[j + 4] : b[j], send = h4 ? b[j] : b[j + 4];
-    c[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-  }
-#pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    const float keep = h2 ? c[j + 2] : c[j], send = h2 ? c[j] : c[j + 2];
-    d[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-  }
-  const float keep = h1 ? d[1] : d[0], send = h1 ? d[0] : d[1];
-  return keep + __shfl_xor_sync(0xffffffffu, send, 1);
-}
 __device__ __forceinline__ void epi_rows_mul_aux(const GemmDev& p, const CUtensorMap* tmD, uint32_t tbuf, int& which,
                                                  int lane, int row_base, int col0, const uint32_t (&r)[32],
                                                  const uint4 (&ax)[4]) {

@@ -80,6 +80,11 @@ def gemm(A, B, *, a_mn=False, b_mn=False, out=None, out_dtype=torch.bfloat16, bi
         rows = out_rows if out_rows is not None else M
         out = torch.empty((rows, N), dtype=out_dtype, device=As[0].device)
     if out.dim() == 3:      # grouped output [G, M, Ng]: the G weight gradients of a merged projection
+        if groups == 1 and out.shape[0] > 1 and N % out.shape[0] == 0:
+            # B is one [., N] matrix (the packed dq|dk|dv buffer): its column groups are simply N / G apart
+            groups = out.shape[0]
+            p.n_groups = groups
+            p.b_group_stride = (N // groups) if b_mn else (N // groups) * Bs[0].stride(0)
         if out.shape[0] != groups or groups * out.shape[2] != N or out.stride(2) != 1:
             raise L.VitbError("gemm: a grouped output must be [n_groups, M, N / n_groups] with unit inner stride")
         p.d_group_stride = out.stride(0)
@@ -199,8 +204,10 @@ def attn_fwd_supported_tc(dh, Nq, Nk, dtype):
 
 
 def _attn_ws_enabled():
-    """VITB_ATTN_WS (read per call): 1 = the persistent warp-specialised attention kernels, 0 = one CTA per tile."""
-    return os.environ.get("VITB_ATTN_WS", "0") != "0"
+    """VITB_ATTN_WS (read per call): 1 (default) = the persistent warp-specialised attention kernels (measured on B200,
+    profiles/attn_ws_r02.txt: forward 0.081 -> 0.051 ms, backward 0.183 -> 0.114 ms at B=128, N=197, H=12);
+    0 = one CTA per tile (vitb_attention_tc.cu), kept for A/B runs."""
+    return os.environ.get("VITB_ATTN_WS", "1") != "0"
 
 
 def _attn_params(q, k, v, o, lse, H):
@@ -236,8 +243,15 @@ def attn_fwd(q, k, v, H, *, use_tc=None):
     return o, lse
 
 
-def attn_bwd(dout, q, k, v, o, lse, H, *, use_tc=None, dq=None, dk=None, dv=None):
-    """Returns (dq, dk, dv).  tc: bf16 gradients; simt: fp32 gradients.  dq/dk/dv may be strided views."""
+def attn_bwd_fuses_colsums(dh, Nq, Nk, dtype):
+    """True when attn_bwd(..., colsums=...) accumulates the q / k / v bias gradients itself (the persistent tcgen05 kernel)."""
+    return dtype == torch.bfloat16 and _attn_ws_enabled() and bool(L.vitb_attn_ws_supported(1, dh, Nq, Nk))
+
+
+def attn_bwd(dout, q, k, v, o, lse, H, *, use_tc=None, dq=None, dk=None, dv=None, colsums=None):
+    """Returns (dq, dk, dv).  tc: bf16 gradients; simt: fp32 gradients.  dq/dk/dv may be strided views.
+    colsums = (cq, ck, cv): fp32 [H*dh] buffers that receive += the column sums of dq / dk / dv (the projection bias
+    gradients); only valid when attn_bwd_fuses_colsums(...) — the other kernels would silently ignore them, so it raises."""
     L.require_cuda(dout, q, k, v, o, lse)
     B, Nq, HD = q.shape
     Nk = k.shape[1]
@@ -268,6 +282,13 @@ def attn_bwd(dout, q, k, v, o, lse, H, *, use_tc=None, dq=None, dk=None, dv=None
         fn = L._vitb_attn_bwd_tc2       # experimental key-split CTA-pair kernel (off unless VITB_ATTN_BWD2=1)
     if use_tc and _attn_ws_enabled() and L.vitb_attn_ws_supported(1, dh, Nq, Nk):
         fn = L._vitb_attn_bwd_ws        # persistent warp-specialised kernel
+    if colsums is not None:
+        if fn is not L._vitb_attn_bwd_ws:
+            raise L.VitbError("attn_bwd: colsums are only produced by the persistent tcgen05 kernel (see attn_bwd_fuses_colsums)")
+        for t in colsums:
+            if t.dtype != torch.float32 or t.numel() != HD or not t.is_contiguous():
+                raise L.VitbError("attn_bwd: colsums must be contiguous fp32 [H*dh]")
+        p.dq_colsum, p.dk_colsum, p.dv_colsum = (t.data_ptr() for t in colsums)
     L.check(fn(C.byref(p), L.stream_ptr(q.device)), "vitb_attn_bwd")
     return dq, dk, dv
 
