@@ -170,23 +170,12 @@ typedef struct vitb_attn_params {
   int64_t dq_batch_stride, dq_row_stride;
   int64_t dk_batch_stride, dk_row_stride;
   int64_t dv_batch_stride, dv_row_stride;
-  /* optional [H * head_dim] fp32, ACCUMULATED (+=): column sums over all (image, token) rows of dq / dk / dv — the bias
-   * gradients of the q / k / v projections, taken from the fp32 accumulators while they are drained (vitb_attn_bwd_ws
-   * only; the other backward kernels ignore them — check vitb_attn_ws_supported and fall back to vitb_colsum3). */
-  float* dq_colsum;
-  float* dk_colsum;
-  float* dv_colsum;
 } vitb_attn_params;
 
 int vitb_attn_supported_tc(int head_dim, int Nq, int Nk);      /* forward AND backward on tcgen05 (head_dim 64, <= 256 tokens) */
 int vitb_attn_fwd_supported_tc(int head_dim, int Nq, int Nk);  /* forward only: also 64 < head_dim <= 128, <= 320 tokens (ViT-H/14) */
 int vitb_attn_fwd_tc(const vitb_attn_params* p, void* stream);
 int vitb_attn_bwd_tc(const vitb_attn_params* p, void* stream);
-/* EXPERIMENTAL (not yet run on a GPU; nothing selects it unless VITB_ATTN_BWD2=1): the tcgen05 backward split by KEY tile
- * over the two CTAs of a cluster (256 TMEM columns and ~98 KB of shared memory per CTA -> two CTAs per SM; the dQ partials
- * of the two key tiles meet through distributed shared memory).  Same contract as vitb_attn_bwd_tc, 128 < N <= 256. */
-int vitb_attn_bwd_tc2_supported(int head_dim, int Nq, int Nk);
-int vitb_attn_bwd_tc2(const vitb_attn_params* p, void* stream);
 /* Persistent warp-specialised generation of the tcgen05 kernels (vitb_attention_ws.cu): one resident CTA per SM walks a
  * contiguous range of (image, head[, query tile]) items; a TMA producer warp, a single-thread tcgen05 issuer and eight
  * CUDA-core warps overlap the loads, MMAs and softmax arithmetic of neighbouring items.  Same contract and shapes as
@@ -245,6 +234,18 @@ int vitb_token_mean_bwd(const float* dg, int dtype, int B, int N, int C, int res
  * torch.isin + blend (res-vit/model.py:469-472,487,524) and approximator row selection (:349-368). */
 int vitb_select_rows(const void* a, const void* b, const float* index, uint32_t member_mask, int rows, int cols,
                      int dtype, void* out, void* stream);
+
+/* Res-ViT scalar losses, each one single-CTA kernel that also writes the gradient its backward needs.
+ * vitb_distill_loss — DistillLoss, res-vit/model.py:40-59: *loss_acc += mean((s - t)^2) over [rows, cols] (rows may be
+ *   strided: the class-token rows of student / teacher); d_student [rows, cols] fp32 (optional) = 2 (s - t) / (rows cols).
+ * vitb_active_loss — ActiveLoss, res-vit/model.py:61-85: ratio = mean of probs[b, n >= reserve_initials, j] (probs
+ *   [B, N, L] fp32); *loss = (ratio + *shift_dev - target)^2; d_probs (optional) = 2 (ratio + shift - target) / count on the
+ *   counted entries, 0 on the reserved tokens.  shift_dev (optional device scalar): global-batch mean minus this shard's
+ *   mean under data parallelism. */
+int vitb_distill_loss(const void* student, int64_t s_row_stride, const void* teacher, int64_t t_row_stride, int dtype, int rows,
+                      int cols, float* loss_acc, float* d_student, void* stream);
+int vitb_active_loss(const float* probs, int B, int N, int L, int reserve_initials, float target, const float* shift_dev,
+                     float* ratio_out, float* loss, float* d_probs, void* stream);
 
 /* ---- input transform in front of the encoder --------------------------------------
  * The per-sample CPU work of the reference's loaders — transforms.Compose([Resize(S), RandomHorizontalFlip(),

@@ -121,8 +121,6 @@ def test_bad_arguments_raise():
         tf(torch.zeros((2, 32, 32, 3), dtype=torch.float32, device=DEV))         # not bytes
 
 
-@pytest.mark.skipif(os.environ.get("VITB_TEST_EXPERIMENTAL") != "1",
-                    reason="loader glue written after the round's GPU budget was spent (VITB_TEST_EXPERIMENTAL=1)")
 @pytest.mark.parametrize("patch", [None, 16])
 def test_batch_loader_on_device_matches_reference_loader(patch):
     """DeviceBatchLoader end to end on the GPU (pinned staging, device transform) against the reference loader's batches."""

@@ -99,8 +99,6 @@ def test_b16_geometry_bf16_mode_logits_within_2e2():
         assert abs(n - fp["norm"]) <= 0.1 * fp["norm"] + 1e-5 * grads[k].numel() ** 0.5, (k, n, fp["norm"])
 
 
-@pytest.mark.skipif(os.environ.get("VITB_TEST_EXPERIMENTAL") != "1",
-                    reason="added after the round's GPU budget was spent; first run in the next round (VITB_TEST_EXPERIMENTAL=1)")
 @pytest.mark.parametrize("mode,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
 def test_l16_geometry_train_step_matches_oracle(mode, tol):
     """Config c3's shapes (ViT-L/16: D = 1024, 16 heads of 64, MLP 4096, N = 197) with 2 layers: logits, loss and every

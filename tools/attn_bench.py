@@ -30,11 +30,5 @@ for (B, N, H) in ((128, 197, 12), (64, 197, 16), (128, 50, 12)):
     dqkv = torch.empty_like(qkv)
     f = timeit(lambda: vitb200.ops.attn_fwd(q, k, v, H))
     b = timeit(lambda: vitb200.ops.attn_bwd(do, q, k, v, o, lse, H, dq=dqkv[:, :, :D], dk=dqkv[:, :, D:2 * D], dv=dqkv[:, :, 2 * D:]))
-    b2 = None
-    if N > 128 and os.environ.get("VITB_BENCH_EXPERIMENTAL") == "1":      # experimental key-split CTA-pair backward
-        os.environ["VITB_ATTN_BWD2"] = "1"
-        b2 = timeit(lambda: vitb200.ops.attn_bwd(do, q, k, v, o, lse, H, dq=dqkv[:, :, :D], dk=dqkv[:, :, D:2 * D], dv=dqkv[:, :, 2 * D:]))
-        os.environ["VITB_ATTN_BWD2"] = "0"
     fl = 4.0 * B * H * N * N * 64
-    print("attn B=%d N=%d H=%d: fwd %.3f ms (%.0f TF)  bwd %.3f ms (%.0f TF)%s" % (B, N, H, f, fl / f / 1e9, b, 2.5 * fl / b / 1e9,
-                                       "" if b2 is None else "  bwd key-split pairs %.3f ms" % b2), flush=True)
+    print("attn B=%d N=%d H=%d: fwd %.3f ms (%.0f TF)  bwd %.3f ms (%.0f TF)" % (B, N, H, f, fl / f / 1e9, b, 2.5 * fl / b / 1e9), flush=True)

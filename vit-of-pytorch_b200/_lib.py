@@ -160,7 +160,6 @@ class AttnParams(C.Structure):
         ("dq_batch_stride", C.c_int64), ("dq_row_stride", C.c_int64),
         ("dk_batch_stride", C.c_int64), ("dk_row_stride", C.c_int64),
         ("dv_batch_stride", C.c_int64), ("dv_row_stride", C.c_int64),
-        ("dq_colsum", C.c_void_p), ("dk_colsum", C.c_void_p), ("dv_colsum", C.c_void_p),
     ]
 
 
@@ -172,8 +171,6 @@ vitb_attn_supported_tc = _sig("vitb_attn_supported_tc", [_i, _i, _i])
 vitb_attn_fwd_supported_tc = _sig("vitb_attn_fwd_supported_tc", [_i, _i, _i])
 _vitb_attn_fwd_tc = _sig("vitb_attn_fwd_tc", [C.POINTER(AttnParams), _vp])
 _vitb_attn_bwd_tc = _sig("vitb_attn_bwd_tc", [C.POINTER(AttnParams), _vp])
-vitb_attn_bwd_tc2_supported = _sig("vitb_attn_bwd_tc2_supported", [_i, _i, _i])
-_vitb_attn_bwd_tc2 = _sig("vitb_attn_bwd_tc2", [C.POINTER(AttnParams), _vp])       # experimental key-split CTA pairs
 vitb_attn_ws_supported = _sig("vitb_attn_ws_supported", [_i, _i, _i, _i])
 _vitb_attn_fwd_ws = _sig("vitb_attn_fwd_ws", [C.POINTER(AttnParams), _vp])         # persistent warp-specialised kernels
 _vitb_attn_bwd_ws = _sig("vitb_attn_bwd_ws", [C.POINTER(AttnParams), _vp])
@@ -195,6 +192,8 @@ _vitb_router_decide_bwd = _sig("vitb_router_decide_bwd", [_vp, _vp, _vp, _vp, _v
 _vitb_token_mean_fwd = _sig("vitb_token_mean_fwd", [_vp, _i, _i, _i, _i, _i, _vp, _vp])
 _vitb_token_mean_bwd = _sig("vitb_token_mean_bwd", [_vp, _i, _i, _i, _i, _i, _vp, _vp])
 _vitb_select_rows = _sig("vitb_select_rows", [_vp, _vp, _vp, C.c_uint32, _i, _i, _i, _vp, _vp])
+_vitb_distill_loss = _sig("vitb_distill_loss", [_vp, _i64, _vp, _i64, _i, _i, _i, _vp, _vp, _vp])
+_vitb_active_loss = _sig("vitb_active_loss", [_vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp])
 _vitb_clip_coef = _sig("vitb_clip_coef", [_vp, _f, _vp, _vp, _vp])
 _vitb_resize_tables_host = _sig("vitb_resize_tables_host", [_i, _i, _vp, _vp, _i, C.POINTER(C.c_int)])
 _vitb_image_prep = _sig("vitb_image_prep", [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _i,
@@ -208,5 +207,5 @@ EXPORTED_SYMBOLS = [
     "vitb_sumsq", "vitb_clip_coef", "vitb_gelu_bwd", "vitb_router_decide_fwd", "vitb_router_decide_bwd",
     "vitb_token_mean_fwd", "vitb_token_mean_bwd", "vitb_select_rows", "vitb_colsum3",
     "vitb_resize_tables_host", "vitb_image_prep", "vitb_gemm_diag", "vitb_gemm_diag_mask",
-    "vitb_attn_bwd_tc2_supported", "vitb_attn_bwd_tc2", "vitb_attn_ws_supported", "vitb_attn_fwd_ws", "vitb_attn_bwd_ws",
+    "vitb_distill_loss", "vitb_active_loss", "vitb_attn_ws_supported", "vitb_attn_fwd_ws", "vitb_attn_bwd_ws",
 ]

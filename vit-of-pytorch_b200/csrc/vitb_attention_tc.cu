@@ -686,273 +686,6 @@ attn_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   if (warp == 0) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
-// ================================================================================================
-// backward, key-split CTA pairs — EXPERIMENTAL (vitb_attn_bwd_tc2; written after round 1's GPU budget was spent, not yet
-// run on a GPU; nothing calls it unless VITB_ATTN_BWD2=1).
-//
-// Why: attn_bwd_tc holds S/dP (256) + dK (128) + dV (128) = 512 TMEM columns, so ONE CTA fits an SM and every phase of
-// its chain (MMA group -> CUDA-core pass -> CTA barrier -> next MMA group) runs exposed: 23 % issue utilisation, 14 %
-// tensor pipe (profiles/sass_analysis_r01d.txt).  Here a head is split by KEY tile over the two CTAs of a cluster:
-// CTA `rank` owns keys [128 rank, 128 rank + 128), needs S/dP for its 128 keys only (128 columns, dQ partial reuses
-// them) plus its own dK and dV tiles (64 + 64) = 256 columns and ~98 KB of shared memory -> TWO CTAs per SM, whose
-// chains interleave.  dK / dV are complete per CTA; dQ needs the sum over both key tiles: rank 1 writes its fp32
-// partial tile into rank 0's (by then free) P buffer through distributed shared memory between two cluster barriers,
-// rank 0 adds, scales and stores.  Every MMA runs at N = 128: key rows past the token count are zero-filled by TMA
-// and masked in P, so both ranks execute the same code.
-// Shapes: head_dim 64, 128 < N <= 256 (two query tiles, two key tiles) — ViT-B/L at 224 px.
-// ================================================================================================
-__device__ __forceinline__ void st_cluster_v4(uint32_t cluster_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-// 16-byte unit u (0..15) of row r in the [128 x 64] fp32 exchange tile: units are XOR-swizzled with the row so that
-// the eight lanes of a quarter-warp (consecutive rows, same unit) hit eight different bank groups
-__device__ __forceinline__ uint32_t xchg_unit(int r, int u) { return static_cast<uint32_t>(r * 256 + ((u ^ (r & 7)) << 4)); }
-
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kAttnThreads, 2)
-attn_bwd_tc2(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-             const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
-             const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmDQ,
-             const __grid_constant__ CUtensorMap tmDK, const __grid_constant__ CUtensorMap tmDV,
-             const __grid_constant__ AttnTc a) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint8_t* sK = smem;                         // this CTA's 128 keys x 64, 128B-swizzled (16 KiB)
-  uint8_t* sV = sK + kChunkBytes;
-  uint8_t* sQ = sV + kChunkBytes;             // current query tile; rank 0 stages its dQ tile here afterwards
-  uint8_t* sDO = sQ + kChunkBytes;
-  uint8_t* sP = sDO + kChunkBytes;            // 2 chunks: O tile (chunk 0) -> P -> dS -> (rank 0) partner's dQ partial
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kChunkBytes);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-  float* red = reinterpret_cast<float*>(bars + 16);   // [2 halves][128 rows] partial D_i
-  const uint32_t bar_kv = smem_u32(bars), bar_q = bar_kv + 8, bar_o = bar_kv + 16, bar_s = bar_kv + 24, bar_dp = bar_kv + 32,
-                 bar_dq = bar_kv + 40, bar_fin = bar_kv + 48;
-
-  pdl_trigger();
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int half = warp >> 2;
-  const uint32_t rank = cluster_ctarank();
-  const int h = blockIdx.y, b = blockIdx.z;
-  const int r = (warp & 3) * 32 + lane;
-  const int key0 = static_cast<int>(rank) * 128;
-  const int nk_valid = min(128, max(0, a.N - key0));   // keys of this tile that exist
-  const uint32_t sP_u = smem_u32(sP), sQ_u = smem_u32(sQ), sDO_u = smem_u32(sDO), sK_u = smem_u32(sK), sV_u = smem_u32(sV);
-  const uint32_t sO_u = sP_u;                 // the O tile lands in chunk 0 of the P buffer and dies once D_i is known
-
-  if (tid == 0) {
-    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
-    tma_prefetch_desc(&tmO);
-    for (int i = 0; i < 7; ++i) mbar_init(bar_kv + 8 * i, 1);
-    fence_barrier_init();
-  }
-  __syncthreads();
-  pdl_wait();
-  if (tid == 0) {
-    mbar_arrive_expect_tx(bar_kv, 2 * kChunkBytes);
-    tma_load_3d(&tmK, bar_kv, sK_u, h * DH, key0, b);
-    tma_load_3d(&tmV, bar_kv, sV_u, h * DH, key0, b);
-    mbar_arrive_expect_tx(bar_q, 2 * kChunkBytes);
-    tma_load_3d(&tmQ, bar_q, sQ_u, h * DH, 0, b);
-    tma_load_3d(&tmDO, bar_q, sDO_u, h * DH, 0, b);
-    mbar_arrive_expect_tx(bar_o, kChunkBytes);
-    tma_load_3d(&tmO, bar_o, sO_u, h * DH, 0, b);
-  }
-  if (warp == 0) { __syncwarp(); tmem_alloc(smem_u32(tmem_slot), 256); tmem_relinquish(); }
-  const float* lse_row = a.lse + (static_cast<long long>(b) * a.H + h) * a.N;
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t trow = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-  const uint32_t t_dk = 128u, t_dv = 192u;    // TMEM columns: [0,128) S / dP / dQ partial, [128,192) dK, [192,256) dV
-  constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);
-  constexpr uint32_t idesc_t = umma_idesc_bf16(128, DH, true, true);
-  constexpr uint32_t idesc_dq = umma_idesc_bf16(128, DH, false, true);
-
-#pragma unroll 1
-  for (int qt = 0; qt < 2; ++qt) {
-    const uint32_t ph = qt & 1;
-    const int row0 = qt * 128;
-    const int row = row0 + r;
-    const float lse2 = ((row < a.N) ? lse_row[row] : INFINITY) * 1.4426950408889634f;
-    if (tid == 0) {
-      if (qt == 0) mbar_wait(bar_kv, 0);
-      mbar_wait(bar_q, ph);
-      tc_fence_after();
-#pragma unroll
-      for (int k = 0; k < DH / 16; ++k)  // S = Q K^T (this tile's 128 keys)
-        umma_bf16_ss(tmem_base, umma_smem_desc_sw128(sQ_u + k * 32, 16, 1024), umma_smem_desc_sw128(sK_u + k * 32, 16, 1024),
-                     idesc_s, k > 0 ? 1u : 0u);
-      umma_commit(bar_s);
-    }
-    __syncwarp();
-    // D_i = rowsum(dO * O): this thread's 32 head-dim columns, from the swizzled tiles
-    mbar_wait(bar_q, ph);
-    mbar_wait(bar_o, ph);
-    {
-      float part = 0.f;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const uint32_t off = swz_unit(r, half * 4 + u);
-        part += dot8_bf16(ld_shared_v4(sO_u + off), ld_shared_v4(sDO_u + off));
-      }
-      red[half * 128 + r] = part;
-    }
-    __syncthreads();        // every thread has read the O tile: P may overwrite it; the partial D_i are visible
-    const float Di = red[r] + red[128 + r];
-    mbar_wait(bar_s, ph);
-    tc_fence_after();
-    // P = exp2(S*c - LSE*log2e) for this thread's 64 key columns -> bf16 -> sP (rows >= N: LSE = +inf -> 0; keys >= N -> 0)
-#pragma unroll 1
-    for (int c = 2 * half; c < 2 * half + 2; ++c) {
-      const int c0 = c * 32;
-      const int kc = c0 >> 6, u0 = (c0 & 63) >> 3;
-      if (c0 >= nk_valid) {   // warp-uniform: no key of this tile in the chunk (rank 1 at N = 197 owns 69 keys) -> zeros
-#pragma unroll
-        for (int u = 0; u < 4; ++u) st_shared_v4(sP_u + kc * kChunkBytes + swz_unit(r, u0 + u), 0u, 0u, 0u, 0u);
-        continue;
-      }
-      uint32_t v[32];
-      tmem_ld_32x32b_x32(trow + c0, v);
-      tmem_ld_wait();
-      float pv[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float e = ex2_approx(fmaf(__uint_as_float(v[j]), a.scale_log2, -lse2));
-        pv[j] = (c0 + j < nk_valid) ? e : 0.f;
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        st_shared_v4(sP_u + kc * kChunkBytes + swz_unit(r, u0 + u), pack_bf16x2(pv[8 * u + 0], pv[8 * u + 1]),
-                     pack_bf16x2(pv[8 * u + 2], pv[8 * u + 3]), pack_bf16x2(pv[8 * u + 4], pv[8 * u + 5]),
-                     pack_bf16x2(pv[8 * u + 6], pv[8 * u + 7]));
-    }
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-#pragma unroll
-      for (int k = 0; k < DH / 16; ++k)  // dP = dO V^T  (overwrites S)
-        umma_bf16_ss(tmem_base, umma_smem_desc_sw128(sDO_u + k * 32, 16, 1024), umma_smem_desc_sw128(sV_u + k * 32, 16, 1024),
-                     idesc_s, k > 0 ? 1u : 0u);
-#pragma unroll
-      for (int k = 0; k < 8; ++k)        // dV += P^T dO : A = P^T (MN-major image of sP), B = dO (MN-major), K = 128 query rows
-        umma_bf16_ss(tmem_base + t_dv, umma_smem_desc_sw128(sP_u + k * 2048, kChunkBytes, 1024),
-                     umma_smem_desc_sw128(sDO_u + k * 2048, 8192, 1024), idesc_t, (qt > 0 || k > 0) ? 1u : 0u);
-      umma_commit(bar_dp);   // after dV too: dS is written over P, which the dV MMAs read
-    }
-    __syncwarp();
-    mbar_wait(bar_dp, ph);
-    tc_fence_after();
-    // dS / c = P * (dP - D), in place over P (the softmax scale c is applied when dQ / dK are drained)
-#pragma unroll 1
-    for (int c = 2 * half; c < 2 * half + 2; ++c) {
-      const int c0 = c * 32;
-      if (c0 >= nk_valid) continue;   // P is zero there, so dS = P * (dP - D) already is
-      uint32_t v[32];
-      tmem_ld_32x32b_x32(trow + c0, v);
-      tmem_ld_wait();
-      const int kc = c0 >> 6, u0 = (c0 & 63) >> 3;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const uint32_t addr = sP_u + kc * kChunkBytes + swz_unit(r, u0 + u);
-        const uint4 pp = ld_shared_v4(addr);
-        const float d0 = bf16_lo(pp.x) * (__uint_as_float(v[8 * u + 0]) - Di);
-        const float d1 = bf16_hi(pp.x) * (__uint_as_float(v[8 * u + 1]) - Di);
-        const float d2 = bf16_lo(pp.y) * (__uint_as_float(v[8 * u + 2]) - Di);
-        const float d3 = bf16_hi(pp.y) * (__uint_as_float(v[8 * u + 3]) - Di);
-        const float d4 = bf16_lo(pp.z) * (__uint_as_float(v[8 * u + 4]) - Di);
-        const float d5 = bf16_hi(pp.z) * (__uint_as_float(v[8 * u + 5]) - Di);
-        const float d6 = bf16_lo(pp.w) * (__uint_as_float(v[8 * u + 6]) - Di);
-        const float d7 = bf16_hi(pp.w) * (__uint_as_float(v[8 * u + 7]) - Di);
-        st_shared_v4(addr, pack_bf16x2(d0, d1), pack_bf16x2(d2, d3), pack_bf16x2(d4, d5), pack_bf16x2(d6, d7));
-      }
-    }
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-#pragma unroll
-      for (int t = 0; t < 8; ++t)        // dQ partial = dS K : A = dS (K-major over this tile's keys), B = K (MN-major)
-        umma_bf16_ss(tmem_base, umma_smem_desc_sw128(sP_u + (t >> 2) * kChunkBytes + (t & 3) * 32, 16, 1024),
-                     umma_smem_desc_sw128(sK_u + t * 2048, 8192, 1024), idesc_dq, t > 0 ? 1u : 0u);
-      umma_commit(bar_dq);
-#pragma unroll
-      for (int k = 0; k < 8; ++k)        // dK += dS^T Q
-        umma_bf16_ss(tmem_base + t_dk, umma_smem_desc_sw128(sP_u + k * 2048, kChunkBytes, 1024),
-                     umma_smem_desc_sw128(sQ_u + k * 2048, 8192, 1024), idesc_t, (qt > 0 || k > 0) ? 1u : 0u);
-      umma_commit(bar_fin);
-    }
-    __syncwarp();
-    mbar_wait(bar_dq, ph);
-    tc_fence_after();
-    uint32_t dq[32];                     // this thread's 32 head-dim columns of its row of the dQ partial (fp32)
-    tmem_ld_32x32b_x32(trow + half * 32, dq);
-    tmem_ld_wait();
-    mbar_wait(bar_fin, ph);              // every MMA of this tile has retired: sP, sQ, sDO are free in THIS CTA
-    tc_fence_before();
-    __syncwarp();                        // the cluster barrier is .aligned: converge after the per-thread spin waits
-    cluster_sync_all();                  // ... and in the partner: rank 0's P buffer may now receive rank 1's partial
-    if (rank == 1) {
-      const uint32_t dst = mapa_shared(sP_u, 0);
-#pragma unroll
-      for (int u = 0; u < 8; ++u)
-        st_cluster_v4(dst + xchg_unit(r, half * 8 + u), dq[4 * u], dq[4 * u + 1], dq[4 * u + 2], dq[4 * u + 3]);
-    }
-    __syncwarp();
-    cluster_sync_all();                  // release / acquire: the partial is visible to rank 0
-    tc_fence_after();
-    if (rank == 0) {
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const uint4 o = ld_shared_v4(sP_u + xchg_unit(r, half * 8 + u));
-        dq[4 * u + 0] = __float_as_uint(__uint_as_float(dq[4 * u + 0]) + __uint_as_float(o.x));
-        dq[4 * u + 1] = __float_as_uint(__uint_as_float(dq[4 * u + 1]) + __uint_as_float(o.y));
-        dq[4 * u + 2] = __float_as_uint(__uint_as_float(dq[4 * u + 2]) + __uint_as_float(o.z));
-        dq[4 * u + 3] = __float_as_uint(__uint_as_float(dq[4 * u + 3]) + __uint_as_float(o.w));
-      }
-      stage_row32_bf16(sQ_u, r, half, dq, a.scale);   // the Q tile is dead (bar_fin): it stages the dQ tile
-    }
-    fence_proxy_async_smem();            // generic reads / writes of sP, sQ, sDO precede the async-proxy traffic below
-    __syncthreads();
-    if (tid == 0) {
-      if (rank == 0) {                   // dQ tile [128 x 64] leaves as one TMA store (rows >= N clipped)
-        tma_store_3d(&tmDQ, sQ_u, h * DH, row0, b);
-        bulk_commit();
-      }
-      if (qt == 0) {                     // next query tile into the same buffers
-        if (rank == 0) bulk_wait_read<0>();   // the store above has finished reading sQ
-        mbar_arrive_expect_tx(bar_q, 2 * kChunkBytes);
-        tma_load_3d(&tmQ, bar_q, sQ_u, h * DH, 128, b);
-        tma_load_3d(&tmDO, bar_q, sDO_u, h * DH, 128, b);
-        mbar_arrive_expect_tx(bar_o, kChunkBytes);
-        tma_load_3d(&tmO, bar_o, sO_u, h * DH, 128, b);
-      }
-    }
-  }
-  // dK, dV of this CTA's key tile: TMEM lane = key within the tile; the two threads of a lane split the 64 columns
-  {
-    uint32_t vk[32], vv[32];
-    tc_fence_after();
-    tmem_ld_32x32b_x32(trow + t_dk + static_cast<uint32_t>(half * 32), vk);
-    tmem_ld_32x32b_x32(trow + t_dv + static_cast<uint32_t>(half * 32), vv);
-    tmem_ld_wait();
-    stage_row32_bf16(sP_u, r, half, vk, a.scale);                  // the P buffer is free (rank 0 consumed the partial)
-    stage_row32_bf16(sP_u + kChunkBytes, r, half, vv, 1.0f);
-  }
-  fence_proxy_async_smem();
-  tc_fence_before();
-  __syncthreads();
-  if (tid == 0) {
-    tma_store_3d(&tmDK, sP_u, h * DH, key0, b);                    // rows >= N clipped by the tensor map
-    tma_store_3d(&tmDV, sP_u + kChunkBytes, h * DH, key0, b);
-    bulk_commit();
-    bulk_wait_all();   // rank 0's dQ stores included: shared memory must outlive the reads
-  }
-  if (warp == 0) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem_base, 256); }
-}
-
 int make_head_map(CUtensorMap* m, const void* base, int H, int N, int B, long long row_stride, long long batch_stride,
                   int box_rows, int dh = DH) {
   uint64_t dims[3] = {(uint64_t)H * dh, (uint64_t)N, (uint64_t)B};
@@ -1091,47 +824,5 @@ extern "C" int vitb_attn_bwd_tc(const vitb_attn_params* p, void* stream_) {
   VITB_CUDA_CHECK(vitb_launch(attn_bwd_tc, grid, dim3(kAttnThreads), smem, reinterpret_cast<cudaStream_t>(stream_), tq, tk,
                               tv, tdo, to, tdq, tdk, tdv, a));
   VITB_LAUNCH_CHECK("attn_bwd_tc");
-  return VITB_OK;
-}
-
-extern "C" int vitb_attn_bwd_tc2_supported(int head_dim, int Nq, int Nk) {
-  return head_dim == DH && Nq == Nk && Nk > 128 && Nk <= 256;
-}
-
-// EXPERIMENTAL key-split CTA-pair backward (see attn_bwd_tc2): same contract as vitb_attn_bwd_tc, 128 < N <= 256.
-extern "C" int vitb_attn_bwd_tc2(const vitb_attn_params* p, void* stream_) {
-  int st = vitb_check_device();
-  if (st != VITB_OK) return st;
-  st = check_common(p, "attn_bwd_tc2");
-  if (st != VITB_OK) return st;
-  if (p->B == 0) return VITB_OK;
-  VITB_REQUIRE(p->Nk > 128, VITB_ERR_UNSUPPORTED_SHAPE, "attn_bwd_tc2: N=%d (needs two key tiles: 128 < N <= 256)", p->Nk);
-  VITB_REQUIRE(p->lse && p->dout && p->dq && p->dk && p->dv, VITB_ERR_BAD_ARG, "attn_bwd_tc2: null tensor");
-  VITB_REQUIRE(p->dq_row_stride % 8 == 0 && p->dk_row_stride % 8 == 0 && p->dv_row_stride % 8 == 0 &&
-                   p->do_row_stride % 8 == 0 && p->dq_batch_stride % 8 == 0 && p->dk_batch_stride % 8 == 0 &&
-                   p->dv_batch_stride % 8 == 0,
-               VITB_ERR_UNSUPPORTED_SHAPE, "attn_bwd_tc2: gradient strides %% 8");
-  const int N = p->Nk;
-  CUtensorMap tq, tk, tv, tdo, to, tdq, tdk, tdv;
-  if ((st = make_head_map(&tq, p->q, p->H, N, p->B, p->q_row_stride, p->q_batch_stride, 128)) != VITB_OK) return st;
-  if ((st = make_head_map(&tk, p->k, p->H, N, p->B, p->k_row_stride, p->k_batch_stride, 128)) != VITB_OK) return st;
-  if ((st = make_head_map(&tv, p->v, p->H, N, p->B, p->v_row_stride, p->v_batch_stride, 128)) != VITB_OK) return st;
-  if ((st = make_head_map(&tdo, p->dout, p->H, N, p->B, p->do_row_stride, p->do_batch_stride, 128)) != VITB_OK) return st;
-  if ((st = make_head_map(&to, p->o, p->H, N, p->B, p->o_row_stride, p->o_batch_stride, 128)) != VITB_OK) return st;
-  if ((st = make_head_map(&tdq, p->dq, p->H, N, p->B, p->dq_row_stride, p->dq_batch_stride, 128)) != VITB_OK) return st;
-  if ((st = make_head_map(&tdk, p->dk, p->H, N, p->B, p->dk_row_stride, p->dk_batch_stride, 128)) != VITB_OK) return st;
-  if ((st = make_head_map(&tdv, p->dv, p->H, N, p->B, p->dv_row_stride, p->dv_batch_stride, 128)) != VITB_OK) return st;
-  AttnTc a{};
-  a.N = N; a.NK = 128; a.H = p->H;
-  a.scale = 1.0f / sqrtf((float)DH);
-  a.scale_log2 = a.scale * 1.4426950408889634f;
-  a.lse = p->lse;
-  // K, V, Q, dO tiles | P buffer (2 chunks) | barriers + TMEM slot | D_i partials | alignment slack
-  const int smem = 4 * kChunkBytes + 2 * kChunkBytes + 128 + 1024 + 1024;
-  VITB_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  dim3 grid(2, p->H, p->B);   // x = key tile = rank in the 2-CTA cluster
-  VITB_CUDA_CHECK(vitb_launch(attn_bwd_tc2, grid, dim3(kAttnThreads), smem, reinterpret_cast<cudaStream_t>(stream_), tq, tk,
-                              tv, tdo, to, tdq, tdk, tdv, a));
-  VITB_LAUNCH_CHECK("attn_bwd_tc2");
   return VITB_OK;
 }

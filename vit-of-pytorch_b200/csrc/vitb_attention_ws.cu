@@ -49,7 +49,6 @@ struct WsParams {
   float scale;       // 1/sqrt(dh)
   float scale_log2;  // scale * log2(e)
   float* lse;     // [B,H,N]
-  float* colsum[3];   // backward, optional: += column sums of dV, dK, dQ ([H * 64] fp32 each; index = accumulator kind)
 };
 
 // UMMA shared-memory descriptors are built once per buffer; k-steps advance the 14-bit start-address field (16-byte
@@ -379,20 +378,12 @@ enum BwdBar {
 // own bulk-store group: no CTA-wide barrier (the first versions synchronised all eight warps twice per drain, 12 times
 // per head: 15 % of the warp samples sat there).  Inlined at three places only (see `drain` in the kernel).
 __device__ __forceinline__ void drain_warp(uint32_t taddr, uint32_t drained_bar, const CUtensorMap* tm, uint32_t stage_w,
-                                        int lane, int col, int row0, int b, float* colsum, int rows_valid) {
+                                        int lane, int col, int row0, int b) {
   uint32_t v[32];
   tmem_ld_32x32b_x32(taddr, v);
   tmem_ld_wait();
   tc_fence_before();
   mbar_arrive(drained_bar);
-  if (colsum != nullptr) {   // bias gradient of the projection: this warp's 32 rows x 32 columns summed over the rows
-    float f[32];
-    const bool row_ok = row0 + lane < rows_valid;      // rows past the token count hold padding (dK / dV: garbage)
-#pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] = row_ok ? __uint_as_float(v[j]) : 0.f;
-    const float sum = warp_transpose_sum32(f, lane);   // lane j: column j
-    atomicAdd(colsum + col + lane, sum);
-  }
   if (lane == 0) bulk_wait_read<0>();          // this warp's previous store has finished reading the staging tile
   __syncwarp();
   const uint32_t x = (static_cast<uint32_t>(lane) >> 1) & 3u;   // SWIZZLE_64B: 16-byte unit ^= address bits [7,9)
@@ -631,9 +622,8 @@ attn_bwd_ws(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       const int hh = w < 2 ? pend_kv_h : (w == 2 ? pend_dq0_h : pend_dq1_h);
       const int bb = w < 2 ? pend_kv_b : (w == 2 ? pend_dq0_b : pend_dq1_b);
       const int row0 = w < 2 ? pend_kv_kt * 128 : (w - 2) * 128;
-      float* cs = w == 0 ? a.colsum[0] : (w == 1 ? a.colsum[1] : a.colsum[2]);
       drain_warp(trow + tcol + static_cast<uint32_t>(drain_col), bar(BB_DVDR + w), tm, stage_w, lane, hh * DH + drain_col,
-                 row0 + drain_row, bb, cs, a.N);
+                 row0 + drain_row, bb);
       if (w == 0) pend_dv = false;
       else if (w == 1) pend_dk = false;
       else if (w == 2) pend_dq0 = false;
@@ -832,8 +822,11 @@ extern "C" int vitb_attn_fwd_ws(const vitb_attn_params* p, void* stream_) {
   a.scale = 1.0f / sqrtf((float)DH);
   a.scale_log2 = a.scale * kLog2e;
   a.lse = p->lse;
-  // TMEM: up to 224 keys -> S buffers at columns 0 and 224, one shared O accumulator at 448; else S at 0 / 256, O over S
-  if (NK <= 224) { a.s_stride = 224; a.o_col = 448; } else { a.s_stride = 256; a.o_col = -1; }
+  // TMEM: S buffers at columns 0 / 256, O(i) overwrites the first 64 columns of S(i).  (A layout with S at 0 / 224 and one
+  // shared O accumulator at 448, which lets S(i+2) start before O(i) is drained, measured 6 % SLOWER at N = 197 —
+  // profiles/attn_ws_r02.txt; the kernel still understands it: s_stride = 224, o_col = 448.)
+  a.s_stride = 256;
+  a.o_col = -1;
   VITB_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int sms = vitb_num_sms();
   const int grid = a.total < sms ? a.total : sms;
@@ -872,7 +865,6 @@ extern "C" int vitb_attn_bwd_ws(const vitb_attn_params* p, void* stream_) {
   a.scale = 1.0f / sqrtf((float)DH);
   a.scale_log2 = a.scale * kLog2e;
   a.lse = p->lse;
-  a.colsum[0] = p->dv_colsum; a.colsum[1] = p->dk_colsum; a.colsum[2] = p->dq_colsum;
   // 14 tiles of 16 KiB | barriers + TMEM slot | D_i partials
   const int smem = 14 * kChunkBytes + 8 * (BB_COUNT + 2) + 2 * 128 * 4;
   VITB_REQUIRE(smem <= 227 * 1024, VITB_ERR_UNSUPPORTED_SHAPE, "attn_bwd_ws: %d B of shared memory", smem);

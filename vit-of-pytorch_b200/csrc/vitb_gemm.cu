@@ -93,7 +93,6 @@ struct GemmDev {
   int aux_grad;      // VITB_EPI_MUL_AUX: aux already holds gelu'(z); the epilogue only multiplies
   int packed_epi;    // GELU + GELU' epilogue on packed fp32 pairs with the bias staged in shared memory (VITB_EPI_PACKED)
   int rowmul;        // VITB_EPI_MUL_AUX in the TMEM register layout: aux rows prefetched a chunk ahead, TMA stores (VITB_EPI_ROWMUL)
-  int rowres;        // fp32 output + fp32 residual in the register layout, 32 x 16 fp32 TMA-store tiles (VITB_EPI_ROWRES, experimental)
   int group_cols;    // Ng of a column-grouped B (merged q|k|v): tile column n0 -> group n0 / Ng; 0 = one group
   long long d_gs;    // distance (elements) between the groups of a grouped fp32 accumulate output; 0 = contiguous D
 };
@@ -545,47 +544,6 @@ __device__ __forceinline__ void epi_rows_mul_aux(const GemmDev& p, const CUtenso
   tma_store_rows_bf16(tmD, tbuf, which, lane, v, row_base, col0);
 }
 
-// ---- fp32 output = acc + bias + fp32 residual in the TMEM register layout (out-projection and fc2 forward) -------
-// EXPERIMENTAL (VITB_EPI_ROWRES=1, off by default: written after the round's GPU budget was spent, not yet run).
-// Same idea as epi_rows_mul_aux: the thread that owns row r reads its own 128 bytes of the residual stream (eight
-// 16-byte loads requested one chunk ahead), adds in registers, and the chunk leaves as two 32 x 16 fp32 tiles
-// (64-byte rows, the 2 KiB SWIZZLE_64B tile geometry of the bf16 path) through TMA stores.
-__device__ __forceinline__ void res_rows_load(const GemmDev& p, int lane, int row_base, int col0, uint4 (&dst)[8]) {
-  const int row = row_base + lane;
-  const char* rp = reinterpret_cast<const char*>(p.residual) + (static_cast<long long>(row) * p.ldr + col0) * 4;
-#pragma unroll
-  for (int u = 0; u < 8; ++u) {
-    dst[u] = make_uint4(0u, 0u, 0u, 0u);
-    if (row < p.M && col0 + 4 * u < p.N && !VITB_DIAG(16)) dst[u] = __ldg(reinterpret_cast<const uint4*>(rp) + u);
-  }
-}
-__device__ __forceinline__ void epi_rows_res_f32(const CUtensorMap* tmD, uint32_t tbuf, int& which, int lane, int row_base,
-                                                 int col0, const uint32_t (&r)[32], const uint4 (&res)[8],
-                                                 uint32_t bias_slot, bool has_bias, int cols_left) {
-  const uint32_t x = (static_cast<uint32_t>(lane) >> 1) & 3u;   // SWIZZLE_64B: 16-byte unit ^= address bits [7,9)
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    if (h * 16 >= cols_left) break;   // warp-uniform: the second half-tile lies wholly past column N
-    const uint32_t buf = tma_tile_acquire(tbuf, which, lane);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int i0 = h * 16 + j * 4;
-      const uint4 rr = res[h * 4 + j];
-      float v0 = __uint_as_float(r[i0 + 0]) + __uint_as_float(rr.x);
-      float v1 = __uint_as_float(r[i0 + 1]) + __uint_as_float(rr.y);
-      float v2 = __uint_as_float(r[i0 + 2]) + __uint_as_float(rr.z);
-      float v3 = __uint_as_float(r[i0 + 3]) + __uint_as_float(rr.w);
-      if (has_bias) {
-        const float4 b = ld_shared_f4_16(bias_slot + static_cast<uint32_t>(i0) * 4u);
-        v0 += b.x; v1 += b.y; v2 += b.z; v3 += b.w;
-      }
-      st_shared_v4(buf + static_cast<uint32_t>(lane) * 64u + ((static_cast<uint32_t>(j) ^ x) << 4), __float_as_uint(v0),
-                   __float_as_uint(v1), __float_as_uint(v2), __float_as_uint(v3));
-    }
-    tma_tile_release(tmD, buf, lane, row_base, col0 + h * 16);
-  }
-}
-
 // Scalar epilogue with every option (row bias, patch-embedding row remap, odd widths): lane == column.
 __device__ __noinline__ void epi_generic(const GemmDev& p, uint32_t stg, int lane, int row_base, int col0,
                                          bool lead_split) {
@@ -631,9 +589,7 @@ __device__ __noinline__ void epi_generic(const GemmDev& p, uint32_t stg, int lan
   }
 }
 
-// XEPI = true compiles the experimental epilogues in (a separate set of kernels, so that the register allocation of
-// the validated ones does not move when an experiment is added).
-template <int BN, bool A_MN, bool B_MN, bool XEPI = false>
+template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kThreads, 1)
 vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
                  const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
@@ -789,9 +745,7 @@ vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const bool has_bias = p.bias != nullptr;
     const bool rowmul = p.rowmul != 0 && mode == 3;   // bf16 MUL_AUX without bias: register layout + TMA stores
     uint4 aux_next[4];                                  // this lane's 64 bytes of aux for the chunk that comes next
-    const bool rowres = XEPI && p.rowres != 0 && mode == 10;   // fp32 out + fp32 residual: register layout + fp32 TMA-store tiles
-    uint4 res_next[8];                                  // this lane's 128 bytes of residual for the chunk that comes next
-    if ((rowmul || rowres) && lane == 0) tma_prefetch_desc(&tmD);
+    if (rowmul && lane == 0) tma_prefetch_desc(&tmD);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile);
       const int n0 = t.n_blk * BN;
@@ -803,8 +757,6 @@ vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const long long d_off = (p.d_gs != 0 && p.group_cols > 0) ? static_cast<long long>(n0 / p.group_cols) * (p.d_gs - p.group_cols) : 0;
       if (rowmul) {
         aux_rows_load(p, lane, row_base, n0 + half * (BN / 64) * 32, aux_next);
-      } else if (rowres) {
-        res_rows_load(p, lane, row_base, n0 + half * (BN / 64) * 32, res_next);
       } else {   // the side operand of this warp's first chunk is requested before the accumulator is waited for
         const int colf = n0 + half * (BN / 64) * 32;
         if (colf < p.N) {
@@ -819,8 +771,8 @@ vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           }
         }
       }
-      float bias_next = 0.f;   // packed / rowres paths: lane j carries bias[col0 + j] of the chunk that comes next
-      if ((packed || rowres) && has_bias) {
+      float bias_next = 0.f;   // packed path: lane j carries bias[col0 + j] of the chunk that comes next
+      if (packed && has_bias) {
         const int colb = n0 + half * (BN / 64) * 32 + lane;
         if (colb < p.N) bias_next = __ldg(p.bias + colb);
       }
@@ -853,22 +805,6 @@ vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           }
           tmem_ld_wait();
           epi_rows_gelu_dg_packed(&tmD, &tmD2, tbuf, tma_which, lane, row_base, col0, r, slot, has_bias);
-          continue;
-        }
-        if (rowres) {
-          const uint32_t slot = bias_slots + static_cast<uint32_t>(c & 1) * 128u;
-          if (has_bias) {
-            asm volatile("st.shared.f32 [%0], %1;" ::"r"(slot + static_cast<uint32_t>(lane) * 4u), "f"(bias_next) : "memory");
-            bias_next = 0.f;
-            if (next_col0 >= 0 && next_col0 + lane < p.N) bias_next = __ldg(p.bias + next_col0 + lane);
-            __syncwarp();
-          }
-          uint4 res_cur[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) res_cur[u] = res_next[u];
-          if (next_col0 >= 0) res_rows_load(p, lane, row_base, next_col0, res_next);   // flies during this chunk
-          tmem_ld_wait();
-          epi_rows_res_f32(&tmD, tbuf, tma_which, lane, row_base, col0, r, res_cur, slot, has_bias, p.N - col0);
           continue;
         }
         if (rowmul) {
@@ -911,7 +847,7 @@ vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
-    if ((tma_path || rowmul || rowres) && lane == 0) bulk_wait_all();   // staging tiles must outlive the stores that read them
+    if ((tma_path || rowmul) && lane == 0) bulk_wait_all();   // staging tiles must outlive the stores that read them
   }
 
   tc_fence_before();
@@ -1111,9 +1047,9 @@ int launch_wgrad_pair(const CUtensorMap* tm, GemmDev d, int M, int N, cudaStream
   return VITB_OK;
 }
 
-template <int BN, bool A_MN, bool B_MN, bool XEPI = false>
+template <int BN, bool A_MN, bool B_MN>
 int launch(const CUtensorMap* tm, const GemmDev& d, int grid, cudaStream_t stream) {
-  auto kern = vitb_gemm_kernel<BN, A_MN, B_MN, XEPI>;
+  auto kern = vitb_gemm_kernel<BN, A_MN, B_MN>;
   VITB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg<BN>::SMEM_BYTES));
   VITB_CUDA_CHECK(vitb_launch(kern, dim3(grid), dim3(kThreads), Cfg<BN>::SMEM_BYTES, stream, tm[0], tm[1], tm[2], tm[3],
@@ -1298,18 +1234,6 @@ extern "C" int VITB_GEMM_ENTRY(const vitb_gemm_params* p, void* stream_) {
       d.rowmul = 1;
     }
   }
-  d.rowres = 0;
-  {
-    const char* re = getenv("VITB_EPI_ROWRES");     // experimental: off unless VITB_EPI_ROWRES=1
-    const bool want = re != nullptr && atoi(re) != 0;
-    if (want && !p->a_mn_major && d.vec_ok && !d.d_bf16 && d.epilogue == VITB_EPI_NONE && p->residual != nullptr && !d.r_bf16 &&
-        !p->accumulate && p->colsum == nullptr && d.split_k == 1 && (reinterpret_cast<uintptr_t>(p->D) & 15u) == 0 &&
-        (reinterpret_cast<uintptr_t>(p->residual) & 15u) == 0) {
-      st = vitb_make_tmap_2d_f32_sw64(&tm[6], p->D, (uint64_t)p->N, (uint64_t)p->M, (uint64_t)p->ldd * 4, 16, 32);
-      if (st != VITB_OK) return st;
-      d.rowres = 1;
-    }
-  }
   // weight gradients (both operands MN-major, fp32 accumulation, one K segment) run on CTA pairs
   // (measured, profiles/gemm_bench_r01b.txt: dW fc1 0.099 -> 0.090 ms, dW fc2 0.104 -> 0.089 ms, i.e. 1.33 PFLOP/s)
   {
@@ -1332,8 +1256,6 @@ extern "C" int VITB_GEMM_ENTRY(const vitb_gemm_params* p, void* stream_) {
 
 #define VITB_DISPATCH(BN_)                                                              \
   do {                                                                                  \
-    if (d.rowres && !p->a_mn_major && !p->b_mn_major) return launch<BN_, false, false, true>(tm, d, grid, stream); \
-    if (d.rowres && !p->a_mn_major && p->b_mn_major) return launch<BN_, false, true, true>(tm, d, grid, stream);   \
     if (!p->a_mn_major && !p->b_mn_major) return launch<BN_, false, false>(tm, d, grid, stream); \
     if (!p->a_mn_major && p->b_mn_major) return launch<BN_, false, true>(tm, d, grid, stream);   \
     if (p->a_mn_major && !p->b_mn_major) return launch<BN_, true, false>(tm, d, grid, stream);   \

@@ -160,6 +160,84 @@ inline int grid_for(long long items, int per_sm = 8) {
   return static_cast<int>(blocks);
 }
 
+// ---- Res-ViT scalar losses -----------------------------------------------------------------
+// Both are single-CTA reductions over a few thousand values that also write the gradient the backward needs, so the
+// autograd node never launches a second pass.
+constexpr int kLossThreads = 512;
+
+__device__ __forceinline__ float block_sum(float v, float* s_part) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+  if (threadIdx.x < 32) {
+    t = threadIdx.x < (kLossThreads >> 5) ? s_part[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) s_part[0] = t;
+  }
+  __syncthreads();
+  t = s_part[0];
+  __syncthreads();
+  return t;
+}
+
+// DistillLoss (res-vit/model.py:40-59): loss = mean((s - t)^2) over rows x cols values; ds = 2 (s - t) / (rows cols).
+// s / t are [rows, cols] slices with row strides (the class-token rows student_out[:, 0, :] / teacher_out[:, 0, :]).
+template <bool BF16>
+__global__ void __launch_bounds__(kLossThreads)
+distill_loss_kernel(const void* __restrict__ s_, long long s_stride, const void* __restrict__ t_, long long t_stride,
+                    int rows, int cols, float* __restrict__ loss_acc, float* __restrict__ ds) {
+  __shared__ float s_part[kLossThreads / 32];
+  const long long n = static_cast<long long>(rows) * cols;
+  const float inv = 1.0f / static_cast<float>(n);
+  float acc = 0.f;
+  for (long long i = threadIdx.x; i < n; i += kLossThreads) {
+    const int r = static_cast<int>(i / cols), c = static_cast<int>(i - static_cast<long long>(r) * cols);
+    float a, b;
+    if (BF16) {
+      a = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(s_)[r * s_stride + c]);
+      b = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(t_)[r * t_stride + c]);
+    } else {
+      a = reinterpret_cast<const float*>(s_)[r * s_stride + c];
+      b = reinterpret_cast<const float*>(t_)[r * t_stride + c];
+    }
+    const float d = a - b;
+    acc += d * d;
+    if (ds) ds[i] = 2.f * d * inv;
+  }
+  const float tot = block_sum(acc, s_part);
+  if (threadIdx.x == 0) *loss_acc += tot * inv;     // accumulates: d_loss sums over the dynamic layers (:648-650)
+}
+
+// ActiveLoss (res-vit/model.py:61-85): ratio = mean of p[b, n >= r0, j]; loss = (ratio + shift - target)^2;
+// dp = 2 (ratio + shift - target) / count for n >= r0, else 0.  p is [B, N, L] fp32.  `shift` (device scalar, optional)
+// carries global-batch mean minus this shard's mean under data parallelism (resvit.ActiveLoss.sync_group).
+__global__ void __launch_bounds__(kLossThreads)
+active_loss_kernel(const float* __restrict__ p, int B, int N, int L, int r0, float target, const float* __restrict__ shift,
+                   float* __restrict__ ratio_out, float* __restrict__ loss, float* __restrict__ dp) {
+  __shared__ float s_part[kLossThreads / 32];
+  const long long n = static_cast<long long>(B) * N * L;
+  const float count = static_cast<float>(static_cast<long long>(B) * (N - r0) * L);
+  float acc = 0.f;
+  for (long long i = threadIdx.x; i < n; i += kLossThreads) {
+    const int tok = static_cast<int>((i / L) % N);
+    if (tok >= r0) acc += p[i];
+  }
+  const float ratio = block_sum(acc, s_part) / count;
+  const float e = ratio + (shift ? *shift : 0.f) - target;
+  if (threadIdx.x == 0) {
+    if (ratio_out) *ratio_out = ratio;
+    if (loss) *loss = e * e;
+  }
+  if (dp) {
+    const float g = 2.f * e / count;
+    for (long long i = threadIdx.x; i < n; i += kLossThreads) {
+      const int tok = static_cast<int>((i / L) % N);
+      dp[i] = tok >= r0 ? g : 0.f;
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -232,6 +310,29 @@ int vitb_select_rows(const void* a, const void* b, const float* index, uint32_t 
   if (dtype == VITB_BF16) select_rows_kernel<true><<<grid_for(total), kThreads, 0, s>>>(a, b, index, member_mask, rows, cols, out);
   else select_rows_kernel<false><<<grid_for(total), kThreads, 0, s>>>(a, b, index, member_mask, rows, cols, out);
   VITB_LAUNCH_CHECK("select_rows_kernel");
+  return VITB_OK;
+}
+
+int vitb_distill_loss(const void* student, int64_t s_row_stride, const void* teacher, int64_t t_row_stride, int dtype, int rows,
+                      int cols, float* loss_acc, float* d_student, void* stream_) {
+  int st = vitb_check_device();
+  if (st != VITB_OK) return st;
+  VITB_REQUIRE(student && teacher && loss_acc && rows > 0 && cols > 0, VITB_ERR_BAD_ARG, "distill_loss: bad args");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  if (dtype == VITB_BF16) distill_loss_kernel<true><<<1, kLossThreads, 0, s>>>(student, s_row_stride, teacher, t_row_stride, rows, cols, loss_acc, d_student);
+  else distill_loss_kernel<false><<<1, kLossThreads, 0, s>>>(student, s_row_stride, teacher, t_row_stride, rows, cols, loss_acc, d_student);
+  VITB_LAUNCH_CHECK("distill_loss_kernel");
+  return VITB_OK;
+}
+
+int vitb_active_loss(const float* probs, int B, int N, int L, int reserve_initials, float target, const float* shift_dev,
+                     float* ratio_out, float* loss, float* d_probs, void* stream_) {
+  int st = vitb_check_device();
+  if (st != VITB_OK) return st;
+  VITB_REQUIRE(probs && B > 0 && N > reserve_initials && L > 0 && (loss || ratio_out || d_probs), VITB_ERR_BAD_ARG, "active_loss: bad args");
+  active_loss_kernel<<<1, kLossThreads, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(probs, B, N, L, reserve_initials, target, shift_dev,
+                                                                                       ratio_out, loss, d_probs);
+  VITB_LAUNCH_CHECK("active_loss_kernel");
   return VITB_OK;
 }
 

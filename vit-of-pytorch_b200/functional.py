@@ -974,11 +974,8 @@ class _EncoderBlockFused(torch.autograd.Function):
             accb, r = _acc(b)
             ret(b, r)
             accs.append(accb.view(-1))
-        # the persistent attention backward sums the columns of dQ / dK / dV (= the projection bias gradients) from its
-        # fp32 accumulators while it drains them; the other kernels leave that to a pass over the bf16 result
-        fused_cs = ops.attn_bwd_fuses_colsums(D // H, N, N, BF16)
         ops.attn_bwd(do.view(Bsz, N, D), qkv3[:, :, :D], qkv3[:, :, D:2 * D], qkv3[:, :, 2 * D:], o, lse, H,
-                     dq=dqkv[:, :, :D], dk=dqkv[:, :, D:2 * D], dv=dqkv[:, :, 2 * D:], colsums=tuple(accs) if fused_cs else None)
+                     dq=dqkv[:, :, :D], dk=dqkv[:, :, D:2 * D], dv=dqkv[:, :, 2 * D:])
         dq2 = dqkv.view(T, 3 * D)
         accs_w = []
         for w in (wq, wk, wv):
@@ -991,8 +988,7 @@ class _EncoderBlockFused(torch.autograd.Function):
         else:
             for i, acc in enumerate(accs_w):
                 ops.gemm(xn, dq2[:, i * D:(i + 1) * D], a_mn=True, b_mn=True, out=acc, accumulate=True)   # dW[K,N] = xn^T dQ
-        if not fused_cs:
-            ops.colsum3(dq2, accs[0], accs[1], accs[2])
+        ops.colsum3(dq2, accs[0], accs[1], accs[2])
         dxn = ops.gemm([dq2[:, :D], dq2[:, D:2 * D], dq2[:, 2 * D:]],
                        [SHADOW.get(w, False)[0].view(D, D) for w in (wq, wk, wv)], b_mn=False, out_dtype=BF16)
         # ---- LN1 backward + residual: dx = dh + LN'(dxn) ----

@@ -243,15 +243,8 @@ def attn_fwd(q, k, v, H, *, use_tc=None):
     return o, lse
 
 
-def attn_bwd_fuses_colsums(dh, Nq, Nk, dtype):
-    """True when attn_bwd(..., colsums=...) accumulates the q / k / v bias gradients itself (the persistent tcgen05 kernel)."""
-    return dtype == torch.bfloat16 and _attn_ws_enabled() and bool(L.vitb_attn_ws_supported(1, dh, Nq, Nk))
-
-
-def attn_bwd(dout, q, k, v, o, lse, H, *, use_tc=None, dq=None, dk=None, dv=None, colsums=None):
-    """Returns (dq, dk, dv).  tc: bf16 gradients; simt: fp32 gradients.  dq/dk/dv may be strided views.
-    colsums = (cq, ck, cv): fp32 [H*dh] buffers that receive += the column sums of dq / dk / dv (the projection bias
-    gradients); only valid when attn_bwd_fuses_colsums(...) — the other kernels would silently ignore them, so it raises."""
+def attn_bwd(dout, q, k, v, o, lse, H, *, use_tc=None, dq=None, dk=None, dv=None):
+    """Returns (dq, dk, dv).  tc: bf16 gradients; simt: fp32 gradients.  dq/dk/dv may be strided views."""
     L.require_cuda(dout, q, k, v, o, lse)
     B, Nq, HD = q.shape
     Nk = k.shape[1]
@@ -278,17 +271,8 @@ def attn_bwd(dout, q, k, v, o, lse, H, *, use_tc=None, dq=None, dk=None, dv=None
     p.dk_batch_stride, p.dk_row_stride = _head_strides(dk, H, dh, "dk")
     p.dv_batch_stride, p.dv_row_stride = _head_strides(dv, H, dh, "dv")
     fn = L._vitb_attn_bwd_tc if use_tc else L._vitb_attn_bwd_simt
-    if use_tc and os.environ.get("VITB_ATTN_BWD2") == "1" and L.vitb_attn_bwd_tc2_supported(dh, Nq, Nk):
-        fn = L._vitb_attn_bwd_tc2       # experimental key-split CTA-pair kernel (off unless VITB_ATTN_BWD2=1)
     if use_tc and _attn_ws_enabled() and L.vitb_attn_ws_supported(1, dh, Nq, Nk):
         fn = L._vitb_attn_bwd_ws        # persistent warp-specialised kernel
-    if colsums is not None:
-        if fn is not L._vitb_attn_bwd_ws:
-            raise L.VitbError("attn_bwd: colsums are only produced by the persistent tcgen05 kernel (see attn_bwd_fuses_colsums)")
-        for t in colsums:
-            if t.dtype != torch.float32 or t.numel() != HD or not t.is_contiguous():
-                raise L.VitbError("attn_bwd: colsums must be contiguous fp32 [H*dh]")
-        p.dq_colsum, p.dk_colsum, p.dv_colsum = (t.data_ptr() for t in colsums)
     L.check(fn(C.byref(p), L.stream_ptr(q.device)), "vitb_attn_bwd")
     return dq, dk, dv
 
@@ -484,6 +468,37 @@ def sumsq(x, out):
 def clip_coef(sumsq_t, max_norm, coef, norm_out=None):
     L.check(L._vitb_clip_coef(L.ptr(sumsq_t), float(max_norm), L.ptr(coef), L.ptr(norm_out),
                               L.stream_ptr(coef.device)), "vitb_clip_coef")
+
+
+# --------------------------------------------------------------------------------------------------
+# Res-ViT scalar losses
+# --------------------------------------------------------------------------------------------------
+def distill_loss(student, teacher, loss_acc, want_grad):
+    """*loss_acc += mean((student - teacher)^2) over two [rows, cols] (row-strided) slices of one dtype; returns the
+    gradient with respect to `student` ([rows, cols] fp32) when want_grad."""
+    L.require_cuda(student, teacher, loss_acc)
+    if student.dim() != 2 or student.shape != teacher.shape or student.stride(1) != 1 or teacher.stride(1) != 1 or \
+            student.dtype != teacher.dtype:
+        raise L.VitbError("distill_loss: student / teacher must be [rows, cols] views of one dtype with unit inner stride")
+    rows, cols = student.shape
+    ds = torch.empty((rows, cols), dtype=torch.float32, device=student.device) if want_grad else None
+    L.check(L._vitb_distill_loss(L.ptr(student), student.stride(0), L.ptr(teacher), teacher.stride(0), L.dtype_code(student),
+                                 rows, cols, L.ptr(loss_acc), L.ptr(ds), L.stream_ptr(student.device)), "vitb_distill_loss")
+    return ds
+
+
+def active_loss(probs, reserve_initials, target, *, shift=None, want_grad=False):
+    """probs [B, N, L] fp32 -> (ratio scalar, loss scalar, d_probs or None); see include/vitb200.h."""
+    L.require_cuda(probs, shift)
+    if probs.dim() != 3 or probs.dtype != torch.float32 or not probs.is_contiguous():
+        raise L.VitbError("active_loss: probs must be contiguous fp32 [B, N, L]")
+    B, N, Lr = probs.shape
+    ratio = torch.empty((), dtype=torch.float32, device=probs.device)
+    loss = torch.empty((), dtype=torch.float32, device=probs.device)
+    dp = torch.empty_like(probs) if want_grad else None
+    L.check(L._vitb_active_loss(L.ptr(probs), B, N, Lr, int(reserve_initials), float(target), L.ptr(shift), L.ptr(ratio),
+                                L.ptr(loss), L.ptr(dp), L.stream_ptr(probs.device)), "vitb_active_loss")
+    return ratio, loss, dp
 
 
 # --------------------------------------------------------------------------------------------------
