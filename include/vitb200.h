@@ -108,6 +108,11 @@ typedef struct vitb_gemm_params {
   int32_t _pad1;
   int64_t b_group_stride;
   int64_t d_group_stride;
+  /* optional DEVICE scalar: the number of rows of A / D that actually hold data (<= M).  Tiles past it are skipped; M
+   * stays the capacity the buffers and tensor maps are built for (rows between *m_dev and the end of its last 128-row
+   * tile are computed from whatever the buffers hold and written — they belong to the caller's scratch capacity).
+   * Token-major GEMMs only (a_mn_major = 0, split_k <= 1, no colsum). */
+  const int32_t* m_dev;
 } vitb_gemm_params;
 
 int vitb_gemm(const vitb_gemm_params* p, void* stream);
@@ -234,6 +239,19 @@ int vitb_token_mean_bwd(const float* dg, int dtype, int B, int N, int C, int res
  * torch.isin + blend (res-vit/model.py:469-472,487,524) and approximator row selection (:349-368). */
 int vitb_select_rows(const void* a, const void* b, const float* index, uint32_t member_mask, int rows, int cols,
                      int dtype, void* out, void* stream);
+
+/* Device-side row compaction for Res-ViT's inference-time token skipping (res-vit/model.py:503-524): nothing
+ * about the selection travels to the host.  index [T] fp32 packed router indices (as vitb_select_rows):
+ *   vitb_compact_rows  rows[*count ...] receives every t with ((member_mask >> (int)index[t]) & 1), *count grows by their
+ *                      number (zero it first); the order of the list is unspecified (every consumer is row-wise).
+ *   vitb_gather_rows   dst[i, :] = src[rows[i], :] for i < *count     (max_rows bounds the launch; cols of dtype f32/bf16,
+ *   vitb_scatter_rows  dst[rows[i], :] = src[i, :] for i < *count      rows 16-byte aligned and a multiple of 16 bytes)
+ * The GEMMs between a gather and a scatter take their row count from the same device scalar (vitb_gemm_params.m_dev). */
+int vitb_compact_rows(const float* index, uint32_t member_mask, int T, int32_t* rows, int32_t* count, void* stream);
+int vitb_gather_rows(const void* src, int64_t src_ld, int dtype, const int32_t* rows, const int32_t* count, int max_rows,
+                     int cols, void* dst, int64_t dst_ld, void* stream);
+int vitb_scatter_rows(const void* src, int64_t src_ld, int dtype, const int32_t* rows, const int32_t* count, int max_rows,
+                      int cols, void* dst, int64_t dst_ld, void* stream);
 
 /* Res-ViT scalar losses, each one single-CTA kernel that also writes the gradient its backward needs.
  * vitb_distill_loss — DistillLoss, res-vit/model.py:40-59: *loss_acc += mean((s - t)^2) over [rows, cols] (rows may be

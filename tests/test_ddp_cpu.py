@@ -73,23 +73,32 @@ def test_grad_reducer_gloo_world_size_2():
     assert all(order == [1, 0] for _, _, order in res), res
 
 
+def _ratio(act, reserve_initials=1):
+    """ActiveLoss's statistic (res-vit/model.py:80-82): mean keep-probability over the non-reserved tokens."""
+    return act[:, reserve_initials:, :].float().mean()
+
+
 def _active_loss_worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         import vitb200
-        from vitb200.resvit import ActiveLoss
+        from vitb200 import functional as VF
         g = torch.Generator().manual_seed(5)
         x = torch.randn(4, 9, 3, generator=g)                       # global batch: 4 images, 9 tokens, 3 dynamic layers
         theta = torch.tensor([0.3, -0.2, 0.1], requires_grad=True)  # the replicated "router parameters"
         shard = x[rank * 2:(rank + 1) * 2]
-        loss = ActiveLoss(0.4, 1, sync_group=True)(torch.sigmoid(shard * theta))
+        # the loss itself is a CUDA kernel (vitb_active_loss); what is checked here on gloo is the host-side exchange it
+        # is wrapped in: value = global mean, gradient = this shard's (functional.global_mean_shift)
+        assert VF.global_mean_needed(True)
+        ratio = _ratio(torch.sigmoid(shard * theta))
+        loss = (ratio + VF.global_mean_shift(ratio, True) - 0.4) ** 2
         loss.backward()
         grad = theta.grad.clone()
         dist.all_reduce(grad)                                       # what the data-parallel wrapper does: average
         grad /= world
-        local = ActiveLoss(0.4, 1)(torch.sigmoid(shard * theta.detach()))
+        local = (_ratio(torch.sigmoid(shard * theta.detach())) - 0.4) ** 2
         q.put((rank, float(loss), grad, float(local)))
     finally:
         dist.destroy_process_group()
@@ -99,7 +108,6 @@ def test_active_loss_global_batch_semantics_gloo_world_size_2():
     """ActiveLoss(sync_group=...) reproduces the loss AND, after the wrapper's gradient averaging, the gradient of the global
     batch (res-vit/model.py:80-83 is (batch mean - target)^2, not linear in the batch mean); without it every replica sees
     its own shard."""
-    from vitb200.resvit import ActiveLoss
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -114,7 +122,7 @@ def test_active_loss_global_batch_semantics_gloo_world_size_2():
     g = torch.Generator().manual_seed(5)
     x = torch.randn(4, 9, 3, generator=g)
     theta = torch.tensor([0.3, -0.2, 0.1], requires_grad=True)
-    ref = ActiveLoss(0.4, 1)(torch.sigmoid(x * theta))              # single process, whole batch
+    ref = (_ratio(torch.sigmoid(x * theta)) - 0.4) ** 2              # single process, whole batch
     ref.backward()
     for rank, loss, grad, local in res:
         assert abs(loss - float(ref)) < 1e-7
@@ -123,10 +131,12 @@ def test_active_loss_global_batch_semantics_gloo_world_size_2():
     assert abs(0.5 * (res[0][3] + res[1][3]) - float(ref)) > 1e-8   # and their average is not the global loss
 
 
-def test_active_loss_without_a_process_group_is_the_reference_formula():
+def test_active_loss_is_a_cuda_kernel_and_stays_local_without_a_process_group():
+    """The loss is vitb_active_loss (GPU parity: tests/test_resvit_gpu.py); CPU tensors are refused — there is no CPU path —
+    and without an initialised process group sync_group=True means local semantics."""
+    import pytest
     from vitb200.resvit import ActiveLoss
-    g = torch.Generator().manual_seed(6)
-    a = torch.rand(3, 7, 2, generator=g)
-    want = (a[:, 1:, :].mean() - 0.6) ** 2
-    assert torch.equal(ActiveLoss(0.6, 1)(a), want)
-    assert torch.equal(ActiveLoss(0.6, 1, sync_group=True)(a), want)      # no process group initialised: local semantics
+    from vitb200 import functional as VF
+    assert not VF.global_mean_needed(True) and not VF.global_mean_needed(None)
+    with pytest.raises(RuntimeError):
+        ActiveLoss(0.6, 1)(torch.rand(3, 7, 2))

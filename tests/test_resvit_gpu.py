@@ -265,3 +265,33 @@ def test_resvit_c5_geometry_bf16_train_and_eval(variant):
                 if p.grad is not None:
                     assert bool(torch.isfinite(p.grad).all()), k
             m.zero_grad(set_to_none=True)
+
+
+def test_resvit_loss_kernels_match_the_reference_formulas():
+    """vitb_distill_loss / vitb_active_loss (value and gradient from one kernel) against res-vit/model.py:40-59, :61-85."""
+    from vitb200 import resvit
+    g = torch.Generator().manual_seed(8)
+    # DistillLoss on strided class-token rows, fp32 and bf16
+    for dt, tol in ((torch.float32, 1e-6), (torch.bfloat16, 1e-6)):
+        s_all = torch.randn(5, 7, 64, generator=g).to(dt)
+        t_all = torch.randn(5, 7, 64, generator=g).to(dt)
+        sr = s_all.float().clone().requires_grad_(True)
+        want = torch.nn.functional.mse_loss(sr[:, 0, :], t_all.float()[:, 0, :])
+        want.backward()
+        sc = s_all.cuda().requires_grad_(True)
+        got = resvit.DistillLoss()(sc[:, 0, :], t_all.cuda()[:, 0, :])
+        (3.0 * got).backward()
+        assert abs(float(got) - float(want)) <= tol * max(1.0, abs(float(want)))
+        assert rel_l2(sc.grad.float().cpu(), 3.0 * sr.grad) < (1e-6 if dt == torch.float32 else 4e-3)
+    # ActiveLoss: masked mean over the non-reserved tokens, squared distance to the target
+    a = torch.rand(3, 9, 4, generator=g)
+    ar = a.clone().requires_grad_(True)
+    want = (ar[:, 1:, :].mean() - 0.4) ** 2
+    want.backward()
+    ac = a.cuda().requires_grad_(True)
+    crit = resvit.ActiveLoss(0.4, 1)
+    got = crit(ac)
+    got.backward()
+    assert abs(float(got) - float(want)) < 1e-7
+    assert rel_l2(ac.grad.cpu(), ar.grad) < 1e-6
+    assert abs(float(crit.metric(ac)["non_low_rank_ratio"]) - float(a[:, 1:, :].mean())) < 1e-6

@@ -68,6 +68,7 @@ class GemmParams(C.Structure):
         ("_pad1", C.c_int32),
         ("b_group_stride", C.c_int64),
         ("d_group_stride", C.c_int64),
+        ("m_dev", C.c_void_p),
     ]
 
 
@@ -192,6 +193,9 @@ _vitb_router_decide_bwd = _sig("vitb_router_decide_bwd", [_vp, _vp, _vp, _vp, _v
 _vitb_token_mean_fwd = _sig("vitb_token_mean_fwd", [_vp, _i, _i, _i, _i, _i, _vp, _vp])
 _vitb_token_mean_bwd = _sig("vitb_token_mean_bwd", [_vp, _i, _i, _i, _i, _i, _vp, _vp])
 _vitb_select_rows = _sig("vitb_select_rows", [_vp, _vp, _vp, C.c_uint32, _i, _i, _i, _vp, _vp])
+_vitb_compact_rows = _sig("vitb_compact_rows", [_vp, C.c_uint32, _i, _vp, _vp, _vp])
+_vitb_gather_rows = _sig("vitb_gather_rows", [_vp, _i64, _i, _vp, _vp, _i, _i, _vp, _i64, _vp])
+_vitb_scatter_rows = _sig("vitb_scatter_rows", [_vp, _i64, _i, _vp, _vp, _i, _i, _vp, _i64, _vp])
 _vitb_distill_loss = _sig("vitb_distill_loss", [_vp, _i64, _vp, _i64, _i, _i, _i, _vp, _vp, _vp])
 _vitb_active_loss = _sig("vitb_active_loss", [_vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp])
 _vitb_clip_coef = _sig("vitb_clip_coef", [_vp, _f, _vp, _vp, _vp])
@@ -207,5 +211,5 @@ EXPORTED_SYMBOLS = [
     "vitb_sumsq", "vitb_clip_coef", "vitb_gelu_bwd", "vitb_router_decide_fwd", "vitb_router_decide_bwd",
     "vitb_token_mean_fwd", "vitb_token_mean_bwd", "vitb_select_rows", "vitb_colsum3",
     "vitb_resize_tables_host", "vitb_image_prep", "vitb_gemm_diag", "vitb_gemm_diag_mask",
-    "vitb_distill_loss", "vitb_active_loss", "vitb_attn_ws_supported", "vitb_attn_fwd_ws", "vitb_attn_bwd_ws",
+    "vitb_distill_loss", "vitb_active_loss", "vitb_compact_rows", "vitb_gather_rows", "vitb_scatter_rows", "vitb_attn_ws_supported", "vitb_attn_fwd_ws", "vitb_attn_bwd_ws",
 ]

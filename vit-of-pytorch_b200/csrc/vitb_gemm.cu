@@ -53,14 +53,25 @@ constexpr int kStgStride = 34;                       // floats per staged row: 8
 constexpr int kStagingFloats = 32 * kStgStride;      // per epilogue warp
 constexpr int kStagingBytes = kEpiWarps * kStagingFloats * 4;
 
-template <int BN>
+// EW = number of epilogue warps.  8 (two per TMEM lane quadrant, 4352 B of staging each: every epilogue) or 16 (four per
+// quadrant, ONE 2 KiB TMA-store tile + a 128 B bias slot each: only the register-layout epilogues that leave through TMA
+// stores).  The bf16 epilogues behind a K = 768 mainloop (GELU + GELU', x gelu', bias) are bound by the latency of their
+// own dependency chains with two warps per scheduler (ncu, profiles/ncu_gemm_fc1_r02.txt: 0.4 IPC per scheduler, no
+// dominant stall); four warps per scheduler hide it.
+template <int EW>
+struct EpiCfg {
+  static constexpr int THREADS = (kEpiWarp0 + EW) * 32;
+  static constexpr int STAGING_BYTES = (EW == 8) ? kStagingBytes : EW * (2048 + 128);
+};
+
+template <int BN, int EW = 8>
 struct Cfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : 6;
   static constexpr int TMEM_COLS = 2 * BN;
   // no alignment slack: the dynamic shared window starts 1024-byte aligned (checked at kernel entry)
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + kStagingBytes + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EpiCfg<EW>::STAGING_BYTES + 256 /*barriers*/;
 };
 
 struct GemmDev {
@@ -93,6 +104,7 @@ struct GemmDev {
   int aux_grad;      // VITB_EPI_MUL_AUX: aux already holds gelu'(z); the epilogue only multiplies
   int packed_epi;    // GELU + GELU' epilogue on packed fp32 pairs with the bias staged in shared memory (VITB_EPI_PACKED)
   int rowmul;        // VITB_EPI_MUL_AUX in the TMEM register layout: aux rows prefetched a chunk ahead, TMA stores (VITB_EPI_ROWMUL)
+  const int* m_dev;  // optional device scalar: rows that hold data (tiles past it are skipped); nullptr = M
   int group_cols;    // Ng of a column-grouped B (merged q|k|v): tile column n0 -> group n0 / Ng; 0 = one group
   long long d_gs;    // distance (elements) between the groups of a grouped fp32 accumulate output; 0 = contiguous D
 };
@@ -388,11 +400,19 @@ __device__ __forceinline__ void epi_vec(const GemmDev& p, uint32_t stg, int lane
 // stores later.  Measured (profiles/gemm_bench_r01b.txt): fc1+GELU 0.167 -> 0.132 ms, fc1+bias 0.114 -> 0.105 ms.
 constexpr int kTmaTileBytes = 32 * 64;
 
-// acquire the next staging tile of this warp: the store that last read it (two stores ago) has drained
+// acquire the next staging tile of this warp: the store that last read it has drained.  NT = 2: two tiles alternate
+// (the store of two stores ago); NT = 1: one tile (the previous store) — the 16-warp epilogue, where the other three
+// warps of the scheduler run while this one waits.
+template <int NT>
 __device__ __forceinline__ uint32_t tma_tile_acquire(uint32_t tbuf, int& which, int lane) {
-  const uint32_t buf = tbuf + static_cast<uint32_t>(which) * kTmaTileBytes;
-  which ^= 1;
-  if (lane == 0) bulk_wait_read<1>();
+  uint32_t buf = tbuf;
+  if constexpr (NT == 2) {
+    buf += static_cast<uint32_t>(which) * kTmaTileBytes;
+    which ^= 1;
+    if (lane == 0) bulk_wait_read<1>();
+  } else {
+    if (lane == 0) bulk_wait_read<0>();
+  }
   __syncwarp();
   return buf;
 }
@@ -412,9 +432,10 @@ __device__ __forceinline__ void tma_tile_release(const CUtensorMap* tm, uint32_t
     bulk_commit();
   }
 }
+template <int NT>
 __device__ __forceinline__ void tma_store_rows_bf16(const CUtensorMap* tm, uint32_t tbuf, int& which, int lane,
                                                     const float (&v)[32], int row_base, int col0) {
-  const uint32_t buf = tma_tile_acquire(tbuf, which, lane);
+  const uint32_t buf = tma_tile_acquire<NT>(tbuf, which, lane);
 #pragma unroll
   for (int j = 0; j < 4; ++j)
     tma_tile_write_unit(buf, lane, j, v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3], v[8 * j + 4], v[8 * j + 5],
@@ -423,7 +444,7 @@ __device__ __forceinline__ void tma_store_rows_bf16(const CUtensorMap* tm, uint3
 }
 
 // One 32-row x 32-column chunk of a bf16 output: bias / GELU in the TMEM register layout, then TMA stores.
-template <int EPI>
+template <int EPI, int NT>
 __device__ __forceinline__ void epi_rows_bf16_tma(const GemmDev& p, const CUtensorMap* tmD, const CUtensorMap* tmD2,
                                                   uint32_t tbuf, int& which, int lane, int row_base, int col0,
                                                   const uint32_t (&r)[32]) {
@@ -442,7 +463,7 @@ __device__ __forceinline__ void epi_rows_bf16_tma(const GemmDev& p, const CUtens
   if constexpr (EPI == VITB_EPI_GELU) {
     if (p.D2 != nullptr && p.d2_grad) {
       // D2 = gelu'(v), D = gelu(v): the derivative goes to its tile 8 columns at a time while v becomes gelu(v)
-      const uint32_t buf = tma_tile_acquire(tbuf, which, lane);
+      const uint32_t buf = tma_tile_acquire<NT>(tbuf, which, lane);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         float d[8];
@@ -452,21 +473,22 @@ __device__ __forceinline__ void epi_rows_bf16_tma(const GemmDev& p, const CUtens
       }
       tma_tile_release(tmD2, buf, lane, row_base, col0);
     } else {
-      if (p.D2 != nullptr) tma_store_rows_bf16(tmD2, tbuf, which, lane, v, row_base, col0);
+      if (p.D2 != nullptr) tma_store_rows_bf16<NT>(tmD2, tbuf, which, lane, v, row_base, col0);
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = gelu_fast_fwd(v[j]);
     }
   }
-  tma_store_rows_bf16(tmD, tbuf, which, lane, v, row_base, col0);
+  tma_store_rows_bf16<NT>(tmD, tbuf, which, lane, v, row_base, col0);
 }
 
 // GELU + GELU' chunk on packed pairs.  The 32 bias values of the chunk sit in this warp's shared-memory slot
 // (published by the epilogue loop one chunk ahead: with 227 KB of shared memory in use there is no L1 left, and
 // the per-chunk __ldg of the bias paid an L2 round trip in front of the math — profiles/ncu_r01c.txt).
+template <int NT>
 __device__ __forceinline__ void epi_rows_gelu_dg_packed(const CUtensorMap* tmD, const CUtensorMap* tmD2, uint32_t tbuf,
                                                         int& which, int lane, int row_base, int col0,
                                                         const uint32_t (&r)[32], uint32_t bias_slot, bool has_bias) {
-  const uint32_t bufd = tma_tile_acquire(tbuf, which, lane);   // derivative tile
+  const uint32_t bufd = tma_tile_acquire<NT>(tbuf, which, lane);   // derivative tile
   uint32_t gq[16];                                               // gelu(v) as packed bf16 pairs, stored after the loop
 #pragma unroll
   for (int j = 0; j < 4; ++j) {                                  // 8 columns per 16-byte unit
@@ -495,7 +517,7 @@ __device__ __forceinline__ void epi_rows_gelu_dg_packed(const CUtensorMap* tmD, 
       st_shared_v4(bufd + static_cast<uint32_t>(lane) * 64u + ((static_cast<uint32_t>(j) ^ x) << 4), dq[0], dq[1], dq[2], dq[3]);
   }
   tma_tile_release(tmD2, bufd, lane, row_base, col0);
-  const uint32_t bufg = tma_tile_acquire(tbuf, which, lane);   // value tile
+  const uint32_t bufg = tma_tile_acquire<NT>(tbuf, which, lane);   // value tile
   const uint32_t x = (static_cast<uint32_t>(lane) >> 1) & 3u;
 #pragma unroll
   for (int j = 0; j < 4; ++j)
@@ -522,6 +544,7 @@ __device__ __forceinline__ void aux_rows_load(const GemmDev& p, int lane, int ro
     if (row < p.M && col0 + 8 * u < p.N && !VITB_DIAG(16)) dst[u] = __ldg(reinterpret_cast<const uint4*>(ap) + u);
   }
 }
+template <int NT>
 __device__ __forceinline__ void epi_rows_mul_aux(const GemmDev& p, const CUtensorMap* tmD, uint32_t tbuf, int& which,
                                                  int lane, int row_base, int col0, const uint32_t (&r)[32],
                                                  const uint4 (&ax)[4]) {
@@ -541,7 +564,7 @@ __device__ __forceinline__ void epi_rows_mul_aux(const GemmDev& p, const CUtenso
     const float s = warp_transpose_sum32(v, lane);
     if (col0 + lane < p.N) atomicAdd(p.colsum + col0 + lane, s);
   }
-  tma_store_rows_bf16(tmD, tbuf, which, lane, v, row_base, col0);
+  tma_store_rows_bf16<NT>(tmD, tbuf, which, lane, v, row_base, col0);
 }
 
 // Scalar epilogue with every option (row bias, patch-embedding row remap, odd widths): lane == column.
@@ -589,14 +612,16 @@ __device__ __noinline__ void epi_generic(const GemmDev& p, uint32_t stg, int lan
   }
 }
 
-template <int BN, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int BN, bool A_MN, bool B_MN, int EW = 8>
+__global__ void __launch_bounds__(EpiCfg<EW>::THREADS, 1)
 vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
                  const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                  const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmD2,
                  const __grid_constant__ GemmDev p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, EW>;
+  constexpr int NT = (EW == 8) ? 2 : 1;           // TMA-store staging tiles per epilogue warp
+  constexpr int CHUNKS = (BN / 32) / (EW / 4);    // 32-column chunks of a tile drained by one epilogue warp
   pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
@@ -605,7 +630,7 @@ vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     __trap();
   }
   float* staging = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES + kStagingBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES + EpiCfg<EW>::STAGING_BYTES);
   // bars: [0,STAGES) full, [STAGES,2*STAGES) empty, then tmem_full[2], tmem_empty[2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
 
@@ -629,7 +654,7 @@ vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull0 + 8 * s, 1);
-      mbar_init(tempty0 + 8 * s, kEpiWarps);  // one arrive per epilogue warp
+      mbar_init(tempty0 + 8 * s, EW);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -643,7 +668,13 @@ vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();   // nothing above touches global memory; everything below may
 
-  const int total_tiles = p.m_tiles * p.n_tiles * p.split_k;
+  // row count from device memory (Res-ViT token compaction): only the tile loop shrinks, every bound stays M
+  int m_tiles = p.m_tiles;
+  if (p.m_dev != nullptr) {
+    const int m_eff = min(max(*p.m_dev, 0), p.M);
+    m_tiles = (m_eff + BM - 1) / BM;
+  }
+  const int total_tiles = m_tiles * p.n_tiles * p.split_k;
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
@@ -721,7 +752,10 @@ vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   } else if (warp >= kEpiWarp0) {
     // =============================== epilogue ===============================
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
-    const uint32_t stg = smem_u32(staging) + static_cast<uint32_t>((warp - kEpiWarp0) * kStagingFloats * 4);
+    const int ew = warp - kEpiWarp0;
+    // EW = 8: a 4352 B slice per warp (fp32 transpose staging, or two TMA tiles + bias slots inside it).
+    // EW = 16: 16 TMA tiles of 2 KiB, then 16 bias slots of 128 B.
+    const uint32_t stg = smem_u32(staging) + static_cast<uint32_t>(EW == 8 ? ew * kStagingFloats * 4 : ew * 2048);
     int acc = 0;
     uint32_t acc_phase = 0;
     // one register-resident mode selects the epilogue instantiation (decided once, not per chunk)
@@ -735,13 +769,14 @@ vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     // but GELU' is faster with coalesced pre-activation loads in the staged layout
     const bool tma_path = p.tma_store != 0 && (mode == 2 || mode == 4);
     uint4 side_raw[8];                            // staged epilogue: side operand of the chunk in flight (see epi_vec_body)
-    const uint32_t tbuf = (stg + 511u) & ~511u;   // two 2 KiB 64B-swizzled tiles inside this warp's staging slice
+    const uint32_t tbuf = (EW == 8) ? ((stg + 511u) & ~511u) : stg;   // 2 KiB 64B-swizzled tile(s) of this warp
     int tma_which = 0;
     if (tma_path && lane == 0) { tma_prefetch_desc(&tmD); if (p.D2 != nullptr) tma_prefetch_desc(&tmD2); }
     // packed GELU + GELU' path: the two 2 KiB store tiles leave 256 B of this warp's 4352 B slice unused (before the
     // tiles when the slice starts 256 B past a 512 B boundary, after them otherwise): two 32-float bias slots
     const bool packed = tma_path && mode == 2 && p.packed_epi != 0 && p.D2 != nullptr && p.d2_grad != 0;
-    const uint32_t bias_slots = (tbuf == stg) ? stg + 2u * kTmaTileBytes : stg;
+    const uint32_t bias_slots = (EW == 8) ? ((tbuf == stg) ? stg + 2u * kTmaTileBytes : stg)
+                                          : smem_u32(staging) + static_cast<uint32_t>(EW * 2048 + ew * 128);
     const bool has_bias = p.bias != nullptr;
     const bool rowmul = p.rowmul != 0 && mode == 3;   // bf16 MUL_AUX without bias: register layout + TMA stores
     uint4 aux_next[4];                                  // this lane's 64 bytes of aux for the chunk that comes next
@@ -752,13 +787,13 @@ vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const int row_base = t.m_blk * BM + q * 32;
       // bias-type terms are added exactly once: by the split that owns the first k-block
       const bool lead_split = (t.g0 == 0);
-      const int half = (warp - kEpiWarp0) >> 2;  // which half of the tile's columns this warp drains
+      const int half = ew >> 2;  // which group of CHUNKS 32-column chunks of the tile this warp drains
       // grouped fp32 accumulate output: group g of the columns starts d_gs (not Ng) elements after group g - 1
       const long long d_off = (p.d_gs != 0 && p.group_cols > 0) ? static_cast<long long>(n0 / p.group_cols) * (p.d_gs - p.group_cols) : 0;
       if (rowmul) {
-        aux_rows_load(p, lane, row_base, n0 + half * (BN / 64) * 32, aux_next);
-      } else {   // the side operand of this warp's first chunk is requested before the accumulator is waited for
-        const int colf = n0 + half * (BN / 64) * 32;
+        aux_rows_load(p, lane, row_base, n0 + half * CHUNKS * 32, aux_next);
+      } else if constexpr (EW == 8) {   // the side operand of this warp's first chunk is requested before the accumulator is waited for
+        const int colf = n0 + half * CHUNKS * 32;
         if (colf < p.N) {
           switch (mode) {
             case 3: side_fetch<true, VITB_EPI_GELU_BWD, 0>(p, lane, row_base, colf, lead_split, side_raw); break;
@@ -773,16 +808,16 @@ vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       }
       float bias_next = 0.f;   // packed path: lane j carries bias[col0 + j] of the chunk that comes next
       if (packed && has_bias) {
-        const int colb = n0 + half * (BN / 64) * 32 + lane;
+        const int colb = n0 + half * CHUNKS * 32 + lane;
         if (colb < p.N) bias_next = __ldg(p.bias + colb);
       }
       mbar_wait(tfull0 + 8 * acc, acc_phase);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
+      for (int c = half * CHUNKS; c < (half + 1) * CHUNKS; ++c) {
         const int col0 = n0 + c * 32;
         if (col0 >= p.N) break;
-        const int next_col0 = (c + 1 < (half + 1) * (BN / 64) && col0 + 32 < p.N) ? col0 + 32 : -1;
+        const int next_col0 = (c + 1 < (half + 1) * CHUNKS && col0 + 32 < p.N) ? col0 + 32 : -1;
         uint32_t r[32];
 #ifdef VITB_GEMM_DIAG
         if (VITB_DIAG(32)) continue;
@@ -794,7 +829,8 @@ vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                                static_cast<uint32_t>(acc * BN + c * 32), r);
         if (packed) {
-          const uint32_t slot = bias_slots + static_cast<uint32_t>(c & 1) * 128u;
+          const uint32_t slot = bias_slots + (EW == 8 ? static_cast<uint32_t>(c & 1) * 128u : 0u);   // (EW 16: one slot; the
+          // warp-level syncs of the previous chunk's store hand-off order its reads before this write)
           if (has_bias) {
             // publish this chunk's bias (requested a chunk ago) and request the next chunk's: the L2 round trip
             // runs under this chunk's math
@@ -804,7 +840,7 @@ vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             __syncwarp();
           }
           tmem_ld_wait();
-          epi_rows_gelu_dg_packed(&tmD, &tmD2, tbuf, tma_which, lane, row_base, col0, r, slot, has_bias);
+          epi_rows_gelu_dg_packed<NT>(&tmD, &tmD2, tbuf, tma_which, lane, row_base, col0, r, slot, has_bias);
           continue;
         }
         if (rowmul) {
@@ -813,15 +849,18 @@ vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           for (int u = 0; u < 4; ++u) aux_cur[u] = aux_next[u];
           if (next_col0 >= 0) aux_rows_load(p, lane, row_base, next_col0, aux_next);   // flies during this chunk
           tmem_ld_wait();
-          epi_rows_mul_aux(p, &tmD, tbuf, tma_which, lane, row_base, col0, r, aux_cur);
+          epi_rows_mul_aux<NT>(p, &tmD, tbuf, tma_which, lane, row_base, col0, r, aux_cur);
           continue;
         }
         tmem_ld_wait();
         if (tma_path) {    // bf16 outputs without residual / column sums: math in registers, tiles leave by TMA
-          if (mode == 2) epi_rows_bf16_tma<VITB_EPI_GELU>(p, &tmD, &tmD2, tbuf, tma_which, lane, row_base, col0, r);
-          else epi_rows_bf16_tma<VITB_EPI_NONE>(p, &tmD, &tmD2, tbuf, tma_which, lane, row_base, col0, r);
+          if (mode == 2) epi_rows_bf16_tma<VITB_EPI_GELU, NT>(p, &tmD, &tmD2, tbuf, tma_which, lane, row_base, col0, r);
+          else epi_rows_bf16_tma<VITB_EPI_NONE, NT>(p, &tmD, &tmD2, tbuf, tma_which, lane, row_base, col0, r);
           continue;
         }
+        if constexpr (EW != 8) {
+          __trap();   // the staged epilogues need the 8-warp staging layout; the host never selects EW = 16 for them
+        } else {
 #pragma unroll
         for (int j = 0; j < 16; ++j) st_shared_v2(stg + lane * (kStgStride * 4) + j * 8, r[2 * j], r[2 * j + 1]);
         __syncwarp();
@@ -840,6 +879,7 @@ vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           default: epi_generic(p, stg, lane, row_base, col0, lead_split); break;
         }
         __syncwarp();
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -1047,12 +1087,12 @@ int launch_wgrad_pair(const CUtensorMap* tm, GemmDev d, int M, int N, cudaStream
   return VITB_OK;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int EW = 8>
 int launch(const CUtensorMap* tm, const GemmDev& d, int grid, cudaStream_t stream) {
-  auto kern = vitb_gemm_kernel<BN, A_MN, B_MN>;
+  auto kern = vitb_gemm_kernel<BN, A_MN, B_MN, EW>;
   VITB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       Cfg<BN>::SMEM_BYTES));
-  VITB_CUDA_CHECK(vitb_launch(kern, dim3(grid), dim3(kThreads), Cfg<BN>::SMEM_BYTES, stream, tm[0], tm[1], tm[2], tm[3],
+                                       Cfg<BN, EW>::SMEM_BYTES));
+  VITB_CUDA_CHECK(vitb_launch(kern, dim3(grid), dim3(EpiCfg<EW>::THREADS), Cfg<BN, EW>::SMEM_BYTES, stream, tm[0], tm[1], tm[2], tm[3],
                               tm[4], tm[5], tm[6], tm[7], d));
   VITB_LAUNCH_CHECK("vitb_gemm_kernel");
   return VITB_OK;
@@ -1119,6 +1159,9 @@ extern "C" int VITB_GEMM_ENTRY(const vitb_gemm_params* p, void* stream_) {
   const int Ng = p->N / ngroups;
   VITB_REQUIRE(ngroups == 1 || Ng % BN == 0, VITB_ERR_UNSUPPORTED_SHAPE,
                "vitb_gemm: group width %d is not a multiple of the %d-column tile", Ng, BN);
+  VITB_REQUIRE(p->m_dev == nullptr || (!p->a_mn_major && p->split_k <= 1 && p->colsum == nullptr && !p->accumulate),
+               VITB_ERR_BAD_ARG, "vitb_gemm: m_dev needs a token-major, non-accumulating GEMM without split-K / colsum");
+  d.m_dev = p->m_dev;
   d.group_cols = ngroups > 1 ? Ng : 0;
   d.d_gs = ngroups > 1 ? p->d_group_stride : 0;
   d.m_tiles = (p->M + BM - 1) / BM;
@@ -1254,8 +1297,16 @@ extern "C" int VITB_GEMM_ENTRY(const vitb_gemm_params* p, void* stream_) {
   const long long total_tiles = (long long)d.m_tiles * d.n_tiles * d.split_k;
   const int grid = (int)(total_tiles < sms ? total_tiles : sms);
 
+  // bf16 epilogues that leave through TMA stores run with 16 epilogue warps (token-major A only: the shapes of the path)
+  bool ew16 = false;
+  {
+    const char* e16 = getenv("VITB_GEMM_EW16");     // VITB_GEMM_EW16=0 keeps the 8-warp epilogue (A/B measurements)
+    ew16 = (e16 == nullptr || atoi(e16) != 0) && !p->a_mn_major && (d.tma_store != 0 || d.rowmul != 0);
+  }
 #define VITB_DISPATCH(BN_)                                                              \
   do {                                                                                  \
+    if (ew16 && !p->b_mn_major) return launch<BN_, false, false, 16>(tm, d, grid, stream); \
+    if (ew16 && p->b_mn_major) return launch<BN_, false, true, 16>(tm, d, grid, stream);   \
     if (!p->a_mn_major && !p->b_mn_major) return launch<BN_, false, false>(tm, d, grid, stream); \
     if (!p->a_mn_major && p->b_mn_major) return launch<BN_, false, true>(tm, d, grid, stream);   \
     if (p->a_mn_major && !p->b_mn_major) return launch<BN_, true, false>(tm, d, grid, stream);   \

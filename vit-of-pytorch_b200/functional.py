@@ -1118,3 +1118,80 @@ def select_rows(a, b, index, member_ids):
     for i in member_ids:
         mask |= 1 << int(i)
     return _SelectRows.apply(a, b, index, mask)
+
+
+# --------------------------------------------------------------------------------------------------
+# Res-ViT scalar losses (one single-CTA kernel each; the kernel also writes the gradient)
+# --------------------------------------------------------------------------------------------------
+class _DistillLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, student, teacher):
+        L.require_cuda(student, teacher)
+        s2 = student if student.dim() == 2 else student.reshape(-1, student.shape[-1])
+        t2 = teacher.detach() if teacher.dim() == 2 else teacher.detach().reshape(-1, teacher.shape[-1])
+        if s2.dtype != t2.dtype:
+            s2, t2 = s2.float(), t2.float()
+        if s2.stride(-1) != 1:
+            s2 = s2.contiguous()
+        if t2.stride(-1) != 1:
+            t2 = t2.contiguous()
+        loss = torch.zeros((), dtype=F32, device=student.device)
+        ds = ops.distill_loss(s2, t2, loss, want_grad=ctx.needs_input_grad[0])
+        ctx.save_for_backward(ds)
+        ctx.meta = (student.shape, student.dtype)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (ds,) = ctx.saved_tensors
+        shape, dt = ctx.meta
+        return (ds * g).view(shape).to(dt), None
+
+
+def distill_loss(student, teacher):
+    """mean((student - teacher.detach())^2)  (DistillLoss, res-vit/model.py:40-59)."""
+    return _DistillLoss.apply(student, teacher)
+
+
+def global_mean_needed(sync_group):
+    if sync_group is None or not (torch.distributed.is_available() and torch.distributed.is_initialized()):
+        return False
+    return torch.distributed.get_world_size(None if sync_group is True else sync_group) > 1
+
+
+def global_mean_shift(shard_mean, sync_group):
+    """(mean over the process group of `shard_mean`) - shard_mean, as a detached tensor: collective plumbing only (one
+    scalar all-reduce; any device / backend), the arithmetic around it is two scalar ops.  Adding it to the shard mean
+    gives a quantity whose VALUE is the global-batch mean and whose GRADIENT is this shard's."""
+    group = None if sync_group is True else sync_group
+    world = torch.distributed.get_world_size(group)
+    m = shard_mean.detach().clone()
+    torch.distributed.all_reduce(m, op=torch.distributed.ReduceOp.SUM, group=group)
+    return (m / world - shard_mean.detach()).contiguous()
+
+
+class _ActiveLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, probs, reserve_initials, target, sync_group):
+        L.require_cuda(probs)
+        p3 = probs.float().contiguous()
+        shift = None
+        if global_mean_needed(sync_group):   # the loss of the GLOBAL batch: one scalar all-reduce of the shard means (SURVEY 8e)
+            ratio, _, _ = ops.active_loss(p3, reserve_initials, target)
+            shift = global_mean_shift(ratio, sync_group)
+        _, loss, dp = ops.active_loss(p3, reserve_initials, target, shift=shift, want_grad=ctx.needs_input_grad[0])
+        ctx.save_for_backward(dp)
+        ctx.meta = (probs.shape, probs.dtype)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (dp,) = ctx.saved_tensors
+        shape, dt = ctx.meta
+        return (dp * g).view(shape).to(dt), None, None, None
+
+
+def active_loss(probs, reserve_initials, target, sync_group=None):
+    """(mean of probs[:, reserve_initials:, :] - target)^2  (ActiveLoss, res-vit/model.py:61-85); with sync_group the mean
+    is the global batch's (value) while the gradient stays this shard's — exact once the replicas' gradients are averaged."""
+    return _ActiveLoss.apply(probs, reserve_initials, target, sync_group)

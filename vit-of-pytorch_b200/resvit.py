@@ -64,8 +64,7 @@ class DistillLoss(nn.Module):
         self.criterion = torch.nn.MSELoss()
 
     def forward(self, student_cls, teacher_cls):
-        d = student_cls.float() - teacher_cls.detach().float()
-        return (d * d).mean()
+        return F.distill_loss(student_cls, teacher_cls)      # vitb_distill_loss: value + gradient in one kernel
 
 
 class ActiveLoss(nn.Module):
@@ -91,15 +90,8 @@ class ActiveLoss(nn.Module):
         return {'non_low_rank_ratio': activation.float().mean(), 'current_target': self.target}
 
     def forward(self, activation):
-        ratio = activation[:, self.reserve_initials:, :].float().mean()
-        if self.sync_group is not None and torch.distributed.is_available() and torch.distributed.is_initialized():
-            group = None if self.sync_group is True else self.sync_group
-            world = torch.distributed.get_world_size(group)
-            if world > 1:
-                m = ratio.detach().clone()
-                torch.distributed.all_reduce(m, op=torch.distributed.ReduceOp.SUM, group=group)
-                ratio = ratio + (m / world - ratio.detach())     # value: global mean; gradient: this shard's
-        return (ratio - self.target) ** 2
+        # vitb_active_loss: masked mean, (m - t)^2 and the gradient in one kernel (+ one scalar all-reduce when synced)
+        return F.active_loss(activation, self.reserve_initials, self.target, self.sync_group)
 
 
 class PositionEmbs(nn.Module):
