@@ -295,3 +295,56 @@ def test_resvit_loss_kernels_match_the_reference_formulas():
     assert abs(float(got) - float(want)) < 1e-7
     assert rel_l2(ac.grad.cpu(), ar.grad) < 1e-6
     assert abs(float(crit.metric(ac)["non_low_rank_ratio"]) - float(a[:, 1:, :].mean())) < 1e-6
+
+
+def test_row_compaction_kernels():
+    """vitb_compact_rows / gather / scatter and the GEMM's device row count (vitb_gemm_params.m_dev)."""
+    import vitb200
+    from vitb200 import ops
+    g = torch.Generator().manual_seed(21)
+    T, D = 1000, 256
+    index = torch.randint(0, 4, (T, 1), generator=g).float().cuda()
+    rows, count = ops.compact_rows(index, [1, 3])
+    torch.cuda.synchronize()
+    want = torch.nonzero((index.view(-1) == 1) | (index.view(-1) == 3)).view(-1).int()
+    n = int(count)
+    assert n == want.numel()
+    assert torch.equal(rows[:n].sort().values.cpu(), want.cpu())
+    for dt in (torch.float32, torch.bfloat16):
+        src = torch.randn(T, D, generator=g).to(dt).cuda()
+        got = ops.gather_rows(src, rows, count)
+        assert torch.equal(got[:n], src[rows[:n].long()])
+        dst = torch.zeros(T, D, dtype=dt, device="cuda")
+        ops.scatter_rows(got, rows, count, dst)
+        ref = torch.zeros_like(dst)
+        ref[rows[:n].long()] = src[rows[:n].long()]
+        assert torch.equal(dst, ref)
+    # a GEMM over `count` rows equals the dense GEMM on those rows; tiles past the count are skipped (sentinel survives)
+    A = (torch.randn(T, D, generator=g) * 0.5).to(torch.bfloat16).cuda()
+    W = (torch.randn(512, D, generator=g) * 0.1).to(torch.bfloat16).cuda()
+    bias = torch.randn(512, generator=g).cuda()
+    dense = ops.gemm(A, W, bias=bias)
+    out = torch.full((T, 512), 7.0, dtype=torch.bfloat16, device="cuda")
+    ops.gemm(A, W, bias=bias, out=out, m_dev=count)
+    torch.cuda.synchronize()
+    assert torch.equal(out[:n], dense[:n])
+    first_skipped = (n + 127) // 128 * 128
+    assert bool((out[first_skipped:] == 7.0).all())
+
+
+@pytest.mark.parametrize("variant", ["bs2", "bs1"])
+def test_resvit_eval_token_compaction_equals_dense_select(variant, monkeypatch):
+    """Inference with device-side token compaction (output projection + MLP on the active rows only) gives the logits of
+    the dense-select path: the skipped rows' results are never used (res-vit/model.py:503-524)."""
+    import vitb200
+    g = torch.load(GOLD)[variant]
+    m = _build(g).eval()
+    res = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("VITB_RESVIT_COMPACT", flag)
+        with torch.no_grad(), vitb200.precision("bf16"):
+            m(g["img"].cuda(), g["labels"].cuda())
+        torch.cuda.synchronize()
+        res[flag] = (m.logits.float().cpu(), torch.cat([w.float() for w in m.acts], -1).cpu())
+    assert torch.equal(res["1"][1], res["0"][1])
+    assert rel_l2(res["1"][0], res["0"][0]) < 1e-5

@@ -53,25 +53,27 @@ constexpr int kStgStride = 34;                       // floats per staged row: 8
 constexpr int kStagingFloats = 32 * kStgStride;      // per epilogue warp
 constexpr int kStagingBytes = kEpiWarps * kStagingFloats * 4;
 
-// EW = number of epilogue warps.  8 (two per TMEM lane quadrant, 4352 B of staging each: every epilogue) or 16 (four per
-// quadrant, ONE 2 KiB TMA-store tile + a 128 B bias slot each: only the register-layout epilogues that leave through TMA
-// stores).  The bf16 epilogues behind a K = 768 mainloop (GELU + GELU', x gelu', bias) are bound by the latency of their
-// own dependency chains with two warps per scheduler (ncu, profiles/ncu_gemm_fc1_r02.txt: 0.4 IPC per scheduler, no
-// dominant stall); four warps per scheduler hide it.
-template <int EW>
+// DS ("deep store") trades one mainloop stage for TMA-store staging: 3 instead of 4 stages of 48 KiB (BN = 256), and FOUR
+// 2 KiB store tiles per epilogue warp instead of two.  Why: the bf16 epilogues behind a K = 768 mainloop (GELU + GELU',
+// x gelu', bias) were not limited by their arithmetic or by the number of warps — doubling the epilogue warps to 16
+// changed nothing (profiles/gemm_ew16_r02.txt) — but by the latency of their own TMA stores: a warp writes 8 to 16 tiles
+// per accumulator tile and could only have two in flight.  Used for the TMA-store epilogues with at most 1024 columns of K
+// (the mainloop of the K = 3072 GEMMs keeps its fourth stage).
+template <bool DS>
 struct EpiCfg {
-  static constexpr int THREADS = (kEpiWarp0 + EW) * 32;
-  static constexpr int STAGING_BYTES = (EW == 8) ? kStagingBytes : EW * (2048 + 128);
+  static constexpr int TILES = DS ? 4 : 2;                              // TMA-store staging tiles per epilogue warp
+  static constexpr int WARP_BYTES = DS ? 4 * 2048 + 256 : kStagingFloats * 4;
+  static constexpr int STAGING_BYTES = kEpiWarps * WARP_BYTES;
 };
 
-template <int BN, int EW = 8>
+template <int BN, bool DS = false>
 struct Cfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int STAGES = ((BN == 256) ? 4 : 6) - (DS ? 1 : 0);
   static constexpr int TMEM_COLS = 2 * BN;
   // no alignment slack: the dynamic shared window starts 1024-byte aligned (checked at kernel entry)
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EpiCfg<EW>::STAGING_BYTES + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EpiCfg<DS>::STAGING_BYTES + 256 /*barriers*/;
 };
 
 struct GemmDev {
@@ -400,19 +402,12 @@ __device__ __forceinline__ void epi_vec(const GemmDev& p, uint32_t stg, int lane
 // stores later.  Measured (profiles/gemm_bench_r01b.txt): fc1+GELU 0.167 -> 0.132 ms, fc1+bias 0.114 -> 0.105 ms.
 constexpr int kTmaTileBytes = 32 * 64;
 
-// acquire the next staging tile of this warp: the store that last read it has drained.  NT = 2: two tiles alternate
-// (the store of two stores ago); NT = 1: one tile (the previous store) — the 16-warp epilogue, where the other three
-// warps of the scheduler run while this one waits.
+// acquire the next staging tile of this warp: the store that last read it (NT stores ago) has drained
 template <int NT>
 __device__ __forceinline__ uint32_t tma_tile_acquire(uint32_t tbuf, int& which, int lane) {
-  uint32_t buf = tbuf;
-  if constexpr (NT == 2) {
-    buf += static_cast<uint32_t>(which) * kTmaTileBytes;
-    which ^= 1;
-    if (lane == 0) bulk_wait_read<1>();
-  } else {
-    if (lane == 0) bulk_wait_read<0>();
-  }
+  const uint32_t buf = tbuf + static_cast<uint32_t>(which) * kTmaTileBytes;
+  which = (which + 1 == NT) ? 0 : which + 1;
+  if (lane == 0) bulk_wait_read<NT - 1>();
   __syncwarp();
   return buf;
 }
@@ -612,16 +607,16 @@ __device__ __noinline__ void epi_generic(const GemmDev& p, uint32_t stg, int lan
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, int EW = 8>
-__global__ void __launch_bounds__(EpiCfg<EW>::THREADS, 1)
+template <int BN, bool A_MN, bool B_MN, bool DS = false>
+__global__ void __launch_bounds__(kThreads, 1)
 vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
                  const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                  const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmD2,
                  const __grid_constant__ GemmDev p) {
-  using C = Cfg<BN, EW>;
-  constexpr int NT = (EW == 8) ? 2 : 1;           // TMA-store staging tiles per epilogue warp
-  constexpr int CHUNKS = (BN / 32) / (EW / 4);    // 32-column chunks of a tile drained by one epilogue warp
+  using C = Cfg<BN, DS>;
+  constexpr int NT = EpiCfg<DS>::TILES;           // TMA-store staging tiles per epilogue warp
+  constexpr int CHUNKS = BN / 64;                 // 32-column chunks of a tile drained by one epilogue warp
   pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
@@ -630,7 +625,7 @@ vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     __trap();
   }
   float* staging = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES + EpiCfg<EW>::STAGING_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES + EpiCfg<DS>::STAGING_BYTES);
   // bars: [0,STAGES) full, [STAGES,2*STAGES) empty, then tmem_full[2], tmem_empty[2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
 
@@ -654,7 +649,7 @@ vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull0 + 8 * s, 1);
-      mbar_init(tempty0 + 8 * s, EW);  // one arrive per epilogue warp
+      mbar_init(tempty0 + 8 * s, kEpiWarps);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -753,9 +748,8 @@ vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     // =============================== epilogue ===============================
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
     const int ew = warp - kEpiWarp0;
-    // EW = 8: a 4352 B slice per warp (fp32 transpose staging, or two TMA tiles + bias slots inside it).
-    // EW = 16: 16 TMA tiles of 2 KiB, then 16 bias slots of 128 B.
-    const uint32_t stg = smem_u32(staging) + static_cast<uint32_t>(EW == 8 ? ew * kStagingFloats * 4 : ew * 2048);
+    // this warp's staging slice: the fp32 transpose staging of the staged epilogues, or the TMA-store tiles + bias slots
+    const uint32_t stg = smem_u32(staging) + static_cast<uint32_t>(ew * EpiCfg<DS>::WARP_BYTES);
     int acc = 0;
     uint32_t acc_phase = 0;
     // one register-resident mode selects the epilogue instantiation (decided once, not per chunk)
@@ -769,14 +763,13 @@ vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     // but GELU' is faster with coalesced pre-activation loads in the staged layout
     const bool tma_path = p.tma_store != 0 && (mode == 2 || mode == 4);
     uint4 side_raw[8];                            // staged epilogue: side operand of the chunk in flight (see epi_vec_body)
-    const uint32_t tbuf = (EW == 8) ? ((stg + 511u) & ~511u) : stg;   // 2 KiB 64B-swizzled tile(s) of this warp
+    const uint32_t tbuf = (stg + 511u) & ~511u;   // NT 2 KiB 64B-swizzled tiles inside this warp's staging slice
     int tma_which = 0;
     if (tma_path && lane == 0) { tma_prefetch_desc(&tmD); if (p.D2 != nullptr) tma_prefetch_desc(&tmD2); }
     // packed GELU + GELU' path: the two 2 KiB store tiles leave 256 B of this warp's 4352 B slice unused (before the
     // tiles when the slice starts 256 B past a 512 B boundary, after them otherwise): two 32-float bias slots
     const bool packed = tma_path && mode == 2 && p.packed_epi != 0 && p.D2 != nullptr && p.d2_grad != 0;
-    const uint32_t bias_slots = (EW == 8) ? ((tbuf == stg) ? stg + 2u * kTmaTileBytes : stg)
-                                          : smem_u32(staging) + static_cast<uint32_t>(EW * 2048 + ew * 128);
+    const uint32_t bias_slots = (tbuf == stg) ? stg + static_cast<uint32_t>(NT) * kTmaTileBytes : stg;
     const bool has_bias = p.bias != nullptr;
     const bool rowmul = p.rowmul != 0 && mode == 3;   // bf16 MUL_AUX without bias: register layout + TMA stores
     uint4 aux_next[4];                                  // this lane's 64 bytes of aux for the chunk that comes next
@@ -792,7 +785,7 @@ vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const long long d_off = (p.d_gs != 0 && p.group_cols > 0) ? static_cast<long long>(n0 / p.group_cols) * (p.d_gs - p.group_cols) : 0;
       if (rowmul) {
         aux_rows_load(p, lane, row_base, n0 + half * CHUNKS * 32, aux_next);
-      } else if constexpr (EW == 8) {   // the side operand of this warp's first chunk is requested before the accumulator is waited for
+      } else {   // the side operand of this warp's first chunk is requested before the accumulator is waited for
         const int colf = n0 + half * CHUNKS * 32;
         if (colf < p.N) {
           switch (mode) {
@@ -829,8 +822,7 @@ vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                                static_cast<uint32_t>(acc * BN + c * 32), r);
         if (packed) {
-          const uint32_t slot = bias_slots + (EW == 8 ? static_cast<uint32_t>(c & 1) * 128u : 0u);   // (EW 16: one slot; the
-          // warp-level syncs of the previous chunk's store hand-off order its reads before this write)
+          const uint32_t slot = bias_slots + static_cast<uint32_t>(c & 1) * 128u;
           if (has_bias) {
             // publish this chunk's bias (requested a chunk ago) and request the next chunk's: the L2 round trip
             // runs under this chunk's math
@@ -858,9 +850,6 @@ vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           else epi_rows_bf16_tma<VITB_EPI_NONE, NT>(p, &tmD, &tmD2, tbuf, tma_which, lane, row_base, col0, r);
           continue;
         }
-        if constexpr (EW != 8) {
-          __trap();   // the staged epilogues need the 8-warp staging layout; the host never selects EW = 16 for them
-        } else {
 #pragma unroll
         for (int j = 0; j < 16; ++j) st_shared_v2(stg + lane * (kStgStride * 4) + j * 8, r[2 * j], r[2 * j + 1]);
         __syncwarp();
@@ -879,7 +868,6 @@ vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           default: epi_generic(p, stg, lane, row_base, col0, lead_split); break;
         }
         __syncwarp();
-        }
       }
       tc_fence_before();
       __syncwarp();
@@ -1087,12 +1075,12 @@ int launch_wgrad_pair(const CUtensorMap* tm, GemmDev d, int M, int N, cudaStream
   return VITB_OK;
 }
 
-template <int BN, bool A_MN, bool B_MN, int EW = 8>
+template <int BN, bool A_MN, bool B_MN, bool DS = false>
 int launch(const CUtensorMap* tm, const GemmDev& d, int grid, cudaStream_t stream) {
-  auto kern = vitb_gemm_kernel<BN, A_MN, B_MN, EW>;
+  auto kern = vitb_gemm_kernel<BN, A_MN, B_MN, DS>;
   VITB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       Cfg<BN, EW>::SMEM_BYTES));
-  VITB_CUDA_CHECK(vitb_launch(kern, dim3(grid), dim3(EpiCfg<EW>::THREADS), Cfg<BN, EW>::SMEM_BYTES, stream, tm[0], tm[1], tm[2], tm[3],
+                                       Cfg<BN, DS>::SMEM_BYTES));
+  VITB_CUDA_CHECK(vitb_launch(kern, dim3(grid), dim3(kThreads), Cfg<BN, DS>::SMEM_BYTES, stream, tm[0], tm[1], tm[2], tm[3],
                               tm[4], tm[5], tm[6], tm[7], d));
   VITB_LAUNCH_CHECK("vitb_gemm_kernel");
   return VITB_OK;
@@ -1297,16 +1285,18 @@ extern "C" int VITB_GEMM_ENTRY(const vitb_gemm_params* p, void* stream_) {
   const long long total_tiles = (long long)d.m_tiles * d.n_tiles * d.split_k;
   const int grid = (int)(total_tiles < sms ? total_tiles : sms);
 
-  // bf16 epilogues that leave through TMA stores run with 16 epilogue warps (token-major A only: the shapes of the path)
-  bool ew16 = false;
+  // bf16 epilogues that leave through TMA stores behind a short mainloop: deep-store configuration (see EpiCfg)
+  bool deep = false;
   {
-    const char* e16 = getenv("VITB_GEMM_EW16");     // VITB_GEMM_EW16=0 keeps the 8-warp epilogue (A/B measurements)
-    ew16 = (e16 == nullptr || atoi(e16) != 0) && !p->a_mn_major && (d.tma_store != 0 || d.rowmul != 0);
+    const char* ds = getenv("VITB_GEMM_DEEPSTORE");     // VITB_GEMM_DEEPSTORE=0 keeps 4 stages / 2 store tiles (A/B measurements)
+    long long ksum = 0;
+    for (int sgm = 0; sgm < p->num_segments; ++sgm) ksum += p->K[sgm];
+    deep = (ds == nullptr || atoi(ds) != 0) && !p->a_mn_major && (d.tma_store != 0 || d.rowmul != 0) && ksum <= 1024;
   }
 #define VITB_DISPATCH(BN_)                                                              \
   do {                                                                                  \
-    if (ew16 && !p->b_mn_major) return launch<BN_, false, false, 16>(tm, d, grid, stream); \
-    if (ew16 && p->b_mn_major) return launch<BN_, false, true, 16>(tm, d, grid, stream);   \
+    if (deep && !p->b_mn_major) return launch<BN_, false, false, true>(tm, d, grid, stream); \
+    if (deep && p->b_mn_major) return launch<BN_, false, true, true>(tm, d, grid, stream);   \
     if (!p->a_mn_major && !p->b_mn_major) return launch<BN_, false, false>(tm, d, grid, stream); \
     if (!p->a_mn_major && p->b_mn_major) return launch<BN_, false, true>(tm, d, grid, stream);   \
     if (p->a_mn_major && !p->b_mn_major) return launch<BN_, true, false>(tm, d, grid, stream);   \

@@ -32,7 +32,7 @@ GEMM_ABLATION = False   # set by tools/epi_ablate.py: route ops.gemm to vitb_gem
 
 def gemm(A, B, *, a_mn=False, b_mn=False, out=None, out_dtype=torch.bfloat16, bias=None,
          row_bias=None, row_bias_group=0, epilogue=EPI_NONE, d2=None, residual=None, aux=None,
-         accumulate=False, split_k=0, row_remap_group=0, out_rows=None, colsum=None):
+         accumulate=False, split_k=0, row_remap_group=0, out_rows=None, colsum=None, m_dev=None):
     """D[M,N] = epilogue(sum_i A_i B_i^T) on the tcgen05 GEMM (contract: include/vitb200.h).
 
     a_mn=False: A_i is [M,K_i]; a_mn=True: A_i is stored [K_i,M].  Same for B with N.
@@ -121,6 +121,10 @@ def gemm(A, B, *, a_mn=False, b_mn=False, out=None, out_dtype=torch.bfloat16, bi
         if colsum.dtype != torch.float32 or colsum.numel() != N or not colsum.is_contiguous():
             raise L.VitbError("gemm: colsum must be contiguous fp32 [N]")
         p.colsum = colsum.data_ptr()
+    if m_dev is not None:       # device scalar: rows of A / D that hold data (Res-ViT token compaction)
+        if m_dev.dtype != torch.int32 or m_dev.numel() != 1 or not m_dev.is_cuda:
+            raise L.VitbError("gemm: m_dev must be an int32 CUDA scalar")
+        p.m_dev = m_dev.data_ptr()
     if PROFILE_GEMM is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -468,6 +472,51 @@ def sumsq(x, out):
 def clip_coef(sumsq_t, max_norm, coef, norm_out=None):
     L.check(L._vitb_clip_coef(L.ptr(sumsq_t), float(max_norm), L.ptr(coef), L.ptr(norm_out),
                               L.stream_ptr(coef.device)), "vitb_clip_coef")
+
+
+# --------------------------------------------------------------------------------------------------
+# Res-ViT token compaction (inference): the row list and its length never leave the device
+# --------------------------------------------------------------------------------------------------
+def _member_mask(member_ids):
+    mask = 0
+    for i in member_ids:
+        mask |= 1 << int(i)
+    return mask
+
+
+def compact_rows(index, member_ids):
+    """index [..., 1] fp32 packed router indices -> (rows int32 [T], count int32 [1]): the rows t whose index is in
+    member_ids, in unspecified order; only rows[:count] is meaningful."""
+    L.require_cuda(index)
+    idx = index.detach().reshape(-1).float().contiguous()
+    T = idx.numel()
+    rows = torch.empty(T, dtype=torch.int32, device=idx.device)
+    count = torch.zeros(1, dtype=torch.int32, device=idx.device)
+    L.check(L._vitb_compact_rows(L.ptr(idx), _member_mask(member_ids), T, L.ptr(rows), L.ptr(count), L.stream_ptr(idx.device)),
+            "vitb_compact_rows")
+    return rows, count
+
+
+def gather_rows(src, rows, count):
+    """dst[i] = src[rows[i]] for i < count; dst has src's capacity ([T, cols]), rows >= count are left uninitialised."""
+    L.require_cuda(src, rows, count)
+    _check_2d_rowmajor(src, "src")
+    dst = torch.empty((rows.numel(), src.shape[1]), dtype=src.dtype, device=src.device)
+    L.check(L._vitb_gather_rows(L.ptr(src), src.stride(0), L.dtype_code(src), L.ptr(rows), L.ptr(count), rows.numel(),
+                                src.shape[1], L.ptr(dst), dst.stride(0), L.stream_ptr(src.device)), "vitb_gather_rows")
+    return dst
+
+
+def scatter_rows(src, rows, count, dst):
+    """dst[rows[i]] = src[i] for i < count (in place)."""
+    L.require_cuda(src, rows, count, dst)
+    _check_2d_rowmajor(src, "src")
+    _check_2d_rowmajor(dst, "dst")
+    if src.dtype != dst.dtype or src.shape[1] != dst.shape[1]:
+        raise L.VitbError("scatter_rows: src / dst must share dtype and width")
+    L.check(L._vitb_scatter_rows(L.ptr(src), src.stride(0), L.dtype_code(src), L.ptr(rows), L.ptr(count), rows.numel(),
+                                 src.shape[1], L.ptr(dst), dst.stride(0), L.stream_ptr(src.device)), "vitb_scatter_rows")
+    return dst
 
 
 # --------------------------------------------------------------------------------------------------

@@ -292,6 +292,13 @@ class BlockPathApproximators(nn.Module):
         return x
 
 
+def _compaction_enabled():
+    """VITB_RESVIT_COMPACT (read per call): 1 (default) = inference skips the inactive tokens' output projection and MLP
+    (device-side row compaction); 0 = the dense-select path (every row computed, rows selected afterwards)."""
+    import os
+    return os.environ.get("VITB_RESVIT_COMPACT", "1") != "0"
+
+
 class TransformerBlock(nn.Module):
     def __init__(self, layer_id: int, args: ModelArgs):
         super().__init__()
@@ -324,6 +331,42 @@ class TransformerBlock(nn.Module):
         x = x if x.dtype == torch.float32 else x.float()
         h = self.attention(self.attention_norm(x), residual=x)
         return h, self.feed_forward(self.ffn_norm(h), residual=h)
+
+    def _eval_compacted(self, x, router_indices, transformer_ids):
+        """Inference with real token skipping (res-vit/model.py:503-524): the attention output projection and the whole
+        MLP run on the ACTIVE rows only, compacted on the device.  Attention itself stays dense over the queries — output
+        row i depends on q_i alone, and at 4 % of the layer's FLOPs a variable-length query kernel would buy little —
+        so q | k | v and softmax(qk^T)v see every token; then
+            rows, count = active rows (device list + device count, nothing is read back)
+            h_c  = o[rows] Wo^T + bo + x[rows]          GEMM over `count` rows (vitb_gemm_params.m_dev)
+            y_c  = h_c + fc2(GELU(fc1(LN(h_c))))        same
+            out  = x, out[rows] = y_c
+        which is exactly `mask * output + (~mask) * x` of the reference: the skipped rows' attention / MLP results are
+        never used there either.  Buffers keep the capacity of the dense tensors (B * N rows)."""
+        from . import ops
+        att, ff = self.attention, self.feed_forward
+        bsz, seqlen, D = x.shape
+        x2 = x.reshape(bsz * seqlen, D)
+        xn = self.attention_norm(x)
+        lora = None
+        if att.use_lora:
+            lora = (att.lora_q.lora_A.weight, att.lora_q.lora_B.weight, att.lora_k.lora_A.weight,
+                    att.lora_k.lora_B.weight, att.lora_v.lora_A.weight, att.lora_v.lora_B.weight)
+        qkv = F.qkv_proj(xn, att.wq.weight, att.wq.bias, att.wk.weight, att.wk.bias, att.wv.weight, att.wv.bias,
+                         layout="nk", lora=lora)
+        o = F.attention_packed(qkv, att.n_local_heads).reshape(bsz * seqlen, D)
+        rows, count = ops.compact_rows(router_indices, transformer_ids)
+        o_c = ops.gather_rows(o, rows, count)
+        x_c = ops.gather_rows(x2, rows, count)
+        h_c = ops.gemm(o_c, F.SHADOW.get(att.wo.weight, False)[0], out_dtype=torch.float32, bias=att.wo.bias.detach(),
+                       residual=x_c, m_dev=count)
+        hn_c = self.ffn_norm(h_c)                                  # (over the capacity; rows past count are scratch)
+        a_c = ops.gemm(hn_c, F.SHADOW.get(ff.fc1.weight, False)[0], bias=ff.fc1.bias.detach(), epilogue=ops.EPI_GELU, m_dev=count)
+        y_c = ops.gemm(a_c, F.SHADOW.get(ff.fc2.weight, False)[0], out_dtype=torch.float32, bias=ff.fc2.bias.detach(),
+                       residual=h_c, m_dev=count)
+        out = x2.clone()
+        ops.scatter_rows(y_c, rows, count, out)
+        return out.view(bsz, seqlen, D)
 
     def forward(self, x, teacher_x=None, block_info=None, LRA_mask=None):
         bsz, seqlen, _ = x.shape
@@ -363,8 +406,12 @@ class TransformerBlock(nn.Module):
             student_out = F.select_rows(transformer_out, x, router_indices, transformer_ids)
             student_out = approximators(student_out, router_indices, approx_ids)
             return teacher_out, student_out, w, block_info
-        # eval: attention for all rows (row i depends on q_i only), keep it on the active rows
         x = x if x.dtype == torch.float32 else x.float()
+        if _compaction_enabled() and not torch.is_grad_enabled() and F.get_precision() == "bf16":
+            student_out = self._eval_compacted(x, router_indices, transformer_ids)
+            student_out = approximators(student_out, router_indices, approx_ids)
+            return student_out, w, block_info
+        # dense eval: attention for all rows (row i depends on q_i only), keep it on the active rows
         attn_plus_x = self.attention(self.attention_norm(x), residual=x)
         h = F.select_rows(attn_plus_x, x, router_indices, transformer_ids)
         output = self.feed_forward(self.ffn_norm(h), residual=h)
