@@ -1,0 +1,37 @@
+"""Times the gradient exchange of the data-parallel step alone: NCCL all-reduce (AVG) of a flat fp32 buffer the size of the
+model's gradients (ViT-B/16: 85.88 M values = 343.5 MB; ViT-L/16: 1213.6 MB), CUDA events, max over ranks.  Launch with
+torchrun --nproc-per-node N.  Prints one line on rank 0: ms per all-reduce, algorithmic and bus bandwidth."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+local = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+world, rank = dist.get_world_size(), dist.get_rank()
+for name, n in (("ViT-B/16", 85_875_556), ("ViT-L/16", 303_400_000), ("Res-ViT trainable", 14_955_896)):
+    buf = torch.randn(n, device=dev)
+    for _ in range(5):
+        dist.all_reduce(buf, op=dist.ReduceOp.AVG)
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        dist.all_reduce(buf, op=dist.ReduceOp.AVG)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / 20], device=dev, dtype=torch.float64)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        t = float(ms) / 1e3
+        gb = n * 4 / 1e9
+        print("all-reduce %s: %.1f MB fp32 on %d GPUs: %.3f ms, algbw %.0f GB/s, busbw %.0f GB/s"
+              % (name, gb * 1e3, world, t * 1e3, gb / t, gb / t * 2 * (world - 1) / world), flush=True)
+    del buf
+dist.barrier()
+torch.cuda.synchronize()
+os._exit(0)

@@ -53,27 +53,19 @@ constexpr int kStgStride = 34;                       // floats per staged row: 8
 constexpr int kStagingFloats = 32 * kStgStride;      // per epilogue warp
 constexpr int kStagingBytes = kEpiWarps * kStagingFloats * 4;
 
-// DS ("deep store") trades one mainloop stage for TMA-store staging: 3 instead of 4 stages of 48 KiB (BN = 256), and FOUR
-// 2 KiB store tiles per epilogue warp instead of two.  Why: the bf16 epilogues behind a K = 768 mainloop (GELU + GELU',
-// x gelu', bias) were not limited by their arithmetic or by the number of warps — doubling the epilogue warps to 16
-// changed nothing (profiles/gemm_ew16_r02.txt) — but by the latency of their own TMA stores: a warp writes 8 to 16 tiles
-// per accumulator tile and could only have two in flight.  Used for the TMA-store epilogues with at most 1024 columns of K
-// (the mainloop of the K = 3072 GEMMs keeps its fourth stage).
-template <bool DS>
-struct EpiCfg {
-  static constexpr int TILES = DS ? 4 : 2;                              // TMA-store staging tiles per epilogue warp
-  static constexpr int WARP_BYTES = DS ? 4 * 2048 + 256 : kStagingFloats * 4;
-  static constexpr int STAGING_BYTES = kEpiWarps * WARP_BYTES;
-};
-
-template <int BN, bool DS = false>
+// Two experiments of round 2 changed this configuration and were removed again because they bought nothing (A/B files
+// under profiles/): 16 epilogue warps instead of 8 (gemm_ew16_r02.txt) and four TMA-store tiles per warp paid for with the
+// fourth mainloop stage (gemm_deepstore_r02.txt).  The bf16 epilogues behind a K = 768 mainloop are therefore limited
+// neither by warp-level latency hiding nor by the depth of their store pipeline; what they share with the mainloop is the
+// L2: a 128 x 256 tile pulls 590 KB of operands for 50 MFLOP, and every output byte competes with that stream.
+template <int BN>
 struct Cfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = ((BN == 256) ? 4 : 6) - (DS ? 1 : 0);
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
   static constexpr int TMEM_COLS = 2 * BN;
   // no alignment slack: the dynamic shared window starts 1024-byte aligned (checked at kernel entry)
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EpiCfg<DS>::STAGING_BYTES + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + kStagingBytes + 256 /*barriers*/;
 };
 
 struct GemmDev {
@@ -607,15 +599,15 @@ __device__ __noinline__ void epi_generic(const GemmDev& p, uint32_t stg, int lan
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, bool DS = false>
+template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kThreads, 1)
 vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
                  const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                  const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmD2,
                  const __grid_constant__ GemmDev p) {
-  using C = Cfg<BN, DS>;
-  constexpr int NT = EpiCfg<DS>::TILES;           // TMA-store staging tiles per epilogue warp
+  using C = Cfg<BN>;
+  constexpr int NT = 2;                           // TMA-store staging tiles per epilogue warp
   constexpr int CHUNKS = BN / 64;                 // 32-column chunks of a tile drained by one epilogue warp
   pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -625,7 +617,7 @@ vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     __trap();
   }
   float* staging = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES + EpiCfg<DS>::STAGING_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES + kStagingBytes);
   // bars: [0,STAGES) full, [STAGES,2*STAGES) empty, then tmem_full[2], tmem_empty[2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
 
@@ -749,7 +741,7 @@ vitb_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
     const int ew = warp - kEpiWarp0;
     // this warp's staging slice: the fp32 transpose staging of the staged epilogues, or the TMA-store tiles + bias slots
-    const uint32_t stg = smem_u32(staging) + static_cast<uint32_t>(ew * EpiCfg<DS>::WARP_BYTES);
+    const uint32_t stg = smem_u32(staging) + static_cast<uint32_t>(ew * kStagingFloats * 4);
     int acc = 0;
     uint32_t acc_phase = 0;
     // one register-resident mode selects the epilogue instantiation (decided once, not per chunk)
@@ -1075,12 +1067,12 @@ int launch_wgrad_pair(const CUtensorMap* tm, GemmDev d, int M, int N, cudaStream
   return VITB_OK;
 }
 
-template <int BN, bool A_MN, bool B_MN, bool DS = false>
+template <int BN, bool A_MN, bool B_MN>
 int launch(const CUtensorMap* tm, const GemmDev& d, int grid, cudaStream_t stream) {
-  auto kern = vitb_gemm_kernel<BN, A_MN, B_MN, DS>;
+  auto kern = vitb_gemm_kernel<BN, A_MN, B_MN>;
   VITB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       Cfg<BN, DS>::SMEM_BYTES));
-  VITB_CUDA_CHECK(vitb_launch(kern, dim3(grid), dim3(kThreads), Cfg<BN, DS>::SMEM_BYTES, stream, tm[0], tm[1], tm[2], tm[3],
+                                       Cfg<BN>::SMEM_BYTES));
+  VITB_CUDA_CHECK(vitb_launch(kern, dim3(grid), dim3(kThreads), Cfg<BN>::SMEM_BYTES, stream, tm[0], tm[1], tm[2], tm[3],
                               tm[4], tm[5], tm[6], tm[7], d));
   VITB_LAUNCH_CHECK("vitb_gemm_kernel");
   return VITB_OK;
@@ -1285,18 +1277,8 @@ extern "C" int VITB_GEMM_ENTRY(const vitb_gemm_params* p, void* stream_) {
   const long long total_tiles = (long long)d.m_tiles * d.n_tiles * d.split_k;
   const int grid = (int)(total_tiles < sms ? total_tiles : sms);
 
-  // bf16 epilogues that leave through TMA stores behind a short mainloop: deep-store configuration (see EpiCfg)
-  bool deep = false;
-  {
-    const char* ds = getenv("VITB_GEMM_DEEPSTORE");     // VITB_GEMM_DEEPSTORE=0 keeps 4 stages / 2 store tiles (A/B measurements)
-    long long ksum = 0;
-    for (int sgm = 0; sgm < p->num_segments; ++sgm) ksum += p->K[sgm];
-    deep = (ds == nullptr || atoi(ds) != 0) && !p->a_mn_major && (d.tma_store != 0 || d.rowmul != 0) && ksum <= 1024;
-  }
 #define VITB_DISPATCH(BN_)                                                              \
   do {                                                                                  \
-    if (deep && !p->b_mn_major) return launch<BN_, false, false, true>(tm, d, grid, stream); \
-    if (deep && p->b_mn_major) return launch<BN_, false, true, true>(tm, d, grid, stream);   \
     if (!p->a_mn_major && !p->b_mn_major) return launch<BN_, false, false>(tm, d, grid, stream); \
     if (!p->a_mn_major && p->b_mn_major) return launch<BN_, false, true>(tm, d, grid, stream);   \
     if (p->a_mn_major && !p->b_mn_major) return launch<BN_, true, false>(tm, d, grid, stream);   \

@@ -408,13 +408,14 @@ class _Mlp(torch.autograd.Function):
         rows = x2.shape[0]
         adt = _act_dtype()
         h = torch.empty((rows, Mh), dtype=adt, device=x.device)
-        z = torch.empty((rows, Mh), dtype=adt, device=x.device)
+        need_bwd = any(ctx.needs_input_grad)     # inference: no second output (77 MB per layer at ViT-B/16 batch 128)
+        z = torch.empty((rows, Mh), dtype=adt, device=x.device) if need_bwd else None
         A, B = _pairs(xo, _weight_operand(w1, (Mh, D)))
         # bf16 activations: the forward epilogue stores gelu'(z) in place of z (it has exp(-z^2/2) and the cdf at
         # hand anyway), so the fc2 dgrad epilogue is a plain multiply instead of 17 instructions per element
         ctx.z_is_grad = adt == BF16
         ops.gemm(A, B, out=h, bias=b1.detach() if b1 is not None else None,
-                 epilogue=ops.EPI_GELU_DG if ctx.z_is_grad else ops.EPI_GELU, d2=z)
+                 epilogue=ops.EPI_GELU_DG if (ctx.z_is_grad and need_bwd) else ops.EPI_GELU, d2=z)
         ho = _operand(h)
         A, B = _pairs(ho, _weight_operand(w2, (Do, Mh)))
         res2 = _as2d(residual, Do) if residual is not None else None
@@ -903,9 +904,13 @@ class _EncoderBlockFused(torch.autograd.Function):
         ops.gemm(o2, SHADOW.get(wo, False)[0].view(D, D), b_mn=True, out=h, bias=bo.detach().view(-1), residual=x2)
         _, hn, _, mean2, rstd2 = ops.layernorm_fwd(h, n2w.detach(), n2b.detach(), eps2)
         a = torch.empty((T, Mh), dtype=BF16, device=dev)
-        z = torch.empty((T, Mh), dtype=BF16, device=dev)
-        # z holds gelu'(fc1 pre-activation), not the pre-activation itself (VITB_EPI_GELU_DG / VITB_EPI_MUL_AUX)
-        ops.gemm(hn, SHADOW.get(w1, False)[0], out=a, bias=b1.detach(), epilogue=ops.EPI_GELU_DG, d2=z)
+        if any(ctx.needs_input_grad):
+            z = torch.empty((T, Mh), dtype=BF16, device=dev)
+            # z holds gelu'(fc1 pre-activation), not the pre-activation itself (VITB_EPI_GELU_DG / VITB_EPI_MUL_AUX)
+            ops.gemm(hn, SHADOW.get(w1, False)[0], out=a, bias=b1.detach(), epilogue=ops.EPI_GELU_DG, d2=z)
+        else:       # inference: no derivative output (77 MB per layer at ViT-B/16 batch 128)
+            z = a
+            ops.gemm(hn, SHADOW.get(w1, False)[0], out=a, bias=b1.detach(), epilogue=ops.EPI_GELU)
         y = torch.empty((T, D), dtype=F32, device=dev)
         ops.gemm(a, SHADOW.get(w2, False)[0], out=y, bias=b2.detach(), residual=h)
         ctx.save_for_backward(x2, xn, mean1, rstd1, qkv, o, lse, h, hn, mean2, rstd2, z, a)
@@ -966,14 +971,14 @@ class _EncoderBlockFused(torch.autograd.Function):
         acc, r = _acc(wo, (D, D))
         ret(wo, r)
         ops.gemm(o.view(T, D), dhb, a_mn=True, b_mn=True, out=acc, accumulate=True)     # dWo[K,N] = o^T dh
-        do = ops.gemm(dhb, SHADOW.get(wo, False)[0].view(D, D), b_mn=False, out_dtype=BF16)
-        qkv3 = qkv.view(Bsz, N, 3 * D)
-        dqkv = torch.empty((Bsz, N, 3 * D), dtype=BF16, device=dev)
         accs = []
         for b in (bq, bk, bv):
             accb, r = _acc(b)
             ret(b, r)
             accs.append(accb.view(-1))
+        do = ops.gemm(dhb, SHADOW.get(wo, False)[0].view(D, D), b_mn=False, out_dtype=BF16, colsum=accs[2])   # + d(bias v)
+        qkv3 = qkv.view(Bsz, N, 3 * D)
+        dqkv = torch.empty((Bsz, N, 3 * D), dtype=BF16, device=dev)
         ops.attn_bwd(do.view(Bsz, N, D), qkv3[:, :, :D], qkv3[:, :, D:2 * D], qkv3[:, :, 2 * D:], o, lse, H,
                      dq=dqkv[:, :, :D], dk=dqkv[:, :, D:2 * D], dv=dqkv[:, :, 2 * D:])
         dq2 = dqkv.view(T, 3 * D)
@@ -988,7 +993,11 @@ class _EncoderBlockFused(torch.autograd.Function):
         else:
             for i, acc in enumerate(accs_w):
                 ops.gemm(xn, dq2[:, i * D:(i + 1) * D], a_mn=True, b_mn=True, out=acc, accumulate=True)   # dW[K,N] = xn^T dQ
-        ops.colsum3(dq2, accs[0], accs[1], accs[2])
+        # bias gradients of q | k | v = column sums of dQ | dK | dV over all tokens.  Two of the three need no pass over
+        # dqkv: sum_j dV[j] = sum_i (sum_j P[i,j]) dO[i] = sum_i dO[i] (softmax rows sum to one) — taken by the GEMM that
+        # produced dO, in its epilogue — and sum_j dK[j] = sum_i (sum_j dS[i,j]) Q[i] = 0 (sum_j dS[i,j] = D_i - D_i: the
+        # scores are invariant to a key bias; the reference's value for it is rounding noise around zero).
+        ops.colsum(dq2[:, :D], accs[0])
         dxn = ops.gemm([dq2[:, :D], dq2[:, D:2 * D], dq2[:, 2 * D:]],
                        [SHADOW.get(w, False)[0].view(D, D) for w in (wq, wk, wv)], b_mn=False, out_dtype=BF16)
         # ---- LN1 backward + residual: dx = dh + LN'(dxn) ----
