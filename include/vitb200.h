@@ -116,13 +116,6 @@ typedef struct vitb_gemm_params {
 } vitb_gemm_params;
 
 int vitb_gemm(const vitb_gemm_params* p, void* stream);
-/* ABLATION BUILD of the same kernel (diagnostics only, results are wrong by construction): vitb_gemm_diag_mask sets a
- * bit mask that switches parts of the epilogue off (1 TMA store issue, 2 epilogue math, 4 TMEM load, 8 staging-tile
- * writes, 16 side / bias loads, 32 all per-chunk work, 64 async-proxy fence, 128 column sums); vitb_gemm_diag then runs
- * the GEMM without them so one GPU call can time what each part costs (tools/epi_ablate.py).  vitb_gemm itself is
- * compiled without any of this. */
-int vitb_gemm_diag_mask(int mask);
-int vitb_gemm_diag(const vitb_gemm_params* p, void* stream);
 
 /* ---- LayerNorm ----------------------------------------------------------------------------------
  * nn.LayerNorm(D, eps) — src/model.py:108,114,146 (calls :119,:127,:155); res-vit/model.py:119-130.

@@ -16,6 +16,19 @@ import vitb200  # noqa: E402
 from vitb200 import ops  # noqa: E402
 
 L = vitb200._lib
+# the ablation build lives in a separate diagnostics library (vit-of-pytorch_b200/build.py --tools), not in the product .so
+import ctypes  # noqa: E402
+import importlib.util  # noqa: E402
+_spec = importlib.util.spec_from_file_location("_vitb_build", os.path.join(os.path.dirname(L.LIB_PATH), "build.py"))
+_b = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(_b)
+if not os.path.exists(_b.TOOLS_LIB):
+    _b.build_tools()
+_tools = ctypes.CDLL(_b.TOOLS_LIB)
+_tools.vitb_gemm_diag.argtypes = [ctypes.POINTER(L.GemmParams), ctypes.c_void_p]
+_tools.vitb_gemm_diag.restype = ctypes.c_int
+_tools.vitb_gemm_diag_mask.argtypes = [ctypes.c_int]
+_tools.vitb_gemm_diag_mask.restype = ctypes.c_int
 
 
 def timeit(fn, iters=20, warm=3):
@@ -55,18 +68,18 @@ cases = {
 }
 masks = [0, 32, 1, 1 | 8, 1 | 8 | 64, 2, 4, 16, 128, 1 | 2 | 8 | 16 | 64 | 128]
 lines = []
-ops.GEMM_ABLATION = True
+ops.GEMM_OVERRIDE = _tools.vitb_gemm_diag
 try:
     for name, fn in cases.items():
         row = []
         for m in masks:
-            assert L.vitb_gemm_diag_mask(m) == 0, L.last_error()
+            assert _tools.vitb_gemm_diag_mask(m) == 0
             row.append("%d:%.4f" % (m, timeit(fn)))
         lines.append("%-38s %s" % (name, "  ".join(row)))
         print(lines[-1], flush=True)
 finally:
-    L.vitb_gemm_diag_mask(0)
-    ops.GEMM_ABLATION = False
+    _tools.vitb_gemm_diag_mask(0)
+    ops.GEMM_OVERRIDE = None
 os.makedirs("gpurun_out", exist_ok=True)
 with open("gpurun_out/epi_ablate.txt", "w") as fh:
     fh.write("mask:ms per launch (ablation build; mask bits in tools/epi_ablate.py)\n" + "\n".join(lines) + "\n")

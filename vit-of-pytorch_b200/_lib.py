@@ -84,8 +84,6 @@ _vitb_last_error = _sig("vitb_last_error", [C.c_char_p, C.c_size_t])
 vitb_device_check = _sig("vitb_device_check", [])
 vitb_struct_size = _sig("vitb_struct_size", [C.c_int])
 _vitb_gemm = _sig("vitb_gemm", [C.POINTER(GemmParams), C.c_void_p])
-_vitb_gemm_diag = _sig("vitb_gemm_diag", [C.POINTER(GemmParams), C.c_void_p])      # ablation build (tools/epi_ablate.py)
-vitb_gemm_diag_mask = _sig("vitb_gemm_diag_mask", [C.c_int])
 
 
 def last_error():
@@ -210,6 +208,6 @@ EXPORTED_SYMBOLS = [
     "vitb_embed_bwd", "vitb_colsum", "vitb_cross_entropy", "vitb_sgd_momentum", "vitb_adamw",
     "vitb_sumsq", "vitb_clip_coef", "vitb_gelu_bwd", "vitb_router_decide_fwd", "vitb_router_decide_bwd",
     "vitb_token_mean_fwd", "vitb_token_mean_bwd", "vitb_select_rows", "vitb_colsum3",
-    "vitb_resize_tables_host", "vitb_image_prep", "vitb_gemm_diag", "vitb_gemm_diag_mask",
+    "vitb_resize_tables_host", "vitb_image_prep",
     "vitb_distill_loss", "vitb_active_loss", "vitb_compact_rows", "vitb_gather_rows", "vitb_scatter_rows", "vitb_attn_ws_supported", "vitb_attn_fwd_ws", "vitb_attn_bwd_ws",
 ]

@@ -34,11 +34,13 @@ def _nvcc():
     raise RuntimeError("nvcc not found (set NVCC)")
 
 
-# extra objects compiled from the same source with other macros: (source, object stem, extra flags)
-VARIANTS = [
+# Diagnostics library (NOT part of the product): objects compiled from the same sources with other macros and linked into
+# libvitb200_tools.so by build_tools() — (source, object stem, extra flags)
+TOOL_VARIANTS = [
     # ablation build of the GEMM (entry points vitb_gemm_diag / vitb_gemm_diag_mask, tools/epi_ablate.py)
     ("vitb_gemm.cu", "vitb_gemm_diag", ["-DVITB_GEMM_DIAG=1"]),
 ]
+TOOLS_LIB = os.path.join(HERE, "libvitb200_tools.so")
 
 
 def sources():
@@ -78,7 +80,7 @@ def build(verbose=False, force=False):
     if force:
         for f in os.listdir(OBJ):
             os.remove(os.path.join(OBJ, f))
-    jobs = [(s, None, ()) for s in sources()] + [(s, stem, tuple(extra)) for s, stem, extra in VARIANTS]
+    jobs = [(s, None, ()) for s in sources()]
     with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
         results = list(ex.map(lambda j: _compile_one(nvcc, j[0], verbose, j[1], j[2]), jobs))
     objs = [r[0] for r in results]
@@ -94,5 +96,21 @@ def build(verbose=False, force=False):
     return LIB
 
 
+def build_tools(verbose=False):
+    """libvitb200_tools.so: the ablation build of the GEMM plus the library-level objects it needs (error text, TMA
+    descriptor encoding).  Loaded only by tools/epi_ablate.py."""
+    nvcc = _nvcc()
+    os.makedirs(OBJ, exist_ok=True)
+    objs = [_compile_one(nvcc, src, verbose, stem, tuple(extra))[0] for src, stem, extra in TOOL_VARIANTS]
+    objs.append(_compile_one(nvcc, "vitb_api.cu", verbose)[0])
+    res = subprocess.run([nvcc, "-shared", "-o", TOOLS_LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"],
+                         capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("link failed:\n%s\n%s" % (res.stdout, res.stderr))
+    return TOOLS_LIB
+
+
 if __name__ == "__main__":
     print(build(verbose="-v" in sys.argv, force="-f" in sys.argv))
+    if "--tools" in sys.argv:
+        print(build_tools(verbose="-v" in sys.argv))

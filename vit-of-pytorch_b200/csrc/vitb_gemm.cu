@@ -24,10 +24,10 @@
 #include "../../include/vitb200.h"
 #include "vitb_common.cuh"
 
-// Ablation build (vit-of-pytorch_b200/build.py compiles this file a second time with -DVITB_GEMM_DIAG=1 into the
-// entry points vitb_gemm_diag / vitb_gemm_diag_mask): a bit mask switches parts of the epilogue OFF so that one GPU
-// call can time the kernel without them (tools/epi_ablate.py).  Results are then WRONG by construction; the product
-// entry point vitb_gemm is compiled without the macro and contains none of this.
+// Ablation build (vit-of-pytorch_b200/build.py --tools compiles this file a second time with -DVITB_GEMM_DIAG=1 into the
+// entry points vitb_gemm_diag / vitb_gemm_diag_mask of a SEPARATE diagnostics library, libvitb200_tools.so): a bit mask
+// switches parts of the epilogue OFF so that one GPU call can time the kernel without them (tools/epi_ablate.py).
+// Results are then WRONG by construction; the product library contains none of this.
 //   1 no TMA store issue   2 no epilogue math   4 no TMEM load   8 no staging-tile writes   16 no side / bias loads
 //   32 no per-chunk work at all (handshakes only: the bare mainloop)   64 no async-proxy fence   128 no column sums
 #ifdef VITB_GEMM_DIAG
@@ -1081,6 +1081,7 @@ int launch(const CUtensorMap* tm, const GemmDev& d, int grid, cudaStream_t strea
 }  // namespace
 
 #ifdef VITB_GEMM_DIAG
+extern "C" int vitb_gemm_diag(const vitb_gemm_params* p, void* stream);
 extern "C" int vitb_gemm_diag_mask(int mask) {   // synchronising; ablation tool only
   VITB_CUDA_CHECK(cudaMemcpyToSymbol(g_diag_mask, &mask, sizeof(int)));
   return VITB_OK;

@@ -27,7 +27,7 @@ def _check_2d_rowmajor(t, what):
                           % (what, tuple(t.shape), tuple(t.stride())))
 
 
-GEMM_ABLATION = False   # set by tools/epi_ablate.py: route ops.gemm to vitb_gemm_diag
+GEMM_OVERRIDE = None    # tools/epi_ablate.py sets this to the ablation build's entry point (a separate tools library)
 
 
 def gemm(A, B, *, a_mn=False, b_mn=False, out=None, out_dtype=torch.bfloat16, bias=None,
@@ -136,8 +136,8 @@ def gemm(A, B, *, a_mn=False, b_mn=False, out=None, out_dtype=torch.bfloat16, bi
             (M * N * residual.element_size() if residual is not None else 0)
         PROFILE_GEMM.append((e0, e1, 2.0 * M * N * ksum, nbytes))
         return out
-    if GEMM_ABLATION:      # tools/epi_ablate.py only: the ablation build of the kernel (results wrong by construction)
-        L.check(L._vitb_gemm_diag(C.byref(p), L.stream_ptr(out.device)), "vitb_gemm_diag")
+    if GEMM_OVERRIDE is not None:      # tools/epi_ablate.py only: the ablation build (results wrong by construction)
+        L.check(GEMM_OVERRIDE(C.byref(p), L.stream_ptr(out.device)), "vitb_gemm_diag")
         return out
     L.check(L._vitb_gemm(C.byref(p), L.stream_ptr(out.device)), "vitb_gemm")
     return out
