@@ -135,6 +135,14 @@ int vitb_layernorm_bwd(const void* dy, int dy_dtype, const float* x, int64_t x_r
                        const float* dres, int64_t dres_row_stride, float* dx_f32,
                        int64_t dx_row_stride, void* dx_bf16, void* dx_bf16_lo, float* dgamma,
                        float* dbeta, float* dcolsum, void* stream);
+/* Same, when only every dres_every-th row has a residual-branch gradient (dres row r / dres_every belongs to row r,
+ * r % dres_every == 0): the class-token-only last encoder block, where of an image's N rows only row 0 is read
+ * downstream (src/model.py:155,210). */
+int vitb_layernorm_bwd_sparse_res(const void* dy, int dy_dtype, const float* x, int64_t x_row_stride,
+                                  const float* mean, const float* rstd, const float* gamma, int rows, int D,
+                                  const float* dres, int64_t dres_row_stride, int dres_every, float* dx_f32,
+                                  int64_t dx_row_stride, void* dx_bf16, void* dx_bf16_lo, float* dgamma,
+                                  float* dbeta, float* dcolsum, void* stream);
 
 /* ---- attention ----------------------------------------------------------------------------------
  * softmax(q k^T / sqrt(dh)) v with no mask and no dropout — SelfAttention.forward
@@ -183,6 +191,12 @@ int vitb_attn_fwd_ws(const vitb_attn_params* p, void* stream);
 int vitb_attn_bwd_ws(const vitb_attn_params* p, void* stream);
 int vitb_attn_fwd_simt(const vitb_attn_params* p, void* stream);
 int vitb_attn_bwd_simt(const vitb_attn_params* p, void* stream);
+/* Single-query attention (Nq == 1: the class-token row of the LAST encoder block, whose other rows nobody reads;
+ * src/model.py:155,210), bf16, head_dim 64, <= 256 keys, 16-byte aligned rows.  The forward is vitb_attn_fwd_simt
+ * (it picks the bandwidth-bound kernel for these shapes); this is the backward with BF16 gradients: dq [B,1,H*64],
+ * dk / dv rows written whole through their strides (they may alias a packed [T, 2D] buffer), nothing to zero. */
+int vitb_attn_q1_supported(int head_dim, int Nk);
+int vitb_attn_q1_bwd(const vitb_attn_params* p, void* stream);
 
 /* ---- operand preparation / embedding stage ---------------------------------------------------- */
 /* hi = bf16(x); lo = bf16(x - hi) (optional).  Weight shadows and fp32-parity operands. */

@@ -264,6 +264,48 @@ def test_attn_single_query_fwd_bwd(dtype, dh, Nk, tol):
     assert rel_l2(dq, qf.grad) < btol and rel_l2(dk, kf.grad) < btol and rel_l2(dv, vf.grad) < btol
 
 
+@pytest.mark.parametrize("Nk,B,H", [(197, 5, 12), (17, 3, 2), (256, 2, 4), (1, 2, 1)])
+def test_attn_single_query_bf16_gradients_into_a_packed_buffer(Nk, B, H):
+    """vitb_attn_q1_bwd: one query per image, bf16 dk | dv written through strides into a packed [B, Nk, 2D] buffer (what
+    the fused last block hands to its grouped weight-gradient GEMM), bf16 dq; forward through the same bandwidth-bound
+    kernel family.  Tolerance: bf16 rounding of the outputs (4e-3) on top of the bf16 attention bar."""
+    import vitb200
+    D = H * 64
+    assert vitb200.ops.attn_q1_supported(64, Nk, torch.bfloat16)
+    q = _randn((B, 1, D), 1, 1.0, torch.bfloat16)
+    kv = _randn((B, Nk, 2 * D), 2, 1.0, torch.bfloat16)
+    k, v = kv[:, :, :D], kv[:, :, D:]
+    o, lse = vitb200.ops.attn_fwd(q, k, v, H, use_tc=False)
+    qf, kf, vf = (t.float().detach().requires_grad_(True) for t in (q, k, v))
+    ro, rlse = _attn_ref(qf, kf, vf, H)
+    assert rel_l2(o, ro) < 1e-2 and rel_l2(lse, rlse) < 1e-5
+    do = _randn((B, 1, D), 4, 1.0, torch.bfloat16)
+    ro.backward(do.float())
+    dkv = torch.full((B, Nk, 2 * D), float("nan"), dtype=torch.bfloat16, device="cuda")
+    dq, dk, dv = vitb200.ops.attn_q1_bwd(do, q, k, v, o, lse, H, dk=dkv[:, :, :D], dv=dkv[:, :, D:])
+    torch.cuda.synchronize()
+    assert dq.dtype == torch.bfloat16 and not torch.isnan(dkv.float()).any()
+    assert rel_l2(dq, qf.grad) < 4e-2 and rel_l2(dkv[:, :, :D], kf.grad) < 4e-2 and rel_l2(dkv[:, :, D:], vf.grad) < 4e-2
+
+
+def test_layernorm_bwd_residual_gradient_on_every_nth_row():
+    """dres_every = N: only rows 0, N, 2N, ... carry a residual-branch gradient (row i of a [rows / N, D] tensor)."""
+    import vitb200
+    B, N, D = 7, 5, 256
+    rows = B * N
+    x = _randn((rows, D), 1); dy = _randn((rows, D), 2).to(torch.bfloat16); gamma = _randn((D,), 3) + 1.0
+    dres0 = _randn((B, D), 4)
+    _, _, _, mean, rstd = vitb200.ops.layernorm_fwd(x, gamma, torch.zeros_like(gamma), 1e-6)
+    dense = torch.zeros(rows, D, device="cuda")
+    dense[::N] = dres0
+    cs_a, cs_b = torch.zeros(D, device="cuda"), torch.zeros(D, device="cuda")
+    dx_a, dxb_a, _ = vitb200.ops.layernorm_bwd(dy, x, mean, rstd, gamma, dres=dense, want_bf16=True, dcolsum=cs_a)
+    dx_b, dxb_b, _ = vitb200.ops.layernorm_bwd(dy, x, mean, rstd, gamma, dres=dres0, dres_every=N, want_bf16=True, dcolsum=cs_b)
+    torch.cuda.synchronize()
+    assert torch.equal(dx_a, dx_b) and torch.equal(dxb_a, dxb_b)
+    assert rel_l2(cs_b, cs_a) < 1e-6
+
+
 # ---------------------------------------------------------------------------------- elementwise etc.
 def test_cast_split():
     import vitb200

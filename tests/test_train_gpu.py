@@ -250,3 +250,47 @@ def test_fused_optimizer_state_dict_round_trip_and_zero_grad_misuse():
     vitb200.functional.cross_entropy(m(img), lab).backward()
     with pytest.raises(RuntimeError, match="optimizer.zero_grad"):
         opt.step()
+
+
+@pytest.mark.parametrize("width,heads", [(128, 2), (256, 4)])
+def test_fused_last_block_and_direct_bias_sums_match_the_composed_path(width, heads, monkeypatch):
+    """The class-token-only last block as ONE autograd node (functional._EncoderBlockRow0: k | v as a grouped GEMM, bf16
+    single-query attention backward into the packed buffer, LayerNorm backward with a residual gradient on rows 0 only) and
+    the column sums that a block's LayerNorm backward adds straight into the upstream block's fc2 bias gradient must give the
+    logits and gradients of the composed path (VITB_ROW0_FUSED=0, VITB_GRAD_SIDE=0) — with the fused optimizer's flat
+    gradient buffer in place, which is what enables both, and also when an auxiliary loss adds a second consumer to a
+    block's output (the hand-over is then rejected and the share added in advance is taken back out)."""
+    import vitb200
+    from vitb200 import functional as F
+    cfg = dict(image_size=(64, 64), patch_size=(16, 16), emb_dim=width, mlp_dim=2 * width, num_heads=heads, num_layers=4,
+               num_classes=16)
+    sd = vit_init.reference_state_dict(cfg, seed=2, scaled=True)
+    g = torch.Generator().manual_seed(11)
+    img = torch.randn(6, 3, 64, 64, generator=g).cuda()
+    lab = torch.randint(0, 16, (6,), generator=g).cuda()
+
+    def run(fused, side, aux):
+        monkeypatch.setenv("VITB_ROW0_FUSED", fused)
+        monkeypatch.setenv("VITB_GRAD_SIDE", side)
+        m = vitb200.VisionTransformer(dropout_rate=0.0, attn_dropout_rate=0.0, **cfg)
+        m.load_state_dict(sd)
+        m = m.cuda().train()
+        opt = vitb200.optim.FusedSGD(m.parameters(), lr=0.01, momentum=0.9)
+        opt.zero_grad()
+        feats = []
+        if aux:
+            m.transformer.encoder_layers[1].register_forward_hook(lambda mod, inp, out: feats.append(out))
+        logits = m(img)
+        loss = vitb200.functional.cross_entropy(logits, lab)
+        if aux:
+            loss = loss + 0.05 * feats[0].float().pow(2).mean()
+        loss.backward()
+        torch.cuda.synchronize()
+        return logits.detach().clone(), {k: p.grad.detach().clone() for k, p in m.named_parameters()}
+
+    for aux in (False, True):
+        lo_ref, g_ref = run("0", "0", aux)
+        lo, gr = run("1", "1", aux)
+        assert rel_l2(lo, lo_ref) < 5e-3, (aux, rel_l2(lo, lo_ref))
+        for k in g_ref:
+            assert grad_close(gr[k], g_ref[k], 2e-2, atol=1e-6), (aux, k, rel_l2(gr[k], g_ref[k]))

@@ -166,6 +166,8 @@ _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 _vitb_layernorm_fwd = _sig("vitb_layernorm_fwd", [_vp, _i, _i64, _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp])
 _vitb_layernorm_bwd = _sig("vitb_layernorm_bwd", [_vp, _i, _vp, _i64, _vp, _vp, _vp, _i, _i, _vp, _i64, _vp, _i64,
                                                    _vp, _vp, _vp, _vp, _vp, _vp])
+_vitb_layernorm_bwd_sparse_res = _sig("vitb_layernorm_bwd_sparse_res", [_vp, _i, _vp, _i64, _vp, _vp, _vp, _i, _i, _vp, _i64, _i,
+                                                                         _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp])
 vitb_attn_supported_tc = _sig("vitb_attn_supported_tc", [_i, _i, _i])
 vitb_attn_fwd_supported_tc = _sig("vitb_attn_fwd_supported_tc", [_i, _i, _i])
 _vitb_attn_fwd_tc = _sig("vitb_attn_fwd_tc", [C.POINTER(AttnParams), _vp])
@@ -175,6 +177,8 @@ _vitb_attn_fwd_ws = _sig("vitb_attn_fwd_ws", [C.POINTER(AttnParams), _vp])      
 _vitb_attn_bwd_ws = _sig("vitb_attn_bwd_ws", [C.POINTER(AttnParams), _vp])
 _vitb_attn_fwd_simt = _sig("vitb_attn_fwd_simt", [C.POINTER(AttnParams), _vp])
 _vitb_attn_bwd_simt = _sig("vitb_attn_bwd_simt", [C.POINTER(AttnParams), _vp])
+vitb_attn_q1_supported = _sig("vitb_attn_q1_supported", [_i, _i])
+_vitb_attn_q1_bwd = _sig("vitb_attn_q1_bwd", [C.POINTER(AttnParams), _vp])           # bf16 gradients, single query
 _vitb_cast_split = _sig("vitb_cast_split", [_vp, _i64, _vp, _vp, _vp])
 _vitb_im2col = _sig("vitb_im2col", [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp])
 _vitb_cls_rows = _sig("vitb_cls_rows", [_vp, _i, _i, _i, _vp, _vp, _vp])
@@ -210,4 +214,5 @@ EXPORTED_SYMBOLS = [
     "vitb_token_mean_fwd", "vitb_token_mean_bwd", "vitb_select_rows", "vitb_colsum3",
     "vitb_resize_tables_host", "vitb_image_prep",
     "vitb_distill_loss", "vitb_active_loss", "vitb_compact_rows", "vitb_gather_rows", "vitb_scatter_rows", "vitb_attn_ws_supported", "vitb_attn_fwd_ws", "vitb_attn_bwd_ws",
+    "vitb_layernorm_bwd_sparse_res", "vitb_attn_q1_supported", "vitb_attn_q1_bwd",
 ]

@@ -344,6 +344,195 @@ attn_q1_bwd(const AttnDev a) {
   }
 }
 
+// ---- single-query attention, bf16, head_dim 64, <= 256 keys: the bandwidth-bound version --------------------------
+// The two kernels above walk the keys one per warp and iteration (a 128-byte load, a warp reduction, the next key):
+// latency-bound at 0.85 TB/s for the class-token-only last block of ViT-B/16 (profiles/launches_r02k_summary.txt).
+// Here eight lanes own one key row (16 bytes = 8 head-dim columns each), a warp covers four keys per load instruction,
+// and ALL of a thread's K and V loads (<= 16 + 16 of 16 bytes) are issued before the first one is consumed.
+// grid: B*H blocks of 4 warps; key j is owned by slot j % 16 = warp * 4 + lane / 8, iteration j / 16.
+constexpr int kQ1FastIt = 16;        // 16 iterations x 16 key slots = 256 keys
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+  f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+__device__ __forceinline__ float dot8(const uint4& u, const float (&q)[8]) {
+  float f[8];
+  unpack8(u, f);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s = fmaf(f[i], q[i], s);
+  return s;
+}
+__device__ __forceinline__ float sum8lanes(float v) {      // over the eight lanes that share a key row
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  return v;
+}
+
+// smem: sc[256] | part[4][64] | red[4]
+__global__ void __launch_bounds__(kQ1Warps * 32)
+attn_q1_fwd64(const AttnDev a) {
+  __shared__ float sc[kQ1FastIt * 16];
+  __shared__ float part[kQ1Warps * 64];
+  __shared__ float red[kQ1Warps];
+  const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slot = warp * 4 + (lane >> 3), c8 = (lane & 7) * 8;
+  const __nv_bfloat16* kp = reinterpret_cast<const __nv_bfloat16*>(a.k) + b * a.k_bs + h * 64 + c8;
+  const __nv_bfloat16* vp = reinterpret_cast<const __nv_bfloat16*>(a.v) + b * a.v_bs + h * 64 + c8;
+  uint4 kr[kQ1FastIt], vr[kQ1FastIt];
+#pragma unroll
+  for (int it = 0; it < kQ1FastIt; ++it) {
+    const int j = it * 16 + slot;
+    kr[it] = make_uint4(0u, 0u, 0u, 0u);
+    if (j < a.Nk) kr[it] = *reinterpret_cast<const uint4*>(kp + j * a.k_rs);
+  }
+#pragma unroll
+  for (int it = 0; it < kQ1FastIt; ++it) {
+    const int j = it * 16 + slot;
+    vr[it] = make_uint4(0u, 0u, 0u, 0u);
+    if (j < a.Nk) vr[it] = *reinterpret_cast<const uint4*>(vp + j * a.v_rs);
+  }
+  float q[8];
+  unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.q) + b * a.q_bs + h * 64 + c8), q);
+  float mx = -INFINITY;
+#pragma unroll
+  for (int it = 0; it < kQ1FastIt; ++it) {
+    const int j = it * 16 + slot;
+    const float s = sum8lanes(dot8(kr[it], q)) * a.scale;
+    if (j < a.Nk) {
+      mx = fmaxf(mx, s);
+      if ((lane & 7) == 0) sc[j] = s;
+    }
+  }
+  mx = block_reduce_q1(mx, red, true);     // its barriers publish sc
+  float sum = 0.f;
+  for (int j = threadIdx.x; j < a.Nk; j += blockDim.x) sum += expf(sc[j] - mx);
+  sum = block_reduce_q1(sum, red, false);
+  const float inv = 1.0f / sum;
+  if (threadIdx.x == 0 && a.lse) a.lse[static_cast<long long>(b) * a.H + h] = mx + logf(sum);
+  float o[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = 0.f;
+#pragma unroll
+  for (int it = 0; it < kQ1FastIt; ++it) {
+    const int j = it * 16 + slot;
+    if (j < a.Nk) {
+      const float pj = expf(sc[j] - mx) * inv;
+      float f[8];
+      unpack8(vr[it], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = fmaf(pj, f[i], o[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {              // the warp's four key slots
+    o[i] += __shfl_xor_sync(0xffffffffu, o[i], 8);
+    o[i] += __shfl_xor_sync(0xffffffffu, o[i], 16);
+  }
+  if (lane < 8) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) part[warp * 64 + c8 + i] = o[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {                    // two columns per lane
+    const int d = 2 * threadIdx.x;
+    float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+    for (int w = 0; w < kQ1Warps; ++w) { o0 += part[w * 64 + d]; o1 += part[w * 64 + d + 1]; }
+    *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(a.o) + b * a.o_bs + h * 64 + d) = pack_bf16x2(o0, o1);
+  }
+}
+
+// dq / dk / dv are BF16 here (the tensor dtype), laid out through their own strides; dk and dv rows are written whole.
+__global__ void __launch_bounds__(kQ1Warps * 32)
+attn_q1_bwd64(const AttnDev a) {
+  __shared__ float part[kQ1Warps * 64];
+  const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slot = warp * 4 + (lane >> 3), c8 = (lane & 7) * 8;
+  const __nv_bfloat16* kp = reinterpret_cast<const __nv_bfloat16*>(a.k) + b * a.k_bs + h * 64 + c8;
+  const __nv_bfloat16* vp = reinterpret_cast<const __nv_bfloat16*>(a.v) + b * a.v_bs + h * 64 + c8;
+  uint4 kr[kQ1FastIt], vr[kQ1FastIt];
+#pragma unroll
+  for (int it = 0; it < kQ1FastIt; ++it) {
+    const int j = it * 16 + slot;
+    kr[it] = make_uint4(0u, 0u, 0u, 0u);
+    vr[it] = make_uint4(0u, 0u, 0u, 0u);
+    if (j < a.Nk) {
+      kr[it] = *reinterpret_cast<const uint4*>(kp + j * a.k_rs);
+      vr[it] = *reinterpret_cast<const uint4*>(vp + j * a.v_rs);
+    }
+  }
+  float q[8], g[8], ov[8];
+  unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.q) + b * a.q_bs + h * 64 + c8), q);
+  unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.dout) + b * a.do_bs + h * 64 + c8), g);
+  unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.o) + b * a.o_bs + h * 64 + c8), ov);
+  float di = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) di = fmaf(g[i], ov[i], di);
+  const float Di = sum8lanes(di);           // every group of eight lanes holds the whole row
+  const float lse = a.lse[static_cast<long long>(b) * a.H + h];
+  __nv_bfloat16* dkp = reinterpret_cast<__nv_bfloat16*>(a.dk) + b * a.dk_bs + h * 64 + c8;
+  __nv_bfloat16* dvp = reinterpret_cast<__nv_bfloat16*>(a.dv) + b * a.dv_bs + h * 64 + c8;
+  float dq[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) dq[i] = 0.f;
+#pragma unroll
+  for (int it = 0; it < kQ1FastIt; ++it) {
+    const int j = it * 16 + slot;
+    const float s = sum8lanes(dot8(kr[it], q));
+    const float dp = sum8lanes(dot8(vr[it], g));
+    if (j < a.Nk) {
+      const float pj = expf(s * a.scale - lse);
+      const float ds = pj * (dp - Di) * a.scale;
+      float kf[8];
+      unpack8(kr[it], kf);
+      uint4 wk, wv;
+      wk.x = pack_bf16x2(ds * q[0], ds * q[1]); wk.y = pack_bf16x2(ds * q[2], ds * q[3]);
+      wk.z = pack_bf16x2(ds * q[4], ds * q[5]); wk.w = pack_bf16x2(ds * q[6], ds * q[7]);
+      wv.x = pack_bf16x2(pj * g[0], pj * g[1]); wv.y = pack_bf16x2(pj * g[2], pj * g[3]);
+      wv.z = pack_bf16x2(pj * g[4], pj * g[5]); wv.w = pack_bf16x2(pj * g[6], pj * g[7]);
+      *reinterpret_cast<uint4*>(dkp + j * a.dk_rs) = wk;
+      *reinterpret_cast<uint4*>(dvp + j * a.dv_rs) = wv;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dq[i] = fmaf(ds, kf[i], dq[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    dq[i] += __shfl_xor_sync(0xffffffffu, dq[i], 8);
+    dq[i] += __shfl_xor_sync(0xffffffffu, dq[i], 16);
+  }
+  if (lane < 8) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) part[warp * 64 + c8 + i] = dq[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int d = 2 * threadIdx.x;
+    float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+    for (int w = 0; w < kQ1Warps; ++w) { o0 += part[w * 64 + d]; o1 += part[w * 64 + d + 1]; }
+    *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(a.dq) + b * a.dq_bs + h * 64 + d) = pack_bf16x2(o0, o1);
+  }
+}
+
+// shapes of the two kernels above: one bf16 query per image, head_dim 64, <= 256 keys, 16-byte aligned rows
+bool q1_fast_ok(const vitb_attn_params* p, bool grads) {
+  auto al8 = [](long long v) { return v % 8 == 0; };
+  auto p16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+  bool ok = p->Nq == 1 && p->dtype == VITB_BF16 && p->head_dim == 64 && p->Nk >= 1 && p->Nk <= 16 * kQ1FastIt &&
+            al8(p->q_batch_stride) && al8(p->k_batch_stride) && al8(p->k_row_stride) && al8(p->v_batch_stride) &&
+            al8(p->v_row_stride) && al8(p->o_batch_stride) && p16(p->q) && p16(p->k) && p16(p->v) && p16(p->o);
+  if (ok && grads)
+    ok = al8(p->do_batch_stride) && al8(p->dq_batch_stride) && al8(p->dk_batch_stride) && al8(p->dk_row_stride) &&
+         al8(p->dv_batch_stride) && al8(p->dv_row_stride) && p16(p->dout) && p16(p->dq) && p16(p->dk) && p16(p->dv);
+  return ok;
+}
+
 // single-query shapes these kernels take: head_dim even and <= 128, 8-byte aligned fp32 gradient rows
 bool q1_ok(const vitb_attn_params* p) {
   return p->Nq == 1 && p->head_dim % 2 == 0 && p->head_dim <= 128 && p->k_row_stride % 2 == 0 && p->v_row_stride % 2 == 0 &&
@@ -365,6 +554,11 @@ extern "C" int vitb_attn_fwd_simt(const vitb_attn_params* p, void* stream_) {
   a.v_bs = p->v_batch_stride; a.v_rs = p->v_row_stride; a.o_bs = p->o_batch_stride; a.o_rs = p->o_row_stride;
   a.B = p->B; a.H = p->H; a.Nq = p->Nq; a.Nk = p->Nk; a.dh = p->head_dim;
   a.scale = 1.0f / sqrtf((float)p->head_dim);
+  if (q1_fast_ok(p, false)) {
+    attn_q1_fwd64<<<p->B * p->H, kQ1Warps * 32, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(a);
+    VITB_LAUNCH_CHECK("attn_q1_fwd64");
+    return VITB_OK;
+  }
   if (q1_ok(p)) {
     const size_t sm1 = sizeof(float) * ((size_t)a.dh + a.Nk + kQ1Warps * a.dh + kQ1Warps);
     VITB_REQUIRE(sm1 <= 200 * 1024, VITB_ERR_UNSUPPORTED_SHAPE, "attn_q1_fwd: Nk=%d", p->Nk);
@@ -447,5 +641,35 @@ extern "C" int vitb_attn_bwd_simt(const vitb_attn_params* p, void* stream_) {
     attn_bwd_simt<false><<<grid, kWarps * 32, smem, stream>>>(a);
   }
   VITB_LAUNCH_CHECK("attn_bwd_simt");
+  return VITB_OK;
+}
+
+// Backward of single-query attention with gradients in the tensor dtype (bf16): the class-token-only last encoder block
+// (EncoderBlock.forward_row0).  bf16, head_dim 64, Nq == 1, Nk <= 256, 16-byte aligned rows; dk / dv rows are written
+// whole (no zeroing needed), dq is [B, 1, H*64].
+extern "C" int vitb_attn_q1_supported(int head_dim, int Nk) { return head_dim == 64 && Nk >= 1 && Nk <= 16 * kQ1FastIt; }
+
+extern "C" int vitb_attn_q1_bwd(const vitb_attn_params* p, void* stream_) {
+  int st = vitb_check_device();
+  if (st != VITB_OK) return st;
+  VITB_REQUIRE(p && p->struct_bytes == (int)sizeof(vitb_attn_params), VITB_ERR_BAD_ARG, "attn_q1_bwd: ABI mismatch");
+  if (p->B == 0) return VITB_OK;
+  VITB_REQUIRE(p->q && p->k && p->v && p->o && p->lse && p->dout && p->dq && p->dk && p->dv, VITB_ERR_BAD_ARG,
+               "attn_q1_bwd: null tensor");
+  VITB_REQUIRE(q1_fast_ok(p, true), VITB_ERR_UNSUPPORTED_SHAPE,
+               "attn_q1_bwd: needs bf16, Nq 1, head_dim 64, <= %d keys, 16-byte aligned rows (Nq=%d dh=%d Nk=%d)",
+               16 * kQ1FastIt, p->Nq, p->head_dim, p->Nk);
+  AttnDev a{};
+  a.q = p->q; a.k = p->k; a.v = p->v; a.o = p->o; a.lse = p->lse;
+  a.q_bs = p->q_batch_stride; a.q_rs = p->q_row_stride; a.k_bs = p->k_batch_stride; a.k_rs = p->k_row_stride;
+  a.v_bs = p->v_batch_stride; a.v_rs = p->v_row_stride; a.o_bs = p->o_batch_stride; a.o_rs = p->o_row_stride;
+  a.B = p->B; a.H = p->H; a.Nq = p->Nq; a.Nk = p->Nk; a.dh = p->head_dim;
+  a.scale = 1.0f / sqrtf((float)p->head_dim);
+  a.dout = p->dout; a.do_bs = p->do_batch_stride; a.do_rs = p->do_row_stride;
+  a.dq = reinterpret_cast<float*>(p->dq); a.dk = reinterpret_cast<float*>(p->dk); a.dv = reinterpret_cast<float*>(p->dv);
+  a.dq_bs = p->dq_batch_stride; a.dq_rs = p->dq_row_stride; a.dk_bs = p->dk_batch_stride; a.dk_rs = p->dk_row_stride;
+  a.dv_bs = p->dv_batch_stride; a.dv_rs = p->dv_row_stride;
+  attn_q1_bwd64<<<p->B * p->H, kQ1Warps * 32, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(a);
+  VITB_LAUNCH_CHECK("attn_q1_bwd64");
   return VITB_OK;
 }

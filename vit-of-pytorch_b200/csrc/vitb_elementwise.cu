@@ -2,6 +2,8 @@
 // operand casts / bf16 hi-lo split, patch extraction, class-token + position rows, the embedding
 // backward reduction, column sums (bias gradients), cross-entropy, fused SGD / AdamW.
 // All use 128-bit coalesced access and grid sizes in multiples of the SM count.
+#include <stdlib.h>
+
 #include "../../include/vitb200.h"
 #include "vitb_common.cuh"
 
@@ -247,7 +249,9 @@ static void colsum_launch(const void* x, int rows, int cols, long long ld, float
   const int ny = kColsumThreads / tb;                 // >= 2 row lanes share a block (and one atomic per column)
   const int bx = (groups + tb - 1) / tb;
   const int warps_per_block = tb * ny / 32;
-  int by = (vitb_num_sms() * 64 + bx * warps_per_block - 1) / (bx * warps_per_block);
+  int warps_per_sm = 64;
+  if (const char* e = getenv("VITB_COLSUM_WARPS")) { const int v = atoi(e); if (v >= 1 && v <= 64) warps_per_sm = v; }   // tuning runs
+  int by = (vitb_num_sms() * warps_per_sm + bx * warps_per_block - 1) / (bx * warps_per_block);
   const int max_by = (rows + 32 * ny - 1) / (32 * ny);
   if (by > max_by) by = max_by;
   if (by < 1) by = 1;

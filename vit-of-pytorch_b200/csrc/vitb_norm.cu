@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(LnBwdCfg<NV>::WARPS * 32, 1)
 ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, long long x_stride,
               const float* __restrict__ mean, const float* __restrict__ rstd,
               const float* __restrict__ gamma, int rows, const float* __restrict__ dres,
-              long long dres_stride, float* __restrict__ dx_f32, long long dx_stride,
+              long long dres_stride, int dres_every, float* __restrict__ dx_f32, long long dx_stride,
               __nv_bfloat16* __restrict__ dx_hi, __nv_bfloat16* __restrict__ dx_lo,
               float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dcolsum) {
   constexpr int D = NV * 128;
@@ -178,8 +178,8 @@ ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, long lo
       d.y = rs * (gy.y - s1 - xh[i].y * s2);
       d.z = rs * (gy.z - s1 - xh[i].z * s2);
       d.w = rs * (gy.w - s1 - xh[i].w * s2);
-      if (dres) {
-        const float4 r = ld4(dres + static_cast<long long>(row) * dres_stride + c);
+      if (dres && (dres_every == 1 || row % dres_every == 0)) {   // dres_every > 1: only every n-th row has a residual gradient
+        const float4 r = ld4(dres + static_cast<long long>(row / dres_every) * dres_stride + c);
         d.x += r.x; d.y += r.y; d.z += r.z; d.w += r.w;
       }
       if constexpr (COLSUM) add4(acc + 2 * D + c, d.x, d.y, d.z, d.w);
@@ -251,17 +251,18 @@ extern "C" int vitb_layernorm_fwd(const void* x, int x_dtype, int64_t x_row_stri
   return VITB_OK;
 }
 
-extern "C" int vitb_layernorm_bwd(const void* dy, int dy_dtype, const float* x, int64_t x_row_stride,
-                                  const float* mean, const float* rstd, const float* gamma, int rows,
-                                  int D, const float* dres, int64_t dres_row_stride, float* dx_f32,
-                                  int64_t dx_row_stride, void* dx_bf16, void* dx_bf16_lo,
-                                  float* dgamma, float* dbeta, float* dcolsum, void* stream_) {
+static int layernorm_bwd_impl(const void* dy, int dy_dtype, const float* x, int64_t x_row_stride,
+                              const float* mean, const float* rstd, const float* gamma, int rows,
+                              int D, const float* dres, int64_t dres_row_stride, int dres_every, float* dx_f32,
+                              int64_t dx_row_stride, void* dx_bf16, void* dx_bf16_lo,
+                              float* dgamma, float* dbeta, float* dcolsum, void* stream_) {
   int st = vitb_check_device();
   if (st != VITB_OK) return st;
   if (rows == 0) return VITB_OK;
   VITB_REQUIRE(rows > 0 && D > 0 && D % 128 == 0, VITB_ERR_UNSUPPORTED_SHAPE,
                "layernorm_bwd: rows=%d D=%d", rows, D);
   VITB_REQUIRE(dy && x && mean && rstd && gamma, VITB_ERR_BAD_ARG, "layernorm_bwd: null input");
+  VITB_REQUIRE(dres_every >= 1, VITB_ERR_BAD_ARG, "layernorm_bwd: dres_every=%d", dres_every);
   VITB_REQUIRE(x_row_stride % 4 == 0 && dres_row_stride % 4 == 0 && dx_row_stride % 4 == 0,
                VITB_ERR_UNSUPPORTED_SHAPE, "layernorm_bwd: row strides must be multiples of 4");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -279,7 +280,7 @@ extern "C" int vitb_layernorm_bwd(const void* dy, int dy_dtype, const float* x, 
                       lerr = (lerr != cudaSuccess) ? lerr :                                                       \
                              vitb_launch(ln_bwd_kernel<NV, DYB, CS>, dim3(grid), dim3(LnBwdCfg<NV>::WARPS * 32), smem,  \
                                          stream, dy, x, x_row_stride, mean, rstd, gamma, rows, dres,              \
-                                         dres_row_stride, dx_f32, dx_row_stride, dh, dl, dgamma, dbeta, dcolsum)))
+                                         dres_row_stride, dres_every, dx_f32, dx_row_stride, dh, dl, dgamma, dbeta, dcolsum)))
   cudaError_t lerr = cudaSuccess;
   if (dy_dtype == VITB_BF16) {
     if (dcolsum) { VITB_LNB(true, true); } else { VITB_LNB(true, false); }
@@ -290,4 +291,25 @@ extern "C" int vitb_layernorm_bwd(const void* dy, int dy_dtype, const float* x, 
   VITB_CUDA_CHECK(lerr);
   VITB_LAUNCH_CHECK("ln_bwd_kernel");
   return VITB_OK;
+}
+
+extern "C" int vitb_layernorm_bwd(const void* dy, int dy_dtype, const float* x, int64_t x_row_stride,
+                                  const float* mean, const float* rstd, const float* gamma, int rows,
+                                  int D, const float* dres, int64_t dres_row_stride, float* dx_f32,
+                                  int64_t dx_row_stride, void* dx_bf16, void* dx_bf16_lo,
+                                  float* dgamma, float* dbeta, float* dcolsum, void* stream_) {
+  return layernorm_bwd_impl(dy, dy_dtype, x, x_row_stride, mean, rstd, gamma, rows, D, dres, dres_row_stride, 1, dx_f32,
+                            dx_row_stride, dx_bf16, dx_bf16_lo, dgamma, dbeta, dcolsum, stream_);
+}
+
+// Same, with a residual-branch gradient that only every dres_every-th row has: dres row r / dres_every is added to
+// row r when r % dres_every == 0 (the class-token-only last encoder block: of the N rows of an image only row 0
+// receives a gradient through the residual connection; src/model.py:155,210).
+extern "C" int vitb_layernorm_bwd_sparse_res(const void* dy, int dy_dtype, const float* x, int64_t x_row_stride,
+                                             const float* mean, const float* rstd, const float* gamma, int rows,
+                                             int D, const float* dres, int64_t dres_row_stride, int dres_every,
+                                             float* dx_f32, int64_t dx_row_stride, void* dx_bf16, void* dx_bf16_lo,
+                                             float* dgamma, float* dbeta, float* dcolsum, void* stream_) {
+  return layernorm_bwd_impl(dy, dy_dtype, x, x_row_stride, mean, rstd, gamma, rows, D, dres, dres_row_stride, dres_every,
+                            dx_f32, dx_row_stride, dx_bf16, dx_bf16_lo, dgamma, dbeta, dcolsum, stream_);
 }

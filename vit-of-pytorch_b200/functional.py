@@ -842,6 +842,26 @@ def _side_take(dy2):
     return e[2], e[3]
 
 
+_DIRECT = object()      # side-channel column sums that already sit in the upstream block's bias-gradient accumulator
+
+
+def _upstream_node(x):
+    """The fused-block autograd node that produced x (its ctx), or None: lets a block's LayerNorm backward add the column
+    sums of dx straight into the fc2 bias gradient of the block upstream instead of handing over a buffer that costs a
+    fill and an add launch per block."""
+    fn = getattr(x, "grad_fn", None)
+    return fn if isinstance(fn, _EncoderBlockFused._backward_cls) else None
+
+
+def _upstream_bias_target(ctx):
+    import os
+    up = getattr(ctx, "up", None)
+    if up is None or os.environ.get("VITB_GRAD_SIDE", "1") == "0":
+        return None
+    tgt = _grad_target(up.params[-1])          # the upstream block's fc2 bias
+    return tgt.view(-1) if tgt is not None else None
+
+
 def _acc(param, shape=None):
     """(fp32 accumulator viewed `shape`, value to return to autograd) for a parameter gradient."""
     tgt = _grad_target(param)
@@ -885,8 +905,9 @@ class _EncoderBlockFused(torch.autograd.Function):
     emit the bf16 operand copy and the neighbouring bias gradients in the same pass."""
 
     @staticmethod
-    def forward(ctx, x, H, eps1, eps2, n1w, n1b, wq, bq, wk, bk, wv, bv, wo, bo, n2w, n2b, w1, b1, w2, b2):
+    def forward(ctx, x, H, eps1, eps2, n1w, n1b, wq, bq, wk, bk, wv, bv, wo, bo, n2w, n2b, w1, b1, w2, b2, up=None):
         L.require_cuda(x)
+        ctx.up = up
         Bsz, N, D = x.shape
         T = Bsz * N
         Mh = w1.shape[0]
@@ -930,6 +951,10 @@ class _EncoderBlockFused(torch.autograd.Function):
         if dy2.dtype != F32 or not dy2.is_contiguous():
             dy2 = dy2.float().contiguous()
         side = _side_take(dy2)
+        # the downstream block may already have added the column sums of ITS dx to this block's fc2 bias gradient
+        # (_upstream_bias_target); it left the bf16 copy of that dx here in case the hand-over is rejected
+        direct_dxb = getattr(ctx, "b2_direct", None)
+        ctx.b2_direct = None
         if side is not None:
             dyb, dy_colsum = side
         else:
@@ -942,10 +967,18 @@ class _EncoderBlockFused(torch.autograd.Function):
         # ---- MLP ----
         acc_b2, r = _acc(b2)
         ret(b2, r)
-        if dy_colsum is not None:
+        if dy_colsum is _DIRECT:
+            pass                               # the downstream block's LayerNorm backward accumulated it in place
+        elif dy_colsum is not None:
             acc_b2.add_(dy_colsum)
         else:
             ops.colsum(dy2, acc_b2)
+            if direct_dxb is not None:
+                # rejected hand-over (a hook or a second consumer changed the gradient on its way here): the sums above are
+                # the true ones, so the share the downstream block added in advance comes back out
+                share = torch.zeros(D, dtype=F32, device=dev)
+                ops.colsum(direct_dxb, share)
+                acc_b2.sub_(share)
         acc_b1, r = _acc(b1)
         ret(b1, r)
         dz = torch.empty((T, Mh), dtype=BF16, device=dev)
@@ -1008,10 +1041,13 @@ class _EncoderBlockFused(torch.autograd.Function):
         need_dx = ctx.needs_input_grad[0]
         dx = None
         if need_dx:
-            colsum_dx = torch.zeros(D, dtype=F32, device=dev)
+            direct = _upstream_bias_target(ctx)
+            colsum_dx = direct if direct is not None else torch.zeros(D, dtype=F32, device=dev)
             dx, dxb, _ = ops.layernorm_bwd(dxn, x2, mean1, rstd1, n1w.detach(), dres=dh, want_f32=True,
                                            want_bf16=True, dgamma=acc_g1, dbeta=acc_be1, dcolsum=colsum_dx)
-            _side_put(dx, dxb, colsum_dx)
+            if direct is not None:
+                ctx.up.b2_direct = dxb
+            _side_put(dx, dxb, _DIRECT if direct is not None else colsum_dx)
             dx = dx.view(ctx.x_shape)
         else:
             ops.layernorm_bwd(dxn, x2, mean1, rstd1, n1w.detach(), dres=dh, want_f32=False, dgamma=acc_g1,
@@ -1019,7 +1055,152 @@ class _EncoderBlockFused(torch.autograd.Function):
         out = [dx, None, None, None]
         for p in ctx.params:
             out.append(grads.get(id(p)) if p.requires_grad else None)
+        out.append(None)                       # up
         return tuple(out)
+
+
+class _EncoderBlockRow0(torch.autograd.Function):
+    """Row 0 (the class token) of the LAST encoder block, y0 = h0 + MLP(LN2(h0)), h0 = x0 + Attn(LN1(x))[0]
+    (src/model.py:117-130 followed by :155,210, which read nothing but row 0 of the block's output), as one autograd node.
+
+    Keys and values need every token: LayerNorm over all rows, k | v as ONE grouped GEMM into a packed [T, 2D] buffer.
+    The query, the output projection and the MLP run on the B class-token rows, read in place through row strides
+    (no gather).  Backward: single-query attention backward with bf16 dk | dv straight into the packed buffer, one
+    grouped weight-gradient GEMM for k | v, one two-segment dgrad, the query's contribution added to rows 0 of it by a
+    GEMM with an in-place residual, and a LayerNorm backward whose residual-branch gradient exists for rows 0 only.
+    Every logit and every parameter gradient equals the full block's: the skipped rows have zero gradient there too."""
+
+    @staticmethod
+    def forward(ctx, x, H, eps1, eps2, n1w, n1b, wq, bq, wk, bk, wv, bv, wo, bo, n2w, n2b, w1, b1, w2, b2, up=None):
+        L.require_cuda(x)
+        ctx.up = up
+        Bsz, N, D = x.shape
+        T = Bsz * N
+        Mh = w1.shape[0]
+        x2 = x.reshape(T, D)
+        if x2.dtype != F32 or not x2.is_contiguous():
+            x2 = x2.float().contiguous()
+        dev = x.device
+        _, xn, _, mean1, rstd1 = ops.layernorm_fwd(x2, n1w.detach(), n1b.detach(), eps1)
+        kv = torch.empty((T, 2 * D), dtype=BF16, device=dev)
+        _qkv_forward(xn, (wk, wv), (bk, bv), D, D, kv)
+        xn0 = xn.view(Bsz, N * D)[:, :D]            # the class-token rows, in place
+        x0 = x2.view(Bsz, N * D)[:, :D]
+        q0 = ops.gemm(xn0, SHADOW.get(wq, False)[0].view(D, D), b_mn=True, bias=bq.detach().view(-1), out_dtype=BF16)
+        kv3 = kv.view(Bsz, N, 2 * D)
+        o0, lse = ops.attn_fwd(q0.view(Bsz, 1, D), kv3[:, :, :D], kv3[:, :, D:], H, use_tc=False)
+        h0 = torch.empty((Bsz, D), dtype=F32, device=dev)
+        ops.gemm(o0.view(Bsz, D), SHADOW.get(wo, False)[0].view(D, D), b_mn=True, out=h0, bias=bo.detach().view(-1),
+                 residual=x0)
+        _, hn0, _, mean2, rstd2 = ops.layernorm_fwd(h0, n2w.detach(), n2b.detach(), eps2)
+        a0 = torch.empty((Bsz, Mh), dtype=BF16, device=dev)
+        if any(ctx.needs_input_grad):
+            z0 = torch.empty((Bsz, Mh), dtype=BF16, device=dev)
+            ops.gemm(hn0, SHADOW.get(w1, False)[0], out=a0, bias=b1.detach(), epilogue=ops.EPI_GELU_DG, d2=z0)
+        else:
+            z0 = a0
+            ops.gemm(hn0, SHADOW.get(w1, False)[0], out=a0, bias=b1.detach(), epilogue=ops.EPI_GELU)
+        y0 = torch.empty((Bsz, D), dtype=F32, device=dev)
+        ops.gemm(a0, SHADOW.get(w2, False)[0], out=y0, bias=b2.detach(), residual=h0)
+        ctx.save_for_backward(x2, xn, mean1, rstd1, kv, q0, o0, lse, h0, hn0, mean2, rstd2, z0, a0)
+        ctx.params = (n1w, n1b, wq, bq, wk, bk, wv, bv, wo, bo, n2w, n2b, w1, b1, w2, b2)
+        ctx.geom = (Bsz, N, D, Mh, H)
+        ctx.x_shape = x.shape
+        return y0
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, xn, mean1, rstd1, kv, q0, o0, lse, h0, hn0, mean2, rstd2, z0, a0 = ctx.saved_tensors
+        n1w, n1b, wq, bq, wk, bk, wv, bv, wo, bo, n2w, n2b, w1, b1, w2, b2 = ctx.params
+        Bsz, N, D, Mh, H = ctx.geom
+        T = Bsz * N
+        dev = dy.device
+        dy2 = dy.reshape(Bsz, D)
+        if dy2.dtype != F32 or not dy2.is_contiguous():
+            dy2 = dy2.float().contiguous()
+        dyb = ops.cast_split(dy2)[0]
+        grads = {}
+
+        def acc_of(p, shape=None):
+            a, r = _acc(p, shape)
+            grads[id(p)] = r
+            return a
+
+        # ---- MLP on the B class-token rows ----
+        ops.colsum(dy2, acc_of(b2))
+        dz = torch.empty((Bsz, Mh), dtype=BF16, device=dev)
+        ops.gemm(dyb, SHADOW.get(w2, False)[0], b_mn=True, out=dz, epilogue=ops.EPI_MUL_AUX, aux=z0, colsum=acc_of(b1))
+        ops.gemm(dyb, a0, a_mn=True, b_mn=True, out=acc_of(w2), accumulate=True)
+        ops.gemm(dz, hn0, a_mn=True, b_mn=True, out=acc_of(w1), accumulate=True)
+        dhn = ops.gemm(dz, SHADOW.get(w1, False)[0], b_mn=True, out_dtype=BF16)
+        dh0, dhb0, _ = ops.layernorm_bwd(dhn, h0, mean2, rstd2, n2w.detach(), dres=dy2, want_f32=True, want_bf16=True,
+                                         dgamma=acc_of(n2w), dbeta=acc_of(n2b), dcolsum=acc_of(bo).view(-1))
+        # ---- attention: one query per image ----
+        ops.gemm(o0.view(Bsz, D), dhb0, a_mn=True, b_mn=True, out=acc_of(wo, (D, D)), accumulate=True)
+        acc_bq, _, acc_bv = [acc_of(b).view(-1) for b in (bq, bk, bv)]      # d(bias k) = 0, see _EncoderBlockFused
+        do0 = ops.gemm(dhb0, SHADOW.get(wo, False)[0].view(D, D), b_mn=False, out_dtype=BF16, colsum=acc_bv)
+        dkv = torch.empty((T, 2 * D), dtype=BF16, device=dev)
+        dkv3 = dkv.view(Bsz, N, 2 * D)
+        kv3 = kv.view(Bsz, N, 2 * D)
+        dq0 = torch.empty((Bsz, 1, D), dtype=BF16, device=dev)
+        ops.attn_q1_bwd(do0.view(Bsz, 1, D), q0.view(Bsz, 1, D), kv3[:, :, :D], kv3[:, :, D:], o0, lse, H,
+                        dq=dq0, dk=dkv3[:, :, :D], dv=dkv3[:, :, D:])
+        dq2 = dq0.view(Bsz, D)
+        xn0 = xn.view(Bsz, N * D)[:, :D]
+        ops.gemm(xn0, dq2, a_mn=True, b_mn=True, out=acc_of(wq, (D, D)), accumulate=True)
+        ops.colsum(dq2, acc_bq)
+        accs_w = [acc_of(w, (D, D)) for w in (wk, wv)]
+        gstack = _uniform_stack(accs_w) if _qkv_merge_enabled() and D % 256 == 0 else None
+        if gstack is not None:
+            ops.gemm(xn, dkv, a_mn=True, b_mn=True, out=gstack, accumulate=True)
+        else:
+            for i, acc in enumerate(accs_w):
+                ops.gemm(xn, dkv[:, i * D:(i + 1) * D], a_mn=True, b_mn=True, out=acc, accumulate=True)
+        dx = None
+        acc_g1, acc_be1 = acc_of(n1w), acc_of(n1b)
+        if ctx.needs_input_grad[0]:
+            dxn = ops.gemm([dkv[:, :D], dkv[:, D:]], [SHADOW.get(w, False)[0].view(D, D) for w in (wk, wv)], b_mn=False,
+                           out_dtype=BF16)
+            dxn0 = dxn.view(Bsz, N * D)[:, :D]
+            ops.gemm(dq2, SHADOW.get(wq, False)[0].view(D, D), b_mn=False, out=dxn0, residual=dxn0)   # rows 0 += dq Wq^T
+            direct = _upstream_bias_target(ctx)
+            colsum_dx = direct if direct is not None else torch.zeros(D, dtype=F32, device=dev)
+            dx, dxb, _ = ops.layernorm_bwd(dxn, x2, mean1, rstd1, n1w.detach(), dres=dh0, dres_every=N, want_f32=True,
+                                           want_bf16=True, dgamma=acc_g1, dbeta=acc_be1, dcolsum=colsum_dx)
+            if direct is not None:
+                ctx.up.b2_direct = dxb
+            _side_put(dx, dxb, _DIRECT if direct is not None else colsum_dx)
+            dx = dx.view(ctx.x_shape)
+        else:
+            # LN1's own parameters still need the gradient that reaches its output
+            dxn = ops.gemm([dkv[:, :D], dkv[:, D:]], [SHADOW.get(w, False)[0].view(D, D) for w in (wk, wv)], b_mn=False,
+                           out_dtype=BF16)
+            dxn0 = dxn.view(Bsz, N * D)[:, :D]
+            ops.gemm(dq2, SHADOW.get(wq, False)[0].view(D, D), b_mn=False, out=dxn0, residual=dxn0)
+            ops.layernorm_bwd(dxn, x2, mean1, rstd1, n1w.detach(), want_f32=False, dgamma=acc_g1, dbeta=acc_be1)
+        out = [dx, None, None, None]
+        for p in ctx.params:
+            out.append(grads.get(id(p)) if p.requires_grad else None)
+        out.append(None)                       # up
+        return tuple(out)
+
+
+def encoder_block_row0(x, H, norm1, q, k, v, o, norm2, fc1, fc2):
+    """Class-token row of the last block as one fused node (bf16 mode, head_dim 64, <= 256 tokens), else None (caller
+    composes ops).  VITB_ROW0_FUSED=0 forces the composed path (A/B runs, tests)."""
+    import os
+    D = x.shape[-1]
+    if _fp32_mode() or D % H != 0 or D % 8 != 0 or not ops.attn_q1_supported(D // H, x.shape[1], BF16):
+        return None
+    if os.environ.get("VITB_ROW0_FUSED", "1") == "0":
+        return None
+    if any(m.bias is None for m in (q, k, v, o, fc1, fc2)):
+        return None
+    if not all(p.requires_grad for m in (norm1, q, k, v, o, norm2, fc1, fc2) for p in m.parameters()) and torch.is_grad_enabled():
+        return None
+    return _EncoderBlockRow0.apply(x, H, norm1.eps, norm2.eps, norm1.weight, norm1.bias, q.weight, q.bias, k.weight,
+                                   k.bias, v.weight, v.bias, o.weight, o.bias, norm2.weight, norm2.bias,
+                                   fc1.weight, fc1.bias, fc2.weight, fc2.bias, _upstream_node(x))
 
 
 def encoder_block(x, H, norm1, q, k, v, o, norm2, fc1, fc2):
@@ -1031,7 +1212,7 @@ def encoder_block(x, H, norm1, q, k, v, o, norm2, fc1, fc2):
         return None
     return _EncoderBlockFused.apply(x, H, norm1.eps, norm2.eps, norm1.weight, norm1.bias, q.weight, q.bias, k.weight,
                                     k.bias, v.weight, v.bias, o.weight, o.bias, norm2.weight, norm2.bias,
-                                    fc1.weight, fc1.bias, fc2.weight, fc2.bias)
+                                    fc1.weight, fc1.bias, fc2.weight, fc2.bias, _upstream_node(x))
 
 
 def clear_grad_side_channel():

@@ -146,6 +146,10 @@ class EncoderBlock(nn.Module):
             _dropout_supported(self.dropout_rate, "EncoderBlock")
         x = x if x.dtype == torch.float32 else x.float()
         a = self.attn
+        fused = F.encoder_block_row0(x, a.heads, self.norm1, a.query, a.key, a.value, a.out, self.norm2,
+                                     self.mlp.fc1, self.mlp.fc2)
+        if fused is not None:
+            return fused
         xn = F.layer_norm(x, self.norm1.weight, self.norm1.bias, self.norm1.eps)          # [B,N,D]
         k = F.linear(xn, a.key.weight, a.key.bias, layout="kn")
         v = F.linear(xn, a.value.weight, a.value.bias, layout="kn")

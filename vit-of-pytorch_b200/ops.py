@@ -164,8 +164,9 @@ def layernorm_fwd(x, gamma, beta, eps, *, want_f32=False, want_bf16=True, want_l
 
 
 def layernorm_bwd(dy, x, mean, rstd, gamma, *, dres=None, want_f32=True, want_bf16=False, want_lo=False,
-                  dgamma=None, dbeta=None, dcolsum=None, dx_out=None):
-    """dx = LN'(dy) + dres.  dgamma/dbeta/dcolsum ([D] fp32) are accumulated in place when given."""
+                  dgamma=None, dbeta=None, dcolsum=None, dx_out=None, dres_every=1):
+    """dx = LN'(dy) + dres.  dgamma/dbeta/dcolsum ([D] fp32) are accumulated in place when given.  dres_every = n > 1:
+    dres has rows / n rows and row i of it belongs to row i * n (the other rows have no residual-branch gradient)."""
     L.require_cuda(dy, x, mean, rstd, gamma, dres)
     _check_2d_rowmajor(x, "x")
     rows, D = x.shape
@@ -179,10 +180,13 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, *, dres=None, want_f32=True, want_bf
     dxl = torch.empty((rows, D), dtype=torch.bfloat16, device=dev) if want_lo else None
     if dres is not None:
         _check_2d_rowmajor(dres, "dres")
-    L.check(L._vitb_layernorm_bwd(L.ptr(dy), L.dtype_code(dy), L.ptr(x), x.stride(0), L.ptr(mean), L.ptr(rstd),
-                                  L.ptr(gamma), rows, D, L.ptr(dres), dres.stride(0) if dres is not None else 0,
-                                  L.ptr(dxf), dxf.stride(0) if dxf is not None else 0, L.ptr(dxh), L.ptr(dxl),
-                                  L.ptr(dgamma), L.ptr(dbeta), L.ptr(dcolsum), L.stream_ptr(dev)),
+    if dres is not None and dres_every > 1 and dres.shape[0] * dres_every < rows:
+        raise L.VitbError("layernorm_bwd: dres has %d rows, needs %d" % (dres.shape[0], (rows + dres_every - 1) // dres_every))
+    L.check(L._vitb_layernorm_bwd_sparse_res(L.ptr(dy), L.dtype_code(dy), L.ptr(x), x.stride(0), L.ptr(mean), L.ptr(rstd),
+                                             L.ptr(gamma), rows, D, L.ptr(dres), dres.stride(0) if dres is not None else 0,
+                                             int(dres_every), L.ptr(dxf), dxf.stride(0) if dxf is not None else 0,
+                                             L.ptr(dxh), L.ptr(dxl), L.ptr(dgamma), L.ptr(dbeta), L.ptr(dcolsum),
+                                             L.stream_ptr(dev)),
             "vitb_layernorm_bwd")
     return dxf, dxh, dxl
 
@@ -278,6 +282,36 @@ def attn_bwd(dout, q, k, v, o, lse, H, *, use_tc=None, dq=None, dk=None, dv=None
     if use_tc and _attn_ws_enabled() and L.vitb_attn_ws_supported(1, dh, Nq, Nk):
         fn = L._vitb_attn_bwd_ws        # persistent warp-specialised kernel
     L.check(fn(C.byref(p), L.stream_ptr(q.device)), "vitb_attn_bwd")
+    return dq, dk, dv
+
+
+def attn_q1_supported(dh, Nk, dtype):
+    """Single-query attention with bf16 gradients (the class-token-only last block): bf16, head_dim 64, <= 256 keys."""
+    return dtype == torch.bfloat16 and bool(L.vitb_attn_q1_supported(dh, Nk))
+
+
+def attn_q1_bwd(dout, q, k, v, o, lse, H, *, dq=None, dk=None, dv=None):
+    """Backward of attn_fwd for ONE query per image (q, o, dout: [B, 1, H*64] bf16): bf16 dq [B,1,HD] and dk / dv
+    [B, Nk, HD] (rows written whole; strided views of a packed buffer are fine)."""
+    L.require_cuda(dout, q, k, v, o, lse)
+    B, Nq, HD = q.shape
+    Nk = k.shape[1]
+    dh = HD // H
+    dev = q.device
+    dq = torch.empty((B, 1, HD), dtype=torch.bfloat16, device=dev) if dq is None else dq
+    dk = torch.empty((B, Nk, HD), dtype=torch.bfloat16, device=dev) if dk is None else dk
+    dv = torch.empty((B, Nk, HD), dtype=torch.bfloat16, device=dev) if dv is None else dv
+    for t in (dq, dk, dv, dout, o):
+        if t.dtype != torch.bfloat16:
+            raise L.VitbError("attn_q1_bwd: bf16 tensors only")
+    p = _attn_params(q, k, v, o, lse, H)
+    p.dout = dout.data_ptr()
+    p.do_batch_stride, p.do_row_stride = _head_strides(dout, H, dh, "dout")
+    p.dq, p.dk, p.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
+    p.dq_batch_stride, p.dq_row_stride = _head_strides(dq, H, dh, "dq")
+    p.dk_batch_stride, p.dk_row_stride = _head_strides(dk, H, dh, "dk")
+    p.dv_batch_stride, p.dv_row_stride = _head_strides(dv, H, dh, "dv")
+    L.check(L._vitb_attn_q1_bwd(C.byref(p), L.stream_ptr(dev)), "vitb_attn_q1_bwd")
     return dq, dk, dv
 
 
