@@ -214,6 +214,18 @@ int vitb_embed_bwd(const float* dx, int B, int N, int D, float* dpos, float* dcl
 /* out = dy * gelu_erf'(z), elementwise over n values of dtype f32 or bf16 (backward of nn.GELU(),
  * src/model.py:33,44; res-vit/model.py:154,158,160,312). */
 int vitb_gelu_bwd(const void* dy, const void* z, void* out, int64_t n, int dtype, void* stream);
+/* nn.Dropout of PositionEmbs / MlpBlock / EncoderBlock (src/model.py:11-20,34-50,110-123), training mode:
+ * y = [residual +] keep * x / (1 - p), keep ~ Bernoulli(1 - p) drawn with Philox4x32-10 from (seed, draw counter).
+ * x: n values of dtype f32 or bf16; y has the dtype of x, or fp32 when a (fp32) residual is given; mask: n bytes
+ * (0 / 1), kept for the backward.  state: two uint64 in DEVICE memory, zeroed once by the caller: state[0] is the draw
+ * counter, advanced by every call ON THE DEVICE, so a CUDA graph that contains the call draws a new mask per replay.
+ * The mask stream is this library's own: it is not torch's CUDA generator stream (which the reference's CPU runs do not
+ * share either); parity for dropout is statistical (tests/test_kernels_gpu.py). */
+int vitb_dropout_fwd(const void* x, int x_dtype, const float* residual, void* y, uint8_t* mask, int64_t n, float p,
+                     uint64_t seed, uint64_t* state, void* stream);
+/* dx = dy * mask / (1 - p); dy / dx of dtype f32 or bf16 independently. */
+int vitb_dropout_bwd(const void* dy, int dy_dtype, const uint8_t* mask, void* dx, int dx_dtype, int64_t n, float p,
+                     void* stream);
 /* out[c] += sum_r x[r,c]  (bias gradients). */
 int vitb_colsum(const void* x, int x_dtype, int rows, int cols, int64_t ld, float* out, void* stream);
 /* Same over a packed [rows, 3*seg_cols] buffer (dq|dk|dv): segment i accumulates into out_i[seg_cols]. */

@@ -306,6 +306,42 @@ def test_layernorm_bwd_residual_gradient_on_every_nth_row():
     assert rel_l2(cs_b, cs_a) < 1e-6
 
 
+@pytest.mark.parametrize("dtype,n,p", [(torch.float32, 1 << 20, 0.1), (torch.bfloat16, 1 << 20, 0.1),
+                                       (torch.float32, 1000003, 0.5), (torch.bfloat16, 7, 0.25)])
+def test_dropout_kernel_statistics_mask_consistency_and_fresh_draws(dtype, n, p):
+    """nn.Dropout (src/model.py:12,35-36,111) as vitb_dropout_fwd / _bwd.  The mask stream is the library's own Philox
+    stream, so parity with torch is statistical: keep rate within 5 sigma of 1 - p, kept values scaled by exactly
+    1 / (1 - p) (bf16: one rounding), dropped ones exactly zero, backward = dy * mask / (1 - p), the residual form adds in
+    fp32, and two calls (as two replays of a captured step would) draw different masks."""
+    import vitb200
+    x = (_randn((n,), 1).abs() + 1.0).to(dtype)    # no zeros, so the mask is visible in y
+    state = torch.zeros(2, dtype=torch.int64, device="cuda")
+    y, mask = vitb200.ops.dropout_fwd(x, p, 1234, state)
+    y2, mask2 = vitb200.ops.dropout_fwd(x, p, 1234, state)
+    torch.cuda.synchronize()
+    assert int(state[0]) == 2 and int(state[1]) == 0
+    keep = mask.float().mean().item()
+    if n > 1000:
+        assert abs(keep - (1 - p)) < 5 * math.sqrt(p * (1 - p) / n), keep
+        assert (mask != mask2).float().mean().item() > 0.5 * 2 * p * (1 - p)      # independent draws differ on 2p(1-p)
+        # no visible structure between neighbours: the keep rate of every fourth element matches too
+        for j in range(4):
+            assert abs(mask[j::4].float().mean().item() - (1 - p)) < 6 * math.sqrt(p * (1 - p) / (n / 4))
+    ref = torch.where(mask.bool(), x.float() / (1 - p), torch.zeros((), device="cuda"))
+    assert rel_l2(y, ref) < (4e-3 if dtype == torch.bfloat16 else 1e-6)
+    assert bool(((y == 0) == (mask == 0)).all())
+    dy = _randn((n,), 2, 1.0, dtype)
+    dx = vitb200.ops.dropout_bwd(dy, mask, p, dtype)
+    refd = torch.where(mask.bool(), dy.float() / (1 - p), torch.zeros((), device="cuda"))
+    assert rel_l2(dx, refd) < (4e-3 if dtype == torch.bfloat16 else 1e-6)
+    if n % 4 == 0:
+        res = _randn((n,), 3)
+        st2 = torch.zeros(2, dtype=torch.int64, device="cuda")
+        yr, mr = vitb200.ops.dropout_fwd(x, p, 99, st2, residual=res)
+        refr = res + torch.where(mr.bool(), x.float() / (1 - p), torch.zeros((), device="cuda"))
+        assert yr.dtype == torch.float32 and rel_l2(yr, refr) < 1e-6
+
+
 # ---------------------------------------------------------------------------------- elementwise etc.
 def test_cast_split():
     import vitb200

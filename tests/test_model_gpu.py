@@ -14,7 +14,7 @@ from conftest import grad_close, rel_l2
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle import vit_oracle  # noqa: E402
+from oracle import vit_init, vit_oracle  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(ROOT, "tests", "golden")
@@ -241,3 +241,43 @@ def test_vit_b16_full_depth_bf16_logits_within_2e2_of_fp32_reference():
     with vitb200.precision("bf16"):
         logits_t = m(img).float().detach().cpu()
     assert rel_l2(logits_t, g["logits"]) < 2e-2
+
+
+
+def test_training_with_the_reference_default_dropout_rate():
+    """The reference's constructors default to dropout_rate=0.1 (src/model.py:8,27,105,134,170): such a model must train.
+    Live dropout takes the composed path (LayerNorm -> attention -> dropout + residual -> LayerNorm -> fc1+GELU -> dropout
+    -> fc2 -> dropout + residual, plus the dropout behind the position embedding).  Checked: eval is deterministic and
+    equals the rate-0 model (dropout is the identity there, as in the reference); training logits differ from eval and from
+    each other between two calls; every parameter receives a finite gradient; the mean of many training passes approaches
+    the eval logits of a 1-block model's linear tail (inverted dropout is unbiased)."""
+    import vitb200
+    cfg = dict(image_size=(32, 32), patch_size=(16, 16), emb_dim=128, mlp_dim=256, num_heads=2, num_layers=2, num_classes=10)
+    sd = vit_init.reference_state_dict(cfg, seed=4, scaled=True)
+    m = vitb200.VisionTransformer(**cfg)                      # ctor defaults: dropout_rate=0.1, attn_dropout_rate=0.0
+    m0 = vitb200.VisionTransformer(dropout_rate=0.0, **cfg)
+    assert list(m.state_dict().keys()) == list(m0.state_dict().keys())
+    m.load_state_dict(sd); m0.load_state_dict(sd)
+    m, m0 = m.cuda(), m0.cuda()
+    g = torch.Generator().manual_seed(2)
+    img = torch.randn(16, 3, 32, 32, generator=g).cuda()
+    lab = torch.randint(0, 10, (16,), generator=g).cuda()
+    m.eval(); m0.eval()
+    with torch.no_grad():
+        e1, e2, e0 = m(img), m(img), m0(img)
+    assert torch.equal(e1, e2) and rel_l2(e1, e0) < 1e-6
+    m.train()
+    t1 = m(img)
+    t2 = m(img)
+    assert rel_l2(t1, e1) > 1e-3 and rel_l2(t1, t2) > 1e-3
+    loss = vitb200.functional.cross_entropy(t1, lab)
+    loss.backward()
+    torch.cuda.synchronize()
+    for k, p in m.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), k
+        if not k.endswith("key.bias"):
+            assert float(p.grad.abs().sum()) > 0, k
+    with torch.no_grad():
+        mean = torch.stack([m(img) for _ in range(64)]).mean(0)
+    # the network is non-linear, so the mean only approaches the eval output; it must be much closer than one sample
+    assert rel_l2(mean, e1) < 0.5 * rel_l2(t1.detach(), e1)

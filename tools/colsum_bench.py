@@ -48,9 +48,10 @@ def timeit(fn, cold):
 
 
 lines = []
-for warps in (64, 48, 32, 24, 16, 12, 8, 4):
+for v4, warps in [(v, w) for v in (0, 1) for w in (64, 48, 32, 24, 16, 8)]:
     os.environ["VITB_COLSUM_WARPS"] = str(warps)
-    row = ["warps/SM %2d" % warps]
+    os.environ["VITB_COLSUM_V4"] = str(v4)
+    row = ["v4=%d warps/SM %2d" % (v4, warps)]
     for name, fn, nbytes in (("dq slice bf16", lambda: ops.colsum(dq[:, :D], acc), T * D * 2),
                              ("dense bf16", lambda: ops.colsum(xb, acc), T * D * 2),
                              ("dense fp32", lambda: ops.colsum(x32, acc), T * D * 4)):

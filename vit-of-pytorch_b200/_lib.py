@@ -184,6 +184,8 @@ _vitb_im2col = _sig("vitb_im2col", [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp])
 _vitb_cls_rows = _sig("vitb_cls_rows", [_vp, _i, _i, _i, _vp, _vp, _vp])
 _vitb_embed_bwd = _sig("vitb_embed_bwd", [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp])
 _vitb_gelu_bwd = _sig("vitb_gelu_bwd", [_vp, _vp, _vp, _i64, _i, _vp])
+_vitb_dropout_fwd = _sig("vitb_dropout_fwd", [_vp, _i, _vp, _vp, _vp, _i64, _f, C.c_uint64, _vp, _vp])
+_vitb_dropout_bwd = _sig("vitb_dropout_bwd", [_vp, _i, _vp, _vp, _i, _i64, _f, _vp])
 _vitb_colsum = _sig("vitb_colsum", [_vp, _i, _i, _i, _i64, _vp, _vp])
 _vitb_colsum3 = _sig("vitb_colsum3", [_vp, _i, _i, _i, _i64, _vp, _vp, _vp, _vp])
 _vitb_cross_entropy = _sig("vitb_cross_entropy", [_vp, _vp, _i, _i, _vp, _vp, _vp])
@@ -214,5 +216,5 @@ EXPORTED_SYMBOLS = [
     "vitb_token_mean_fwd", "vitb_token_mean_bwd", "vitb_select_rows", "vitb_colsum3",
     "vitb_resize_tables_host", "vitb_image_prep",
     "vitb_distill_loss", "vitb_active_loss", "vitb_compact_rows", "vitb_gather_rows", "vitb_scatter_rows", "vitb_attn_ws_supported", "vitb_attn_fwd_ws", "vitb_attn_bwd_ws",
-    "vitb_layernorm_bwd_sparse_res", "vitb_attn_q1_supported", "vitb_attn_q1_bwd",
+    "vitb_layernorm_bwd_sparse_res", "vitb_attn_q1_supported", "vitb_attn_q1_bwd", "vitb_dropout_fwd", "vitb_dropout_bwd",
 ]

@@ -170,15 +170,15 @@ embed_bwd_kernel(const float* __restrict__ dx, int Bsz, int N, int D, float* __r
 
 // out[c] += sum_r x[r, c].  A thread owns 16 bytes of a row (8 bf16 / 4 fp32 columns; 4 bf16 columns when the width
 // is not a multiple of 8).  Block = (column groups) x (NY row lanes); the block's row slice is walked NY rows at a
-// time with 8 independent loads per thread, the NY partial sums meet in shared memory and one atomic per column and
-// block goes out.  HBM-bound: rows * cols * esize bytes read once; ptxas keeps the kernel at 32 registers, so the
-// loads in flight come from occupancy (64 warps per SM), and the grid is sized for exactly that.
+// time with 8 independent loads per thread, the NY partial sums meet in shared memory and one 16-byte vector reduction
+// per four columns and block goes out.  HBM-bound: rows * cols * esize bytes read once; ptxas keeps the kernel at 32
+// registers, so the loads in flight come from occupancy; the grid is sized for 32 warps per SM (measured best).
 constexpr int kColsumThreads = 512;
 template <bool BF16, int VEC>   // VEC = columns per thread: 8 or 4 (bf16), 4 (fp32)
 __global__ void __launch_bounds__(kColsumThreads)
 colsum_kernel(const void* __restrict__ x_, int rows, int cols, long long ld_, float* __restrict__ out0,
-              float* __restrict__ out1, float* __restrict__ out2, int seg_cols) {
-  extern __shared__ float colsum_part[];   // [blockDim.y][blockDim.x * VEC]
+              float* __restrict__ out1, float* __restrict__ out2, int seg_cols, bool v4) {
+  extern __shared__ __align__(16) float colsum_part[];   // [blockDim.y][blockDim.x * VEC]
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
   const bool live = c < cols;
   const int rows_per = (rows + gridDim.y - 1) / gridDim.y;
@@ -223,20 +223,45 @@ colsum_kernel(const void* __restrict__ x_, int rows, int cols, long long ld_, fl
 #pragma unroll
   for (int j = 0; j < VEC; ++j) colsum_part[threadIdx.y * width + threadIdx.x * VEC + j] = s[j];
   __syncthreads();
-  if (threadIdx.y == 0 && live) {
-    const int seg = c / seg_cols;     // seg_cols is a multiple of VEC: a thread never straddles two segments
-    float* out = (seg == 0 ? out0 : (seg == 1 ? out1 : out2)) - static_cast<long long>(seg) * seg_cols;
-#pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-      float t = s[j];
-      for (int y = 1; y < ny; ++y) t += colsum_part[y * width + threadIdx.x * VEC + j];
-      atomicAdd(out + c + j, t);
+  // fold the row lanes; consecutive threads own consecutive columns, so a warp's 32 scalar reductions are one 128-byte
+  // transaction at L2.  (The first version let the lanes that loaded 8 columns each reduce them: 32 bytes between lanes,
+  // eight transactions per warp instruction, issued by a fifth of the block — the tail was the longest part of the
+  // kernel, profiles/colsum_r02.txt.  VITB_COLSUM_V4=1 sends red.global.add.v4.f32 per four columns instead, for A/B runs.)
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  const int nthr = blockDim.x * blockDim.y;
+  const int cbase = blockIdx.x * width;
+  if (!v4) {
+    for (int cl = tid; cl < width; cl += nthr) {
+      const int cc = cbase + cl;
+      if (cc >= cols) break;
+      float t = colsum_part[cl];
+      for (int y = 1; y < ny; ++y) t += colsum_part[y * width + cl];
+      const int seg = cc / seg_cols;
+      float* dst = (seg == 0 ? out0 : (seg == 1 ? out1 : out2)) - static_cast<long long>(seg) * seg_cols + cc;
+      atomicAdd(dst, t);
+    }
+    return;
+  }
+  for (int q4 = tid; q4 * 4 < width; q4 += nthr) {
+    const int cc = cbase + q4 * 4;
+    if (cc >= cols) break;
+    float4 t = *reinterpret_cast<const float4*>(colsum_part + q4 * 4);
+    for (int y = 1; y < ny; ++y) {
+      const float4 u = *reinterpret_cast<const float4*>(colsum_part + y * width + q4 * 4);
+      t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+    }
+    const int seg = cc / seg_cols;    // seg_cols is a multiple of 4: a quad never straddles two segments
+    float* dst = (seg == 0 ? out0 : (seg == 1 ? out1 : out2)) - static_cast<long long>(seg) * seg_cols + cc;
+    if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(t.x), "f"(t.y), "f"(t.z), "f"(t.w) : "memory");
+    } else {
+      atomicAdd(dst, t.x); atomicAdd(dst + 1, t.y); atomicAdd(dst + 2, t.z); atomicAdd(dst + 3, t.w);
     }
   }
 }
 
 // grid for the above: x over column groups with the block width that wastes the fewest lanes (2304 bf16 columns are
-// 288 groups = 3 blocks of 96 x 5), y over row slices of >= 32 rows per row lane, 64 warps per SM in total
+// 288 groups = 3 blocks of 96 x 5), y over row slices of >= 8 rows per row lane, 32 warps per SM in total
 template <bool BF16, int VEC>
 static void colsum_launch(const void* x, int rows, int cols, long long ld, float* o0, float* o1, float* o2, int seg_cols,
                           cudaStream_t stream) {
@@ -249,14 +274,16 @@ static void colsum_launch(const void* x, int rows, int cols, long long ld, float
   const int ny = kColsumThreads / tb;                 // >= 2 row lanes share a block (and one atomic per column)
   const int bx = (groups + tb - 1) / tb;
   const int warps_per_block = tb * ny / 32;
-  int warps_per_sm = 64;
+  int warps_per_sm = 32;     // measured best of 4..64 on B200 (profiles/colsum_r02.txt)
   if (const char* e = getenv("VITB_COLSUM_WARPS")) { const int v = atoi(e); if (v >= 1 && v <= 64) warps_per_sm = v; }   // tuning runs
   int by = (vitb_num_sms() * warps_per_sm + bx * warps_per_block - 1) / (bx * warps_per_block);
-  const int max_by = (rows + 32 * ny - 1) / (32 * ny);
+  const int max_by = (rows + 8 * ny - 1) / (8 * ny);     // at least one round of 8 loads per thread
   if (by > max_by) by = max_by;
   if (by < 1) by = 1;
   const size_t smem = static_cast<size_t>(ny) * tb * VEC * sizeof(float);
-  colsum_kernel<BF16, VEC><<<dim3(bx, by), dim3(tb, ny), smem, stream>>>(x, rows, cols, ld, o0, o1, o2, seg_cols);
+  bool v4 = false;
+  if (const char* e = getenv("VITB_COLSUM_V4")) v4 = atoi(e) != 0;     // tuning runs
+  colsum_kernel<BF16, VEC><<<dim3(bx, by), dim3(tb, ny), smem, stream>>>(x, rows, cols, ld, o0, o1, o2, seg_cols, v4);
 }
 static void colsum_dispatch(const void* x, int x_dtype, int rows, int cols, long long ld, float* o0, float* o1, float* o2,
                             int seg_cols, cudaStream_t stream) {
@@ -451,6 +478,100 @@ gelu_bwd_kernel(const void* __restrict__ dy_, const void* __restrict__ z_, void*
 
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------
+// Dropout (nn.Dropout of PositionEmbs / MlpBlock / EncoderBlock, src/model.py:11-20,34-50,110-123).
+// y = [residual +] keep * x / (1 - p), keep ~ Bernoulli(1 - p) from Philox4x32-10 keyed by (seed, draw counter), one
+// counter-mode call per four consecutive elements.  The draw counter lives in DEVICE memory (state[0]) and is advanced
+// by the kernel itself, so a step replayed from a CUDA graph draws a fresh mask every replay: every block reads the
+// counter when it starts; the block that takes the last ticket (state[1]) — by then every block has started — stores
+// counter + 1 and clears the tickets.  The mask is kept (one byte per element) for the backward.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t k0, uint32_t k1, uint4 c) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return c;
+}
+
+template <bool BF16, bool RES>
+__global__ void __launch_bounds__(kThreads)
+dropout_fwd_kernel(const void* __restrict__ x_, const float* __restrict__ res, void* __restrict__ y_,
+                   uint8_t* __restrict__ mask, long long n, uint32_t keep_below, float scale,
+                   unsigned long long seed, unsigned long long* __restrict__ state) {
+  const unsigned long long draw = *reinterpret_cast<volatile unsigned long long*>(state);
+  const uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
+  const long long n4 = (n + 3) >> 2;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const uint4 r = philox4x32_10(k0, k1, make_uint4(static_cast<uint32_t>(i), static_cast<uint32_t>(i >> 32),
+                                                     static_cast<uint32_t>(draw), static_cast<uint32_t>(draw >> 32)));
+    const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+    const long long e0 = i << 2;
+    if (e0 + 3 < n) {
+      float4 v;
+      if constexpr (BF16) {
+        const uint2 a = reinterpret_cast<const uint2*>(x_)[i];
+        v = make_float4(bf16_lo(a.x), bf16_hi(a.x), bf16_lo(a.y), bf16_hi(a.y));
+      } else {
+        v = reinterpret_cast<const float4*>(x_)[i];
+      }
+      uchar4 m;
+      m.x = rr[0] < keep_below; m.y = rr[1] < keep_below; m.z = rr[2] < keep_below; m.w = rr[3] < keep_below;
+      v.x = m.x ? v.x * scale : 0.f; v.y = m.y ? v.y * scale : 0.f; v.z = m.z ? v.z * scale : 0.f; v.w = m.w ? v.w * scale : 0.f;
+      reinterpret_cast<uchar4*>(mask)[i] = m;
+      if constexpr (RES) {
+        const float4 q = reinterpret_cast<const float4*>(res)[i];
+        reinterpret_cast<float4*>(y_)[i] = make_float4(q.x + v.x, q.y + v.y, q.z + v.z, q.w + v.w);
+      } else if constexpr (BF16) {
+        uint2 o;
+        o.x = pack_bf16x2(v.x, v.y); o.y = pack_bf16x2(v.z, v.w);
+        reinterpret_cast<uint2*>(y_)[i] = o;
+      } else {
+        reinterpret_cast<float4*>(y_)[i] = v;
+      }
+    } else {
+      for (int j = 0; j < 4 && e0 + j < n; ++j) {
+        const long long e = e0 + j;
+        float v = BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x_)[e]) : reinterpret_cast<const float*>(x_)[e];
+        const uint8_t m = rr[j] < keep_below;
+        v = m ? v * scale : 0.f;
+        mask[e] = m;
+        if constexpr (RES) reinterpret_cast<float*>(y_)[e] = res[e] + v;
+        else if constexpr (BF16) reinterpret_cast<__nv_bfloat16*>(y_)[e] = __float2bfloat16(v);
+        else reinterpret_cast<float*>(y_)[e] = v;
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned long long t = atomicAdd(state + 1, 1ull);
+    if (t == gridDim.x - 1) {       // every block has read `draw` before it took its ticket
+      state[1] = 0ull;
+      state[0] = draw + 1ull;
+      __threadfence();
+    }
+  }
+}
+
+// dx = dy * mask / (1 - p)
+template <bool IN_BF16, bool OUT_BF16>
+__global__ void __launch_bounds__(kThreads)
+dropout_bwd_kernel(const void* __restrict__ dy_, const uint8_t* __restrict__ mask, void* __restrict__ dx_, long long n,
+                   float scale) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < n; e += stride) {
+    const float d = IN_BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(dy_)[e]) : reinterpret_cast<const float*>(dy_)[e];
+    const float v = mask[e] ? d * scale : 0.f;
+    if constexpr (OUT_BF16) reinterpret_cast<__nv_bfloat16*>(dx_)[e] = __float2bfloat16(v);
+    else reinterpret_cast<float*>(dx_)[e] = v;
+  }
+}
+
 extern "C" {
 
 int vitb_gelu_bwd(const void* dy, const void* z, void* out, int64_t n, int dtype, void* stream_) {
@@ -463,6 +584,52 @@ int vitb_gelu_bwd(const void* dy, const void* z, void* out, int64_t n, int dtype
   else
     gelu_bwd_kernel<false><<<grid_for((n + 3) / 4), kThreads, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(dy, z, out, n);
   VITB_LAUNCH_CHECK("gelu_bwd_kernel");
+  return VITB_OK;
+}
+
+int vitb_dropout_fwd(const void* x, int x_dtype, const float* residual, void* y, uint8_t* mask, int64_t n, float p,
+                     uint64_t seed, uint64_t* state, void* stream_) {
+  int st = vitb_check_device();
+  if (st != VITB_OK) return st;
+  if (n == 0) return VITB_OK;
+  VITB_REQUIRE(x && y && mask && state && n > 0, VITB_ERR_BAD_ARG, "dropout_fwd: bad args");
+  VITB_REQUIRE(p >= 0.f && p < 1.f, VITB_ERR_BAD_ARG, "dropout_fwd: p=%f must be in [0, 1)", (double)p);
+  VITB_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(residual)) & 15u) == 0 &&
+               (reinterpret_cast<uintptr_t>(mask) & 3u) == 0 && (reinterpret_cast<uintptr_t>(state) & 7u) == 0,
+               VITB_ERR_BAD_ARG, "dropout_fwd: x / y / residual must be 16-byte aligned, mask 4-byte, state 8-byte");
+  const double keep = 1.0 - (double)p;
+  const double kb = keep * 4294967296.0;
+  const uint32_t keep_below = kb >= 4294967295.0 ? 0xFFFFFFFFu : static_cast<uint32_t>(kb);
+  const float scale = static_cast<float>(1.0 / keep);
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const int grid = grid_for((n + 3) / 4);
+  unsigned long long* sp = reinterpret_cast<unsigned long long*>(state);
+  if (x_dtype == VITB_BF16) {
+    if (residual) dropout_fwd_kernel<true, true><<<grid, kThreads, 0, stream>>>(x, residual, y, mask, n, keep_below, scale, seed, sp);
+    else dropout_fwd_kernel<true, false><<<grid, kThreads, 0, stream>>>(x, residual, y, mask, n, keep_below, scale, seed, sp);
+  } else {
+    if (residual) dropout_fwd_kernel<false, true><<<grid, kThreads, 0, stream>>>(x, residual, y, mask, n, keep_below, scale, seed, sp);
+    else dropout_fwd_kernel<false, false><<<grid, kThreads, 0, stream>>>(x, residual, y, mask, n, keep_below, scale, seed, sp);
+  }
+  VITB_LAUNCH_CHECK("dropout_fwd_kernel");
+  return VITB_OK;
+}
+
+int vitb_dropout_bwd(const void* dy, int dy_dtype, const uint8_t* mask, void* dx, int dx_dtype, int64_t n, float p,
+                     void* stream_) {
+  int st = vitb_check_device();
+  if (st != VITB_OK) return st;
+  if (n == 0) return VITB_OK;
+  VITB_REQUIRE(dy && mask && dx && n > 0 && p >= 0.f && p < 1.f, VITB_ERR_BAD_ARG, "dropout_bwd: bad args");
+  const float scale = static_cast<float>(1.0 / (1.0 - (double)p));
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const int grid = grid_for(n);
+  const bool ib = dy_dtype == VITB_BF16, ob = dx_dtype == VITB_BF16;
+  if (ib && ob) dropout_bwd_kernel<true, true><<<grid, kThreads, 0, stream>>>(dy, mask, dx, n, scale);
+  else if (ib) dropout_bwd_kernel<true, false><<<grid, kThreads, 0, stream>>>(dy, mask, dx, n, scale);
+  else if (ob) dropout_bwd_kernel<false, true><<<grid, kThreads, 0, stream>>>(dy, mask, dx, n, scale);
+  else dropout_bwd_kernel<false, false><<<grid, kThreads, 0, stream>>>(dy, mask, dx, n, scale);
+  VITB_LAUNCH_CHECK("dropout_bwd_kernel");
   return VITB_OK;
 }
 

@@ -167,6 +167,12 @@ ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, long lo
     }
     s1 = warp_sum(s1) * (1.0f / D);
     s2 = warp_sum(s2) * (1.0f / D);
+    // residual-branch gradient of this row: every row has one, or (dres_every = n > 1) only rows 0, n, 2n, ...
+    const float* dres_row = nullptr;
+    if (dres) {
+      if (dres_every == 1) dres_row = dres + static_cast<long long>(row) * dres_stride;
+      else if (row % dres_every == 0) dres_row = dres + static_cast<long long>(row / dres_every) * dres_stride;
+    }
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = (i * 32 + lane) * 4;
@@ -178,8 +184,8 @@ ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, long lo
       d.y = rs * (gy.y - s1 - xh[i].y * s2);
       d.z = rs * (gy.z - s1 - xh[i].z * s2);
       d.w = rs * (gy.w - s1 - xh[i].w * s2);
-      if (dres && (dres_every == 1 || row % dres_every == 0)) {   // dres_every > 1: only every n-th row has a residual gradient
-        const float4 r = ld4(dres + static_cast<long long>(row / dres_every) * dres_stride + c);
+      if (dres_row) {
+        const float4 r = ld4(dres_row + c);
         d.x += r.x; d.y += r.y; d.z += r.z; d.w += r.w;
       }
       if constexpr (COLSUM) add4(acc + 2 * D + c, d.x, d.y, d.z, d.w);
@@ -194,6 +200,9 @@ ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, long lo
   // fold the warps' slices, then one global atomic per column and block
   __syncthreads();
   constexpr int NSUM = COLSUM ? 3 : 2;
+  // one scalar reduction per column, consecutive lanes on consecutive columns: a warp's 32 reductions are ONE 128-byte
+  // transaction at L2.  (red.global.add.v4.f32 here — four columns per lane — made this kernel 36 % slower, 56 -> 76 us
+  // per launch, profiles/launches_r02n.csv: each lane's 16 bytes travel as a transaction of their own.)
   for (int i = threadIdx.x; i < NSUM * D; i += blockDim.x) {
     float t = 0.f;
 #pragma unroll 4

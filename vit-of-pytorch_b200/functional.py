@@ -461,6 +461,69 @@ def mlp(x, w1, b1, w2, b2, *, residual=None, out_dtype=None):
 
 
 # --------------------------------------------------------------------------------------------------
+# dropout
+# --------------------------------------------------------------------------------------------------
+class DropoutSite:
+    """RNG state of one nn.Dropout of the reference (src/model.py:12,35-36,111): a seed and a draw counter in device
+    memory that the kernel itself advances (so a captured step draws a fresh mask per replay).  Not a registered buffer:
+    the state-dict keys stay the reference's.  Seeds differ per site and per rank."""
+    _sites = 0
+
+    def __init__(self):
+        DropoutSite._sites += 1
+        self.index = DropoutSite._sites
+        self._state = None
+        self._seed = None
+
+    def get(self, device):
+        if self._state is None or self._state.device != device:
+            import torch.distributed as dist
+            rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+            self._seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + self.index * 0xD1B54A32D192ED03 + rank * 0x94D049BB133111EB) & ((1 << 64) - 1)
+            self._state = torch.zeros(2, dtype=torch.int64, device=device)
+        return self._seed, self._state
+
+
+class _Dropout(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, residual, p, site):
+        L.require_cuda(x)
+        xc = x if x.is_contiguous() else x.contiguous()
+        if xc.dtype not in (F32, BF16):
+            xc = xc.float()
+        res = None
+        if residual is not None:
+            res = residual if (residual.dtype == F32 and residual.is_contiguous()) else residual.float().contiguous()
+        seed, state = site.get(x.device)
+        y, mask = ops.dropout_fwd(xc, p, seed, state, residual=res)
+        ctx.save_for_backward(mask)
+        ctx.p, ctx.x_dtype, ctx.res_dtype = p, x.dtype, (residual.dtype if residual is not None else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        mask, = ctx.saved_tensors
+        dx = ops.dropout_bwd(dy, mask, ctx.p, ctx.x_dtype if ctx.x_dtype in (F32, BF16) else F32) if ctx.needs_input_grad[0] else None
+        if dx is not None and dx.dtype != ctx.x_dtype:
+            dx = dx.to(ctx.x_dtype)
+        dres = None
+        if ctx.res_dtype is not None and ctx.needs_input_grad[1]:
+            dres = dy if dy.dtype == ctx.res_dtype else dy.to(ctx.res_dtype)
+        return dx, dres, None, None
+
+
+def dropout(x, p, training, site, *, residual=None):
+    """nn.Dropout(p)(x) [+ residual] (src/model.py:19-20,45-50,122-124).  Identity (plus the residual) when not training
+    or p == 0; the mask comes from this library's Philox stream, not torch's generator."""
+    if not training or not p:
+        return x if residual is None else x.float() + residual
+    if p >= 1.0:
+        z = torch.zeros_like(x, dtype=F32 if residual is not None else x.dtype)
+        return z if residual is None else z + residual
+    return _Dropout.apply(x, residual, float(p), site)
+
+
+# --------------------------------------------------------------------------------------------------
 # LayerNorm
 # --------------------------------------------------------------------------------------------------
 class _LayerNorm(torch.autograd.Function):

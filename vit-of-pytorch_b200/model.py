@@ -15,12 +15,10 @@ import torch.nn as nn
 from . import functional as F
 
 
-def _dropout_supported(rate, what):
-    if rate and rate > 0:
-        # The reference's presets set every dropout rate to 0.0 (src/config.py:64-65).  The fused
-        # path has no dropout kernel; refuse rather than silently diverge.
-        raise NotImplementedError(
-            "%s: dropout_rate > 0 is not implemented in the B200 path (reference presets use 0.0)" % what)
+def _drop_active(module):
+    """Dropout of this module is live: training mode and a rate > 0 (the reference's presets use 0.0, src/config.py:64-65,
+    its constructors default to 0.1).  Live dropout takes the composed path: the fused block nodes have no mask inputs."""
+    return module.training and bool(module.dropout_rate) and module.dropout_rate > 0
 
 
 class PositionEmbs(nn.Module):
@@ -32,11 +30,11 @@ class PositionEmbs(nn.Module):
         self.pos_embedding = nn.Parameter(torch.randn(1, num_patches + 1, emb_dim))
         self.dropout_rate = dropout_rate
         self.dropout = None
+        self._site = F.DropoutSite()
 
     def forward(self, x):
-        if self.training:
-            _dropout_supported(self.dropout_rate, "PositionEmbs")
-        return x.float() + self.pos_embedding  # one elementwise add; only used when called standalone
+        out = x.float() + self.pos_embedding  # one elementwise add; only used when called standalone
+        return F.dropout(out, self.dropout_rate, _drop_active(self), self._site)
 
 
 class MlpBlock(nn.Module):
@@ -51,10 +49,14 @@ class MlpBlock(nn.Module):
         self.dropout_rate = dropout_rate
         self.dropout1 = None
         self.dropout2 = None
+        self._site1, self._site2 = F.DropoutSite(), F.DropoutSite()
 
     def forward(self, x, residual=None):
-        if self.training:
-            _dropout_supported(self.dropout_rate, "MlpBlock")
+        if _drop_active(self):      # fc1 -> GELU -> dropout -> fc2 -> dropout (src/model.py:42-51)
+            t = F.linear(x, self.fc1.weight, self.fc1.bias, act="gelu")
+            t = F.dropout(t, self.dropout_rate, True, self._site1)
+            t = F.linear(t, self.fc2.weight, self.fc2.bias)
+            return F.dropout(t, self.dropout_rate, True, self._site2, residual=residual)
         return F.mlp(x, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias, residual=residual)
 
 
@@ -119,13 +121,17 @@ class EncoderBlock(nn.Module):
         self.attn = SelfAttention(in_dim, heads=num_heads, dropout_rate=attn_dropout_rate)
         self.dropout_rate = dropout_rate
         self.dropout = None
+        self._site = F.DropoutSite()
         self.norm2 = nn.LayerNorm(in_dim)
         self.mlp = MlpBlock(in_dim, mlp_dim, in_dim, dropout_rate)
 
     def forward(self, x):
-        if self.training:
-            _dropout_supported(self.dropout_rate, "EncoderBlock")
         x = x if x.dtype == torch.float32 else x.float()
+        if _drop_active(self):      # x + dropout(attn(LN1 x)); h + MLP-with-dropout(LN2 h)  (src/model.py:117-130)
+            out = F.layer_norm(x, self.norm1.weight, self.norm1.bias, self.norm1.eps)
+            h = F.dropout(self.attn(out), self.dropout_rate, True, self._site, residual=x)
+            out = F.layer_norm(h, self.norm2.weight, self.norm2.bias, self.norm2.eps)
+            return self.mlp(out, residual=h)
         if x.dim() == 3:
             y = F.encoder_block(x, self.attn.heads, self.norm1, self.attn.query, self.attn.key, self.attn.value,
                                 self.attn.out, self.norm2, self.mlp.fc1, self.mlp.fc2)
@@ -142,8 +148,8 @@ class EncoderBlock(nn.Module):
         (src/model.py:155,210).  Keys and values still need every token, but the query, the output projection
         and the whole MLP are per-row, so they run on B rows instead of B*N; every logit and every parameter
         gradient is unchanged (the skipped rows have exactly zero gradient in the reference as well)."""
-        if self.training:
-            _dropout_supported(self.dropout_rate, "EncoderBlock")
+        if _drop_active(self):
+            return self.forward(x)[:, 0]
         x = x if x.dtype == torch.float32 else x.float()
         a = self.attn
         fused = F.encoder_block_row0(x, a.heads, self.norm1, a.query, a.key, a.value, a.out, self.norm2,
@@ -174,7 +180,11 @@ class Encoder(nn.Module):
         self.norm = nn.LayerNorm(emb_dim)
 
     def forward(self, x, pos_added=False, norm_rows=None):
-        out = x if pos_added else self.pos_embedding(x)
+        if pos_added:       # the add was folded into the patch-embedding epilogue; the dropout behind it (src/model.py:19-20) was not
+            pe = self.pos_embedding
+            out = F.dropout(x, pe.dropout_rate, _drop_active(pe), pe._site)
+        else:
+            out = self.pos_embedding(x)
         layers = list(self.encoder_layers)
         row0_only = norm_rows == 0 and len(layers) > 0 and F.get_precision() == "bf16"
         for layer in (layers[:-1] if row0_only else layers):

@@ -441,6 +441,33 @@ def gelu_bwd(dy, z):
     return out
 
 
+def dropout_fwd(x, p, seed, state, *, residual=None):
+    """(y, mask): y = [residual +] keep * x / (1 - p).  x: contiguous fp32 / bf16; residual: contiguous fp32 of x's shape;
+    state: uint64-as-int64 CUDA tensor [2], zero-initialised once per dropout site (the draw counter lives there)."""
+    L.require_cuda(x, residual, state)
+    if not x.is_contiguous() or (residual is not None and (not residual.is_contiguous() or residual.dtype != torch.float32
+                                                           or residual.shape != x.shape)):
+        raise L.VitbError("dropout_fwd: x (and the fp32 residual of the same shape) must be contiguous")
+    if state.dtype != torch.int64 or state.numel() != 2:
+        raise L.VitbError("dropout_fwd: state must be an int64 CUDA tensor with two elements")
+    y = torch.empty(x.shape, dtype=torch.float32 if residual is not None else x.dtype, device=x.device)
+    mask = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    L.check(L._vitb_dropout_fwd(L.ptr(x), L.dtype_code(x), L.ptr(residual), L.ptr(y), L.ptr(mask), x.numel(), float(p),
+                                int(seed) & 0xFFFFFFFFFFFFFFFF, L.ptr(state), L.stream_ptr(x.device)), "vitb_dropout_fwd")
+    return y, mask
+
+
+def dropout_bwd(dy, mask, p, out_dtype):
+    """dx = dy * mask / (1 - p) in `out_dtype`."""
+    L.require_cuda(dy, mask)
+    if not dy.is_contiguous() or dy.shape != mask.shape:
+        dy = dy.contiguous()
+    dx = torch.empty(dy.shape, dtype=out_dtype, device=dy.device)
+    L.check(L._vitb_dropout_bwd(L.ptr(dy), L.dtype_code(dy), L.ptr(mask), L.ptr(dx), L.dtype_code(dx), dy.numel(), float(p),
+                                L.stream_ptr(dy.device)), "vitb_dropout_bwd")
+    return dx
+
+
 def colsum(x, out):
     """out[c] += sum_r x[r,c]."""
     L.require_cuda(x, out)
