@@ -67,13 +67,13 @@ int vitb_check_device() {
   return VITB_OK;
 }
 
-bool vitb_pdl_enabled() {
+bool vitb_pdl_enabled(int family) {
   // Programmatic dependent launch is compiled into the heavy kernels (griddepcontrol.launch_dependents / .wait) but
   // stays OFF: measured twice (round 1: 6,297 vs 6,330 images/s; round 2, profiles/pdl_ab_r02.txt: 7,100 vs 7,181) it is
   // slower on a power-capped B200, and in round 2 one optimizer round-trip test differed at 1.7e-4 with it on — an
   // ordering it exposes has not been tracked down.  VITB_PDL_EXPERIMENTAL=1 turns it on for that investigation only.
-  const char* e = getenv("VITB_PDL_EXPERIMENTAL");
-  return e != nullptr && atoi(e) != 0;
+  const char* e = getenv("VITB_PDL_EXPERIMENTAL");   // bit mask over kernel families: 1 GEMM, 2 LayerNorm, 4 attention
+  return e != nullptr && (atoi(e) & family) != 0;
 }
 
 int vitb_num_sms() {

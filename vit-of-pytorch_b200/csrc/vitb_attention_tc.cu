@@ -750,7 +750,7 @@ int launch_fwd_gen(const vitb_attn_params* p, cudaStream_t stream) {
   VITB_REQUIRE(smem <= 227 * 1024, VITB_ERR_UNSUPPORTED_SHAPE, "attn_fwd_tc_gen: %d B of shared memory", smem);
   VITB_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_tc_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   dim3 grid((N + 127) / 128, p->H, p->B);
-  VITB_CUDA_CHECK(vitb_launch(attn_fwd_tc_gen, grid, dim3(kAttnThreads), smem, stream, tq, tk, tv, a));
+  VITB_CUDA_CHECK(vitb_launch<kPdlAttn>(attn_fwd_tc_gen, grid, dim3(kAttnThreads), smem, stream, tq, tk, tv, a));
   VITB_LAUNCH_CHECK("attn_fwd_tc_gen");
   return VITB_OK;
 }
@@ -780,7 +780,7 @@ extern "C" int vitb_attn_fwd_tc(const vitb_attn_params* p, void* stream_) {
   dim3 grid((N + 127) / 128, p->H, p->B);
   CUtensorMap to;
   if ((st = make_head_map(&to, p->o, p->H, N, p->B, p->o_row_stride, p->o_batch_stride, 128)) != VITB_OK) return st;
-  VITB_CUDA_CHECK(vitb_launch(attn_fwd_tc, grid, dim3(kAttnThreads), smem, reinterpret_cast<cudaStream_t>(stream_), tq, tk,
+  VITB_CUDA_CHECK(vitb_launch<kPdlAttn>(attn_fwd_tc, grid, dim3(kAttnThreads), smem, reinterpret_cast<cudaStream_t>(stream_), tq, tk,
                               tv, to, a));
   VITB_LAUNCH_CHECK("attn_fwd_tc");
   return VITB_OK;
@@ -821,7 +821,7 @@ extern "C" int vitb_attn_bwd_tc(const vitb_attn_params* p, void* stream_) {
   if ((st = make_head_map(&tdq, p->dq, p->H, N, p->B, p->dq_row_stride, p->dq_batch_stride, 128)) != VITB_OK) return st;
   if ((st = make_head_map(&tdk, p->dk, p->H, N, p->B, p->dk_row_stride, p->dk_batch_stride, 128)) != VITB_OK) return st;
   if ((st = make_head_map(&tdv, p->dv, p->H, N, p->B, p->dv_row_stride, p->dv_batch_stride, 128)) != VITB_OK) return st;
-  VITB_CUDA_CHECK(vitb_launch(attn_bwd_tc, grid, dim3(kAttnThreads), smem, reinterpret_cast<cudaStream_t>(stream_), tq, tk,
+  VITB_CUDA_CHECK(vitb_launch<kPdlAttn>(attn_bwd_tc, grid, dim3(kAttnThreads), smem, reinterpret_cast<cudaStream_t>(stream_), tq, tk,
                               tv, tdo, to, tdq, tdk, tdv, a));
   VITB_LAUNCH_CHECK("attn_bwd_tc");
   return VITB_OK;

@@ -830,7 +830,7 @@ extern "C" int vitb_attn_fwd_ws(const vitb_attn_params* p, void* stream_) {
   VITB_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int sms = vitb_num_sms();
   const int grid = a.total < sms ? a.total : sms;
-  VITB_CUDA_CHECK(vitb_launch(attn_fwd_ws, dim3(grid), dim3(kFwdThreads), smem, reinterpret_cast<cudaStream_t>(stream_), tq, tk,
+  VITB_CUDA_CHECK(vitb_launch<kPdlAttn>(attn_fwd_ws, dim3(grid), dim3(kFwdThreads), smem, reinterpret_cast<cudaStream_t>(stream_), tq, tk,
                               tv, to, a));
   VITB_LAUNCH_CHECK("attn_fwd_ws");
   return VITB_OK;
@@ -871,7 +871,7 @@ extern "C" int vitb_attn_bwd_ws(const vitb_attn_params* p, void* stream_) {
   VITB_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int sms = vitb_num_sms();
   const int grid = a.total < sms ? a.total : sms;
-  VITB_CUDA_CHECK(vitb_launch(attn_bwd_ws, dim3(grid), dim3(kBwdThreads), smem, reinterpret_cast<cudaStream_t>(stream_), tq, tk,
+  VITB_CUDA_CHECK(vitb_launch<kPdlAttn>(attn_bwd_ws, dim3(grid), dim3(kBwdThreads), smem, reinterpret_cast<cudaStream_t>(stream_), tq, tk,
                               tv, tdo, to, tdq, tdk, tdv, a));
   VITB_LAUNCH_CHECK("attn_bwd_ws");
   return VITB_OK;

@@ -61,9 +61,11 @@ int vitb_num_sms();        // SM count of the current device
 // allocation, descriptor prefetch) and BEFORE its first global-memory access, so the next kernel's CTAs are
 // scheduled and set up while the previous grid drains, yet never touch memory before it has completed and
 // flushed.  Kernels launched without the attribute (torch's, the small element-wise ones) serialise as usual.
-bool vitb_pdl_enabled();   // vitb_api.cu: environment switch VITB_PDL (round-1 validation)
+// vitb_api.cu: VITB_PDL_EXPERIMENTAL is a bit mask over kernel families (1 GEMM, 2 LayerNorm, 4 attention); default 0
+bool vitb_pdl_enabled(int family);
+constexpr int kPdlGemm = 1, kPdlNorm = 2, kPdlAttn = 4;
 
-template <typename... Exp, typename... Act>
+template <int FAMILY, typename... Exp, typename... Act>
 inline cudaError_t vitb_launch(void (*kernel)(Exp...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                                Act&&... args) {
   cudaLaunchConfig_t cfg = {};
@@ -75,7 +77,7 @@ inline cudaError_t vitb_launch(void (*kernel)(Exp...), dim3 grid, dim3 block, si
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = vitb_pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = vitb_pdl_enabled(FAMILY) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<Act&&>(args)...);
 }
 

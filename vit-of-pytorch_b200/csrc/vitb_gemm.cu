@@ -1072,7 +1072,7 @@ int launch(const CUtensorMap* tm, const GemmDev& d, int grid, cudaStream_t strea
   auto kern = vitb_gemm_kernel<BN, A_MN, B_MN>;
   VITB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg<BN>::SMEM_BYTES));
-  VITB_CUDA_CHECK(vitb_launch(kern, dim3(grid), dim3(kThreads), Cfg<BN>::SMEM_BYTES, stream, tm[0], tm[1], tm[2], tm[3],
+  VITB_CUDA_CHECK(vitb_launch<kPdlGemm>(kern, dim3(grid), dim3(kThreads), Cfg<BN>::SMEM_BYTES, stream, tm[0], tm[1], tm[2], tm[3],
                               tm[4], tm[5], tm[6], tm[7], d));
   VITB_LAUNCH_CHECK("vitb_gemm_kernel");
   return VITB_OK;

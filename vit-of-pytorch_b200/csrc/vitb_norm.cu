@@ -249,10 +249,10 @@ extern "C" int vitb_layernorm_fwd(const void* x, int x_dtype, int64_t x_row_stri
   __nv_bfloat16* yl = reinterpret_cast<__nv_bfloat16*>(y_bf16_lo);
   cudaError_t lerr = cudaSuccess;
   if (x_dtype == VITB_BF16) {
-    VITB_NV_SWITCH(nv, (lerr = vitb_launch(ln_fwd_kernel<NV, true>, dim3(grid), dim3(kWarpsPerBlock * 32), 0, stream,
+    VITB_NV_SWITCH(nv, (lerr = vitb_launch<kPdlNorm>(ln_fwd_kernel<NV, true>, dim3(grid), dim3(kWarpsPerBlock * 32), 0, stream,
                                            x, x_row_stride, rows, gamma, beta, eps, y_f32, yh, yl, mean, rstd)));
   } else {
-    VITB_NV_SWITCH(nv, (lerr = vitb_launch(ln_fwd_kernel<NV, false>, dim3(grid), dim3(kWarpsPerBlock * 32), 0, stream,
+    VITB_NV_SWITCH(nv, (lerr = vitb_launch<kPdlNorm>(ln_fwd_kernel<NV, false>, dim3(grid), dim3(kWarpsPerBlock * 32), 0, stream,
                                            x, x_row_stride, rows, gamma, beta, eps, y_f32, yh, yl, mean, rstd)));
   }
   VITB_CUDA_CHECK(lerr);
@@ -287,7 +287,7 @@ static int layernorm_bwd_impl(const void* dy, int dy_dtype, const float* x, int6
   VITB_NV_SWITCH(nv, (lerr = cudaFuncSetAttribute(ln_bwd_kernel<NV, DYB, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                                   static_cast<int>(LnBwdCfg<NV>::SMEM)),                          \
                       lerr = (lerr != cudaSuccess) ? lerr :                                                       \
-                             vitb_launch(ln_bwd_kernel<NV, DYB, CS>, dim3(grid), dim3(LnBwdCfg<NV>::WARPS * 32), smem,  \
+                             vitb_launch<kPdlNorm>(ln_bwd_kernel<NV, DYB, CS>, dim3(grid), dim3(LnBwdCfg<NV>::WARPS * 32), smem,  \
                                          stream, dy, x, x_row_stride, mean, rstd, gamma, rows, dres,              \
                                          dres_row_stride, dres_every, dx_f32, dx_row_stride, dh, dl, dgamma, dbeta, dcolsum)))
   cudaError_t lerr = cudaSuccess;
