@@ -116,6 +116,28 @@ def gemm_traffic():
 
 
 # ---------------------------------------------------------------------------------------------------
+# NVLink byte counters of one GPU (NVML field values, KiB, summed over its links): evidence that the gradient exchange
+# travels over NVLink, and how many bytes per step it moves
+# ---------------------------------------------------------------------------------------------------
+def nvlink_bytes(gpu_index):
+    """(tx_bytes, rx_bytes) counted so far on all NVLinks of the GPU, or None when NVML has no such counters."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        vals = pynvml.nvmlDeviceGetFieldValues(h, [(pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, 0xFFFFFFFF),
+                                                   (pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX, 0xFFFFFFFF)])
+        out = []
+        for v in vals:
+            if v.nvmlReturn != 0:
+                return None
+            out.append(int(v.value.ullVal) * 1024)
+        return tuple(out)
+    except Exception:  # noqa: BLE001 - the counters are evidence, not a dependency
+        return None
+
+
+# ---------------------------------------------------------------------------------------------------
 # clocks sampled DURING the timed region
 # ---------------------------------------------------------------------------------------------------
 class ClockSampler:
@@ -350,6 +372,7 @@ def main():
         # res-vit/train.py:272-277,65: AdamW(1e-4, wd 0.05) over the trainable set + clip_grad_norm_(1.0)
         opt = vitb200.optim.FusedAdamW([q for q in model.parameters() if q.requires_grad], lr=1e-4, weight_decay=0.05,
                                        max_grad_norm=1.0)
+        resvit.bind_optimizer(model, opt)   # approximators whose key does not occur in a batch are skipped, as torch's AdamW does
         sched = None
         gflop_ref = gflop_exec = resvit_train_gflop(classes=classes)
         if world > 1:   # ActiveLoss is (batch mean - target)^2: make it the loss of the GLOBAL batch (one scalar all-reduce)
@@ -442,12 +465,14 @@ def main():
     barrier()
     t_wall0 = time.time()
     launches0 = vitb200._lib.LAUNCHES[0]
+    nvl0 = nvlink_bytes(local) if (world > 1 and rank == 0) else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         loss = step(img_d, lab_d)
     e1.record()
     torch.cuda.synchronize()
+    nvl1 = nvlink_bytes(local) if nvl0 is not None else None
     ms = e0.elapsed_time(e1)
     launches = vitb200._lib.LAUNCHES[0] - launches0
     if graphed is not None:
@@ -508,6 +533,10 @@ def main():
                        "l2": "per-step working set (GBs of activations) exceeds the 126 MB L2; no flush needed",
                        "weights": "reference constructor, seed 0, attention/pos weights x0.02 (SURVEY F5)"},
             "clocks": clocks,
+            "nvlink": (None if nvl1 is None else
+                       {"tx_bytes_per_step_rank0": (nvl1[0] - nvl0[0]) / args.steps, "rx_bytes_per_step_rank0": (nvl1[1] - nvl0[1]) / args.steps,
+                        "grad_bytes": sum(p.numel() for p in net.parameters() if p.requires_grad) * 4,
+                        "source": "NVML NVLINK_THROUGHPUT_DATA_TX/RX of rank 0's GPU over the timed steps"}),
             "e2e": {"value": ips_e2e, "unit": "images/s", "h2d_bytes_per_step": img_h.numel() * 4 + lab_h.numel() * 8,
                     "d2h_bytes_per_step": 4, "last_loss": last},
             "gpu_launches": launches,

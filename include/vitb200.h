@@ -258,6 +258,10 @@ int vitb_token_mean_bwd(const float* dg, int dtype, int B, int N, int C, int res
  * torch.isin + blend (res-vit/model.py:469-472,487,524) and approximator row selection (:349-368). */
 int vitb_select_rows(const void* a, const void* b, const float* index, uint32_t member_mask, int rows, int cols,
                      int dtype, void* out, void* stream);
+/* Same; additionally *any_member = 1 (int32, device, never cleared here) when at least one row was a member: whether an
+ * approximator's key occurred in the batch, i.e. whether the reference's module ran at all (res-vit/model.py:363-367). */
+int vitb_select_rows_flag(const void* a, const void* b, const float* index, uint32_t member_mask, int rows, int cols,
+                          int dtype, void* out, int32_t* any_member, void* stream);
 
 /* Device-side row compaction for Res-ViT's inference-time token skipping (res-vit/model.py:503-524): nothing
  * about the selection travels to the host.  index [T] fp32 packed router indices (as vitb_select_rows):
@@ -329,6 +333,16 @@ int vitb_sgd_momentum(float* p, const float* g, float* m, int64_t n, float lr, c
 int vitb_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, const float* hyper_dev, float beta1,
                float beta2, float eps, float weight_decay, int step, const int* step_dev,
                const float* grad_scale_dev, void* shadow_hi, void* shadow_lo, void* stream);
+/* The same update when single parameters of the flat buffer may have to be left alone: torch.optim.AdamW skips a parameter
+ * whose .grad is None — no weight decay, no moment decay, and its own step count (the bias corrections) does not advance.
+ * In Res-ViT that is a BlockPathApproximators member whose key did not occur in the batch (res-vit/model.py:349-368,
+ * res-vit/train.py:272-277).  seg_end[nseg]: ascending end offsets of the parameters in the flat buffer; seg_flag[nseg]:
+ * index into flags[] (int32, device; non-zero = received a gradient this step) or -1 = always updated; seg_step[nseg]: the
+ * parameters' own step counts (fp32, device), advanced here for the live ones before the update.  hyper_dev = {lr, beta1,
+ * beta2, weight_decay} on the device. */
+int vitb_adamw_segments(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper_dev, float eps,
+                        const float* grad_scale_dev, void* shadow_hi, void* shadow_lo, const int64_t* seg_end,
+                        const int32_t* seg_flag, const int32_t* flags, float* seg_step, int nseg, void* stream);
 int vitb_sumsq(const float* x, int64_t n, float* out, void* stream);
 int vitb_clip_coef(const float* sumsq, float max_norm, float* coef, float* norm_out, void* stream);
 

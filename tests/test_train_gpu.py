@@ -294,3 +294,93 @@ def test_fused_last_block_and_direct_bias_sums_match_the_composed_path(width, he
         assert rel_l2(lo, lo_ref) < 5e-3, (aux, rel_l2(lo, lo_ref))
         for k in g_ref:
             assert grad_close(gr[k], g_ref[k], 2e-2, atol=1e-6), (aux, k, rel_l2(gr[k], g_ref[k]))
+
+
+def test_fused_adamw_skips_parameters_without_a_gradient_like_torch():
+    """torch.optim.AdamW leaves a parameter whose .grad is None alone: no weight decay, no moment decay, and ITS step
+    count (the bias corrections) stands still.  FusedAdamW.register_skippable + the device flag reproduce that on the
+    flat buffers: three steps, the middle one without a gradient for parameter B."""
+    import vitb200
+    g = torch.Generator().manual_seed(4)
+    shapes = [(7, 130), (64, 33), (5,)]
+    init = [torch.randn(s, generator=g) for s in shapes]
+    grads = [[torch.randn(s, generator=g) * 0.1 for s in shapes] for _ in range(3)]
+    ref_p = [t.clone().requires_grad_(True) for t in init]
+    ref = torch.optim.AdamW(ref_p, lr=3e-3, betas=(0.9, 0.95), weight_decay=0.1)
+    ps = [torch.nn.Parameter(t.clone().cuda()) for t in init]
+    opt = vitb200.optim.FusedAdamW(ps, lr=3e-3, betas=(0.9, 0.95), weight_decay=0.1)
+    flag = opt.register_skippable([ps[1]])
+    for it in range(3):
+        live_b = it != 1
+        for p, gr, j in zip(ref_p, grads[it], range(3)):
+            p.grad = None if (j == 1 and not live_b) else gr.clone()
+        ref.step()
+        opt.zero_grad()
+        assert int(flag) == 0
+        for p, gr, j in zip(ps, grads[it], range(3)):
+            if j == 1 and not live_b:
+                continue                      # the flat gradient stays zero, the flag stays 0
+            p.grad.copy_(gr.cuda())
+        if live_b:
+            flag.fill_(1)
+        opt.step()
+        torch.cuda.synchronize()
+        for p, r in zip(ps, ref_p):
+            assert rel_l2(p.detach().cpu(), r.detach()) < 1e-6, it
+    sd = opt.state_dict()["state"]
+    assert float(sd[0]["step"]) == 3 and float(sd[1]["step"]) == 2 and float(sd[2]["step"]) == 3
+    assert rel_l2(sd[1]["exp_avg"].cpu(), ref.state[ref_p[1]]["exp_avg"]) < 1e-6
+
+
+def test_resvit_approximators_that_saw_no_token_are_left_alone_by_adamw():
+    """res-vit/model.py:363-367 runs an approximator only for keys that occur in the batch, so the others have no gradient
+    and torch's AdamW (res-vit/train.py:272-277) does not touch them.  With resvit.bind_optimizer the selection kernel
+    reports which approximators saw a token and FusedAdamW skips the rest.  block_size 2 (keys 0, 1, 2), two steps: in the
+    first only keys 0 and 3 occur, in the second keys 0 and 2; the reference loop is restated in plain torch."""
+    import vitb200
+    from vitb200 import resvit
+    dim, rank, T = 128, 32, 96
+    g = torch.Generator().manual_seed(8)
+    mod = resvit.BlockPathApproximators(dim, rank, 2)
+    for p in mod.parameters():
+        p.data = torch.randn(p.shape, generator=g) * 0.05
+    init = {k: v.detach().clone() for k, v in mod.named_parameters()}
+    mod = mod.cuda().train()
+    ref_p = {k: v.clone().requires_grad_(True) for k, v in init.items()}
+    ref_opt = torch.optim.AdamW(list(ref_p.values()), lr=1e-2, weight_decay=0.1)
+    opt = vitb200.optim.FusedAdamW(list(mod.parameters()), lr=1e-2, weight_decay=0.1)
+    assert resvit.bind_optimizer(mod, opt) == 3
+    named = dict(mod.named_parameters())
+    xs = [torch.randn(2, T // 2, dim, generator=g) for _ in range(2)]
+    idxs = [torch.tensor([0, 3] * (T // 2)).float().view(2, T // 2, 1), torch.tensor([2, 0, 0] * (T // 3)).float().view(2, T // 2, 1)]
+    for step, (x, idx) in enumerate(zip(xs, idxs)):
+        # reference semantics (res-vit/model.py:349-368) in plain torch, fp32
+        for p in ref_p.values():
+            p.grad = None
+        out = x.clone()
+        for key in (0, 1, 2):
+            sub = idx.squeeze(-1) == key
+            if sub.any():
+                dw, uw = ref_p["approximators.%d.down_proj.weight" % key], ref_p["approximators.%d.up_proj.weight" % key]
+                out = out.clone()
+                out[sub] = out[sub] @ dw.t() @ uw.t() + out[sub]
+        out.pow(2).mean().backward()
+        ref_opt.step()
+        with vitb200.precision("fp32"):
+            opt.zero_grad()
+            y = mod(x.cuda(), idx.cuda(), [0, 1, 2])
+            y.float().pow(2).mean().backward()
+            opt.step()
+        torch.cuda.synchronize()
+        absent = [k for k in (0, 1, 2) if not bool((idx == k).any())]
+        assert absent, step
+        for k, p in named.items():
+            key = int(k.split(".")[1])
+            if step == 0 and key in absent:
+                assert torch.equal(p.detach().cpu(), init[k]), (step, k)       # never touched: bit-identical
+            delta_ref = ref_p[k].detach() - init[k]
+            delta = p.detach().cpu() - init[k]
+            assert grad_close(delta, delta_ref, 5e-3, atol=1e-6), (step, k, rel_l2(delta, delta_ref))
+    steps = {k: float(v["step"]) for k, v in zip(named, opt.state_dict()["state"].values())}
+    assert steps["approximators.0.down_proj.weight"] == 2 and steps["approximators.1.down_proj.weight"] == 0 \
+        and steps["approximators.2.up_proj.weight"] == 1, steps

@@ -7,6 +7,9 @@ import sys
 import torch
 import torch.distributed as dist
 
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bench import nvlink_bytes  # noqa: E402
+
 local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
@@ -19,11 +22,13 @@ for name, n in (("ViT-B/16", 85_875_556), ("ViT-L/16", 303_400_000), ("Res-ViT t
     torch.cuda.synchronize()
     dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nv0 = nvlink_bytes(local) if rank == 0 else None
     e0.record()
     for _ in range(20):
         dist.all_reduce(buf, op=dist.ReduceOp.AVG)
     e1.record()
     torch.cuda.synchronize()
+    nv1 = nvlink_bytes(local) if nv0 is not None else None
     ms = torch.tensor([e0.elapsed_time(e1) / 20], device=dev, dtype=torch.float64)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     if rank == 0:
@@ -31,6 +36,11 @@ for name, n in (("ViT-B/16", 85_875_556), ("ViT-L/16", 303_400_000), ("Res-ViT t
         gb = n * 4 / 1e9
         print("all-reduce %s: %.1f MB fp32 on %d GPUs: %.3f ms, algbw %.0f GB/s, busbw %.0f GB/s"
               % (name, gb * 1e3, world, t * 1e3, gb / t, gb / t * 2 * (world - 1) / world), flush=True)
+        if nv1 is not None:
+            print("    NVLink counters of rank 0 per all-reduce: tx %.1f MB, rx %.1f MB (NVML NVLINK_THROUGHPUT_DATA)"
+                  % ((nv1[0] - nv0[0]) / 20 / 1e6, (nv1[1] - nv0[1]) / 20 / 1e6), flush=True)
+        else:
+            print("    NVLink counters: not available through NVML on this box", flush=True)
     del buf
 dist.barrier()
 torch.cuda.synchronize()

@@ -410,6 +410,71 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
   }
 }
 
+// The same update over a flat buffer whose parameters (segments) can be SKIPPED individually: torch.optim.AdamW leaves a
+// parameter whose .grad is None untouched — no weight decay, no moment decay, its own step count does not advance
+// (res-vit/train.py:272-277 with BlockPathApproximators, res-vit/model.py:349-368: an approximator whose key did not occur
+// in the batch never ran).  seg_end[s] = end offset of segment s (ascending); seg_flag[s] = index into flags[] (int32,
+// non-zero = the parameter received a gradient this step) or -1 = always live; seg_step[s] = that parameter's own step
+// count (already advanced for this step by adamw_advance_kernel).  A block walks a contiguous chunk, so a thread finds its
+// segment once (binary search) and then only moves a cursor.
+__global__ void __launch_bounds__(kThreads)
+adamw_seg_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                 long long n, const float* __restrict__ hyper_dev, float eps, const float* __restrict__ grad_scale_dev,
+                 __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, const long long* __restrict__ seg_end,
+                 const int* __restrict__ seg_flag, const int* __restrict__ flags, const float* __restrict__ seg_step,
+                 int nseg) {
+  const float lr = hyper_dev[0], b1 = hyper_dev[1], b2 = hyper_dev[2], wd = hyper_dev[3];
+  const float gs = grad_scale_dev ? *grad_scale_dev : 1.f;
+  const long long per_block = ((n + gridDim.x - 1) / gridDim.x + blockDim.x - 1) / blockDim.x * blockDim.x;
+  const long long c0 = static_cast<long long>(blockIdx.x) * per_block;
+  const long long c1 = c0 + per_block < n ? c0 + per_block : n;
+  long long i = c0 + threadIdx.x;
+  if (i >= c1) return;
+  int lo_s = 0, hi_s = nseg - 1;
+  while (lo_s < hi_s) {                       // first segment that ends behind i
+    const int mid = (lo_s + hi_s) >> 1;
+    if (seg_end[mid] > i) hi_s = mid; else lo_s = mid + 1;
+  }
+  int seg = lo_s;
+  long long end = seg_end[seg];
+  bool live = false;
+  float bc1 = 1.f, bc2s = 1.f;
+  auto load_seg = [&]() {
+    const int f = seg_flag[seg];
+    live = f < 0 || flags[f] != 0;
+    const float stepf = seg_step[seg];
+    bc1 = 1.f - powf(b1, stepf);
+    bc2s = sqrtf(1.f - powf(b2, stepf));
+  };
+  load_seg();
+  for (; i < c1; i += blockDim.x) {
+    while (i >= end && seg < nseg - 1) { ++seg; end = seg_end[seg]; load_seg(); }
+    if (!live) continue;
+    float pv = p[i];
+    const float gv = g[i] * gs;
+    pv *= (1.f - lr * wd);
+    const float mv = b1 * m[i] + (1.f - b1) * gv;
+    const float vv = b2 * v[i] + (1.f - b2) * gv * gv;
+    m[i] = mv;
+    v[i] = vv;
+    const float denom = sqrtf(vv) / bc2s + eps;
+    pv -= (lr / bc1) * (mv / denom);
+    p[i] = pv;
+    if (hi) hi[i] = __float2bfloat16(pv);
+    if (lo) lo[i] = __float2bfloat16(pv - bf16_round(pv));
+  }
+}
+
+// seg_step[s] += 1 for every segment that is live this step
+__global__ void adamw_advance_kernel(const int* __restrict__ seg_flag, const int* __restrict__ flags,
+                                     float* __restrict__ seg_step, int nseg) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < nseg) {
+    const int f = seg_flag[s];
+    if (f < 0 || flags[f] != 0) seg_step[s] += 1.f;
+  }
+}
+
 // out[0] += sum x^2   (for clip_grad_norm_)
 __global__ void __launch_bounds__(kThreads)
 sumsq_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
@@ -745,6 +810,24 @@ int vitb_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr
       p, g, m, v, n, lr, hyper_dev, beta1, beta2, eps, weight_decay, step, step_dev, grad_scale_dev,
       reinterpret_cast<__nv_bfloat16*>(shadow_hi), reinterpret_cast<__nv_bfloat16*>(shadow_lo));
   VITB_LAUNCH_CHECK("adamw_kernel");
+  return VITB_OK;
+}
+
+int vitb_adamw_segments(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper_dev, float eps,
+                        const float* grad_scale_dev, void* shadow_hi, void* shadow_lo, const int64_t* seg_end,
+                        const int32_t* seg_flag, const int32_t* flags, float* seg_step, int nseg, void* stream_) {
+  int st = vitb_check_device();
+  if (st != VITB_OK) return st;
+  if (n == 0) return VITB_OK;
+  VITB_REQUIRE(p && g && m && v && n > 0 && hyper_dev && seg_end && seg_flag && seg_step && nseg >= 1, VITB_ERR_BAD_ARG,
+               "adamw_segments: bad args");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  adamw_advance_kernel<<<(nseg + 255) / 256, 256, 0, stream>>>(seg_flag, flags, seg_step, nseg);
+  VITB_LAUNCH_CHECK("adamw_advance_kernel");
+  adamw_seg_kernel<<<grid_for(n), kThreads, 0, stream>>>(
+      p, g, m, v, n, hyper_dev, eps, grad_scale_dev, reinterpret_cast<__nv_bfloat16*>(shadow_hi),
+      reinterpret_cast<__nv_bfloat16*>(shadow_lo), reinterpret_cast<const long long*>(seg_end), seg_flag, flags, seg_step, nseg);
+  VITB_LAUNCH_CHECK("adamw_seg_kernel");
   return VITB_OK;
 }
 

@@ -136,7 +136,7 @@ token_mean_bwd_kernel(const float* __restrict__ dg, int Bsz, int N, int Cc, int 
 template <bool BF16>
 __global__ void __launch_bounds__(kThreads)
 select_rows_kernel(const void* __restrict__ a_, const void* __restrict__ b_, const float* __restrict__ index,
-                   unsigned mask, int rows, int cols, void* __restrict__ out_) {
+                   unsigned mask, int rows, int cols, void* __restrict__ out_, int* __restrict__ any_member) {
   constexpr int V = BF16 ? 8 : 4;  // elements per 16-byte vector
   const int cv = cols / V;
   const long long total = static_cast<long long>(rows) * cv;
@@ -145,6 +145,7 @@ select_rows_kernel(const void* __restrict__ a_, const void* __restrict__ b_, con
     const int t = static_cast<int>(i / cv);
     const int idx = static_cast<int>(index[t]);
     const bool sel = (idx >= 0 && idx < 32) ? ((mask >> idx) & 1u) : false;
+    if (any_member != nullptr && sel && i % cv == 0) *any_member = 1;   // benign race: every writer stores 1
     const void* src = sel ? a_ : b_;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
     if (src) v = reinterpret_cast<const uint4*>(src)[i];
@@ -297,8 +298,8 @@ int vitb_token_mean_bwd(const float* dg, int dtype, int B, int N, int C, int res
   return VITB_OK;
 }
 
-int vitb_select_rows(const void* a, const void* b, const float* index, uint32_t member_mask, int rows, int cols,
-                     int dtype, void* out, void* stream_) {
+int vitb_select_rows_flag(const void* a, const void* b, const float* index, uint32_t member_mask, int rows, int cols,
+                          int dtype, void* out, int32_t* any_member, void* stream_) {
   int st = vitb_check_device();
   if (st != VITB_OK) return st;
   if (rows == 0 || cols == 0) return VITB_OK;
@@ -307,10 +308,15 @@ int vitb_select_rows(const void* a, const void* b, const float* index, uint32_t 
   VITB_REQUIRE(cols % V == 0, VITB_ERR_UNSUPPORTED_SHAPE, "select_rows: cols %d must be a multiple of %d", cols, V);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
   const long long total = static_cast<long long>(rows) * (cols / V);
-  if (dtype == VITB_BF16) select_rows_kernel<true><<<grid_for(total), kThreads, 0, s>>>(a, b, index, member_mask, rows, cols, out);
-  else select_rows_kernel<false><<<grid_for(total), kThreads, 0, s>>>(a, b, index, member_mask, rows, cols, out);
+  if (dtype == VITB_BF16) select_rows_kernel<true><<<grid_for(total), kThreads, 0, s>>>(a, b, index, member_mask, rows, cols, out, any_member);
+  else select_rows_kernel<false><<<grid_for(total), kThreads, 0, s>>>(a, b, index, member_mask, rows, cols, out, any_member);
   VITB_LAUNCH_CHECK("select_rows_kernel");
   return VITB_OK;
+}
+
+int vitb_select_rows(const void* a, const void* b, const float* index, uint32_t member_mask, int rows, int cols,
+                     int dtype, void* out, void* stream_) {
+  return vitb_select_rows_flag(a, b, index, member_mask, rows, cols, dtype, out, nullptr, stream_);
 }
 
 int vitb_distill_loss(const void* student, int64_t s_row_stride, const void* teacher, int64_t t_row_stride, int dtype, int rows,

@@ -1336,7 +1336,7 @@ def token_mean(x, reserve_initials):
 
 class _SelectRows(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, a, b, index, member_mask):
+    def forward(ctx, a, b, index, member_mask, any_flag=None):
         ref = a if a is not None else b
         L.require_cuda(ref, index)
         cols = ref.shape[-1]
@@ -1345,7 +1345,7 @@ class _SelectRows(torch.autograd.Function):
         b2 = b.reshape(-1, cols).contiguous() if b is not None else None
         if a2 is not None and b2 is not None and a2.dtype != b2.dtype:
             a2, b2 = a2.float(), b2.float()
-        out = ops.select_rows(a2, b2, idx, member_mask)
+        out = ops.select_rows(a2, b2, idx, member_mask, any_flag)
         ctx.save_for_backward(idx)
         ctx.cfg = (member_mask, a.shape if a is not None else None, b.shape if b is not None else None,
                    a.dtype if a is not None else None, b.dtype if b is not None else None)
@@ -1361,16 +1361,17 @@ class _SelectRows(torch.autograd.Function):
             da = ops.select_rows(g2, None, idx, mask).view(ash).to(adt)
         if bsh is not None and ctx.needs_input_grad[1]:
             db = ops.select_rows(None, g2, idx, mask).view(bsh).to(bdt)
-        return da, db, None, None
+        return da, db, None, None, None
 
 
-def select_rows(a, b, index, member_ids):
+def select_rows(a, b, index, member_ids, any_flag=None):
     """out[t] = a[t] if int(index[t]) in member_ids else b[t]; a or b may be None (zeros).  index: [..., 1]
-    fp32 packed router indices; member_ids: iterable of ints < 32 (torch.isin + blend, res-vit/model.py:469-487)."""
+    fp32 packed router indices; member_ids: iterable of ints < 32 (torch.isin + blend, res-vit/model.py:469-487).
+    any_flag: optional int32 CUDA scalar that the kernel sets to 1 when some row is a member."""
     mask = 0
     for i in member_ids:
         mask |= 1 << int(i)
-    return _SelectRows.apply(a, b, index, mask)
+    return _SelectRows.apply(a, b, index, mask, any_flag)
 
 
 # --------------------------------------------------------------------------------------------------

@@ -525,6 +525,24 @@ def adamw(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, *, grad_scale=N
                           L.ptr(shadow_hi), L.ptr(shadow_lo), L.stream_ptr(p.device)), "vitb_adamw")
 
 
+def adamw_segments(p, g, m, v, eps, hyper_dev, seg_end, seg_flag, flags, seg_step, *, grad_scale=None, shadow_hi=None,
+                   shadow_lo=None):
+    """AdamW over a flat buffer whose parameters can be skipped one by one (torch's `grad is None`): seg_end int64 [S]
+    ascending end offsets, seg_flag int32 [S] (index into `flags`, -1 = always live), flags int32 [F] (non-zero = got a
+    gradient this step), seg_step fp32 [S] per-parameter step counts (advanced here for the live ones)."""
+    L.require_cuda(p, g, m, v, seg_end, seg_flag, flags, seg_step)
+    _check_hyper(hyper_dev)
+    if hyper_dev is None:
+        raise L.VitbError("adamw_segments: hyper_dev is required")
+    if (seg_end.dtype != torch.int64 or seg_flag.dtype != torch.int32 or flags.dtype != torch.int32 or
+            seg_step.dtype != torch.float32 or seg_flag.numel() != seg_end.numel() or seg_step.numel() != seg_end.numel()):
+        raise L.VitbError("adamw_segments: seg_end int64 [S], seg_flag int32 [S], flags int32 [F], seg_step fp32 [S]")
+    L.check(L._vitb_adamw_segments(L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), p.numel(), L.ptr(hyper_dev), float(eps),
+                                   L.ptr(grad_scale), L.ptr(shadow_hi), L.ptr(shadow_lo), L.ptr(seg_end), L.ptr(seg_flag),
+                                   L.ptr(flags), L.ptr(seg_step), seg_end.numel(), L.stream_ptr(p.device)),
+            "vitb_adamw_segments")
+
+
 def sumsq(x, out):
     L.require_cuda(x, out)
     L.check(L._vitb_sumsq(L.ptr(x), x.numel(), L.ptr(out), L.stream_ptr(x.device)), "vitb_sumsq")
@@ -662,8 +680,9 @@ def token_mean_bwd(dg, B, N, reserve_initials, dtype):
     return dx
 
 
-def select_rows(a, b, index, member_mask):
-    """out[t,:] = member(index[t]) ? a[t,:] : b[t,:] on 2-D contiguous tensors; a or b may be None (zeros)."""
+def select_rows(a, b, index, member_mask, any_flag=None):
+    """out[t,:] = member(index[t]) ? a[t,:] : b[t,:] on 2-D contiguous tensors; a or b may be None (zeros).  any_flag
+    (int32 CUDA scalar, optional) is set to 1 when at least one row is a member (never cleared here)."""
     ref = a if a is not None else b
     L.require_cuda(ref, index)
     if not ref.is_contiguous() or (a is not None and b is not None and (a.shape != b.shape or a.dtype != b.dtype or not b.is_contiguous())):
@@ -671,6 +690,9 @@ def select_rows(a, b, index, member_mask):
     rows = index.numel()
     cols = ref.numel() // rows
     out = torch.empty_like(ref)
-    L.check(L._vitb_select_rows(L.ptr(a), L.ptr(b), L.ptr(index), int(member_mask) & 0xFFFFFFFF, rows, cols,
-                                L.dtype_code(ref), L.ptr(out), L.stream_ptr(ref.device)), "vitb_select_rows")
+    if any_flag is not None and (any_flag.dtype != torch.int32 or any_flag.numel() != 1 or not any_flag.is_cuda):
+        raise L.VitbError("select_rows: any_flag must be an int32 CUDA scalar")
+    L.check(L._vitb_select_rows_flag(L.ptr(a), L.ptr(b), L.ptr(index), int(member_mask) & 0xFFFFFFFF, rows, cols,
+                                     L.dtype_code(ref), L.ptr(out), L.ptr(any_flag), L.stream_ptr(ref.device)),
+            "vitb_select_rows")
     return out

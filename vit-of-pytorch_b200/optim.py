@@ -227,15 +227,82 @@ class FusedAdamW(_FusedBase):
         self._steps = 0
         # device-resident step counter: step() can be captured in a CUDA graph
         self._step_dev = torch.zeros((), dtype=torch.int32, device=dev)
+        self._seg = None            # per-parameter segment tables, built by the first register_skippable()
 
     def _hyper(self, g):
         return [float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["weight_decay"])]
+
+    # ---- parameters that may go without a gradient (torch.optim.AdamW skips `p.grad is None`: no weight decay, no moment
+    # decay, the parameter's own step count stands still).  With flat buffers "no gradient" has to be said explicitly:
+    # register_skippable(params) returns an int32 device flag; whoever computes those parameters' gradients sets it
+    # non-zero during the step (Res-ViT: BlockPathApproximators, through vitb_select_rows_flag, when the approximator's
+    # key occurred in the batch); zero_grad() clears it.  Unregistered parameters are always updated.
+    def register_skippable(self, params):
+        params = list(params)
+        if self._seg is None:
+            self._build_segments()
+        k = self._n_flags
+        if k >= self._flags.numel():
+            raise RuntimeError("FusedAdamW: more than %d skippable parameter sets" % self._flags.numel())
+        self._n_flags += 1
+        for p in params:
+            loc = self._seg_of.get(id(p))
+            if loc is None:
+                raise ValueError("register_skippable: parameter is not managed by this optimizer")
+            gi, j = loc
+            self._seg[gi][1][j] = k         # seg_flag (device int32): a tiny element write
+        return self._flags[k:k + 1]
+
+    def _build_segments(self):
+        dev = self._flat[0].flat_p.device
+        self._flags = torch.zeros(256, dtype=torch.int32, device=dev)
+        self._n_flags = 0
+        self._seg, self._seg_of = [], {}
+        for gi, fg in enumerate(self._flat):
+            ends = fg.offsets[1:] + [fg.total]
+            seg_end = torch.tensor(ends, dtype=torch.int64, device=dev)
+            seg_flag = torch.full((len(ends),), -1, dtype=torch.int32, device=dev)
+            seg_step = torch.full((len(ends),), float(self._steps), dtype=torch.float32, device=dev)
+            self._seg.append((seg_end, seg_flag, seg_step))
+            for j, p in enumerate(fg.params):
+                self._seg_of[id(p)] = (gi, j)
+
+    def zero_grad(self, set_to_none=False):
+        super().zero_grad(set_to_none)
+        if self._seg is not None:
+            self._flags.zero_()
 
     def _state_buffers(self):
         return {"exp_avg": self._m, "exp_avg_sq": self._v}
 
     def _extra_state(self):
         return {"step": torch.tensor(float(self._step_dev.item()))}
+
+    def state_dict(self):
+        sd = super().state_dict()
+        if self._seg is not None:       # per-parameter step counts, as torch.optim.AdamW keeps them
+            idx = 0
+            for gi, fg in enumerate(self._flat):
+                steps = self._seg[gi][2].tolist()
+                order = {id(p): i for i, p in enumerate(fg.params)}
+                for p in self.param_groups[gi]["params"]:
+                    j = order.get(id(p))
+                    if j is not None and idx in sd["state"]:
+                        sd["state"][idx]["step"] = torch.tensor(float(steps[j]))
+                    idx += 1
+        return sd
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        if self._seg is not None:
+            idx = 0
+            for gi, fg in enumerate(self._flat):
+                order = {id(p): i for i, p in enumerate(fg.params)}
+                for p in self.param_groups[gi]["params"]:
+                    j, entry = order.get(id(p)), state_dict["state"].get(idx)
+                    if j is not None and entry is not None and "step" in entry:
+                        self._seg[gi][2][j] = float(entry["step"])
+                    idx += 1
 
     def _load_extra_state(self, extra):
         step = int(float(extra.get("step", 0)))
@@ -259,9 +326,15 @@ class FusedAdamW(_FusedBase):
             ops.clip_coef(self._sumsq, self.max_grad_norm, self._coef, self.grad_norm)
             coef = self._coef
         want_lo = F.get_precision() == "fp32"
-        for fg, g, m, v, hyper in zip(self._flat, self.param_groups, self._m, self._v, self._hyper_dev):
+        for gi, (fg, g, m, v, hyper) in enumerate(zip(self._flat, self.param_groups, self._m, self._v, self._hyper_dev)):
             if want_lo:
                 fg.ensure_lo()
+            if self._seg is not None:
+                seg_end, seg_flag, seg_step = self._seg[gi]
+                ops.adamw_segments(fg.flat_p, fg.flat_g, m, v, g["eps"], hyper, seg_end, seg_flag, self._flags, seg_step,
+                                   grad_scale=coef, shadow_hi=fg.flat_hi, shadow_lo=fg.flat_lo)
+                fg.mark_fresh()
+                continue
             ops.adamw(fg.flat_p, fg.flat_g, m, v, g["lr"], g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"],
                       self._steps, grad_scale=coef, shadow_hi=fg.flat_hi, shadow_lo=fg.flat_lo, hyper_dev=hyper,
                       step_dev=self._step_dev)

@@ -278,6 +278,7 @@ class BlockPathApproximators(nn.Module):
             if key == total - 1:
                 continue
             self.approximators[str(key)] = LowRankApproximator(dim, rank)
+        self._live_flags = {}       # key -> int32 device flag "this approximator saw a token this step" (bind_optimizer)
 
     def forward(self, x, router_indices, LRA_mask):
         keys = LRA_mask.tolist() if torch.is_tensor(LRA_mask) else list(LRA_mask)
@@ -287,9 +288,27 @@ class BlockPathApproximators(nn.Module):
                 continue
             ap = self.approximators[ks]
             t = F.linear(x, ap.down_proj.weight)
-            t = F.select_rows(t, None, router_indices, [int(key)])
+            # the reference runs the approximator only `if sub_mask.any()` (res-vit/model.py:363-367): whether it ran —
+            # whether its parameters have a gradient at all — is recorded for the optimizer by the selection kernel
+            t = F.select_rows(t, None, router_indices, [int(key)], any_flag=self._live_flags.get(ks) if self.training else None)
             x = F.linear(t, ap.up_proj.weight, residual=x)
         return x
+
+
+def bind_optimizer(model, optimizer):
+    """Tell a FusedAdamW which parameters may go without a gradient in a step: the members of every
+    BlockPathApproximators, whose modules the reference only runs for keys that occur in the batch
+    (res-vit/model.py:363-367) — torch.optim.AdamW then skips them entirely (`p.grad is None`: no weight decay, no moment
+    decay, no step).  Without this call such parameters see a zero gradient and are decayed like the rest."""
+    n = 0
+    for m in model.modules():
+        if isinstance(m, BlockPathApproximators):
+            for ks, ap in m.approximators.items():
+                ps = [p for p in ap.parameters() if p.requires_grad]
+                if ps:
+                    m._live_flags[ks] = optimizer.register_skippable(ps)
+                    n += 1
+    return n
 
 
 def _compaction_enabled():
