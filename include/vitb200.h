@@ -195,6 +195,12 @@ int vitb_attn_bwd_simt(const vitb_attn_params* p, void* stream);
  * src/model.py:155,210), bf16, head_dim 64, <= 256 keys, 16-byte aligned rows.  The forward is vitb_attn_fwd_simt
  * (it picks the bandwidth-bound kernel for these shapes); this is the backward with BF16 gradients: dq [B,1,H*64],
  * dk / dv rows written whole through their strides (they may alias a packed [T, 2D] buffer), nothing to zero. */
+/* tcgen05 backward for ANY number of tokens (bf16, head_dim 64, Nq == Nk): 384 px inputs give 577 tokens
+ * (src/config.py:12).  Key blocks of 256 are spread over CTAs, each streams every query tile; dq_acc is an fp32
+ * [B, N, H*64] scratch buffer ZEROED BY THE CALLER that collects dQ (red.global.add) before it is written to p->dq as bf16.
+ * Gradients are bf16 as in vitb_attn_bwd_tc. */
+int vitb_attn_bwd_long_supported(int head_dim, int Nq, int Nk);
+int vitb_attn_bwd_tc_long(const vitb_attn_params* p, float* dq_acc, void* stream);
 int vitb_attn_q1_supported(int head_dim, int Nk);
 int vitb_attn_q1_bwd(const vitb_attn_params* p, void* stream);
 

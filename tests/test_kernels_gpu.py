@@ -173,8 +173,8 @@ def test_attn_ws_persistent_kernels(N, B, H, monkeypatch):
 def test_attn_tc_general_shapes_forward(dh, N, H, simt):
     """tcgen05 forward for 64 <= head_dim <= 128 and any token count: ViT-H/14 at 224 px (head_dim 80, 257 tokens:
     two MMAs per S row block, a partially used second head-dim chunk) and the 384 px evaluation resolution
-    (577 tokens for */16, 730 for h14: several key blocks, online softmax).  The backward of these shapes stays on
-    the SIMT kernel."""
+    (577 tokens for */16, 730 for h14: several key blocks, online softmax).  The backward of these shapes runs on
+    vitb_attn_bwd_tc_long (next test); here the CUDA-core backward is checked against the same forward."""
     import vitb200
     B = 2
     D = H * dh
@@ -196,8 +196,51 @@ def test_attn_tc_general_shapes_forward(dh, N, H, simt):
     do = _randn((B, N, D), 7, 1.0, torch.bfloat16)
     qf, kf, vf = (t.float().detach().requires_grad_(True) for t in (q, k, v))
     _attn_ref(qf, kf, vf, H)[0].backward(do.float())
-    dq, dk, dv = vitb200.ops.attn_bwd(do, q, k, v, o, lse, H)
+    dq, dk, dv = vitb200.ops.attn_bwd(do, q, k, v, o, lse, H, use_tc=False)
     assert rel_l2(dq, qf.grad) < 4e-2 and rel_l2(dk, kf.grad) < 4e-2 and rel_l2(dv, vf.grad) < 4e-2
+
+
+@pytest.mark.parametrize("dh,N,B,H", [(64, 577, 2, 12), (64, 257, 3, 2), (64, 300, 2, 3), (64, 730, 1, 2), (64, 512, 2, 1),
+                                      (64, 197, 2, 2), (64, 40, 2, 1),
+                                      (80, 257, 2, 16), (80, 730, 1, 2), (80, 50, 2, 3), (96, 300, 2, 2), (112, 256, 1, 2),
+                                      (128, 130, 2, 3)])
+def test_attn_tc_backward_any_token_count(dh, N, B, H):
+    """tcgen05 backward for ANY number of tokens (vitb_attn_bwd_tc_long).  head_dim 64: 577 tokens is the 384 px
+    resolution of */16 (src/config.py:12); key blocks of 256 run on separate CTAs and add their shares of dQ into an fp32
+    buffer; 257 and 300 leave a nearly empty second block, 512 two full ones, 197 and 40 a single block.  64 < head_dim
+    <= 128: ViT-H/14 (head_dim 80, 257 tokens at 224 px, 730 at 384 px; src/config.py:95-104) — the head dimension spans
+    two column chunks, key blocks of 128.  Compared with the fp32 reference at the bf16 attention bar (P and dS are
+    rounded to bf16 before the second MMAs), packed q|k|v and packed gradient buffer as the model uses them."""
+    import vitb200
+    from vitb200 import _lib as L
+    import ctypes as C
+    D = H * dh
+    qkv = _randn((B, N, 3 * D), 900 + N, 1.0, torch.bfloat16)
+    q, k, v = qkv[:, :, :D], qkv[:, :, D:2 * D], qkv[:, :, 2 * D:]
+    o, lse = vitb200.ops.attn_fwd(q, k, v, H)
+    do = _randn((B, N, D), 11, 1.0, torch.bfloat16)
+    qf, kf, vf = (t.float().detach().requires_grad_(True) for t in (q, k, v))
+    _attn_ref(qf, kf, vf, H)[0].backward(do.float())
+    assert vitb200.ops.attn_bwd_supported_any(dh, N, N, torch.bfloat16)
+    dqkv = torch.full((B, N, 3 * D), float("nan"), dtype=torch.bfloat16, device="cuda")
+    dq, dk, dv = dqkv[:, :, :D], dqkv[:, :, D:2 * D], dqkv[:, :, 2 * D:]
+    # straight through the C ABI, so that <= 256 tokens take the key-block kernel too
+    p = vitb200.ops._attn_params(q, k, v, o, lse, H)
+    p.dout = do.data_ptr()
+    p.do_batch_stride, p.do_row_stride = do.stride(0), do.stride(1)
+    p.dq, p.dk, p.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
+    p.dq_batch_stride = p.dk_batch_stride = p.dv_batch_stride = dqkv.stride(0)
+    p.dq_row_stride = p.dk_row_stride = p.dv_row_stride = dqkv.stride(1)
+    acc = torch.zeros((B, N, D), dtype=torch.float32, device="cuda")
+    L.check(L._vitb_attn_bwd_tc_long(C.byref(p), L.ptr(acc), L.stream_ptr(q.device)), "vitb_attn_bwd_tc_long")
+    torch.cuda.synchronize()
+    assert not torch.isnan(dqkv.float()).any()
+    assert rel_l2(dq, qf.grad) < 4e-2 and rel_l2(dk, kf.grad) < 4e-2 and rel_l2(dv, vf.grad) < 4e-2, \
+        (rel_l2(dq, qf.grad), rel_l2(dk, kf.grad), rel_l2(dv, vf.grad))
+    if N > 256 or dh != 64:     # and through ops.attn_bwd, which picks this kernel for these shapes
+        dq2, dk2, dv2 = vitb200.ops.attn_bwd(do, q, k, v, o, lse, H)
+        assert dq2.dtype == torch.bfloat16
+        assert rel_l2(dq2, qf.grad) < 4e-2 and rel_l2(dk2, kf.grad) < 4e-2 and rel_l2(dv2, vf.grad) < 4e-2
 
 
 def test_attn_tc_c2_size_runs_and_matches_on_a_slice():

@@ -177,6 +177,8 @@ _vitb_attn_fwd_ws = _sig("vitb_attn_fwd_ws", [C.POINTER(AttnParams), _vp])      
 _vitb_attn_bwd_ws = _sig("vitb_attn_bwd_ws", [C.POINTER(AttnParams), _vp])
 _vitb_attn_fwd_simt = _sig("vitb_attn_fwd_simt", [C.POINTER(AttnParams), _vp])
 _vitb_attn_bwd_simt = _sig("vitb_attn_bwd_simt", [C.POINTER(AttnParams), _vp])
+vitb_attn_bwd_long_supported = _sig("vitb_attn_bwd_long_supported", [_i, _i, _i])
+_vitb_attn_bwd_tc_long = _sig("vitb_attn_bwd_tc_long", [C.POINTER(AttnParams), _vp, _vp])   # any token count, head_dim 64
 vitb_attn_q1_supported = _sig("vitb_attn_q1_supported", [_i, _i])
 _vitb_attn_q1_bwd = _sig("vitb_attn_q1_bwd", [C.POINTER(AttnParams), _vp])           # bf16 gradients, single query
 _vitb_cast_split = _sig("vitb_cast_split", [_vp, _i64, _vp, _vp, _vp])
@@ -219,5 +221,5 @@ EXPORTED_SYMBOLS = [
     "vitb_resize_tables_host", "vitb_image_prep",
     "vitb_distill_loss", "vitb_active_loss", "vitb_compact_rows", "vitb_gather_rows", "vitb_scatter_rows", "vitb_attn_ws_supported", "vitb_attn_fwd_ws", "vitb_attn_bwd_ws",
     "vitb_layernorm_bwd_sparse_res", "vitb_attn_q1_supported", "vitb_attn_q1_bwd", "vitb_dropout_fwd", "vitb_dropout_bwd",
-    "vitb_adamw_segments", "vitb_select_rows_flag",
+    "vitb_adamw_segments", "vitb_select_rows_flag", "vitb_attn_bwd_long_supported", "vitb_attn_bwd_tc_long",
 ]

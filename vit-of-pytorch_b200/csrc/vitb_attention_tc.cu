@@ -36,6 +36,8 @@ struct AttnTc {
   float scale;       // 1/sqrt(dh)
   float scale_log2;  // scale * log2(e)
   float* lse;  // [B,H,N]   (q, k, v, o, dO and the gradients move through tensor maps)
+  // attn_bwd_tc<true> (more than 256 tokens): dQ of a key block is ADDED into this fp32 [B, N, H*64] buffer
+  float* dq_acc;
 };
 
 // ================================================================================================
@@ -426,6 +428,13 @@ attn_fwd_tc_gen(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 //   * TMEM reads are issued two chunks per wait; the dK / dV drain keeps independent register blocks
 // ================================================================================================
 
+// LONG = true: any number of tokens.  blockIdx.z picks a block of up to 256 keys; the CTA keeps that block's K, V, dK, dV
+// and streams ALL query tiles past it through two Q / dO / O buffers (the tile after next is requested as soon as a tile
+// retires).  dQ of a query tile is the sum over the key blocks, i.e. over CTAs: each adds its part into an fp32 buffer
+// (red.global.add), which vitb_attn_bwd_tc_long converts to bf16 afterwards.  D_i is recomputed per key block from the
+// O / dO tiles (cheaper than a pre-pass).  With one key block (<= 256 tokens) nothing changes: LONG = false is the
+// kernel the persistent attn_bwd_ws superseded for the headline shape.
+template <bool LONG>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
              const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
@@ -434,17 +443,19 @@ attn_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
              const __grid_constant__ AttnTc a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  const int NK = a.NK;
-  const int kv_bytes = NK * 128;
+  const int kb0 = LONG ? static_cast<int>(blockIdx.z) * 256 : 0;                 // first key of this CTA's block
+  const int NK = LONG ? min(256, (a.N - kb0 + 15) & ~15) : a.NK;                  // keys of the block, padded to 16
+  const int kv_bytes = a.NK * 128;                                                // a.NK = rows of the K / V TMA box, always written whole
   const int mtiles = (NK + 127) >> 7;        // 128-key M tiles of dK / dV
   const int nchunks = mtiles * 2;            // the P / dS image always holds whole M tiles
-  const int qtiles = (a.N + 127) >> 7;       // <= 2 (N <= 256)
+  const int qtiles = (a.N + 127) >> 7;       // <= 2 unless LONG
+  const int nbuf = LONG ? 2 : qtiles;        // Q / dO / O tile buffers
   uint8_t* sK = smem;
   uint8_t* sV = sK + kv_bytes;
-  uint8_t* sQ = sV + kv_bytes;               // [qtiles] tiles of 128 x 64 bf16
-  uint8_t* sDO = sQ + qtiles * kChunkBytes;
-  uint8_t* sO = sDO + qtiles * kChunkBytes;
-  uint8_t* sP = sO + qtiles * kChunkBytes;   // P, then dS in place
+  uint8_t* sQ = sV + kv_bytes;               // [nbuf] tiles of 128 x 64 bf16
+  uint8_t* sDO = sQ + nbuf * kChunkBytes;
+  uint8_t* sO = sDO + nbuf * kChunkBytes;
+  uint8_t* sP = sO + nbuf * kChunkBytes;   // P, then dS in place
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + nchunks * kChunkBytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
   float* red = reinterpret_cast<float*>(bars + 16);   // [2 halves][128 rows] partial D_i
@@ -474,8 +485,8 @@ attn_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     mbar_arrive_expect_tx(bar_q, 3 * kChunkBytes);
     tma_load_3d(&tmQ, bar_q, sQ_u, h * DH, 0, b);
     mbar_arrive_expect_tx(bar_kv, 2 * kv_bytes);
-    tma_load_3d(&tmK, bar_kv, sK_u, h * DH, 0, b);
-    tma_load_3d(&tmV, bar_kv, sV_u, h * DH, 0, b);
+    tma_load_3d(&tmK, bar_kv, sK_u, h * DH, kb0, b);
+    tma_load_3d(&tmV, bar_kv, sV_u, h * DH, kb0, b);
     tma_load_3d(&tmDO, bar_q, sDO_u, h * DH, 0, b);
     tma_load_3d(&tmO, bar_q, sO_u, h * DH, 0, b);
     if (qtiles > 1) {
@@ -505,12 +516,14 @@ attn_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     const uint32_t ph = qt & 1;
     const int row0 = qt * 128;
     const int row = row0 + r;
-    const uint32_t sQ_t = sQ_u + qt * kChunkBytes, sDO_t = sDO_u + qt * kChunkBytes, sO_t = sO_u + qt * kChunkBytes;
+    const int buf = qt % nbuf;                                  // tile buffer and the parity of its barrier
+    const uint32_t bar_qt = bar_q + 8 * buf, ph_q = static_cast<uint32_t>((qt / nbuf) & 1);
+    const uint32_t sQ_t = sQ_u + buf * kChunkBytes, sDO_t = sDO_u + buf * kChunkBytes, sO_t = sO_u + buf * kChunkBytes;
     const float lse2 = lse_next * 1.4426950408889634f;
     if (qt + 1 < qtiles) lse_next = (row + 128 < a.N) ? lse_row[row + 128] : INFINITY;
     if (tid == 0) {
       if (qt == 0) mbar_wait(bar_kv, 0);
-      mbar_wait(bar_q + 8 * qt, 0);
+      mbar_wait(bar_qt, ph_q);
       tc_fence_after();
       const uint32_t idesc = umma_idesc_bf16(128, NK, false, false);
 #pragma unroll
@@ -521,7 +534,7 @@ attn_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     }
     __syncwarp();
     // partial D_i = sum over this thread's 32 head-dim columns of dO * O, from the swizzled TMA tiles
-    mbar_wait(bar_q + 8 * qt, 0);
+    mbar_wait(bar_qt, ph_q);
     {
       float part = 0.f;
 #pragma unroll
@@ -536,14 +549,14 @@ attn_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     // P = exp2(S*c - LSE*log2e) -> bf16 -> sP   (rows >= N and keys >= N give exactly 0)
     auto emit_p = [&](const uint32_t (&v)[32], int c0) {
       float pv[32];   // rows >= N carry LSE = +inf, so exp2(-inf) zeroes them without a row predicate
-      if (c0 + 32 <= a.N) {
+      if (kb0 + c0 + 32 <= a.N) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) pv[j] = ex2_approx(fmaf(__uint_as_float(v[j]), a.scale_log2, -lse2));
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const float e = ex2_approx(fmaf(__uint_as_float(v[j]), a.scale_log2, -lse2));
-          pv[j] = (c0 + j < a.N) ? e : 0.f;
+          pv[j] = (kb0 + c0 + j < a.N) ? e : 0.f;
         }
       }
       const int kc = c0 >> 6, u0 = (c0 & 63) >> 3, nunits = (c0 + 32 <= NK) ? 4 : 2;
@@ -645,7 +658,19 @@ attn_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       uint32_t v[32];
       tmem_ld_32x32b_x32(trow + half * 32, v);
       tmem_ld_wait();
-      stage_row32_bf16(sO_t, r, half, v, a.scale);   // this tile's O buffer is dead once D_i is known
+      if constexpr (LONG) {
+        // this key block's share of dQ: 32 fp32 columns of the row, added to the accumulation buffer
+        if (row < a.N) {
+          float* dst = a.dq_acc + (static_cast<long long>(b) * a.N + row) * (static_cast<long long>(a.H) * DH) + h * DH + half * 32;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(v[j]) * a.scale),
+                         "f"(__uint_as_float(v[j + 1]) * a.scale), "f"(__uint_as_float(v[j + 2]) * a.scale),
+                         "f"(__uint_as_float(v[j + 3]) * a.scale) : "memory");
+        }
+      } else {
+        stage_row32_bf16(sO_t, r, half, v, a.scale);   // this tile's O buffer is dead once D_i is known
+      }
     }
     fence_proxy_async_smem();
     // the next query tile overwrites sP and TMEM[0,256): wait until every MMA of this tile (dK included)
@@ -654,9 +679,18 @@ attn_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (tid == 0) {   // dQ tile [128 x 64] leaves as one TMA store (rows >= N clipped)
-      tma_store_3d(&tmDQ, sO_t, h * DH, row0, b);
-      bulk_commit();
+    if (tid == 0) {
+      if constexpr (LONG) {
+        if (qt + 2 < qtiles) {   // this tile's buffers are free (every MMA that read them has retired): fetch the tile after next
+          mbar_arrive_expect_tx(bar_qt, 3 * kChunkBytes);
+          tma_load_3d(&tmQ, bar_qt, sQ_t, h * DH, row0 + 256, b);
+          tma_load_3d(&tmDO, bar_qt, sDO_t, h * DH, row0 + 256, b);
+          tma_load_3d(&tmO, bar_qt, sO_t, h * DH, row0 + 256, b);
+        }
+      } else {   // dQ tile [128 x 64] leaves as one TMA store (rows >= N clipped)
+        tma_store_3d(&tmDQ, sO_t, h * DH, row0, b);
+        bulk_commit();
+      }
     }
   }
   // dK, dV: TMEM lane = key within the M tile; the two threads of a lane split the 64 head-dim columns
@@ -677,12 +711,273 @@ attn_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   __syncthreads();
   if (tid == 0) {
     for (int mt = 0; mt < mtiles; ++mt) {
-      tma_store_3d(&tmDK, sP_u + (2 * mt) * kChunkBytes, h * DH, mt * 128, b);
-      tma_store_3d(&tmDV, sP_u + (2 * mt + 1) * kChunkBytes, h * DH, mt * 128, b);
+      tma_store_3d(&tmDK, sP_u + (2 * mt) * kChunkBytes, h * DH, kb0 + mt * 128, b);
+      tma_store_3d(&tmDV, sP_u + (2 * mt + 1) * kChunkBytes, h * DH, kb0 + mt * 128, b);
     }
     bulk_commit();
     bulk_wait_all();   // dQ stores included: shared memory must outlive the reads
   }
+  if (warp == 0) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// ================================================================================================
+// backward, wide heads: 64 < head_dim <= 128 (multiple of 16), any number of tokens — ViT-H/14 is head_dim 80
+// (src/config.py:95-104), 257 tokens at 224 px.  Same algorithm as attn_bwd_tc<true>, re-dimensioned:
+//   * the head dimension spans two 64-column 128B-swizzled chunks (the second TMA box reads 64 columns even when fewer
+//     belong to the head: the K-major MMAs stop after head_dim / 16 steps, the MN-major ones take N = head_dim with the
+//     chunk distance as the descriptor's leading-dimension offset — exactly as attn_fwd_tc_gen consumes V)
+//   * a CTA owns a block of 128 keys (one M tile): TMEM = S / dP / dQ in [0, 128), dK in [128, 128 + head_dim),
+//     dV in [256, 256 + head_dim); shared memory = K, V (2 x 2 chunks) | ONE Q / dO / O tile set (3 x 2 chunks) | P / dS
+//     (2 chunks) = 192 KB, so the next query tile is requested only when the current one has retired
+//   * dQ is added to the fp32 accumulation buffer, dK / dV leave as plain 16-byte global stores (no TMA-store tiles)
+// ================================================================================================
+struct AttnWide {
+  int N, H, dh;
+  float scale, scale_log2;
+  float* lse;
+  float* dq_acc;                       // [B, N, H*dh] fp32, zeroed by the caller
+  __nv_bfloat16 *dk, *dv;
+  long long dk_bs, dk_rs, dv_bs, dv_rs;
+};
+
+__global__ void __launch_bounds__(kAttnThreads, 1)
+attn_bwd_tc_wide(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
+                 const __grid_constant__ CUtensorMap tmO, const __grid_constant__ AttnWide a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  constexpr int T2 = 2 * kChunkBytes;          // one [128 x 128-column] tile: two 64-column chunks
+  const int dh = a.dh;
+  const int kb0 = static_cast<int>(blockIdx.z) * 128;
+  const int NK = min(128, (a.N - kb0 + 15) & ~15);
+  const int qtiles = (a.N + 127) >> 7;
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + T2;
+  uint8_t* sQ = sV + T2;
+  uint8_t* sDO = sQ + T2;
+  uint8_t* sO = sDO + T2;
+  uint8_t* sP = sO + T2;                       // [128 queries x 128 keys]: P, then dS in place
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + T2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  float* red = reinterpret_cast<float*>(bars + 16);   // [2 halves][128 rows] partial D_i
+  const uint32_t bar_kv = smem_u32(bars), bar_q = bar_kv + 8, bar_s = bar_kv + 16, bar_dp = bar_kv + 24,
+                 bar_dq = bar_kv + 32, bar_fin = bar_kv + 40;
+
+  pdl_trigger();
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int half = warp >> 2;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int r = (warp & 3) * 32 + lane;
+  const ColRange cr = my_chunks(NK, half);
+  const uint32_t sP_u = smem_u32(sP), sQ_u = smem_u32(sQ), sDO_u = smem_u32(sDO), sO_u = smem_u32(sO), sK_u = smem_u32(sK),
+                 sV_u = smem_u32(sV);
+  const int ksteps = dh >> 4;                  // 16-column steps of the head dimension
+  // this thread's share of a row's head-dim columns, in 16-column units: half 0 takes the larger part
+  const int u16b = half ? (ksteps + 1) / 2 : 0, u16e = half ? ksteps : (ksteps + 1) / 2;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
+    tma_prefetch_desc(&tmO);
+    for (int i = 0; i < 6; ++i) mbar_init(bar_kv + 8 * i, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  pdl_wait();
+  auto load_q_tile = [&](int row0) {           // Q, dO, O of one query tile: 3 tiles x 2 chunks
+    mbar_arrive_expect_tx(bar_q, 3 * T2);
+    for (int c = 0; c < 2; ++c) {
+      tma_load_3d(&tmQ, bar_q, sQ_u + c * kChunkBytes, h * dh + 64 * c, row0, b);
+      tma_load_3d(&tmDO, bar_q, sDO_u + c * kChunkBytes, h * dh + 64 * c, row0, b);
+      tma_load_3d(&tmO, bar_q, sO_u + c * kChunkBytes, h * dh + 64 * c, row0, b);
+    }
+  };
+  if (tid == 0) {
+    load_q_tile(0);
+    mbar_arrive_expect_tx(bar_kv, 2 * T2);
+    for (int c = 0; c < 2; ++c) {
+      tma_load_3d(&tmK, bar_kv, sK_u + c * kChunkBytes, h * dh + 64 * c, kb0, b);
+      tma_load_3d(&tmV, bar_kv, sV_u + c * kChunkBytes, h * dh + 64 * c, kb0, b);
+    }
+  }
+  if (warp == 0) { __syncwarp(); tmem_alloc(smem_u32(tmem_slot), 512); tmem_relinquish(); }
+  for (int i = tid; i < T2 / 16; i += kAttnThreads) st_shared_v4(sP_u + i * 16, 0u, 0u, 0u, 0u);   // key columns >= NK stay zero
+  const float* lse_row = a.lse + (static_cast<long long>(b) * a.H + h) * a.N;
+  float lse_next = (r < a.N) ? lse_row[r] : INFINITY;
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t trow = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+  const uint32_t T_DK = 128u, T_DV = 256u;
+
+  for (int qt = 0; qt < qtiles; ++qt) {
+    const uint32_t ph = qt & 1;
+    const int row0 = qt * 128;
+    const int row = row0 + r;
+    const float lse2 = lse_next * 1.4426950408889634f;
+    if (qt + 1 < qtiles) lse_next = (row + 128 < a.N) ? lse_row[row + 128] : INFINITY;
+    if (tid == 0) {
+      if (qt == 0) mbar_wait(bar_kv, 0);
+      mbar_wait(bar_q, ph);
+      tc_fence_after();
+      const uint32_t idesc = umma_idesc_bf16(128, NK, false, false);
+      for (int ks = 0; ks < ksteps; ++ks)      // S = Q K^T over head_dim / 16 steps (chunk ks / 4)
+        umma_bf16_ss(tmem_base, umma_smem_desc_sw128(sQ_u + (ks >> 2) * kChunkBytes + (ks & 3) * 32, 16, 1024),
+                     umma_smem_desc_sw128(sK_u + (ks >> 2) * kChunkBytes + (ks & 3) * 32, 16, 1024), idesc, ks > 0 ? 1u : 0u);
+      umma_commit(bar_s);
+    }
+    __syncwarp();
+    mbar_wait(bar_q, ph);
+    {   // partial D_i over this thread's share of the head-dim columns
+      float part = 0.f;
+      for (int u = 2 * u16b; u < 2 * u16e; ++u) {
+        const uint32_t off = static_cast<uint32_t>((u >> 3) * kChunkBytes) + swz_unit(r, u & 7);
+        part += dot8_bf16(ld_shared_v4(sO_u + off), ld_shared_v4(sDO_u + off));
+      }
+      red[half * 128 + r] = part;
+    }
+    mbar_wait(bar_s, ph);
+    tc_fence_after();
+    auto emit_p = [&](const uint32_t (&v)[32], int c0) {
+      float pv[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float e = ex2_approx(fmaf(__uint_as_float(v[j]), a.scale_log2, -lse2));
+        pv[j] = (kb0 + c0 + j < a.N) ? e : 0.f;
+      }
+      const int kc = c0 >> 6, u0 = (c0 & 63) >> 3, nunits = (c0 + 32 <= NK) ? 4 : 2;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (u < nunits)
+          st_shared_v4(sP_u + kc * kChunkBytes + swz_unit(r, u0 + u), pack_bf16x2(pv[8 * u + 0], pv[8 * u + 1]),
+                       pack_bf16x2(pv[8 * u + 2], pv[8 * u + 3]), pack_bf16x2(pv[8 * u + 4], pv[8 * u + 5]),
+                       pack_bf16x2(pv[8 * u + 6], pv[8 * u + 7]));
+    };
+    for (int c = cr.c_begin; c < cr.c_end; ++c) {
+      uint32_t v0[32];
+      issue_chunk(trow, c * 32, NK, v0);
+      tmem_ld_wait();
+      emit_p(v0, c * 32);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    const float Di = red[r] + red[128 + r];
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t idesc_dp = umma_idesc_bf16(128, NK, false, false);
+      for (int ks = 0; ks < ksteps; ++ks)      // dP = dO V^T (overwrites S)
+        umma_bf16_ss(tmem_base, umma_smem_desc_sw128(sDO_u + (ks >> 2) * kChunkBytes + (ks & 3) * 32, 16, 1024),
+                     umma_smem_desc_sw128(sV_u + (ks >> 2) * kChunkBytes + (ks & 3) * 32, 16, 1024), idesc_dp, ks > 0 ? 1u : 0u);
+      // dV += P^T dO : A = P^T (MN-major image of sP: 128 keys = two 64-key chunks), B = dO (MN-major, N = head_dim
+      // across the two column chunks), K = 128 query rows in 8 steps
+      const uint32_t idesc_t = umma_idesc_bf16(128, dh, true, true);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        umma_bf16_ss(tmem_base + T_DV, umma_smem_desc_sw128(sP_u + k * 2048, kChunkBytes, 1024),
+                     umma_smem_desc_sw128(sDO_u + k * 2048, kChunkBytes, 1024), idesc_t, (qt > 0 || k > 0) ? 1u : 0u);
+      umma_commit(bar_dp);
+    }
+    __syncwarp();
+    mbar_wait(bar_dp, ph);
+    tc_fence_after();
+    auto emit_ds = [&](const uint32_t (&v)[32], int c0) {
+      const int kc = c0 >> 6, u0 = (c0 & 63) >> 3, nunits = (c0 + 32 <= NK) ? 4 : 2;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (u < nunits) {
+          const uint32_t addr = sP_u + kc * kChunkBytes + swz_unit(r, u0 + u);
+          const uint4 pp = ld_shared_v4(addr);
+          const float d0 = bf16_lo(pp.x) * (__uint_as_float(v[8 * u + 0]) - Di);
+          const float d1 = bf16_hi(pp.x) * (__uint_as_float(v[8 * u + 1]) - Di);
+          const float d2 = bf16_lo(pp.y) * (__uint_as_float(v[8 * u + 2]) - Di);
+          const float d3 = bf16_hi(pp.y) * (__uint_as_float(v[8 * u + 3]) - Di);
+          const float d4 = bf16_lo(pp.z) * (__uint_as_float(v[8 * u + 4]) - Di);
+          const float d5 = bf16_hi(pp.z) * (__uint_as_float(v[8 * u + 5]) - Di);
+          const float d6 = bf16_lo(pp.w) * (__uint_as_float(v[8 * u + 6]) - Di);
+          const float d7 = bf16_hi(pp.w) * (__uint_as_float(v[8 * u + 7]) - Di);
+          st_shared_v4(addr, pack_bf16x2(d0, d1), pack_bf16x2(d2, d3), pack_bf16x2(d4, d5), pack_bf16x2(d6, d7));
+        }
+      }
+    };
+    for (int c = cr.c_begin; c < cr.c_end; ++c) {
+      uint32_t v0[32];
+      issue_chunk(trow, c * 32, NK, v0);
+      tmem_ld_wait();
+      emit_ds(v0, c * 32);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      // dQ = dS K : A = dS (K-major over keys), B = K (MN-major: keys x head_dim, chunk distance kChunkBytes)
+      const uint32_t idesc_dq = umma_idesc_bf16(128, dh, false, true);
+      const int nks = NK >> 4;
+      for (int t = 0; t < nks; ++t)
+        umma_bf16_ss(tmem_base, umma_smem_desc_sw128(sP_u + (t >> 2) * kChunkBytes + (t & 3) * 32, 16, 1024),
+                     umma_smem_desc_sw128(sK_u + t * 2048, kChunkBytes, 1024), idesc_dq, t > 0 ? 1u : 0u);
+      umma_commit(bar_dq);
+      const uint32_t idesc_t = umma_idesc_bf16(128, dh, true, true);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)              // dK += dS^T Q
+        umma_bf16_ss(tmem_base + T_DK, umma_smem_desc_sw128(sP_u + k * 2048, kChunkBytes, 1024),
+                     umma_smem_desc_sw128(sQ_u + k * 2048, kChunkBytes, 1024), idesc_t, (qt > 0 || k > 0) ? 1u : 0u);
+      umma_commit(bar_fin);
+    }
+    __syncwarp();
+    mbar_wait(bar_dq, ph);
+    tc_fence_after();
+    for (int u = u16b; u < u16e; ++u) {        // this key block's share of dQ, 16 columns at a time
+      uint32_t v[16];
+      tmem_ld_32x32b_x16(trow + static_cast<uint32_t>(u * 16), v);
+      tmem_ld_wait();
+      if (row < a.N) {
+        float* dst = a.dq_acc + (static_cast<long long>(b) * a.N + row) * (static_cast<long long>(a.H) * dh) + h * dh + u * 16;
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(v[j]) * a.scale),
+                       "f"(__uint_as_float(v[j + 1]) * a.scale), "f"(__uint_as_float(v[j + 2]) * a.scale),
+                       "f"(__uint_as_float(v[j + 3]) * a.scale) : "memory");
+      }
+    }
+    mbar_wait(bar_fin, ph);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (tid == 0 && qt + 1 < qtiles) load_q_tile(row0 + 128);   // the tile set is free: every MMA that read it has retired
+  }
+  // dK, dV: TMEM lane = key of the block; 16-column units split between the two threads of a lane
+  {
+    const int key = kb0 + r;
+    for (int u = u16b; u < u16e; ++u) {
+      uint32_t vk[16], vv[16];
+      tmem_ld_32x32b_x16(trow + T_DK + static_cast<uint32_t>(u * 16), vk);
+      tmem_ld_32x32b_x16(trow + T_DV + static_cast<uint32_t>(u * 16), vv);
+      tmem_ld_wait();
+      if (key < a.N) {
+        uint4* dk = reinterpret_cast<uint4*>(a.dk + b * a.dk_bs + static_cast<long long>(key) * a.dk_rs + h * dh + u * 16);
+        uint4* dv = reinterpret_cast<uint4*>(a.dv + b * a.dv_bs + static_cast<long long>(key) * a.dv_rs + h * dh + u * 16);
+#pragma unroll
+        for (int q4 = 0; q4 < 2; ++q4) {
+          uint4 ok, ov;
+          ok.x = pack_bf16x2(__uint_as_float(vk[8 * q4 + 0]) * a.scale, __uint_as_float(vk[8 * q4 + 1]) * a.scale);
+          ok.y = pack_bf16x2(__uint_as_float(vk[8 * q4 + 2]) * a.scale, __uint_as_float(vk[8 * q4 + 3]) * a.scale);
+          ok.z = pack_bf16x2(__uint_as_float(vk[8 * q4 + 4]) * a.scale, __uint_as_float(vk[8 * q4 + 5]) * a.scale);
+          ok.w = pack_bf16x2(__uint_as_float(vk[8 * q4 + 6]) * a.scale, __uint_as_float(vk[8 * q4 + 7]) * a.scale);
+          ov.x = pack_bf16x2(__uint_as_float(vv[8 * q4 + 0]), __uint_as_float(vv[8 * q4 + 1]));
+          ov.y = pack_bf16x2(__uint_as_float(vv[8 * q4 + 2]), __uint_as_float(vv[8 * q4 + 3]));
+          ov.z = pack_bf16x2(__uint_as_float(vv[8 * q4 + 4]), __uint_as_float(vv[8 * q4 + 5]));
+          ov.w = pack_bf16x2(__uint_as_float(vv[8 * q4 + 6]), __uint_as_float(vv[8 * q4 + 7]));
+          dk[q4] = ok;
+          dv[q4] = ov;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
   if (warp == 0) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
@@ -813,7 +1108,7 @@ extern "C" int vitb_attn_bwd_tc(const vitb_attn_params* p, void* stream_) {
   // K, V | Q, dO, O tiles of every query tile | one P/dS image | barriers + TMEM slot | D_i partials | alignment slack
   const int smem = 2 * kv_bytes + 3 * qtiles * kChunkBytes + nchunks * kChunkBytes + 128 + 1024 + 1024;
   VITB_REQUIRE(smem <= 227 * 1024, VITB_ERR_UNSUPPORTED_SHAPE, "attn_bwd_tc: %d B of shared memory", smem);
-  VITB_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  VITB_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   dim3 grid(p->H, p->B);
   VITB_REQUIRE(p->dq_batch_stride % 8 == 0 && p->dk_batch_stride % 8 == 0 && p->dv_batch_stride % 8 == 0,
                VITB_ERR_UNSUPPORTED_SHAPE, "attn_bwd_tc: gradient batch strides %% 8");
@@ -821,8 +1116,123 @@ extern "C" int vitb_attn_bwd_tc(const vitb_attn_params* p, void* stream_) {
   if ((st = make_head_map(&tdq, p->dq, p->H, N, p->B, p->dq_row_stride, p->dq_batch_stride, 128)) != VITB_OK) return st;
   if ((st = make_head_map(&tdk, p->dk, p->H, N, p->B, p->dk_row_stride, p->dk_batch_stride, 128)) != VITB_OK) return st;
   if ((st = make_head_map(&tdv, p->dv, p->H, N, p->B, p->dv_row_stride, p->dv_batch_stride, 128)) != VITB_OK) return st;
-  VITB_CUDA_CHECK(vitb_launch<kPdlAttn>(attn_bwd_tc, grid, dim3(kAttnThreads), smem, reinterpret_cast<cudaStream_t>(stream_), tq, tk,
+  VITB_CUDA_CHECK(vitb_launch<kPdlAttn>(attn_bwd_tc<false>, grid, dim3(kAttnThreads), smem, reinterpret_cast<cudaStream_t>(stream_), tq, tk,
                               tv, tdo, to, tdq, tdk, tdv, a));
   VITB_LAUNCH_CHECK("attn_bwd_tc");
+  return VITB_OK;
+}
+
+// fp32 dQ accumulation buffer [rows, cols] -> bf16 dq through its strides (rows = B*N, cols = H*64)
+namespace {
+__global__ void __launch_bounds__(256)
+dq_to_bf16_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dq, int N, int cols, long long dq_bs, long long dq_rs,
+                  long long total4) {
+  const int c4 = cols >> 2;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = i / c4;
+    const int c = static_cast<int>(i - row * c4) * 4;
+    const float4 v = reinterpret_cast<const float4*>(acc)[i];
+    const long long bimg = row / N, n = row - bimg * N;
+    uint2 o;
+    o.x = pack_bf16x2(v.x, v.y);
+    o.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(dq + bimg * dq_bs + n * dq_rs + c) = o;
+  }
+}
+}  // namespace
+
+extern "C" int vitb_attn_bwd_long_supported(int head_dim, int Nq, int Nk) {
+  return head_dim >= DH && head_dim <= 128 && head_dim % 16 == 0 && Nq == Nk && Nk >= 1;
+}
+
+namespace {
+int launch_bwd_wide(const vitb_attn_params* p, float* dq_acc, cudaStream_t stream) {
+  const int N = p->Nk, dh = p->head_dim;
+  int st;
+  CUtensorMap tq, tk, tv, tdo, to;
+  if ((st = make_head_map(&tq, p->q, p->H, N, p->B, p->q_row_stride, p->q_batch_stride, 128, dh)) != VITB_OK) return st;
+  if ((st = make_head_map(&tk, p->k, p->H, N, p->B, p->k_row_stride, p->k_batch_stride, 128, dh)) != VITB_OK) return st;
+  if ((st = make_head_map(&tv, p->v, p->H, N, p->B, p->v_row_stride, p->v_batch_stride, 128, dh)) != VITB_OK) return st;
+  if ((st = make_head_map(&tdo, p->dout, p->H, N, p->B, p->do_row_stride, p->do_batch_stride, 128, dh)) != VITB_OK) return st;
+  if ((st = make_head_map(&to, p->o, p->H, N, p->B, p->o_row_stride, p->o_batch_stride, 128, dh)) != VITB_OK) return st;
+  AttnWide a{};
+  a.N = N; a.H = p->H; a.dh = dh;
+  a.scale = 1.0f / sqrtf((float)dh);
+  a.scale_log2 = a.scale * 1.4426950408889634f;
+  a.lse = p->lse;
+  a.dq_acc = dq_acc;
+  a.dk = reinterpret_cast<__nv_bfloat16*>(p->dk); a.dk_bs = p->dk_batch_stride; a.dk_rs = p->dk_row_stride;
+  a.dv = reinterpret_cast<__nv_bfloat16*>(p->dv); a.dv_bs = p->dv_batch_stride; a.dv_rs = p->dv_row_stride;
+  // K, V | Q, dO, O | P / dS: six [128 x 128-column] tiles | barriers + TMEM slot | D_i partials | alignment slack
+  const int smem = 6 * 2 * kChunkBytes + 128 + 1024 + 1024;
+  VITB_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_tc_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  dim3 grid(p->H, p->B, (N + 127) / 128);
+  VITB_CUDA_CHECK(vitb_launch<kPdlAttn>(attn_bwd_tc_wide, grid, dim3(kAttnThreads), smem, stream, tq, tk, tv, tdo, to, a));
+  VITB_LAUNCH_CHECK("attn_bwd_tc_wide");
+  return VITB_OK;
+}
+}  // namespace
+
+// Backward for ANY number of tokens (head_dim 64): 384 px fine-tuning gives 577 tokens (src/config.py:12).  dq_acc is an
+// fp32 [B, N, H*64] scratch buffer that the CALLER has zeroed; the key-block CTAs add their shares of dQ into it and a
+// second kernel writes p->dq (bf16) from it.  dk / dv are written directly.
+extern "C" int vitb_attn_bwd_tc_long(const vitb_attn_params* p, float* dq_acc, void* stream_) {
+  int st = vitb_check_device();
+  if (st != VITB_OK) return st;
+  VITB_REQUIRE(p && p->struct_bytes == (int)sizeof(vitb_attn_params), VITB_ERR_BAD_ARG, "attn_bwd_tc_long: ABI mismatch");
+  VITB_REQUIRE(p->dtype == VITB_BF16 && vitb_attn_bwd_long_supported(p->head_dim, p->Nq, p->Nk), VITB_ERR_UNSUPPORTED_SHAPE,
+               "attn_bwd_tc_long: bf16, head_dim 64..128 (multiple of 16), Nq == Nk (dh=%d Nq=%d Nk=%d)", p->head_dim, p->Nq, p->Nk);
+  if (p->B == 0) return VITB_OK;
+  VITB_REQUIRE(p->q && p->k && p->v && p->o && p->lse && p->dout && p->dq && p->dk && p->dv && dq_acc, VITB_ERR_BAD_ARG,
+               "attn_bwd_tc_long: null tensor");
+  VITB_REQUIRE(((reinterpret_cast<uintptr_t>(dq_acc) | reinterpret_cast<uintptr_t>(p->dq) | reinterpret_cast<uintptr_t>(p->dk) |
+                 reinterpret_cast<uintptr_t>(p->dv)) & 15u) == 0,
+               VITB_ERR_BAD_ARG, "attn_bwd_tc_long: dq_acc, dq, dk, dv must be 16-byte aligned");
+  const long long strides[] = {p->q_row_stride, p->k_row_stride, p->v_row_stride, p->o_row_stride, p->do_row_stride,
+                               p->dq_row_stride, p->dk_row_stride, p->dv_row_stride, p->q_batch_stride, p->k_batch_stride,
+                               p->v_batch_stride, p->o_batch_stride, p->do_batch_stride, p->dq_batch_stride, p->dk_batch_stride,
+                               p->dv_batch_stride};
+  for (long long sv : strides) VITB_REQUIRE(sv % 8 == 0, VITB_ERR_UNSUPPORTED_SHAPE, "attn_bwd_tc_long: strides must be multiples of 8");
+  const int N = p->Nk;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const int cols = p->H * p->head_dim;
+  const long long total4 = static_cast<long long>(p->B) * N * (cols / 4);
+  long long blocks = (total4 + 255) / 256;
+  const long long cap = static_cast<long long>(vitb_num_sms()) * 16;
+  if (blocks > cap) blocks = cap;
+  if (p->head_dim != DH) {       // wide heads: 128-key blocks, two head-dim chunks
+    if ((st = launch_bwd_wide(p, dq_acc, stream)) != VITB_OK) return st;
+    dq_to_bf16_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(dq_acc, reinterpret_cast<__nv_bfloat16*>(p->dq), N, cols,
+                                                                    p->dq_batch_stride, p->dq_row_stride, total4);
+    VITB_LAUNCH_CHECK("dq_to_bf16_kernel");
+    return VITB_OK;
+  }
+  const int kv_box = N >= 256 ? 256 : ((N + 15) & ~15);
+  CUtensorMap tq, tk, tv, tdo, to, tdq, tdk, tdv;
+  if ((st = make_head_map(&tq, p->q, p->H, N, p->B, p->q_row_stride, p->q_batch_stride, 128)) != VITB_OK) return st;
+  if ((st = make_head_map(&tk, p->k, p->H, N, p->B, p->k_row_stride, p->k_batch_stride, kv_box)) != VITB_OK) return st;
+  if ((st = make_head_map(&tv, p->v, p->H, N, p->B, p->v_row_stride, p->v_batch_stride, kv_box)) != VITB_OK) return st;
+  if ((st = make_head_map(&tdo, p->dout, p->H, N, p->B, p->do_row_stride, p->do_batch_stride, 128)) != VITB_OK) return st;
+  if ((st = make_head_map(&to, p->o, p->H, N, p->B, p->o_row_stride, p->o_batch_stride, 128)) != VITB_OK) return st;
+  if ((st = make_head_map(&tdq, p->dq, p->H, N, p->B, p->dq_row_stride, p->dq_batch_stride, 128)) != VITB_OK) return st;
+  if ((st = make_head_map(&tdk, p->dk, p->H, N, p->B, p->dk_row_stride, p->dk_batch_stride, 128)) != VITB_OK) return st;
+  if ((st = make_head_map(&tdv, p->dv, p->H, N, p->B, p->dv_row_stride, p->dv_batch_stride, 128)) != VITB_OK) return st;
+  AttnTc a{};
+  a.N = N; a.NK = kv_box; a.H = p->H;
+  a.scale = 1.0f / sqrtf((float)DH);
+  a.scale_log2 = a.scale * 1.4426950408889634f;
+  a.lse = p->lse;
+  a.dq_acc = dq_acc;
+  // K, V boxes (256 keys each) | two Q / dO / O tile buffers | the P / dS image (4 chunks) | barriers + TMEM slot | D_i | slack
+  const int smem = 2 * kv_box * 128 + 3 * 2 * kChunkBytes + 4 * kChunkBytes + 128 + 1024 + 1024;
+  VITB_REQUIRE(smem <= 227 * 1024, VITB_ERR_UNSUPPORTED_SHAPE, "attn_bwd_tc_long: %d B of shared memory", smem);
+  VITB_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  dim3 grid(p->H, p->B, (N + 255) / 256);
+  VITB_CUDA_CHECK(vitb_launch<kPdlAttn>(attn_bwd_tc<true>, grid, dim3(kAttnThreads), smem, stream, tq, tk, tv, tdo, to, tdq, tdk, tdv, a));
+  VITB_LAUNCH_CHECK("attn_bwd_tc<long>");
+  dq_to_bf16_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(dq_acc, reinterpret_cast<__nv_bfloat16*>(p->dq), N, cols,
+                                                                  p->dq_batch_stride, p->dq_row_stride, total4);
+  VITB_LAUNCH_CHECK("dq_to_bf16_kernel");
   return VITB_OK;
 }

@@ -712,7 +712,7 @@ class _AttentionPacked(torch.autograd.Function):
         if not do.is_contiguous():
             do = do.contiguous()
         q, k, v = qkv[:, :, :HD], qkv[:, :, HD:2 * HD], qkv[:, :, 2 * HD:]
-        use_tc = ops.attn_supported_tc(HD // H, N, N, qkv.dtype)
+        use_tc = ops.attn_bwd_supported_any(HD // H, N, N, qkv.dtype)
         gdt = BF16 if use_tc else F32
         dqkv = torch.empty((B, N, HD3), dtype=gdt, device=qkv.device)
         ops.attn_bwd(do, q, k, v, o, lse, H, use_tc=use_tc, dq=dqkv[:, :, :HD], dk=dqkv[:, :, HD:2 * HD],

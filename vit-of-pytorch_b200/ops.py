@@ -206,6 +206,11 @@ def attn_supported_tc(dh, Nq, Nk, dtype):
     return dtype == torch.bfloat16 and bool(L.vitb_attn_supported_tc(dh, Nq, Nk))
 
 
+def attn_bwd_supported_any(dh, Nq, Nk, dtype):
+    """tcgen05 backward for these shapes: the <= 256-token kernels or the key-block kernel (head_dim 64, any count)."""
+    return dtype == torch.bfloat16 and bool(L.vitb_attn_supported_tc(dh, Nq, Nk) or L.vitb_attn_bwd_long_supported(dh, Nq, Nk))
+
+
 def attn_fwd_supported_tc(dh, Nq, Nk, dtype):
     """tcgen05 forward: the above plus wide heads (64 < head_dim <= 128, <= 320 tokens: ViT-H/14)."""
     return dtype == torch.bfloat16 and bool(L.vitb_attn_fwd_supported_tc(dh, Nq, Nk))
@@ -258,7 +263,7 @@ def attn_bwd(dout, q, k, v, o, lse, H, *, use_tc=None, dq=None, dk=None, dv=None
     Nk = k.shape[1]
     dh = HD // H
     if use_tc is None:
-        use_tc = attn_supported_tc(dh, Nq, Nk, q.dtype)
+        use_tc = attn_bwd_supported_any(dh, Nq, Nk, q.dtype)
     gdt = torch.bfloat16 if use_tc else torch.float32
     if dq is None:
         dq = torch.zeros((B, Nq, HD), dtype=gdt, device=q.device) if not use_tc else torch.empty((B, Nq, HD), dtype=gdt, device=q.device)
@@ -278,6 +283,11 @@ def attn_bwd(dout, q, k, v, o, lse, H, *, use_tc=None, dq=None, dk=None, dv=None
     p.dq_batch_stride, p.dq_row_stride = _head_strides(dq, H, dh, "dq")
     p.dk_batch_stride, p.dk_row_stride = _head_strides(dk, H, dh, "dk")
     p.dv_batch_stride, p.dv_row_stride = _head_strides(dv, H, dh, "dv")
+    if use_tc and not L.vitb_attn_supported_tc(dh, Nq, Nk):
+        # more than 256 tokens: key blocks on separate CTAs, dQ summed in an fp32 scratch buffer
+        dq_acc = torch.zeros((B, Nq, HD), dtype=torch.float32, device=q.device)
+        L.check(L._vitb_attn_bwd_tc_long(C.byref(p), L.ptr(dq_acc), L.stream_ptr(q.device)), "vitb_attn_bwd_tc_long")
+        return dq, dk, dv
     fn = L._vitb_attn_bwd_tc if use_tc else L._vitb_attn_bwd_simt
     if use_tc and _attn_ws_enabled() and L.vitb_attn_ws_supported(1, dh, Nq, Nk):
         fn = L._vitb_attn_bwd_ws        # persistent warp-specialised kernel
