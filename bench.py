@@ -85,6 +85,11 @@ CONFIGS = {   # BASELINE.json configs[1..4]
     "c5": dict(kind="resvit_train", arch="b16", batch=128, classes=100,
                workload="Res-ViT B/16 224px fine-tune step (router target 0.4, LoRA rank 8, approximator rank 256, block_size 1; "
                         "CE + active + distill losses, AdamW + clip 1.0), batch %d/GPU, C=100"),
+    # not BASELINE.json configs: the shapes the key-block attention backward exists for (profiles/)
+    "h14train": dict(kind="vit_train", arch="h14", batch=32, classes=100,
+                     workload="ViT-H/14 224px train step (N=257 tokens, head_dim 80; fwd+bwd+SGD), batch %d/GPU, C=100"),
+    "b16_384": dict(kind="vit_train", arch="b16", batch=32, classes=100, image=384,
+                    workload="ViT-B/16 384px train step (N=577 tokens; fwd+bwd+SGD), batch %d/GPU, C=100"),
 }
 
 
@@ -353,6 +358,7 @@ def main():
     cfg = CONFIGS[args.config]
     kind, arch, classes = cfg["kind"], cfg["arch"], cfg["classes"]
     B = args.batch if args.batch > 0 else cfg["batch"]
+    image = cfg.get("image", IMG)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -382,7 +388,7 @@ def main():
             c, a, d, e, metric = net(img, labels)
             return c + a + d
     else:
-        model = vitb200.build_vit(arch, IMG, classes)
+        model = vitb200.build_vit(arch, image, classes)
         with torch.no_grad():                    # SURVEY.md F5 recipe: trained-like scale for attention / pos weights
             for k, v in model.state_dict().items():
                 if k.endswith(("attn.query.weight", "attn.key.weight", "attn.value.weight", "attn.out.weight",
@@ -390,7 +396,7 @@ def main():
                     v.mul_(0.02)
         model = model.to(dev)
         model.train(train)
-        fwd_ref, fwd_exec = vit_gflop(arch, IMG, classes)
+        fwd_ref, fwd_exec = vit_gflop(arch, image, classes)
         gflop_ref, gflop_exec = (3 * fwd_ref, 3 * fwd_exec) if train else (fwd_ref, fwd_exec)
         opt = sched = None
         if train:
@@ -411,7 +417,7 @@ def main():
     graph_one = world > 1 and args.ddp_mode == "graph1"
     net = vitb200.ddp.DataParallel(model, opt) if (world > 1 and args.ddp_mode == "overlap") else model
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    img_d = torch.randn(B, 3, IMG, IMG, generator=gen, device=dev)
+    img_d = torch.randn(B, 3, image, image, generator=gen, device=dev)
     lab_d = torch.randint(0, classes, (B,), generator=gen, device=dev)
     img_h = img_d.cpu().pin_memory()
     lab_h = lab_d.cpu().pin_memory()

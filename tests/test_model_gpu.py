@@ -139,6 +139,34 @@ def test_l16_geometry_train_step_matches_oracle(mode, tol):
             assert abs(n - rn) <= 0.1 * rn + 1e-5 * grads[k].numel() ** 0.5, (k, n, rn)
 
 
+@pytest.mark.parametrize("name,cfg", [
+    ("384 px, 577 tokens, head_dim 64", dict(image_size=(384, 384), patch_size=(16, 16), emb_dim=128, mlp_dim=256, num_heads=2)),
+    ("ViT-H/14-like, 257 tokens, head_dim 80", dict(image_size=(224, 224), patch_size=(14, 14), emb_dim=1280, mlp_dim=2560, num_heads=16)),
+])
+def test_long_and_wide_attention_train_step_bf16(name, cfg):
+    """Training at the reference's 384 px resolution (src/config.py:12: 577 tokens) and at ViT-H/14's head shape
+    (src/config.py:95-104: head_dim 80, 257 tokens): the whole step runs on the tcgen05 kernels — fused blocks, the
+    key-block attention backward — and agrees with the fp32 oracle: logits within 2e-2, every gradient within 6e-2."""
+    import vitb200
+    cfg = dict(cfg, num_layers=3, num_classes=10, attn_dropout_rate=0.0, dropout_rate=0.0)
+    torch.manual_seed(21)
+    m = vitb200.VisionTransformer(**cfg)
+    sd = vit_oracle.scaled_init_({k: v.detach().clone() for k, v in m.state_dict().items()})
+    m.load_state_dict(sd)
+    gen = torch.Generator().manual_seed(22)
+    img = torch.randn(3, 3, *cfg["image_size"], generator=gen)
+    labels = torch.randint(0, 10, (3,), generator=gen)
+    logits, loss, grads = _run(m.cuda().train(), img, labels, "bf16")
+    osd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    ref_loss = vit_oracle.vit_loss(img, labels, osd)
+    ref_loss.backward()
+    ref_logits = vit_oracle.vit_logits(img, sd)
+    assert rel_l2(logits, ref_logits) < 2e-2, rel_l2(logits, ref_logits)
+    for k, v in osd.items():
+        if not k.endswith("key.bias"):
+            assert grad_close(grads[k], v.grad, 6e-2, atol=1e-6), (name, k, rel_l2(grads[k], v.grad))
+
+
 @pytest.mark.parametrize("arch,img,patch", [("b32", 224, 32), ("h14-ish", 224, 14)])
 def test_other_geometries_fp32_forward(arch, img, patch):
     """N=50 (patch 32) and N=257 / head_dim 80 / K=588 (patch 14): the non-power-of-two tails."""

@@ -1267,9 +1267,12 @@ def encoder_block_row0(x, H, norm1, q, k, v, o, norm2, fc1, fc2):
 
 
 def encoder_block(x, H, norm1, q, k, v, o, norm2, fc1, fc2):
-    """Fused block when possible (bf16 mode, head_dim 64, <= 256 tokens), else None (caller composes ops)."""
+    """Fused block when possible (bf16 mode, attention shapes the tcgen05 kernels take forward AND backward: head_dim
+    64..128 in steps of 16, any token count), else None (caller composes ops)."""
     D = x.shape[-1]
-    if _fp32_mode() or D % H != 0 or not ops.attn_supported_tc(D // H, x.shape[1], x.shape[1], BF16):
+    N = x.shape[1]
+    if _fp32_mode() or D % H != 0 or D % 8 != 0 or not (ops.attn_fwd_supported_tc(D // H, N, N, BF16) and
+                                                        ops.attn_bwd_supported_any(D // H, N, N, BF16)):
         return None
     if not all(p.requires_grad for m in (norm1, q, k, v, o, norm2, fc1, fc2) for p in m.parameters()) and torch.is_grad_enabled():
         return None

@@ -208,7 +208,12 @@ def attn_supported_tc(dh, Nq, Nk, dtype):
 
 def attn_bwd_supported_any(dh, Nq, Nk, dtype):
     """tcgen05 backward for these shapes: the <= 256-token kernels or the key-block kernel (head_dim 64, any count)."""
-    return dtype == torch.bfloat16 and bool(L.vitb_attn_supported_tc(dh, Nq, Nk) or L.vitb_attn_bwd_long_supported(dh, Nq, Nk))
+    if dtype != torch.bfloat16:
+        return False
+    if L.vitb_attn_supported_tc(dh, Nq, Nk):
+        return True
+    # VITB_ATTN_BWD_LONG=0: these shapes go back to the fp32 CUDA-core backward (A/B runs, profiles/attn_long_bwd_r02.txt)
+    return os.environ.get("VITB_ATTN_BWD_LONG", "1") != "0" and bool(L.vitb_attn_bwd_long_supported(dh, Nq, Nk))
 
 
 def attn_fwd_supported_tc(dh, Nq, Nk, dtype):
