@@ -1136,6 +1136,8 @@ extern "C" int VITB_GEMM_ENTRY(const vitb_gemm_params* p, void* stream_) {
   // tile width: 256 unless that pads N more than 128 would
   const int pad256 = ((p->N + 255) / 256) * 256 - p->N;
   const int pad128 = ((p->N + 127) / 128) * 128 - p->N;
+  // (128-column tiles for the narrow N = 768 outputs, whose 3-4 wide tiles per CTA leave the first mainloop and the last
+  // epilogue uncovered, were measured: no gain for the out-projection, 30-50 % slower elsewhere, profiles/gemm_narrow_tiles_r02.txt)
   const int BN = (pad256 <= pad128) ? 256 : 128;
   const int Ng = p->N / ngroups;
   VITB_REQUIRE(ngroups == 1 || Ng % BN == 0, VITB_ERR_UNSUPPORTED_SHAPE,
