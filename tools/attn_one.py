@@ -7,8 +7,9 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import vitb200  # noqa: E402
 
-B, N, H = 128, 197, 12
-D = H * 64
+# ATTN_SHAPE="B,N,H,dh" picks another shape (e.g. 32,577,12,64: the key-block backward at 384 px)
+B, N, H, dh = (int(t) for t in os.environ.get("ATTN_SHAPE", "128,197,12,64").split(","))
+D = H * dh
 qkv = (torch.randn(B, N, 3 * D, device="cuda") * 0.5).to(torch.bfloat16)
 q, k, v = qkv[:, :, :D], qkv[:, :, D:2 * D], qkv[:, :, 2 * D:]
 do = torch.randn(B, N, D, device="cuda").to(torch.bfloat16)

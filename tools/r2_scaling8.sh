@@ -14,7 +14,9 @@ run() {  # name, extra args
 }
 run c2_graph1 --config c2 --ddp-mode graph1
 timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 --master-port 29911 tools/allreduce_bench.py \
-  > "gpurun_out/${R}_n${N}_allreduce.log" 2>&1; echo "allreduce rc=$?"; grep all-reduce "gpurun_out/${R}_n${N}_allreduce.log"
-run c3_graph1 --config c3 --ddp-mode graph1
-run c5_graph1 --config c5 --ddp-mode graph1
-run c2_overlap --config c2 --ddp-mode overlap
+  > "gpurun_out/${R}_n${N}_allreduce.log" 2>&1; echo "allreduce rc=$?"; grep -i "all-reduce\|nvlink" "gpurun_out/${R}_n${N}_allreduce.log"
+if [ "${SCALE_ALL:-1}" = "1" ]; then
+  run c3_graph1 --config c3 --ddp-mode graph1
+  run c5_graph1 --config c5 --ddp-mode graph1
+fi
+if [ "${SCALE_OVERLAP:-0}" = "1" ]; then run c2_overlap --config c2 --ddp-mode overlap; fi
