@@ -75,12 +75,14 @@ def load_jax(path):
         return keys, [z[k] for k in keys]
 
 
-def load_checkpoint(path, map_location="cpu"):
-    """state dict from a reference `.pth` or a JAX ViT `.npz` (src/checkpoint.py:7-17)."""
+def load_checkpoint(path, map_location="cpu", trusted=False):
+    """state dict from a reference `.pth` or a JAX ViT `.npz` (src/checkpoint.py:7-17).  `.pth` files are unpickled with
+    weights_only=True (tensors and plain containers: all the reference's layout holds, src/train.py:69-81);
+    trusted=True allows arbitrary pickles, for files you wrote yourself."""
     if path.endswith("npz"):
         return convert_jax_pytorch(*load_jax(path))
     if path.endswith("pth"):
-        ck = torch.load(path, map_location=map_location, weights_only=False)
+        ck = torch.load(path, map_location=map_location, weights_only=not trusted)
         return ck["state_dict"] if isinstance(ck, dict) and "state_dict" in ck else ck
     raise ValueError("checkpoint format {} not supported yet!".format(path.split(".")[-1]))
 

@@ -125,7 +125,9 @@ class EncoderBlock(nn.Module):
         self.norm2 = nn.LayerNorm(in_dim)
         self.mlp = MlpBlock(in_dim, mlp_dim, in_dim, dropout_rate)
 
-    def forward(self, x):
+    def forward(self, x, row0=False):
+        if row0:
+            return self.forward_row0(x)
         x = x if x.dtype == torch.float32 else x.float()
         if _drop_active(self):      # x + dropout(attn(LN1 x)); h + MLP-with-dropout(LN2 h)  (src/model.py:117-130)
             out = F.layer_norm(x, self.norm1.weight, self.norm1.bias, self.norm1.eps)
@@ -190,7 +192,8 @@ class Encoder(nn.Module):
         for layer in (layers[:-1] if row0_only else layers):
             out = layer(out)
         if row0_only:
-            out = layers[-1].forward_row0(out)          # [B, D]: only the class-token row is ever read
+            out = layers[-1](out, row0=True)            # [B, D]: only the class-token row is ever read (through __call__,
+                                                        # so that module hooks — the data-parallel bucket trigger — fire)
         elif norm_rows is not None:
             out = out[:, norm_rows]
         return F.layer_norm(out, self.norm.weight, self.norm.bias, self.norm.eps, out_dtype=torch.float32)
