@@ -282,7 +282,9 @@ int vitb_gather_rows(const void* src, int64_t src_ld, int dtype, const int32_t* 
 int vitb_scatter_rows(const void* src, int64_t src_ld, int dtype, const int32_t* rows, const int32_t* count, int max_rows,
                       int cols, void* dst, int64_t dst_ld, void* stream);
 
-/* Res-ViT scalar losses, each one single-CTA kernel that also writes the gradient its backward needs.
+/* Res-ViT scalar losses; the reduction also writes the gradient its backward needs (no second pass).
+ * A grid of blocks with one atomic per block: vitb_distill_loss is one launch, vitb_active_loss three small ones (sum,
+ * gradient, scalars) behind a 4-byte memset of *ratio_out, which is REQUIRED (it carries the sum between the launches).
  * vitb_distill_loss — DistillLoss, res-vit/model.py:40-59: *loss_acc += mean((s - t)^2) over [rows, cols] (rows may be
  *   strided: the class-token rows of student / teacher); d_student [rows, cols] fp32 (optional) = 2 (s - t) / (rows cols).
  * vitb_active_loss — ActiveLoss, res-vit/model.py:61-85: ratio = mean of probs[b, n >= reserve_initials, j] (probs

@@ -162,8 +162,10 @@ inline int grid_for(long long items, int per_sm = 8) {
 }
 
 // ---- Res-ViT scalar losses -----------------------------------------------------------------
-// Both are single-CTA reductions over a few thousand values that also write the gradient the backward needs, so the
-// autograd node never launches a second pass.
+// Reductions over 10^5 values that also write the gradient the backward needs, so the autograd node never launches a
+// second pass.  They started as single-CTA kernels; at the benchmarked geometry that was 0.13 ms per DistillLoss call
+// (ten per step) and 0.43 ms per ActiveLoss call — 4.7 % of the Res-ViT fine-tune step (profiles/launches_r02z_c5.csv) —
+// latency-bound on one SM.  Now: a grid of blocks, one atomic per block.
 constexpr int kLossThreads = 512;
 
 __device__ __forceinline__ float block_sum(float v, float* s_part) {
@@ -192,7 +194,8 @@ distill_loss_kernel(const void* __restrict__ s_, long long s_stride, const void*
   const long long n = static_cast<long long>(rows) * cols;
   const float inv = 1.0f / static_cast<float>(n);
   float acc = 0.f;
-  for (long long i = threadIdx.x; i < n; i += kLossThreads) {
+  const long long stride = static_cast<long long>(gridDim.x) * kLossThreads;
+  for (long long i = static_cast<long long>(blockIdx.x) * kLossThreads + threadIdx.x; i < n; i += stride) {
     const int r = static_cast<int>(i / cols), c = static_cast<int>(i - static_cast<long long>(r) * cols);
     float a, b;
     if (BF16) {
@@ -207,36 +210,44 @@ distill_loss_kernel(const void* __restrict__ s_, long long s_stride, const void*
     if (ds) ds[i] = 2.f * d * inv;
   }
   const float tot = block_sum(acc, s_part);
-  if (threadIdx.x == 0) *loss_acc += tot * inv;     // accumulates: d_loss sums over the dynamic layers (:648-650)
+  if (threadIdx.x == 0) atomicAdd(loss_acc, tot * inv);   // accumulates: d_loss sums over the dynamic layers (:648-650)
 }
 
 // ActiveLoss (res-vit/model.py:61-85): ratio = mean of p[b, n >= r0, j]; loss = (ratio + shift - target)^2;
 // dp = 2 (ratio + shift - target) / count for n >= r0, else 0.  p is [B, N, L] fp32.  `shift` (device scalar, optional)
 // carries global-batch mean minus this shard's mean under data parallelism (resvit.ActiveLoss.sync_group).
+// Three launches: the sum over a grid of blocks into *sum (zeroed by a memset node), the gradient from it, the two scalars.
 __global__ void __launch_bounds__(kLossThreads)
-active_loss_kernel(const float* __restrict__ p, int B, int N, int L, int r0, float target, const float* __restrict__ shift,
-                   float* __restrict__ ratio_out, float* __restrict__ loss, float* __restrict__ dp) {
+active_sum_kernel(const float* __restrict__ p, long long n, int N, int L, int r0, float* __restrict__ sum) {
   __shared__ float s_part[kLossThreads / 32];
-  const long long n = static_cast<long long>(B) * N * L;
-  const float count = static_cast<float>(static_cast<long long>(B) * (N - r0) * L);
   float acc = 0.f;
-  for (long long i = threadIdx.x; i < n; i += kLossThreads) {
+  const long long stride = static_cast<long long>(gridDim.x) * kLossThreads;
+  for (long long i = static_cast<long long>(blockIdx.x) * kLossThreads + threadIdx.x; i < n; i += stride) {
     const int tok = static_cast<int>((i / L) % N);
     if (tok >= r0) acc += p[i];
   }
-  const float ratio = block_sum(acc, s_part) / count;
+  const float tot = block_sum(acc, s_part);
+  if (threadIdx.x == 0) atomicAdd(sum, tot);
+}
+
+__global__ void __launch_bounds__(kLossThreads)
+active_grad_kernel(const float* __restrict__ sum, long long n, int N, int L, int r0, float count, float target,
+                   const float* __restrict__ shift, float* __restrict__ dp) {
+  const float e = *sum / count + (shift ? *shift : 0.f) - target;
+  const float g = 2.f * e / count;
+  const long long stride = static_cast<long long>(gridDim.x) * kLossThreads;
+  for (long long i = static_cast<long long>(blockIdx.x) * kLossThreads + threadIdx.x; i < n; i += stride) {
+    const int tok = static_cast<int>((i / L) % N);
+    dp[i] = tok >= r0 ? g : 0.f;
+  }
+}
+
+__global__ void active_final_kernel(float* __restrict__ sum_then_ratio, float count, float target, const float* __restrict__ shift,
+                                    float* __restrict__ loss) {
+  const float ratio = *sum_then_ratio / count;
   const float e = ratio + (shift ? *shift : 0.f) - target;
-  if (threadIdx.x == 0) {
-    if (ratio_out) *ratio_out = ratio;
-    if (loss) *loss = e * e;
-  }
-  if (dp) {
-    const float g = 2.f * e / count;
-    for (long long i = threadIdx.x; i < n; i += kLossThreads) {
-      const int tok = static_cast<int>((i / L) % N);
-      dp[i] = tok >= r0 ? g : 0.f;
-    }
-  }
+  *sum_then_ratio = ratio;
+  if (loss) *loss = e * e;
 }
 
 }  // namespace
@@ -325,8 +336,9 @@ int vitb_distill_loss(const void* student, int64_t s_row_stride, const void* tea
   if (st != VITB_OK) return st;
   VITB_REQUIRE(student && teacher && loss_acc && rows > 0 && cols > 0, VITB_ERR_BAD_ARG, "distill_loss: bad args");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
-  if (dtype == VITB_BF16) distill_loss_kernel<true><<<1, kLossThreads, 0, s>>>(student, s_row_stride, teacher, t_row_stride, rows, cols, loss_acc, d_student);
-  else distill_loss_kernel<false><<<1, kLossThreads, 0, s>>>(student, s_row_stride, teacher, t_row_stride, rows, cols, loss_acc, d_student);
+  const int grid = grid_for((static_cast<long long>(rows) * cols + 3) / 4, 2);   // about four values per thread
+  if (dtype == VITB_BF16) distill_loss_kernel<true><<<grid, kLossThreads, 0, s>>>(student, s_row_stride, teacher, t_row_stride, rows, cols, loss_acc, d_student);
+  else distill_loss_kernel<false><<<grid, kLossThreads, 0, s>>>(student, s_row_stride, teacher, t_row_stride, rows, cols, loss_acc, d_student);
   VITB_LAUNCH_CHECK("distill_loss_kernel");
   return VITB_OK;
 }
@@ -335,9 +347,16 @@ int vitb_active_loss(const float* probs, int B, int N, int L, int reserve_initia
                      float* ratio_out, float* loss, float* d_probs, void* stream_) {
   int st = vitb_check_device();
   if (st != VITB_OK) return st;
-  VITB_REQUIRE(probs && B > 0 && N > reserve_initials && L > 0 && (loss || ratio_out || d_probs), VITB_ERR_BAD_ARG, "active_loss: bad args");
-  active_loss_kernel<<<1, kLossThreads, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(probs, B, N, L, reserve_initials, target, shift_dev,
-                                                                                       ratio_out, loss, d_probs);
+  VITB_REQUIRE(probs && ratio_out && B > 0 && N > reserve_initials && L > 0, VITB_ERR_BAD_ARG,
+               "active_loss: bad args (ratio_out is required: it carries the sum between the launches)");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  const long long n = static_cast<long long>(B) * N * L;
+  const float count = static_cast<float>(static_cast<long long>(B) * (N - reserve_initials) * L);
+  const int grid = grid_for((n + 3) / 4, 2);
+  VITB_CUDA_CHECK(cudaMemsetAsync(ratio_out, 0, sizeof(float), s));
+  active_sum_kernel<<<grid, kLossThreads, 0, s>>>(probs, n, N, L, reserve_initials, ratio_out);
+  if (d_probs) active_grad_kernel<<<grid, kLossThreads, 0, s>>>(ratio_out, n, N, L, reserve_initials, count, target, shift_dev, d_probs);
+  active_final_kernel<<<1, 1, 0, s>>>(ratio_out, count, target, shift_dev, loss);
   VITB_LAUNCH_CHECK("active_loss_kernel");
   return VITB_OK;
 }

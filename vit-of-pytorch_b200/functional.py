@@ -267,6 +267,16 @@ def _as2d(t, cols):
 # --------------------------------------------------------------------------------------------------
 # Linear (nn.Linear [N,K] and LinearGeneral [K,N]) with fused bias / GELU / residual epilogue
 # --------------------------------------------------------------------------------------------------
+def _dy_operand(dy2):
+    """bf16 GEMM operand pieces of an incoming fp32 gradient: the bf16 copy its producer left in the backward side
+    channel (a LayerNorm backward writes it in the same pass, see _side_put) when there is one, else a cast."""
+    if dy2.dtype == F32 and not _fp32_mode() and dy2.is_contiguous():
+        side = _side_take(dy2)
+        if side is not None:
+            return [side[0]]
+    return _operand(dy2)
+
+
 class _Linear(torch.autograd.Function):
     """y = act(x W^T + b + row_bias[row // group]) (+ residual).
 
@@ -351,7 +361,7 @@ class _Linear(torch.autograd.Function):
             dyp = dy2.new_zeros((dy2.shape[0], Np))
             dyp[:, :N] = dy2
             dy2 = dyp
-        dyo = _operand(dy2)
+        dyo = _dy_operand(dy2)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             A, B = _pairs(dyo, ctx.wo)
@@ -436,7 +446,7 @@ class _Mlp(torch.autograd.Function):
         if not dy2.is_contiguous():
             dy2 = dy2.contiguous()
         dres = dy.reshape(ctx.res[0]).to(ctx.res[1]) if (ctx.res is not None and ctx.needs_input_grad[5]) else None
-        dyo = _operand(dy2)
+        dyo = _dy_operand(dy2)
         # dz = (dy W2) * gelu'(z)
         A, B = _pairs(dyo, _weight_operand(w2, (Do, Mh)))
         dz = ops.gemm(A, B, b_mn=True, out_dtype=ctx.z.dtype,
@@ -570,6 +580,67 @@ def layer_norm(x, weight, bias, eps=1e-5, *, out_dtype=None):
     if out_dtype is None:
         out_dtype = _act_dtype()
     return _LayerNorm.apply(x, weight, bias, eps, out_dtype)
+
+
+class _LayerNormSkip(torch.autograd.Function):
+    """(LayerNorm(x), x) for a pre-LN residual connection, h = x + f(LN(x)): the second output is x itself, to be handed
+    to f's last GEMM as its residual.  Forward costs nothing extra; the point is the backward, where the gradient of the
+    branch (d LN) and the gradient of the skip arrive at ONE node: the LayerNorm-backward kernel adds the skip gradient in
+    its only pass (its `dres` input) and writes the bf16 copy of the sum for the GEMMs upstream — instead of autograd
+    adding two fp32 [T, D] tensors in a separate kernel and the upstream GEMM casting the result."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps, out_dtype):
+        L.require_cuda(x, weight, bias)
+        D = x.shape[-1]
+        x2 = x.reshape(-1, D)
+        yf, yh, _, mean, rstd = ops.layernorm_fwd(x2, weight.detach(), bias.detach(), eps,
+                                                  want_f32=out_dtype == F32, want_bf16=out_dtype == BF16)
+        ctx.save_for_backward(x2, mean, rstd)
+        ctx.weight, ctx.bias = weight, bias
+        ctx.x_shape = x.shape
+        y = yf if out_dtype == F32 else yh
+        return y.view(*x.shape[:-1], D), x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, dy, dskip):
+        x2, mean, rstd = ctx.saved_tensors
+        weight, bias = ctx.weight, ctx.bias
+        D = x2.shape[1]
+        need_wb = weight.requires_grad or bias.requires_grad
+        gt, bt = _grad_target(weight), _grad_target(bias)
+        dg = (gt if gt is not None else torch.zeros(D, dtype=F32, device=x2.device)) if need_wb else None
+        db = (bt if bt is not None else torch.zeros(D, dtype=F32, device=x2.device)) if need_wb else None
+        dres = None
+        if dskip is not None:
+            dres = dskip.reshape(-1, D)
+            if dres.dtype != F32 or not dres.is_contiguous():
+                dres = dres.float().contiguous()
+        if dy is None:       # only the skip was used
+            dx = dres.view(ctx.x_shape) if dres is not None else None
+        else:
+            dy2 = dy.reshape(-1, D)
+            if not dy2.is_contiguous():
+                dy2 = dy2.contiguous()
+            want_bf16 = not _fp32_mode()
+            dxf, dxh, _ = ops.layernorm_bwd(dy2, x2, mean, rstd, weight.detach(), dres=dres, want_f32=True,
+                                            want_bf16=want_bf16, dgamma=dg, dbeta=db)
+            if dxh is not None:
+                _side_put(dxf, dxh, None)     # whoever receives exactly this tensor finds its bf16 copy there
+            dx = dxf.view(ctx.x_shape)
+        return (dx if ctx.needs_input_grad[0] else None,
+                dg if (need_wb and gt is None and weight.requires_grad and dy is not None) else None,
+                db if (need_wb and bt is None and bias.requires_grad and dy is not None) else None, None, None)
+
+
+def layer_norm_skip(x, weight, bias, eps=1e-5, *, out_dtype=None):
+    """(LayerNorm(x), x): use the second value as the residual of the branch that consumes the first (see _LayerNormSkip).
+    Falls back to (layer_norm(x), x) when x is not a contiguous fp32 tensor."""
+    if out_dtype is None:
+        out_dtype = _act_dtype()
+    if x.dtype != F32 or not x.is_contiguous():
+        return _LayerNorm.apply(x, weight, bias, eps, out_dtype), x
+    return _LayerNormSkip.apply(x, weight, bias, eps, out_dtype)
 
 
 # --------------------------------------------------------------------------------------------------

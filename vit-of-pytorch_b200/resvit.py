@@ -348,6 +348,14 @@ class TransformerBlock(nn.Module):
     def _dense(self, x):
         """h = x + attn(LN(x)); out = h + ffn(LN(h)) — both adds in the producing GEMM's epilogue."""
         x = x if x.dtype == torch.float32 else x.float()
+        if torch.is_grad_enabled() and x.requires_grad:
+            # LayerNorm and the skip connection as one autograd node: its backward adds the two gradients in the LayerNorm
+            # kernel and leaves the bf16 copy for the GEMMs upstream (functional._LayerNormSkip)
+            an, fn = self.attention_norm.layer_norm, self.ffn_norm.layer_norm
+            xn, xr = F.layer_norm_skip(x, an.weight, an.bias, an.eps)
+            h = self.attention(xn, residual=xr)
+            hn, hr = F.layer_norm_skip(h, fn.weight, fn.bias, fn.eps)
+            return h, self.feed_forward(hn, residual=hr)
         h = self.attention(self.attention_norm(x), residual=x)
         return h, self.feed_forward(self.ffn_norm(h), residual=h)
 
