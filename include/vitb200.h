@@ -149,9 +149,12 @@ int vitb_layernorm_bwd_sparse_res(const void* dy, int dy_dtype, const float* x, 
  * src/model.py:90-97, Attention.forward res-vit/model.py:273-293 — and its backward.
  * Element (b, n, h, d) of a tensor lives at base + b*batch_stride + n*row_stride + h*head_dim + d
  * (strides in elements), so q/k/v can alias one packed [T, 3D] projection output.
- *   *_tc  : tcgen05/TMEM kernels, bf16, head_dim 64, Nq == Nk <= 256; gradients dq/dk/dv are bf16.
- *   *_simt: CUDA-core fp32 math, dtype f32 or bf16, any head_dim, Nk <= 320, Nq != Nk allowed;
- *           gradients dq/dk/dv are FP32 and dq must be zeroed by the caller (atomic accumulation).
+ *   *_tc  : tcgen05/TMEM kernels, bf16, Nq == Nk; gradients dq/dk/dv are bf16.  vitb_attn_fwd_tc takes head_dim
+ *           64..128 (multiples of 16) and any token count; vitb_attn_bwd_tc head_dim 64 and <= 256 tokens;
+ *           vitb_attn_bwd_tc_long (below) any token count and head_dim 64..128.
+ *   *_simt: CUDA-core fp32 math, dtype f32 or bf16, any head_dim, Nk <= 320, Nq != Nk allowed: the fp32 parity mode
+ *           and asymmetric query / key counts; gradients dq/dk/dv are FP32 and dq must be zeroed by the caller
+ *           (atomic accumulation).
  * lse is [B, H, Nq] fp32 (log-sum-exp of the scaled scores), written by fwd and read by bwd.
  */
 typedef struct vitb_attn_params {

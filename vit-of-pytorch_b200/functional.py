@@ -1033,10 +1033,12 @@ class _EncoderBlockFused(torch.autograd.Function):
     """y = h + MLP(LN2(h)),  h = x + Attn(LN1(x))   (src/model.py:117-130), weights in LinearGeneral
     ("kn") layout for attention and nn.Linear ("nk") layout for the MLP.
 
-    Forward: 2 LayerNorm kernels, 6 tcgen05 GEMMs (q, k, v into one packed buffer; out+residual; fc1+GELU;
-    fc2+residual), 1 tcgen05 attention.  Backward: 10 GEMMs (GELU' and bias-gradient column sums ride in
-    their epilogues), 1 attention backward, 2 LayerNorm backwards that add the residual-branch gradient,
-    emit the bf16 operand copy and the neighbouring bias gradients in the same pass."""
+    Forward: 2 LayerNorm kernels, 4 tcgen05 GEMMs (q | k | v as ONE grouped GEMM into a packed buffer; out+residual;
+    fc1+GELU+GELU'; fc2+residual), 1 tcgen05 attention.  Backward: 8 GEMMs (dgrad fc2 x gelu', dW fc2, dW fc1, dgrad
+    fc1, dW out, dgrad out, the three q | k | v weight gradients as ONE grouped GEMM, dgrad qkv as three K-segments;
+    bias-gradient column sums ride in their epilogues), 1 attention backward, 1 column sum (query bias), 2 LayerNorm
+    backwards that add the residual-branch gradient, emit the bf16 operand copy and the neighbouring bias gradients in
+    the same pass.  `up`: the fused node that produced x, if any (see _upstream_bias_target)."""
 
     @staticmethod
     def forward(ctx, x, H, eps1, eps2, n1w, n1b, wq, bq, wk, bk, wv, bv, wo, bo, n2w, n2b, w1, b1, w2, b2, up=None):

@@ -262,7 +262,9 @@ def attn_fwd(q, k, v, H, *, use_tc=None):
 
 
 def attn_bwd(dout, q, k, v, o, lse, H, *, use_tc=None, dq=None, dk=None, dv=None):
-    """Returns (dq, dk, dv).  tc: bf16 gradients; simt: fp32 gradients.  dq/dk/dv may be strided views."""
+    """Returns (dq, dk, dv).  use_tc (default: whenever a tcgen05 kernel takes the shape — bf16, Nq == Nk, head_dim 64..128):
+    bf16 gradients from the persistent kernel (<= 256 tokens, head_dim 64) or the key-block kernel (anything else);
+    otherwise the fp32 CUDA-core kernel with fp32 gradients.  dq/dk/dv may be strided views."""
     L.require_cuda(dout, q, k, v, o, lse)
     B, Nq, HD = q.shape
     Nk = k.shape[1]
