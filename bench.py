@@ -324,7 +324,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the config's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of one CUDA graph")
-    ap.add_argument("--ddp-mode", default="graph1", choices=["graph1", "graph2", "overlap"],
+    ap.add_argument("--ddp-mode", default="graph1", choices=["graph1", "nvlink", "graph2", "overlap"],
                     help="N > 1: graph1 = the whole step incl. one gradient all-reduce as ONE CUDA graph (default, same launch "
                          "mode as N = 1); graph2 = fwd+bwd graph, one eager all-reduce, optimizer graph "
                          "(train.GraphedDataParallelStep); overlap = eager launches, per-block all-reduces overlapped with "
@@ -366,6 +366,12 @@ def main():
     vitb200.set_precision("bf16")
     torch.manual_seed(0)                     # same constructor RNG sequence as the reference (tests/test_oracle.py)
     train = kind != "vit_infer"
+    # gradient exchange at N > 1: "graph1" = one NCCL all-reduce inside the step graph; "nvlink" = the same with
+    # vitb_p2p_allreduce (our kernel over NVLink peer memory / NVSwitch multicast) in its place
+    xchg = None
+    if world > 1 and train and args.ddp_mode == "nvlink" and not args.no_graph and not args.graph_ddp:
+        xchg = vitb200.p2p.NvlinkExchange()
+    gfac = xchg.allocate if xchg is not None else None
     if kind == "resvit_train":
         # res-vit/config.py presets + the fine-tune switches of BASELINE.json configs[4] (res-vit/ft_resvit.sh)
         from vitb200 import resvit
@@ -377,7 +383,7 @@ def main():
         model = model.to(dev).train()
         # res-vit/train.py:272-277,65: AdamW(1e-4, wd 0.05) over the trainable set + clip_grad_norm_(1.0)
         opt = vitb200.optim.FusedAdamW([q for q in model.parameters() if q.requires_grad], lr=1e-4, weight_decay=0.05,
-                                       max_grad_norm=1.0)
+                                       max_grad_norm=1.0, grad_buffer_factory=gfac)
         resvit.bind_optimizer(model, opt)   # approximators whose key does not occur in a batch are skipped, as torch's AdamW does
         sched = None
         gflop_ref = gflop_exec = resvit_train_gflop(classes=classes)
@@ -400,7 +406,7 @@ def main():
         gflop_ref, gflop_exec = (3 * fwd_ref, 3 * fwd_exec) if train else (fwd_ref, fwd_exec)
         opt = sched = None
         if train:
-            opt = vitb200.optim.FusedSGD(model.parameters(), lr=LR, momentum=0.9)
+            opt = vitb200.optim.FusedSGD(model.parameters(), lr=LR, momentum=0.9, grad_buffer_factory=gfac)
             # the reference's schedule (src/train.py:159-163, config defaults src/config.py:39-42): the step starts at
             # max_lr / 25; lr AND the cycled momentum reach the kernels through device scalars, so they also drive the graph
             sched = torch.optim.lr_scheduler.OneCycleLR(opt, max_lr=LR, pct_start=WARMUP_STEPS / TRAIN_STEPS, total_steps=TRAIN_STEPS)
@@ -414,7 +420,7 @@ def main():
     if not train:
         args.ddp_mode = "replicas"           # inference: independent replicas, no exchange
     graph_ddp = world > 1 and args.ddp_mode == "graph2"
-    graph_one = world > 1 and args.ddp_mode == "graph1"
+    graph_one = world > 1 and args.ddp_mode in ("graph1", "nvlink")
     net = vitb200.ddp.DataParallel(model, opt) if (world > 1 and args.ddp_mode == "overlap") else model
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     img_d = torch.randn(B, 3, image, image, generator=gen, device=dev)
@@ -440,7 +446,7 @@ def main():
         graphed = vitb200.train.GraphedDataParallelStep(net, opt, img_d, lab_d)
     elif train and not args.no_graph and (world == 1 or graph_one):
         try:   # the whole step (fwd + bwd + all-reduce + optimizer) as one replayable CUDA graph
-            graphed = vitb200.train.GraphedTrainStep(net, opt, img_d, lab_d, data_parallel=graph_one,
+            graphed = vitb200.train.GraphedTrainStep(net, opt, img_d, lab_d, data_parallel=graph_one, exchange=xchg,
                                                      forward_loss=forward_loss if kind == "resvit_train" else None)
         except Exception as exc:  # noqa: BLE001 - report and measure eagerly rather than die
             if world > 1:
@@ -534,6 +540,8 @@ def main():
                        if graphed is not None else "eager (Python launches)",
                        "grad_exchange": (None if (world == 1 or not train) else
                                          {"graph1": "one NCCL all-reduce (AVG) of the flat fp32 gradient buffer, a node of the step graph",
+                                          "nvlink": "vitb_p2p_allreduce (one kernel over NVLink peer memory, %s), a node of the step graph"
+                                                    % (xchg.mode if xchg is not None else "-"),
                                           "graph2": "one eager NCCL all-reduce between two graphs",
                                           "overlap": "per-block NCCL all-reduces on a side stream, overlapped with backward"}[args.ddp_mode]),
                        "l2": "per-step working set (GBs of activations) exceeds the 126 MB L2; no flush needed",

@@ -241,6 +241,18 @@ int vitb_colsum(const void* x, int x_dtype, int rows, int cols, int64_t ld, floa
 int vitb_colsum3(const void* x, int x_dtype, int rows, int seg_cols, int64_t ld, float* out0, float* out1,
                  float* out2, void* stream);
 
+/* ---- gradient exchange over NVLink peer memory ---------------------------------------------------
+ * all-reduce (sum x scale: scale = 1 / world gives the average) of the flat fp32 gradient buffer of a data-parallel step —
+ * nn.DataParallel's gradient reduction, src/train.py:128-129 — as ONE kernel per rank.  bufs[world]: every rank's mapping
+ * of every rank's buffer (symmetric memory; this rank's own buffer is bufs[rank]); pads[world]: the same for a signal pad of
+ * vitb_p2p_pad_words() uint32 words per rank, ZEROED ONCE by the caller before the first call; multicast: the NVSwitch
+ * multicast address of the buffer (the switch then does the sum: NVLS) or null (peer loads / stores).  n fp32 elements, a
+ * multiple of 4.  Every rank must call it, with the same n, once per step, on a stream with nothing else in flight (the
+ * blocks of all ranks meet at two in-kernel barriers).  Replayable from a CUDA graph. */
+int vitb_p2p_pad_words(void);
+int vitb_p2p_allreduce(float* const* bufs, uint32_t* const* pads, float* multicast, int rank, int world, int64_t n,
+                       float scale, void* stream);
+
 /* ---- Res-ViT routing ---------------------------------------------------------------------------
  * Decision tail of RouterModule.forward (res-vit/model.py:189-211) + _router2indices (:169-173).
  * logits [T, bs, 2] fp32 (T = B*N tokens, token n = t %% N is "reserved" when n < reserve_initials):

@@ -42,6 +42,56 @@ for name, n in (("ViT-B/16", 85_875_556), ("ViT-L/16", 303_400_000), ("Res-ViT t
         else:
             print("    NVLink counters: not available through NVML on this box", flush=True)
     del buf
+# the same exchange with vitb_p2p_allreduce: one kernel of ours over NVLink peer memory (NVSwitch multicast when offered)
+import vitb200  # noqa: E402
+for use_mc in (True, False):
+    try:
+        n = 85_875_556
+        x = vitb200.p2p.NvlinkExchange(use_multicast=use_mc)
+        g = x.allocate(n, dev)
+        ref = torch.empty_like(g)
+        gen = torch.Generator(device=dev).manual_seed(100 + rank)
+        src = torch.randn(n, device=dev, generator=gen)
+        g.copy_(src)
+        ref.copy_(src)
+        dist.all_reduce(ref, op=dist.ReduceOp.AVG)
+        x.all_reduce_avg()
+        torch.cuda.synchronize()
+        err = float((g - ref).abs().max() / ref.abs().max())
+        for _ in range(3):
+            x.all_reduce_avg()
+        torch.cuda.synchronize()
+        dist.barrier()
+        nv0 = nvlink_bytes(local) if rank == 0 else None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            x.all_reduce_avg()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1) / 20], device=dev, dtype=torch.float64)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        # and replayed from a CUDA graph, as the training step does
+        gr = torch.cuda.CUDAGraph()
+        s2 = torch.cuda.Stream()
+        with torch.cuda.stream(s2):
+            with torch.cuda.graph(gr, stream=s2):
+                x.all_reduce_avg()
+            g.copy_(src)
+            gr.replay()
+            torch.cuda.synchronize()
+            err_g = float((g - ref).abs().max() / ref.abs().max())
+        if rank == 0:
+            t = float(ms) / 1e3
+            gb = n * 4 / 1e9
+            print("vitb_p2p_allreduce ViT-B/16 (%s, requested multicast=%s): %.1f MB fp32 on %d GPUs: %.3f ms, algbw %.0f GB/s; "
+                  "max |diff| vs NCCL %.2e (eager) %.2e (graph replay)" % (x.mode, use_mc, gb * 1e3, world, t * 1e3, gb / t, err, err_g),
+                  flush=True)
+        del x, g, ref, src
+    except Exception as exc:  # noqa: BLE001
+        if rank == 0:
+            print("vitb_p2p_allreduce (multicast=%s) failed: %r" % (use_mc, exc), flush=True)
+    dist.barrier()
 dist.barrier()
 torch.cuda.synchronize()
 os._exit(0)

@@ -5,7 +5,7 @@ The directory name carries a hyphen (it mirrors the reference repo's name), so i
 the `vitb200` shim at the repo root:  `import vitb200`.
 Importing loads libvitb200.so and fails loudly when it is missing — there is no fallback path.
 """
-from . import _lib, ops, functional, config, model, optim, ddp, resvit, lra_tables, train, checkpoint, input_pipeline  # noqa: F401
+from . import _lib, ops, functional, config, model, optim, ddp, p2p, resvit, lra_tables, train, checkpoint, input_pipeline  # noqa: F401
 from .functional import set_precision, get_precision, precision, SHADOW  # noqa: F401
 from .model import (VisionTransformer, Encoder, EncoderBlock, SelfAttention, MlpBlock, MLPBlock,  # noqa: F401
                     LinearGeneral, PositionEmbs, PositionEmbedding)

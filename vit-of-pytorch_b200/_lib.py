@@ -194,6 +194,8 @@ _vitb_cross_entropy = _sig("vitb_cross_entropy", [_vp, _vp, _i, _i, _vp, _vp, _v
 _vitb_sgd_momentum = _sig("vitb_sgd_momentum", [_vp, _vp, _vp, _i64, _f, _vp, _f, _f, _f, _i, _i, _vp, _vp, _vp])
 _vitb_adamw = _sig("vitb_adamw", [_vp, _vp, _vp, _vp, _i64, _f, _vp, _f, _f, _f, _f, _i, _vp, _vp, _vp, _vp, _vp])
 _vitb_adamw_segments = _sig("vitb_adamw_segments", [_vp, _vp, _vp, _vp, _i64, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp])
+vitb_p2p_pad_words = _sig("vitb_p2p_pad_words", [])
+_vitb_p2p_allreduce = _sig("vitb_p2p_allreduce", [_vp, _vp, _vp, _i, _i, _i64, _f, _vp])
 _vitb_sumsq = _sig("vitb_sumsq", [_vp, _i64, _vp, _vp])
 _vitb_router_decide_fwd = _sig("vitb_router_decide_fwd", [_vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp])
 _vitb_router_decide_bwd = _sig("vitb_router_decide_bwd", [_vp, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _i, _i, _f, _vp, _vp])
@@ -222,4 +224,5 @@ EXPORTED_SYMBOLS = [
     "vitb_distill_loss", "vitb_active_loss", "vitb_compact_rows", "vitb_gather_rows", "vitb_scatter_rows", "vitb_attn_ws_supported", "vitb_attn_fwd_ws", "vitb_attn_bwd_ws",
     "vitb_layernorm_bwd_sparse_res", "vitb_attn_q1_supported", "vitb_attn_q1_bwd", "vitb_dropout_fwd", "vitb_dropout_bwd",
     "vitb_adamw_segments", "vitb_select_rows_flag", "vitb_attn_bwd_long_supported", "vitb_attn_bwd_tc_long",
+    "vitb_p2p_pad_words", "vitb_p2p_allreduce",
 ]

@@ -19,7 +19,7 @@ _ALIGN = 64  # elements: 256-byte aligned fp32 slices, 128-byte aligned bf16 sli
 
 
 class _FlatGroup:
-    def __init__(self, params):
+    def __init__(self, params, grad_buffer_factory=None):
         params = F.packed_order([p for p in params if p.requires_grad])
         if not params:
             raise ValueError("no trainable parameters")
@@ -34,7 +34,11 @@ class _FlatGroup:
             total += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
         self.params, self.offsets, self.total = params, offs, total
         self.flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
+        # the gradient buffer may come from outside: p2p.NvlinkExchange.allocate puts it into symmetric memory
+        self.flat_g = (grad_buffer_factory(total, dev) if grad_buffer_factory is not None
+                       else torch.zeros(total, dtype=torch.float32, device=dev))
+        if self.flat_g.numel() != total or self.flat_g.dtype != torch.float32 or not self.flat_g.is_contiguous():
+            raise ValueError("grad_buffer_factory must return a contiguous fp32 tensor of the requested size")
         self.flat_hi = torch.zeros(total, dtype=torch.bfloat16, device=dev)
         self.flat_lo = None
         for p, off in zip(params, offs):
@@ -66,8 +70,10 @@ class _FlatGroup:
 
 
 class _FusedBase(torch.optim.Optimizer):
-    def _init_flat(self):
-        self._flat = [_FlatGroup(g["params"]) for g in self.param_groups]
+    def _init_flat(self, grad_buffer_factory=None):
+        if grad_buffer_factory is not None and len(self.param_groups) != 1:
+            raise NotImplementedError("grad_buffer_factory expects one parameter group")
+        self._flat = [_FlatGroup(g["params"], grad_buffer_factory) for g in self.param_groups]
         # device-resident hyper-parameters (4 floats per group, see _hyper): a captured CUDA graph of step() keeps
         # following whatever an LR scheduler writes into param_groups (OneCycleLR cycles lr AND momentum / beta1)
         self._hyper_host = [self._hyper(g) for g in self.param_groups]
@@ -174,10 +180,11 @@ class _FusedBase(torch.optim.Optimizer):
 
 
 class FusedSGD(_FusedBase):
-    def __init__(self, params, lr=1e-3, momentum=0.0, dampening=0.0, weight_decay=0.0, nesterov=False):
+    def __init__(self, params, lr=1e-3, momentum=0.0, dampening=0.0, weight_decay=0.0, nesterov=False,
+                 grad_buffer_factory=None):
         defaults = dict(lr=lr, momentum=momentum, dampening=dampening, weight_decay=weight_decay, nesterov=nesterov)
         super().__init__(params, defaults)
-        self._init_flat()
+        self._init_flat(grad_buffer_factory)
         self._bufs = [torch.zeros_like(fg.flat_p) if g["momentum"] != 0 else None
                       for fg, g in zip(self._flat, self.param_groups)]
         self._steps = 0
@@ -213,10 +220,11 @@ class FusedSGD(_FusedBase):
 
 
 class FusedAdamW(_FusedBase):
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, max_grad_norm=None):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, max_grad_norm=None,
+                 grad_buffer_factory=None):
         defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
         super().__init__(params, defaults)
-        self._init_flat()
+        self._init_flat(grad_buffer_factory)
         self._m = [torch.zeros_like(fg.flat_p) for fg in self._flat]
         self._v = [torch.zeros_like(fg.flat_p) for fg in self._flat]
         self.max_grad_norm = max_grad_norm

@@ -105,7 +105,7 @@ class DeviceMetrics:
 
 class GraphedTrainStep:
     def __init__(self, net, optimizer, example_images, example_labels, loss_fn=None, warmup=3, forward_loss=None,
-                 data_parallel=False, process_group=None, broadcast=True):
+                 data_parallel=False, process_group=None, broadcast=True, exchange=None):
         """forward_loss(net, images, labels) -> scalar loss overrides the default loss_fn(net(images), labels)
         (Res-ViT: `lambda net, x, y: sum_of(net(x, y)[:3])`, res-vit/train.py:30,51-52).
 
@@ -114,12 +114,16 @@ class GraphedTrainStep:
         CAPTURE STREAM, so the collective is a node of the same graph — the launch mode is the same at N = 1 and N > 1.
         The exchange is not overlapped with the backward pass on purpose: overlapped NCCL kernels take SMs from the
         persistent one-CTA-per-SM GEMM / attention kernels, whose statically scheduled tiles then wait for them (round 1:
-        0.90 efficiency at 8 GPUs with per-block overlapped buckets); one 344 MB all-reduce over NVSwitch costs ~0.5 ms."""
+        0.90 efficiency at 8 GPUs with per-block overlapped buckets); one 344 MB all-reduce over NVSwitch costs 1 - 1.5 ms.
+
+        exchange=p2p.NvlinkExchange (whose allocate() the optimizer was given as grad_buffer_factory): the exchange is
+        vitb_p2p_allreduce — one kernel of ours over NVLink peer memory / NVSwitch multicast — instead of NCCL's all-reduce."""
         self.forward_loss = forward_loss
         if not example_images.is_cuda:
             raise RuntimeError("GraphedTrainStep needs CUDA (B200) tensors")
         self.net, self.opt = net, optimizer
         self.dist, self.group, self.flat_g = None, process_group, None
+        self.exchange = exchange if data_parallel else None
         if data_parallel:
             import torch.distributed as dist
             if not dist.is_initialized():
@@ -128,6 +132,9 @@ class GraphedTrainStep:
                 raise NotImplementedError("data_parallel expects a fused optimizer with one parameter group")
             fg = optimizer._flat[0]
             self.dist, self.flat_g = dist, fg.flat_g
+            if exchange is not None and (exchange.buf is None or exchange.buf.data_ptr() != fg.flat_g.data_ptr()):
+                raise ValueError("exchange: the optimizer's gradient buffer is not the exchange's symmetric buffer "
+                                 "(construct the optimizer with grad_buffer_factory=exchange.allocate)")
             if broadcast:
                 dist.broadcast(fg.flat_p, src=0, group=process_group)
                 for p in fg.params:
@@ -158,7 +165,9 @@ class GraphedTrainStep:
             self.logits = self.net(self.images)      # static output of the captured step (for DeviceMetrics)
             loss = self.loss_fn(self.logits, self.labels)
         loss.backward()
-        if self.dist is not None:
+        if self.exchange is not None:
+            self.exchange.all_reduce_avg()
+        elif self.dist is not None:
             self.dist.all_reduce(self.flat_g, op=self.dist.ReduceOp.AVG, group=self.group)
         self.opt.step()
         return loss
