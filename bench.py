@@ -324,7 +324,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the config's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of one CUDA graph")
-    ap.add_argument("--ddp-mode", default="graph1", choices=["graph1", "nvlink", "graph2", "overlap"],
+    ap.add_argument("--ddp-mode", default="auto", choices=["auto", "graph1", "nvlink", "graph2", "overlap"],
                     help="N > 1: graph1 = the whole step incl. one gradient all-reduce as ONE CUDA graph (default, same launch "
                          "mode as N = 1); graph2 = fwd+bwd graph, one eager all-reduce, optimizer graph "
                          "(train.GraphedDataParallelStep); overlap = eager launches, per-block all-reduces overlapped with "
@@ -368,10 +368,36 @@ def main():
     train = kind != "vit_infer"
     # gradient exchange at N > 1: "graph1" = one NCCL all-reduce inside the step graph; "nvlink" = the same with
     # vitb_p2p_allreduce (our kernel over NVLink peer memory / NVSwitch multicast) in its place
+    # "auto" (default) = "nvlink" when the symmetric gradient buffer can be set up on every rank, else "graph1"
     xchg = None
-    if world > 1 and train and args.ddp_mode == "nvlink" and not args.no_graph and not args.graph_ddp:
+    if world > 1 and train and args.ddp_mode in ("auto", "nvlink") and not args.no_graph and not args.graph_ddp:
         xchg = vitb200.p2p.NvlinkExchange()
-    gfac = xchg.allocate if xchg is not None else None
+    elif args.ddp_mode == "auto":
+        args.ddp_mode = "graph1"
+
+    def make_optimizer(build):
+        """build(grad_buffer_factory) -> optimizer.  With an NVLink exchange the gradient buffer goes into symmetric
+        memory; if that fails on ANY rank, every rank falls back to an ordinary buffer and the NCCL all-reduce."""
+        nonlocal xchg
+        if xchg is None:
+            return build(None)
+        opt_, ok = None, 1
+        try:
+            opt_ = build(xchg.allocate)
+        except Exception as exc:  # noqa: BLE001
+            ok = 0
+            print("bench: symmetric gradient buffer unavailable on rank %d (%r)" % (rank, exc), file=sys.stderr)
+        flag = torch.tensor([ok], device=dev, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag) == 1:
+            args.ddp_mode = "nvlink"
+            return opt_
+        if args.ddp_mode == "nvlink":
+            raise RuntimeError("--ddp-mode nvlink: the symmetric gradient buffer could not be set up on every rank")
+        xchg, args.ddp_mode = None, "graph1"
+        if rank == 0:
+            print("bench: falling back to the NCCL all-reduce (--ddp-mode graph1)", file=sys.stderr)
+        return build(None)
     if kind == "resvit_train":
         # res-vit/config.py presets + the fine-tune switches of BASELINE.json configs[4] (res-vit/ft_resvit.sh)
         from vitb200 import resvit
@@ -382,8 +408,8 @@ def main():
             model.pos_embedding.pos_embedding.mul_(0.02)
         model = model.to(dev).train()
         # res-vit/train.py:272-277,65: AdamW(1e-4, wd 0.05) over the trainable set + clip_grad_norm_(1.0)
-        opt = vitb200.optim.FusedAdamW([q for q in model.parameters() if q.requires_grad], lr=1e-4, weight_decay=0.05,
-                                       max_grad_norm=1.0, grad_buffer_factory=gfac)
+        opt = make_optimizer(lambda fac: vitb200.optim.FusedAdamW([q for q in model.parameters() if q.requires_grad], lr=1e-4,
+                                                                  weight_decay=0.05, max_grad_norm=1.0, grad_buffer_factory=fac))
         resvit.bind_optimizer(model, opt)   # approximators whose key does not occur in a batch are skipped, as torch's AdamW does
         sched = None
         gflop_ref = gflop_exec = resvit_train_gflop(classes=classes)
@@ -406,7 +432,7 @@ def main():
         gflop_ref, gflop_exec = (3 * fwd_ref, 3 * fwd_exec) if train else (fwd_ref, fwd_exec)
         opt = sched = None
         if train:
-            opt = vitb200.optim.FusedSGD(model.parameters(), lr=LR, momentum=0.9, grad_buffer_factory=gfac)
+            opt = make_optimizer(lambda fac: vitb200.optim.FusedSGD(model.parameters(), lr=LR, momentum=0.9, grad_buffer_factory=fac))
             # the reference's schedule (src/train.py:159-163, config defaults src/config.py:39-42): the step starts at
             # max_lr / 25; lr AND the cycled momentum reach the kernels through device scalars, so they also drive the graph
             sched = torch.optim.lr_scheduler.OneCycleLR(opt, max_lr=LR, pct_start=WARMUP_STEPS / TRAIN_STEPS, total_steps=TRAIN_STEPS)
