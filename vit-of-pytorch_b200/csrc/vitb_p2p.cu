@@ -59,7 +59,7 @@ __device__ __forceinline__ void cross_gpu_barrier(const P2pArgs& a, unsigned rou
     const unsigned* mine = a.pad[a.rank] + blockIdx.x * kMaxWorld + threadIdx.x;
     long long spins = 0;
     while (ld_acquire_sys(mine) < round) {
-      if (++spins > (1ll << 26)) __trap();           // a lost peer must trap (after some seconds), never hang the box
+      if (++spins > (1ll << 30)) __trap();           // a lost peer must trap (after ~10 minutes: ranks may be skewed by seconds), never hang the box
       __nanosleep(40);
     }
   }
